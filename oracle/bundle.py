@@ -1,0 +1,150 @@
+"""bundle() driver and bundle_cov() — oracle restatement (test infrastructure).
+
+Follows `code/bundle/bundle.m:78-192,267-358,449-491` and
+`code/bundle/bundle_cov.m:63-117,135-214,221-478`, `private/invblock.m:29-41,86-90`,
+`misc/mkblkdiag.m:49-60`.
+"""
+import time
+from types import SimpleNamespace as NS
+
+import numpy as np
+import scipy.linalg as sla
+import scipy.sparse as sp
+
+from . import lsa
+from .cameramodel import brown_euler_cam4
+from .dbatstruct import buildserialindices, buildweightmatrix, deserialize, serialize
+
+
+def bundle(s, damping='gna', maxIter=20, convTol=1e-6, absTerm=False, doTrace=False,
+           singularTest=True, pmDof=False):
+    """bundle.m:1-491 → (s, ok, iters, s0, E)."""
+    for pri, est in ((s.prior.IO, s.bundle.est.IO), (s.prior.EO, s.bundle.est.EO),
+                     (s.prior.OP, s.bundle.est.OP)):                 # :137-154
+        pri.use[~est] = False
+    if s.bundle.serial is None or s.bundle.deserial is None:         # :156-159
+        buildserialindices(s)
+    x0 = serialize(s)                                                # :162
+    resFun = lambda x, want_jac=True: brown_euler_cam4(x, s, want_jac)   # :165
+    vetoFun = None
+    W = buildweightmatrix(s)                                         # :175
+    if absTerm:                                                      # :186-192
+        termFun = lambda Jp, r: np.linalg.norm(r) <= convTol
+    else:
+        termFun = lambda Jp, r: np.linalg.norm(Jp) <= convTol * np.linalg.norm(r)
+    E = NS(maxIter=maxIter, convTol=convTol, absTerm=absTerm, singularTest=singularTest)
+    t0 = time.process_time()
+    damping = damping.lower()
+    if damping == 'gna':                                             # :275-295
+        mu, alphaMin = 0.1, 1e-9
+        x, code, iters, final, X, res, alpha = lsa.gauss_newton_armijo(
+            resFun, vetoFun, x0, W, maxIter, termFun, doTrace, singularTest, mu, alphaMin)
+        E.damping = NS(name='gna', alpha=alpha, mu=mu, alphaMin=alphaMin)
+    elif damping == 'lm':                                            # :296-315
+        lambda0 = -1e-10
+        lambdaMin = lambda0
+        x, code, iters, final, X, res, lam = lsa.levenberg_marquardt(
+            resFun, vetoFun, x0, W, maxIter, termFun, doTrace, lambda0, lambdaMin)
+        E.damping = NS(name='lm', **{'lambda': lam}, lambda0=lam[0], lambdaMin=lam[0])
+    elif damping == 'lmp':                                           # :316-335
+        rhoBad, rhoGood = 0.25, 0.75
+        delta0 = np.linalg.norm(x0)
+        x, code, iters, final, X, res, delta, rho, step = lsa.levenberg_marquardt_powell(
+            resFun, vetoFun, x0, W, maxIter, termFun, doTrace, delta0, rhoBad, rhoGood)
+        E.damping = NS(name='lmp', delta=delta, rho=rho, delta0=delta0, rhoBad=rhoBad,
+                       rhoGood=rhoGood, step=step)
+    else:
+        raise ValueError('Unknown damping')
+    E.time = time.process_time() - t0
+    E.res, E.trace, E.code, E.usedIters, E.final = res, X, code, iters, final   # :341-348
+    E.final.factorized = None
+    E.x = x
+    ok = code == 0
+    if ok:                                                           # :356-358
+        IO, EO, OP = deserialize(s, x)
+        s.IO.val, s.EO.val, s.OP.val = IO, EO, OP
+    # residuals (:449-462): IP residuals mm -> px
+    resIP = final.unweighted.r[s.post.res.ix.IP].reshape(2, -1, order='F')
+    s.post.res.IP = resIP / s.IO.sensor.pxSize[:, s.IP.cam]
+    p = 0
+    if pmDof:                                                        # :470-472
+        seen_op = np.zeros(s.OP.val.shape[1], bool); seen_op[s.IP.op] = True
+        seen_im = np.zeros(s.EO.val.shape[1], bool); seen_im[s.IP.img] = True
+        p = np.count_nonzero(~s.bundle.est.OP[:, seen_op]) + \
+            np.count_nonzero(~s.bundle.est.EO[0:6, seen_im])
+    r = E.final.weighted.r                                           # :476-491
+    dof = len(r) + p - len(x)
+    s0 = np.sqrt((r @ r) / dof)
+    s.post.sigmas = s0 * s.IP.sigmas
+    E.numObs, E.numParams, E.redundancy, E.s0 = len(r), len(x), dof, s0
+    return s, ok, iters, s0, E
+
+
+# --------------------------------------------------------------------------- bundle_cov
+def _prepare(s, e):
+    """bundle_cov.m:63-117: permute N to [OP;EO;IO], Cholesky, split L=[LA 0;LB LC]."""
+    J = e.final.weighted.J
+    JTJ = (J.T @ J).toarray()
+    def bix(ser, shape):
+        b = np.full(shape[0] * shape[1], -1, dtype=np.int64)
+        b[ser.src] = ser.dest
+        return b
+    bOP = bix(s.bundle.serial.OP, s.bundle.est.OP.shape)
+    bEO = bix(s.bundle.serial.EO, s.bundle.est.EO.shape)
+    bIO = bix(s.bundle.serial.IO, s.bundle.est.IO.shape)
+    p = np.concatenate([bOP, bEO, bIO])
+    p = p[p >= 0]                                                    # :83-84
+    nOP = np.count_nonzero(bOP >= 0)
+    try:
+        L = np.linalg.cholesky(JTJ[np.ix_(p, p)])                    # :87
+        fail = False
+    except np.linalg.LinAlgError:
+        L = np.full(JTJ.shape, np.nan)
+        fail = True
+    e.final.factorized = NS(p=p, L=L, nOP=nOP, fail=fail)
+    return e
+
+
+def _invblock_sqrt(L, p, ix):
+    """invblock.m:29-41 ('sqrt'): v2 = L\\Ip(:,ix); x = v2'*v2."""
+    invP = np.empty(len(p), dtype=np.int64)
+    invP[p] = np.arange(len(p))
+    n = L.shape[0]
+    rhs = np.zeros((n, len(ix)))
+    rhs[invP[ix], np.arange(len(ix))] = 1.0
+    v2 = sla.solve_triangular(L, rhs, lower=True)
+    return v2.T @ v2
+
+
+def bundle_cov(s, e, *which):
+    """bundle_cov.m:1-214.  which ∈ {'CXX','CIO','CEO','COP','CIOF','CEOF','COPF'}.
+
+    Returns dense arrays (the reference returns sparse matrices of the same shape):
+    CIOF (NC*nImg)^2, CEOF (6*nImg)^2, COPF (3*nOP)^2, CIO/CEO/COP block-diagonal of
+    those, CXX n x n — each scaled by s0^2 (:213).
+    """
+    if e.final.factorized is None:
+        _prepare(s, e)
+    F = e.final.factorized
+    out = []
+    for w in which:
+        w = w.lower()
+        if w == 'cxx':                                               # :138-145, invblock 'direct'
+            C = _invblock_sqrt(F.L, F.p, np.arange(len(F.p)))
+        elif w in ('ciof', 'ceof', 'copf', 'cio', 'ceo', 'cop'):
+            key = w[1:3].upper()
+            des = getattr(s.bundle.deserial, key)
+            shape = getattr(s.bundle.est, key).shape
+            N = shape[0] * shape[1]
+            C = np.zeros((N, N))
+            if F.fail:
+                C[np.ix_(des.dest, des.dest)] = np.nan
+            else:
+                C[np.ix_(des.dest, des.dest)] = _invblock_sqrt(F.L, F.p, des.src)   # :148-196
+            if len(w) == 3:                                          # block-diagonal (:198-211)
+                mask = np.kron(np.eye(shape[1]), np.ones((shape[0], shape[0])))     # mkblkdiag.m
+                C = C * mask
+        else:
+            raise ValueError(w)
+        out.append(e.s0 ** 2 * C)
+    return out[0] if len(out) == 1 else out

@@ -1,0 +1,51 @@
+#!/usr/bin/env python
+"""Regenerate tests/golden/ from the read-only reference checkout (/root/reference).
+
+Run in the build container only (the GPU box has no /root/reference; tests read the
+committed copies).  Copies DATA fixtures (inputs + the reference's golden result
+files) — never reference source code.
+"""
+import os
+import shutil
+import sys
+
+REF = os.environ.get('DBAT_REFERENCE', '/root/reference')
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+FILES = {
+    'camcaldemo': [
+        'data/script/camcaldemo/camcaldemo.xml',
+        'data/script/camcaldemo/images/images.txt',
+        'data/script/camcaldemo/measurements/markpts.txt',
+        'data/script/camcaldemo/reference/camcal-fixed.txt',
+        'data/script/camcaldemo/result/c4040z.xml',
+        'data/script/camcaldemo/result/camera_stations.txt',
+        'data/script/camcaldemo/result/report.txt',
+        'data/script/camcaldemo/result/top_residuals.txt',
+    ],
+    'dbatexports': [
+        'data/dbat/dbatexports/camcal-dbatreport.txt',
+        'data/dbat/dbatexports/camcal-dbatreport-model2.txt',
+        'data/dbat/dbatexports/camcal-dbatreport-model3.txt',
+        'data/dbat/dbatexports/camcal-dbatreport-model4.txt',
+        'data/dbat/dbatexports/camcal-dbatreport-model5.txt',
+        'data/dbat/dbatexports/camcal-dbatreport-model1.txt',
+        'data/dbat/dbatexports/camcal-dbatreport-model-1.txt',
+    ],
+}
+
+
+def main():
+    if not os.path.isdir(REF):
+        sys.exit('reference checkout not found at %s' % REF)
+    for sub, files in FILES.items():
+        for f in files:
+            rel = f.split(sub + '/', 1)[1] if sub + '/' in f else os.path.basename(f)
+            dst = os.path.join(HERE, sub, rel)
+            os.makedirs(os.path.dirname(dst), exist_ok=True)
+            shutil.copyfile(os.path.join(REF, f), dst)
+            print('copied', f, '->', os.path.relpath(dst, HERE))
+
+
+if __name__ == '__main__':
+    main()
