@@ -1,0 +1,126 @@
+"""ctypes binding of libdbatgpu.so (include/dbat_gpu.h).
+
+This is the same C ABI a MATLAB MEX gateway binds (mex/dbat_mex.c).  There is no CPU
+fallback: if the library is missing or no CUDA device is present, calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libdbatgpu.so')
+
+METHOD = {'gm': 0, 'gna': 1, 'lm': 2, 'lmp': 3}
+COV = {'cio': 1, 'ceo': 2, 'cop': 3, 'cxx_cam': 4}
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int64)
+
+
+class ProblemDesc(C.Structure):
+    _fields_ = [
+        ('nImg', C.c_int64), ('nOP', C.c_int64), ('nIP', C.c_int64),
+        ('distModel', C.c_int32), ('nK', C.c_int32), ('nP', C.c_int32),
+        ('IOval', c_dp), ('EOval', c_dp), ('OPval', c_dp), ('IPval', c_dp), ('IPstd', c_dp),
+        ('IPimg', c_ip), ('IPop', c_ip), ('pxSize', c_dp),
+        ('n', C.c_int64),
+        ('IOdes_src', c_ip), ('IOdes_dest', c_ip), ('nIOdes', C.c_int64),
+        ('EOdes_src', c_ip), ('EOdes_dest', c_ip), ('nEOdes', C.c_int64),
+        ('OPdes_src', c_ip), ('OPdes_dest', c_ip), ('nOPdes', C.c_int64),
+        ('nPriorIO', C.c_int64), ('nPriorEO', C.c_int64), ('nPriorOP', C.c_int64),
+        ('prior_x', c_ip), ('prior_val', c_dp), ('prior_std', c_dp),
+    ]
+
+
+class Opts(C.Structure):
+    _fields_ = [
+        ('maxIter', C.c_int32), ('convTol', C.c_double), ('absTerm', C.c_int32),
+        ('singularTest', C.c_int32), ('doTrace', C.c_int32),
+        ('lambda0', C.c_double), ('lambdaMin', C.c_double), ('delta0', C.c_double),
+        ('mu', C.c_double), ('eta', C.c_double), ('alphaMin', C.c_double),
+    ]
+
+
+class Result(C.Structure):
+    _fields_ = [
+        ('x', c_dp), ('p', c_dp), ('r_w', c_dp), ('r_u', c_dp), ('trace', c_dp),
+        ('rr', c_dp), ('damping', c_dp), ('rhos', c_dp), ('steps', C.POINTER(C.c_int32)),
+        ('code', C.c_int32), ('iters', C.c_int32),
+        ('nTrace', C.c_int32), ('nRr', C.c_int32), ('nDamping', C.c_int32), ('nRhos', C.c_int32),
+        ('seconds', C.c_double), ('launches', C.c_int64),
+    ]
+
+
+EXPORTS = ['dbat_create', 'dbat_destroy', 'dbat_last_error', 'dbat_num_unknowns',
+           'dbat_num_residuals', 'dbat_eval', 'dbat_jacobian_nnz', 'dbat_jacobian_csc',
+           'dbat_default_opts', 'dbat_solve', 'dbat_normal_step', 'dbat_cov',
+           'dbat_comm_unique_id', 'dbat_comm_init', 'dbat_phase_times']
+
+_lib = None
+
+
+def lib():
+    """Load libdbatgpu.so (raises if it has not been built: no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError('libdbatgpu.so not built: run `python -m dbat_b200.build` '
+                           '(or __graft_entry__.build()); there is no CPU fallback')
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.dbat_create.argtypes = [C.POINTER(ProblemDesc), C.POINTER(vp)]
+    L.dbat_create.restype = C.c_int
+    L.dbat_destroy.argtypes = [vp]
+    L.dbat_destroy.restype = None
+    L.dbat_last_error.argtypes = [vp]
+    L.dbat_last_error.restype = C.c_char_p
+    L.dbat_num_unknowns.argtypes = [vp]
+    L.dbat_num_unknowns.restype = C.c_int64
+    L.dbat_num_residuals.argtypes = [vp]
+    L.dbat_num_residuals.restype = C.c_int64
+    L.dbat_eval.argtypes = [vp, c_dp, c_dp, C.c_int]
+    L.dbat_eval.restype = C.c_int
+    L.dbat_jacobian_nnz.argtypes = [vp, C.c_int, C.POINTER(C.c_int64)]
+    L.dbat_jacobian_nnz.restype = C.c_int
+    L.dbat_jacobian_csc.argtypes = [vp, C.c_int, c_ip, c_ip, c_dp]
+    L.dbat_jacobian_csc.restype = C.c_int
+    L.dbat_default_opts.argtypes = [C.c_int, C.POINTER(Opts)]
+    L.dbat_default_opts.restype = None
+    L.dbat_solve.argtypes = [vp, C.c_int, C.POINTER(Opts), c_dp, C.POINTER(Result)]
+    L.dbat_solve.restype = C.c_int
+    L.dbat_normal_step.argtypes = [vp, c_dp, C.c_double, C.c_int, c_dp, c_dp]
+    L.dbat_normal_step.restype = C.c_int
+    L.dbat_cov.argtypes = [vp, C.c_int, C.c_double, c_dp]
+    L.dbat_cov.restype = C.c_int
+    L.dbat_comm_unique_id.argtypes = [C.c_void_p]
+    L.dbat_comm_unique_id.restype = C.c_int
+    L.dbat_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_void_p]
+    L.dbat_comm_init.restype = C.c_int
+    L.dbat_phase_times.argtypes = [vp, C.POINTER(C.c_char_p), c_dp, c_ip, C.c_int]
+    L.dbat_phase_times.restype = C.c_int
+    _lib = L
+    return L
+
+
+def dptr(a):
+    return a.ctypes.data_as(c_dp) if a is not None else None
+
+
+def iptr(a):
+    return a.ctypes.data_as(c_ip) if a is not None else None
+
+
+def f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def i64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int64))
+
+
+class DbatError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__('libdbatgpu error %d: %s' % (code, msg))
+        self.code = code

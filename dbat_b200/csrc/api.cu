@@ -1,0 +1,1084 @@
+// api.cu — C ABI (include/dbat_gpu.h), problem flattening, and the host-side optimiser
+// drivers.  Control flow of the optimisers is copied literally from the reference
+// (code/bundle/lsa/levenberg_marquardt.m:54-247, levenberg_marquardt_powell.m:60-335,
+// gauss_newton_armijo.m:75-290); all vector work stays on the device and only a handful of
+// scalars cross to the host per trial step.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+#include <dlfcn.h>
+
+#include "../../include/dbat_gpu.h"
+#include "kernels.cuh"
+#include "launch.h"
+
+int64_t g_dbat_launches = 0;
+static std::string g_create_err;
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+            return DBAT_E_CUDA;                                                                    \
+        }                                                                                          \
+    } while (0)
+
+enum { SC_RR = 0, SC_JP2 = 1, SC_RJP = 2, SC_TRACE = 3, SC_A = 4, SC_B = 5, SC_C = 6, SC_PRR = 7, SC_N = 16 };
+enum { PH_EVAL = 0, PH_SCHUR, PH_CHOL, PH_SOLVE, PH_TRIAL, PH_JP, PH_N };
+static const char* kPhaseNames[PH_N] = {"eval_jac_assembly", "build_schur", "cholesky", "solve_backsub",
+                                        "trial_residual", "jp_stats"};
+
+// --------------------------------------------------------------------------------------------
+// NCCL through dlopen (torch ships libnccl.so.2; no link-time dependency)
+// --------------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid;
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(void**, int, nccl_uid, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static bool nccl_load() {
+    if (g_nccl.lib) return true;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) { g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+    if (!g_nccl.lib) return false;
+    g_nccl.GetUniqueId = (int (*)(nccl_uid*))dlsym(g_nccl.lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void**, int, nccl_uid, int))dlsym(g_nccl.lib, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
+    return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce;
+}
+
+// --------------------------------------------------------------------------------------------
+struct dbat_handle {
+    std::string err;
+    cudaStream_t st = nullptr;
+    DevProblem P{};
+    int NC = 0, m = 0, nIOrec = 0;
+    int nPriorIO = 0, nPriorEO = 0, nPriorOP = 0;
+    // host copies (CSC export, covariance layout)
+    std::vector<int> h_img_cm, h_pt_cm, h_img_start, h_pt_start, h_pm2cm;
+    std::vector<int> h_sh_col, h_eo_col, h_op_col, h_io_col;   // io_col: NC x nImg
+    std::vector<int> h_prior_col;
+    std::vector<double> h_prior_isig;
+    // device allocations
+    std::vector<void*> allocs;
+    int *d_IOsrc = nullptr, *d_IOdst = nullptr, *d_EOsrc = nullptr, *d_EOdst = nullptr, *d_OPsrc = nullptr, *d_OPdst = nullptr;
+    int nIOdes = 0, nEOdes = 0, nOPdes = 0;
+    int *d_rep = nullptr, *d_img_chunk_start = nullptr, *d_col2pt = nullptr;
+    double *d_tmpG = nullptr, *d_partial = nullptr, *d_scal = nullptr;
+    double* h_scal = nullptr;           // pinned
+    double *d_x = nullptr, *d_t = nullptr, *d_p = nullptr, *d_pgn = nullptr, *d_g = nullptr, *d_pc = nullptr;
+    double *d_camDiag = nullptr, *d_camG = nullptr, *d_diagN = nullptr, *d_dscale = nullptr;
+    double *d_r = nullptr;              // m doubles (export)
+    CholWork chol;
+    bool params_valid = false;          // parameter arrays correspond to d_x
+    bool normal_valid = false;          // Gram / point records correspond to d_x
+    // comm
+    void* comm = nullptr; int nranks = 1, rank = 0;
+    // CSC cache
+    std::vector<int64_t> cscJc, cscIr; std::vector<double> cscV; int cscWeighted = -1;
+    // phase timing
+    std::vector<cudaEvent_t> ev; size_t evUsed = 0;
+    struct Span { int ph; size_t a, b; };
+    std::vector<Span> spans;
+    double phase_ms[PH_N] = {0}; int64_t phase_cnt[PH_N] = {0};
+};
+
+template <typename T>
+static int dev_alloc(dbat_handle* h, T** p, size_t count) {
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)p, sizeof(T) * count);
+    if (e != cudaSuccess) { h->err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return DBAT_E_OOM; }
+    h->allocs.push_back(*p);
+    return 0;
+}
+template <typename T>
+static int dev_upload(dbat_handle* h, T** p, const std::vector<T>& v) {
+    int rc = dev_alloc(h, p, v.size());
+    if (rc) return rc;
+    if (!v.empty()) {
+        cudaError_t e = cudaMemcpy(*p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { h->err = std::string("cudaMemcpy: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
+    }
+    return 0;
+}
+
+static size_t ph_begin(dbat_handle* h) {
+    if (h->evUsed + 2 > h->ev.size()) return (size_t)-1;
+    size_t a = h->evUsed++;
+    cudaEventRecord(h->ev[a], h->st);
+    return a;
+}
+static void ph_end(dbat_handle* h, int ph, size_t a) {
+    if (a == (size_t)-1) return;
+    size_t b = h->evUsed++;
+    cudaEventRecord(h->ev[b], h->st);
+    h->spans.push_back({ph, a, b});
+}
+static void ph_reset(dbat_handle* h) {
+    h->evUsed = 0; h->spans.clear();
+    for (int i = 0; i < PH_N; ++i) { h->phase_ms[i] = 0; h->phase_cnt[i] = 0; }
+}
+static void ph_collect(dbat_handle* h) {
+    cudaStreamSynchronize(h->st);
+    for (auto& s : h->spans) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev[s.a], h->ev[s.b]);
+        h->phase_ms[s.ph] += ms; h->phase_cnt[s.ph]++;
+    }
+    h->spans.clear(); h->evUsed = 0;
+}
+
+// --------------------------------------------------------------------------------------------
+// create
+// --------------------------------------------------------------------------------------------
+static int fail_create(dbat_handle* h, int code, const std::string& msg) {
+    g_create_err = msg;
+    if (h) dbat_destroy(h);
+    return code;
+}
+
+extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
+    if (!d || !out) { g_create_err = "null argument"; return DBAT_E_BADARG; }
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail_create(nullptr, DBAT_E_CUDA, "no CUDA device available (libdbatgpu has no CPU fallback)");
+    dbat_handle* h = new dbat_handle();
+    const int nImg = (int)d->nImg, nOP = (int)d->nOP, nObs = (int)d->nIP;
+    const int nK = d->nK, nP = d->nP, NC = 5 + nK + nP;
+    if (d->distModel < 2 || d->distModel > 5)
+        return fail_create(h, DBAT_E_UNSUPPORTED, "distModel must be 2..5 (legacy models 1/-1 are not built yet)");
+    if (nK > DBAT_KMAX || nP > DBAT_PMAX || nK < 0 || nP < 0 || nP == 1)
+        return fail_create(h, DBAT_E_UNSUPPORTED, "nK/nP outside the compiled limits");
+    if (d->n <= 0 || nImg <= 0) return fail_create(h, DBAT_E_BADARG, "empty problem");
+    h->NC = NC;
+    DevProblem& P = h->P;
+    P.nImg = nImg; P.nOP = nOP; P.nObs = nObs; P.nK = nK; P.nP = nP; P.model = d->distModel - 2;
+    P.n = (int)d->n;
+
+    // ---- column maps from the deserialisation indices (multi_res.m:58-63)
+    std::vector<int> colIO((size_t)NC * nImg, -1), colEO((size_t)6 * nImg, -1), colOP((size_t)3 * nOP, -1);
+    auto fill = [&](std::vector<int>& col, const int64_t* src, const int64_t* dst, int64_t cnt) -> bool {
+        for (int64_t k = 0; k < cnt; ++k) {
+            const int64_t dd = dst[k] - 1, ss = src[k] - 1;
+            if (dd < 0 || dd >= (int64_t)col.size() || ss < 0 || ss >= d->n) return false;
+            col[dd] = (int)ss;
+        }
+        return true;
+    };
+    if (!fill(colIO, d->IOdes_src, d->IOdes_dest, d->nIOdes) || !fill(colEO, d->EOdes_src, d->EOdes_dest, d->nEOdes) ||
+        !fill(colOP, d->OPdes_src, d->OPdes_dest, d->nOPdes))
+        return fail_create(h, DBAT_E_BADARG, "deserialisation index out of range");
+    const int nC = (int)(d->n - d->nOPdes);
+    for (int c : colOP) if (c >= 0 && c < nC) return fail_create(h, DBAT_E_UNSUPPORTED, "x must be ordered [IO;EO;OP]");
+    for (int c : colIO) if (c >= nC) return fail_create(h, DBAT_E_UNSUPPORTED, "x must be ordered [IO;EO;OP]");
+    for (int c : colEO) if (c >= nC) return fail_create(h, DBAT_E_UNSUPPORTED, "x must be ordered [IO;EO;OP]");
+    P.nC = nC;
+
+    // ---- observations: 0-based, verify (image, OP) ordering
+    h->h_img_cm.resize(nObs); h->h_pt_cm.resize(nObs);
+    std::vector<char> imgHasObs(nImg, 0);
+    for (int k = 0; k < nObs; ++k) {
+        const int64_t i = d->IPimg[k] - 1, j = d->IPop[k] - 1;
+        if (i < 0 || i >= nImg || j < 0 || j >= nOP) return fail_create(h, DBAT_E_BADARG, "IPimg/IPop out of range");
+        if (k > 0 && (i < h->h_img_cm[k - 1] || (i == h->h_img_cm[k - 1] && j <= h->h_pt_cm[k - 1])))
+            return fail_create(h, DBAT_E_BADARG, "image points must be sorted by (image, OP) without duplicates");
+        h->h_img_cm[k] = (int)i; h->h_pt_cm[k] = (int)j; imgHasObs[i] = 1;
+    }
+    // ---- structure checks: one shared IO block; every EO column owned by one image
+    h->h_sh_col.assign(DBAT_NSLOT, -1);
+    auto slot_of = [&](int row) { return row < 5 ? row : (row < 5 + nK ? DBAT_SLOT_K + (row - 5) : DBAT_SLOT_P + (row - 5 - nK)); };
+    int firstImg = -1;
+    for (int i = 0; i < nImg; ++i) if (imgHasObs[i]) { firstImg = i; break; }
+    for (int r = 0; r < NC; ++r) {
+        int v = firstImg >= 0 ? colIO[(size_t)firstImg * NC + r] : -1;
+        for (int i = 0; i < nImg; ++i)
+            if (imgHasObs[i] && colIO[(size_t)i * NC + r] != v)
+                return fail_create(h, DBAT_E_UNSUPPORTED,
+                                   "IO parameters must form one block shared by all images (image-variant / "
+                                   "multi-camera IO is not built yet)");
+        h->h_sh_col[slot_of(r)] = v;
+    }
+    {
+        std::vector<int> owner(nC, -1);
+        for (int i = 0; i < nImg; ++i)
+            for (int a = 0; a < 6; ++a) {
+                const int c = colEO[(size_t)i * 6 + a];
+                if (c < 0) continue;
+                if (owner[c] >= 0 && owner[c] != i) return fail_create(h, DBAT_E_UNSUPPORTED, "shared EO blocks are not built yet");
+                owner[c] = i;
+            }
+        int prev = -1;   // EO columns must ascend with (image, element): serialisation order
+        for (int i = 0; i < nImg; ++i)
+            for (int a = 0; a < 6; ++a) {
+                const int c = colEO[(size_t)i * 6 + a];
+                if (c < 0) continue;
+                if (c <= prev) return fail_create(h, DBAT_E_UNSUPPORTED, "EO columns must be in serialisation order");
+                prev = c;
+            }
+        for (int s = 0; s < DBAT_NSLOT; ++s)
+            if (h->h_sh_col[s] >= 0 && prev >= 0) {
+                int minEO = nC;
+                for (int c : colEO) if (c >= 0) minEO = std::min(minEO, c);
+                if (h->h_sh_col[s] > minEO) return fail_create(h, DBAT_E_UNSUPPORTED, "IO columns must precede EO columns in x");
+            }
+    }
+    h->h_io_col = colIO; h->h_eo_col = colEO; h->h_op_col = colOP;
+
+    // ---- unique IO records (by value of the whole IO column + pixel size)
+    std::vector<int> ioOfImg(nImg, 0), rep;
+    {
+        std::map<std::vector<double>, int> seen;
+        for (int i = 0; i < nImg; ++i) {
+            std::vector<double> key(d->IOval + (size_t)i * NC, d->IOval + (size_t)(i + 1) * NC);
+            auto it = seen.find(key);
+            if (it == seen.end()) { it = seen.emplace(key, (int)rep.size()).first; rep.push_back(i); }
+            ioOfImg[i] = it->second;
+        }
+    }
+    h->nIOrec = (int)rep.size();
+
+    // ---- weights, orderings, chunks
+    std::vector<double2> uv_cm(nObs), isig_cm(nObs), uv_pm(nObs), isig_pm(nObs);
+    for (int k = 0; k < nObs; ++k) {
+        const int i = h->h_img_cm[k];
+        uv_cm[k] = make_double2(d->IPval[2 * (size_t)k], d->IPval[2 * (size_t)k + 1]);
+        const double sx = d->IPstd[2 * (size_t)k] * d->pxSize[2 * (size_t)i];
+        const double sy = d->IPstd[2 * (size_t)k + 1] * d->pxSize[2 * (size_t)i + 1];
+        isig_cm[k] = make_double2(1.0 / sx, 1.0 / sy);           // buildweightmatrix.m:13-23, R = chol(W)
+    }
+    h->h_img_start.assign(nImg + 1, 0);
+    for (int k = 0; k < nObs; ++k) h->h_img_start[h->h_img_cm[k] + 1]++;
+    for (int i = 0; i < nImg; ++i) h->h_img_start[i + 1] += h->h_img_start[i];
+    h->h_pt_start.assign(nOP + 1, 0);
+    for (int k = 0; k < nObs; ++k) h->h_pt_start[h->h_pt_cm[k] + 1]++;
+    for (int j = 0; j < nOP; ++j) h->h_pt_start[j + 1] += h->h_pt_start[j];
+    h->h_pm2cm.resize(nObs);
+    std::vector<int> img_pm(nObs);
+    {
+        std::vector<int> fillp(h->h_pt_start.begin(), h->h_pt_start.end() - 1);
+        for (int k = 0; k < nObs; ++k) {                       // stable: images ascend inside a point
+            const int o = fillp[h->h_pt_cm[k]]++;
+            h->h_pm2cm[o] = k; img_pm[o] = h->h_img_cm[k]; uv_pm[o] = uv_cm[k]; isig_pm[o] = isig_cm[k];
+        }
+    }
+    std::vector<Chunk> chunks;
+    std::vector<int> img_chunk_start(nImg + 1, 0);
+    for (int i = 0; i < nImg; ++i) {
+        img_chunk_start[i] = (int)chunks.size();
+        for (int s = h->h_img_start[i]; s < h->h_img_start[i + 1]; s += DBAT_CHUNK)
+            chunks.push_back({i, s, std::min(DBAT_CHUNK, h->h_img_start[i + 1] - s), 0});
+    }
+    img_chunk_start[nImg] = (int)chunks.size();
+    P.nChunks = (int)chunks.size();
+
+    // ---- prior observations
+    const int nPrior = (int)(d->nPriorIO + d->nPriorEO + d->nPriorOP);
+    h->nPriorIO = (int)d->nPriorIO; h->nPriorEO = (int)d->nPriorEO; h->nPriorOP = (int)d->nPriorOP;
+    P.nPrior = nPrior;
+    h->h_prior_col.resize(nPrior); h->h_prior_isig.resize(nPrior);
+    std::vector<double> prior_val(nPrior);
+    for (int k = 0; k < nPrior; ++k) {
+        const int64_t c = d->prior_x[k] - 1;
+        if (c < 0 || c >= d->n) return fail_create(h, DBAT_E_BADARG, "prior_x out of range");
+        if (!(d->prior_std[k] > 0)) return fail_create(h, DBAT_E_BADARG, "prior std must be positive");
+        h->h_prior_col[k] = (int)c; prior_val[k] = d->prior_val[k]; h->h_prior_isig[k] = 1.0 / d->prior_std[k];
+    }
+    h->m = 2 * nObs + nPrior;
+    std::vector<int> col2pt(std::max(1, P.n - nC), -1);
+    for (int e = 0; e < 3 * nOP; ++e) if (colOP[e] >= 0) col2pt[colOP[e] - nC] = e;
+
+    // ---- device side
+    if (cudaStreamCreate(&h->st) != cudaSuccess) return fail_create(h, DBAT_E_CUDA, "cudaStreamCreate failed");
+    int rc = 0;
+#define UP(ptr, vec) if ((rc = dev_upload(h, &ptr, vec))) return fail_create(h, rc, h->err)
+#define AL(ptr, cnt) if ((rc = dev_alloc(h, &ptr, (size_t)(cnt)))) return fail_create(h, rc, h->err)
+    double2 *d_uv_cm, *d_isig_cm, *d_uv_pm, *d_isig_pm; int *d_pt_cm, *d_img_cm, *d_img_pm, *d_pm2cm, *d_pt_start;
+    Chunk* d_chunks; int *d_sh, *d_eo, *d_op, *d_pc; double *d_pv, *d_pi;
+    UP(d_uv_cm, uv_cm); UP(d_isig_cm, isig_cm); UP(d_uv_pm, uv_pm); UP(d_isig_pm, isig_pm);
+    UP(d_pt_cm, h->h_pt_cm); UP(d_img_cm, h->h_img_cm); UP(d_img_pm, img_pm); UP(d_pm2cm, h->h_pm2cm);
+    UP(d_pt_start, h->h_pt_start); UP(d_chunks, chunks);
+    UP(d_sh, h->h_sh_col); UP(d_eo, colEO); UP(d_op, colOP);
+    UP(d_pc, h->h_prior_col); UP(d_pv, prior_val); UP(d_pi, h->h_prior_isig);
+    P.uv_cm = d_uv_cm; P.isig_cm = d_isig_cm; P.pt_cm = d_pt_cm; P.img_cm = d_img_cm;
+    P.uv_pm = d_uv_pm; P.isig_pm = d_isig_pm; P.img_pm = d_img_pm; P.pm2cm = d_pm2cm; P.pt_start = d_pt_start;
+    P.chunks = d_chunks; P.sh_col = d_sh; P.eo_col = d_eo; P.op_col = d_op;
+    P.prior_col = d_pc; P.prior_val = d_pv; P.prior_isig = d_pi;
+    {
+        std::vector<double> io(d->IOval, d->IOval + (size_t)NC * nImg), eo(d->EOval, d->EOval + (size_t)6 * nImg),
+            op(d->OPval, d->OPval + (size_t)3 * nOP);
+        UP(P.IOval, io); UP(P.EOval, eo); UP(P.OPval, op);
+        std::vector<ImgRec> recs(nImg);
+        for (int i = 0; i < nImg; ++i) {
+            memset(&recs[i], 0, sizeof(ImgRec));
+            recs[i].sz = d->pxSize[2 * (size_t)i];                // multi_res.m:138 passes sz(1)
+            recs[i].io = ioOfImg[i];
+        }
+        UP(P.img, recs);
+        AL(P.io, h->nIOrec);
+        UP(h->d_rep, rep);
+    }
+    auto to_int = [&](const int64_t* p, int64_t cnt, bool isDest) { std::vector<int> v(cnt); for (int64_t k = 0; k < cnt; ++k) v[k] = (int)(p[k] - 1); (void)isDest; return v; };
+    h->nIOdes = (int)d->nIOdes; h->nEOdes = (int)d->nEOdes; h->nOPdes = (int)d->nOPdes;
+    { auto v = to_int(d->IOdes_src, d->nIOdes, false); UP(h->d_IOsrc, v); }
+    { auto v = to_int(d->IOdes_dest, d->nIOdes, true); UP(h->d_IOdst, v); }
+    { auto v = to_int(d->EOdes_src, d->nEOdes, false); UP(h->d_EOsrc, v); }
+    { auto v = to_int(d->EOdes_dest, d->nEOdes, true); UP(h->d_EOdst, v); }
+    { auto v = to_int(d->OPdes_src, d->nOPdes, false); UP(h->d_OPsrc, v); }
+    { auto v = to_int(d->OPdes_dest, d->nOPdes, true); UP(h->d_OPdst, v); }
+    UP(h->d_img_chunk_start, img_chunk_start); UP(h->d_col2pt, col2pt);
+    P.ldS = std::max(128, ((nC + 127) / 128) * 128);
+    AL(P.chunkG, (size_t)std::max(1, P.nChunks) * DBAT_GSZ);
+    AL(P.imgG, (size_t)nImg * DBAT_GSZ);
+    AL(P.shG, DBAT_GSZ);
+    AL(P.pt, (size_t)std::max(1, nOP) * DBAT_PT_STRIDE);
+    AL(P.W, (size_t)std::max(1, nObs) * DBAT_W_STRIDE);
+    AL(P.S, (size_t)P.ldS * P.ldS);
+    AL(P.rhs, P.ldS);
+    AL(h->d_tmpG, (size_t)64 * DBAT_GSZ);
+    const int nPartial = 2 * ((std::max(nObs, P.n) + 255) / 256) + 64;
+    AL(h->d_partial, nPartial);
+    AL(h->d_scal, SC_N);
+    AL(h->d_x, P.n); AL(h->d_t, P.n); AL(h->d_p, P.n); AL(h->d_pgn, P.n); AL(h->d_g, P.n); AL(h->d_pc, P.ldS);
+    AL(h->d_camDiag, std::max(1, nC)); AL(h->d_camG, std::max(1, nC)); AL(h->d_diagN, P.n); AL(h->d_dscale, P.n);
+    AL(h->d_r, h->m);
+    if (cudaMallocHost((void**)&h->h_scal, sizeof(double) * SC_N) != cudaSuccess)
+        return fail_create(h, DBAT_E_OOM, "cudaMallocHost failed");
+    chol_alloc(h->chol, nC, P.ldS);
+    h->ev.resize(4096);
+    for (auto& e : h->ev) cudaEventCreate(&e);
+    cudaMemset(h->d_p, 0, sizeof(double) * P.n);
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail_create(h, DBAT_E_CUDA, "device error during create");
+    *out = h;
+    return DBAT_OK;
+}
+
+extern "C" void dbat_destroy(dbat_handle* h) {
+    if (!h) return;
+    if (h->st) cudaStreamSynchronize(h->st);
+    for (void* p : h->allocs) cudaFree(p);
+    if (h->h_scal) cudaFreeHost(h->h_scal);
+    chol_free(h->chol);
+    for (auto& e : h->ev) cudaEventDestroy(e);
+    if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+extern "C" const char* dbat_last_error(const dbat_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+extern "C" int64_t dbat_num_unknowns(const dbat_handle* h) { return h ? h->P.n : 0; }
+extern "C" int64_t dbat_num_residuals(const dbat_handle* h) { return h ? h->m : 0; }
+
+// --------------------------------------------------------------------------------------------
+// evaluation building blocks
+// --------------------------------------------------------------------------------------------
+static int allreduce(dbat_handle* h, double* buf, size_t cnt) {
+    if (h->nranks <= 1) return 0;
+    int rc = g_nccl.AllReduce(buf, buf, cnt, /*ncclDouble*/ 8, /*ncclSum*/ 0, h->comm, h->st);
+    if (rc != 0) { h->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); return DBAT_E_NCCL; }
+    return 0;
+}
+
+// scatter device vector xdev into the parameter arrays and rebuild the per-image records
+static void set_params(dbat_handle* h, const double* xdev) {
+    launch_deserialize(xdev, h->d_IOsrc, h->d_IOdst, h->P.IOval, h->nIOdes, h->st);
+    launch_deserialize(xdev, h->d_EOsrc, h->d_EOdst, h->P.EOval, h->nEOdes, h->st);
+    launch_deserialize(xdev, h->d_OPsrc, h->d_OPdst, h->P.OPval, h->nOPdes, h->st);
+    launch_param_setup(h->P, h->d_rep, h->nIOrec, h->st);
+}
+
+static inline double gram_host(const double* G, int R, int C) {
+    if (R < C) std::swap(R, C);
+    const int p = R >> 3, q = C >> 3, i = R & 7, j = C & 7;
+    return G[(p * (p + 1) / 2 + q) * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1)];
+}
+
+// residual + Jacobian + assembly at d_x.  On return h_scal[SC_RR] = r'r (global).
+static int eval_full(dbat_handle* h) {
+    size_t a = ph_begin(h);
+    set_params(h, h->d_x);
+    h->params_valid = true;
+    launch_cam_side(h->P, h->d_img_chunk_start, h->d_tmpG, h->st);
+    launch_point_side(h->P, h->st);
+    launch_prior_apply(h->P, h->d_x, h->d_camDiag, h->d_camG, h->d_col2pt, h->st);
+    if (h->nranks > 1) {
+        int rc = allreduce(h, h->P.imgG, (size_t)h->P.nImg * DBAT_GSZ);
+        if (!rc) rc = allreduce(h, h->P.shG, DBAT_GSZ);
+        if (rc) return rc;
+    }
+    // r'r = Gram(r,r) + prior rows
+    static double hG[DBAT_GSZ];
+    launch_prior_rr(h->P, h->d_x, h->d_partial, h->d_scal, SC_PRR, h->st);
+    cudaMemcpyAsync(hG, h->P.shG, sizeof(double) * DBAT_GSZ, cudaMemcpyDeviceToHost, h->st);
+    cudaMemcpyAsync(h->h_scal + SC_PRR, h->d_scal + SC_PRR, sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    ph_end(h, PH_EVAL, a);
+    cudaStreamSynchronize(h->st);
+    h->h_scal[SC_RR] = gram_host(hG, DBAT_COL_R, DBAT_COL_R) + h->h_scal[SC_PRR];
+    h->normal_valid = true;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string("eval_full: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
+    return 0;
+}
+
+// weighted r'r at device vector xdev (residual only)
+static int eval_rr(dbat_handle* h, const double* xdev, double* rr) {
+    size_t a = ph_begin(h);
+    set_params(h, xdev);
+    h->params_valid = (xdev == h->d_x);
+    launch_resid(h->P, xdev, h->d_partial, h->d_scal, SC_RR, nullptr, 1, h->st);
+    if (h->nranks > 1) { int rc = allreduce(h, h->d_scal + SC_RR, 1); if (rc) return rc; }
+    cudaMemcpyAsync(h->h_scal + SC_RR, h->d_scal + SC_RR, sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    ph_end(h, PH_TRIAL, a);
+    cudaError_t e = cudaStreamSynchronize(h->st);
+    if (e != cudaSuccess) { h->err = std::string("eval_rr: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
+    *rr = h->h_scal[SC_RR];
+    return 0;
+}
+
+// |J v|^2 and r'(J v) with J, r at d_x
+static int eval_jp(dbat_handle* h, const double* v, double* jp2, double* rjp) {
+    size_t a = ph_begin(h);
+    if (!h->params_valid) { set_params(h, h->d_x); h->params_valid = true; }
+    launch_jp(h->P, h->d_x, v, h->d_partial, h->d_scal, SC_JP2, SC_RJP, h->st);
+    if (h->nranks > 1) { int rc = allreduce(h, h->d_scal + SC_JP2, 2); if (rc) return rc; }
+    cudaMemcpyAsync(h->h_scal + SC_JP2, h->d_scal + SC_JP2, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    ph_end(h, PH_JP, a);
+    cudaError_t e = cudaStreamSynchronize(h->st);
+    if (e != cudaSuccess) { h->err = std::string("eval_jp: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
+    *jp2 = h->h_scal[SC_JP2]; *rjp = h->h_scal[SC_RJP];
+    return 0;
+}
+
+static int dev_dot(dbat_handle* h, const double* a, const double* b, int n, double* out) {
+    launch_dot(a, b, n, h->d_partial, h->d_scal, SC_A, h->st);
+    cudaMemcpyAsync(h->h_scal + SC_A, h->d_scal + SC_A, sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    if (cudaStreamSynchronize(h->st) != cudaSuccess) { h->err = "dot failed"; return DBAT_E_CUDA; }
+    *out = h->h_scal[SC_A];
+    return 0;
+}
+
+// Solve the (damped, optionally Jacobi-scaled) normal equations at d_x -> step in `pout`.
+// singular: 1 if the reduced system was not positive definite / numerically singular.
+static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, int* singular) {
+    DevProblem& P = h->P;
+    size_t a = ph_begin(h);
+    launch_build_S(P, h->d_camDiag, h->d_camG, lambda, h->st);
+    if (h->nranks > 1 && h->rank != 0) {
+        // only rank 0 contributes N_cc + lambda*I and -g_c; the others add their Schur terms to zero
+        cudaMemsetAsync(P.S, 0, sizeof(double) * (size_t)P.ldS * P.ldS, h->st);
+        cudaMemsetAsync(P.rhs, 0, sizeof(double) * P.ldS, h->st);
+    }
+    launch_schur(P, lambda, h->st);
+    if (h->nranks > 1) {
+        int rc = allreduce(h, P.S, (size_t)P.ldS * P.ldS);
+        if (!rc) rc = allreduce(h, P.rhs, P.ldS);
+        if (rc) return rc;
+    }
+    if (jacobi) {
+        launch_diag(P, h->d_camDiag, h->d_diagN, h->st);
+        launch_inv_sqrt(h->d_diagN, h->d_dscale, P.nC, h->st);
+        launch_scale_S(P, h->d_dscale, h->st);
+    }
+    ph_end(h, PH_SCHUR, a);
+    a = ph_begin(h);
+    chol_factor(h->chol, P.S, h->st);
+    ph_end(h, PH_CHOL, a);
+    a = ph_begin(h);
+    cudaMemcpyAsync(h->d_pc, P.rhs, sizeof(double) * P.ldS, cudaMemcpyDeviceToDevice, h->st);
+    chol_solve(h->chol, P.S, h->d_pc, h->st);
+    if (jacobi) launch_mul(h->d_pc, h->d_dscale, h->d_pc, P.nC, h->st);
+    launch_backsub(P, lambda, h->d_pc, pout, h->st);
+    int info = 0; double mm[2] = {1, 1};
+    cudaMemcpyAsync(&info, h->chol.info, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+    cudaMemcpyAsync(mm, h->chol.minmax, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    ph_end(h, PH_SOLVE, a);
+    cudaError_t e = cudaStreamSynchronize(h->st);
+    if (e != cudaSuccess) { h->err = std::string("solve_step: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
+    // MATLAB's mldivide warns (singularMatrix / nearlySingularMatrix) when rcond < eps; with the
+    // Cholesky factor rcond ~ (min pivot / max pivot)^2.
+    const double ratio = mm[1] > 0 ? mm[0] / mm[1] : 0.0;
+    *singular = (info != 0) || !(ratio * ratio > 2.220446049250313e-16);
+    return 0;
+}
+
+// full gradient g = J'r into d_g (camera part from the Grams, point part from the records)
+__global__ void k_gradient(DevProblem P, const double* __restrict__ camG, double* __restrict__ g);
+
+// --------------------------------------------------------------------------------------------
+// public evaluation entry points
+// --------------------------------------------------------------------------------------------
+extern "C" int dbat_eval(dbat_handle* h, const double* x, double* r, int weighted) {
+    if (!h || !x) return DBAT_E_BADARG;
+    CK(cudaMemcpyAsync(h->d_x, x, sizeof(double) * h->P.n, cudaMemcpyHostToDevice, h->st));
+    set_params(h, h->d_x);
+    h->params_valid = true; h->normal_valid = false; h->cscWeighted = -1;
+    launch_resid(h->P, h->d_x, h->d_partial, h->d_scal, SC_RR, h->d_r, weighted, h->st);
+    if (r) CK(cudaMemcpyAsync(r, h->d_r, sizeof(double) * h->m, cudaMemcpyDeviceToHost, h->st));
+    CK(cudaStreamSynchronize(h->st));
+    return DBAT_OK;
+}
+
+static int build_csc(dbat_handle* h, int weighted) {
+    if (h->cscWeighted == weighted) return 0;
+    if (h->nranks > 1) { h->err = "Jacobian export is single-rank only"; return DBAT_E_UNSUPPORTED; }
+    DevProblem& P = h->P;
+    if (!h->params_valid) { set_params(h, h->d_x); h->params_valid = true; }
+    const int LD = DBAT_NSLOT + 9;
+    double* dJ = nullptr;
+    const size_t cnt = (size_t)std::max(1, P.nObs) * 2 * LD;
+    CK(cudaMalloc(&dJ, sizeof(double) * cnt));
+    launch_export_jac(P, dJ, weighted, h->st);
+    std::vector<double> J(cnt);
+    cudaError_t e = cudaMemcpyAsync(J.data(), dJ, sizeof(double) * cnt, cudaMemcpyDeviceToHost, h->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+    cudaFree(dJ);
+    if (e != cudaSuccess) { h->err = std::string("export: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
+    // column -> (kind, index)
+    const int n = P.n, nC = P.nC;
+    std::vector<int> kind(n, -1), idx(n, -1);
+    for (int s = 0; s < DBAT_NSLOT; ++s) if (h->h_sh_col[s] >= 0) { kind[h->h_sh_col[s]] = 0; idx[h->h_sh_col[s]] = s; }
+    for (int e2 = 0; e2 < 6 * P.nImg; ++e2) if (h->h_eo_col[e2] >= 0) { kind[h->h_eo_col[e2]] = 1; idx[h->h_eo_col[e2]] = e2; }
+    for (int e2 = 0; e2 < 3 * P.nOP; ++e2) if (h->h_op_col[e2] >= 0) { kind[h->h_op_col[e2]] = 2; idx[h->h_op_col[e2]] = e2; }
+    std::vector<std::vector<int>> priorOfCol;   // rows of prior observations per column (rare)
+    std::map<int, std::vector<int>> priorMap;
+    for (int k = 0; k < P.nPrior; ++k) priorMap[h->h_prior_col[k]].push_back(k);
+    h->cscJc.assign(n + 1, 0); h->cscIr.clear(); h->cscV.clear();
+    h->cscIr.reserve((size_t)P.nObs * 2 * 18); h->cscV.reserve((size_t)P.nObs * 2 * 18);
+    auto push = [&](int64_t row, double v) { if (v != 0.0) { h->cscIr.push_back(row); h->cscV.push_back(v); } };
+    (void)nC;
+    for (int c = 0; c < n; ++c) {
+        if (kind[c] == 0) {
+            const int s = idx[c];
+            for (int k = 0; k < P.nObs; ++k) {
+                push(2 * (int64_t)k, J[((size_t)k * 2) * LD + s]);
+                push(2 * (int64_t)k + 1, J[((size_t)k * 2 + 1) * LD + s]);
+            }
+        } else if (kind[c] == 1) {
+            const int i = idx[c] / 6, a2 = idx[c] % 6;
+            for (int k = h->h_img_start[i]; k < h->h_img_start[i + 1]; ++k) {
+                push(2 * (int64_t)k, J[((size_t)k * 2) * LD + DBAT_NSLOT + a2]);
+                push(2 * (int64_t)k + 1, J[((size_t)k * 2 + 1) * LD + DBAT_NSLOT + a2]);
+            }
+        } else if (kind[c] == 2) {
+            const int j = idx[c] / 3, t = idx[c] % 3;
+            for (int o = h->h_pt_start[j]; o < h->h_pt_start[j + 1]; ++o) {
+                const int k = h->h_pm2cm[o];
+                push(2 * (int64_t)k, J[((size_t)k * 2) * LD + DBAT_NSLOT + 6 + t]);
+                push(2 * (int64_t)k + 1, J[((size_t)k * 2 + 1) * LD + DBAT_NSLOT + 6 + t]);
+            }
+        }
+        auto it = priorMap.find(c);
+        if (it != priorMap.end())
+            for (int k : it->second) push(2 * (int64_t)P.nObs + k, weighted ? h->h_prior_isig[k] : 1.0);
+        h->cscJc[c + 1] = (int64_t)h->cscIr.size();
+    }
+    h->cscWeighted = weighted;
+    return 0;
+}
+extern "C" int dbat_jacobian_nnz(dbat_handle* h, int weighted, int64_t* nnz) {
+    if (!h || !nnz) return DBAT_E_BADARG;
+    int rc = build_csc(h, weighted ? 1 : 0);
+    if (rc) return rc;
+    *nnz = (int64_t)h->cscIr.size();
+    return DBAT_OK;
+}
+extern "C" int dbat_jacobian_csc(dbat_handle* h, int weighted, int64_t* Jc, int64_t* Ir, double* vals) {
+    if (!h || !Jc || !Ir || !vals) return DBAT_E_BADARG;
+    int rc = build_csc(h, weighted ? 1 : 0);
+    if (rc) return rc;
+    memcpy(Jc, h->cscJc.data(), sizeof(int64_t) * h->cscJc.size());
+    memcpy(Ir, h->cscIr.data(), sizeof(int64_t) * h->cscIr.size());
+    memcpy(vals, h->cscV.data(), sizeof(double) * h->cscV.size());
+    return DBAT_OK;
+}
+
+extern "C" int dbat_normal_step(dbat_handle* h, const double* x, double lambda, int jacobi_scale, double* p,
+                                double* stats) {
+    if (!h) return DBAT_E_BADARG;
+    if (x) { CK(cudaMemcpyAsync(h->d_x, x, sizeof(double) * h->P.n, cudaMemcpyHostToDevice, h->st)); h->cscWeighted = -1; }
+    ph_reset(h);
+    const int64_t l0 = g_dbat_launches;
+    int rc = eval_full(h);
+    if (rc) return rc;
+    int sing = 0;
+    rc = solve_step(h, lambda, jacobi_scale != 0, h->d_p, &sing);
+    if (rc) return rc;
+    double jp2 = 0, rjp = 0;
+    rc = eval_jp(h, h->d_p, &jp2, &rjp);
+    if (rc) return rc;
+    if (p) CK(cudaMemcpyAsync(p, h->d_p, sizeof(double) * h->P.n, cudaMemcpyDeviceToHost, h->st));
+    ph_collect(h);
+    if (stats) { stats[0] = 0.5 * h->h_scal[SC_RR]; stats[1] = jp2; stats[2] = rjp; stats[3] = sing; stats[4] = (double)(g_dbat_launches - l0); }
+    return DBAT_OK;
+}
+
+extern "C" int dbat_phase_times(const dbat_handle* h, const char** names, double* ms, int64_t* count, int cap) {
+    if (!h) return 0;
+    int n = std::min(cap, (int)PH_N);
+    for (int i = 0; i < n; ++i) { if (names) names[i] = kPhaseNames[i]; if (ms) ms[i] = h->phase_ms[i]; if (count) count[i] = h->phase_cnt[i]; }
+    return n;
+}
+
+// --------------------------------------------------------------------------------------------
+// optimisers
+// --------------------------------------------------------------------------------------------
+extern "C" void dbat_default_opts(int method, dbat_opts* o) {
+    if (!o) return;
+    memset(o, 0, sizeof(*o));
+    o->maxIter = 20; o->convTol = 1e-6; o->absTerm = 0; o->singularTest = 1; o->doTrace = 0;
+    o->lambda0 = -1e-10; o->lambdaMin = -1e-10;           // bundle.m:301-304
+    o->delta0 = -1.0;                                     // norm(x0), bundle.m:325
+    o->alphaMin = 1e-9;                                   // bundle.m:283
+    if (method == DBAT_METHOD_LMP) { o->mu = 0.25; o->eta = 0.75; }   // bundle.m:321-322
+    else { o->mu = 0.1; o->eta = 0.0; }                   // bundle.m:281
+}
+
+struct TraceOut {
+    dbat_result* res; int n; int cap;
+    void store_x(dbat_handle* h, int col) {
+        if (res->trace && col < cap)
+            cudaMemcpyAsync(res->trace + (size_t)col * n, h->d_x, sizeof(double) * n, cudaMemcpyDeviceToHost, h->st);
+        if (col + 1 > res->nTrace) res->nTrace = std::min(col + 1, cap);
+    }
+};
+
+static bool term_fun(const dbat_opts* o, double jp2, double rr) {
+    // bundle.m:186-192
+    if (o->absTerm) return std::sqrt(rr) <= o->convTol;
+    return std::sqrt(jp2) <= o->convTol * std::sqrt(rr);
+}
+
+// cheap structural-rank screen standing in for sprank(J)<n (levenberg_marquardt.m:126-135):
+// every unknown needs at least one residual row, every point/image needs as many rows as free
+// coordinates, and m >= n.
+static bool structurally_deficient(dbat_handle* h) {
+    DevProblem& P = h->P;
+    if (h->nranks > 1) return false;
+    if (h->m < P.n) return true;
+    std::vector<int> priorCnt(P.n, 0);
+    for (int c : h->h_prior_col) priorCnt[c]++;
+    for (int j = 0; j < P.nOP; ++j) {
+        int freec = 0, pri = 0;
+        for (int t = 0; t < 3; ++t) { const int c = h->h_op_col[3 * (size_t)j + t]; if (c >= 0) { ++freec; pri += priorCnt[c]; } }
+        if (freec && 2 * (h->h_pt_start[j + 1] - h->h_pt_start[j]) + pri < freec) return true;
+    }
+    for (int i = 0; i < P.nImg; ++i) {
+        int freec = 0, pri = 0;
+        for (int a = 0; a < 6; ++a) { const int c = h->h_eo_col[6 * (size_t)i + a]; if (c >= 0) { ++freec; pri += priorCnt[c]; } }
+        if (freec && 2 * (h->h_img_start[i + 1] - h->h_img_start[i]) + pri < freec) return true;
+    }
+    return false;
+}
+
+static int trace_sum(dbat_handle* h, double* tr) {
+    launch_diag(h->P, h->d_camDiag, h->d_diagN, h->st);
+    return dev_dot(h, h->d_diagN, nullptr, h->P.n, tr);
+}
+
+static int solve_lm(dbat_handle* h, const dbat_opts* o, dbat_result* res, TraceOut& T) {
+    // levenberg_marquardt.m:54-247
+    DevProblem& P = h->P;
+    const int nn = P.n;
+    int n = 0, code = 0, rc;
+    if ((rc = eval_full(h))) return rc;                               // :76-82
+    double rr = h->h_scal[SC_RR], f = 0.5 * rr;
+    double lambda0 = o->lambda0, lambdaMin = o->lambdaMin;
+    if (lambda0 < 0 || lambdaMin < 0) {                               // :88-95
+        double tr = 0; if ((rc = trace_sum(h, &tr))) return rc;
+        if (lambda0 < 0) lambda0 = std::fabs(lambda0) * tr / nn;
+        if (lambdaMin < 0) lambdaMin = std::fabs(lambdaMin) * tr / nn;
+    }
+    double lambda = lambda0;
+    if (lambda < lambdaMin) lambda = 0.0;
+    res->nDamping = 0; res->nRr = 0;
+    res->damping[res->nDamping++] = lambda;                           // :106
+    double prevLambda = NAN, jp2 = 0, rjp = 0;
+    const int cap = o->maxIter + 2;
+    while (true) {
+        while (n <= o->maxIter) {                                     // :117
+            int sing = 0;
+            if ((rc = solve_step(h, lambda, false, h->d_p, &sing))) return rc;   // :119
+            if (res->nRr < cap + 1) res->rr[res->nRr++] = std::sqrt(rr);      // :122
+            if (n == 0 && structurally_deficient(h)) { code = -4; break; }   // :126-135
+            if (res->nDamping < cap + 1) res->damping[res->nDamping++] = lambda;   // :136
+            if (o->doTrace) printf("Levenberg-Marquardt: iteration %d, residual norm=%.2g, lambda=%.2g\n", n, std::sqrt(rr), lambda);
+            T.store_x(h, n);                                          // :149-156
+            n++;                                                      // :159
+            if ((rc = eval_jp(h, h->d_p, &jp2, &rjp))) return rc;     // :162
+            launch_axpy(1.0, h->d_p, h->d_x, h->d_t, nn, h->st);      // :165 t=x+p
+            double rrNew = 0;
+            if ((rc = eval_rr(h, h->d_t, &rrNew))) return rc;         // :166-167
+            const double fNew = 0.5 * rrNew;
+            if (fNew < f) {                                           // :177 (no veto function)
+                std::swap(h->d_x, h->d_t);
+                lambda = lambda / 10;                                 // :181
+                if (lambda < lambdaMin) lambda = 0.0;
+                if ((rc = eval_full(h))) return rc;                   // :188-194
+                rr = h->h_scal[SC_RR]; f = 0.5 * rr;
+                break;
+            } else {
+                lambda = (lambda == 0.0) ? lambdaMin : lambda * 10;   // :198-206
+            }
+        }
+        if (code != 0) break;
+        if (prevLambda == 0.0 && term_fun(o, jp2, rr)) break;         // :217
+        prevLambda = lambda;                                          // :222
+        if (n > o->maxIter) { code = -1; break; }
+    }
+    T.store_x(h, n);                                                  // :238-240
+    if (res->nRr < cap + 1) res->rr[res->nRr++] = std::sqrt(rr);      // :242
+    res->code = code; res->iters = n;
+    return 0;
+}
+
+static int solve_gna(dbat_handle* h, const dbat_opts* o, dbat_result* res, TraceOut& T) {
+    // gauss_newton_armijo.m:75-290
+    DevProblem& P = h->P;
+    const int nn = P.n;
+    int n = 0, code = 0, rc;
+    const int cap = o->maxIter + 2;
+    res->nDamping = 0; res->nRr = 0;
+    T.store_x(h, 0);                                                  // :82
+    double rr = 0;
+    while (true) {
+        if ((rc = eval_full(h))) return rc;                           // :112-116
+        rr = h->h_scal[SC_RR];
+        if (res->nRr < cap + 1) res->rr[res->nRr++] = std::sqrt(rr);
+        if (o->doTrace) printf("Gauss-Newton-Armijo: iteration %d, residual norm=%.2g\n", n, std::sqrt(rr));
+        if (n == 0 && structurally_deficient(h)) {                    // :132-143
+            code = -4; cudaMemsetAsync(h->d_p, 0xff, sizeof(double) * nn, h->st); break;
+        }
+        int sing = 0;
+        if ((rc = solve_step(h, 0.0, true, h->d_p, &sing))) return rc;   // :166-174
+        if (o->singularTest && sing) { code = -2; break; }            // :176-184
+        double jp2 = 0, rjp = 0;
+        if ((rc = eval_jp(h, h->d_p, &jp2, &rjp))) return rc;         // :187
+        if (term_fun(o, jp2, rr)) break;                              // :191
+        n++;
+        // linesearch (:249-290)
+        const double f0 = 0.5 * rr, fp0 = rjp;
+        double alpha = 1.0; bool found = false; double rrT = rr;
+        while (alpha >= o->alphaMin) {
+            launch_axpy(alpha, h->d_p, h->d_x, h->d_t, nn, h->st);
+            if ((rc = eval_rr(h, h->d_t, &rrT))) return rc;
+            if (0.5 * rrT < f0 + o->mu * alpha * fp0) { found = true; break; }
+            alpha /= 2;
+        }
+        if (found) { std::swap(h->d_x, h->d_t); rr = rrT; h->params_valid = true; h->normal_valid = false; }
+        else { alpha = 0.0; h->params_valid = false; }
+        if (res->nDamping < cap + 1) res->damping[res->nDamping++] = alpha;
+        T.store_x(h, n);
+        if (alpha == 0.0) { code = -3; if (res->nRr < cap + 1) { res->rr[res->nRr] = res->rr[res->nRr - 1]; res->nRr++; } break; }   // :217-223
+        if (n > o->maxIter) { code = -1; if (res->nRr < cap + 1) res->rr[res->nRr++] = std::sqrt(rr); break; }   // :225-231
+    }
+    res->code = code; res->iters = n;
+    res->nTrace = std::min(n + 1, cap);
+    return 0;
+}
+
+__global__ void k_gradient(DevProblem P, const double* __restrict__ camG, double* __restrict__ g) {
+    // g = J'r : shared IO from the summed Gram, EO from the per-image Grams, OP from the records
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    auto gat = [](const double* G, int R, int C) {
+        if (R < C) { const int q = R; R = C; C = q; }
+        const int p = R >> 3, q = C >> 3, i = R & 7, j = C & 7;
+        return G[(p * (p + 1) / 2 + q) * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1)];
+    };
+    if (t < DBAT_NSLOT) { const int c = P.sh_col[t]; if (c >= 0) g[c] = gat(P.shG, t, DBAT_COL_R) + camG[c]; }
+    if (t < 6 * P.nImg) {
+        const int c = P.eo_col[t];
+        if (c >= 0) g[c] = gat(P.imgG + (size_t)(t / 6) * DBAT_GSZ, DBAT_COL_EO + t % 6, DBAT_COL_R) + camG[c];
+    }
+    if (t < 3 * P.nOP) { const int c = P.op_col[t]; if (c >= 0) g[c] = P.pt[(size_t)(t / 3) * DBAT_PT_STRIDE + 6 + t % 3]; }
+}
+
+static int solve_lmp(dbat_handle* h, const dbat_opts* o, dbat_result* res, TraceOut& T) {
+    // levenberg_marquardt_powell.m:60-335
+    DevProblem& P = h->P;
+    const int nn = P.n;
+    int n = 0, code = 0, rc;
+    const int cap = o->maxIter + 2;
+    res->nDamping = 0; res->nRr = 0; res->nRhos = 0;
+    double delta = o->delta0;
+    if (!(delta > 0)) { double xx = 0; if ((rc = dev_dot(h, h->d_x, h->d_x, nn, &xx))) return rc; delta = std::sqrt(xx); }   // bundle.m:325
+    if ((rc = eval_full(h))) return rc;                               // :95-99
+    double rr = h->h_scal[SC_RR], f = 0.5 * rr;
+    int ntr = 0;
+    while (true) {
+        if (res->nRr < cap + 1) res->rr[res->nRr++] = std::sqrt(rr);  // :109
+        if (n == 0 && structurally_deficient(h)) { code = -4; break; }   // :113-122
+        // dogleg (:232-335)
+        int sing = 0, step = 0;
+        if ((rc = solve_step(h, 0.0, true, h->d_pgn, &sing))) return rc;
+        double pgn2 = 0; if ((rc = dev_dot(h, h->d_pgn, h->d_pgn, nn, &pgn2))) return rc;
+        const double npGN = std::sqrt(pgn2);
+        double jp2 = 0, rjp = 0;
+        if (npGN <= delta) {                                          // :281-286
+            cudaMemcpyAsync(h->d_p, h->d_pgn, sizeof(double) * nn, cudaMemcpyDeviceToDevice, h->st);
+            step = 0;
+        } else {
+            int nt = std::max(std::max(3 * P.nOP, 6 * P.nImg), DBAT_NSLOT);
+            k_gradient<<<(nt + 255) / 256, 256, 0, h->st>>>(P, h->d_camG, h->d_g); count_launch();
+            double gg = 0, jg2 = 0, dummy = 0;
+            if ((rc = dev_dot(h, h->d_g, h->d_g, nn, &gg))) return rc;
+            if ((rc = eval_jp(h, h->d_g, &jg2, &dummy))) return rc;
+            const double lambdaStar = gg / jg2;                       // :309  (g'Hg = |J g|^2)
+            const double nCP = lambdaStar * std::sqrt(gg);
+            if (nCP > delta) {                                        // :313-318
+                cudaMemsetAsync(h->d_p, 0, sizeof(double) * nn, h->st);
+                launch_axpy(-delta / std::sqrt(gg), h->d_g, h->d_p, h->d_p, nn, h->st);
+                step = 2;
+            } else {                                                  // :324-332
+                double gp = 0; if ((rc = dev_dot(h, h->d_g, h->d_pgn, nn, &gp))) return rc;
+                // CP = -ls*g ;  A=|CP-pGN|^2, B=2 CP.(pGN-CP), C=|CP|^2-delta^2
+                const double cp2 = lambdaStar * lambdaStar * gg, cpp = -lambdaStar * gp;
+                const double A = cp2 - 2 * cpp + pgn2, B = 2 * (cpp - cp2), C = cp2 - delta * delta;
+                const double k = (-B + std::sqrt(B * B - 4 * A * C)) / (2 * A);
+                // p = CP + k (pGN - CP) = (1-k)(-ls) g + k pGN
+                cudaMemsetAsync(h->d_p, 0, sizeof(double) * nn, h->st);
+                launch_axpy(k, h->d_pgn, h->d_p, h->d_p, nn, h->st);
+                launch_axpy(-(1 - k) * lambdaStar, h->d_g, h->d_p, h->d_p, nn, h->st);
+                step = 1;
+            }
+        }
+        if (res->nDamping < cap + 1) res->damping[res->nDamping++] = delta;   // :128
+        if (res->steps && n < cap) res->steps[n] = step;
+        if ((rc = eval_jp(h, h->d_p, &jp2, &rjp))) return rc;         // :131-132
+        if (step == 0 && term_fun(o, jp2, rr)) break;                 // :134
+        launch_axpy(1.0, h->d_p, h->d_x, h->d_t, nn, h->st);          // :143
+        double rrT = 0;
+        if ((rc = eval_rr(h, h->d_t, &rrT))) return rc;
+        const double ft = 0.5 * rrT;
+        const double predicted = -rjp - 0.5 * jp2;                    // :153
+        const double actual = f - ft;
+        const double rho = actual / predicted;
+        if (res->rhos && res->nRhos < cap) res->rhos[res->nRhos] = rho;
+        res->nRhos++;
+        if (o->doTrace) printf("Levenberg-Marquardt-Powell: iteration %d, residual norm=%.2g, delta=%.2g, step=%d, rho=%.1f\n", n, std::sqrt(rr), delta, step, rho);
+        if (rho <= o->mu || !(rho == rho)) {                          // :166-179
+            delta = delta / 2;
+            if (delta > npGN) delta = delta / std::exp2(std::ceil(std::log2(delta / npGN)));
+        } else {                                                      // :180-195
+            std::swap(h->d_x, h->d_t);
+            if ((rc = eval_full(h))) return rc;
+            rr = h->h_scal[SC_RR]; f = 0.5 * rr;
+            if (rho >= o->eta) delta = delta * 2;
+        }
+        T.store_x(h, n);                                              // :197-204 T(:,n+1)=x
+        ntr = n + 1;
+        n++;
+        if (n > o->maxIter) { code = -1; break; }
+    }
+    res->code = code; res->iters = n;
+    res->nTrace = std::min(ntr, n);                                   // :226 T=T(:,1:n)
+    if (res->nRhos > cap) res->nRhos = cap;
+    return 0;
+}
+
+extern "C" int dbat_solve(dbat_handle* h, int method, const dbat_opts* opts, const double* x0, dbat_result* res) {
+    if (!h || !opts || !x0 || !res || !res->x || !res->rr || !res->damping) return DBAT_E_BADARG;
+    if (method == DBAT_METHOD_GM) { h->err = "gauss_markov is broken via bundle() in the reference (bundle.m:273); not provided"; return DBAT_E_UNSUPPORTED; }
+    const int nn = h->P.n;
+    CK(cudaMemcpyAsync(h->d_x, x0, sizeof(double) * nn, cudaMemcpyHostToDevice, h->st));
+    CK(cudaMemsetAsync(h->d_p, 0, sizeof(double) * nn, h->st));
+    h->cscWeighted = -1; h->params_valid = false; h->normal_valid = false;
+    ph_reset(h);
+    const int64_t l0 = g_dbat_launches;
+    res->nTrace = 0; res->code = 0; res->iters = 0; res->nRhos = 0;
+    TraceOut T{res, nn, opts->maxIter + 2};
+    auto t0 = std::chrono::steady_clock::now();
+    int rc;
+    switch (method) {
+        case DBAT_METHOD_LM: rc = solve_lm(h, opts, res, T); break;
+        case DBAT_METHOD_GNA: rc = solve_gna(h, opts, res, T); break;
+        case DBAT_METHOD_LMP: rc = solve_lmp(h, opts, res, T); break;
+        default: h->err = "unknown method"; return DBAT_E_BADARG;
+    }
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(h->st));
+    res->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    res->launches = g_dbat_launches - l0;
+    // final outputs
+    CK(cudaMemcpyAsync(res->x, h->d_x, sizeof(double) * nn, cudaMemcpyDeviceToHost, h->st));
+    if (res->p) CK(cudaMemcpyAsync(res->p, h->d_p, sizeof(double) * nn, cudaMemcpyDeviceToHost, h->st));
+    if (res->r_w || res->r_u) {
+        set_params(h, h->d_x); h->params_valid = true;
+        if (res->r_w) {
+            launch_resid(h->P, h->d_x, h->d_partial, h->d_scal, SC_PRR, h->d_r, 1, h->st);
+            CK(cudaMemcpyAsync(res->r_w, h->d_r, sizeof(double) * h->m, cudaMemcpyDeviceToHost, h->st));
+            CK(cudaStreamSynchronize(h->st));
+        }
+        if (res->r_u) {
+            launch_resid(h->P, h->d_x, h->d_partial, h->d_scal, SC_PRR, h->d_r, 0, h->st);
+            CK(cudaMemcpyAsync(res->r_u, h->d_r, sizeof(double) * h->m, cudaMemcpyDeviceToHost, h->st));
+        }
+    }
+    ph_collect(h);
+    CK(cudaStreamSynchronize(h->st));
+    return DBAT_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// posterior covariance (bundle_cov.m): everything from the undamped reduced system
+//   C_cam = inv(S) ;  COP_j = V_j^-1 + V_j^-1 W~_j' C_cam W~_j V_j^-1   
+// --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_cop(DevProblem P, const double* __restrict__ C, int ldc,
+                                              const double* __restrict__ dsc, double s02, double* __restrict__ out);
+
+extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
+    if (!h || !out) return DBAT_E_BADARG;
+    if (h->nranks > 1) { h->err = "dbat_cov is single-rank only"; return DBAT_E_UNSUPPORTED; }
+    DevProblem& P = h->P;
+    int rc;
+    if (!h->normal_valid) { if ((rc = eval_full(h))) return rc; }
+    // undamped, Jacobi-scaled reduced system -> factor -> explicit inverse
+    launch_build_S(P, h->d_camDiag, h->d_camG, 0.0, h->st);
+    launch_schur(P, 0.0, h->st);
+    launch_diag(P, h->d_camDiag, h->d_diagN, h->st);
+    launch_inv_sqrt(h->d_diagN, h->d_dscale, P.nC, h->st);
+    launch_scale_S(P, h->d_dscale, h->st);
+    chol_factor(h->chol, P.S, h->st);
+    double *Z = nullptr, *C = nullptr;
+    const size_t sz = sizeof(double) * (size_t)P.ldS * P.ldS;
+    if (cudaMalloc(&Z, sz) != cudaSuccess || cudaMalloc(&C, sz) != cudaSuccess) {
+        if (Z) cudaFree(Z);
+        h->err = "out of memory for the covariance workspace"; return DBAT_E_OOM;
+    }
+    chol_inverse(h->chol, P.S, Z, C, h->st);
+    int info = 0;
+    cudaMemcpyAsync(&info, h->chol.info, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+    cudaError_t e = cudaStreamSynchronize(h->st);
+    if (e != cudaSuccess) { cudaFree(Z); cudaFree(C); h->err = std::string("dbat_cov: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
+    const double s02 = s0 * s0;
+    const int nC = P.nC, ld = P.ldS;
+    if (which == DBAT_COV_COP) {
+        double* dOut = nullptr;
+        cudaMalloc(&dOut, sizeof(double) * 9 * (size_t)std::max(1, P.nOP));
+        cudaMemsetAsync(dOut, 0, sizeof(double) * 9 * (size_t)std::max(1, P.nOP), h->st);
+        if (P.nOP > 0) { k_cop<<<(P.nOP + 3) / 4, 128, 0, h->st>>>(P, C, ld, h->d_dscale, s02, dOut); count_launch(); }
+        cudaMemcpyAsync(out, dOut, sizeof(double) * 9 * (size_t)P.nOP, cudaMemcpyDeviceToHost, h->st);
+        e = cudaStreamSynchronize(h->st);
+        cudaFree(dOut);
+    } else {
+        // bring the camera covariance to the host and unscale: C = D Cs D
+        std::vector<double> hc((size_t)ld * ld), dsc(std::max(1, nC));
+        cudaMemcpy(hc.data(), C, sz, cudaMemcpyDeviceToHost);
+        cudaMemcpy(dsc.data(), h->d_dscale, sizeof(double) * nC, cudaMemcpyDeviceToHost);
+        auto cv = [&](int a, int b) { return (info != 0) ? NAN : s02 * hc[(size_t)b * ld + a] * dsc[a] * dsc[b]; };
+        if (which == DBAT_COV_CXX_CAM) {
+            for (int b = 0; b < nC; ++b) for (int a = 0; a < nC; ++a) out[(size_t)b * nC + a] = cv(a, b);
+        } else if (which == DBAT_COV_CEO || which == DBAT_COV_CIO) {
+            const int R = which == DBAT_COV_CEO ? 6 : h->NC;
+            const std::vector<int>& col = which == DBAT_COV_CEO ? h->h_eo_col : h->h_io_col;
+            for (int i = 0; i < P.nImg; ++i)
+                for (int b = 0; b < R; ++b)
+                    for (int a = 0; a < R; ++a) {
+                        const int ca = col[(size_t)i * R + a], cb = col[(size_t)i * R + b];
+                        out[((size_t)i * R + b) * R + a] = (ca >= 0 && cb >= 0) ? cv(ca, cb) : 0.0;
+                    }
+        } else { cudaFree(Z); cudaFree(C); h->err = "unknown covariance selector"; return DBAT_E_BADARG; }
+    }
+    cudaFree(Z); cudaFree(C);
+    if (e != cudaSuccess) { h->err = std::string("dbat_cov: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
+    return info != 0 ? DBAT_E_NOTSPD : DBAT_OK;
+}
+
+// COP: one warp per point.  Row set of W~_j: shared IO slots (NSLOT) then 6 per observation.
+// u_a = sum_b Cs[col_a,col_b] d_a d_b T_b ,  COP = Vi + sum_a T_a' u_a   with T_a = W_a Vi (1x3)
+__global__ void __launch_bounds__(128) k_cop(DevProblem P, const double* __restrict__ C, int ldc,
+                                              const double* __restrict__ dsc, double s02, double* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (j >= P.nOP) return;
+    const int* opc = P.op_col + 3 * (size_t)j;
+    if (opc[0] < 0 && opc[1] < 0 && opc[2] < 0) return;
+    const double* rec = P.pt + (size_t)j * DBAT_PT_STRIDE;
+    // Vi (undamped) — same arithmetic as point_inverse in schur.cu
+    double a00 = rec[0], a01 = rec[1], a02 = rec[2], a11 = rec[3], a12 = rec[4], a22 = rec[5];
+    const bool f0 = opc[0] >= 0, f1 = opc[1] >= 0, f2 = opc[2] >= 0;
+    if (!f0) a00 = 1.0; if (!f1) a11 = 1.0; if (!f2) a22 = 1.0;
+    const double l00 = sqrt(a00), l10 = a01 / l00, l20 = a02 / l00;
+    const double l11 = sqrt(a11 - l10 * l10), l21 = (a12 - l20 * l10) / l11;
+    const double l22 = sqrt(a22 - l20 * l20 - l21 * l21);
+    const double m00 = 1.0 / l00, m11 = 1.0 / l11, m22 = 1.0 / l22;
+    const double m10 = -l10 * m00 * m11, m21 = -l21 * m11 * m22, m20 = -(l20 * m00 + l21 * m10) * m22;
+    double Vi[6] = {m00 * m00 + m10 * m10 + m20 * m20, m10 * m11 + m20 * m21, m20 * m22,
+                    m11 * m11 + m21 * m21, m21 * m22, m22 * m22};
+    if (!f0) { Vi[0] = 0; Vi[1] = 0; Vi[2] = 0; }
+    if (!f1) { Vi[1] = 0; Vi[3] = 0; Vi[4] = 0; }
+    if (!f2) { Vi[2] = 0; Vi[4] = 0; Vi[5] = 0; }
+    const int o0 = P.pt_start[j], k = P.pt_start[j + 1] - o0;
+    const int nRows = DBAT_NSLOT + 6 * k;
+    auto row_col = [&](int a) -> int {
+        if (a < DBAT_NSLOT) return P.sh_col[a];
+        const int o = (a - DBAT_NSLOT) / 6, e = (a - DBAT_NSLOT) % 6;
+        return P.eo_col[6 * (size_t)P.img_pm[o0 + o] + e];
+    };
+    auto row_T = [&](int a, double T[3]) {
+        const double* w = (a < DBAT_NSLOT) ? rec + DBAT_PT_WSH + 3 * a
+                                           : P.W + (size_t)(o0 + (a - DBAT_NSLOT) / 6) * DBAT_W_STRIDE + 3 * ((a - DBAT_NSLOT) % 6);
+        T[0] = Vi[0] * w[0] + Vi[1] * w[1] + Vi[2] * w[2];
+        T[1] = Vi[1] * w[0] + Vi[3] * w[1] + Vi[4] * w[2];
+        T[2] = Vi[2] * w[0] + Vi[4] * w[1] + Vi[5] * w[2];
+    };
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    for (int a = lane; a < nRows; a += 32) {
+        const int ca = row_col(a);
+        if (ca < 0) continue;
+        double Ta[3]; row_T(a, Ta);
+        double u[3] = {0, 0, 0};
+        for (int b = 0; b < nRows; ++b) {
+            const int cb = row_col(b);
+            if (cb < 0) continue;
+            double Tb[3]; row_T(b, Tb);
+            const double c = C[(size_t)cb * ldc + ca] * dsc[ca] * dsc[cb];
+            u[0] += c * Tb[0]; u[1] += c * Tb[1]; u[2] += c * Tb[2];
+        }
+        acc[0] += Ta[0] * u[0]; acc[1] += Ta[0] * u[1]; acc[2] += Ta[0] * u[2];
+        acc[3] += Ta[1] * u[1]; acc[4] += Ta[1] * u[2]; acc[5] += Ta[2] * u[2];
+    }
+#pragma unroll
+    for (int q = 0; q < 6; ++q)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    if (lane == 0) {
+        double* o9 = out + 9 * (size_t)j;
+        const double c00 = s02 * (Vi[0] + acc[0]), c01 = s02 * (Vi[1] + acc[1]), c02 = s02 * (Vi[2] + acc[2]);
+        const double c11 = s02 * (Vi[3] + acc[3]), c12 = s02 * (Vi[4] + acc[4]), c22 = s02 * (Vi[5] + acc[5]);
+        o9[0] = c00; o9[1] = c01; o9[2] = c02; o9[3] = c01; o9[4] = c11; o9[5] = c12; o9[6] = c02; o9[7] = c12; o9[8] = c22;
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// multi-GPU plumbing
+// --------------------------------------------------------------------------------------------
+extern "C" int dbat_comm_unique_id(void* id128) {
+    if (!id128) return DBAT_E_BADARG;
+    if (!nccl_load()) { g_create_err = "libnccl.so.2 not found"; return DBAT_E_NCCL; }
+    nccl_uid id;
+    if (g_nccl.GetUniqueId(&id) != 0) return DBAT_E_NCCL;
+    memcpy(id128, &id, sizeof(id));
+    return DBAT_OK;
+}
+extern "C" int dbat_comm_init(dbat_handle* h, int nranks, int rank, const void* id128) {
+    if (!h || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return DBAT_E_BADARG;
+    if (nranks == 1) { h->nranks = 1; h->rank = 0; return DBAT_OK; }
+    if (!nccl_load()) { h->err = "libnccl.so.2 not found"; return DBAT_E_NCCL; }
+    nccl_uid id; memcpy(&id, id128, sizeof(id));
+    int rc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
+    if (rc != 0) { h->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); return DBAT_E_NCCL; }
+    h->nranks = nranks; h->rank = rank;
+    return DBAT_OK;
+}

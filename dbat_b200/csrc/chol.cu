@@ -1,0 +1,351 @@
+// chol.cu — dense FP64 blocked Cholesky of the reduced camera system on the FP64 tensor
+// pipe (DMMA mma.sync.m8n8k4.f64), triangular solves and the explicit inverse used by the
+// posterior covariances.  Replaces MATLAB's `\` / chol (CHOLMOD) call sites
+// code/bundle/lsa/levenberg_marquardt.m:119, gauss_newton_armijo.m:172,
+// code/bundle/bundle_cov.m:87.
+//
+// Right-looking, block size 128:  for k: L_kk = chol(A_kk) (+ inv(L_kk)) ;
+//   A_ik <- A_ik inv(L_kk)'  (GEMM) ;  A_ij -= L_ik L_jk'  for i>=j>k (GEMM, lower tiles only).
+// The two GEMM shapes share one 128x128x16 double-buffered cp.async kernel ("NT": both
+// operands column-major, C = beta*C + alpha*A*B').
+#include <cstdio>
+#include "launch.h"
+
+#define NB 128
+#define KS 16                 // k-slice per pipeline stage
+#define SLD 136               // smem row stride (doubles): 128 + 8 -> conflict-free fragment loads
+#define GEMM_STAGES 3
+#define GEMM_SMEM (GEMM_STAGES * 2 * KS * SLD * 8)
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
+
+// C(tile) = beta*C + alpha * A(rows of tile, 0:K) * B(rows of tile col, 0:K)'
+// tile list: if tri!=0 the 1-D grid enumerates lower-triangular tile pairs (ti>=tj) of an
+// nt x nt tile grid; otherwise blockIdx.x = ti, blockIdx.y = tj.
+__global__ void __launch_bounds__(256, 1)
+k_gemm_nt(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
+          double* __restrict__ C, int ldc, int K, double alpha, double beta, int tri) {
+    extern __shared__ __align__(16) double sm[];
+    int ti, tj;
+    if (tri) {
+        const int t = blockIdx.x;
+        ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        while (ti * (ti + 1) / 2 > t) --ti;
+        tj = t - ti * (ti + 1) / 2;
+    } else { ti = blockIdx.x; tj = blockIdx.y; }
+    const double* Ag = A + (size_t)ti * NB;
+    const double* Bg = B + (size_t)tj * NB;
+    double* Cg = C + (size_t)tj * NB * ldc + (size_t)ti * NB;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp & 3) * 32;      // warp tile origin (rows), 4 warps along M
+    const int wn = (warp >> 2) * 64;     // 2 warps along N
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    const int nk = K / KS;
+    auto load_stage = [&](int stage, int kt) {
+        double* As = sm + (size_t)stage * 2 * KS * SLD;
+        double* Bs = As + KS * SLD;
+        // 16 k-columns x 128 rows per operand = 1024 chunks of 16 B; 4 per thread per operand
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int chunk = tid + c * 256;
+            const int kk = chunk >> 6, m = (chunk & 63) * 2;
+            cp_async16(As + kk * SLD + m, Ag + (size_t)(kt * KS + kk) * lda + m);
+            cp_async16(Bs + kk * SLD + m, Bg + (size_t)(kt * KS + kk) * ldb + m);
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < GEMM_STAGES - 1; ++s) { if (s < nk) load_stage(s, s); cp_async_commit(); }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<GEMM_STAGES - 2>();
+        __syncthreads();
+        if (kt + GEMM_STAGES - 1 < nk) load_stage((kt + GEMM_STAGES - 1) % GEMM_STAGES, kt + GEMM_STAGES - 1);
+        cp_async_commit();
+        const double* As = sm + (size_t)(kt % GEMM_STAGES) * 2 * KS * SLD;
+        const double* Bs = As + KS * SLD;
+#pragma unroll
+        for (int k0 = 0; k0 < KS; k0 += 4) {
+            double af[4], bf[8];
+            const double* ap = As + (k0 + (lane & 3)) * SLD + wm + (lane >> 2);
+            const double* bp = Bs + (k0 + (lane & 3)) * SLD + wn + (lane >> 2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = ap[8 * i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bf[j] = bp[8 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+    // epilogue: C fragment (row = lane/4, cols 2*(lane%4)+{0,1}) per 8x8 tile
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int r = wm + 8 * i + (lane >> 2);
+            const int c = wn + 8 * j + 2 * (lane & 3);
+            double* p0 = Cg + (size_t)c * ldc + r;
+            double* p1 = p0 + ldc;
+            if (beta == 0.0) { *p0 = alpha * acc[i][j][0]; *p1 = alpha * acc[i][j][1]; }
+            else { *p0 = beta * *p0 + alpha * acc[i][j][0]; *p1 = beta * *p1 + alpha * acc[i][j][1]; }
+        }
+}
+
+static void gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc,
+                    int mt, int nt, int K, double alpha, double beta, bool tri, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM); attr = true; }
+    if (mt <= 0 || nt <= 0) return;
+    if (tri) k_gemm_nt<<<mt * (mt + 1) / 2, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, 1);
+    else     k_gemm_nt<<<dim3(mt, nt), 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, 0);
+    count_launch();
+}
+
+// Cholesky of one 128x128 diagonal block in shared memory + inverse of its factor.
+// One thread per row.  L lives in the lower triangle of As; inv(L)' is built in the strictly
+// upper triangle of the same buffer (its diagonal in dg[]), so one 132 KB tile suffices.
+#define PLD 129
+__global__ void __launch_bounds__(128, 1)
+k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, int* __restrict__ info,
+           double* __restrict__ minmax) {
+    extern __shared__ __align__(16) double sm[];
+    double* As = sm;                    // [128][PLD] row-major
+    double* dg = sm + NB * PLD;         // [128] diagonal of inv(L)
+    const int i = threadIdx.x;
+    for (int c = 0; c < NB; ++c) As[i * PLD + c] = (c <= i) ? A[(size_t)c * lda + i] : 0.0;
+    __syncthreads();
+    bool bad = false;
+    double dmin = 1e300, dmax = 0.0;
+    for (int j = 0; j < NB; ++j) {
+        const double d = As[j * PLD + j];
+        if (!(d > 0.0)) bad = true;
+        const double l = sqrt(d);
+        dmin = fmin(dmin, l); dmax = fmax(dmax, l);
+        double lij = 0.0;
+        if (i > j) { lij = As[i * PLD + j] / l; As[i * PLD + j] = lij; }
+        __syncthreads();
+        if (i == j) As[j * PLD + j] = l;
+        if (i > j) {
+            double* row = As + i * PLD;
+#pragma unroll 4
+            for (int c = j + 1; c <= i; ++c) row[c] -= lij * As[c * PLD + j];
+        }
+        __syncthreads();
+    }
+    if (i == 0) {
+        if (bad) atomicCAS(info, 0, blk + 1);
+        double omin = minmax[0], omax = minmax[1];
+        if (blk == 0) { omin = dmin; omax = dmax; }
+        minmax[0] = fmin(omin, dmin); minmax[1] = fmax(omax, dmax);
+    }
+    // write L back (lower triangle)
+    for (int c = 0; c <= i; ++c) A[(size_t)c * lda + i] = As[i * PLD + c];
+    // X = inv(L): thread c owns column c of X, stored transposed in row c (upper part) of As
+    {
+        const int c = i;
+        double xdiag = 0.0;
+        for (int r = c; r < NB; ++r) {
+            double s = (r == c) ? 1.0 : 0.0;
+            const double* Lr = As + r * PLD;
+            for (int k = c; k < r; ++k) s -= Lr[k] * (k == c ? xdiag : As[c * PLD + k]);
+            const double v = s / Lr[r];
+            if (r == c) xdiag = v; else As[c * PLD + r] = v;
+        }
+        dg[c] = xdiag;
+    }
+    __syncthreads();
+    double* out = invL + (size_t)blk * NB * NB;          // column-major 128x128, lower triangular
+    for (int cc = 0; cc < NB; ++cc)
+        out[(size_t)cc * NB + i] = (i > cc) ? As[cc * PLD + i] : (i == cc ? dg[cc] : 0.0);
+}
+
+void chol_alloc(CholWork& w, int n, int ld) {
+    w.n = n; w.ld = ld; w.nb = ld / NB;
+    cudaMalloc(&w.invL, sizeof(double) * (size_t)w.nb * NB * NB);
+    cudaMalloc(&w.info, sizeof(int));
+    cudaMalloc(&w.minmax, sizeof(double) * 2);
+}
+void chol_free(CholWork& w) {
+    if (w.invL) cudaFree(w.invL);
+    if (w.info) cudaFree(w.info);
+    if (w.minmax) cudaFree(w.minmax);
+    w = CholWork();
+}
+
+void chol_factor(CholWork& w, double* A, cudaStream_t st) {
+    static bool attr = false;
+    const int psmem = (NB * PLD + NB) * 8;
+    if (!attr) { cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem); attr = true; }
+    cudaMemsetAsync(w.info, 0, sizeof(int), st);
+    const int ld = w.ld, nb = w.nb;
+    for (int k = 0; k < nb; ++k) {
+        double* Akk = A + (size_t)k * NB * ld + (size_t)k * NB;
+        k_potrf128<<<1, 128, psmem, st>>>(Akk, ld, w.invL, k, w.info, w.minmax);
+        count_launch();
+        const int rem = nb - k - 1;
+        if (rem <= 0) break;
+        double* Apanel = Akk + NB;                         // rows below the diagonal block
+        // L_ik = A_ik * inv(L_kk)'   (in place: each CTA reads its whole 128x128 tile first)
+        gemm_nt(Apanel, ld, w.invL + (size_t)k * NB * NB, NB, Apanel, ld, rem, 1, NB, 1.0, 0.0, false, st);
+        // A_ij -= L_ik L_jk'  (lower tiles of the trailing matrix)
+        double* Atrail = A + (size_t)(k + 1) * NB * ld + (size_t)(k + 1) * NB;
+        gemm_nt(Apanel, ld, Apanel, ld, Atrail, ld, rem, rem, NB, -1.0, 1.0, true, st);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// triangular solves with the blocked factor (uses the stored inverses of the diagonal blocks)
+// ---------------------------------------------------------------------------------------------
+// forward step k: CTA r handles row block k+r.  y_k = invL_kk * b_k ; r==0 stores y_k, else
+// b_i -= L_ik y_k.
+__global__ void __launch_bounds__(128) k_fwd_step(const double* __restrict__ A, int ld,
+                                                   const double* __restrict__ invL, int k,
+                                                   double* __restrict__ b, double* __restrict__ y) {
+    __shared__ double bk[NB], yk[NB];
+    const int t = threadIdx.x;
+    bk[t] = b[(size_t)k * NB + t];
+    __syncthreads();
+    const double* iL = invL + (size_t)k * NB * NB;
+    double s = 0.0;
+    for (int c = 0; c <= t; ++c) s += iL[(size_t)c * NB + t] * bk[c];      // lower triangular
+    // (loop bound differs per thread; reads stay coalesced across t for each c)
+    yk[t] = s;
+    __syncthreads();
+    const int i = k + blockIdx.x;
+    if (blockIdx.x == 0) { y[(size_t)k * NB + t] = s; return; }
+    const double* Lik = A + (size_t)k * NB * ld + (size_t)i * NB;
+    double u = 0.0;
+#pragma unroll 8
+    for (int c = 0; c < NB; ++c) u += Lik[(size_t)c * ld + t] * yk[c];
+    b[(size_t)i * NB + t] -= u;
+}
+// backward step k: x_k = invL_kk' * y_k ; CTA j<k: y_j -= L_kj' x_k ; CTA j==k stores x_k.
+__global__ void __launch_bounds__(256) k_bwd_step(const double* __restrict__ A, int ld,
+                                                   const double* __restrict__ invL, int k,
+                                                   double* __restrict__ y, double* __restrict__ x) {
+    __shared__ double yk[NB], xk[NB];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (t < NB) yk[t] = y[(size_t)k * NB + t];
+    __syncthreads();
+    const double* iL = invL + (size_t)k * NB * NB;
+    for (int c = warp; c < NB; c += 8) {                  // x_k[c] = sum_t invL[t][c] y_k[t], t>=c
+        double s = 0.0;
+        for (int r = lane; r < NB; r += 32) s += iL[(size_t)c * NB + r] * yk[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) xk[c] = s;
+    }
+    __syncthreads();
+    const int j = blockIdx.x;                             // 0..k
+    if (j == k) { if (t < NB) x[(size_t)k * NB + t] = xk[t]; return; }
+    const double* Lkj = A + (size_t)j * NB * ld + (size_t)k * NB;
+    for (int c = warp; c < NB; c += 8) {
+        double s = 0.0;
+        for (int r = lane; r < NB; r += 32) s += Lkj[(size_t)c * ld + r] * xk[r];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) y[(size_t)j * NB + c] -= s;
+    }
+}
+
+static double* g_solve_tmp = nullptr;
+static int g_solve_tmp_n = 0;
+void chol_solve(const CholWork& w, const double* A, double* b, cudaStream_t st) {
+    if (g_solve_tmp_n < w.ld) {
+        if (g_solve_tmp) cudaFree(g_solve_tmp);
+        cudaMalloc(&g_solve_tmp, sizeof(double) * w.ld);
+        g_solve_tmp_n = w.ld;
+    }
+    double* y = g_solve_tmp;
+    for (int k = 0; k < w.nb; ++k) { k_fwd_step<<<w.nb - k, 128, 0, st>>>(A, w.ld, w.invL, k, b, y); count_launch(); }
+    for (int k = w.nb - 1; k >= 0; --k) { k_bwd_step<<<k + 1, 256, 0, st>>>(A, w.ld, w.invL, k, y, b); count_launch(); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// explicit inverse: Z = inv(L) by block forward substitution (GEMMs), then C = Z'Z = inv(A)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_copy_block(const double* __restrict__ src, int lds, double* __restrict__ dst, int ldd) {
+    const int c = blockIdx.x, r = threadIdx.x;
+    dst[(size_t)c * ldd + r] = src[(size_t)c * lds + r];
+}
+__global__ void k_mirror_lower(double* __restrict__ C, int ld) {
+    const int c = blockIdx.y * 32 + threadIdx.y, r = blockIdx.x * 32 + threadIdx.x;
+    if (r > c) C[(size_t)r * ld + c] = C[(size_t)c * ld + r];   // upper(c,r) := lower(r,c)
+}
+// Zt(by.., bx..) = Z(bx.., by..)'  on 32x32 tiles of a 128x128 block
+__global__ void k_transpose(const double* __restrict__ Z, double* __restrict__ Zt, int ld) {
+    __shared__ double tile[32][33];
+    const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+    tile[threadIdx.y][threadIdx.x] = Z[(size_t)(by + threadIdx.y) * ld + bx + threadIdx.x];
+    __syncthreads();
+    Zt[(size_t)(bx + threadIdx.y) * ld + by + threadIdx.x] = tile[threadIdx.x][threadIdx.y];
+}
+// out(:,c) = -M * T(:,c) for a 128x128 lower-triangular M (column-major); also writes the
+// transposed result outT(c, r) = out(r, c).  One CTA per 32 columns; in place (out == T) is fine.
+__global__ void __launch_bounds__(128) k_left_mul_neg(const double* __restrict__ M, const double* T,
+                                                       int ldt, double* out, int ldo,
+                                                       double* __restrict__ outT, int ldoT) {
+    __shared__ double Ts[NB][33];
+    const int c0 = blockIdx.x * 32, t = threadIdx.x;
+    for (int c = 0; c < 32; ++c) Ts[t][c] = T[(size_t)(c0 + c) * ldt + t];
+    __syncthreads();
+    double acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = 0.0;
+    for (int k = 0; k <= t; ++k) {
+        const double m = M[(size_t)k * NB + t];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) acc[c] += m * Ts[k][c];
+    }
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+        out[(size_t)(c0 + c) * ldo + t] = -acc[c];
+        outT[(size_t)t * ldoT + c0 + c] = -acc[c];
+    }
+}
+
+// Z and C are ld x ld scratch/output buffers.  On return C holds the full symmetric inv(A);
+// Z holds inv(L)' (upper triangular).
+void chol_inverse(const CholWork& w, const double* A, double* Z, double* C, cudaStream_t st) {
+    const int ld = w.ld, nb = w.nb;
+    double* Zt = C;                                       // C doubles as storage for Z' until the end
+    cudaMemsetAsync(Z, 0, sizeof(double) * (size_t)ld * ld, st);
+    cudaMemsetAsync(Zt, 0, sizeof(double) * (size_t)ld * ld, st);
+    const dim3 tb(32, 32), tg(NB / 32, NB / 32);
+    for (int i = 0; i < nb; ++i) {
+        double* Zii = Z + (size_t)i * NB * ld + (size_t)i * NB;
+        k_copy_block<<<NB, NB, 0, st>>>(w.invL + (size_t)i * NB * NB, NB, Zii, ld);
+        k_transpose<<<tg, tb, 0, st>>>(Zii, Zt + (size_t)i * NB * ld + (size_t)i * NB, ld);
+        count_launch(2);
+        if (i == 0) continue;
+        // T = L(i,0:i) * Z(0:i,0:i)  (NT with B = Z'),  written into Z(i,0:i)
+        double* T = Z + (size_t)i * NB;
+        gemm_nt(A + (size_t)i * NB, ld, Zt, ld, T, ld, 1, i, NB * i, 1.0, 0.0, false, st);
+        // Z(i,0:i) = -inv(L_ii) * T   (+ transposed copy into Zt(0:i, i))
+        k_left_mul_neg<<<(NB * i) / 32, 128, 0, st>>>(w.invL + (size_t)i * NB * NB, T, ld, T, ld,
+                                                       Zt + (size_t)i * NB * ld, ld);
+        count_launch();
+    }
+    // C = Z'Z = Zt * Zt'.  C aliases Zt, so move Zt into Z first.
+    cudaMemcpyAsync(Z, Zt, sizeof(double) * (size_t)ld * ld, cudaMemcpyDeviceToDevice, st);
+    gemm_nt(Z, ld, Z, ld, C, ld, nb, nb, ld, 1.0, 0.0, true, st);
+    k_mirror_lower<<<dim3(ld / 32, ld / 32), dim3(32, 32), 0, st>>>(C, ld);
+    count_launch();
+}

@@ -1,0 +1,551 @@
+// eval.cu — residual / Jacobian / normal-equation assembly kernels (sm_100a).
+//
+// Replaces the reference's sparse-Jacobian build and J'*J product
+// (code/bundle/cameramodel/multi_res.m:56-315, code/bundle/lsa/levenberg_marquardt.m:76-82)
+// with two recompute-instead-of-materialise passes over the observations:
+//   k_cam_side   (camera-major order): Gram matrix of the weighted rows [A_io | A_eo | r] per
+//                image chunk on the FP64 tensor pipe (DMMA m8n8k4) -> N_io,io, N_io,eo, U_i,
+//                g_io, g_eo and r'r in one shot; fixed chunk->image->total summation order,
+//                so the result is bit-reproducible.
+//   k_point_side (point-major order, one thread per object point): V_j, g_j, the IO x OP
+//                cross block and the per-observation EO x OP cross blocks W_o.
+// Both are HBM-bound streams (48-52 B read per observation).
+#include "kernels.cuh"
+#include "launch.h"
+
+// ---------------------------------------------------------------------------------------------
+// small utilities
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Deterministic block sum (blockDim.x multiple of 32, <= 1024); result valid in thread 0.
+__device__ __forceinline__ double block_sum(double v, double* sm /* >= 32 doubles */) {
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) sm[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+        t = (l < (int)(blockDim.x >> 5)) ? sm[l] : 0.0;
+        t = warp_sum(t);
+    }
+    return t;
+}
+
+__global__ void k_scatter(const double* __restrict__ x, const int* __restrict__ src,
+                          const int* __restrict__ dest, double* __restrict__ arr, int cnt) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < cnt) arr[dest[k]] = x[src[k]];
+}
+
+// deserialize.m:28-30 on device: scatter x into the IO/EO/OP value arrays.
+void launch_deserialize(const double* x, const int* src, const int* dest, double* arr, int cnt,
+                        cudaStream_t st) {
+    if (cnt <= 0) return;
+    k_scatter<<<(cnt + 255) / 256, 256, 0, st>>>(x, src, dest, arr, cnt);
+    count_launch();
+}
+
+__global__ void k_image_setup(DevProblem P) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nImg) return;
+    const double* e = P.EOval + 6 * (size_t)i;
+    ImgRec& g = P.img[i];
+    g.q0[0] = e[0]; g.q0[1] = e[1]; g.q0[2] = e[2];
+    sincos(e[3], &g.sw, &g.cw);
+    sincos(e[4], &g.sp, &g.cp);
+    sincos(e[5], &g.sk, &g.ck);
+}
+
+// IO records in slot layout from the IOval columns of the representative images.
+__global__ void k_io_setup(DevProblem P, const int* __restrict__ rep, int nIO) {
+    int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= nIO) return;
+    const int NC = 5 + P.nK + P.nP;
+    const double* c = P.IOval + (size_t)NC * rep[u];
+    IORec& r = P.io[u];
+    for (int s = 0; s < DBAT_NSLOT; ++s) r.v[s] = 0.0;
+    for (int s = 0; s < 5; ++s) r.v[s] = c[s];
+    for (int k = 0; k < P.nK; ++k) r.v[DBAT_SLOT_K + k] = c[5 + k];
+    for (int k = 0; k < P.nP; ++k) r.v[DBAT_SLOT_P + k] = c[5 + P.nK + k];
+}
+
+void launch_param_setup(const DevProblem& P, const int* rep, int nIO, cudaStream_t st) {
+    k_image_setup<<<(P.nImg + 127) / 128, 128, 0, st>>>(P);
+    k_io_setup<<<(nIO + 127) / 128, 128, 0, st>>>(P, rep, nIO);
+    count_launch(2);
+}
+
+// ---------------------------------------------------------------------------------------------
+// camera side: Gram of weighted rows on the FP64 tensor pipe
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+#define XT_LD 68   // 64 rows + 4: fragment loads (8 cols x 4 rows) hit 32 distinct bank pairs
+
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_cam_side(DevProblem P) {
+    extern __shared__ __align__(16) double smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* Xt = smem + (size_t)warp * DBAT_GW * XT_LD;    // [GW][XT_LD] per warp
+    const Chunk ck = P.chunks[blockIdx.x];
+    const ImgRec g = P.img[ck.img];
+    const IORec io = P.io[g.io];
+
+    double acc[DBAT_GTP][2];
+#pragma unroll
+    for (int t = 0; t < DBAT_GTP; ++t) { acc[t][0] = 0.0; acc[t][1] = 0.0; }
+    // padding columns stay zero for the whole kernel
+    for (int c = DBAT_COL_R + 1; c < DBAT_GW; ++c) {
+        Xt[c * XT_LD + 2 * lane] = 0.0; Xt[c * XT_LD + 2 * lane + 1] = 0.0;
+    }
+
+    for (int base = warp * 32; base < ck.count; base += 128) {
+        const int k = base + lane;
+        ObsJac o;
+        double w0 = 0.0, w1 = 0.0;
+        const bool valid = k < ck.count;
+        if (valid) {
+            const int idx = ck.start + k;
+            const double2 uv = P.uv_cm[idx];
+            const double2 is = P.isig_cm[idx];
+            const int j = P.pt_cm[idx];
+            const double Q[3] = {P.OPval[3 * (size_t)j], P.OPval[3 * (size_t)j + 1],
+                                 P.OPval[3 * (size_t)j + 2]};
+            obs_model<MODEL, true, false>(Q, g, io, P.nK, P.nP, uv.x, uv.y, o);
+            w0 = is.x; w1 = is.y;
+        }
+        __syncwarp();
+        double2* col;
+#pragma unroll
+        for (int s = 0; s < DBAT_NSLOT; ++s) {
+            col = reinterpret_cast<double2*>(Xt + s * XT_LD) + lane;
+            *col = valid ? make_double2(o.dIO[s][0] * w0, o.dIO[s][1] * w1) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            col = reinterpret_cast<double2*>(Xt + (DBAT_COL_EO + c) * XT_LD) + lane;
+            *col = valid ? make_double2(o.dC[0][c] * w0, o.dC[1][c] * w1) : make_double2(0.0, 0.0);
+            col = reinterpret_cast<double2*>(Xt + (DBAT_COL_EO + 3 + c) * XT_LD) + lane;
+            *col = valid ? make_double2(o.dA[0][c] * w0, o.dA[1][c] * w1) : make_double2(0.0, 0.0);
+        }
+        col = reinterpret_cast<double2*>(Xt + DBAT_COL_R * XT_LD) + lane;
+        *col = valid ? make_double2(o.r[0] * w0, o.r[1] * w1) : make_double2(0.0, 0.0);
+        __syncwarp();
+        // G(p,q) += X(:,p-tile)' X(:,q-tile): A and B fragments share one load pattern
+        const double* fr = Xt + (lane >> 2) * XT_LD + (lane & 3);
+#pragma unroll 4
+        for (int k0 = 0; k0 < 64; k0 += 4) {
+            double f[DBAT_GT];
+#pragma unroll
+            for (int t = 0; t < DBAT_GT; ++t) f[t] = fr[t * 8 * XT_LD + k0];
+            int tp = 0;
+#pragma unroll
+            for (int p = 0; p < DBAT_GT; ++p)
+#pragma unroll
+                for (int q = 0; q <= p; ++q) { dmma884(acc[tp][0], acc[tp][1], f[p], f[q]); ++tp; }
+        }
+    }
+    // cross-warp reduction in fixed order, then one partial Gram per chunk
+    __syncthreads();
+    double* red = smem;                                     // [4][GTP*2][32]
+#pragma unroll
+    for (int t = 0; t < DBAT_GTP; ++t) {
+        red[(warp * DBAT_GTP * 2 + 2 * t) * 32 + lane] = acc[t][0];
+        red[(warp * DBAT_GTP * 2 + 2 * t + 1) * 32 + lane] = acc[t][1];
+    }
+    __syncthreads();
+    double* out = P.chunkG + (size_t)blockIdx.x * DBAT_GSZ;
+    for (int e = threadIdx.x; e < DBAT_GSZ; e += 128) {
+        const int t = e >> 6, l = (e & 63) >> 1, h = e & 1;
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) s += red[(w * DBAT_GTP * 2 + 2 * t + h) * 32 + l];
+        out[e] = s;
+    }
+}
+
+// per-image Gram = sum of its chunk Grams in chunk order
+__global__ void k_cam_reduce(DevProblem P, const int* __restrict__ img_chunk_start) {
+    const int i = blockIdx.x;
+    const int c0 = img_chunk_start[i], c1 = img_chunk_start[i + 1];
+    for (int e = threadIdx.x; e < DBAT_GSZ; e += blockDim.x) {
+        double s = 0.0;
+        for (int c = c0; c < c1; ++c) s += P.chunkG[(size_t)c * DBAT_GSZ + e];
+        P.imgG[(size_t)i * DBAT_GSZ + e] = s;
+    }
+}
+
+// sum over images, two fixed levels (64 groups, then 1)
+__global__ void k_sh_reduce1(DevProblem P, double* __restrict__ tmp) {
+    const int gsz = (P.nImg + gridDim.x - 1) / gridDim.x;
+    const int i0 = blockIdx.x * gsz, i1 = min(P.nImg, i0 + gsz);
+    for (int e = threadIdx.x; e < DBAT_GSZ; e += blockDim.x) {
+        double s = 0.0;
+        for (int i = i0; i < i1; ++i) s += P.imgG[(size_t)i * DBAT_GSZ + e];
+        tmp[(size_t)blockIdx.x * DBAT_GSZ + e] = s;
+    }
+}
+__global__ void k_sh_reduce2(DevProblem P, const double* __restrict__ tmp, int ngroups) {
+    for (int e = threadIdx.x; e < DBAT_GSZ; e += blockDim.x) {
+        double s = 0.0;
+        for (int gI = 0; gI < ngroups; ++gI) s += tmp[(size_t)gI * DBAT_GSZ + e];
+        P.shG[e] = s;
+    }
+}
+
+template <int MODEL>
+static void launch_cam_side_t(const DevProblem& P, const int* img_chunk_start, double* tmp,
+                              cudaStream_t st) {
+    const size_t smem = (size_t)4 * DBAT_GW * XT_LD * sizeof(double);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(k_cam_side<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done = true;
+    }
+    if (P.nChunks > 0) k_cam_side<MODEL><<<P.nChunks, 128, smem, st>>>(P);
+    k_cam_reduce<<<P.nImg, 128, 0, st>>>(P, img_chunk_start);
+    k_sh_reduce1<<<64, 128, 0, st>>>(P, tmp);
+    k_sh_reduce2<<<1, 128, 0, st>>>(P, tmp, 64);
+    count_launch(4);
+}
+
+void launch_cam_side(const DevProblem& P, const int* img_chunk_start, double* tmp, cudaStream_t st) {
+    switch (P.model) {
+        case 0: launch_cam_side_t<0>(P, img_chunk_start, tmp, st); break;
+        case 1: launch_cam_side_t<1>(P, img_chunk_start, tmp, st); break;
+        case 2: launch_cam_side_t<2>(P, img_chunk_start, tmp, st); break;
+        default: launch_cam_side_t<3>(P, img_chunk_start, tmp, st); break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// point side: one thread per object point
+// ---------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_point_side(DevProblem P) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.nOP) return;
+    const double Q[3] = {P.OPval[3 * (size_t)j], P.OPval[3 * (size_t)j + 1], P.OPval[3 * (size_t)j + 2]};
+    double m[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) m[t] = P.op_col[3 * (size_t)j + t] >= 0 ? 1.0 : 0.0;
+    double V[6] = {0, 0, 0, 0, 0, 0}, gq[3] = {0, 0, 0};
+    double Wsh[DBAT_NSLOT][3];
+#pragma unroll
+    for (int s = 0; s < DBAT_NSLOT; ++s) { Wsh[s][0] = 0.0; Wsh[s][1] = 0.0; Wsh[s][2] = 0.0; }
+    const int o0 = P.pt_start[j], o1 = P.pt_start[j + 1];
+    for (int ob = o0; ob < o1; ++ob) {
+        const double2 uv = P.uv_pm[ob];
+        const double2 is = P.isig_pm[ob];
+        const ImgRec g = P.img[P.img_pm[ob]];
+        const IORec io = P.io[g.io];
+        ObsJac o;
+        obs_model<MODEL, true, true>(Q, g, io, P.nK, P.nP, uv.x, uv.y, o);
+        double A[2][3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) { A[0][t] = o.dOP[0][t] * is.x * m[t]; A[1][t] = o.dOP[1][t] * is.y * m[t]; }
+        const double r0 = o.r[0] * is.x, r1 = o.r[1] * is.y;
+        V[0] += A[0][0] * A[0][0] + A[1][0] * A[1][0];
+        V[1] += A[0][0] * A[0][1] + A[1][0] * A[1][1];
+        V[2] += A[0][0] * A[0][2] + A[1][0] * A[1][2];
+        V[3] += A[0][1] * A[0][1] + A[1][1] * A[1][1];
+        V[4] += A[0][1] * A[0][2] + A[1][1] * A[1][2];
+        V[5] += A[0][2] * A[0][2] + A[1][2] * A[1][2];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) gq[t] += A[0][t] * r0 + A[1][t] * r1;
+#pragma unroll
+        for (int s = 0; s < DBAT_NSLOT; ++s) {
+            const double a0 = o.dIO[s][0] * is.x, a1 = o.dIO[s][1] * is.y;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) Wsh[s][t] += a0 * A[0][t] + a1 * A[1][t];
+        }
+        double* Wo = P.W + (size_t)ob * DBAT_W_STRIDE;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double a0 = o.dC[0][c] * is.x, a1 = o.dC[1][c] * is.y;
+            const double b0 = o.dA[0][c] * is.x, b1 = o.dA[1][c] * is.y;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                Wo[c * 3 + t] = a0 * A[0][t] + a1 * A[1][t];
+                Wo[(3 + c) * 3 + t] = b0 * A[0][t] + b1 * A[1][t];
+            }
+        }
+    }
+    double* rec = P.pt + (size_t)j * DBAT_PT_STRIDE;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rec[k] = V[k];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) rec[6 + t] = gq[t];
+    rec[9] = 0.0;
+#pragma unroll
+    for (int s = 0; s < DBAT_NSLOT; ++s)
+#pragma unroll
+        for (int t = 0; t < 3; ++t) rec[DBAT_PT_WSH + 3 * s + t] = Wsh[s][t];
+}
+
+// prior observations (prior_obs.m:28-65): rows (x_k - prior)/sigma with unit Jacobian.
+// OP priors fold into the point records; camera-side priors go to camPriorDiag/G (length nC).
+__global__ void k_prior_apply(DevProblem P, const double* __restrict__ x,
+                              double* __restrict__ camDiag, double* __restrict__ camG,
+                              const int* __restrict__ col2pt /* n-nC: 3*pt+t */) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P.nPrior) return;
+    const int c = P.prior_col[k];
+    const double w = P.prior_isig[k];
+    const double r = (x[c] - P.prior_val[k]) * w;        // weighted residual
+    if (c < P.nC) {
+        camDiag[c] += w * w;                             // distinct columns: no race
+        camG[c] += w * r;
+    } else {
+        const int e = col2pt[c - P.nC];
+        const int j = e / 3, t = e % 3;
+        double* rec = P.pt + (size_t)j * DBAT_PT_STRIDE;
+        const int d = (t == 0) ? 0 : (t == 1 ? 3 : 5);
+        rec[d] += w * w;
+        rec[6 + t] += w * r;
+    }
+}
+
+template <int MODEL>
+static void launch_point_side_t(const DevProblem& P, cudaStream_t st) {
+    if (P.nOP > 0) k_point_side<MODEL><<<(P.nOP + 127) / 128, 128, 0, st>>>(P);
+    count_launch();
+}
+void launch_point_side(const DevProblem& P, cudaStream_t st) {
+    switch (P.model) {
+        case 0: launch_point_side_t<0>(P, st); break;
+        case 1: launch_point_side_t<1>(P, st); break;
+        case 2: launch_point_side_t<2>(P, st); break;
+        default: launch_point_side_t<3>(P, st); break;
+    }
+}
+void launch_prior_apply(const DevProblem& P, const double* x, double* camDiag, double* camG,
+                        const int* col2pt, cudaStream_t st) {
+    cudaMemsetAsync(camDiag, 0, sizeof(double) * P.nC, st);
+    cudaMemsetAsync(camG, 0, sizeof(double) * P.nC, st);
+    if (P.nPrior > 0) {
+        k_prior_apply<<<(P.nPrior + 127) / 128, 128, 0, st>>>(P, x, camDiag, camG, col2pt);
+        count_launch();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// residual only (trial points) and J*p statistics
+// ---------------------------------------------------------------------------------------------
+#define RES_BLOCK 256
+template <int MODEL, bool WRITE>
+__global__ void __launch_bounds__(RES_BLOCK) k_resid(DevProblem P, double* __restrict__ partial,
+                                                      double2* __restrict__ r_out, int weighted) {
+    __shared__ double sm[32];
+    double s = 0.0;
+    const int k = blockIdx.x * RES_BLOCK + threadIdx.x;
+    if (k < P.nObs) {
+        const double2 uv = P.uv_cm[k];
+        const double2 is = P.isig_cm[k];
+        const int j = P.pt_cm[k];
+        const ImgRec g = P.img[P.img_cm[k]];
+        const IORec io = P.io[g.io];
+        const double Q[3] = {P.OPval[3 * (size_t)j], P.OPval[3 * (size_t)j + 1], P.OPval[3 * (size_t)j + 2]};
+        ObsJac o;
+        obs_model<MODEL, false, false>(Q, g, io, P.nK, P.nP, uv.x, uv.y, o);
+        const double r0 = o.r[0] * is.x, r1 = o.r[1] * is.y;
+        s = r0 * r0 + r1 * r1;
+        if (WRITE) r_out[k] = weighted ? make_double2(r0, r1) : make_double2(o.r[0], o.r[1]);
+    }
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+
+// prior rows: residual (x - prior) [* 1/sigma]; sum of squares of the weighted rows
+__global__ void k_prior_resid(DevProblem P, const double* __restrict__ x, double* __restrict__ partial,
+                              double* __restrict__ r_out, int weighted) {
+    __shared__ double sm[32];
+    double s = 0.0;
+    for (int k = threadIdx.x; k < P.nPrior; k += blockDim.x) {
+        const double d = x[P.prior_col[k]] - P.prior_val[k];
+        const double r = d * P.prior_isig[k];
+        s += r * r;
+        if (r_out) r_out[k] = weighted ? r : d;
+    }
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) partial[0] = s;
+}
+
+// out[slot] = sum(partial[0..n)) in a fixed order (single block)
+__global__ void k_final_sum(const double* __restrict__ partial, int n, double* __restrict__ out, int slot,
+                            int accumulate) {
+    __shared__ double sm[32];
+    double s = 0.0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) s += partial[k];
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) out[slot] = accumulate ? out[slot] + s : s;
+}
+
+template <int MODEL>
+static void launch_resid_t(const DevProblem& P, const double* x, double* partial, double* scal, int slot,
+                           double* r_out, int weighted, cudaStream_t st) {
+    const int nb = (P.nObs + RES_BLOCK - 1) / RES_BLOCK;
+    if (nb > 0) {
+        if (r_out) k_resid<MODEL, true><<<nb, RES_BLOCK, 0, st>>>(P, partial, (double2*)r_out, weighted);
+        else       k_resid<MODEL, false><<<nb, RES_BLOCK, 0, st>>>(P, partial, nullptr, weighted);
+    }
+    k_final_sum<<<1, 256, 0, st>>>(partial, nb, scal, slot, 0);
+    count_launch(2);
+    if (P.nPrior > 0) {
+        k_prior_resid<<<1, 256, 0, st>>>(P, x, partial, r_out ? r_out + 2 * (size_t)P.nObs : nullptr, weighted);
+        k_final_sum<<<1, 32, 0, st>>>(partial, 1, scal, slot, 1);
+        count_launch(2);
+    }
+}
+// scal[slot] = r'r (weighted) at the current parameter arrays; optionally writes r (m doubles).
+void launch_resid(const DevProblem& P, const double* x, double* partial, double* scal, int slot,
+                  double* r_out, int weighted, cudaStream_t st) {
+    switch (P.model) {
+        case 0: launch_resid_t<0>(P, x, partial, scal, slot, r_out, weighted, st); break;
+        case 1: launch_resid_t<1>(P, x, partial, scal, slot, r_out, weighted, st); break;
+        case 2: launch_resid_t<2>(P, x, partial, scal, slot, r_out, weighted, st); break;
+        default: launch_resid_t<3>(P, x, partial, scal, slot, r_out, weighted, st); break;
+    }
+}
+
+// scal[slot] = sum of squared weighted prior residuals at x
+void launch_prior_rr(const DevProblem& P, const double* x, double* partial, double* scal, int slot, cudaStream_t st) {
+    if (P.nPrior > 0) {
+        k_prior_resid<<<1, 256, 0, st>>>(P, x, partial, nullptr, 1);
+        k_final_sum<<<1, 32, 0, st>>>(partial, 1, scal, slot, 0);
+        count_launch(2);
+    } else {
+        cudaMemsetAsync(scal + slot, 0, sizeof(double), st);
+    }
+}
+
+// (J p) per observation, recomputed: sums of (Jp)^2 and r.(Jp)
+template <int MODEL>
+__global__ void __launch_bounds__(RES_BLOCK) k_jp(DevProblem P, const double* __restrict__ p,
+                                                   double* __restrict__ partial, int nb) {
+    __shared__ double sm[32];
+    double s2 = 0.0, sr = 0.0;
+    const int k = blockIdx.x * RES_BLOCK + threadIdx.x;
+    if (k < P.nObs) {
+        const double2 uv = P.uv_cm[k];
+        const double2 is = P.isig_cm[k];
+        const int j = P.pt_cm[k];
+        const int i = P.img_cm[k];
+        const ImgRec g = P.img[i];
+        const IORec io = P.io[g.io];
+        const double Q[3] = {P.OPval[3 * (size_t)j], P.OPval[3 * (size_t)j + 1], P.OPval[3 * (size_t)j + 2]};
+        ObsJac o;
+        obs_model<MODEL, true, true>(Q, g, io, P.nK, P.nP, uv.x, uv.y, o);
+        double j0 = 0.0, j1 = 0.0;
+#pragma unroll
+        for (int s = 0; s < DBAT_NSLOT; ++s) {
+            const int c = P.sh_col[s];
+            if (c >= 0) { const double pv = p[c]; j0 += o.dIO[s][0] * pv; j1 += o.dIO[s][1] * pv; }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            int c = P.eo_col[6 * (size_t)i + a];
+            if (c >= 0) { const double pv = p[c]; j0 += o.dC[0][a] * pv; j1 += o.dC[1][a] * pv; }
+            c = P.eo_col[6 * (size_t)i + 3 + a];
+            if (c >= 0) { const double pv = p[c]; j0 += o.dA[0][a] * pv; j1 += o.dA[1][a] * pv; }
+            c = P.op_col[3 * (size_t)j + a];
+            if (c >= 0) { const double pv = p[c]; j0 += o.dOP[0][a] * pv; j1 += o.dOP[1][a] * pv; }
+        }
+        j0 *= is.x; j1 *= is.y;
+        s2 = j0 * j0 + j1 * j1;
+        sr = (o.r[0] * is.x) * j0 + (o.r[1] * is.y) * j1;
+    }
+    s2 = block_sum(s2, sm);
+    sr = block_sum(sr, sm);
+    if (threadIdx.x == 0) { partial[blockIdx.x] = s2; partial[nb + blockIdx.x] = sr; }
+}
+__global__ void k_prior_jp(DevProblem P, const double* __restrict__ x, const double* __restrict__ p,
+                           double* __restrict__ partial) {
+    __shared__ double sm[32];
+    double s2 = 0.0, sr = 0.0;
+    for (int k = threadIdx.x; k < P.nPrior; k += blockDim.x) {
+        const int c = P.prior_col[k];
+        const double w = P.prior_isig[k];
+        const double jp = p[c] * w;
+        s2 += jp * jp;
+        sr += (x[c] - P.prior_val[k]) * w * jp;
+    }
+    s2 = block_sum(s2, sm);
+    sr = block_sum(sr, sm);
+    if (threadIdx.x == 0) { partial[0] = s2; partial[1] = sr; }
+}
+template <int MODEL>
+static void launch_jp_t(const DevProblem& P, const double* x, const double* p, double* partial,
+                        double* scal, int slot2, int slotr, cudaStream_t st) {
+    const int nb = (P.nObs + RES_BLOCK - 1) / RES_BLOCK;
+    if (nb > 0) k_jp<MODEL><<<nb, RES_BLOCK, 0, st>>>(P, p, partial, nb);
+    k_final_sum<<<1, 256, 0, st>>>(partial, nb, scal, slot2, 0);
+    k_final_sum<<<1, 256, 0, st>>>(partial + nb, nb, scal, slotr, 0);
+    count_launch(3);
+    if (P.nPrior > 0) {
+        k_prior_jp<<<1, 256, 0, st>>>(P, x, p, partial);
+        k_final_sum<<<1, 32, 0, st>>>(partial, 1, scal, slot2, 1);
+        k_final_sum<<<1, 32, 0, st>>>(partial + 1, 1, scal, slotr, 1);
+        count_launch(3);
+    }
+}
+// scal[slot2] = |J p|^2, scal[slotr] = r'(J p) with J, r at the current parameter arrays.
+void launch_jp(const DevProblem& P, const double* x, const double* p, double* partial, double* scal,
+               int slot2, int slotr, cudaStream_t st) {
+    switch (P.model) {
+        case 0: launch_jp_t<0>(P, x, p, partial, scal, slot2, slotr, st); break;
+        case 1: launch_jp_t<1>(P, x, p, partial, scal, slot2, slotr, st); break;
+        case 2: launch_jp_t<2>(P, x, p, partial, scal, slot2, slotr, st); break;
+        default: launch_jp_t<3>(P, x, p, partial, scal, slot2, slotr, st); break;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense per-observation Jacobian blocks for the CSC export (one-off, end of a run)
+// layout per observation: [2 rows][NSLOT IO | 3 dC | 3 dA | 3 dOP] = 2 x 23 doubles
+// ---------------------------------------------------------------------------------------------
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_export_jac(DevProblem P, double* __restrict__ out, int weighted) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P.nObs) return;
+    const double2 uv = P.uv_cm[k];
+    const double2 is = P.isig_cm[k];
+    const int j = P.pt_cm[k];
+    const ImgRec g = P.img[P.img_cm[k]];
+    const IORec io = P.io[g.io];
+    const double Q[3] = {P.OPval[3 * (size_t)j], P.OPval[3 * (size_t)j + 1], P.OPval[3 * (size_t)j + 2]};
+    ObsJac o;
+    obs_model<MODEL, true, true>(Q, g, io, P.nK, P.nP, uv.x, uv.y, o);
+    const double w0 = weighted ? is.x : 1.0, w1 = weighted ? is.y : 1.0;
+    const int LD = DBAT_NSLOT + 9;
+    double* r0 = out + (size_t)k * 2 * LD;
+    double* r1 = r0 + LD;
+#pragma unroll
+    for (int s = 0; s < DBAT_NSLOT; ++s) { r0[s] = o.dIO[s][0] * w0; r1[s] = o.dIO[s][1] * w1; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        r0[DBAT_NSLOT + c] = o.dC[0][c] * w0;      r1[DBAT_NSLOT + c] = o.dC[1][c] * w1;
+        r0[DBAT_NSLOT + 3 + c] = o.dA[0][c] * w0;  r1[DBAT_NSLOT + 3 + c] = o.dA[1][c] * w1;
+        r0[DBAT_NSLOT + 6 + c] = o.dOP[0][c] * w0; r1[DBAT_NSLOT + 6 + c] = o.dOP[1][c] * w1;
+    }
+}
+void launch_export_jac(const DevProblem& P, double* out, int weighted, cudaStream_t st) {
+    if (P.nObs <= 0) return;
+    const int nb = (P.nObs + 127) / 128;
+    switch (P.model) {
+        case 0: k_export_jac<0><<<nb, 128, 0, st>>>(P, out, weighted); break;
+        case 1: k_export_jac<1><<<nb, 128, 0, st>>>(P, out, weighted); break;
+        case 2: k_export_jac<2><<<nb, 128, 0, st>>>(P, out, weighted); break;
+        default: k_export_jac<3><<<nb, 128, 0, st>>>(P, out, weighted); break;
+    }
+    count_launch();
+}

@@ -1,0 +1,53 @@
+// kernels.cuh — device-side problem view and kernel declarations shared by the .cu files.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "model.cuh"
+
+#define DBAT_GW 24                 // Gram width: NSLOT(14) IO | 6 EO | 1 r | pad  (3 tiles of 8)
+#define DBAT_GT 3                  // 8-wide tiles
+#define DBAT_GTP 6                 // lower-triangular tile pairs
+#define DBAT_GSZ (DBAT_GTP * 64)   // doubles per Gram in C-fragment tile layout
+#define DBAT_COL_EO DBAT_NSLOT     // first EO column in the Gram
+#define DBAT_COL_R (DBAT_NSLOT + 6)
+#define DBAT_CHUNK 1024            // max observations per camera-side chunk (one CTA)
+#define DBAT_PT_STRIDE 52          // doubles per point record: V[6] g[3] pad Wsh[14][3]
+#define DBAT_PT_WSH 10
+#define DBAT_W_STRIDE 18           // doubles per observation cross block W_o (6 EO x 3 OP)
+
+static_assert(DBAT_NSLOT + 7 <= DBAT_GW, "Gram width");
+
+struct Chunk { int img, start, count, pad; };
+
+// Device view of one problem (all pointers are device pointers).
+struct DevProblem {
+    int nImg, nOP, nObs, nK, nP, model;
+    int n;                 // unknowns
+    int nC;                // camera-side unknowns (IO+EO) = order of the reduced system
+    int nChunks;
+    int ldS;               // leading dimension of S (multiple of 128)
+    int nPrior;
+    // observations, camera-major (reference row order: obs k -> rows 2k,2k+1)
+    const double2* uv_cm; const double2* isig_cm; const int* pt_cm; const int* img_cm;
+    // observations, point-major
+    const double2* uv_pm; const double2* isig_pm; const int* img_pm; const int* pm2cm;
+    const int* pt_start;   // nOP+1
+    const Chunk* chunks;
+    // current parameter values
+    double* IOval; double* EOval; double* OPval;   // NC x nImg, 6 x nImg, 3 x nOP
+    ImgRec* img; IORec* io;
+    // column maps (0-based x column, -1 = fixed)
+    const int* sh_col;     // NSLOT
+    const int* eo_col;     // nImg x 6
+    const int* op_col;     // nOP x 3
+    // prior observations
+    const int* prior_col; const double* prior_val; const double* prior_isig;
+    // normal-equation storage
+    double* chunkG;        // nChunks x GSZ   partial Grams
+    double* imgG;          // nImg x GSZ      per-image Gram (IO|EO|r)
+    double* shG;           // GSZ             sum over images
+    double* pt;            // nOP x PT_STRIDE point records
+    double* W;             // nObs x 18       cross blocks, point-major order
+    double* S;             // ldS x ldS       reduced system (lower triangle), column-major
+    double* rhs;           // ldS             reduced right-hand side
+};

@@ -1,0 +1,54 @@
+// launch.h — host-side launchers (one per kernel family) shared by the translation units.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+struct DevProblem;
+
+// every kernel launch of the library is counted (reported as gpu_launches by bench.py)
+extern int64_t g_dbat_launches;
+static inline void count_launch(int n = 1) { g_dbat_launches += n; }
+
+// eval.cu
+void launch_deserialize(const double* x, const int* src, const int* dest, double* arr, int cnt, cudaStream_t st);
+void launch_param_setup(const DevProblem& P, const int* rep, int nIO, cudaStream_t st);
+void launch_cam_side(const DevProblem& P, const int* img_chunk_start, double* tmp, cudaStream_t st);
+void launch_point_side(const DevProblem& P, cudaStream_t st);
+void launch_prior_apply(const DevProblem& P, const double* x, double* camDiag, double* camG,
+                        const int* col2pt, cudaStream_t st);
+void launch_resid(const DevProblem& P, const double* x, double* partial, double* scal, int slot,
+                  double* r_out, int weighted, cudaStream_t st);
+void launch_prior_rr(const DevProblem& P, const double* x, double* partial, double* scal, int slot, cudaStream_t st);
+void launch_jp(const DevProblem& P, const double* x, const double* p, double* partial, double* scal,
+               int slot2, int slotr, cudaStream_t st);
+void launch_export_jac(const DevProblem& P, double* out, int weighted, cudaStream_t st);
+
+// schur.cu
+void launch_diag(const DevProblem& P, const double* camDiag, double* diagN, cudaStream_t st);
+void launch_build_S(const DevProblem& P, const double* camDiag, const double* camG, double lambda,
+                    cudaStream_t st);
+void launch_schur(const DevProblem& P, double lambda, cudaStream_t st);
+void launch_scale_S(const DevProblem& P, const double* d, cudaStream_t st);
+void launch_backsub(const DevProblem& P, double lambda, const double* pc, double* p, cudaStream_t st);
+void launch_vec_ops_sum(const double* a, int n, double* partial, double* scal, int slot, cudaStream_t st);
+void launch_dot(const double* a, const double* b, int n, double* partial, double* scal, int slot, cudaStream_t st);
+void launch_axpy(double alpha, const double* x, const double* y, double* out, int n, cudaStream_t st);
+void launch_inv_sqrt(const double* in, double* out, int n, cudaStream_t st);
+void launch_mul(const double* a, const double* b, double* out, int n, cudaStream_t st);
+
+// chol.cu
+struct CholWork {
+    int n = 0, ld = 0, nb = 0;      // order, leading dimension (multiple of 128), # 128-blocks
+    double* invL = nullptr;         // nb x 128 x 128 inverses of the diagonal blocks
+    int* info = nullptr;            // device flag: 0 ok, k>0 = first non-positive pivot (1-based)
+    double* minmax = nullptr;       // device: [0]=min pivot, [1]=max pivot (of L's diagonal)
+};
+void chol_alloc(CholWork& w, int n, int ld);
+void chol_free(CholWork& w);
+// In-place lower Cholesky of the ld x ld column-major matrix A (rows/cols >= n are padding and
+// must hold the identity).  Asynchronous; read w.info afterwards.
+void chol_factor(CholWork& w, double* A, cudaStream_t st);
+// Solve L L' x = b in place (b length ld, padding entries ignored).
+void chol_solve(const CholWork& w, const double* A, double* b, cudaStream_t st);
+// Z = inv(L) (lower) into Zout (ld x ld); then C = Z'Z (= inv(A)) full symmetric into Cout.
+void chol_inverse(const CholWork& w, const double* A, double* Z, double* C, cudaStream_t st);

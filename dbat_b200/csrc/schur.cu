@@ -1,0 +1,377 @@
+// schur.cu — damped step: batched 3x3 point-block inverses, Schur reduction onto the dense
+// camera/IO system, back-substitution.  Replaces `p=(JTJ+lambda*I)\(-JTr)`
+// (code/bundle/lsa/levenberg_marquardt.m:119) and the Jacobi-scaled variant
+// (gauss_newton_armijo.m:166-174) with the block elimination of SURVEY.md Appendix A:
+//   S = N_cc + lambda*I - sum_j W~_j (V_j + lambda*I)^-1 W~_j',   rhs = -g_c + sum_j W~_j (..)^-1 g_j
+//   p_j = (V_j + lambda*I)^-1 (-g_j - W~_j' p_c)
+#include "kernels.cuh"
+#include "launch.h"
+
+__device__ __forceinline__ double gram_at(const double* __restrict__ G, int R, int C) {
+    if (R < C) { const int t = R; R = C; C = t; }
+    const int p = R >> 3, q = C >> 3, i = R & 7, j = C & 7;
+    const int tp = p * (p + 1) / 2 + q;
+    return G[tp * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1)];
+}
+
+// inverse of the damped 3x3 point block; fixed coordinates (mask 0) get a unit diagonal.
+// Cholesky based (the block is SPD).  Returns false if not positive definite.
+__device__ __forceinline__ bool point_inverse(const double* __restrict__ rec, const int* __restrict__ opc,
+                                              double lambda, double Vi[6]) {
+    double a00 = rec[0], a01 = rec[1], a02 = rec[2], a11 = rec[3], a12 = rec[4], a22 = rec[5];
+    const bool f0 = opc[0] >= 0, f1 = opc[1] >= 0, f2 = opc[2] >= 0;
+    a00 = f0 ? a00 + lambda : 1.0;
+    a11 = f1 ? a11 + lambda : 1.0;
+    a22 = f2 ? a22 + lambda : 1.0;
+    bool ok = a00 > 0.0;
+    const double l00 = sqrt(a00);
+    const double l10 = a01 / l00, l20 = a02 / l00;
+    const double d1 = a11 - l10 * l10;
+    ok = ok && d1 > 0.0;
+    const double l11 = sqrt(d1);
+    const double l21 = (a12 - l20 * l10) / l11;
+    const double d2 = a22 - l20 * l20 - l21 * l21;
+    ok = ok && d2 > 0.0;
+    const double l22 = sqrt(d2);
+    // M = inv(L)
+    const double m00 = 1.0 / l00, m11 = 1.0 / l11, m22 = 1.0 / l22;
+    const double m10 = -l10 * m00 * m11;
+    const double m21 = -l21 * m11 * m22;
+    const double m20 = -(l20 * m00 + l21 * m10) * m22;
+    // Vi = M' M
+    Vi[0] = m00 * m00 + m10 * m10 + m20 * m20;
+    Vi[1] = m10 * m11 + m20 * m21;
+    Vi[2] = m20 * m22;
+    Vi[3] = m11 * m11 + m21 * m21;
+    Vi[4] = m21 * m22;
+    Vi[5] = m22 * m22;
+    if (!f0) { Vi[0] = 0.0; Vi[1] = 0.0; Vi[2] = 0.0; }
+    if (!f1) { Vi[1] = 0.0; Vi[3] = 0.0; Vi[4] = 0.0; }
+    if (!f2) { Vi[2] = 0.0; Vi[4] = 0.0; Vi[5] = 0.0; }
+    return ok;
+}
+
+__device__ __forceinline__ void symv3(const double Vi[6], const double w[3], double y[3]) {
+    y[0] = Vi[0] * w[0] + Vi[1] * w[1] + Vi[2] * w[2];
+    y[1] = Vi[1] * w[0] + Vi[3] * w[1] + Vi[4] * w[2];
+    y[2] = Vi[2] * w[0] + Vi[4] * w[1] + Vi[5] * w[2];
+}
+
+// diag(J'J) for every unknown (Jacobi scaling, trace for lambda0)
+__global__ void k_diag(DevProblem P, const double* __restrict__ camDiag, double* __restrict__ diagN) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < DBAT_NSLOT) {
+        const int c = P.sh_col[t];
+        if (c >= 0) diagN[c] = gram_at(P.shG, t, t) + camDiag[c];
+    }
+    if (t < P.nImg * 6) {
+        const int i = t / 6, a = t % 6;
+        const int c = P.eo_col[t];
+        if (c >= 0) diagN[c] = gram_at(P.imgG + (size_t)i * DBAT_GSZ, DBAT_COL_EO + a, DBAT_COL_EO + a) + camDiag[c];
+    }
+    if (t < P.nOP * 3) {
+        const int j = t / 3, a = t % 3;
+        const int c = P.op_col[t];
+        if (c >= 0) diagN[c] = P.pt[(size_t)j * DBAT_PT_STRIDE + (a == 0 ? 0 : (a == 1 ? 3 : 5))];
+    }
+}
+void launch_diag(const DevProblem& P, const double* camDiag, double* diagN, cudaStream_t st) {
+    int n = P.nOP * 3;
+    if (P.nImg * 6 > n) n = P.nImg * 6;
+    if (DBAT_NSLOT > n) n = DBAT_NSLOT;
+    k_diag<<<(n + 255) / 256, 256, 0, st>>>(P, camDiag, diagN);
+    count_launch();
+}
+
+// S := N_cc + lambda*I (lower triangle), rhs := -g_c ; padding rows get a unit diagonal
+__global__ void k_build_S(DevProblem P, const double* __restrict__ camDiag, const double* __restrict__ camG,
+                          double lambda) {
+    const int i = blockIdx.x;         // image index, or nImg for the shared block
+    const size_t ld = P.ldS;
+    if (i < P.nImg) {
+        const double* G = P.imgG + (size_t)i * DBAT_GSZ;
+        const int* ec = P.eo_col + 6 * (size_t)i;
+        for (int e = threadIdx.x; e < 6 * (6 + DBAT_NSLOT + 1); e += blockDim.x) {
+            const int a = e / (6 + DBAT_NSLOT + 1), b = e % (6 + DBAT_NSLOT + 1);
+            const int row = ec[a];
+            if (row < 0) continue;
+            if (b < 6) {                                   // EO x EO
+                const int col = ec[b];
+                if (col < 0 || col > row) continue;
+                double v = gram_at(G, DBAT_COL_EO + a, DBAT_COL_EO + b);
+                if (a == b) v += camDiag[row] + lambda;
+                P.S[(size_t)col * ld + row] = v;
+            } else if (b < 6 + DBAT_NSLOT) {               // EO x shared IO (IO columns come first in x)
+                const int col = P.sh_col[b - 6];
+                if (col < 0) continue;
+                P.S[(size_t)col * ld + row] = gram_at(G, DBAT_COL_EO + a, b - 6);
+            } else {
+                P.rhs[row] = -(gram_at(G, DBAT_COL_EO + a, DBAT_COL_R) + camG[row]);
+            }
+        }
+    } else {
+        for (int e = threadIdx.x; e < DBAT_NSLOT * (DBAT_NSLOT + 1); e += blockDim.x) {
+            const int a = e / (DBAT_NSLOT + 1), b = e % (DBAT_NSLOT + 1);
+            const int row = P.sh_col[a];
+            if (row < 0) continue;
+            if (b < DBAT_NSLOT) {
+                const int col = P.sh_col[b];
+                if (col < 0 || col > row) continue;
+                double v = gram_at(P.shG, a, b);
+                if (a == b) v += camDiag[row] + lambda;
+                P.S[(size_t)col * ld + row] = v;
+            } else {
+                P.rhs[row] = -(gram_at(P.shG, a, DBAT_COL_R) + camG[row]);
+            }
+        }
+        for (int k = P.nC + threadIdx.x; k < P.ldS; k += blockDim.x) {
+            P.S[(size_t)k * ld + k] = 1.0;
+            P.rhs[k] = 0.0;
+        }
+    }
+}
+void launch_build_S(const DevProblem& P, const double* camDiag, const double* camG, double lambda,
+                    cudaStream_t st) {
+    cudaMemsetAsync(P.S, 0, sizeof(double) * (size_t)P.ldS * P.ldS, st);
+    k_build_S<<<P.nImg + 1, 128, 0, st>>>(P, camDiag, camG, lambda);
+    count_launch();
+}
+
+// Schur update, one warp per object point (v1: FP64 atomics into the dense lower triangle).
+__global__ void __launch_bounds__(256) k_schur(DevProblem P, double lambda, double* __restrict__ shAcc) {
+    const int lane = threadIdx.x & 31;
+    const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int nWarps = (gridDim.x * blockDim.x) >> 5;
+    const size_t ld = P.ldS;
+    // shared x shared accumulators: entries e = lane + 32*k of the NSLOT x (NSLOT+1) table
+    constexpr int NE = DBAT_NSLOT * (DBAT_NSLOT + 1);
+    constexpr int NEL = (NE + 31) / 32;
+    double accSh[NEL];
+#pragma unroll
+    for (int k = 0; k < NEL; ++k) accSh[k] = 0.0;
+
+    for (int j = warpGlobal; j < P.nOP; j += nWarps) {
+        const double* rec = P.pt + (size_t)j * DBAT_PT_STRIDE;
+        const int* opc = P.op_col + 3 * (size_t)j;
+        if (opc[0] < 0 && opc[1] < 0 && opc[2] < 0) continue;
+        double Vi[6];
+        point_inverse(rec, opc, lambda, Vi);
+        const double gj[3] = {rec[6], rec[7], rec[8]};
+        double Vg[3];
+        symv3(Vi, gj, Vg);
+        const int o0 = P.pt_start[j], k = P.pt_start[j + 1] - o0;
+        // local x local pair blocks: item = (pair, a)
+        const int nItems = k * (k + 1) / 2 * 6;
+        for (int it = lane; it < nItems; it += 32) {
+            const int pr = it / 6, a = it - pr * 6;
+            int o = (int)((sqrt(8.0 * pr + 1.0) - 1.0) * 0.5);
+            while ((o + 1) * (o + 2) / 2 <= pr) ++o;
+            while (o * (o + 1) / 2 > pr) --o;
+            const int o2 = pr - o * (o + 1) / 2;            // o2 <= o  => image(o2) <= image(o)
+            const int row = P.eo_col[6 * (size_t)P.img_pm[o0 + o] + a];
+            if (row < 0) continue;
+            const double* Wa = P.W + (size_t)(o0 + o) * DBAT_W_STRIDE + 3 * a;
+            const double wa[3] = {Wa[0], Wa[1], Wa[2]};
+            double ya[3];
+            symv3(Vi, wa, ya);
+            const int* ec2 = P.eo_col + 6 * (size_t)P.img_pm[o0 + o2];
+            const double* Wb = P.W + (size_t)(o0 + o2) * DBAT_W_STRIDE;
+#pragma unroll
+            for (int b = 0; b < 6; ++b) {
+                const int col = ec2[b];
+                if (col < 0 || col > row) continue;
+                const double v = ya[0] * Wb[3 * b] + ya[1] * Wb[3 * b + 1] + ya[2] * Wb[3 * b + 2];
+                atomicAdd(&P.S[(size_t)col * ld + row], -v);
+            }
+            if (o2 == 0) {                                   // once per (o, a): rhs and shared x local
+                atomicAdd(&P.rhs[row], ya[0] * gj[0] + ya[1] * gj[1] + ya[2] * gj[2]);
+#pragma unroll
+                for (int s = 0; s < DBAT_NSLOT; ++s) {
+                    const int col = P.sh_col[s];
+                    if (col < 0) continue;
+                    const double* ws = rec + DBAT_PT_WSH + 3 * s;
+                    atomicAdd(&P.S[(size_t)col * ld + row], -(ya[0] * ws[0] + ya[1] * ws[1] + ya[2] * ws[2]));
+                }
+            }
+        }
+        // shared x shared (+ rhs): accumulate in registers, flushed once per warp
+#pragma unroll
+        for (int kk = 0; kk < NEL; ++kk) {
+            const int e = lane + 32 * kk;
+            if (e < NE) {
+                const int a = e / (DBAT_NSLOT + 1), b = e - a * (DBAT_NSLOT + 1);
+                const double* wa = rec + DBAT_PT_WSH + 3 * a;
+                if (b < DBAT_NSLOT) {
+                    if (b <= a) {
+                        const double* wb = rec + DBAT_PT_WSH + 3 * b;
+                        const double w3[3] = {wb[0], wb[1], wb[2]};
+                        double y[3];
+                        symv3(Vi, w3, y);
+                        accSh[kk] += wa[0] * y[0] + wa[1] * y[1] + wa[2] * y[2];
+                    }
+                } else {
+                    accSh[kk] += wa[0] * Vg[0] + wa[1] * Vg[1] + wa[2] * Vg[2];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int kk = 0; kk < NEL; ++kk) {
+        const int e = lane + 32 * kk;
+        if (e < NE) atomicAdd(&shAcc[e], accSh[kk]);
+    }
+}
+__global__ void k_schur_sh_apply(DevProblem P, const double* __restrict__ shAcc) {
+    const size_t ld = P.ldS;
+    for (int e = threadIdx.x; e < DBAT_NSLOT * (DBAT_NSLOT + 1); e += blockDim.x) {
+        const int a = e / (DBAT_NSLOT + 1), b = e % (DBAT_NSLOT + 1);
+        const int row = P.sh_col[a];
+        if (row < 0) continue;
+        if (b < DBAT_NSLOT) {
+            const int col = P.sh_col[b];
+            if (col < 0 || b > a) continue;
+            P.S[(size_t)col * ld + row] -= shAcc[e];
+        } else {
+            P.rhs[row] += shAcc[e];
+        }
+    }
+}
+static double* g_shAcc = nullptr;
+void launch_schur(const DevProblem& P, double lambda, cudaStream_t st) {
+    if (!g_shAcc) cudaMalloc(&g_shAcc, sizeof(double) * DBAT_NSLOT * (DBAT_NSLOT + 1));
+    cudaMemsetAsync(g_shAcc, 0, sizeof(double) * DBAT_NSLOT * (DBAT_NSLOT + 1), st);
+    int nb = (P.nOP + 7) / 8;
+    if (nb > 148 * 8) nb = 148 * 8;
+    if (nb < 1) nb = 1;
+    k_schur<<<nb, 256, 0, st>>>(P, lambda, g_shAcc);
+    k_schur_sh_apply<<<1, 256, 0, st>>>(P, g_shAcc);
+    count_launch(2);
+}
+
+// S := D S D (lower triangle), rhs := D rhs   (Jacobi column scaling, gauss_newton_armijo.m:166-172)
+__global__ void k_scale_S(DevProblem P, const double* __restrict__ d) {
+    const int c = blockIdx.y;
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= P.nC || r >= P.nC || r < c) return;
+    P.S[(size_t)c * P.ldS + r] *= d[r] * d[c];
+    if (c == 0) P.rhs[r] *= d[r];
+}
+void launch_scale_S(const DevProblem& P, const double* d, cudaStream_t st) {
+    dim3 grid((P.nC + 255) / 256, P.nC);
+    k_scale_S<<<grid, 256, 0, st>>>(P, d);
+    count_launch();
+}
+
+// back-substitution for the object points; p[0:nC] must already hold the camera/IO step
+__global__ void __launch_bounds__(128) k_backsub(DevProblem P, double lambda, double* __restrict__ p) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.nOP) return;
+    const int* opc = P.op_col + 3 * (size_t)j;
+    if (opc[0] < 0 && opc[1] < 0 && opc[2] < 0) return;
+    const double* rec = P.pt + (size_t)j * DBAT_PT_STRIDE;
+    double Vi[6];
+    point_inverse(rec, opc, lambda, Vi);
+    double t[3] = {-rec[6], -rec[7], -rec[8]};
+#pragma unroll
+    for (int s = 0; s < DBAT_NSLOT; ++s) {
+        const int c = P.sh_col[s];
+        if (c < 0) continue;
+        const double pv = p[c];
+        const double* ws = rec + DBAT_PT_WSH + 3 * s;
+        t[0] -= ws[0] * pv; t[1] -= ws[1] * pv; t[2] -= ws[2] * pv;
+    }
+    const int o0 = P.pt_start[j], o1 = P.pt_start[j + 1];
+    for (int ob = o0; ob < o1; ++ob) {
+        const int* ec = P.eo_col + 6 * (size_t)P.img_pm[ob];
+        const double* Wo = P.W + (size_t)ob * DBAT_W_STRIDE;
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const int c = ec[a];
+            if (c < 0) continue;
+            const double pv = p[c];
+            t[0] -= Wo[3 * a] * pv; t[1] -= Wo[3 * a + 1] * pv; t[2] -= Wo[3 * a + 2] * pv;
+        }
+    }
+    double y[3];
+    symv3(Vi, t, y);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) if (opc[a] >= 0) p[opc[a]] = y[a];
+}
+void launch_backsub(const DevProblem& P, double lambda, const double* pc, double* p, cudaStream_t st) {
+    if (pc != p) cudaMemcpyAsync(p, pc, sizeof(double) * P.nC, cudaMemcpyDeviceToDevice, st);
+    if (P.nOP > 0) { k_backsub<<<(P.nOP + 127) / 128, 128, 0, st>>>(P, lambda, p); count_launch(); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// deterministic vector helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum2(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__global__ void k_dot_partial(const double* __restrict__ a, const double* __restrict__ b, int n,
+                              double* __restrict__ partial) {
+    __shared__ double sm[32];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    double v = (k < n) ? a[k] * (b ? b[k] : 1.0) : 0.0;
+    v = warp_sum2(v);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0;
+        t = warp_sum2(t);
+        if (threadIdx.x == 0) partial[blockIdx.x] = t;
+    }
+}
+__global__ void k_final_sum2(const double* __restrict__ partial, int n, double* __restrict__ out, int slot) {
+    __shared__ double sm[32];
+    double s = 0.0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) s += partial[k];
+    s = warp_sum2(s);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = threadIdx.x < (blockDim.x >> 5) ? sm[threadIdx.x] : 0.0;
+        t = warp_sum2(t);
+        if (threadIdx.x == 0) out[slot] = t;
+    }
+}
+void launch_dot(const double* a, const double* b, int n, double* partial, double* scal, int slot,
+                cudaStream_t st) {
+    const int nb = (n + 255) / 256;
+    if (nb > 0) k_dot_partial<<<nb, 256, 0, st>>>(a, b, n, partial);
+    k_final_sum2<<<1, 256, 0, st>>>(partial, nb, scal, slot);
+    count_launch(2);
+}
+void launch_vec_ops_sum(const double* a, int n, double* partial, double* scal, int slot, cudaStream_t st) {
+    launch_dot(a, nullptr, n, partial, scal, slot, st);
+}
+__global__ void k_axpy(double alpha, const double* __restrict__ x, const double* __restrict__ y,
+                       double* __restrict__ out, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = y[k] + alpha * x[k];
+}
+void launch_axpy(double alpha, const double* x, const double* y, double* out, int n, cudaStream_t st) {
+    if (n <= 0) return;
+    k_axpy<<<(n + 255) / 256, 256, 0, st>>>(alpha, x, y, out, n);
+    count_launch();
+}
+__global__ void k_inv_sqrt(const double* __restrict__ in, double* __restrict__ out, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = 1.0 / sqrt(in[k]);
+}
+void launch_inv_sqrt(const double* in, double* out, int n, cudaStream_t st) {
+    if (n <= 0) return;
+    k_inv_sqrt<<<(n + 255) / 256, 256, 0, st>>>(in, out, n);
+    count_launch();
+}
+__global__ void k_mul(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) out[k] = a[k] * b[k];
+}
+void launch_mul(const double* a, const double* b, double* out, int n, cudaStream_t st) {
+    if (n <= 0) return;
+    k_mul<<<(n + 255) / 256, 256, 0, st>>>(a, b, out, n);
+    count_launch();
+}

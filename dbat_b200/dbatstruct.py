@@ -1,0 +1,169 @@
+"""Host-side DBAT problem struct and (de)serialisation indices for the B200 path.
+
+Mirrors the reference's struct layout (`code/misc/emptydbatstruct.m:8-182`) and index
+contract (`code/misc/buildserialindices.m:57-221`, `serialize.m:14-18`,
+`deserialize.m:28-30`, `buildweightmatrix.m:13-43`) so that the same struct goes in and
+out of `bundle()`.  Vectorised NumPy; indices are 0-based here and converted to MATLAB's
+1-based int64 only at the C ABI (`dbat_b200/_lib.py`).
+"""
+from types import SimpleNamespace as NS
+
+import numpy as np
+
+
+def new_struct(IOval, EOval, OPval, IPval, ip_img, ip_op, pxSize, imSize,
+               distModel=3, nK=3, nP=2, IPstd=1.0, IOblock=None, EOblock=None):
+    """Assemble a DBAT struct from flat arrays; image points are sorted by (image, OP)
+    as `prob2dbatstruct.m:349-365` does."""
+    IOval = np.array(IOval, dtype=float, order='F')
+    EOval = np.array(EOval, dtype=float, order='F')
+    OPval = np.array(OPval, dtype=float, order='F')
+    NC, nImg = IOval.shape
+    nOP = OPval.shape[1]
+    ip_img = np.asarray(ip_img, dtype=np.int64)
+    ip_op = np.asarray(ip_op, dtype=np.int64)
+    order = np.lexsort((ip_op, ip_img))
+    nIP = len(order)
+    if np.ndim(IPstd) == 0:
+        IPstd = np.full((2, nIP), float(IPstd))
+    else:
+        IPstd = np.array(np.broadcast_to(np.asarray(IPstd, dtype=float), (2, nIP))[:, order])
+    s = NS()
+    s.IO = NS(val=IOval,
+              model=NS(distModel=np.full(nImg, distModel, dtype=int), nK=nK, nP=nP),
+              sensor=NS(pxSize=np.array(np.broadcast_to(pxSize, (2, nImg)), dtype=float),
+                        imSize=np.array(np.broadcast_to(imSize, (2, nImg)), dtype=float)),
+              struct=NS(block=np.ones((NC, nImg), dtype=int) if IOblock is None
+                        else np.array(IOblock, dtype=int), leading=None))
+    s.EO = NS(val=EOval, cam=np.zeros(nImg, dtype=int),
+              struct=NS(block=np.tile(np.arange(1, nImg + 1), (6, 1)) if EOblock is None
+                        else np.array(EOblock, dtype=int), leading=None))
+    s.OP = NS(val=OPval, id=np.arange(nOP))
+    s.IP = NS(val=np.array(IPval, dtype=float)[:, order], std=IPstd, img=ip_img[order],
+              op=ip_op[order], cam=ip_img[order].copy(), sigmas=np.array([1.0]))
+    s.prior = NS(
+        IO=NS(use=np.zeros((NC, nImg), bool), val=np.full((NC, nImg), np.nan),
+              std=np.full((NC, nImg), np.nan)),
+        EO=NS(use=np.zeros((6, nImg), bool), val=np.full((6, nImg), np.nan),
+              std=np.full((6, nImg), np.nan)),
+        OP=NS(use=np.zeros((3, nOP), bool), val=np.full((3, nOP), np.nan),
+              std=np.full((3, nOP), np.nan)))
+    s.bundle = NS(est=NS(IO=np.zeros((NC, nImg), bool), EO=np.ones((6, nImg), bool),
+                         OP=np.ones((3, nOP), bool)), serial=None, deserial=None)
+    s.post = NS(res=NS(ix=None), cov=NS(CEO=None, COP=None), std=NS())
+    return s
+
+
+def _serializeblock(block, est, useObs, distinct=False):
+    """buildserialindices.m:162-221: leading element of every estimated block per row,
+    serial (matrix -> x) and deserial (x -> matrix, with fan-out over repeated ids)."""
+    nr, ncol = block.shape
+    if distinct:                                     # every column its own block (OP)
+        leading = est.copy()
+        dist = np.full(nr * ncol, -1, dtype=np.int64)
+        lead_lin = np.flatnonzero(leading.ravel(order='F'))
+        dist[lead_lin] = np.arange(len(lead_lin))
+    else:
+        blk = np.where(est, block, 0)
+        leading = np.zeros(blk.shape, bool)
+        rep = np.full(blk.shape, -1, dtype=np.int64)  # column of the leading element of (row, col)
+        for i in range(nr):
+            row = blk[i]
+            nz = np.flatnonzero(row)
+            if len(nz) == 0:
+                continue
+            _, first, inv = np.unique(row[nz], return_index=True, return_inverse=True)
+            leading[i, nz[first]] = True
+            rep[i, nz] = nz[first][inv]
+        lead_lin = np.flatnonzero(leading.ravel(order='F'))
+        pos = np.full(nr * ncol, -1, dtype=np.int64)
+        pos[lead_lin] = np.arange(len(lead_lin))
+        rows = np.broadcast_to(np.arange(nr)[:, None], blk.shape)
+        lin_rep = rows + nr * rep                      # linear index of the leading element
+        dist2 = np.where(rep >= 0, pos[np.where(rep >= 0, lin_rep, 0)], -1)
+        dist = dist2.ravel(order='F')
+    serial = NS(src=lead_lin, dest=np.arange(len(lead_lin)))
+    serial.obs = np.flatnonzero(useObs.ravel(order='F')[lead_lin])
+    dest = np.flatnonzero(dist >= 0)
+    deserial = NS(dest=dest, src=dist[dest])
+    return leading, serial, deserial, np.flatnonzero(leading.any(axis=0))
+
+
+def buildserialindices(s):
+    """buildserialindices.m:57-159 with the default order [IO; EO; OP]."""
+    IOlead, IOser, IOdes, blockIx = _serializeblock(
+        np.asarray(s.IO.struct.block), s.bundle.est.IO, s.prior.IO.use)
+    nImg = s.EO.val.shape[1]
+    if len(blockIx) == 0:
+        s.EO.cam = np.arange(nImg)
+    elif len(blockIx) == 1:
+        s.EO.cam = np.full(nImg, blockIx[0])
+    else:
+        s.EO.cam = np.full(nImg, -1)
+    EOlead, EOser, EOdes, _ = _serializeblock(
+        np.asarray(s.EO.struct.block), s.bundle.est.EO, s.prior.EO.use)
+    _, OPser, OPdes, _ = _serializeblock(np.zeros((3, s.OP.val.shape[1]), int),
+                                         s.bundle.est.OP, s.prior.OP.use, distinct=True)
+    n = 0
+    for ser, des in ((IOser, IOdes), (EOser, EOdes), (OPser, OPdes)):
+        ser.dest = ser.dest + n
+        des.src = des.src + n
+        n += len(ser.dest)
+    s.IO.struct.leading = IOlead
+    s.EO.struct.leading = EOlead
+    s.prior.IO.use = s.prior.IO.use & IOlead
+    s.prior.EO.use = s.prior.EO.use & EOlead
+    s.bundle.serial = NS(IO=IOser, EO=EOser, OP=OPser, n=n)
+    s.bundle.deserial = NS(IO=IOdes, EO=EOdes, OP=OPdes, n=n)
+    base = 0
+    ixs = []
+    for k in (2 * len(s.IP.img), len(IOser.obs), len(EOser.obs), len(OPser.obs)):
+        ixs.append(np.arange(base, base + k))
+        base += k
+    s.post.res.ix = NS(IP=ixs[0], IO=ixs[1], EO=ixs[2], OP=ixs[3], n=base)
+    return s
+
+
+def _lin(a):
+    return np.asarray(a).reshape(-1, order='F')
+
+
+def serialize(s):
+    """serialize.m:14-18."""
+    x = np.full(s.bundle.serial.n, np.nan)
+    x[s.bundle.serial.IO.dest] = _lin(s.IO.val)[s.bundle.serial.IO.src]
+    x[s.bundle.serial.EO.dest] = _lin(s.EO.val)[s.bundle.serial.EO.src]
+    x[s.bundle.serial.OP.dest] = _lin(s.OP.val)[s.bundle.serial.OP.src]
+    return x
+
+
+def deserialize(s, x):
+    """deserialize.m:28-30 (two-argument form): returns the struct updated in place."""
+    for name in ('IO', 'EO', 'OP'):
+        fld = getattr(s, name)
+        des = getattr(s.bundle.deserial, name)
+        v = _lin(fld.val).copy()
+        v[des.dest] = x[des.src]
+        fld.val = v.reshape(fld.val.shape, order='F')
+    return s
+
+
+def buildweightmatrix(s):
+    """buildweightmatrix.m:13-43 → diag(W) (length m)."""
+    stdIPmm = s.IP.std * s.IO.sensor.pxSize[:, s.IP.cam]
+    d = np.full(s.post.res.ix.n, np.nan)
+    d[s.post.res.ix.IP] = _lin(stdIPmm) ** 2
+    d[s.post.res.ix.IO] = _lin(s.prior.IO.std)[_lin(s.prior.IO.use)] ** 2
+    d[s.post.res.ix.EO] = _lin(s.prior.EO.std)[_lin(s.prior.EO.use)] ** 2
+    d[s.post.res.ix.OP] = _lin(s.prior.OP.std)[_lin(s.prior.OP.use)] ** 2
+    return 1.0 / d
+
+
+def seteoest_depend(s, camNo=0):
+    """seteoest.m:90-128: 'depend' datum."""
+    offset = s.EO.val[0:3, :] - s.EO.val[0:3, camNo][:, None]
+    i, j = np.argwhere(offset == offset.max())[0]
+    s.bundle.est.EO[:] = True
+    s.bundle.est.EO[:, camNo] = False
+    s.bundle.est.EO[i, j] = False
+    return s

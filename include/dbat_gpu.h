@@ -1,0 +1,159 @@
+/* dbat_gpu.h — C ABI of libdbatgpu.so, the B200-native bundle-adjustment inner loop.
+ *
+ * Drop-in boundary for the hot path of niclasborlin/dbat (reference paths below are
+ * relative to the reference checkout).  The reference has no FFI for this path; the
+ * only precedent is its experimental MEX set (code/test/postcov/icpc_mex.c:495-611:
+ * gateway validates inputs, MATLAB owns every returned array, errors are raised as
+ * "DBAT:<fn>:<id>").  This ABI is what a MEX gateway (mex/dbat_mex.c) or the ctypes
+ * host layer (dbat_b200/_lib.py) binds.  Plain pointers and sizes only; the library
+ * copies every input (caller keeps ownership) and writes results into caller-allocated
+ * buffers.  Index vectors are 1-based int64 exactly as MATLAB holds them.
+ *
+ * Entry point                         replaces (reference file:line)
+ *   dbat_create / dbat_destroy         resFun=@(x)brown_euler_cam4(x,s) closure + W
+ *                                      (code/bundle/bundle.m:156-175)
+ *   dbat_eval                          [f,J]=brown_euler_cam4(x,s)
+ *                                      (code/bundle/cameramodel/brown_euler_cam4.m:22-183,
+ *                                       multi_res.m:14-315, lsa/prior_obs.m:28-65)
+ *   dbat_jacobian_nnz/_csc             sparse J returned by the same call (multi_res.m:313)
+ *   dbat_solve (method LM)             code/bundle/lsa/levenberg_marquardt.m:54-247
+ *   dbat_solve (method LMP)            code/bundle/lsa/levenberg_marquardt_powell.m:60-335
+ *   dbat_solve (method GNA)            code/bundle/lsa/gauss_newton_armijo.m:75-290
+ *   dbat_cov                           code/bundle/bundle_cov.m:63-478
+ *   dbat_comm_init                     (new) NCCL communicator for point-sharded runs
+ *
+ * Not thread-safe per handle.  All functions return 0 or a negative DBAT_E_* code and
+ * never throw; dbat_last_error() gives the message.  Optimiser OUTCOME codes keep the
+ * reference's values (0 ok, -1 max iterations, -2 singular, -3 line search, -4
+ * structural rank) in dbat_result.code.
+ */
+#ifndef DBAT_GPU_H
+#define DBAT_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBAT_OK             0
+#define DBAT_E_BADARG      -101
+#define DBAT_E_CUDA        -102
+#define DBAT_E_NCCL        -103
+#define DBAT_E_OOM         -104
+#define DBAT_E_NOTSPD      -105
+#define DBAT_E_UNSUPPORTED -106
+#define DBAT_E_STATE       -107
+
+#define DBAT_METHOD_GM  0
+#define DBAT_METHOD_GNA 1
+#define DBAT_METHOD_LM  2
+#define DBAT_METHOD_LMP 3
+
+/* which-selectors of dbat_cov (bundle_cov.m:135-214) */
+#define DBAT_COV_CIO  1   /* out: NC x NC x nImg  (zero rows/cols for fixed elements) */
+#define DBAT_COV_CEO  2   /* out: 6 x 6 x nImg */
+#define DBAT_COV_COP  3   /* out: 3 x 3 x nOP */
+#define DBAT_COV_CXX_CAM 4 /* out: nCam x nCam dense covariance of the IO+EO unknowns (x order) */
+
+typedef struct dbat_handle dbat_handle;
+
+/* Flat view of the DBAT struct `s` (code/misc/emptydbatstruct.m:8-182) after
+ * buildserialindices (code/misc/buildserialindices.m:57-221).  Matrices are
+ * column-major double as MATLAB stores them. */
+typedef struct dbat_problem_desc {
+    int64_t nImg, nOP, nIP;       /* images, object points, image points                */
+    int32_t distModel, nK, nP;    /* s.IO.model.*  (NC = 5+nK+nP rows in IOval)          */
+    const double  *IOval;         /* NC x nImg   s.IO.val [cc;px;py;as;sk;K..;P..]       */
+    const double  *EOval;         /* 6  x nImg   s.EO.val [X;Y;Z;omega;phi;kappa]        */
+    const double  *OPval;         /* 3  x nOP    s.OP.val                                */
+    const double  *IPval;         /* 2  x nIP    s.IP.val (pixels), columns sorted by (image, OP) */
+    const double  *IPstd;         /* 2  x nIP    s.IP.std (pixels)                       */
+    const int64_t *IPimg;         /* nIP  image (1-based) of every IP column: [~,j]=find(s.IP.vis) */
+    const int64_t *IPop;          /* nIP  OP column (1-based): [i,~]=find(s.IP.vis)      */
+    const double  *pxSize;        /* 2  x nImg   s.IO.sensor.pxSize                      */
+    int64_t n;                    /* s.bundle.serial.n, number of unknowns               */
+    const int64_t *IOdes_src, *IOdes_dest; int64_t nIOdes;  /* s.bundle.deserial.IO      */
+    const int64_t *EOdes_src, *EOdes_dest; int64_t nEOdes;  /* s.bundle.deserial.EO      */
+    const int64_t *OPdes_src, *OPdes_dest; int64_t nOPdes;  /* s.bundle.deserial.OP      */
+    /* prior observations in residual-row order IO,EO,OP (prior_obs.m:28-65):
+     * x index = serial.*.dest(serial.*.obs), value = prior.*.val(src(obs)),
+     * std = prior.*.std(use) */
+    int64_t nPriorIO, nPriorEO, nPriorOP;
+    const int64_t *prior_x;       /* nPriorIO+nPriorEO+nPriorOP, 1-based                 */
+    const double  *prior_val, *prior_std;
+} dbat_problem_desc;
+
+/* Optimiser constants; defaults are those hard-coded in bundle.m:281-283,301-304,321-325. */
+typedef struct dbat_opts {
+    int32_t maxIter;        /* bundle.m:78 (20) */
+    double  convTol;        /* bundle.m:87 (1e-6) */
+    int32_t absTerm;        /* bundle.m:186-192 */
+    int32_t singularTest;   /* GNA only */
+    int32_t doTrace;        /* print one line per iteration */
+    double  lambda0, lambdaMin;  /* LM: negative => scaled by trace(J0'J0)/n (-1e-10) */
+    double  delta0;              /* LMP: <=0 => norm(x0) */
+    double  mu, eta;             /* GNA: mu=0.1 ; LMP: mu=rhoBad 0.25, eta=rhoGood 0.75 */
+    double  alphaMin;            /* GNA 1e-9 */
+} dbat_opts;
+
+/* Caller-allocated result buffers (MATLAB-owned in the MEX gateway). cap = maxIter+2. */
+typedef struct dbat_result {
+    double  *x;             /* n        final estimate */
+    double  *p;             /* n        final step (final.p) */
+    double  *r_w, *r_u;     /* m        final weighted / unweighted residual (may be NULL) */
+    double  *trace;         /* n x cap  iteration trace T (may be NULL) */
+    double  *rr;            /* cap+1    residual norms */
+    double  *damping;       /* cap+1    lambdas (LM) / deltas (LMP) / alphas (GNA) */
+    double  *rhos;          /* cap      LMP gain ratios (may be NULL) */
+    int32_t *steps;         /* cap      LMP step types (may be NULL) */
+    int32_t  code;          /* 0, -1, -2, -3, -4 as in the reference */
+    int32_t  iters;         /* n (trial count for LM) */
+    int32_t  nTrace, nRr, nDamping, nRhos;   /* used lengths */
+    double   seconds;       /* wall time inside the optimiser loop */
+    int64_t  launches;      /* CUDA kernels launched by this call */
+} dbat_result;
+
+int  dbat_create(const dbat_problem_desc *desc, dbat_handle **out);
+void dbat_destroy(dbat_handle *h);
+const char *dbat_last_error(const dbat_handle *h);   /* h may be NULL: last create error */
+
+int64_t dbat_num_unknowns(const dbat_handle *h);
+int64_t dbat_num_residuals(const dbat_handle *h);
+
+/* Residual (and Jacobian state) at x.  r (length m, may be NULL) receives the
+ * UNWEIGHTED residual in reference row order; weighted!=0 gives R*f instead. */
+int dbat_eval(dbat_handle *h, const double *x, double *r, int weighted);
+
+/* Sparse Jacobian at the x of the last dbat_eval / dbat_solve, MATLAB CSC layout
+ * (Jc n+1 column pointers 0-based, Ir 0-based rows, exact zeros dropped as
+ * find()/sparse() do in multi_res.m:150-313). Call _nnz first, allocate, then _csc. */
+int dbat_jacobian_nnz(dbat_handle *h, int weighted, int64_t *nnz);
+int dbat_jacobian_csc(dbat_handle *h, int weighted, int64_t *Jc, int64_t *Ir, double *vals);
+
+void dbat_default_opts(int method, dbat_opts *opts);
+int  dbat_solve(dbat_handle *h, int method, const dbat_opts *opts, const double *x0,
+                dbat_result *res);
+
+/* One pass of the hot path at x without optimiser logic (bench + tests):
+ * residual+Jacobian+assembly, Schur with damping lambda, Cholesky, back-substitution.
+ * p (n) receives the step; stats[0]=f=1/2 r'r, [1]=|Jp|^2 placeholder, [2]=trace(J'J). */
+int dbat_normal_step(dbat_handle *h, const double *x, double lambda, int jacobi_scale,
+                     double *p, double *stats);
+
+/* Posterior covariances from the undamped factorisation at the current x, times s0^2. */
+int dbat_cov(dbat_handle *h, int which, double s0, double *out);
+
+/* Multi-GPU: one process per GPU.  unique_id = the 128 bytes of ncclGetUniqueId from
+ * rank 0 (dbat_comm_unique_id), distributed by the host plumbing (torch.distributed). */
+int dbat_comm_unique_id(void *id128);
+int dbat_comm_init(dbat_handle *h, int nranks, int rank, const void *id128);
+
+/* Per-phase device time (ms) of the last dbat_solve / dbat_normal_step, for bench.py:
+ * names[i] is a static string; returns the number of phases written (<= cap). */
+int dbat_phase_times(const dbat_handle *h, const char **names, double *ms, int64_t *count, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DBAT_GPU_H */
