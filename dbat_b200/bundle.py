@@ -27,7 +27,10 @@ class Problem:
     sparse Jacobian) exactly like `[f,J]=feval(resFun,x)`.
     """
 
-    def __init__(self, s, points=None):
+    def __init__(self, s, points=None, cam_priors=True):
+        """points=(lo,hi): keep only object points lo..hi-1 and their observations (one shard of
+        a point-partitioned multi-GPU run; x stays the global vector).  cam_priors=False drops
+        the IO/EO prior observations (they are counted on rank 0 only)."""
         if s.bundle.serial is None or s.bundle.deserial is None:
             buildserialindices(s)
         L = _lib.lib()
@@ -39,7 +42,11 @@ class Problem:
         keep = {}
         d = _lib.ProblemDesc()
         nImg, nOP = s.EO.val.shape[1], s.OP.val.shape[1]
-        d.nImg, d.nOP, d.nIP = nImg, nOP, len(s.IP.img)
+        lo, hi = (0, nOP) if points is None else points
+        self.points = (lo, hi)
+        sel = slice(None) if points is None else np.flatnonzero((s.IP.op >= lo) & (s.IP.op < hi))
+        d.nImg, d.nOP = nImg, hi - lo
+        d.nIP = len(s.IP.img) if points is None else len(sel)
         d.distModel, d.nK, d.nP = int(dm[0]), int(s.IO.model.nK), int(s.IO.model.nP)
 
         def put(name, arr, kind):
@@ -49,25 +56,35 @@ class Problem:
 
         put('IOval', _lin(s.IO.val), 'd')
         put('EOval', _lin(s.EO.val[0:6]), 'd')
-        put('OPval', _lin(s.OP.val), 'd')
-        put('IPval', _lin(s.IP.val), 'd')
-        put('IPstd', _lin(s.IP.std), 'd')
-        put('IPimg', s.IP.img + 1, 'i')
-        put('IPop', s.IP.op + 1, 'i')
+        put('OPval', _lin(s.OP.val[:, lo:hi]), 'd')
+        put('IPval', _lin(s.IP.val[:, sel]), 'd')
+        put('IPstd', _lin(s.IP.std[:, sel]), 'd')
+        put('IPimg', s.IP.img[sel] + 1, 'i')
+        put('IPop', s.IP.op[sel] - lo + 1, 'i')
         put('pxSize', _lin(s.IO.sensor.pxSize), 'd')
         d.n = ser.n
         for nm in ('IO', 'EO', 'OP'):
             dd = getattr(des, nm)
-            put(nm + 'des_src', dd.src + 1, 'i')
-            put(nm + 'des_dest', dd.dest + 1, 'i')
-            setattr(d, 'n%sdes' % nm, len(dd.src))
+            src, dest = dd.src, dd.dest
+            if nm == 'OP' and points is not None:
+                k = (dest >= 3 * lo) & (dest < 3 * hi)
+                src, dest = src[k], dest[k] - 3 * lo
+            put(nm + 'des_src', src + 1, 'i')
+            put(nm + 'des_dest', dest + 1, 'i')
+            setattr(d, 'n%sdes' % nm, len(src))
         px, pv, ps = [], [], []
         for nm in ('IO', 'EO', 'OP'):                      # prior_obs.m:28-65, buildweightmatrix.m:26-31
             sr, pr = getattr(ser, nm), getattr(s.prior, nm)
-            px.append(sr.dest[sr.obs] + 1)
-            pv.append(_lin(pr.val)[sr.src[sr.obs]])
-            ps.append(_lin(pr.std)[_lin(pr.use)])
-            setattr(d, 'nPrior' + nm, len(sr.obs))
+            xi = sr.dest[sr.obs] + 1
+            vv = _lin(pr.val)[sr.src[sr.obs]]
+            sd = _lin(pr.std)[_lin(pr.use)]
+            if nm == 'OP' and points is not None:
+                k = (sr.src[sr.obs] >= 3 * lo) & (sr.src[sr.obs] < 3 * hi)
+                xi, vv, sd = xi[k], vv[k], sd[k]
+            if nm != 'OP' and not cam_priors:
+                xi, vv, sd = xi[:0], vv[:0], sd[:0]
+            px.append(xi); pv.append(vv); ps.append(sd)
+            setattr(d, 'nPrior' + nm, len(xi))
         put('prior_x', np.concatenate(px), 'i')
         put('prior_val', np.concatenate(pv), 'd')
         put('prior_std', np.concatenate(ps), 'd')
@@ -117,14 +134,18 @@ class Problem:
                                         _lib.dptr(V)))
         return sp.csc_matrix((V[:nnz.value], Ir[:nnz.value], Jc), shape=(self.m, self.n))
 
-    def normal_step(self, x, lam=0.0, jacobi=False):
-        """One pass of the hot path (eval + assembly + Schur + Cholesky + back-substitution)."""
-        x = _lib.f64(x)
-        p = np.empty(self.n)
+    def normal_step(self, x=None, lam=0.0, jacobi=False, trial=False, accept=False, p_out=None,
+                    want_p=True):
+        """One pass of the hot path (eval + assembly + Schur + Cholesky + back-substitution
+        [+ trial residual]).  x=None reuses the device-resident iterate."""
+        xa = _lib.f64(x) if x is not None else None
+        p = p_out if p_out is not None else (np.empty(self.n) if want_p else None)
         st = np.zeros(8)
-        self._check(_lib.lib().dbat_normal_step(self._h, _lib.dptr(x), float(lam), int(jacobi),
+        flags = int(jacobi) | (2 if trial else 0) | (4 if accept else 0)
+        self._check(_lib.lib().dbat_normal_step(self._h, _lib.dptr(xa), float(lam), flags,
                                                 _lib.dptr(p), _lib.dptr(st)))
-        return p, dict(f=st[0], jp2=st[1], rjp=st[2], singular=bool(st[3]), launches=int(st[4]))
+        return p, dict(f=st[0], jp2=st[1], rjp=st[2], singular=bool(st[3]), launches=int(st[4]),
+                       f_new=st[5], device_ms=st[6])
 
     def phase_times(self):
         names = (C.c_char_p * 16)()

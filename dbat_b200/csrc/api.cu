@@ -30,9 +30,9 @@ static std::string g_create_err;
     } while (0)
 
 enum { SC_RR = 0, SC_JP2 = 1, SC_RJP = 2, SC_TRACE = 3, SC_A = 4, SC_B = 5, SC_C = 6, SC_PRR = 7, SC_N = 16 };
-enum { PH_EVAL = 0, PH_SCHUR, PH_CHOL, PH_SOLVE, PH_TRIAL, PH_JP, PH_N };
+enum { PH_EVAL = 0, PH_SCHUR, PH_CHOL, PH_SOLVE, PH_TRIAL, PH_JP, PH_TOTAL, PH_N };
 static const char* kPhaseNames[PH_N] = {"eval_jac_assembly", "build_schur", "cholesky", "solve_backsub",
-                                        "trial_residual", "jp_stats"};
+                                        "trial_residual", "jp_stats", "total"};
 
 // --------------------------------------------------------------------------------------------
 // NCCL through dlopen (torch ships libnccl.so.2; no link-time dependency)
@@ -340,7 +340,7 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     { auto v = to_int(d->OPdes_src, d->nOPdes, false); UP(h->d_OPsrc, v); }
     { auto v = to_int(d->OPdes_dest, d->nOPdes, true); UP(h->d_OPdst, v); }
     UP(h->d_img_chunk_start, img_chunk_start); UP(h->d_col2pt, col2pt);
-    P.ldS = std::max(128, ((nC + 127) / 128) * 128);
+    P.ldS = std::max(128, ((nC + 1 + 127) / 128) * 128);   // >= 1 padding row: carries the rhs (chol_put_rhs)
     AL(P.chunkG, (size_t)std::max(1, P.nChunks) * DBAT_GSZ);
     AL(P.imgG, (size_t)nImg * DBAT_GSZ);
     AL(P.shG, DBAT_GSZ);
@@ -413,14 +413,18 @@ static int eval_full(dbat_handle* h) {
     launch_cam_side(h->P, h->d_img_chunk_start, h->d_tmpG, h->st);
     launch_point_side(h->P, h->st);
     launch_prior_apply(h->P, h->d_x, h->d_camDiag, h->d_camG, h->d_col2pt, h->st);
-    if (h->nranks > 1) {
-        int rc = allreduce(h, h->P.imgG, (size_t)h->P.nImg * DBAT_GSZ);
-        if (!rc) rc = allreduce(h, h->P.shG, DBAT_GSZ);
-        if (rc) return rc;
-    }
     // r'r = Gram(r,r) + prior rows
     static double hG[DBAT_GSZ];
     launch_prior_rr(h->P, h->d_x, h->d_partial, h->d_scal, SC_PRR, h->st);
+    if (h->nranks > 1) {
+        // camera-side sums are partial per rank (each rank holds a subset of the points)
+        int rc = allreduce(h, h->P.imgG, (size_t)h->P.nImg * DBAT_GSZ);
+        if (!rc) rc = allreduce(h, h->P.shG, DBAT_GSZ);
+        if (!rc) rc = allreduce(h, h->d_camDiag, h->P.nC);
+        if (!rc) rc = allreduce(h, h->d_camG, h->P.nC);
+        if (!rc) rc = allreduce(h, h->d_scal + SC_PRR, 1);
+        if (rc) return rc;
+    }
     cudaMemcpyAsync(hG, h->P.shG, sizeof(double) * DBAT_GSZ, cudaMemcpyDeviceToHost, h->st);
     cudaMemcpyAsync(h->h_scal + SC_PRR, h->d_scal + SC_PRR, sizeof(double), cudaMemcpyDeviceToHost, h->st);
     ph_end(h, PH_EVAL, a);
@@ -461,7 +465,20 @@ static int eval_jp(dbat_handle* h, const double* v, double* jp2, double* rjp) {
     return 0;
 }
 
+// dot product of two vectors in x layout.  With several ranks the camera part [0,nC) is
+// replicated and the point part [nC,n) is distributed (zero outside the owned columns).
 static int dev_dot(dbat_handle* h, const double* a, const double* b, int n, double* out) {
+    if (h->nranks > 1 && n == h->P.n) {
+        const int nC = h->P.nC;
+        launch_dot(a, b, nC, h->d_partial, h->d_scal, SC_A, h->st);
+        launch_dot(a + nC, b ? b + nC : nullptr, n - nC, h->d_partial, h->d_scal, SC_B, h->st);
+        int rc = allreduce(h, h->d_scal + SC_B, 1);
+        if (rc) return rc;
+        cudaMemcpyAsync(h->h_scal + SC_A, h->d_scal + SC_A, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+        if (cudaStreamSynchronize(h->st) != cudaSuccess) { h->err = "dot failed"; return DBAT_E_CUDA; }
+        *out = h->h_scal[SC_A] + h->h_scal[SC_B];
+        return 0;
+    }
     launch_dot(a, b, n, h->d_partial, h->d_scal, SC_A, h->st);
     cudaMemcpyAsync(h->h_scal + SC_A, h->d_scal + SC_A, sizeof(double), cudaMemcpyDeviceToHost, h->st);
     if (cudaStreamSynchronize(h->st) != cudaSuccess) { h->err = "dot failed"; return DBAT_E_CUDA; }
@@ -493,10 +510,10 @@ static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, 
     }
     ph_end(h, PH_SCHUR, a);
     a = ph_begin(h);
+    chol_put_rhs(h->chol, P.S, P.rhs, h->st);
     chol_factor(h->chol, P.S, h->st);
     ph_end(h, PH_CHOL, a);
     a = ph_begin(h);
-    cudaMemcpyAsync(h->d_pc, P.rhs, sizeof(double) * P.ldS, cudaMemcpyDeviceToDevice, h->st);
     chol_solve(h->chol, P.S, h->d_pc, h->st);
     if (jacobi) launch_mul(h->d_pc, h->d_dscale, h->d_pc, P.nC, h->st);
     launch_backsub(P, lambda, h->d_pc, pout, h->st);
@@ -604,23 +621,38 @@ extern "C" int dbat_jacobian_csc(dbat_handle* h, int weighted, int64_t* Jc, int6
     return DBAT_OK;
 }
 
-extern "C" int dbat_normal_step(dbat_handle* h, const double* x, double lambda, int jacobi_scale, double* p,
+extern "C" int dbat_normal_step(dbat_handle* h, const double* x, double lambda, int flags, double* p,
                                 double* stats) {
+    // flags: bit0 Jacobi scaling, bit1 also evaluate the trial point x+p, bit2 accept it when f decreases
     if (!h) return DBAT_E_BADARG;
-    if (x) { CK(cudaMemcpyAsync(h->d_x, x, sizeof(double) * h->P.n, cudaMemcpyHostToDevice, h->st)); h->cscWeighted = -1; }
     ph_reset(h);
+    const size_t tot = ph_begin(h);
+    if (x) { CK(cudaMemcpyAsync(h->d_x, x, sizeof(double) * h->P.n, cudaMemcpyHostToDevice, h->st)); h->cscWeighted = -1; }
     const int64_t l0 = g_dbat_launches;
     int rc = eval_full(h);
     if (rc) return rc;
+    const double f = 0.5 * h->h_scal[SC_RR];
     int sing = 0;
-    rc = solve_step(h, lambda, jacobi_scale != 0, h->d_p, &sing);
+    rc = solve_step(h, lambda, (flags & 1) != 0, h->d_p, &sing);
     if (rc) return rc;
-    double jp2 = 0, rjp = 0;
+    double jp2 = 0, rjp = 0, fNew = NAN;
     rc = eval_jp(h, h->d_p, &jp2, &rjp);
     if (rc) return rc;
     if (p) CK(cudaMemcpyAsync(p, h->d_p, sizeof(double) * h->P.n, cudaMemcpyDeviceToHost, h->st));
+    if (flags & 2) {
+        launch_axpy(1.0, h->d_p, h->d_x, h->d_t, h->P.n, h->st);
+        double rrT = 0;
+        rc = eval_rr(h, h->d_t, &rrT);
+        if (rc) return rc;
+        fNew = 0.5 * rrT;
+        if ((flags & 4) && fNew < f) { std::swap(h->d_x, h->d_t); h->params_valid = true; h->normal_valid = false; h->cscWeighted = -1; }
+    }
+    ph_end(h, PH_TOTAL, tot);
     ph_collect(h);
-    if (stats) { stats[0] = 0.5 * h->h_scal[SC_RR]; stats[1] = jp2; stats[2] = rjp; stats[3] = sing; stats[4] = (double)(g_dbat_launches - l0); }
+    if (stats) {
+        stats[0] = f; stats[1] = jp2; stats[2] = rjp; stats[3] = sing; stats[4] = (double)(g_dbat_launches - l0);
+        stats[5] = fNew; stats[6] = h->phase_ms[PH_TOTAL];
+    }
     return DBAT_OK;
 }
 
@@ -683,6 +715,7 @@ static bool structurally_deficient(dbat_handle* h) {
 }
 
 static int trace_sum(dbat_handle* h, double* tr) {
+    cudaMemsetAsync(h->d_diagN, 0, sizeof(double) * h->P.n, h->st);
     launch_diag(h->P, h->d_camDiag, h->d_diagN, h->st);
     return dev_dot(h, h->d_diagN, nullptr, h->P.n, tr);
 }
@@ -830,6 +863,7 @@ static int solve_lmp(dbat_handle* h, const dbat_opts* o, dbat_result* res, Trace
             step = 0;
         } else {
             int nt = std::max(std::max(3 * P.nOP, 6 * P.nImg), DBAT_NSLOT);
+            cudaMemsetAsync(h->d_g, 0, sizeof(double) * nn, h->st);
             k_gradient<<<(nt + 255) / 256, 256, 0, h->st>>>(P, h->d_camG, h->d_g); count_launch();
             double gg = 0, jg2 = 0, dummy = 0;
             if ((rc = dev_dot(h, h->d_g, h->d_g, nn, &gg))) return rc;

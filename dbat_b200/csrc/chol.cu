@@ -119,61 +119,157 @@ static void gemm_nt(const double* A, int lda, const double* B, int ldb, double* 
 }
 
 // Cholesky of one 128x128 diagonal block in shared memory + inverse of its factor.
-// One thread per row.  L lives in the lower triangle of As; inv(L)' is built in the strictly
-// upper triangle of the same buffer (its diagonal in dg[]), so one 132 KB tile suffices.
+// 256 threads, left-looking over 16-column panels:  (1) panel -= L(:,0:c0) L(panel,0:c0)'
+// (2) warp 0 factors the 16x16 diagonal block  (3) one thread per row solves the rows below.
+// inv(L) is then built block-wise (16x16 blocks, all blocks of one sub-diagonal in parallel)
+// into the strictly upper triangle of the same tile (transposed), its diagonal in dg[].
 #define PLD 129
-__global__ void __launch_bounds__(128, 1)
-k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, int* __restrict__ info,
-           double* __restrict__ minmax) {
+#define PB 16
+__global__ void __launch_bounds__(256, 1)
+k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, int nvalid,
+           int* __restrict__ info, double* __restrict__ minmax) {
     extern __shared__ __align__(16) double sm[];
     double* As = sm;                    // [128][PLD] row-major
     double* dg = sm + NB * PLD;         // [128] diagonal of inv(L)
-    const int i = threadIdx.x;
-    for (int c = 0; c < NB; ++c) As[i * PLD + c] = (c <= i) ? A[(size_t)c * lda + i] : 0.0;
-    __syncthreads();
-    bool bad = false;
-    double dmin = 1e300, dmax = 0.0;
-    for (int j = 0; j < NB; ++j) {
-        const double d = As[j * PLD + j];
-        if (!(d > 0.0)) bad = true;
-        const double l = sqrt(d);
-        dmin = fmin(dmin, l); dmax = fmax(dmax, l);
-        double lij = 0.0;
-        if (i > j) { lij = As[i * PLD + j] / l; As[i * PLD + j] = lij; }
-        __syncthreads();
-        if (i == j) As[j * PLD + j] = l;
-        if (i > j) {
-            double* row = As + i * PLD;
-#pragma unroll 4
-            for (int c = j + 1; c <= i; ++c) row[c] -= lij * As[c * PLD + j];
-        }
-        __syncthreads();
-    }
-    if (i == 0) {
-        if (bad) atomicCAS(info, 0, blk + 1);
-        double omin = minmax[0], omax = minmax[1];
-        if (blk == 0) { omin = dmin; omax = dmax; }
-        minmax[0] = fmin(omin, dmin); minmax[1] = fmax(omax, dmax);
-    }
-    // write L back (lower triangle)
-    for (int c = 0; c <= i; ++c) A[(size_t)c * lda + i] = As[i * PLD + c];
-    // X = inv(L): thread c owns column c of X, stored transposed in row c (upper part) of As
+    double* rd = dg + NB;               // [16] reciprocal pivots of the current panel
+    double* Tb = rd + PB;               // [7][16][17] scratch for the inverse
+    __shared__ int s_bad;
+    __shared__ double s_min, s_max;
+    const int t = threadIdx.x;
     {
-        const int c = i;
-        double xdiag = 0.0;
-        for (int r = c; r < NB; ++r) {
-            double s = (r == c) ? 1.0 : 0.0;
-            const double* Lr = As + r * PLD;
-            for (int k = c; k < r; ++k) s -= Lr[k] * (k == c ? xdiag : As[c * PLD + k]);
-            const double v = s / Lr[r];
-            if (r == c) xdiag = v; else As[c * PLD + r] = v;
+        const int i = t & 127, h = t >> 7;
+        for (int c = h * 64; c < h * 64 + 64; ++c) As[i * PLD + c] = (c <= i) ? A[(size_t)c * lda + i] : 0.0;
+    }
+    if (t == 0) { s_bad = 0; s_min = 1e300; s_max = 0.0; }
+    __syncthreads();
+    for (int c0 = 0; c0 < NB; c0 += PB) {
+        if (c0 > 0) {                                   // (1) left-looking update of the panel
+            const int i = t & 127, h = t >> 7;
+            if (i >= c0) {
+                double acc[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc[q] = 0.0;
+                const double* Li = As + i * PLD;
+                const double* Lj = As + (c0 + 8 * h) * PLD;
+#pragma unroll 4
+                for (int k = 0; k < c0; ++k) {
+                    const double a = Li[k];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) acc[q] += a * Lj[q * PLD + k];
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int j = c0 + 8 * h + q;
+                    if (j <= i) As[i * PLD + j] -= acc[q];
+                }
+            }
         }
-        dg[c] = xdiag;
+        __syncthreads();
+        if (t < 32) {                                   // (2) 16x16 diagonal block, lane = row
+            const int r = t & 15;
+            const bool act = t < 16;
+            for (int j = 0; j < PB; ++j) {
+                const double d = As[(c0 + j) * PLD + c0 + j];
+                const double l = sqrt(d);
+                if (t == 0) {
+                    if (!(d > 0.0)) s_bad = 1;
+                    if (blk * NB + c0 + j < nvalid) { s_min = fmin(s_min, l); s_max = fmax(s_max, l); }
+                    rd[j] = 1.0 / l;
+                }
+                __syncwarp();
+                double lrj = 0.0;
+                if (act && r > j) { lrj = As[(c0 + r) * PLD + c0 + j] / l; As[(c0 + r) * PLD + c0 + j] = lrj; }
+                if (act && r == j) As[(c0 + j) * PLD + c0 + j] = l;
+                __syncwarp();
+                if (act && r > j)
+                    for (int c = j + 1; c <= r; ++c) As[(c0 + r) * PLD + c0 + c] -= lrj * As[(c0 + c) * PLD + c0 + j];
+                __syncwarp();
+            }
+        }
+        __syncthreads();
+        if (t < NB && t >= c0 + PB) {                   // (3) rows below: row * inv(L_dd)'
+            double* row = As + t * PLD + c0;
+            double x[PB];
+#pragma unroll
+            for (int j = 0; j < PB; ++j) {
+                double s = row[j];
+                const double* Lj = As + (c0 + j) * PLD + c0;
+#pragma unroll
+                for (int k = 0; k < j; ++k) s -= x[k] * Lj[k];
+                x[j] = s * rd[j];
+            }
+#pragma unroll
+            for (int j = 0; j < PB; ++j) row[j] = x[j];
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        if (s_bad) atomicCAS(info, 0, blk + 1);
+        double omin = minmax[0], omax = minmax[1];
+        if (blk == 0) { omin = 1e300; omax = 0.0; }
+        minmax[0] = fmin(omin, s_min); minmax[1] = fmax(omax, s_max);
+    }
+    {   // write L back (lower triangle): thread pair per row
+        const int i = t & 127, h = t >> 7;
+        for (int c = h * 64; c < h * 64 + 64; ++c) if (c <= i) A[(size_t)c * lda + i] = As[i * PLD + c];
+    }
+    // ---- inverse.  X(r,c), r>c is stored at As[c][r]; X(c,c) in dg[c].
+    if (t < NB) {                                       // 16x16 diagonal blocks: thread = column
+        const int b0 = (t >> 4) * PB, c = t & 15;
+        double x[PB];
+#pragma unroll
+        for (int r = 0; r < PB; ++r) {
+            double s = (r == c) ? 1.0 : 0.0;
+            const double* Lr = As + (b0 + r) * PLD + b0;
+#pragma unroll
+            for (int k = 0; k < r; ++k) if (k >= c) s -= Lr[k] * x[k];
+            x[r] = (r >= c) ? s / Lr[r] : 0.0;
+        }
+        dg[b0 + c] = x[c];
+#pragma unroll
+        for (int r = 0; r < PB; ++r) if (r > c) As[(b0 + c) * PLD + b0 + r] = x[r];
     }
     __syncthreads();
+    const int ti = t >> 4, tj = t & 15;
+    auto Xat = [&](int r, int c) -> double {            // X(r,c) for r>=c
+        return (r > c) ? As[c * PLD + r] : dg[c];
+    };
+    for (int d = 1; d < NB / PB; ++d) {                 // sub-diagonal d: blocks (jb+d, jb)
+        const int nblk = NB / PB - d;
+        for (int q = 0; q < nblk; ++q) {
+            const int jb = q, ib = q + d;
+            double s = 0.0;
+            const double* Li = As + (ib * PB + ti) * PLD;
+            // kb = jb: X block is lower triangular (k >= j)
+            {
+                const int kb0 = jb * PB, j = jb * PB + tj;
+#pragma unroll
+                for (int k = 0; k < PB; ++k) if (k >= tj) s += Li[kb0 + k] * Xat(kb0 + k, j);
+            }
+            for (int kb = jb + 1; kb < ib; ++kb) {
+                const int kb0 = kb * PB;
+                const double* Xc = As + (jb * PB + tj) * PLD + kb0;   // X(kb0+k, j) = As[j][kb0+k]
+#pragma unroll
+                for (int k = 0; k < PB; ++k) s += Li[kb0 + k] * Xc[k];
+            }
+            Tb[(q * PB + ti) * 17 + tj] = s;
+        }
+        __syncthreads();
+        for (int q = 0; q < nblk; ++q) {
+            const int jb = q, ib = q + d, i0 = ib * PB;
+            double s = 0.0;
+#pragma unroll
+            for (int m = 0; m < PB; ++m) if (m <= ti) s += Xat(i0 + ti, i0 + m) * Tb[(q * PB + m) * 17 + tj];
+            As[(jb * PB + tj) * PLD + i0 + ti] = -s;    // X(i0+ti, jb*PB+tj)
+        }
+        __syncthreads();
+    }
     double* out = invL + (size_t)blk * NB * NB;          // column-major 128x128, lower triangular
-    for (int cc = 0; cc < NB; ++cc)
-        out[(size_t)cc * NB + i] = (i > cc) ? As[cc * PLD + i] : (i == cc ? dg[cc] : 0.0);
+    {
+        const int i = t & 127, h = t >> 7;
+        for (int cc = h * 64; cc < h * 64 + 64; ++cc)
+            out[(size_t)cc * NB + i] = (i > cc) ? As[cc * PLD + i] : (i == cc ? dg[cc] : 0.0);
+    }
 }
 
 void chol_alloc(CholWork& w, int n, int ld) {
@@ -191,13 +287,13 @@ void chol_free(CholWork& w) {
 
 void chol_factor(CholWork& w, double* A, cudaStream_t st) {
     static bool attr = false;
-    const int psmem = (NB * PLD + NB) * 8;
+    const int psmem = (NB * PLD + NB + PB + 7 * PB * 17) * 8;
     if (!attr) { cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem); attr = true; }
     cudaMemsetAsync(w.info, 0, sizeof(int), st);
     const int ld = w.ld, nb = w.nb;
     for (int k = 0; k < nb; ++k) {
         double* Akk = A + (size_t)k * NB * ld + (size_t)k * NB;
-        k_potrf128<<<1, 128, psmem, st>>>(Akk, ld, w.invL, k, w.info, w.minmax);
+        k_potrf128<<<1, 256, psmem, st>>>(Akk, ld, w.invL, k, w.n, w.info, w.minmax);
         count_launch();
         const int rem = nb - k - 1;
         if (rem <= 0) break;
@@ -211,71 +307,95 @@ void chol_factor(CholWork& w, double* A, cudaStream_t st) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// triangular solves with the blocked factor (uses the stored inverses of the diagonal blocks)
+// triangular solves.  The forward substitution is folded into the factorisation: the caller
+// stores rhs' in the last (padding) row of A with a huge diagonal entry, so after chol_factor
+// that row holds y' = (L^-1 rhs)'.  Only the backward substitution L'x = y remains.
 // ---------------------------------------------------------------------------------------------
-// forward step k: CTA r handles row block k+r.  y_k = invL_kk * b_k ; r==0 stores y_k, else
-// b_i -= L_ik y_k.
-__global__ void __launch_bounds__(128) k_fwd_step(const double* __restrict__ A, int ld,
-                                                   const double* __restrict__ invL, int k,
-                                                   double* __restrict__ b, double* __restrict__ y) {
-    __shared__ double bk[NB], yk[NB];
-    const int t = threadIdx.x;
-    bk[t] = b[(size_t)k * NB + t];
-    __syncthreads();
-    const double* iL = invL + (size_t)k * NB * NB;
-    double s = 0.0;
-    for (int c = 0; c <= t; ++c) s += iL[(size_t)c * NB + t] * bk[c];      // lower triangular
-    // (loop bound differs per thread; reads stay coalesced across t for each c)
-    yk[t] = s;
-    __syncthreads();
-    const int i = k + blockIdx.x;
-    if (blockIdx.x == 0) { y[(size_t)k * NB + t] = s; return; }
-    const double* Lik = A + (size_t)k * NB * ld + (size_t)i * NB;
-    double u = 0.0;
-#pragma unroll 8
-    for (int c = 0; c < NB; ++c) u += Lik[(size_t)c * ld + t] * yk[c];
-    b[(size_t)i * NB + t] -= u;
+__global__ void k_put_rhs_row(double* __restrict__ A, int ld, const double* __restrict__ rhs, int n) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n) A[(size_t)c * ld + ld - 1] = rhs[c];
+    if (c == 0) A[(size_t)(ld - 1) * ld + ld - 1] = 1e300;
 }
-// backward step k: x_k = invL_kk' * y_k ; CTA j<k: y_j -= L_kj' x_k ; CTA j==k stores x_k.
+__global__ void k_get_y_row(const double* __restrict__ A, int ld, double* __restrict__ y, int n) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < ld) y[c] = (c < n) ? A[(size_t)c * ld + ld - 1] : 0.0;
+}
+void chol_put_rhs(const CholWork& w, double* A, const double* rhs, cudaStream_t st) {
+    k_put_rhs_row<<<(w.n + 255) / 256, 256, 0, st>>>(A, w.ld, rhs, w.n);
+    count_launch();
+}
+
+// out[c] (c = 0..127) = sum_r M[r + c*ldm] * v[r], M 128x128 column-major.  256 threads.
+// Each warp owns 16 columns and processes them 4 at a time (16 independent loads in flight).
+__device__ __forceinline__ void tmatvec128(const double* __restrict__ M, size_t ldm, const double* v_sm,
+                                           double* out_sm) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double v[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = v_sm[lane + 32 * i];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+        double s[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double* col = M + (size_t)(warp * 16 + g * 4 + q) * ldm;
+            s[q] = col[lane] * v[0] + col[lane + 32] * v[1] + col[lane + 64] * v[2] + col[lane + 96] * v[3];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out_sm[warp * 16 + g * 4 + q] = s[q];
+        }
+    }
+}
+// x_last = invL_last' * y_last
+__global__ void __launch_bounds__(256) k_bwd_first(const double* __restrict__ invL, int k,
+                                                    const double* __restrict__ y, double* __restrict__ x) {
+    __shared__ double v[NB], o[NB];
+    if (threadIdx.x < NB) v[threadIdx.x] = y[(size_t)k * NB + threadIdx.x];
+    __syncthreads();
+    tmatvec128(invL + (size_t)k * NB * NB, NB, v, o);
+    __syncthreads();
+    if (threadIdx.x < NB) x[(size_t)k * NB + threadIdx.x] = o[threadIdx.x];
+}
+// step k: CTA j<k: y_j -= L_kj' x_k ; the CTA of block k-1 then forms x_{k-1} = invL_{k-1}' y_{k-1}
 __global__ void __launch_bounds__(256) k_bwd_step(const double* __restrict__ A, int ld,
                                                    const double* __restrict__ invL, int k,
                                                    double* __restrict__ y, double* __restrict__ x) {
-    __shared__ double yk[NB], xk[NB];
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    if (t < NB) yk[t] = y[(size_t)k * NB + t];
+    __shared__ double v[NB], o[NB];
+    const int t = threadIdx.x, j = blockIdx.x;
+    if (t < NB) v[t] = x[(size_t)k * NB + t];
     __syncthreads();
-    const double* iL = invL + (size_t)k * NB * NB;
-    for (int c = warp; c < NB; c += 8) {                  // x_k[c] = sum_t invL[t][c] y_k[t], t>=c
-        double s = 0.0;
-        for (int r = lane; r < NB; r += 32) s += iL[(size_t)c * NB + r] * yk[r];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) xk[c] = s;
-    }
+    tmatvec128(A + (size_t)j * NB * ld + (size_t)k * NB, (size_t)ld, v, o);
     __syncthreads();
-    const int j = blockIdx.x;                             // 0..k
-    if (j == k) { if (t < NB) x[(size_t)k * NB + t] = xk[t]; return; }
-    const double* Lkj = A + (size_t)j * NB * ld + (size_t)k * NB;
-    for (int c = warp; c < NB; c += 8) {
-        double s = 0.0;
-        for (int r = lane; r < NB; r += 32) s += Lkj[(size_t)c * ld + r] * xk[r];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) y[(size_t)j * NB + c] -= s;
-    }
+    double yj = 0.0;
+    if (t < NB) { yj = y[(size_t)j * NB + t] - o[t]; y[(size_t)j * NB + t] = yj; }
+    if (j != k - 1) return;
+    __syncthreads();
+    if (t < NB) v[t] = yj;
+    __syncthreads();
+    tmatvec128(invL + (size_t)j * NB * NB, NB, v, o);
+    __syncthreads();
+    if (t < NB) x[(size_t)j * NB + t] = o[t];
 }
 
 static double* g_solve_tmp = nullptr;
 static int g_solve_tmp_n = 0;
-void chol_solve(const CholWork& w, const double* A, double* b, cudaStream_t st) {
+// After chol_factor on a matrix prepared with chol_put_rhs: x (length ld) = A^-1 rhs.
+void chol_solve(const CholWork& w, const double* A, double* x, cudaStream_t st) {
     if (g_solve_tmp_n < w.ld) {
         if (g_solve_tmp) cudaFree(g_solve_tmp);
         cudaMalloc(&g_solve_tmp, sizeof(double) * w.ld);
         g_solve_tmp_n = w.ld;
     }
     double* y = g_solve_tmp;
-    for (int k = 0; k < w.nb; ++k) { k_fwd_step<<<w.nb - k, 128, 0, st>>>(A, w.ld, w.invL, k, b, y); count_launch(); }
-    for (int k = w.nb - 1; k >= 0; --k) { k_bwd_step<<<k + 1, 256, 0, st>>>(A, w.ld, w.invL, k, y, b); count_launch(); }
+    k_get_y_row<<<(w.ld + 255) / 256, 256, 0, st>>>(A, w.ld, y, w.n);
+    k_bwd_first<<<1, 256, 0, st>>>(w.invL, w.nb - 1, y, x);
+    count_launch(2);
+    for (int k = w.nb - 1; k >= 1; --k) { k_bwd_step<<<k, 256, 0, st>>>(A, w.ld, w.invL, k, y, x); count_launch(); }
 }
 
 // ---------------------------------------------------------------------------------------------

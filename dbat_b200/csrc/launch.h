@@ -48,7 +48,10 @@ void chol_free(CholWork& w);
 // In-place lower Cholesky of the ld x ld column-major matrix A (rows/cols >= n are padding and
 // must hold the identity).  Asynchronous; read w.info afterwards.
 void chol_factor(CholWork& w, double* A, cudaStream_t st);
-// Solve L L' x = b in place (b length ld, padding entries ignored).
-void chol_solve(const CholWork& w, const double* A, double* b, cudaStream_t st);
+// Store rhs' in the last padding row of A (before chol_factor): the forward substitution then
+// happens inside the factorisation.  Requires ld > n.
+void chol_put_rhs(const CholWork& w, double* A, const double* rhs, cudaStream_t st);
+// After chol_factor on a matrix prepared with chol_put_rhs: x (length ld) = A^-1 rhs.
+void chol_solve(const CholWork& w, const double* A, double* x, cudaStream_t st);
 // Z = inv(L) (lower) into Zout (ld x ld); then C = Z'Z (= inv(A)) full symmetric into Cout.
 void chol_inverse(const CholWork& w, const double* A, double* Z, double* C, cudaStream_t st);

@@ -104,20 +104,31 @@ def make_scene(nImg=1000, nOP=200000, rays=10, seed=SEED, noise_px=0.5, start_no
             take[b0:b0 + 100000] = ok & (np.cumsum(ok, axis=1) <= rays)
         return idx, take
 
-    mrg = 0.0
-    OP = np.empty((3, nOP))
-    idx = np.empty((nOP, kq), dtype=np.int64)
-    take = np.zeros((nOP, kq), dtype=bool)
-    bad = np.arange(nOP)
-    for _ in range(1000):                              # rejection sampling: exactly `rays` rays per point
-        OP[0:2, bad] = rng.uniform(-mrg, L + mrg, (2, len(bad)))
-        OP[2, bad] = rng.uniform(0, 30, len(bad))
-        idx[bad], take[bad] = visible(OP.T[bad])
-        bad = bad[take[bad].sum(axis=1) < rays]
-        if len(bad) == 0:
-            break
-    else:
+    def place():
+        OP = np.empty((3, nOP))
+        idx = np.empty((nOP, kq), dtype=np.int64)
+        take = np.zeros((nOP, kq), dtype=bool)
+        bad = np.arange(nOP)
+        for _ in range(1000):                          # rejection sampling: exactly `rays` rays per point
+            OP[0:2, bad] = rng.uniform(0, L, (2, len(bad)))
+            OP[2, bad] = rng.uniform(0, 30, len(bad))
+            idx[bad], take[bad] = visible(OP.T[bad])
+            bad = bad[take[bad].sum(axis=1) < rays]
+            if len(bad) == 0:
+                return OP, idx, take
         raise RuntimeError('could not place all object points')
+
+    min_obs = min(20, max(4, (rays * nOP) // (4 * nImg)))
+    for attempt in range(8):                           # stations that end up starved look straight down
+        OP, idx, take = place()
+        cnt = np.bincount(idx[take], minlength=nImg)
+        starved = np.flatnonzero(cnt < min_obs)
+        if len(starved) == 0:
+            break
+        EO[3:5, starved] *= 0.25
+        M = _rot(EO[3:6])
+    else:
+        raise RuntimeError('some stations see too few points')
     pj, slot = np.nonzero(take)
     ip_op = pj
     ip_img = idx[pj, slot]

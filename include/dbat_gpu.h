@@ -137,8 +137,12 @@ int  dbat_solve(dbat_handle *h, int method, const dbat_opts *opts, const double 
 
 /* One pass of the hot path at x without optimiser logic (bench + tests):
  * residual+Jacobian+assembly, Schur with damping lambda, Cholesky, back-substitution.
- * p (n) receives the step; stats[0]=f=1/2 r'r, [1]=|Jp|^2 placeholder, [2]=trace(J'J). */
-int dbat_normal_step(dbat_handle *h, const double *x, double lambda, int jacobi_scale,
+ * x == NULL reuses the device-resident iterate; p (n, may be NULL) receives the step.
+ * flags: bit0 Jacobi column scaling, bit1 also evaluate the trial point x+p, bit2 accept the
+ * trial point when f decreases (one Levenberg-Marquardt iteration).
+ * stats (8 doubles): [0] f=1/2 r'r, [1] |Jp|^2, [2] r'Jp, [3] singular flag, [4] kernel
+ * launches, [5] f(x+p) or NaN, [6] device time in ms (CUDA events on the library stream). */
+int dbat_normal_step(dbat_handle *h, const double *x, double lambda, int flags,
                      double *p, double *stats);
 
 /* Posterior covariances from the undamped factorisation at the current x, times s0^2. */

@@ -25,6 +25,9 @@ def bundle(s, damping='gna', maxIter=20, convTol=1e-6, absTerm=False, doTrace=Fa
     if s.bundle.serial is None or s.bundle.deserial is None:         # :156-159
         buildserialindices(s)
     x0 = serialize(s)                                                # :162
+    nOPx = len(s.bundle.serial.OP.dest)                              # ordering hint, see lsa._PERM
+    lsa.set_ordering(np.concatenate([np.arange(len(x0) - nOPx, len(x0)),
+                                     np.arange(len(x0) - nOPx)[::-1]]))
     resFun = lambda x, want_jac=True: brown_euler_cam4(x, s, want_jac)   # :165
     vetoFun = None
     W = buildweightmatrix(s)                                         # :175

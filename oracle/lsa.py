@@ -18,15 +18,34 @@ import scipy.sparse.linalg as spla
 from scipy.sparse.csgraph import structural_rank
 
 
+# Fill-reducing ordering handed to the sparse factorisation.  MATLAB's `\\` lets CHOLMOD pick
+# an AMD ordering; SuperLU's own orderings do poorly on this arrow structure, so bundle()
+# installs the ordering the reference itself uses for its explicit Cholesky,
+# p=[OP;EO;IO] (bundle_cov.m:73-84), which confines the fill to the camera block.
+_PERM = None
+
+
+def set_ordering(perm):
+    global _PERM
+    _PERM = None if perm is None else np.asarray(perm)
+
+
 def _solve_spd(A, b):
     """MATLAB `A\\b` for sparse symmetric A.  Returns (x, singular_flag)."""
     A = sp.csc_matrix(A)
+    perm = _PERM if (_PERM is not None and len(_PERM) == A.shape[0]) else None
     with warnings.catch_warnings():
         warnings.simplefilter('error', spla.MatrixRankWarning)
         try:
-            lu = spla.splu(A, permc_spec='MMD_AT_PLUS_A', diag_pivot_thresh=0.0,
-                           options=dict(SymmetricMode=True))
-            x = lu.solve(b)
+            if perm is not None:
+                lu = spla.splu(A[perm][:, perm].tocsc(), permc_spec='NATURAL', diag_pivot_thresh=0.0,
+                               options=dict(SymmetricMode=True))
+                x = np.empty(len(b))
+                x[perm] = lu.solve(b[perm])
+            else:
+                lu = spla.splu(A, permc_spec='MMD_AT_PLUS_A', diag_pivot_thresh=0.0,
+                               options=dict(SymmetricMode=True))
+                x = lu.solve(b)
         except (RuntimeError, spla.MatrixRankWarning):
             return np.full(len(b), np.nan), True
     if not np.all(np.isfinite(x)):
