@@ -55,7 +55,7 @@ class Result(C.Structure):
 EXPORTS = ['dbat_create', 'dbat_destroy', 'dbat_last_error', 'dbat_num_unknowns',
            'dbat_num_residuals', 'dbat_eval', 'dbat_jacobian_nnz', 'dbat_jacobian_csc',
            'dbat_default_opts', 'dbat_solve', 'dbat_normal_step', 'dbat_cov',
-           'dbat_comm_unique_id', 'dbat_comm_init', 'dbat_phase_times']
+           'dbat_comm_unique_id', 'dbat_comm_init', 'dbat_phase_times', 'dbat_dense_chol_solve']
 
 _lib = None
 
@@ -100,6 +100,8 @@ def lib():
     L.dbat_comm_init.restype = C.c_int
     L.dbat_phase_times.argtypes = [vp, C.POINTER(C.c_char_p), c_dp, c_ip, C.c_int]
     L.dbat_phase_times.restype = C.c_int
+    L.dbat_dense_chol_solve.argtypes = [C.c_int64, c_dp, c_dp, c_dp, c_dp, C.c_int, c_dp]
+    L.dbat_dense_chol_solve.restype = C.c_int
     _lib = L
     return L
 
@@ -124,3 +126,18 @@ class DbatError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__('libdbatgpu error %d: %s' % (code, msg))
         self.code = code
+
+
+def dense_chol_solve(A, b, want_inverse=False, repeat=1):
+    """x = A^-1 b (and optionally A^-1) on the device; returns (x, Ainv or None, ms)."""
+    A = np.asfortranarray(np.asarray(A, dtype=np.float64))
+    n = A.shape[0]
+    b = f64(b)
+    x = np.empty(n)
+    Ainv = np.empty((n, n), order='F') if want_inverse else None
+    ms = C.c_double()
+    rc = lib().dbat_dense_chol_solve(n, A.ctypes.data_as(c_dp), dptr(b), dptr(x),
+                                     Ainv.ctypes.data_as(c_dp) if want_inverse else None, repeat, C.byref(ms))
+    if rc != 0:
+        raise DbatError(rc, lib().dbat_last_error(None).decode())
+    return x, Ainv, ms.value

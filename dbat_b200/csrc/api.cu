@@ -1096,6 +1096,61 @@ __global__ void __launch_bounds__(128) k_cop(DevProblem P, const double* __restr
 }
 
 // --------------------------------------------------------------------------------------------
+// stand-alone access to the dense solver (unit tests, profiling)
+// --------------------------------------------------------------------------------------------
+extern "C" int dbat_dense_chol_solve(int64_t n, const double* A, const double* b, double* x, double* Ainv,
+                                     int repeat, double* ms_out) {
+    if (n <= 0 || !A || !b || !x) return DBAT_E_BADARG;
+    const int ld = std::max(128, (int)((n + 1 + 127) / 128) * 128);
+    double *dA = nullptr, *dA0 = nullptr, *drhs = nullptr, *dx = nullptr, *Z = nullptr, *Cc = nullptr;
+    const size_t sz = sizeof(double) * (size_t)ld * ld;
+    std::vector<double> hA((size_t)ld * ld, 0.0), hb(ld, 0.0);
+    for (int64_t c = 0; c < n; ++c) for (int64_t r = 0; r < n; ++r) hA[(size_t)c * ld + r] = A[(size_t)c * n + r];
+    for (int64_t k = n; k < ld; ++k) hA[(size_t)k * ld + k] = 1.0;
+    for (int64_t k = 0; k < n; ++k) hb[k] = b[k];
+    if (cudaMalloc(&dA, sz) || cudaMalloc(&dA0, sz) || cudaMalloc(&drhs, sizeof(double) * ld) || cudaMalloc(&dx, sizeof(double) * ld)) {
+        g_create_err = "dbat_dense_chol_solve: out of memory"; return DBAT_E_OOM;
+    }
+    cudaMemcpy(dA0, hA.data(), sz, cudaMemcpyHostToDevice);
+    cudaMemcpy(drhs, hb.data(), sizeof(double) * ld, cudaMemcpyHostToDevice);
+    CholWork w; chol_alloc(w, (int)n, ld);
+    cudaStream_t st; cudaStreamCreate(&st);
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int it = 0; it < std::max(1, repeat); ++it) {
+        cudaMemcpyAsync(dA, dA0, sz, cudaMemcpyDeviceToDevice, st);
+        cudaEventRecord(e0, st);
+        chol_put_rhs(w, dA, drhs, st);
+        chol_factor(w, dA, st);
+        chol_solve(w, dA, dx, st);
+        cudaEventRecord(e1, st);
+        cudaStreamSynchronize(st);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms);
+    }
+    int info = 0;
+    cudaMemcpy(&info, w.info, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaMemcpy(hb.data(), dx, sizeof(double) * ld, cudaMemcpyDeviceToHost);
+    for (int64_t k = 0; k < n; ++k) x[k] = hb[k];
+    if (Ainv) {
+        // the inverse needs the plain factor (no rhs row)
+        cudaMemcpyAsync(dA, dA0, sz, cudaMemcpyDeviceToDevice, st);
+        chol_factor(w, dA, st);
+        if (cudaMalloc(&Z, sz) || cudaMalloc(&Cc, sz)) { g_create_err = "out of memory"; return DBAT_E_OOM; }
+        chol_inverse(w, dA, Z, Cc, st);
+        cudaStreamSynchronize(st);
+        cudaMemcpy(hA.data(), Cc, sz, cudaMemcpyDeviceToHost);
+        for (int64_t c = 0; c < n; ++c) for (int64_t r = 0; r < n; ++r) Ainv[(size_t)c * n + r] = hA[(size_t)c * ld + r];
+        cudaFree(Z); cudaFree(Cc);
+    }
+    if (ms_out) *ms_out = best;
+    cudaError_t e = cudaDeviceSynchronize();
+    chol_free(w); cudaFree(dA); cudaFree(dA0); cudaFree(drhs); cudaFree(dx);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
+    if (e != cudaSuccess) { g_create_err = std::string("dbat_dense_chol_solve: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
+    return info != 0 ? DBAT_E_NOTSPD : DBAT_OK;
+}
+
+// --------------------------------------------------------------------------------------------
 // multi-GPU plumbing
 // --------------------------------------------------------------------------------------------
 extern "C" int dbat_comm_unique_id(void* id128) {

@@ -15,7 +15,6 @@
 #define KS 16                 // k-slice per pipeline stage
 #define SLD 136               // smem row stride (doubles): 128 + 8 -> conflict-free fragment loads
 #define GEMM_STAGES 3
-#define GEMM_SMEM (GEMM_STAGES * 2 * KS * SLD * 8)
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -29,44 +28,53 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
 
 // C(tile) = beta*C + alpha * A(rows of tile, 0:K) * B(rows of tile col, 0:K)'
-// tile list: if tri!=0 the 1-D grid enumerates lower-triangular tile pairs (ti>=tj) of an
-// nt x nt tile grid; otherwise blockIdx.x = ti, blockIdx.y = tj.
-__global__ void __launch_bounds__(256, 1)
+// CTA tile 128 x 64 (8 warps as 4 x 2, warp tile 32 x 32), 3-stage cp.async pipeline, two CTAs
+// per SM so that one CTA's C read-modify-write epilogue overlaps the other's main loop.
+// tile list: if tri!=0 the 1-D grid enumerates the tiles (ti, tj) with 64*tj <= 128*ti+127 of the
+// lower triangle; otherwise blockIdx.x = ti (128 rows), blockIdx.y = tj (64 columns).
+#define TN 64
+#define GEMM_SMEM (GEMM_STAGES * KS * (SLD + SLDB) * 8)
+#define SLDB 72               // 64 + 8
+__global__ void __launch_bounds__(256, 2)
 k_gemm_nt(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
           double* __restrict__ C, int ldc, int K, double alpha, double beta, int tri) {
     extern __shared__ __align__(16) double sm[];
     int ti, tj;
     if (tri) {
         const int t = blockIdx.x;
-        ti = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-        while (ti * (ti + 1) / 2 > t) --ti;
-        tj = t - ti * (ti + 1) / 2;
+        ti = (int)((sqrt(4.0 * t + 1.0) - 1.0) * 0.5);
+        while ((ti + 1) * (ti + 2) <= t) ++ti;
+        while (ti * (ti + 1) > t) --ti;
+        tj = t - ti * (ti + 1);
     } else { ti = blockIdx.x; tj = blockIdx.y; }
     const double* Ag = A + (size_t)ti * NB;
-    const double* Bg = B + (size_t)tj * NB;
-    double* Cg = C + (size_t)tj * NB * ldc + (size_t)ti * NB;
+    const double* Bg = B + (size_t)tj * TN;
+    double* Cg = C + (size_t)tj * TN * ldc + (size_t)ti * NB;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp & 3) * 32;      // warp tile origin (rows), 4 warps along M
-    const int wn = (warp >> 2) * 64;     // 2 warps along N
-    double acc[4][8][2];
+    const int wm = (warp & 3) * 32;      // 4 warps along M
+    const int wn = (warp >> 2) * 32;     // 2 warps along N
+    double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
     const int nk = K / KS;
     auto load_stage = [&](int stage, int kt) {
-        double* As = sm + (size_t)stage * 2 * KS * SLD;
+        double* As = sm + (size_t)stage * KS * (SLD + SLDB);
         double* Bs = As + KS * SLD;
-        // 16 k-columns x 128 rows per operand = 1024 chunks of 16 B; 4 per thread per operand
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < 4; ++c) {                      // A: 16 x 128 doubles = 1024 chunks of 16 B
             const int chunk = tid + c * 256;
             const int kk = chunk >> 6, m = (chunk & 63) * 2;
             cp_async16(As + kk * SLD + m, Ag + (size_t)(kt * KS + kk) * lda + m);
-            cp_async16(Bs + kk * SLD + m, Bg + (size_t)(kt * KS + kk) * ldb + m);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {                      // B: 16 x 64 doubles = 512 chunks
+            const int chunk = tid + c * 256;
+            const int kk = chunk >> 5, m = (chunk & 31) * 2;
+            cp_async16(Bs + kk * SLDB + m, Bg + (size_t)(kt * KS + kk) * ldb + m);
         }
     };
 #pragma unroll
@@ -76,45 +84,61 @@ k_gemm_nt(const double* __restrict__ A, int lda, const double* __restrict__ B, i
         __syncthreads();
         if (kt + GEMM_STAGES - 1 < nk) load_stage((kt + GEMM_STAGES - 1) % GEMM_STAGES, kt + GEMM_STAGES - 1);
         cp_async_commit();
-        const double* As = sm + (size_t)(kt % GEMM_STAGES) * 2 * KS * SLD;
+        const double* As = sm + (size_t)(kt % GEMM_STAGES) * KS * (SLD + SLDB);
         const double* Bs = As + KS * SLD;
 #pragma unroll
         for (int k0 = 0; k0 < KS; k0 += 4) {
-            double af[4], bf[8];
+            double af[4], bf[4];
             const double* ap = As + (k0 + (lane & 3)) * SLD + wm + (lane >> 2);
-            const double* bp = Bs + (k0 + (lane & 3)) * SLD + wn + (lane >> 2);
+            const double* bp = Bs + (k0 + (lane & 3)) * SLDB + wn + (lane >> 2);
 #pragma unroll
             for (int i = 0; i < 4; ++i) af[i] = ap[8 * i];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bf[j] = bp[8 * j];
+            for (int j = 0; j < 4; ++j) bf[j] = bp[8 * j];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
     }
     cp_async_wait<0>();
     // epilogue: C fragment (row = lane/4, cols 2*(lane%4)+{0,1}) per 8x8 tile
+    if (beta == 0.0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int r = wm + 8 * i + (lane >> 2);
-            const int c = wn + 8 * j + 2 * (lane & 3);
-            double* p0 = Cg + (size_t)c * ldc + r;
-            double* p1 = p0 + ldc;
-            if (beta == 0.0) { *p0 = alpha * acc[i][j][0]; *p1 = alpha * acc[i][j][1]; }
-            else { *p0 = beta * *p0 + alpha * acc[i][j][0]; *p1 = beta * *p1 + alpha * acc[i][j][1]; }
-        }
+            for (int j = 0; j < 4; ++j) {
+                double* p0 = Cg + (size_t)(wn + 8 * j + 2 * (lane & 3)) * ldc + wm + 8 * i + (lane >> 2);
+                p0[0] = alpha * acc[i][j][0]; p0[ldc] = alpha * acc[i][j][1];
+            }
+    } else {
+        double cv[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const double* p0 = Cg + (size_t)(wn + 8 * j + 2 * (lane & 3)) * ldc + wm + 8 * i + (lane >> 2);
+                cv[i][j][0] = p0[0]; cv[i][j][1] = p0[ldc];
+            }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double* p0 = Cg + (size_t)(wn + 8 * j + 2 * (lane & 3)) * ldc + wm + 8 * i + (lane >> 2);
+                p0[0] = beta * cv[i][j][0] + alpha * acc[i][j][0];
+                p0[ldc] = beta * cv[i][j][1] + alpha * acc[i][j][1];
+            }
+    }
 }
 
+// mt = number of 128-row tiles, nt = number of 128-column blocks (two 64-wide tiles each)
 static void gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc,
                     int mt, int nt, int K, double alpha, double beta, bool tri, cudaStream_t st) {
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM); attr = true; }
     if (mt <= 0 || nt <= 0) return;
-    if (tri) k_gemm_nt<<<mt * (mt + 1) / 2, 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, 1);
-    else     k_gemm_nt<<<dim3(mt, nt), 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, 0);
+    if (tri) k_gemm_nt<<<mt * (mt + 1), 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, 1);
+    else     k_gemm_nt<<<dim3(mt, 2 * nt), 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, 0);
     count_launch();
 }
 
@@ -131,8 +155,8 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
     extern __shared__ __align__(16) double sm[];
     double* As = sm;                    // [128][PLD] row-major
     double* dg = sm + NB * PLD;         // [128] diagonal of inv(L)
-    double* rd = dg + NB;               // [16] reciprocal pivots of the current panel
-    double* Tb = rd + PB;               // [7][16][17] scratch for the inverse
+    double* Xd = dg + NB;               // [16][17] inverse of the current diagonal block
+    double* Tb = Xd + PB * 17;          // [7][16][17] scratch for the inverse
     __shared__ int s_bad;
     __shared__ double s_min, s_max;
     const int t = threadIdx.x;
@@ -165,41 +189,70 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
             }
         }
         __syncthreads();
-        if (t < 32) {                                   // (2) 16x16 diagonal block, lane = row
+        if (t < 32) {                                   // (2) 16x16 diagonal block in registers
+            // lane r (0..15; the upper half-warp mirrors it) holds row r; column j is broadcast
+            // with shuffles, so the 16 elimination steps never touch shared memory.
             const int r = t & 15;
-            const bool act = t < 16;
+            double row[PB];
+#pragma unroll
+            for (int c = 0; c < PB; ++c) row[c] = As[(c0 + r) * PLD + c0 + c];
+#pragma unroll
             for (int j = 0; j < PB; ++j) {
-                const double d = As[(c0 + j) * PLD + c0 + j];
-                const double l = sqrt(d);
+                const double d = __shfl_sync(0xffffffffu, row[j], j);
+                const double l = sqrt(d), inv = 1.0 / l;
                 if (t == 0) {
                     if (!(d > 0.0)) s_bad = 1;
                     if (blk * NB + c0 + j < nvalid) { s_min = fmin(s_min, l); s_max = fmax(s_max, l); }
-                    rd[j] = 1.0 / l;
                 }
-                __syncwarp();
-                double lrj = 0.0;
-                if (act && r > j) { lrj = As[(c0 + r) * PLD + c0 + j] / l; As[(c0 + r) * PLD + c0 + j] = lrj; }
-                if (act && r == j) As[(c0 + j) * PLD + c0 + j] = l;
-                __syncwarp();
-                if (act && r > j)
-                    for (int c = j + 1; c <= r; ++c) As[(c0 + r) * PLD + c0 + c] -= lrj * As[(c0 + c) * PLD + c0 + j];
-                __syncwarp();
+                row[j] = (r == j) ? l : (r > j ? row[j] * inv : 0.0);
+#pragma unroll
+                for (int c = j + 1; c < PB; ++c) {
+                    const double lcj = __shfl_sync(0xffffffffu, row[j], c);
+                    if (r >= c) row[c] -= row[j] * lcj;
+                }
+            }
+            // inverse of the block: lane c builds column c of X = L^-1 by forward substitution,
+            // fetching L(rr,k) from lane rr
+            const int c = r;
+            double x[PB];
+#pragma unroll
+            for (int rr = 0; rr < PB; ++rr) {
+                double sacc = (rr == c) ? 1.0 : 0.0;
+#pragma unroll
+                for (int k = 0; k < rr; ++k) {
+                    const double lrk = __shfl_sync(0xffffffffu, row[k], rr);
+                    if (k >= c) sacc -= lrk * x[k];
+                }
+                const double lrr = __shfl_sync(0xffffffffu, row[rr], rr);
+                x[rr] = (rr >= c) ? sacc / lrr : 0.0;
+            }
+            if (t < PB) {
+#pragma unroll
+                for (int cc = 0; cc < PB; ++cc) if (cc <= r) As[(c0 + r) * PLD + c0 + cc] = row[cc];
+#pragma unroll
+                for (int rr = 0; rr < PB; ++rr) Xd[rr * 17 + c] = x[rr];      // Xd(rr,c), zero above the diagonal
             }
         }
         __syncthreads();
-        if (t < NB && t >= c0 + PB) {                   // (3) rows below: row * inv(L_dd)'
-            double* row = As + t * PLD + c0;
-            double x[PB];
+        if (t < NB && t >= c0 + PB) {                   // (3) rows below: row * inv(L_dd)' = row * Xd'
+            double* rowp = As + t * PLD + c0;
+            double a[PB], o[PB];
+#pragma unroll
+            for (int k = 0; k < PB; ++k) a[k] = rowp[k];
 #pragma unroll
             for (int j = 0; j < PB; ++j) {
-                double s = row[j];
-                const double* Lj = As + (c0 + j) * PLD + c0;
+                double sacc = 0.0;
 #pragma unroll
-                for (int k = 0; k < j; ++k) s -= x[k] * Lj[k];
-                x[j] = s * rd[j];
+                for (int k = 0; k <= j; ++k) sacc += a[k] * Xd[j * 17 + k];
+                o[j] = sacc;
             }
 #pragma unroll
-            for (int j = 0; j < PB; ++j) row[j] = x[j];
+            for (int j = 0; j < PB; ++j) rowp[j] = o[j];
+        }
+        if (t >= NB && t < NB + PB) {                   // keep the block inverse for the X phase
+            const int c = t - NB;
+            dg[c0 + c] = Xd[c * 17 + c];
+            for (int rr = c + 1; rr < PB; ++rr) As[(c0 + c) * PLD + c0 + rr] = Xd[rr * 17 + c];
         }
         __syncthreads();
     }
@@ -214,22 +267,6 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
         for (int c = h * 64; c < h * 64 + 64; ++c) if (c <= i) A[(size_t)c * lda + i] = As[i * PLD + c];
     }
     // ---- inverse.  X(r,c), r>c is stored at As[c][r]; X(c,c) in dg[c].
-    if (t < NB) {                                       // 16x16 diagonal blocks: thread = column
-        const int b0 = (t >> 4) * PB, c = t & 15;
-        double x[PB];
-#pragma unroll
-        for (int r = 0; r < PB; ++r) {
-            double s = (r == c) ? 1.0 : 0.0;
-            const double* Lr = As + (b0 + r) * PLD + b0;
-#pragma unroll
-            for (int k = 0; k < r; ++k) if (k >= c) s -= Lr[k] * x[k];
-            x[r] = (r >= c) ? s / Lr[r] : 0.0;
-        }
-        dg[b0 + c] = x[c];
-#pragma unroll
-        for (int r = 0; r < PB; ++r) if (r > c) As[(b0 + c) * PLD + b0 + r] = x[r];
-    }
-    __syncthreads();
     const int ti = t >> 4, tj = t & 15;
     auto Xat = [&](int r, int c) -> double {            // X(r,c) for r>=c
         return (r > c) ? As[c * PLD + r] : dg[c];
@@ -277,32 +314,60 @@ void chol_alloc(CholWork& w, int n, int ld) {
     cudaMalloc(&w.invL, sizeof(double) * (size_t)w.nb * NB * NB);
     cudaMalloc(&w.info, sizeof(int));
     cudaMalloc(&w.minmax, sizeof(double) * 2);
+    cudaMalloc(&w.panel, sizeof(double) * (size_t)ld * NB);
 }
 void chol_free(CholWork& w) {
     if (w.invL) cudaFree(w.invL);
     if (w.info) cudaFree(w.info);
     if (w.minmax) cudaFree(w.minmax);
+    if (w.panel) cudaFree(w.panel);
     w = CholWork();
 }
 
+static cudaStream_t g_aux = nullptr;
+static cudaEvent_t g_evA = nullptr, g_evB = nullptr;
+
+// Right-looking blocked Cholesky with one step of look-ahead: as soon as block column k+1 has
+// received the update of step k, its potrf + panel solve run on a second stream while the main
+// stream finishes the rest of the trailing update of step k.
 void chol_factor(CholWork& w, double* A, cudaStream_t st) {
     static bool attr = false;
-    const int psmem = (NB * PLD + NB + PB + 7 * PB * 17) * 8;
-    if (!attr) { cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem); attr = true; }
+    const int psmem = (NB * PLD + NB + PB * 17 + 7 * PB * 17) * 8;
+    if (!attr) {
+        cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
+        cudaStreamCreateWithFlags(&g_aux, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&g_evA, cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&g_evB, cudaEventDisableTiming);
+        attr = true;
+    }
     cudaMemsetAsync(w.info, 0, sizeof(int), st);
     const int ld = w.ld, nb = w.nb;
-    for (int k = 0; k < nb; ++k) {
-        double* Akk = A + (size_t)k * NB * ld + (size_t)k * NB;
-        k_potrf128<<<1, 256, psmem, st>>>(Akk, ld, w.invL, k, w.n, w.info, w.minmax);
+    auto diag = [&](int k) { return A + (size_t)k * NB * ld + (size_t)k * NB; };
+    auto panel_step = [&](int k, cudaStream_t s) {        // potrf(k) + L_ik = A_ik inv(L_kk)' (in place)
+        k_potrf128<<<1, 256, psmem, s>>>(diag(k), ld, w.invL, k, w.n, w.info, w.minmax);
         count_launch();
         const int rem = nb - k - 1;
-        if (rem <= 0) break;
-        double* Apanel = Akk + NB;                         // rows below the diagonal block
-        // L_ik = A_ik * inv(L_kk)'   (in place: each CTA reads its whole 128x128 tile first)
-        gemm_nt(Apanel, ld, w.invL + (size_t)k * NB * NB, NB, Apanel, ld, rem, 1, NB, 1.0, 0.0, false, st);
-        // A_ij -= L_ik L_jk'  (lower tiles of the trailing matrix)
-        double* Atrail = A + (size_t)(k + 1) * NB * ld + (size_t)(k + 1) * NB;
-        gemm_nt(Apanel, ld, Apanel, ld, Atrail, ld, rem, rem, NB, -1.0, 1.0, true, st);
+        if (rem <= 0) return;
+        // two CTAs share each 128-row tile (64 columns each), so the product cannot be formed in
+        // place: write it to the panel workspace and copy back
+        gemm_nt(diag(k) + NB, ld, w.invL + (size_t)k * NB * NB, NB, w.panel, ld, rem, 1, NB, 1.0, 0.0, false, s);
+        cudaMemcpy2DAsync(diag(k) + NB, sizeof(double) * ld, w.panel, sizeof(double) * ld,
+                          sizeof(double) * (size_t)rem * NB, NB, cudaMemcpyDeviceToDevice, s);
+    };
+    panel_step(0, st);
+    for (int k = 0; k + 1 < nb; ++k) {
+        const int rem = nb - k - 1;
+        double* Apanel = diag(k) + NB;                     // L(k+1:, k)
+        // (a) block column k+1 of the trailing matrix: A(k+1:, k+1) -= L(k+1:, k) L(k+1, k)'
+        gemm_nt(Apanel, ld, Apanel, ld, diag(k + 1), ld, rem, 1, NB, -1.0, 1.0, false, st);
+        cudaEventRecord(g_evA, st);
+        // (b) look-ahead on the aux stream
+        cudaStreamWaitEvent(g_aux, g_evA, 0);
+        panel_step(k + 1, g_aux);
+        cudaEventRecord(g_evB, g_aux);
+        // (c) the rest of the trailing update: A(k+2:, k+2:) -= L(k+2:, k) L(k+2:, k)'  (lower tiles)
+        if (rem > 1) gemm_nt(Apanel + NB, ld, Apanel + NB, ld, diag(k + 2), ld, rem - 1, rem - 1, NB, -1.0, 1.0, true, st);
+        cudaStreamWaitEvent(st, g_evB, 0);
     }
 }
 

@@ -148,6 +148,13 @@ int dbat_normal_step(dbat_handle *h, const double *x, double lambda, int flags,
 /* Posterior covariances from the undamped factorisation at the current x, times s0^2. */
 int dbat_cov(dbat_handle *h, int which, double s0, double *out);
 
+/* The dense solver on its own (unit tests / profiling): x = A^-1 b for a symmetric positive
+ * definite column-major n x n matrix through the same blocked FP64 Cholesky the reduced camera
+ * system uses; Ainv (n x n, may be NULL) receives the explicit inverse used by dbat_cov.
+ * ms_out: best device time of `repeat` factor+solve passes (CUDA events). */
+int dbat_dense_chol_solve(int64_t n, const double *A, const double *b, double *x, double *Ainv,
+                          int repeat, double *ms_out);
+
 /* Multi-GPU: one process per GPU.  unique_id = the 128 bytes of ncclGetUniqueId from
  * rank 0 (dbat_comm_unique_id), distributed by the host plumbing (torch.distributed). */
 int dbat_comm_unique_id(void *id128);

@@ -1,0 +1,135 @@
+"""Pin the CPU oracle against the reference's own golden result files (camcal XML project,
+data/script/camcaldemo/result/* copied into tests/golden/camcaldemo by make_golden.py)."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from camcal_fixture import GOLD, camcal_struct, golden_camera_xml, golden_eo
+from oracle import loaders
+from oracle.bundle import bundle, bundle_cov
+from oracle.cameramodel import brown_euler_cam4
+from oracle.dbatstruct import buildserialindices, serialize
+
+
+@pytest.fixture(scope='module')
+def gna_run():
+    s = camcal_struct('default', seed=1)
+    s, ok, iters, s0, E = bundle(s, 'gna')
+    assert ok
+    return s, iters, s0, E
+
+
+def test_report_numbers(gna_run):
+    """report.txt: 423 params (9 IO, 126 EO, 288 OP), 4148 observations, sigma0 1.6148,
+    last error 98.556, redundancy 3725."""
+    s, iters, s0, E = gna_run
+    rep = open(os.path.join(GOLD, 'result', 'report.txt')).read()
+    assert E.numParams == int(re.search(r'Number of params:\s+(\d+)', rep).group(1)) == 423
+    assert E.numObs == int(re.search(r'Number of observations:\s+(\d+)', rep).group(1)) == 4148
+    assert E.redundancy == int(re.search(r'Redundancy\s+(\d+)', rep).group(1))
+    assert len(s.bundle.serial.IO.dest) == 9 and len(s.bundle.serial.EO.dest) == 126
+    sig = float(re.search(r'Sigma0:\s+([\d.]+)', rep).group(1))
+    assert abs(s0 - sig) < 5e-5
+    last = float(re.search(r'Last error:\s+([\d.]+)', rep).group(1))
+    assert abs(E.res[-1] - last) < 5e-4
+
+
+def test_io_18_digits(gna_run):
+    """result/c4040z.xml: cc, pp, K1-3, P1-2, aspect printed with 18 digits.  The golden run
+    itself stopped at convTol=1e-6, so agreement is limited by its own convergence error."""
+    s, _, _, _ = gna_run
+    gold = loaders.load_camcal_script(GOLD, golden_camera_xml()).IO.val[:, 0]
+    est = s.IO.val[:, 0]
+    np.testing.assert_allclose(est[[0, 1, 2]], gold[[0, 1, 2]], rtol=2e-8)       # cc, px, py
+    np.testing.assert_allclose(est[3], gold[3], rtol=1e-5)                       # aspect
+    np.testing.assert_allclose(est[5:10], gold[5:10], rtol=5e-6)                 # K1-3, P1-2
+
+
+def test_eo_and_posterior_std(gna_run):
+    """result/camera_stations.txt: EO values and posterior std devs (bundle_cov 'CEO')."""
+    s, _, _, E = gna_run
+    ids, EOg, stdg = golden_eo()
+    np.testing.assert_allclose(s.EO.val, EOg, atol=2e-8)
+    CEO = bundle_cov(s, E, 'CEO')
+    sd = np.sqrt(np.diag(CEO)).reshape(6, -1, order='F')
+    # the file prints every std dev multiplied by 180/pi (header: "Unit: degrees")
+    np.testing.assert_allclose(sd * 180 / np.pi, stdg, rtol=1e-6)
+
+
+def test_top_residuals(gna_run):
+    """result/top_residuals.txt: 50 largest image residuals (pixels), 6 printed digits."""
+    s, _, _, _ = gna_run
+    rows = loaders.load_table(os.path.join(GOLD, 'result', 'top_residuals.txt'))
+    idmap = {(int(s.OP.id[j]), int(s.EO.id[i])): k for k, (i, j) in enumerate(zip(s.IP.img, s.IP.op))}
+    for r in rows:
+        k = idmap[(int(r[0]), int(r[1]))]
+        np.testing.assert_allclose(s.post.res.IP[:, k], [float(r[4]), float(r[5])], atol=2e-6)
+
+
+def test_known_answer_residual_at_golden_parameters():
+    """residual formula at the golden IO/EO reproduces the control-point rows
+    of top_residuals.txt (independent of any optimiser)."""
+    s = loaders.load_camcal_script(GOLD, golden_camera_xml())
+    _, EOg, _ = golden_eo()
+    s.EO.val = EOg
+    s.OP.val[:, ~s.prior.OP.isCtrl] = 0.0
+    s.bundle.est.IO[:] = False
+    s.bundle.est.OP[:] = False
+    buildserialindices(s)
+    f, _ = brown_euler_cam4(serialize(s), s, False)
+    res_px = f.reshape(2, -1, order='F') / s.IO.sensor.pxSize[:, s.IP.cam]
+    rows = loaders.load_table(os.path.join(GOLD, 'result', 'top_residuals.txt'))
+    idmap = {(int(s.OP.id[j]), int(s.EO.id[i])): k for k, (i, j) in enumerate(zip(s.IP.img, s.IP.op))}
+    n = 0
+    for r in rows:
+        if int(r[0]) > 1000:
+            k = idmap[(int(r[0]), int(r[1]))]
+            np.testing.assert_allclose(res_px[:, k], [float(r[4]), float(r[5])], atol=2e-6)
+            n += 1
+    assert n >= 30
+
+
+@pytest.mark.parametrize('damping', ['lm', 'lmp'])
+def test_other_dampings_reach_the_same_minimum(gna_run, damping):
+    s, _, s0, E = gna_run
+    s2 = camcal_struct('default', seed=1)
+    s2, ok, _, s02, E2 = bundle(s2, damping)
+    assert ok
+    np.testing.assert_allclose(s02, s0, rtol=1e-9)
+    np.testing.assert_allclose(E2.x, E.x, rtol=1e-6, atol=1e-9)
+
+
+def test_analytic_jacobian_matches_central_differences():
+    """The reference's own unit-test method (private/full_self_test.m, jacapprox.m h=1e-6, thr 1e-8)
+    for all four modular models."""
+    from oracle.cameramodel import res_euler_brown
+    rng = np.random.default_rng(5)
+    m = 5
+    Q = 3 + rng.random((3, m)); ang = rng.random(3) * np.pi / 6; q0 = rng.random(3)
+    f = 1 + rng.random(); u = rng.random((2, m)); K = rng.random(4) * 0.1; P = rng.random(3) * 0.1
+    sz = rng.random() / 10; u0 = rng.random(2); b = rng.random(2) * 0.1
+    for model in range(4):
+        v, d = res_euler_brown(model, Q, q0, ang, f, u, sz, u0, K, P, b, True)
+
+        def num(fun, x0):
+            x0 = np.array(x0, dtype=float)
+            out = []
+            for k in range(x0.size):
+                e = np.zeros(x0.size); e[k] = 1e-6
+                out.append((fun((x0.ravel() + e).reshape(x0.shape)) - fun((x0.ravel() - e).reshape(x0.shape))) / 2e-6)
+            return np.array(out)            # (nparam, 2, m)
+        F = lambda **kw: res_euler_brown(model, kw.get('Q', Q), kw.get('q0', q0), kw.get('ang', ang), kw.get('f', f),
+                                         u, sz, kw.get('u0', u0), kw.get('K', K), kw.get('P', P), kw.get('b', b), False)[0]
+        np.testing.assert_allclose(num(lambda x: F(q0=x), q0), np.transpose(d['dQ0'], (2, 1, 0)), atol=1e-7)
+        np.testing.assert_allclose(num(lambda x: F(ang=x), ang), np.transpose(d['dA'], (2, 1, 0)), atol=1e-7)
+        np.testing.assert_allclose(num(lambda x: F(f=x[0]), [f])[0], d['dF'].T, atol=1e-7)
+        np.testing.assert_allclose(num(lambda x: F(u0=x), u0), np.transpose(d['dU0'], (2, 1, 0)), atol=1e-7)
+        np.testing.assert_allclose(num(lambda x: F(K=x), K), np.transpose(d['dK'], (2, 1, 0)), atol=1e-7)
+        np.testing.assert_allclose(num(lambda x: F(P=x), P), np.transpose(d['dP'], (2, 1, 0)), atol=1e-7)
+        if model > 0:
+            np.testing.assert_allclose(num(lambda x: F(b=x), b), np.transpose(d['dB'], (2, 1, 0)), atol=1e-7)
+        nq = num(lambda x: F(Q=x.reshape(3, m, order='F')), Q.reshape(-1, order='F'))   # (3m,2,m)
+        for j in range(m):
+            np.testing.assert_allclose(nq[3 * j:3 * j + 3, :, j], d['dQ'][j].T, atol=1e-7)
