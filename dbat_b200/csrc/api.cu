@@ -1143,6 +1143,10 @@ extern "C" int dbat_dense_chol_solve(int64_t n, const double* A, const double* b
         cudaFree(Z); cudaFree(Cc);
     }
     if (ms_out) *ms_out = best;
+#ifdef POTRF_PROFILE
+    { double pr[10]; cudaMemcpy(pr, w.minmax, sizeof(pr), cudaMemcpyDeviceToHost);
+      printf("potrf cycles: load %.0f | update %.0f | diag %.0f | rows %.0f | writeback %.0f | Xoff %.0f | out %.0f\n", pr[2], pr[3], pr[4], pr[5], pr[6], pr[7], pr[8]); }
+#endif
     cudaError_t e = cudaDeviceSynchronize();
     chol_free(w); cudaFree(dA); cudaFree(dA0); cudaFree(drhs); cudaFree(dx);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);

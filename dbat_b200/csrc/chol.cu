@@ -157,83 +157,105 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
     double* dg = sm + NB * PLD;         // [128] diagonal of inv(L)
     double* Xd = dg + NB;               // [16][17] inverse of the current diagonal block
     double* Tb = Xd + PB * 17;          // [7][16][17] scratch for the inverse
+    double* colb = Tb + 7 * PB * 17;    // [2][16] column exchange buffer of the diagonal-block factorisation
+    double* XdAll = colb + 2 * PB;      // [8][16][17] inverses of all diagonal blocks, zero above the diagonal
     __shared__ int s_bad;
     __shared__ double s_min, s_max;
     const int t = threadIdx.x;
+#ifdef POTRF_PROFILE
+    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tl = clock64();
+#define TICK(k) { __syncthreads(); const long long n_ = clock64(); tk[k] += n_ - tl; tl = n_; }
+#else
+#define TICK(k)
+#endif
     {
         const int i = t & 127, h = t >> 7;
-        for (int c = h * 64; c < h * 64 + 64; ++c) As[i * PLD + c] = (c <= i) ? A[(size_t)c * lda + i] : 0.0;
+        const double* src = A + i;
+#pragma unroll 16
+        for (int c = h * 64; c < h * 64 + 64; ++c) As[i * PLD + c] = (c <= i) ? src[(size_t)c * lda] : 0.0;
     }
     if (t == 0) { s_bad = 0; s_min = 1e300; s_max = 0.0; }
     __syncthreads();
+    TICK(0)
     for (int c0 = 0; c0 < NB; c0 += PB) {
-        if (c0 > 0) {                                   // (1) left-looking update of the panel
-            const int i = t & 127, h = t >> 7;
-            if (i >= c0) {
-                double acc[8];
+        if (c0 > 0) {                                   // (1) left-looking update of the panel (DMMA)
+            // P(i, j) -= sum_k L(i,k) L(j,k), i in [c0,128), j in [c0,c0+16), k < c0.
+            // warp w owns the 8-row tiles c0/8 + w, + w+8 ; two 8-column tiles each.
+            const int lane = t & 31, warp = t >> 5;
+            const int fr = lane >> 2, fk = lane & 3;
+            const double* Bp0 = As + (c0 + fr) * PLD + fk;          // B(k,n) = L(c0+n, k)
+            const double* Bp1 = Bp0 + 8 * PLD;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) acc[q] = 0.0;
-                const double* Li = As + i * PLD;
-                const double* Lj = As + (c0 + 8 * h) * PLD;
+            for (int half = 0; half < 2; ++half) {
+                const int i0 = c0 + 8 * (warp + 8 * half);
+                if (i0 < NB) {
+                    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+                    const double* Ap = As + (i0 + fr) * PLD + fk;
 #pragma unroll 4
-                for (int k = 0; k < c0; ++k) {
-                    const double a = Li[k];
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) acc[q] += a * Lj[q * PLD + k];
-                }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int j = c0 + 8 * h + q;
-                    if (j <= i) As[i * PLD + j] -= acc[q];
+                    for (int k0 = 0; k0 < c0; k0 += 4) {
+                        const double a = Ap[k0], b0 = Bp0[k0], b1 = Bp1[k0];
+                        dmma(c00, c01, a, b0);
+                        dmma(c10, c11, a, b1);
+                    }
+                    double* Cp = As + (i0 + fr) * PLD + c0 + 2 * fk;
+                    Cp[0] -= c00; Cp[1] -= c01; Cp[8] -= c10; Cp[9] -= c11;
                 }
             }
         }
         __syncthreads();
-        if (t < 32) {                                   // (2) 16x16 diagonal block in registers
-            // lane r (0..15; the upper half-warp mirrors it) holds row r; column j is broadcast
-            // with shuffles, so the 16 elimination steps never touch shared memory.
+        TICK(1)
+        if (t < 32) {                                   // (2) 16x16 diagonal block, lane = row
+            // Row r lives in registers; the finished column j travels through a small double-
+            // buffered shared array (one STS + broadcast LDS per step instead of 15 shuffles).
             const int r = t & 15;
-            double row[PB];
+            double row[PB], invd[PB];
 #pragma unroll
             for (int c = 0; c < PB; ++c) row[c] = As[(c0 + r) * PLD + c0 + c];
 #pragma unroll
             for (int j = 0; j < PB; ++j) {
                 const double d = __shfl_sync(0xffffffffu, row[j], j);
-                const double l = sqrt(d), inv = 1.0 / l;
+                const double inv = rsqrt(d);
+                const double l = d * inv;
+                invd[j] = inv;
                 if (t == 0) {
                     if (!(d > 0.0)) s_bad = 1;
                     if (blk * NB + c0 + j < nvalid) { s_min = fmin(s_min, l); s_max = fmax(s_max, l); }
                 }
                 row[j] = (r == j) ? l : (r > j ? row[j] * inv : 0.0);
+                double* cb = colb + (j & 1) * PB;
+                if (t < PB) cb[r] = row[j];
+                __syncwarp();
 #pragma unroll
                 for (int c = j + 1; c < PB; ++c) {
-                    const double lcj = __shfl_sync(0xffffffffu, row[j], c);
-                    if (r >= c) row[c] -= row[j] * lcj;
+                    row[c] -= row[j] * cb[c];           // entries above the diagonal are scratch
                 }
-            }
-            // inverse of the block: lane c builds column c of X = L^-1 by forward substitution,
-            // fetching L(rr,k) from lane rr
-            const int c = r;
-            double x[PB];
-#pragma unroll
-            for (int rr = 0; rr < PB; ++rr) {
-                double sacc = (rr == c) ? 1.0 : 0.0;
-#pragma unroll
-                for (int k = 0; k < rr; ++k) {
-                    const double lrk = __shfl_sync(0xffffffffu, row[k], rr);
-                    if (k >= c) sacc -= lrk * x[k];
-                }
-                const double lrr = __shfl_sync(0xffffffffu, row[rr], rr);
-                x[rr] = (rr >= c) ? sacc / lrr : 0.0;
             }
             if (t < PB) {
 #pragma unroll
                 for (int cc = 0; cc < PB; ++cc) if (cc <= r) As[(c0 + r) * PLD + c0 + cc] = row[cc];
+            }
+            __syncwarp();
+            // inverse of the block: lane c builds column c of X = L^-1 (rows of L are broadcast reads)
+            const int c = r;
+            double x[PB];
 #pragma unroll
-                for (int rr = 0; rr < PB; ++rr) Xd[rr * 17 + c] = x[rr];      // Xd(rr,c), zero above the diagonal
+            for (int rr = 0; rr < PB; ++rr) {
+                double s0 = (rr == c) ? 1.0 : 0.0, s1 = 0.0;
+                const double* Lr = As + (c0 + rr) * PLD + c0;
+#pragma unroll
+                for (int k = 0; k < rr; ++k) {
+                    if (k & 1) s1 -= Lr[k] * x[k]; else s0 -= Lr[k] * x[k];
+                }
+                x[rr] = (rr >= c) ? (s0 + s1) * invd[rr] : 0.0;
+            }
+            if (t < PB) {
+                double* Xa = XdAll + (c0 / PB) * PB * 17;
+#pragma unroll
+                for (int rr = 0; rr < PB; ++rr) { Xd[rr * 17 + c] = x[rr]; Xa[rr * 17 + c] = x[rr]; }   // zero above the diagonal
             }
         }
         __syncthreads();
+        TICK(2)
         if (t < NB && t >= c0 + PB) {                   // (3) rows below: row * inv(L_dd)' = row * Xd'
             double* rowp = As + t * PLD + c0;
             double a[PB], o[PB];
@@ -255,6 +277,7 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
             for (int rr = c + 1; rr < PB; ++rr) As[(c0 + c) * PLD + c0 + rr] = Xd[rr * 17 + c];
         }
         __syncthreads();
+        TICK(3)
     }
     if (t == 0) {
         if (s_bad) atomicCAS(info, 0, blk + 1);
@@ -266,54 +289,67 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
         const int i = t & 127, h = t >> 7;
         for (int c = h * 64; c < h * 64 + 64; ++c) if (c <= i) A[(size_t)c * lda + i] = As[i * PLD + c];
     }
+    TICK(4)
     // ---- inverse.  X(r,c), r>c is stored at As[c][r]; X(c,c) in dg[c].
-    const int ti = t >> 4, tj = t & 15;
-    auto Xat = [&](int r, int c) -> double {            // X(r,c) for r>=c
-        return (r > c) ? As[c * PLD + r] : dg[c];
-    };
-    for (int d = 1; d < NB / PB; ++d) {                 // sub-diagonal d: blocks (jb+d, jb)
-        const int nblk = NB / PB - d;
-        for (int q = 0; q < nblk; ++q) {
-            const int jb = q, ib = q + d;
-            double s = 0.0;
-            const double* Li = As + (ib * PB + ti) * PLD;
-            // kb = jb: X block is lower triangular (k >= j)
-            {
-                const int kb0 = jb * PB, j = jb * PB + tj;
+    {
+        // X(ib,jb) = -inv(L_ib,ib) * sum_{kb=jb}^{ib-1} L(ib,kb) X(kb,jb), one sub-diagonal d = ib-jb
+        // at a time; every 16x16 block is 2x2 DMMA tiles, tile tasks are dealt round-robin to warps.
+        const int lane = t & 31, warp = t >> 5;
+        const int fr = lane >> 2, fk = lane & 3;
+        for (int d = 1; d < NB / PB; ++d) {
+            const int ntask = (NB / PB - d) * 4;
+            for (int task = warp; task < ntask; task += 8) {
+                const int q = task >> 2, tm = (task >> 1) & 1, tn = task & 1;
+                const int jb = q, ib = q + d;
+                double c0v = 0.0, c1v = 0.0;
+                const double* Ap = As + (ib * PB + 8 * tm + fr) * PLD + fk;              // L(ib rows, k)
+                {   // kb = jb: B(k,n) = Xd_jb(k, 8tn+n) (zero padded)
+                    const double* Bx = XdAll + jb * PB * 17 + fk * 17 + 8 * tn + fr;
 #pragma unroll
-                for (int k = 0; k < PB; ++k) if (k >= tj) s += Li[kb0 + k] * Xat(kb0 + k, j);
+                    for (int k0 = 0; k0 < PB; k0 += 4) dmma(c0v, c1v, Ap[jb * PB + k0], Bx[k0 * 17]);
+                }
+                const double* Bp = As + (jb * PB + 8 * tn + fr) * PLD + fk;              // X(k, j) = As[j][k]
+                for (int kb = jb + 1; kb < ib; ++kb) {
+#pragma unroll
+                    for (int k0 = 0; k0 < PB; k0 += 4) dmma(c0v, c1v, Ap[kb * PB + k0], Bp[kb * PB + k0]);
+                }
+                double* Tq = Tb + (q * PB + 8 * tm + fr) * 17 + 8 * tn + 2 * fk;
+                Tq[0] = c0v; Tq[1] = c1v;
             }
-            for (int kb = jb + 1; kb < ib; ++kb) {
-                const int kb0 = kb * PB;
-                const double* Xc = As + (jb * PB + tj) * PLD + kb0;   // X(kb0+k, j) = As[j][kb0+k]
+            __syncthreads();
+            for (int task = warp; task < ntask; task += 8) {
+                const int q = task >> 2, tm = (task >> 1) & 1, tn = task & 1;
+                const int jb = q, ib = q + d;
+                double c0v = 0.0, c1v = 0.0;
+                const double* Ax = XdAll + ib * PB * 17 + (8 * tm + fr) * 17 + fk;       // Xd_ib(i, m)
+                const double* Bt = Tb + (q * PB + fk) * 17 + 8 * tn + fr;                // T(m, n)
 #pragma unroll
-                for (int k = 0; k < PB; ++k) s += Li[kb0 + k] * Xc[k];
+                for (int k0 = 0; k0 < PB; k0 += 4) dmma(c0v, c1v, Ax[k0], Bt[k0 * 17]);
+                // X(ib*16 + 8tm + fr, jb*16 + 8tn + 2fk + {0,1}) stored transposed
+                double* Xo = As + (jb * PB + 8 * tn + 2 * fk) * PLD + ib * PB + 8 * tm + fr;
+                Xo[0] = -c0v; Xo[PLD] = -c1v;
             }
-            Tb[(q * PB + ti) * 17 + tj] = s;
+            __syncthreads();
         }
-        __syncthreads();
-        for (int q = 0; q < nblk; ++q) {
-            const int jb = q, ib = q + d, i0 = ib * PB;
-            double s = 0.0;
-#pragma unroll
-            for (int m = 0; m < PB; ++m) if (m <= ti) s += Xat(i0 + ti, i0 + m) * Tb[(q * PB + m) * 17 + tj];
-            As[(jb * PB + tj) * PLD + i0 + ti] = -s;    // X(i0+ti, jb*PB+tj)
-        }
-        __syncthreads();
     }
+    TICK(5)
     double* out = invL + (size_t)blk * NB * NB;          // column-major 128x128, lower triangular
     {
         const int i = t & 127, h = t >> 7;
         for (int cc = h * 64; cc < h * 64 + 64; ++cc)
             out[(size_t)cc * NB + i] = (i > cc) ? As[cc * PLD + i] : (i == cc ? dg[cc] : 0.0);
     }
+    TICK(6)
+#ifdef POTRF_PROFILE
+    if (t == 0 && blk == 1) for (int k = 0; k < 8; ++k) minmax[2 + k] = (double)tk[k];
+#endif
 }
 
 void chol_alloc(CholWork& w, int n, int ld) {
     w.n = n; w.ld = ld; w.nb = ld / NB;
     cudaMalloc(&w.invL, sizeof(double) * (size_t)w.nb * NB * NB);
     cudaMalloc(&w.info, sizeof(int));
-    cudaMalloc(&w.minmax, sizeof(double) * 2);
+    cudaMalloc(&w.minmax, sizeof(double) * 16);
     cudaMalloc(&w.panel, sizeof(double) * (size_t)ld * NB);
 }
 void chol_free(CholWork& w) {
@@ -332,7 +368,7 @@ static cudaEvent_t g_evA = nullptr, g_evB = nullptr;
 // stream finishes the rest of the trailing update of step k.
 void chol_factor(CholWork& w, double* A, cudaStream_t st) {
     static bool attr = false;
-    const int psmem = (NB * PLD + NB + PB * 17 + 7 * PB * 17) * 8;
+    const int psmem = (NB * PLD + NB + PB * 17 + 7 * PB * 17 + 2 * PB + 8 * PB * 17) * 8;
     if (!attr) {
         cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
         cudaStreamCreateWithFlags(&g_aux, cudaStreamNonBlocking);
