@@ -39,7 +39,7 @@ ALG_BYTES = {   # algorithmic HBM bytes per observation (DESIGN.md "Kernels")
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
     ap.add_argument('--nimg', type=int, default=C4['nImg'])
@@ -227,12 +227,12 @@ def main():
         return time.perf_counter() - t0, dev_ms, launches
 
     # device-resident arm
-    P.normal_step(x0, lam, trial=True, accept=False, want_p=False)       # upload x0
-    timed(args.warmup, True)
-    P.normal_step(x0, lam, trial=True, accept=False, want_p=False)       # restart the path at x0
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    P.normal_step(x0, lam, trial=True, accept=False, want_p=False)       # upload x0
+    timed(args.warmup, True)
+    P.normal_step(x0, lam, trial=True, accept=False, want_p=False)       # restart the path at x0
     wall, dev_ms, launches = timed(args.steps, True)
     phases = P.phase_times() if hasattr(P, 'phase_times') else {}
     # end-to-end arm (host x in, host p out every step)
@@ -281,7 +281,7 @@ def main():
     ph_ms = {k: v[0] for k, v in phases.items() if k != 'total'}
     dom = max(ph_ms, key=ph_ms.get) if ph_ms else 'cholesky'
     line['dominant_phase'] = dom
-    if dom == 'cholesky' and world == 1:
+    if dom == 'cholesky':
         fp64 = fp64_peak_tflops()
         ach = (nRed ** 3 / 3.0) / (ph_ms['cholesky'] * 1e-3) / 1e12
         line['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': fp64, 'unit': 'TFLOP/s',

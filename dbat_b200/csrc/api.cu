@@ -182,7 +182,11 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     if (!fill(colIO, d->IOdes_src, d->IOdes_dest, d->nIOdes) || !fill(colEO, d->EOdes_src, d->EOdes_dest, d->nEOdes) ||
         !fill(colOP, d->OPdes_src, d->OPdes_dest, d->nOPdes))
         return fail_create(h, DBAT_E_BADARG, "deserialisation index out of range");
-    const int nC = (int)(d->n - d->nOPdes);
+    // camera-side unknowns x[0:nC]: everything up to the last IO/EO column (a point-sharded problem
+    // lists only its own OP columns, so n - nOPdes would be wrong there)
+    int nC = 0;
+    for (int c : colIO) nC = std::max(nC, c + 1);
+    for (int c : colEO) nC = std::max(nC, c + 1);
     for (int c : colOP) if (c >= 0 && c < nC) return fail_create(h, DBAT_E_UNSUPPORTED, "x must be ordered [IO;EO;OP]");
     for (int c : colIO) if (c >= nC) return fail_create(h, DBAT_E_UNSUPPORTED, "x must be ordered [IO;EO;OP]");
     for (int c : colEO) if (c >= nC) return fail_create(h, DBAT_E_UNSUPPORTED, "x must be ordered [IO;EO;OP]");

@@ -483,19 +483,69 @@ __global__ void __launch_bounds__(256) k_bwd_step(const double* __restrict__ A, 
     if (t < NB) x[(size_t)j * NB + t] = o[t];
 }
 
+// Whole backward substitution in one cooperative launch: CTA j owns block j of the solution,
+// keeps y_j in shared memory, applies y_j -= L_kj' x_k as soon as x_k is published (flag),
+// then publishes x_j = invL_j' y_j.  All CTAs are co-resident (cooperative launch), so the
+// spin-waits cannot deadlock.
+__global__ void __launch_bounds__(256) k_bwd_coop(const double* __restrict__ A, int ld,
+                                                   const double* __restrict__ invL, int nb,
+                                                   const double* __restrict__ y, double* x, int* flags) {
+    __shared__ double v[NB], o[NB], yj[NB];
+    const int t = threadIdx.x, j = blockIdx.x;
+    if (t < NB) yj[t] = y[(size_t)j * NB + t];
+    __syncthreads();
+    for (int k = nb - 1; k > j; --k) {
+        if (t == 0) { while (atomicAdd(&flags[k], 0) == 0) { } }
+        __syncthreads();
+        if (t < NB) v[t] = __ldcg(x + (size_t)k * NB + t);
+        __syncthreads();
+        tmatvec128(A + (size_t)j * NB * ld + (size_t)k * NB, (size_t)ld, v, o);
+        __syncthreads();
+        if (t < NB) yj[t] -= o[t];
+        __syncthreads();
+    }
+    tmatvec128(invL + (size_t)j * NB * NB, NB, yj, o);
+    __syncthreads();
+    if (t < NB) x[(size_t)j * NB + t] = o[t];
+    __threadfence();
+    __syncthreads();
+    if (t == 0) atomicExch(&flags[j], 1);
+}
+
 static double* g_solve_tmp = nullptr;
+static int* g_solve_flags = nullptr;
 static int g_solve_tmp_n = 0;
+static int g_coop_max = -1;
 // After chol_factor on a matrix prepared with chol_put_rhs: x (length ld) = A^-1 rhs.
 void chol_solve(const CholWork& w, const double* A, double* x, cudaStream_t st) {
     if (g_solve_tmp_n < w.ld) {
-        if (g_solve_tmp) cudaFree(g_solve_tmp);
+        if (g_solve_tmp) { cudaFree(g_solve_tmp); cudaFree(g_solve_flags); }
         cudaMalloc(&g_solve_tmp, sizeof(double) * w.ld);
+        cudaMalloc(&g_solve_flags, sizeof(int) * (w.ld / NB + 1));
         g_solve_tmp_n = w.ld;
+    }
+    if (g_coop_max < 0) {
+        int dev = 0, coop = 0, sms = 0, occ = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_bwd_coop, 256, 0);
+        g_coop_max = coop ? sms * occ : 0;
     }
     double* y = g_solve_tmp;
     k_get_y_row<<<(w.ld + 255) / 256, 256, 0, st>>>(A, w.ld, y, w.n);
+    count_launch();
+    if (w.nb <= g_coop_max) {
+        cudaMemsetAsync(g_solve_flags, 0, sizeof(int) * w.nb, st);
+        const double* Ac = A; const double* iL = w.invL; int ld = w.ld, nb = w.nb; const double* yc = y;
+        int* fl = g_solve_flags;
+        void* args[] = {(void*)&Ac, (void*)&ld, (void*)&iL, (void*)&nb, (void*)&yc, (void*)&x, (void*)&fl};
+        cudaLaunchCooperativeKernel((void*)k_bwd_coop, dim3(w.nb), dim3(256), args, 0, st);
+        count_launch();
+        return;
+    }
     k_bwd_first<<<1, 256, 0, st>>>(w.invL, w.nb - 1, y, x);
-    count_launch(2);
+    count_launch();
     for (int k = w.nb - 1; k >= 1; --k) { k_bwd_step<<<k, 256, 0, st>>>(A, w.ld, w.invL, k, y, x); count_launch(); }
 }
 
