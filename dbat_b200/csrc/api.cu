@@ -159,14 +159,16 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     dbat_handle* h = new dbat_handle();
     const int nImg = (int)d->nImg, nOP = (int)d->nOP, nObs = (int)d->nIP;
     const int nK = d->nK, nP = d->nP, NC = 5 + nK + nP;
-    if (d->distModel < 2 || d->distModel > 5)
-        return fail_create(h, DBAT_E_UNSUPPORTED, "distModel must be 2..5 (legacy models 1/-1 are not built yet)");
+    const bool legacy = (d->distModel == 1 || d->distModel == -1);
+    if (!legacy && (d->distModel < 2 || d->distModel > 5))
+        return fail_create(h, DBAT_E_BADARG, "distModel must be -1, 1, 2, 3, 4 or 5");
     if (nK > DBAT_KMAX || nP > DBAT_PMAX || nK < 0 || nP < 0 || nP == 1)
         return fail_create(h, DBAT_E_UNSUPPORTED, "nK/nP outside the compiled limits");
     if (d->n <= 0 || nImg <= 0) return fail_create(h, DBAT_E_BADARG, "empty problem");
     h->NC = NC;
     DevProblem& P = h->P;
-    P.nImg = nImg; P.nOP = nOP; P.nObs = nObs; P.nK = nK; P.nP = nP; P.model = d->distModel - 2;
+    P.nImg = nImg; P.nOP = nOP; P.nObs = nObs; P.nK = nK; P.nP = nP; // kernel MODEL: 0..3 = res_euler_brown_0..3 (distModel 2..5); legacy 1 == model 2 arithmetic; -1 = forward Brown
+    P.model = legacy ? (d->distModel == 1 ? 0 : 4) : d->distModel - 2;
     P.n = (int)d->n;
 
     // ---- column maps from the deserialisation indices (multi_res.m:58-63)
@@ -207,6 +209,13 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     auto slot_of = [&](int row) { return row < 5 ? row : (row < 5 + nK ? DBAT_SLOT_K + (row - 5) : DBAT_SLOT_P + (row - 5 - nK)); };
     int firstImg = -1;
     for (int i = 0; i < nImg; ++i) if (imgHasObs[i]) { firstImg = i; break; }
+    if (legacy) {
+        // brown_euler_cam4.m:39-41,186-188: est.IO(:,2:end)=false, EO.cam(:)=1, IP.cam(:)=1
+        for (int i = 1; i < nImg; ++i)
+            for (int r = 0; r < NC; ++r) colIO[(size_t)i * NC + r] = colIO[r];
+        colIO[3] = -1; colIO[4] = -1;          // aspect / skew do not exist in the legacy models
+        for (int i = 1; i < nImg; ++i) { colIO[(size_t)i * NC + 3] = -1; colIO[(size_t)i * NC + 4] = -1; }
+    }
     for (int r = 0; r < NC; ++r) {
         int v = firstImg >= 0 ? colIO[(size_t)firstImg * NC + r] : -1;
         for (int i = 0; i < nImg; ++i)
@@ -247,7 +256,8 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     {
         std::map<std::vector<double>, int> seen;
         for (int i = 0; i < nImg; ++i) {
-            std::vector<double> key(d->IOval + (size_t)i * NC, d->IOval + (size_t)(i + 1) * NC);
+            const int src = legacy ? 0 : i;
+            std::vector<double> key(d->IOval + (size_t)src * NC, d->IOval + (size_t)(src + 1) * NC);
             auto it = seen.find(key);
             if (it == seen.end()) { it = seen.emplace(key, (int)rep.size()).first; rep.push_back(i); }
             ioOfImg[i] = it->second;
@@ -260,8 +270,9 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     for (int k = 0; k < nObs; ++k) {
         const int i = h->h_img_cm[k];
         uv_cm[k] = make_double2(d->IPval[2 * (size_t)k], d->IPval[2 * (size_t)k + 1]);
-        const double sx = d->IPstd[2 * (size_t)k] * d->pxSize[2 * (size_t)i];
-        const double sy = d->IPstd[2 * (size_t)k + 1] * d->pxSize[2 * (size_t)i + 1];
+        const int ic = legacy ? 0 : i;
+        const double sx = d->IPstd[2 * (size_t)k] * d->pxSize[2 * (size_t)ic];
+        const double sy = d->IPstd[2 * (size_t)k + 1] * d->pxSize[2 * (size_t)ic + 1];
         isig_cm[k] = make_double2(1.0 / sx, 1.0 / sy);           // buildweightmatrix.m:13-23, R = chol(W)
     }
     h->h_img_start.assign(nImg + 1, 0);
@@ -328,7 +339,8 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
         std::vector<ImgRec> recs(nImg);
         for (int i = 0; i < nImg; ++i) {
             memset(&recs[i], 0, sizeof(ImgRec));
-            recs[i].sz = d->pxSize[2 * (size_t)i];                // multi_res.m:138 passes sz(1)
+            recs[i].sz = d->pxSize[2 * (size_t)(legacy ? 0 : i)];   // multi_res.m:138 passes sz(1)
+            recs[i].szy = legacy ? d->pxSize[1] : recs[i].sz;        // legacy: multiscalepts uses both axes
             recs[i].io = ioOfImg[i];
         }
         UP(P.img, recs);

@@ -223,7 +223,8 @@ void launch_cam_side(const DevProblem& P, const int* img_chunk_start, double* tm
         case 0: launch_cam_side_t<0>(P, img_chunk_start, tmp, st); break;
         case 1: launch_cam_side_t<1>(P, img_chunk_start, tmp, st); break;
         case 2: launch_cam_side_t<2>(P, img_chunk_start, tmp, st); break;
-        default: launch_cam_side_t<3>(P, img_chunk_start, tmp, st); break;
+        case 3: launch_cam_side_t<3>(P, img_chunk_start, tmp, st); break;
+        default: launch_cam_side_t<4>(P, img_chunk_start, tmp, st); break;
     }
 }
 
@@ -325,7 +326,8 @@ void launch_point_side(const DevProblem& P, cudaStream_t st) {
         case 0: launch_point_side_t<0>(P, st); break;
         case 1: launch_point_side_t<1>(P, st); break;
         case 2: launch_point_side_t<2>(P, st); break;
-        default: launch_point_side_t<3>(P, st); break;
+        case 3: launch_point_side_t<3>(P, st); break;
+        default: launch_point_side_t<4>(P, st); break;
     }
 }
 void launch_prior_apply(const DevProblem& P, const double* x, double* camDiag, double* camG,
@@ -413,7 +415,8 @@ void launch_resid(const DevProblem& P, const double* x, double* partial, double*
         case 0: launch_resid_t<0>(P, x, partial, scal, slot, r_out, weighted, st); break;
         case 1: launch_resid_t<1>(P, x, partial, scal, slot, r_out, weighted, st); break;
         case 2: launch_resid_t<2>(P, x, partial, scal, slot, r_out, weighted, st); break;
-        default: launch_resid_t<3>(P, x, partial, scal, slot, r_out, weighted, st); break;
+        case 3: launch_resid_t<3>(P, x, partial, scal, slot, r_out, weighted, st); break;
+        default: launch_resid_t<4>(P, x, partial, scal, slot, r_out, weighted, st); break;
     }
 }
 
@@ -505,7 +508,8 @@ void launch_jp(const DevProblem& P, const double* x, const double* p, double* pa
         case 0: launch_jp_t<0>(P, x, p, partial, scal, slot2, slotr, st); break;
         case 1: launch_jp_t<1>(P, x, p, partial, scal, slot2, slotr, st); break;
         case 2: launch_jp_t<2>(P, x, p, partial, scal, slot2, slotr, st); break;
-        default: launch_jp_t<3>(P, x, p, partial, scal, slot2, slotr, st); break;
+        case 3: launch_jp_t<3>(P, x, p, partial, scal, slot2, slotr, st); break;
+        default: launch_jp_t<4>(P, x, p, partial, scal, slot2, slotr, st); break;
     }
 }
 
@@ -545,7 +549,8 @@ void launch_export_jac(const DevProblem& P, double* out, int weighted, cudaStrea
         case 0: k_export_jac<0><<<nb, 128, 0, st>>>(P, out, weighted); break;
         case 1: k_export_jac<1><<<nb, 128, 0, st>>>(P, out, weighted); break;
         case 2: k_export_jac<2><<<nb, 128, 0, st>>>(P, out, weighted); break;
-        default: k_export_jac<3><<<nb, 128, 0, st>>>(P, out, weighted); break;
+        case 3: k_export_jac<3><<<nb, 128, 0, st>>>(P, out, weighted); break;
+        default: k_export_jac<4><<<nb, 128, 0, st>>>(P, out, weighted); break;
     }
     count_launch();
 }

@@ -22,10 +22,10 @@
 struct __align__(16) ImgRec {
     double sw, cw, sp, cp, sk, ck;        // sin/cos of omega, phi, kappa
     double q0[3];                         // camera centre
-    double sz;                            // pixel size (pxSize(1,img), multi_res.m:138)
+    double sz;                            // pixel size x (pxSize(1,img), multi_res.m:138)
     int    io;                            // index of this image's IO record
     int    pad_;
-    double pad2_;
+    double szy;                           // pixel size y: = sz for models 2-5, pxSize(2,.) for the legacy models
 };
 static_assert(sizeof(ImgRec) == 96, "ImgRec layout");
 
@@ -105,8 +105,13 @@ __device__ __forceinline__ void brown(const double a[2], const double* Kt, int n
     }
 }
 
-// MODEL = distModel-2 (res_euler_brown_<MODEL>.m).  JAC_CAM: also IO/EO partials;
-// JAC_OP: also OP partials.  Residual rows are x then y, in mm, UNWEIGHTED.
+// MODEL = distModel-2 (res_euler_brown_<MODEL>.m) for models 2..5; legacy model 1 is
+// arithmetically identical to model 2 (brown_euler_cam4.m:46-59: v = pp - f*h - (m - ld(m-pp)))
+// and runs as MODEL 0; MODEL 4 is the forward (computer-vision) model -1
+// (brown_euler_cam4.m:193-208,238-281; cammodel/browndist.m:103-253):
+//   v = pp + w + ld(w) - m,  w = -f*h,  distortion evaluated at the projected point.
+// JAC_CAM: also IO/EO partials; JAC_OP: also OP partials.  Residual rows are x then y, in mm,
+// UNWEIGHTED.
 template <int MODEL, bool JAC_CAM, bool JAC_OP>
 __device__ __forceinline__ void obs_model(const double Q[3], const ImgRec& g, const IORec& io,
                                           int nK, int nP, double ux, double uy, ObsJac& o) {
@@ -122,27 +127,29 @@ __device__ __forceinline__ void obs_model(const double Q[3], const ImgRec& g, co
     const double lhs0 = -f * h0, lhs1 = -f * h1;                                   // eulerpinhole2 with -f
 
     // image side
-    const double y0 = g.sz * ux, y1 = -g.sz * uy;                                  // scale2, aniscale2([1;-1])
+    const double y0 = g.sz * ux, y1 = -g.szy * uy;                                 // scale2, aniscale2([1;-1])
     const double px = io.v[1], py = io.v[2], b1 = io.v[3], b2 = io.v[4];
     double Kt[DBAT_KMAX], Pt[DBAT_PMAX];
+    const double sgn = (MODEL == 4) ? 1.0 : -1.0;      // backward models distort with -K,-P
 #pragma unroll
-    for (int k = 0; k < DBAT_KMAX; ++k) Kt[k] = -io.v[DBAT_SLOT_K + k];
+    for (int k = 0; k < DBAT_KMAX; ++k) Kt[k] = sgn * io.v[DBAT_SLOT_K + k];
 #pragma unroll
-    for (int k = 0; k < DBAT_PMAX; ++k) Pt[k] = -io.v[DBAT_SLOT_P + k];
+    for (int k = 0; k < DBAT_PMAX; ++k) Pt[k] = sgn * io.v[DBAT_SLOT_P + k];
     constexpr int NPW = DBAT_KMAX > DBAT_PMAX ? DBAT_KMAX : DBAT_PMAX;
     double a[2], l[2], D[2][2], pw[NPW], ts[2], opr;
     double x0, x1;
     if (MODEL == 3) { x0 = (1.0 + b1) * y0 - px; x1 = y1 - py; }                   // aniscale2b then xlat2
     else            { x0 = y0 - px;              x1 = y1 - py; }
-    if (MODEL == 1) { a[0] = (1.0 + b1) * x0 + b2 * x1; a[1] = x1; }               // affine2 before brown
-    else            { a[0] = x0; a[1] = x1; }
-    brown<JAC_CAM>(a, Kt, nK, Pt, nP, l, D, pw, ts, opr);
+    if (MODEL == 1)      { a[0] = (1.0 + b1) * x0 + b2 * x1; a[1] = x1; }          // affine2 before brown
+    else if (MODEL == 4) { a[0] = lhs0; a[1] = lhs1; }                             // forward: distort the projection
+    else                 { a[0] = x0; a[1] = x1; }
+    brown<(JAC_CAM || JAC_OP)>(a, Kt, nK, Pt, nP, l, D, pw, ts, opr);
     double rhs0, rhs1;
     if (MODEL == 2)      { rhs0 = (1.0 + b1) * l[0] + b2 * l[1]; rhs1 = l[1]; }    // affine2 after brown
     else if (MODEL == 3) { rhs0 = l[0] + b2 * l[1];              rhs1 = l[1]; }    // skew after brown
     else                 { rhs0 = l[0];                          rhs1 = l[1]; }
-    o.r[0] = lhs0 - rhs0;
-    o.r[1] = lhs1 - rhs1;
+    if (MODEL == 4) { o.r[0] = px + l[0] - y0; o.r[1] = py + l[1] - y1; }          // ptDist - m
+    else            { o.r[0] = lhs0 - rhs0;    o.r[1] = lhs1 - rhs1; }
 
     if (JAC_CAM || JAC_OP) {
         // H = dpinhole = zi*[1 0 -h0; 0 1 -h1]; G = -f*H*M'  (2x3) = d lhs / dQ
@@ -150,8 +157,10 @@ __device__ __forceinline__ void obs_model(const double Q[3], const ImgRec& g, co
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             // (H M')[0][c] = zi*(M[c][0] - h0*M[c][2])
-            G[0][c] = -f * zi * (M[c][0] - h0 * M[c][2]);
-            G[1][c] = -f * zi * (M[c][1] - h1 * M[c][2]);
+            const double g0 = -f * zi * (M[c][0] - h0 * M[c][2]);
+            const double g1 = -f * zi * (M[c][1] - h1 * M[c][2]);
+            if (MODEL == 4) { G[0][c] = D[0][0] * g0 + D[0][1] * g1; G[1][c] = D[1][0] * g0 + D[1][1] * g1; }   // (I+G_ld) dxy
+            else            { G[0][c] = g0; G[1][c] = g1; }
         }
         if (JAC_OP) {
 #pragma unroll
@@ -177,13 +186,19 @@ __device__ __forceinline__ void obs_model(const double Q[3], const ImgRec& g, co
             w[2][0] = q1; w[2][1] = -q0; w[2][2] = 0.0;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                o.dA[0][k] = -f * zi * (w[k][0] - h0 * w[k][2]);
-                o.dA[1][k] = -f * zi * (w[k][1] - h1 * w[k][2]);
+                const double g0 = -f * zi * (w[k][0] - h0 * w[k][2]);
+                const double g1 = -f * zi * (w[k][1] - h1 * w[k][2]);
+                if (MODEL == 4) { o.dA[0][k] = D[0][0] * g0 + D[0][1] * g1; o.dA[1][k] = D[1][0] * g0 + D[1][1] * g1; }
+                else            { o.dA[0][k] = g0; o.dA[1][k] = g1; }
             }
             // IO partials
 #pragma unroll
             for (int s = 0; s < DBAT_NSLOT; ++s) { o.dIO[s][0] = 0.0; o.dIO[s][1] = 0.0; }
-            o.dIO[0][0] = -h0; o.dIO[0][1] = -h1;                                  // dv/df = -h
+            if (MODEL == 4) {                                                       // (I+G_ld) * (-h), dv/dpp = I
+                o.dIO[0][0] = -(D[0][0] * h0 + D[0][1] * h1); o.dIO[0][1] = -(D[1][0] * h0 + D[1][1] * h1);
+            } else {
+                o.dIO[0][0] = -h0; o.dIO[0][1] = -h1;                              // dv/df = -h
+            }
             // E = d rhs / d a-chain; model specific outer 2x2 "T" applied after brown
             double T00 = 1.0, T01 = 0.0;                                           // T = [T00 T01; 0 1]
             if (MODEL == 2) { T00 = 1.0 + b1; T01 = b2; }
@@ -192,7 +207,9 @@ __device__ __forceinline__ void obs_model(const double Q[3], const ImgRec& g, co
             const double TD00 = T00 * D[0][0] + T01 * D[1][0], TD01 = T00 * D[0][1] + T01 * D[1][1];
             const double TD10 = D[1][0], TD11 = D[1][1];
             // dv/du0 = T*D*A  (A = affine before brown for model 3(=MODEL 1), else I)
-            if (MODEL == 1) {
+            if (MODEL == 4) {
+                o.dIO[1][0] = 1.0; o.dIO[2][1] = 1.0;
+            } else if (MODEL == 1) {
                 o.dIO[1][0] = TD00 * (1.0 + b1); o.dIO[1][1] = TD10 * (1.0 + b1);
                 o.dIO[2][0] = TD00 * b2 + TD01;  o.dIO[2][1] = TD10 * b2 + TD11;
             } else {

@@ -39,9 +39,11 @@ def scene(model=3, seed=7, nImg=21, nOP=100, rays=10, priors=False, fixed_pts=0)
         s.IO.val[3, :] = 2e-4
         s.IO.val[4, :] = -1e-4 if model >= 3 else 0.0
         s.IO.val[5:10, :] = truth['IO'][5:10, None] * 0.5
-        if model == 2:
+        if model in (2, 1, -1):   # setcamest masks aspect/skew for |model|<3 (setcamest.m:46-58)
             s.IO.val[3:5, :] = 0.0
             s.bundle.est.IO[3:5, :] = False
+        if model == -1:           # forward model: distortion acts on the ideal point
+            s.IO.val[5:10, :] *= -1
     if fixed_pts:
         s.bundle.est.OP[:, :fixed_pts] = False
         s.bundle.est.OP[2, fixed_pts] = False            # one partially fixed point
@@ -64,6 +66,8 @@ CASES = {
     'model2': dict(model=2),
     'model4': dict(model=4),
     'model5': dict(model=5),
+    'model1': dict(model=1),
+    'model-1': dict(model=-1),
     'priors+fixed': dict(model=3, priors=True, fixed_pts=4),
     'ragged': dict(model=3, rays=3, nOP=150, seed=11),
 }
@@ -133,7 +137,7 @@ def _decisions(rr):
     return [bool(rr[i + 1] != rr[i]) for i in range(len(rr) - 1)]
 
 
-@pytest.mark.parametrize('case', ['model3', 'model4', 'priors+fixed', 'ragged'])
+@pytest.mark.parametrize('case', ['model3', 'model4', 'model1', 'model-1', 'priors+fixed', 'ragged'])
 @pytest.mark.parametrize('damping', ['gna', 'lmp', 'lm'])
 def test_optimisers(case, damping):
     s, _ = scene(**CASES[case])
@@ -229,7 +233,7 @@ def test_structural_rank_deficiency_code():
 
 def test_unsupported_configurations_fail_loudly():
     s, _ = scene(model=3)
-    s.IO.model.distModel[:] = -1
+    s.IO.model.distModel[:] = 7
     with pytest.raises(dbat_b200._lib.DbatError):
         dbat_b200.Problem(s)
     s, _ = scene(model=3)
@@ -281,3 +285,18 @@ def test_dense_cholesky_solver(n):
     assert relmax(Ai, Ar) < 1e-10
     with pytest.raises(_lib.DbatError):
         _lib.dense_chol_solve(A - 2 * n * np.eye(n), b)        # not positive definite
+
+
+@pytest.mark.parametrize('model,sigma0', [(-1, 1.62168), (1, 1.68901), (2, 1.68901), (3, 1.6148),
+                                          (4, 1.61247), (5, 1.6148)])
+def test_camcal_all_models_golden_sigma0(model, sigma0):
+    """data/dbat/dbatexports/camcal-dbatreport-model*.txt: sigma0 of the six distortion models
+    (camcaldemo_allmodels.m), CUDA path against the reference's golden numbers."""
+    s = camcal_struct('default', seed=1)
+    s.IO.model.distModel[:] = model
+    if abs(model) < 3:
+        s.bundle.est.IO[3:5, :] = False
+    s, ok, iters, s0, E = dbat_b200.bundle(s, 'gna')
+    assert ok
+    assert abs(s0 - sigma0) < 6e-6 * (10 if sigma0 == 1.6148 else 1)
+    assert E.numParams == (422 if abs(model) < 3 else 423)

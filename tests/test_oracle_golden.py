@@ -133,3 +133,20 @@ def test_analytic_jacobian_matches_central_differences():
         nq = num(lambda x: F(Q=x.reshape(3, m, order='F')), Q.reshape(-1, order='F'))   # (3m,2,m)
         for j in range(m):
             np.testing.assert_allclose(nq[3 * j:3 * j + 3, :, j], d['dQ'][j].T, atol=1e-7)
+
+
+@pytest.mark.parametrize('model,sigma0', [(-1, 1.62168), (1, 1.68901), (2, 1.68901), (3, 1.6148),
+                                          (4, 1.61247), (5, 1.6148)])
+def test_all_models_golden_sigma0(model, sigma0):
+    """data/dbat/dbatexports/camcal-dbatreport-model{-1,1,2,3,4,5}.txt (camcaldemo_allmodels.m):
+    sigma0 and parameter count of every distortion model, including the legacy code path."""
+    rep = open(os.path.join(os.path.dirname(GOLD), 'dbatexports', 'camcal-dbatreport-model%d.txt' % model)).read()
+    assert abs(float(re.search(r'Sigma0:\s+([\d.]+)', rep).group(1)) - sigma0) < 1e-9
+    s = camcal_struct('default', seed=1)
+    s.IO.model.distModel[:] = model
+    if abs(model) < 3:
+        s.bundle.est.IO[3:5, :] = False            # setcamest.m:46-58
+    s, ok, iters, s0, E = bundle(s, 'gna')
+    assert ok
+    assert abs(s0 - sigma0) < 6e-6 * (10 if sigma0 == 1.6148 else 1)
+    assert E.numParams == int(re.search(r'Number of params:\s+(\d+)', rep).group(1))
