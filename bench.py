@@ -190,7 +190,7 @@ def main():
 
     # scene: config 4 per rank (weak scaling over points; the same 1000 stations)
     nImg, nOP = args.nimg, args.nop * world
-    s, _ = make_scene(nImg, nOP, rays=C4['rays'])
+    s, _ = make_scene(nImg, nOP, rays=C4['rays'], cache_dir=os.environ.get('DBAT_SCENE_CACHE', '/tmp'))
     nObsGlobal = len(s.IP.img)
     x0 = dbat_b200.serialize(s)
     if world > 1:

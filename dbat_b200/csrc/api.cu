@@ -364,6 +364,26 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     AL(P.W, (size_t)std::max(1, nObs) * DBAT_W_STRIDE);
     AL(P.S, (size_t)P.ldS * P.ldS);
     AL(P.rhs, P.ldS);
+    {   // deterministic Schur index: inverse permutation, point of every pm observation, pair blocks
+        std::vector<int> cm2pm(nObs), pt_pm(nObs);
+        for (int o = 0; o < nObs; ++o) { cm2pm[h->h_pm2cm[o]] = o; pt_pm[o] = h->h_pt_cm[h->h_pm2cm[o]]; }
+        int *d_cm2pm, *d_pt_pm, *d_img_start;
+        UP(d_cm2pm, cm2pm); UP(d_pt_pm, pt_pm); UP(d_img_start, h->h_img_start);
+        P.cm2pm = d_cm2pm; P.pt_pm = d_pt_pm; P.img_start = d_img_start;
+        std::vector<long long> pair_off(nOP + 1, 0);
+        for (int j = 0; j < nOP; ++j) {
+            const long long k = h->h_pt_start[j + 1] - h->h_pt_start[j];
+            pair_off[j + 1] = pair_off[j] + k * (k + 1) / 2;
+        }
+        long long *dp = nullptr, *dk = nullptr, *doff = nullptr; int nBlk = 0;
+        if (build_pair_index(d_pt_start, d_img_pm, pair_off.data(), nOP, nImg, &dp, &dk, &doff, &nBlk, h->st))
+            return fail_create(h, DBAT_E_OOM, "out of memory while building the Schur pair index");
+        h->allocs.push_back(dp); h->allocs.push_back(dk); h->allocs.push_back(doff);
+        P.pairs = dp; P.blk_key = dk; P.blk_off = doff; P.nBlk = nBlk;
+        AL(P.Y, (size_t)std::max(1, nObs) * DBAT_W_STRIDE);
+        AL(P.ptaux, (size_t)std::max(1, nOP) * DBAT_PTAUX_STRIDE);
+        AL(P.shPart, (size_t)((nOP + DBAT_SHCHUNK - 1) / DBAT_SHCHUNK + 1) * DBAT_NSLOT * DBAT_SHCOLS);
+    }
     AL(h->d_tmpG, (size_t)64 * DBAT_GSZ);
     const int nPartial = 2 * ((std::max(nObs, P.n) + 255) / 256) + 64;
     AL(h->d_partial, nPartial);

@@ -390,19 +390,28 @@ void chol_factor(CholWork& w, double* A, cudaStream_t st) {
         cudaMemcpy2DAsync(diag(k) + NB, sizeof(double) * ld, w.panel, sizeof(double) * ld,
                           sizeof(double) * (size_t)rem * NB, NB, cudaMemcpyDeviceToDevice, s);
     };
+    // Steps are taken in pairs so that the bulk of the trailing matrix is updated with K = 256
+    // (half the C traffic and epilogues of two K = 128 updates):
+    //   k   : potrf + panel solve (arrives through the look-ahead of the previous pair)
+    //   k+1 : column block k+1 -= L(:,k) L(k+1,k)'  (K=128), potrf + panel solve
+    //   k+2 : column block k+2 -= L(:,k:k+1) L(k+2,k:k+1)'  (K=256), then potrf + panel solve on the
+    //         aux stream while the main stream updates the remaining columns >= k+3 with K=256.
     panel_step(0, st);
-    for (int k = 0; k + 1 < nb; ++k) {
-        const int rem = nb - k - 1;
-        double* Apanel = diag(k) + NB;                     // L(k+1:, k)
-        // (a) block column k+1 of the trailing matrix: A(k+1:, k+1) -= L(k+1:, k) L(k+1, k)'
-        gemm_nt(Apanel, ld, Apanel, ld, diag(k + 1), ld, rem, 1, NB, -1.0, 1.0, false, st);
+    int k = 0;
+    for (; k + 1 < nb; k += 2) {
+        const int rem1 = nb - k - 1;                       // row blocks below block k
+        gemm_nt(diag(k) + NB, ld, diag(k) + NB, ld, diag(k + 1), ld, rem1, 1, NB, -1.0, 1.0, false, st);
+        panel_step(k + 1, st);
+        const int rem2 = nb - k - 2;                       // row blocks below block k+1
+        if (rem2 <= 0) break;
+        const double* P2 = A + (size_t)k * NB * ld + (size_t)(k + 2) * NB;       // L(k+2:, k:k+1), 256 columns
+        gemm_nt(P2, ld, P2, ld, diag(k + 2), ld, rem2, 1, 2 * NB, -1.0, 1.0, false, st);
         cudaEventRecord(g_evA, st);
-        // (b) look-ahead on the aux stream
         cudaStreamWaitEvent(g_aux, g_evA, 0);
-        panel_step(k + 1, g_aux);
+        panel_step(k + 2, g_aux);
         cudaEventRecord(g_evB, g_aux);
-        // (c) the rest of the trailing update: A(k+2:, k+2:) -= L(k+2:, k) L(k+2:, k)'  (lower tiles)
-        if (rem > 1) gemm_nt(Apanel + NB, ld, Apanel + NB, ld, diag(k + 2), ld, rem - 1, rem - 1, NB, -1.0, 1.0, true, st);
+        if (rem2 > 1)
+            gemm_nt(P2 + NB, ld, P2 + NB, ld, diag(k + 3), ld, rem2 - 1, rem2 - 1, 2 * NB, -1.0, 1.0, true, st);
         cudaStreamWaitEvent(st, g_evB, 0);
     }
 }

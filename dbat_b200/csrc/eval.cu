@@ -89,10 +89,13 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+#ifndef DBAT_EVAL_MINBLOCKS
+#define DBAT_EVAL_MINBLOCKS 2
+#endif
 #define XT_LD 68   // 64 rows + 4: fragment loads (8 cols x 4 rows) hit 32 distinct bank pairs
 
 template <int MODEL>
-__global__ void __launch_bounds__(128) k_cam_side(DevProblem P) {
+__global__ void __launch_bounds__(128, DBAT_EVAL_MINBLOCKS) k_cam_side(DevProblem P) {
     extern __shared__ __align__(16) double smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* Xt = smem + (size_t)warp * DBAT_GW * XT_LD;    // [GW][XT_LD] per warp
@@ -232,7 +235,7 @@ void launch_cam_side(const DevProblem& P, const int* img_chunk_start, double* tm
 // point side: one thread per object point
 // ---------------------------------------------------------------------------------------------
 template <int MODEL>
-__global__ void __launch_bounds__(128) k_point_side(DevProblem P) {
+__global__ void __launch_bounds__(128, DBAT_EVAL_MINBLOCKS) k_point_side(DevProblem P) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.nOP) return;
     const double Q[3] = {P.OPval[3 * (size_t)j], P.OPval[3 * (size_t)j + 1], P.OPval[3 * (size_t)j + 2]};

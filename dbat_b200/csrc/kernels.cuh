@@ -13,7 +13,11 @@
 #define DBAT_CHUNK 1024            // max observations per camera-side chunk (one CTA)
 #define DBAT_PT_STRIDE 52          // doubles per point record: V[6] g[3] pad Wsh[14][3]
 #define DBAT_PT_WSH 10
-#define DBAT_W_STRIDE 18           // doubles per observation cross block W_o (6 EO x 3 OP)
+#define DBAT_W_STRIDE 18
+#define DBAT_PTAUX_STRIDE 46       // Vg[3], pad, Ysh[14][3]
+#define DBAT_PTAUX_YSH 4
+#define DBAT_SHCOLS 16              // NSLOT shared columns + rhs + pad
+#define DBAT_SHCHUNK 1024           // points per CTA in the shared x shared reduction           // doubles per observation cross block W_o (6 EO x 3 OP)
 
 static_assert(DBAT_NSLOT + 7 <= DBAT_GW, "Gram width");
 
@@ -50,4 +54,15 @@ struct DevProblem {
     double* W;             // nObs x 18       cross blocks, point-major order
     double* S;             // ldS x ldS       reduced system (lower triangle), column-major
     double* rhs;           // ldS             reduced right-hand side
+    // deterministic Schur reduction (index built once at create, schur_index.cu)
+    double* Y;             // nObs x 18       Y_o = W_o (V_j + lambda I)^-1, point-major order
+    double* ptaux;         // nOP x PTAUX_STRIDE : Vg[3], pad, Ysh[14][3]
+    const int* img_start;  // nImg+1 camera-major observation ranges
+    const int* cm2pm;      // camera-major observation -> point-major index
+    const int* pt_pm;      // point of every point-major observation
+    const long long* pairs;      // sorted (oA<<32|oB) pm-index pairs, grouped by camera-pair block
+    const long long* blk_key;    // nBlk: imgA * nImg + imgB  (imgA >= imgB)
+    const long long* blk_off;    // nBlk+1 offsets into pairs
+    int nBlk;
+    double* shPart;        // per-CTA partials of the shared x shared reduction
 };

@@ -36,6 +36,11 @@ void launch_axpy(double alpha, const double* x, const double* y, double* out, in
 void launch_inv_sqrt(const double* in, double* out, int n, cudaStream_t st);
 void launch_mul(const double* a, const double* b, double* out, int n, cudaStream_t st);
 
+// schur_index.cu
+int build_pair_index(const int* d_pt_start, const int* d_img_pm, const long long* h_pair_off, int nOP,
+                     int nImg, long long** d_pairs, long long** d_blk_key, long long** d_blk_off, int* nBlk,
+                     cudaStream_t st);
+
 // chol.cu
 struct CholWork {
     int n = 0, ld = 0, nb = 0;      // order, leading dimension (multiple of 128), # 128-blocks

@@ -60,8 +60,28 @@ def _pixel_from_ideal(l, io):
 
 
 def make_scene(nImg=1000, nOP=200000, rays=10, seed=SEED, noise_px=0.5, start_noise=1.0,
-               build_indices=True):
-    """Return a DBAT struct (start values) plus a dict with the ground truth."""
+               build_indices=True, cache_dir=None):
+    """Return a DBAT struct (start values) plus a dict with the ground truth.
+
+    cache_dir: directory for a pickle of the generated scene (the generator is deterministic in
+    its arguments; bench.py uses this so that repeated runs on one box skip the ~1 min of host work).
+    """
+    if cache_dir is not None:
+        import os
+        import pickle
+        key = 'dbat_scene_%d_%d_%d_%d_%g_%g_%d.pkl' % (nImg, nOP, rays, seed, noise_px, start_noise, build_indices)
+        path = os.path.join(cache_dir, key)
+        if os.path.exists(path):
+            with open(path, 'rb') as fh:
+                return pickle.load(fh)
+        out = make_scene(nImg, nOP, rays, seed, noise_px, start_noise, build_indices, None)
+        try:
+            with open(path + '.tmp%d' % os.getpid(), 'wb') as fh:
+                pickle.dump(out, fh, protocol=4)
+            os.replace(path + '.tmp%d' % os.getpid(), path)
+        except OSError:
+            pass
+        return out
     rng = np.random.default_rng(seed)
     H = 110.0
     A_fp = (H * 24 / 24) * (H * 16 / 24)

@@ -300,3 +300,33 @@ def test_camcal_all_models_golden_sigma0(model, sigma0):
     assert ok
     assert abs(s0 - sigma0) < 6e-6 * (10 if sigma0 == 1.6148 else 1)
     assert E.numParams == (422 if abs(model) < 3 else 423)
+
+
+def test_deterministic_schur_mode_subprocess():
+    """DBAT_SCHUR=det selects the atomics-free pair-index Schur kernels: same step as the oracle,
+    and bit-identical from run to run."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, copy, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import dbat_b200
+from test_gpu_parity import scene, CASES
+from oracle.cameramodel import brown_euler_cam4
+from oracle.dbatstruct import buildweightmatrix, serialize
+s, _ = scene(**CASES['priors+fixed'])
+x0 = serialize(s); W = buildweightmatrix(s)
+P = dbat_b200.Problem(copy.deepcopy(s))
+p1, st1 = P.normal_step(x0, 10.0, False)
+p2, st2 = P.normal_step(x0, 10.0, False)
+assert np.array_equal(p1, p2), 'not bit-reproducible'
+ro, Jo = brown_euler_cam4(x0, s, True)
+Jw = Jo.multiply(np.sqrt(W)[:, None]).tocsc(); rw = ro * np.sqrt(W)
+N = (Jw.T @ Jw).toarray()
+po = np.linalg.solve(N + 10.0 * np.eye(N.shape[0]), -(Jw.T @ rw))
+assert np.abs(p1 - po).max() / np.abs(po).max() < 5e-9
+print('DET-OK')
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DBAT_SCHUR='det')
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert 'DET-OK' in out.stdout, out.stdout + out.stderr
