@@ -444,6 +444,7 @@ static inline double gram_host(const double* G, int R, int C) {
 // residual + Jacobian + assembly at d_x.  On return h_scal[SC_RR] = r'r (global).
 static int eval_full(dbat_handle* h) {
     size_t a = ph_begin(h);
+    h->cscWeighted = -1;                    // any cached Jacobian export belongs to an older x
     set_params(h, h->d_x);
     h->params_valid = true;
     launch_cam_side(h->P, h->d_img_chunk_start, h->d_tmpG, h->st);
@@ -728,9 +729,48 @@ static bool term_fun(const dbat_opts* o, double jp2, double rr) {
     return std::sqrt(jp2) <= o->convTol * std::sqrt(rr);
 }
 
-// cheap structural-rank screen standing in for sprank(J)<n (levenberg_marquardt.m:126-135):
-// every unknown needs at least one residual row, every point/image needs as many rows as free
-// coordinates, and m >= n.
+// sprank(J) < n (levenberg_marquardt.m:126-135, gauss_newton_armijo.m:132-143): maximum bipartite
+// matching between the columns and rows of the exported sparse Jacobian (exact zeros dropped, like
+// the reference's J).  Greedy initialisation + augmenting paths (iterative DFS).  Only used when the
+// problem is small enough to export J on every run; larger problems use the counting screen below.
+static int build_csc(dbat_handle* h, int weighted);
+static bool matching_deficient(dbat_handle* h) {
+    if (build_csc(h, 1)) return false;
+    const int n = h->P.n, m = h->m;
+    const std::vector<int64_t>& Jc = h->cscJc; const std::vector<int64_t>& Ir = h->cscIr;
+    std::vector<int> matchRow(m, -1), matchCol(n, -1), stamp(m, -1);
+    int matched = 0;
+    for (int c = 0; c < n; ++c)                                  // greedy pass
+        for (int64_t e = Jc[c]; e < Jc[c + 1]; ++e)
+            if (matchRow[Ir[e]] < 0) { matchRow[Ir[e]] = c; matchCol[c] = (int)Ir[e]; ++matched; break; }
+    std::vector<int> stackCol; std::vector<int64_t> stackPos; std::vector<int> pathRow;
+    for (int c0 = 0; c0 < n && matched < n; ++c0) {
+        if (matchCol[c0] >= 0) continue;
+        // iterative DFS for an augmenting path starting at the free column c0
+        stackCol.assign(1, c0); stackPos.assign(1, Jc[c0]); pathRow.clear();
+        bool found = false;
+        while (!stackCol.empty() && !found) {
+            const int c = stackCol.back();
+            int64_t& pos = stackPos.back();
+            if (pos >= Jc[c + 1]) { stackCol.pop_back(); stackPos.pop_back(); if (!pathRow.empty()) pathRow.pop_back(); continue; }
+            const int r = (int)Ir[pos++];
+            if (stamp[r] == c0) continue;
+            stamp[r] = c0;
+            if (matchRow[r] < 0) { pathRow.push_back(r); found = true; break; }
+            pathRow.push_back(r);
+            stackCol.push_back(matchRow[r]); stackPos.push_back(Jc[matchRow[r]]);
+        }
+        if (found) {                                              // flip the path: column k takes row pathRow[k]
+            for (size_t k = 0; k < stackCol.size(); ++k) { matchRow[pathRow[k]] = stackCol[k]; matchCol[stackCol[k]] = pathRow[k]; }
+            ++matched;
+        }
+    }
+    h->cscWeighted = -1; h->cscIr.clear(); h->cscIr.shrink_to_fit(); h->cscV.clear(); h->cscV.shrink_to_fit();
+    return matched < n;
+}
+
+// counting screen (necessary conditions of a full structural rank): every unknown needs at least
+// one residual row, every point/image needs as many rows as free coordinates, and m >= n.
 static bool structurally_deficient(dbat_handle* h) {
     DevProblem& P = h->P;
     if (h->nranks > 1) return false;
@@ -747,6 +787,7 @@ static bool structurally_deficient(dbat_handle* h) {
         for (int a = 0; a < 6; ++a) { const int c = h->h_eo_col[6 * (size_t)i + a]; if (c >= 0) { ++freec; pri += priorCnt[c]; } }
         if (freec && 2 * (h->h_img_start[i + 1] - h->h_img_start[i]) + pri < freec) return true;
     }
+    if ((int64_t)P.nObs <= 300000) return matching_deficient(h);   // exact test where exporting J is cheap
     return false;
 }
 

@@ -115,3 +115,96 @@ def load_camera_stations(path):
     ids = np.array([int(r[1]) for r in rows])
     vals = np.array([[float(v) for v in r[2:14]] for r in rows]).T
     return ids, vals[0:6], vals[6:12]
+
+
+# --------------------------------------------------------------------------- PhotoModeler text export
+def load_pm_export(path):
+    """Subset of `code/file/loadpm.m:104-330`: 5 header lines, per-image 6-line blocks
+    (id name; outer x y z kappa phi omega [deg]; std; cov (blank); inner f xp yp xs ys K1 K2 K3 P1 P2;
+    std), control points `id x y z sx sy sz`, object points (same columns), mark points
+    `photo(0-based) id x y sx sy`; sections end with a blank line."""
+    lines = open(path).read().split('\n')
+    hdr2 = lines[1].split()
+    job = {'imSz': np.array([float(hdr2[2]), float(hdr2[3])]),
+           'defCam': np.array([float(v) for v in lines[3].split()])}
+    k = 5
+    images = []
+    while k < len(lines):
+        tok = lines[k].split()
+        if len(tok) < 2 or tok[1].replace('.', '').replace('-', '').isdigit():
+            break
+        outer = np.array([float(v) for v in lines[k + 1].split()[1:]])
+        inner = np.array([float(v) for v in lines[k + 4].split()[1:]])
+        images.append({'id': int(tok[0]), 'name': tok[1], 'outer': outer, 'inner': inner})
+        k += 6
+    def table(k):
+        while k < len(lines) and not lines[k].strip():
+            k += 1
+        rows = []
+        while k < len(lines) and lines[k].strip():
+            rows.append([float(v) for v in lines[k].split()])
+            k += 1
+        return np.array(rows), k
+    ctrl, k = table(k)
+    obj, k = table(k)
+    mark, k = table(k)
+    return {'job': job, 'images': images, 'ctrlPts': ctrl, 'objPts': obj, 'markPts': mark}
+
+
+def prague_cam_struct(root, stub):
+    """The prague2016 'cam' projects C1 ('fixed') / C2 ('weighted') as `prague2016_pm.m:100-215` sets
+    them up: `prob2dbatstruct` (`misc/prob2dbatstruct.m:198-420`: model 1, square pixels from the sensor
+    height, py/K/P sign flips, angles = outer([6,5,4]) deg), fixed camera (`setcamest(s,'not','all')`),
+    control points from `ref/ctrlpts-<stub>.txt` shifted by the mean offset to PhotoModeler's frame
+    (`:166-190`) and set with `setcpt` (std 0 => fixed, otherwise prior observation).  EO and OP start
+    values are PhotoModeler's own estimates from the export (the demo recomputes them by resection /
+    intersection; the converged result does not depend on that)."""
+    import os
+    prob = load_pm_export(os.path.join(root, 'pmexports', '%s-no-orient-pmexport.txt' % stub))
+    nImg = len(prob['images'])
+    ids = np.unique(np.concatenate([prob['ctrlPts'][:, 0], prob['objPts'][:, 0]])).astype(int)
+    op_of = {v: i for i, v in enumerate(ids)}
+    nK, nP = 3, 2
+    inner = prob['job']['defCam']
+    imSz = prob['job']['imSz']
+    IO = np.zeros((5 + nK + nP, nImg))
+    IO[0] = inner[0]
+    IO[1], IO[2] = inner[1], -inner[2]
+    IO[5:8] = -inner[5:8, None]
+    IO[8:10] = -inner[8:10, None]
+    px = inner[3:5] / imSz
+    IO[3] = 1 - px[0] / px[1]
+    pxSize = np.array([[px[1]], [px[1]]])
+    EO = np.zeros((6, nImg))
+    for i, im in enumerate(prob['images']):
+        EO[0:3, i] = im['outer'][0:3]
+        EO[3:6, i] = np.deg2rad(im['outer'][[5, 4, 3]])
+    OP = np.full((3, len(ids)), np.nan)
+    for r in np.vstack([prob['ctrlPts'], prob['objPts']]):
+        OP[:, op_of[int(r[0])]] = r[1:4]
+    mk = prob['markPts']
+    keep = np.array([int(r[1]) in op_of for r in mk])
+    mk = mk[keep]
+    s = new_struct(IO, EO, OP, mk[:, 2:4].T, mk[:, 0].astype(int), np.array([op_of[int(v)] for v in mk[:, 1]]),
+                   pxSize, imSz[:, None], 1, nK, nP, mk[:, 4:6].T)
+    s.OP.id = ids
+    s.bundle.est.IO[:] = False
+    s.bundle.est.EO[:] = True
+    s.bundle.est.OP[:] = True
+    cp = load_table(os.path.join(root, 'ref', 'ctrlpts-%s.txt' % stub))
+    cp_id = [int(r[0]) for r in cp]
+    cp_pos = np.array([[float(v) for v in r[2:5]] for r in cp]).T
+    cp_std = np.array([[float(v) for v in r[5:8]] if len(r) >= 8 else [0.0, 0.0, 0.0] for r in cp]).T
+    pm_pos = np.array([prob['ctrlPts'][prob['ctrlPts'][:, 0] == i, 1:4][0] for i in cp_id]).T
+    cp_pos = cp_pos + np.mean(pm_pos - cp_pos, axis=1, keepdims=True)     # prague2016_pm.m:174-190
+    s.prior.OP.isCtrl = np.zeros(len(ids), bool)
+    for k, i in enumerate(cp_id):                                          # setcpt.m
+        j = op_of[i]
+        s.prior.OP.val[:, j] = cp_pos[:, k]
+        s.OP.val[:, j] = cp_pos[:, k]
+        s.prior.OP.std[:, j] = cp_std[:, k]
+        fixed = np.all(cp_std[:, k] == 0)
+        s.prior.OP.use[:, j] = not fixed
+        s.bundle.est.OP[:, j] = not fixed
+        s.prior.OP.isCtrl[j] = True
+    return s

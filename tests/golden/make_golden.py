@@ -23,6 +23,14 @@ FILES = {
         'data/script/camcaldemo/result/report.txt',
         'data/script/camcaldemo/result/top_residuals.txt',
     ],
+    'prague2016cam': [
+        'data/prague2016/cam/pmexports/weighted-no-orient-pmexport.txt',
+        'data/prague2016/cam/pmexports/fixed-no-orient-pmexport.txt',
+        'data/prague2016/cam/ref/ctrlpts-weighted.txt',
+        'data/prague2016/cam/ref/ctrlpts-fixed.txt',
+        'data/prague2016/cam/dbatexports/weighted-no-orient-dbatreport.txt',
+        'data/prague2016/cam/dbatexports/fixed-no-orient-dbatreport.txt',
+    ],
     'dbatexports': [
         'data/dbat/dbatexports/camcal-dbatreport.txt',
         'data/dbat/dbatexports/camcal-dbatreport-model2.txt',
@@ -41,6 +49,8 @@ def main():
     for sub, files in FILES.items():
         for f in files:
             rel = f.split(sub + '/', 1)[1] if sub + '/' in f else os.path.basename(f)
+            if sub == 'prague2016cam':
+                rel = f.split('data/prague2016/cam/', 1)[1]
             dst = os.path.join(HERE, sub, rel)
             os.makedirs(os.path.dirname(dst), exist_ok=True)
             shutil.copyfile(os.path.join(REF, f), dst)

@@ -150,3 +150,20 @@ def test_all_models_golden_sigma0(model, sigma0):
     assert ok
     assert abs(s0 - sigma0) < 6e-6 * (10 if sigma0 == 1.6148 else 1)
     assert E.numParams == int(re.search(r'Number of params:\s+(\d+)', rep).group(1))
+
+
+PRAGUE = os.path.join(os.path.dirname(GOLD), 'prague2016cam')
+
+
+@pytest.mark.parametrize('stub,sigma0,nparams,nobs,last', [('weighted', 1.60984, 426, 4160, 98.3715),
+                                                           ('fixed', 1.78095, 414, 4148, 108.827)])
+def test_prague2016_cam_golden(stub, sigma0, nparams, nobs, last):
+    """data/prague2016/cam/dbatexports/{weighted,fixed}-no-orient-dbatreport.txt: PhotoModeler export,
+    legacy model 1, fixed camera, fixed / weighted control points (12 prior OP observations)."""
+    s = loaders.prague_cam_struct(PRAGUE, stub)
+    s, ok, iters, s0, E = bundle(s, 'gna')
+    assert ok
+    assert abs(s0 - sigma0) < 6e-6
+    assert (E.numParams, E.numObs) == (nparams, nobs)
+    assert E.redundancy == 3734
+    assert abs(E.res[-1] - last) < 6e-4
