@@ -49,35 +49,52 @@ def parse():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md): one
+    long-running `nvidia-smi -lms 50` whose lines are collected by this thread."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+        self.t_mark = None
 
     def run(self):
-        while not self.stop_flag:
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                line = line.strip()
+                if line:
+                    self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
+        except Exception:
+            pass
+
+    def mark(self):
+        """Only samples taken after this call count (start of the timed region)."""
+        self.t_mark = time.perf_counter()
+
+    def stop(self):
+        self.stop_flag = True
+        if self.proc is not None:
             try:
-                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                      '--format=csv,noheader,nounits'], capture_output=True, text=True,
-                                     timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(',')])
+                self.proc.kill()
             except Exception:
                 pass
-            time.sleep(0.1)
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
+        rows = [r for t, r in self.rows if self.t_mark is None or t >= self.t_mark]
+        sm = [float(r[0]) for r in rows if r and r[0].replace('.', '').isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) > 1 and r[1].replace('.', '').isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({names[k] for r in self.rows if len(r) >= 7 for k in range(4)
+        reasons = sorted({names[k] for r in rows if len(r) >= 7 for k in range(4)
                           if r[3 + k].lower().startswith('active')})
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None,
-                'reasons': reasons, 'samples': len(self.rows)}
+                'reasons': reasons, 'samples': len(rows)}
 
 
 def cpu_lm_iteration_sample(nImg=100, nOP=20000, iters=2):
@@ -233,12 +250,13 @@ def main():
     P.normal_step(x0, lam, trial=True, accept=False, want_p=False)       # upload x0
     timed(args.warmup, True)
     P.normal_step(x0, lam, trial=True, accept=False, want_p=False)       # restart the path at x0
+    sampler.mark()
     wall, dev_ms, launches = timed(args.steps, True)
     phases = P.phase_times() if hasattr(P, 'phase_times') else {}
     # end-to-end arm (host x in, host p out every step)
     timed(min(args.warmup, 3), False)
     wall_e2e, _, _ = timed(args.steps, False)
-    sampler.stop_flag = True
+    sampler.stop()
 
     t = torch.tensor([wall, wall_e2e, float(np.sum(dev_ms))], dtype=torch.float64, device='cuda')
     if world > 1:

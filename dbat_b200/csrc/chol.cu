@@ -9,6 +9,7 @@
 // The two GEMM shapes share one 128x128x16 double-buffered cp.async kernel ("NT": both
 // operands column-major, C = beta*C + alpha*A*B').
 #include <cstdio>
+#include <cstdlib>
 #include "launch.h"
 
 #define NB 128
@@ -155,8 +156,8 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
     extern __shared__ __align__(16) double sm[];
     double* As = sm;                    // [128][PLD] row-major
     double* dg = sm + NB * PLD;         // [128] diagonal of inv(L)
-    double* Xd = dg + NB;               // [16][17] inverse of the current diagonal block
-    double* Tb = Xd + PB * 17;          // [7][16][17] scratch for the inverse
+    double* rd = dg + NB;               // [16] reciprocal pivots of the current diagonal block (+ pad to 16*17)
+    double* Tb = rd + PB * 17;          // [7][16][17] scratch for the inverse
     double* colb = Tb + 7 * PB * 17;    // [2][16] column exchange buffer of the diagonal-block factorisation
     double* XdAll = colb + 2 * PB;      // [8][16][17] inverses of all diagonal blocks, zero above the diagonal
     __shared__ int s_bad;
@@ -189,14 +190,19 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
             for (int half = 0; half < 2; ++half) {
                 const int i0 = c0 + 8 * (warp + 8 * half);
                 if (i0 < NB) {
-                    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+                    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;     // two independent accumulator sets:
+                    double e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0;     // halves the dependent DMMA chain
                     const double* Ap = As + (i0 + fr) * PLD + fk;
-#pragma unroll 4
-                    for (int k0 = 0; k0 < c0; k0 += 4) {
+#pragma unroll 2
+                    for (int k0 = 0; k0 < c0; k0 += 8) {
                         const double a = Ap[k0], b0 = Bp0[k0], b1 = Bp1[k0];
+                        const double a2 = Ap[k0 + 4], b02 = Bp0[k0 + 4], b12 = Bp1[k0 + 4];
                         dmma(c00, c01, a, b0);
                         dmma(c10, c11, a, b1);
+                        dmma(e00, e01, a2, b02);
+                        dmma(e10, e11, a2, b12);
                     }
+                    c00 += e00; c01 += e01; c10 += e10; c11 += e11;
                     double* Cp = As + (i0 + fr) * PLD + c0 + 2 * fk;
                     Cp[0] -= c00; Cp[1] -= c01; Cp[8] -= c10; Cp[9] -= c11;
                 }
@@ -206,22 +212,27 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
         TICK(1)
         if (t < 32) {                                   // (2) 16x16 diagonal block, lane = row
             // Row r lives in registers; the finished column j travels through a small double-
-            // buffered shared array (one STS + broadcast LDS per step instead of 15 shuffles).
+            // buffered shared array.  The next pivot is taken from lane j+1's own registers
+            // (cand), so the pivot chain does not wait for the shared-memory exchange.
             const int r = t & 15;
-            double row[PB], invd[PB];
+            double row[PB];
 #pragma unroll
             for (int c = 0; c < PB; ++c) row[c] = As[(c0 + r) * PLD + c0 + c];
+            double d = __shfl_sync(0xffffffffu, row[0], 0);
 #pragma unroll
             for (int j = 0; j < PB; ++j) {
-                const double d = __shfl_sync(0xffffffffu, row[j], j);
                 const double inv = rsqrt(d);
                 const double l = d * inv;
-                invd[j] = inv;
                 if (t == 0) {
                     if (!(d > 0.0)) s_bad = 1;
                     if (blk * NB + c0 + j < nvalid) { s_min = fmin(s_min, l); s_max = fmax(s_max, l); }
+                    rd[j] = inv;
                 }
                 row[j] = (r == j) ? l : (r > j ? row[j] * inv : 0.0);
+                if (j + 1 < PB) {
+                    const double cand = row[j + 1] - row[j] * row[j];      // exact for lane j+1
+                    d = __shfl_sync(0xffffffffu, cand, j + 1);
+                }
                 double* cb = colb + (j & 1) * PB;
                 if (t < PB) cb[r] = row[j];
                 __syncwarp();
@@ -234,9 +245,28 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
 #pragma unroll
                 for (int cc = 0; cc < PB; ++cc) if (cc <= r) As[(c0 + r) * PLD + c0 + cc] = row[cc];
             }
-            __syncwarp();
-            // inverse of the block: lane c builds column c of X = L^-1 (rows of L are broadcast reads)
-            const int c = r;
+        }
+        __syncthreads();
+        TICK(2)
+        if (t < NB) {
+            if (t >= c0 + PB) {                         // (3) rows below: solve x L_dd' = a (right-looking)
+                double* rowp = As + t * PLD + c0;
+                double a[PB];
+#pragma unroll
+                for (int k = 0; k < PB; ++k) a[k] = rowp[k];
+#pragma unroll
+                for (int j = 0; j < PB; ++j) {
+                    a[j] *= rd[j];
+#pragma unroll
+                    for (int k = j + 1; k < PB; ++k) a[k] -= a[j] * As[(c0 + k) * PLD + c0 + j];
+                }
+#pragma unroll
+                for (int j = 0; j < PB; ++j) rowp[j] = a[j];
+            }
+        } else if (t < NB + 32) {
+            // concurrently (warp 4): inverse of the diagonal block for the X phase; lane c builds
+            // column c of X = L_dd^-1 (rows of L are broadcast reads)
+            const int c = t & 15;
             double x[PB];
 #pragma unroll
             for (int rr = 0; rr < PB; ++rr) {
@@ -246,35 +276,17 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
                 for (int k = 0; k < rr; ++k) {
                     if (k & 1) s1 -= Lr[k] * x[k]; else s0 -= Lr[k] * x[k];
                 }
-                x[rr] = (rr >= c) ? (s0 + s1) * invd[rr] : 0.0;
+                x[rr] = (rr >= c) ? (s0 + s1) * rd[rr] : 0.0;
             }
-            if (t < PB) {
+            if (t < NB + PB) {
                 double* Xa = XdAll + (c0 / PB) * PB * 17;
 #pragma unroll
-                for (int rr = 0; rr < PB; ++rr) { Xd[rr * 17 + c] = x[rr]; Xa[rr * 17 + c] = x[rr]; }   // zero above the diagonal
+                for (int rr = 0; rr < PB; ++rr) {
+                    Xa[rr * 17 + c] = x[rr];                          // zero above the diagonal
+                    if (rr > c) As[(c0 + c) * PLD + c0 + rr] = x[rr];  // transposed, for the X phase
+                }
+                dg[c0 + c] = x[c];
             }
-        }
-        __syncthreads();
-        TICK(2)
-        if (t < NB && t >= c0 + PB) {                   // (3) rows below: row * inv(L_dd)' = row * Xd'
-            double* rowp = As + t * PLD + c0;
-            double a[PB], o[PB];
-#pragma unroll
-            for (int k = 0; k < PB; ++k) a[k] = rowp[k];
-#pragma unroll
-            for (int j = 0; j < PB; ++j) {
-                double sacc = 0.0;
-#pragma unroll
-                for (int k = 0; k <= j; ++k) sacc += a[k] * Xd[j * 17 + k];
-                o[j] = sacc;
-            }
-#pragma unroll
-            for (int j = 0; j < PB; ++j) rowp[j] = o[j];
-        }
-        if (t >= NB && t < NB + PB) {                   // keep the block inverse for the X phase
-            const int c = t - NB;
-            dg[c0 + c] = Xd[c * 17 + c];
-            for (int rr = c + 1; rr < PB; ++rr) As[(c0 + c) * PLD + c0 + rr] = Xd[rr * 17 + c];
         }
         __syncthreads();
         TICK(3)
@@ -371,7 +383,12 @@ void chol_factor(CholWork& w, double* A, cudaStream_t st) {
     const int psmem = (NB * PLD + NB + PB * 17 + 7 * PB * 17 + 2 * PB + 8 * PB * 17) * 8;
     if (!attr) {
         cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
-        cudaStreamCreateWithFlags(&g_aux, cudaStreamNonBlocking);
+        {   // the look-ahead stream carries the critical path: its CTAs must be dispatched ahead of the
+            // remaining CTAs of the trailing update running on the main stream
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            cudaStreamCreateWithPriority(&g_aux, cudaStreamNonBlocking, hi);
+        }
         cudaEventCreateWithFlags(&g_evA, cudaEventDisableTiming);
         cudaEventCreateWithFlags(&g_evB, cudaEventDisableTiming);
         attr = true;
@@ -397,6 +414,24 @@ void chol_factor(CholWork& w, double* A, cudaStream_t st) {
     //   k+2 : column block k+2 -= L(:,k:k+1) L(k+2,k:k+1)'  (K=256), then potrf + panel solve on the
     //         aux stream while the main stream updates the remaining columns >= k+3 with K=256.
     panel_step(0, st);
+    static int pair_mode = -1;
+    if (pair_mode < 0) { const char* e = getenv("DBAT_CHOL_PAIR"); pair_mode = (e && e[0] == '1') ? 1 : 0;   // default: single-step (faster on B200: 6.7 vs 7.3 ms at n=6002) }
+    if (!pair_mode) {
+        // single-step look-ahead: every potrf + panel solve runs on the aux stream under the
+        // trailing update (K = 128) of the previous step
+        for (int k = 0; k + 1 < nb; ++k) {
+            const int rem = nb - k - 1;
+            double* Apanel = diag(k) + NB;
+            gemm_nt(Apanel, ld, Apanel, ld, diag(k + 1), ld, rem, 1, NB, -1.0, 1.0, false, st);
+            cudaEventRecord(g_evA, st);
+            cudaStreamWaitEvent(g_aux, g_evA, 0);
+            panel_step(k + 1, g_aux);
+            cudaEventRecord(g_evB, g_aux);
+            if (rem > 1) gemm_nt(Apanel + NB, ld, Apanel + NB, ld, diag(k + 2), ld, rem - 1, rem - 1, NB, -1.0, 1.0, true, st);
+            cudaStreamWaitEvent(st, g_evB, 0);
+        }
+        return;
+    }
     int k = 0;
     for (; k + 1 < nb; k += 2) {
         const int rem1 = nb - k - 1;                       // row blocks below block k
