@@ -369,6 +369,7 @@ void chol_free(CholWork& w) {
     if (w.info) cudaFree(w.info);
     if (w.minmax) cudaFree(w.minmax);
     if (w.panel) cudaFree(w.panel);
+    if (w.graphExec) cudaGraphExecDestroy((cudaGraphExec_t)w.graphExec);
     w = CholWork();
 }
 
@@ -378,7 +379,7 @@ static cudaEvent_t g_evA = nullptr, g_evB = nullptr;
 // Right-looking blocked Cholesky with one step of look-ahead: as soon as block column k+1 has
 // received the update of step k, its potrf + panel solve run on a second stream while the main
 // stream finishes the rest of the trailing update of step k.
-void chol_factor(CholWork& w, double* A, cudaStream_t st) {
+static void chol_factor_body(CholWork& w, double* A, cudaStream_t st) {
     static bool attr = false;
     const int psmem = (NB * PLD + NB + PB * 17 + 7 * PB * 17 + 2 * PB + 8 * PB * 17) * 8;
     if (!attr) {
@@ -450,6 +451,38 @@ void chol_factor(CholWork& w, double* A, cudaStream_t st) {
             gemm_nt(P2 + NB, ld, P2 + NB, ld, diag(k + 3), ld, rem2 - 1, rem2 - 1, 2 * NB, -1.0, 1.0, true, st);
         cudaStreamWaitEvent(st, g_evB, 0);
     }
+}
+
+
+// The launch sequence of a factorisation is static for a given (matrix, size): it is captured into
+// a CUDA graph on its second use and replayed afterwards, which removes most of the host launch
+// latency from the 47-step dependency chain.  DBAT_CHOL_GRAPH=0 disables this.
+void chol_factor(CholWork& w, double* A, cudaStream_t st) {
+    static int use_graph = -1;
+    if (use_graph < 0) { const char* e = getenv("DBAT_CHOL_GRAPH"); use_graph = (e && e[0] == '0') ? 0 : 1; }
+    if (!use_graph || w.nb < 4) { chol_factor_body(w, A, st); return; }
+    if (w.graphExec && w.graphA == A && w.graphStream == st) {
+        if (cudaGraphLaunch((cudaGraphExec_t)w.graphExec, st) == cudaSuccess) { count_launch(w.graphLaunches); return; }
+        cudaGetLastError();
+    }
+    if (w.seen != A) {                       // first use with this matrix: plain launch (also warms the statics)
+        w.seen = A;
+        chol_factor_body(w, A, st);
+        return;
+    }
+    if (w.graphExec) { cudaGraphExecDestroy((cudaGraphExec_t)w.graphExec); w.graphExec = nullptr; }
+    const int64_t l0 = g_dbat_launches;
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); chol_factor_body(w, A, st); return; }
+    chol_factor_body(w, A, st);
+    if (cudaStreamEndCapture(st, &graph) != cudaSuccess || !graph) { cudaGetLastError(); w.seen = nullptr; chol_factor_body(w, A, st); return; }
+    cudaGraphExec_t exec = nullptr;
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(graph); w.seen = nullptr; chol_factor_body(w, A, st); return; }
+    cudaGraphDestroy(graph);
+    w.graphExec = exec; w.graphA = A; w.graphStream = st; w.graphLaunches = (int)(g_dbat_launches - l0);
+    g_dbat_launches = l0;                    // the capture itself launched nothing
+    cudaGraphLaunch(exec, st);
+    count_launch(w.graphLaunches);
 }
 
 // ---------------------------------------------------------------------------------------------

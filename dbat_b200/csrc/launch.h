@@ -48,6 +48,9 @@ struct CholWork {
     int* info = nullptr;            // device flag: 0 ok, k>0 = first non-positive pivot (1-based)
     double* minmax = nullptr;       // device: [0]=min pivot, [1]=max pivot (of L's diagonal)
     double* panel = nullptr;        // ld x 128 workspace for the panel solve
+    void* graphExec = nullptr;      // captured launch sequence of chol_factor (cudaGraphExec_t)
+    const double* graphA = nullptr; const double* seen = nullptr; cudaStream_t graphStream = nullptr;
+    int graphLaunches = 0;
 };
 void chol_alloc(CholWork& w, int n, int ld);
 void chol_free(CholWork& w);
