@@ -1221,8 +1221,14 @@ extern "C" int dbat_dense_chol_solve(int64_t n, const double* A, const double* b
     }
     if (ms_out) *ms_out = best;
 #ifdef POTRF_PROFILE
-    { double pr[10]; cudaMemcpy(pr, w.minmax, sizeof(pr), cudaMemcpyDeviceToHost);
-      printf("potrf cycles: load %.0f | update %.0f | diag %.0f | rows %.0f | writeback %.0f | Xoff %.0f | out %.0f\n", pr[2], pr[3], pr[4], pr[5], pr[6], pr[7], pr[8]); }
+    {   // per warp, per panel: [end of D / W] [after S1] [end of R] [after S2], then the end of the tail
+        double pr[16 + 16 * 40]; cudaMemcpy(pr, w.minmax, sizeof(pr), cudaMemcpyDeviceToHost);
+        for (int wp = 0; wp < 16; ++wp) {
+            printf("potrf trace warp %d:", wp);
+            for (int k = 0; k < 33; ++k) printf(" %.0f", pr[16 + wp * 40 + k]);
+            printf("\n");
+        }
+    }
 #endif
     cudaError_t e = cudaDeviceSynchronize();
     chol_free(w); cudaFree(dA); cudaFree(dA0); cudaFree(drhs); cudaFree(dx);

@@ -14,7 +14,9 @@
 
 #define NB 128
 #define KS 16                 // k-slice per pipeline stage
-#define SLD 136               // smem row stride (doubles): 128 + 8 -> conflict-free fragment loads
+#ifndef SLD
+#define SLD 132               // smem row stride (doubles) = 4 mod 16: the 8-byte fragment loads of a half-warp
+#endif                        // (addresses (lane&3)*SLD + lane/4) fall into 16 distinct 8-byte banks
 #define GEMM_STAGES 3
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
@@ -35,7 +37,9 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // lower triangle; otherwise blockIdx.x = ti (128 rows), blockIdx.y = tj (64 columns).
 #define TN 64
 #define GEMM_SMEM (GEMM_STAGES * KS * (SLD + SLDB) * 8)
-#define SLDB 72               // 64 + 8
+#ifndef SLDB
+#define SLDB 68               // 64 + 4, same argument
+#endif
 __global__ void __launch_bounds__(256, 2)
 k_gemm_nt(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
           double* __restrict__ C, int ldc, int K, double alpha, double beta, int tri) {
@@ -151,8 +155,8 @@ static void gemm_nt(const double* A, int lda, const double* B, int ldb, double* 
 #define PLD 129
 #define PB 16
 __global__ void __launch_bounds__(256, 1)
-k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, int nvalid,
-           int* __restrict__ info, double* __restrict__ minmax) {
+k_potrf128_v1(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, int nvalid,
+              int* __restrict__ info, double* __restrict__ minmax) {
     extern __shared__ __align__(16) double sm[];
     double* As = sm;                    // [128][PLD] row-major
     double* dg = sm + NB * PLD;         // [128] diagonal of inv(L)
@@ -357,11 +361,403 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
 #endif
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_potrf128: Cholesky of one 128x128 diagonal block + inverse of its factor, organised around
+// the only inherently serial part, the 128 pivots.
+//
+//   warp 0 ("pivot warp")   D(p): factors the 16x16 diagonal block of panel p in registers
+//                           (lane r < 16 holds row r; lanes 16..31 carry the columns of the
+//                           identity through the same column sweep, so inv(L_pp) falls out of the
+//                           same instruction stream), then after the panel solve updates the next
+//                           diagonal block first (U-critical) and goes straight on to D(p+1).
+//   warps 1..7 ("workers")  W(p), running under D(p+1): the rest of the rank-16 trailing update
+//                           of panel p, row block p of inv(L) (X_p,0:p = -inv(L_pp) L_p,0:p X_0:p,0:p),
+//                           and the write-back of the finished panel / inverse rows to global.
+//   all warps               R(p): L_ip = A_ip inv(L_pp)' for the 8-row tiles below the block (DMMA).
+//
+// Shared tile As is column-major with stride 132 (= 4 mod 16: every DMMA fragment load below is
+// bank-conflict free).  L lives in the lower triangle; X = inv(L) is stored transposed in the
+// strictly upper triangle (X(r,c), r > c, at As[r*PLD2 + c]), its diagonal blocks also zero-padded
+// in XdAll for use as DMMA operands.
+// ---------------------------------------------------------------------------------------------
+#define PLD2 132
+#define XLD 20
+#define TLD 12
+#define POTRF_SMEM_DOUBLES (NB * PLD2 + 8 * PB * XLD + 2 * PB + 32)
+
+__device__ __forceinline__ double rsqrt_nr(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));      // ~20 bits
+    double h = d * y, e = fma(-h, y, 1.0);
+    y = fma(0.5 * y, e, y);                                        // ~40 bits
+    h = d * y; e = fma(-h, y, 1.0);
+    return fma(0.5 * y, e, y);                                     // full precision
+}
+
+#ifdef POTRF_PROFILE
+#define PTRACE(slot) { if (lane == 0 && blk == 1) ptrace[(slot)] = (double)(clock64() - tstart); }
+#else
+#define PTRACE(slot)
+#endif
+
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bar_sync_named(int id, int n) { asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive_named(int id, int n) { asm volatile("bar.arrive %0, %1;" :: "r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, int bytes) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+
+// D(p): one warp.  As holds the fully updated diagonal block at (c0, c0).  The pivot chain runs
+// in LDL' form: v(:,j) is the unscaled column u(:,j), d_j the pivot.  Between two pivots there are
+// only: the hardware reciprocal seed y of d_j, one quartic Newton step folded into the scaled
+// column entry  w = u(j+1,j)/d_j = (u y)(1+e)(1+e^2), e = 1 - d y  (relative error e^4), the update
+// d_{j+1} = a(j+1,j+1) - w u(j+1,j) and one shuffle.  Square roots (L(:,j) = u(:,j)/sqrt(d_j)) are
+// off the chain.  Lanes 16..31 carry the columns of the identity through the same sweep: they end
+// up holding inv(L_pp) (b_r -= (b_j/d_j) u(r,j) is the same update, x_j = b_j/sqrt(d_j) the same
+// scaling).
+__device__ __forceinline__ void potrf_diag16(double* As, double* Xd, double* colb, int c0,
+                                             int lane, int gcol0, int nvalid, double& lmin, double& lmax,
+                                             int& bad) {
+    const int r = lane & 15;
+    const bool isX = lane >= 16;
+    double v[PB];
+#pragma unroll
+    for (int c = 0; c < PB; ++c) {
+        const double a = As[(c0 + c) * PLD2 + c0 + r];
+        v[c] = isX ? (c == r ? 1.0 : 0.0) : a;
+    }
+    double d = __shfl_sync(0xffffffffu, v[0], 0);
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+        double* cb = colb + (j & 1) * PB;
+        if (!isX) cb[r] = v[j];                  // unscaled column j, final since the end of step j-1
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+        const double e = fma(-d, y, 1.0);        // 1/d = y (1 + e + e^2 + ...), |e| ~ 2^-20
+        const double vy = v[j] * y;
+        const double dj = d;
+        if (j + 1 < PB) {
+            // next pivot (lane j+1): a - u^2/d with 1/d = y (1 + t), t = e + e^2  (error e^3);
+            // only e -> t -> cand sit between the reciprocal seed and the shuffle
+            const double q = v[j] * vy;
+            const double base = v[j + 1] - q;
+            const double t = fma(e, e, e);
+            const double cand = fma(-q, t, base);
+            d = __shfl_sync(0xffffffffu, cand, j + 1);
+        }
+        const double e2 = e * e;
+        const double vy1 = fma(vy, e, vy);
+        const double w = fma(vy1, e2, vy1);      // lanes r > j: u(r,j)/d_j ; X lanes: b_j/d_j  (error e^4)
+        __syncwarp();
+#pragma unroll
+        for (int c = j + 1; c < PB; ++c) v[c] = fma(-w, cb[c], v[c]);
+        // off the chain: scale column j
+        const double isd = rsqrt_nr(dj);
+        if (!(dj > 0.0)) bad = 1;
+        if (gcol0 + j < nvalid) { const double l = dj * isd; lmin = fmin(lmin, l); lmax = fmax(lmax, l); }
+        v[j] *= isd;
+    }
+    if (!isX) {
+#pragma unroll
+        for (int c = 0; c < PB; ++c) if (c <= r) As[(c0 + c) * PLD2 + c0 + r] = v[c];
+    } else {
+#pragma unroll
+        for (int j = 0; j < PB; ++j) {
+            Xd[j * XLD + r] = v[j];                                   // zero above the diagonal
+            if (j > r) As[(c0 + j) * PLD2 + c0 + r] = v[j];          // X(j, r) transposed into the upper triangle
+        }
+    }
+}
+
+// R(p) for NT (1 or 2) 8-row tiles below the diagonal block: L(i, panel) = A(i, panel) * inv(L_pp)',
+// one accumulator per k-step (all DMMAs independent).  The result stays in res[e][tn][0..1]
+// (C fragments: row lane/4, panel columns 8tn + 2(lane%4) + {0,1}) and is stored to As.
+template <int NT>
+__device__ __forceinline__ void potrf_rtiles(double* As, const double* Xd, int c0, int q0, int q1, int lane,
+                                             double (&res)[2][2][2]) {
+    const int fr = lane >> 2, fk = lane & 3;
+    const double* pb = Xd + fr * XLD + fk;                               // B(k,n) = Xd(n,k)
+    const double* pa = As + (c0 + fk) * PLD2 + c0 + PB + fr;
+    double r[NT][2][4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double b0v = pb[4 * k], b1v = pb[8 * XLD + 4 * k];
+#pragma unroll
+        for (int e = 0; e < NT; ++e) {
+            const double a = pa[4 * k * PLD2 + 8 * (e ? q1 : q0)];
+            r[e][0][k][0] = r[e][0][k][1] = r[e][1][k][0] = r[e][1][k][1] = 0.0;
+            dmma(r[e][0][k][0], r[e][0][k][1], a, b0v);
+            dmma(r[e][1][k][0], r[e][1][k][1], a, b1v);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < NT; ++e) {
+        double* pc = As + (c0 + 2 * fk) * PLD2 + c0 + PB + 8 * (e ? q1 : q0) + fr;
+#pragma unroll
+        for (int tn = 0; tn < 2; ++tn) {
+            res[e][tn][0] = (r[e][tn][0][0] + r[e][tn][1][0]) + (r[e][tn][2][0] + r[e][tn][3][0]);
+            res[e][tn][1] = (r[e][tn][0][1] + r[e][tn][1][1]) + (r[e][tn][2][1] + r[e][tn][3][1]);
+            pc[8 * tn * PLD2] = res[e][tn][0];
+            pc[(8 * tn + 1) * PLD2] = res[e][tn][1];
+        }
+    }
+}
+
+// U(p), one group of four 8x8 tiles (list positions t0..t0+3 of the trailing lower triangle; the
+// first three positions belong to the next diagonal block and are done by the pivot warp):
+// A(i,j) -= L(i,panel p) L(j,panel p)', one accumulator per k-step: 16 independent DMMAs.
+__device__ __forceinline__ void potrf_update_group(double* As, const unsigned char* tij, int p, int t0, int ntile,
+                                                   int lane) {
+    const int fr = lane >> 2, fk = lane & 3;
+    const int c0 = PB * p, b0 = c0 + PB;
+    const double* pa0 = As + (c0 + fk) * PLD2 + b0 + fr;
+    int ti[4], tj[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const int t = min(t0 + e, ntile - 1);
+        ti[e] = tij[2 * t]; tj[e] = tij[2 * t + 1];
+    }
+    double acc[4][4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            acc[e][k][0] = acc[e][k][1] = 0.0;
+            dmma(acc[e][k][0], acc[e][k][1], pa0[4 * k * PLD2 + 8 * ti[e]], pa0[4 * k * PLD2 + 8 * tj[e]]);
+        }
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        if (t0 + e < ntile) {
+            double* pc = As + (b0 + 8 * tj[e] + 2 * fk) * PLD2 + b0 + 8 * ti[e] + fr;
+            pc[0] -= (acc[e][0][0] + acc[e][1][0]) + (acc[e][2][0] + acc[e][3][0]);
+            pc[PLD2] -= (acc[e][0][1] + acc[e][1][1]) + (acc[e][2][1] + acc[e][3][1]);
+        }
+    }
+}
+
+// inv(L), right-looking by row blocks.  The slot of X(ib, jb) (ib > jb; transposed in the upper
+// triangle: X(r,c) at As[r*PLD2 + c]) first accumulates T(ib,jb) = sum_{jb<=kb<ib} L(ib,kb) X(kb,jb).
+// One task = one 8-column tile (jb, tn) of row block p:
+//   finalise  X(p, tile) = -inv(L_pp) T(p, tile)            (jb < p; needs D(p))
+//   propagate T(ib, tile) += L(ib, p) X(p, tile), ib > p    (needs R(p))
+__device__ __forceinline__ void potrf_x_task(double* As, const double* XdAll, int p, int x, int lane,
+                                             double* __restrict__ out) {
+    const int fr = lane >> 2, fk = lane & 3;
+    const int c0 = PB * p;
+    const int jb = x >> 1, tn = x & 1;
+    const int col0 = PB * jb + 8 * tn;
+    double bx[4];
+    if (jb < p) {
+        const double* pt = As + (c0 + fk) * PLD2 + col0 + fr;                  // T(k, n)
+        const double* pxa = XdAll + p * PB * XLD + fr * XLD + fk;             // Xd_p(i, k)
+        double x0[4][2], x1[4][2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const double b = pt[4 * k * PLD2];
+            x0[k][0] = x0[k][1] = x1[k][0] = x1[k][1] = 0.0;
+            dmma(x0[k][0], x0[k][1], pxa[4 * k], b);
+            dmma(x1[k][0], x1[k][1], pxa[8 * XLD + 4 * k], b);
+        }
+        const double xa = -((x0[0][0] + x0[1][0]) + (x0[2][0] + x0[3][0]));
+        const double xb = -((x0[0][1] + x0[1][1]) + (x0[2][1] + x0[3][1]));
+        const double xc = -((x1[0][0] + x1[1][0]) + (x1[2][0] + x1[3][0]));
+        const double xd = -((x1[0][1] + x1[1][1]) + (x1[2][1] + x1[3][1]));
+        double* px = As + (c0 + fr) * PLD2 + col0 + 2 * fk;                    // X(c0 + i, col) transposed
+        px[0] = xa; px[1] = xb;
+        px[8 * PLD2] = xc; px[8 * PLD2 + 1] = xd;
+        double* po = out + (size_t)(col0 + 2 * fk) * NB + c0 + fr;
+        po[0] = xa; po[NB] = xb;
+        po[8] = xc; po[NB + 8] = xd;
+        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bx[k] = pt[4 * k * PLD2];                 // X(p)(k, n), now final
+    } else {
+        const double* pd = XdAll + p * PB * XLD + fk * XLD + 8 * tn + fr;     // Xd_p(k, 8tn + n)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bx[k] = pd[4 * k * XLD];
+    }
+    const double* pa = As + (c0 + fk) * PLD2 + fr;                             // L(row, c0 + k)
+#pragma unroll 2
+    for (int ib = p + 1; ib < NB / PB; ++ib) {
+        double a0[4][2], a1[4][2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            a0[k][0] = a0[k][1] = a1[k][0] = a1[k][1] = 0.0;
+            dmma(a0[k][0], a0[k][1], pa[4 * k * PLD2 + PB * ib], bx[k]);
+            dmma(a1[k][0], a1[k][1], pa[4 * k * PLD2 + PB * ib + 8], bx[k]);
+        }
+        double* pc = As + (PB * ib + fr) * PLD2 + col0 + 2 * fk;
+        const double s00 = (a0[0][0] + a0[1][0]) + (a0[2][0] + a0[3][0]), s01 = (a0[0][1] + a0[1][1]) + (a0[2][1] + a0[3][1]);
+        const double s10 = (a1[0][0] + a1[1][0]) + (a1[2][0] + a1[3][0]), s11 = (a1[0][1] + a1[1][1]) + (a1[2][1] + a1[3][1]);
+        if (jb == p) { pc[0] = s00; pc[1] = s01; pc[8 * PLD2] = s10; pc[8 * PLD2 + 1] = s11; }
+        else { pc[0] += s00; pc[1] += s01; pc[8 * PLD2] += s10; pc[8 * PLD2 + 1] += s11; }
+    }
+}
+
+// W(p): the tasks of one round, handed out through a shared counter (X tasks first, they are longer).
+__device__ __forceinline__ void potrf_worker(double* As, const double* XdAll, const unsigned char* tij, int* ctr,
+                                             int p, int lane, double* __restrict__ out) {
+    const int m = 14 - 2 * p;
+    const int ntile = m * (m + 1) / 2;
+    const int nX = p < NB / PB - 1 ? 2 * (p + 1) : 2 * p;       // the last row block has nothing to propagate to
+    const int nU = ntile > 3 ? (ntile - 3 + 3) / 4 : 0;
+    for (;;) {
+        int task = 0;
+        if (lane == 0) task = atomicAdd(ctr + p, 1);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if (task >= nX + nU) break;
+        if (task < nX) potrf_x_task(As, XdAll, p, task, lane, out);
+        else potrf_update_group(As, tij, p, 3 + 4 * (task - nX), ntile, lane);
+    }
+}
+
+// IO warp, after panel p is final: its columns go back to global with one bulk copy each
+// (lower triangle; for odd columns the copy starts one row above the diagonal to stay 16-byte
+// aligned - the strictly upper triangle of a diagonal block of A is scratch), and the 16x16
+// diagonal block of inv(L).  The zeros of inv(L) above the diagonal are never written: the
+// buffer is cleared once at allocation.
+__device__ __forceinline__ void potrf_io(const double* As, const double* XdAll, int p, int lane,
+                                         double* __restrict__ A, int lda, double* __restrict__ out) {
+    const int c0 = PB * p;
+    if (lane < PB) {
+        const int c = c0 + lane, rs = c & ~1;
+        bulk_store(A + (size_t)c * lda + rs, As + c * PLD2 + rs, (NB - rs) * 8);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int idx = lane + 32 * k, i = idx & 15, cc = idx >> 4;
+        if (cc <= i) out[(size_t)(c0 + cc) * NB + c0 + i] = XdAll[p * PB * XLD + i * XLD + cc];
+    }
+}
+
+#define POTRF_THREADS 512
+__global__ void __launch_bounds__(POTRF_THREADS, 1)
+k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, int nvalid,
+           int* __restrict__ info, double* __restrict__ minmax) {
+    extern __shared__ __align__(16) double sm[];
+    double* As = sm;                          // [128 columns][PLD2]
+    double* XdAll = As + NB * PLD2;           // [8][16][XLD]
+    double* colb = XdAll + 8 * PB * XLD;      // [2][16]
+    unsigned char* tij = (unsigned char*)(colb + 2 * PB);   // [105][2] (ti, tj) of the lower-triangular tile list
+    int* ctr = (int*)(tij + 224);             // [8] task counters
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    double* out = invL + (size_t)blk * NB * NB;
+    double lmin = 1e300, lmax = 0.0;
+    int bad = 0;
+#ifdef POTRF_PROFILE
+    const long long tstart = clock64();
+    double* ptrace = minmax + 16 + warp * 40;     // per warp: 4 stamps per panel
+#endif
+    // Roles (16 warps, 4 per scheduler).  Warp 0: pivots.  Warps 4, 8, 12 share its scheduler and
+    // FP64 pipe: warp 4 only moves data (write-backs), 8 and 12 only take part in the barriers.
+    // The other 12 warps are the DMMA workers.
+    const bool isPivot = warp == 0, isIO = warp == 4, isWorker = (warp & 3) != 0;
+    const int wid = (warp >> 2) * 3 + (warp & 3) - 1;        // worker id 0..11 (workers only)
+    // ---- load the lower triangle (16-byte chunks).  The pivot warp fetches only the first
+    //      diagonal block and starts as soon as that has landed.
+    if (isPivot) {
+        for (int idx = lane; idx < PB * (PB / 2); idx += 32) {
+            const int c = idx >> 3, ci = idx & 7;
+            cp_async16(As + c * PLD2 + 2 * ci, A + (size_t)c * lda + 2 * ci);
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncwarp();
+    } else {
+        for (int idx = t - 32; idx < NB * (NB / 2); idx += POTRF_THREADS - 32) {
+            const int c = idx >> 6, ci = idx & 63;
+            if (2 * ci + 1 >= c && !(c < PB && ci < PB / 2))
+                cp_async16(As + c * PLD2 + 2 * ci, A + (size_t)c * lda + 2 * ci);
+        }
+        cp_async_commit();
+        const int u = t - 32;
+        if (u < 105) {
+            int i = (int)((sqrtf(8.0f * u + 1.0f) - 1.0f) * 0.5f);
+            while ((i + 1) * (i + 2) / 2 <= u) ++i;
+            while (i * (i + 1) / 2 > u) --i;
+            tij[2 * u] = (unsigned char)i; tij[2 * u + 1] = (unsigned char)(u - i * (i + 1) / 2);
+        }
+        if (u >= 128 && u < 136) ctr[u - 128] = 0;
+    }
+    for (int p = 0; p < NB / PB; ++p) {
+        const int c0 = PB * p;
+        const int m = 14 - 2 * p;                 // 8-row tiles below the diagonal block
+        if (isPivot) {
+            potrf_diag16(As, XdAll + p * PB * XLD, colb, c0, lane, blk * NB + c0, nvalid, lmin, lmax, bad);
+        } else if (p > 0) {
+            if (isIO) potrf_io(As, XdAll, p - 1, lane, A, lda, out);
+            else if (isWorker) potrf_worker(As, XdAll, tij, ctr, p - 1, lane, out);
+        } else {
+            cp_async_wait<0>();
+        }
+        PTRACE(4 * p + 0)
+        fence_async_smem();
+        __syncthreads();                          // S1: D(p) and W(p-1) complete
+        if (isPivot) {
+            // the two row tiles the next diagonal block depends on, then that block's update
+            // straight from the result registers: with the panel columns taken in the order the
+            // C fragments hold them, (lane/4, lane%4) has the A and the B operand of every k-step
+            if (m >= 2) {
+                const int fr = lane >> 2, fk = lane & 3;
+                double R[2][2][2];
+                potrf_rtiles<2>(As, XdAll + p * PB * XLD, c0, 0, 1, lane, R);
+                fence_async_smem();
+                bar_arrive_named(1, POTRF_THREADS);
+                PTRACE(4 * p + 1)
+                double u[3][4][2];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const double a0 = R[0][k >> 1][k & 1], a1 = R[1][k >> 1][k & 1];
+                    u[0][k][0] = u[0][k][1] = u[1][k][0] = u[1][k][1] = u[2][k][0] = u[2][k][1] = 0.0;
+                    dmma(u[0][k][0], u[0][k][1], a0, a0);
+                    dmma(u[1][k][0], u[1][k][1], a1, a0);
+                    dmma(u[2][k][0], u[2][k][1], a1, a1);
+                }
+                const int b0 = c0 + PB;
+                double* pc = As + (b0 + 2 * fk) * PLD2 + b0 + fr;
+                pc[0] -= (u[0][0][0] + u[0][1][0]) + (u[0][2][0] + u[0][3][0]);
+                pc[PLD2] -= (u[0][0][1] + u[0][1][1]) + (u[0][2][1] + u[0][3][1]);
+                pc[8] -= (u[1][0][0] + u[1][1][0]) + (u[1][2][0] + u[1][3][0]);
+                pc[PLD2 + 8] -= (u[1][0][1] + u[1][1][1]) + (u[1][2][1] + u[1][3][1]);
+                pc[8 * PLD2 + 8] -= (u[2][0][0] + u[2][1][0]) + (u[2][2][0] + u[2][3][0]);
+                pc[9 * PLD2 + 8] -= (u[2][0][1] + u[2][1][1]) + (u[2][2][1] + u[2][3][1]);
+                __syncwarp();
+            } else {
+                bar_arrive_named(1, POTRF_THREADS);
+            }
+            PTRACE(4 * p + 2)
+        } else {
+            if (isWorker && 2 + wid < m) {        // the other row tiles, one per worker
+                double R[2][2][2];
+                potrf_rtiles<1>(As, XdAll + p * PB * XLD, c0, 2 + wid, 2 + wid, lane, R);
+            }
+            fence_async_smem();
+            PTRACE(4 * p + 1)
+            bar_sync_named(1, POTRF_THREADS);     // S2: panel p final (the pivot warp only arrives)
+        }
+    }
+    // tail: finalise row block 7 of the inverse, last diagonal block (IO warp)
+    if (isIO) {
+        potrf_io(As, XdAll, NB / PB - 1, lane, A, lda, out);
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    } else if (isWorker || isPivot) potrf_worker(As, XdAll, tij, ctr, NB / PB - 1, lane, out);
+    PTRACE(4 * 8 + 0)
+    if (t == 0) {
+        if (bad) atomicCAS(info, 0, blk + 1);
+        double omin = minmax[0], omax = minmax[1];
+        if (blk == 0) { omin = 1e300; omax = 0.0; }
+        minmax[0] = fmin(omin, lmin); minmax[1] = fmax(omax, lmax);
+    }
+}
+
 void chol_alloc(CholWork& w, int n, int ld) {
     w.n = n; w.ld = ld; w.nb = ld / NB;
     cudaMalloc(&w.invL, sizeof(double) * (size_t)w.nb * NB * NB);
+    cudaMemset(w.invL, 0, sizeof(double) * (size_t)w.nb * NB * NB);   // k_potrf128 never writes the zeros above the diagonal
     cudaMalloc(&w.info, sizeof(int));
-    cudaMalloc(&w.minmax, sizeof(double) * 16);
+    cudaMalloc(&w.minmax, sizeof(double) * (16 + 16 * 40));
     cudaMalloc(&w.panel, sizeof(double) * (size_t)ld * NB);
 }
 void chol_free(CholWork& w) {
@@ -381,9 +777,13 @@ static cudaEvent_t g_evA = nullptr, g_evB = nullptr;
 // stream finishes the rest of the trailing update of step k.
 static void chol_factor_body(CholWork& w, double* A, cudaStream_t st) {
     static bool attr = false;
-    const int psmem = (NB * PLD + NB + PB * 17 + 7 * PB * 17 + 2 * PB + 8 * PB * 17) * 8;
+    const int psmem1 = (NB * PLD + NB + PB * 17 + 7 * PB * 17 + 2 * PB + 8 * PB * 17) * 8;
+    const int psmem = POTRF_SMEM_DOUBLES * 8;
+    static int potrf_v1 = 0;
     if (!attr) {
+        { const char* e = getenv("DBAT_POTRF"); potrf_v1 = (e && e[0] == '1') ? 1 : 0; }
         cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
+        cudaFuncSetAttribute(k_potrf128_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem1);
         {   // the look-ahead stream carries the critical path: its CTAs must be dispatched ahead of the
             // remaining CTAs of the trailing update running on the main stream
             int lo = 0, hi = 0;
@@ -398,7 +798,8 @@ static void chol_factor_body(CholWork& w, double* A, cudaStream_t st) {
     const int ld = w.ld, nb = w.nb;
     auto diag = [&](int k) { return A + (size_t)k * NB * ld + (size_t)k * NB; };
     auto panel_step = [&](int k, cudaStream_t s) {        // potrf(k) + L_ik = A_ik inv(L_kk)' (in place)
-        k_potrf128<<<1, 256, psmem, s>>>(diag(k), ld, w.invL, k, w.n, w.info, w.minmax);
+        if (potrf_v1) k_potrf128_v1<<<1, 256, psmem1, s>>>(diag(k), ld, w.invL, k, w.n, w.info, w.minmax);
+        else k_potrf128<<<1, POTRF_THREADS, psmem, s>>>(diag(k), ld, w.invL, k, w.n, w.info, w.minmax);
         count_launch();
         const int rem = nb - k - 1;
         if (rem <= 0) return;
