@@ -31,18 +31,24 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
 
 // C(tile) = beta*C + alpha * A(rows of tile, 0:K) * B(rows of tile col, 0:K)'
-// CTA tile 128 x 64 (8 warps as 4 x 2, warp tile 32 x 32), 3-stage cp.async pipeline, two CTAs
-// per SM so that one CTA's C read-modify-write epilogue overlaps the other's main loop.
-// tile list: if tri!=0 the 1-D grid enumerates the tiles (ti, tj) with 64*tj <= 128*ti+127 of the
-// lower triangle; otherwise blockIdx.x = ti (128 rows), blockIdx.y = tj (64 columns).
-#define TN 64
-#define GEMM_SMEM (GEMM_STAGES * KS * (SLD + SLDB) * 8)
-#ifndef SLDB
-#define SLDB 68               // 64 + 4, same argument
-#endif
-__global__ void __launch_bounds__(256, 2)
-k_gemm_nt(const double* __restrict__ A, int lda, const double* __restrict__ B, int ldb,
-          double* __restrict__ C, int ldc, int K, double alpha, double beta, int tri) {
+// CTA tile BM x BN, one warp per 32 x 32 sub-tile (BM/32 warps along M, BN/32 along N), 3-stage
+// cp.async pipeline.  Smem strides BM+4 / BN+4 (= 4 mod 16): the 8-byte fragment loads of a
+// half-warp (addresses (lane&3)*stride + lane/4) fall into 16 distinct banks.
+//   <128, 64>  trailing update (two CTAs per SM: one CTA's C read-modify-write epilogue overlaps
+//              the other's main loop)
+//   < 64, 64>  the look-ahead column update on the critical path (4x the CTAs, 1/4 the latency)
+//   < 32,128>  panel solve on the critical path; the CTA owns whole rows and K spans the whole
+//              panel, so C may alias A (every A slice is in shared memory before the epilogue)
+// tile list: if tri != 0 the 1-D grid enumerates the tiles (ti, tj) with BN*tj <= BM*ti + BM-1 of
+// the lower triangle (BM = 2 BN only); otherwise blockIdx.x = ti, blockIdx.y = tj.
+template <int BM, int BN>
+__global__ void __launch_bounds__(BM * BN / 32, (BM * BN >= 8192) ? 2 : 3)
+k_gemm_nt(const double* A, int lda, const double* __restrict__ B, int ldb,
+          double* C, int ldc, int K, double alpha, double beta, int tri) {
+    constexpr int NT = BM * BN / 32;              // threads
+    constexpr int WM = BM / 32;                   // warps along M
+    constexpr int LA = BM + 4, LB = BN + 4;
+    constexpr int STAGE = KS * (LA + LB);
     extern __shared__ __align__(16) double sm[];
     int ti, tj;
     if (tri) {
@@ -52,13 +58,13 @@ k_gemm_nt(const double* __restrict__ A, int lda, const double* __restrict__ B, i
         while (ti * (ti + 1) > t) --ti;
         tj = t - ti * (ti + 1);
     } else { ti = blockIdx.x; tj = blockIdx.y; }
-    const double* Ag = A + (size_t)ti * NB;
-    const double* Bg = B + (size_t)tj * TN;
-    double* Cg = C + (size_t)tj * TN * ldc + (size_t)ti * NB;
+    const double* Ag = A + (size_t)ti * BM;
+    const double* Bg = B + (size_t)tj * BN;
+    double* Cg = C + (size_t)tj * BN * ldc + (size_t)ti * BM;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp & 3) * 32;      // 4 warps along M
-    const int wn = (warp >> 2) * 32;     // 2 warps along N
+    const int wm = (warp % WM) * 32;
+    const int wn = (warp / WM) * 32;
     double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -67,19 +73,19 @@ k_gemm_nt(const double* __restrict__ A, int lda, const double* __restrict__ B, i
 
     const int nk = K / KS;
     auto load_stage = [&](int stage, int kt) {
-        double* As = sm + (size_t)stage * KS * (SLD + SLDB);
-        double* Bs = As + KS * SLD;
+        double* As = sm + (size_t)stage * STAGE;
+        double* Bs = As + KS * LA;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {                      // A: 16 x 128 doubles = 1024 chunks of 16 B
-            const int chunk = tid + c * 256;
-            const int kk = chunk >> 6, m = (chunk & 63) * 2;
-            cp_async16(As + kk * SLD + m, Ag + (size_t)(kt * KS + kk) * lda + m);
+        for (int c = 0; c < KS * BM / 2 / NT; ++c) {       // A: KS x BM doubles in 16-byte chunks
+            const int chunk = tid + c * NT;
+            const int kk = chunk / (BM / 2), m = (chunk % (BM / 2)) * 2;
+            cp_async16(As + kk * LA + m, Ag + (size_t)(kt * KS + kk) * lda + m);
         }
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {                      // B: 16 x 64 doubles = 512 chunks
-            const int chunk = tid + c * 256;
-            const int kk = chunk >> 5, m = (chunk & 31) * 2;
-            cp_async16(Bs + kk * SLDB + m, Bg + (size_t)(kt * KS + kk) * ldb + m);
+        for (int c = 0; c < KS * BN / 2 / NT; ++c) {
+            const int chunk = tid + c * NT;
+            const int kk = chunk / (BN / 2), m = (chunk % (BN / 2)) * 2;
+            cp_async16(Bs + kk * LB + m, Bg + (size_t)(kt * KS + kk) * ldb + m);
         }
     };
 #pragma unroll
@@ -89,13 +95,13 @@ k_gemm_nt(const double* __restrict__ A, int lda, const double* __restrict__ B, i
         __syncthreads();
         if (kt + GEMM_STAGES - 1 < nk) load_stage((kt + GEMM_STAGES - 1) % GEMM_STAGES, kt + GEMM_STAGES - 1);
         cp_async_commit();
-        const double* As = sm + (size_t)(kt % GEMM_STAGES) * KS * (SLD + SLDB);
-        const double* Bs = As + KS * SLD;
+        const double* As = sm + (size_t)(kt % GEMM_STAGES) * STAGE;
+        const double* Bs = As + KS * LA;
 #pragma unroll
         for (int k0 = 0; k0 < KS; k0 += 4) {
             double af[4], bf[4];
-            const double* ap = As + (k0 + (lane & 3)) * SLD + wm + (lane >> 2);
-            const double* bp = Bs + (k0 + (lane & 3)) * SLDB + wn + (lane >> 2);
+            const double* ap = As + (k0 + (lane & 3)) * LA + wm + (lane >> 2);
+            const double* bp = Bs + (k0 + (lane & 3)) * LB + wn + (lane >> 2);
 #pragma unroll
             for (int i = 0; i < 4; ++i) af[i] = ap[8 * i];
 #pragma unroll
@@ -136,14 +142,28 @@ k_gemm_nt(const double* __restrict__ A, int lda, const double* __restrict__ B, i
     }
 }
 
+template <int BM, int BN> constexpr int gemm_smem() { return GEMM_STAGES * KS * (BM + 4 + BN + 4) * 8; }
+template <int BM, int BN> static void gemm_attr() {
+    static bool done = false;
+    if (!done) { cudaFuncSetAttribute(k_gemm_nt<BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<BM, BN>()); done = true; }
+}
+
 // mt = number of 128-row tiles, nt = number of 128-column blocks (two 64-wide tiles each)
 static void gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc,
                     int mt, int nt, int K, double alpha, double beta, bool tri, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(k_gemm_nt, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM); attr = true; }
+    gemm_attr<128, 64>();
     if (mt <= 0 || nt <= 0) return;
-    if (tri) k_gemm_nt<<<mt * (mt + 1), 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, 1);
-    else     k_gemm_nt<<<dim3(mt, 2 * nt), 256, GEMM_SMEM, st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, 0);
+    if (tri) k_gemm_nt<128, 64><<<mt * (mt + 1), 256, gemm_smem<128, 64>(), st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, 1);
+    else     k_gemm_nt<128, 64><<<dim3(mt, 2 * nt), 256, gemm_smem<128, 64>(), st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, 0);
+    count_launch();
+}
+// Latency-oriented variants for the critical path: rows x cols in units of BM x BN tiles.
+template <int BM, int BN>
+static void gemm_nt_small(const double* A, int lda, const double* B, int ldb, double* C, int ldc,
+                          int rows, int cols, int K, double alpha, double beta, cudaStream_t st) {
+    gemm_attr<BM, BN>();
+    if (rows <= 0 || cols <= 0) return;
+    k_gemm_nt<BM, BN><<<dim3(rows / BM, cols / BN), BM * BN / 32, gemm_smem<BM, BN>(), st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, 0);
     count_launch();
 }
 
@@ -803,11 +823,9 @@ static void chol_factor_body(CholWork& w, double* A, cudaStream_t st) {
         count_launch();
         const int rem = nb - k - 1;
         if (rem <= 0) return;
-        // two CTAs share each 128-row tile (64 columns each), so the product cannot be formed in
-        // place: write it to the panel workspace and copy back
-        gemm_nt(diag(k) + NB, ld, w.invL + (size_t)k * NB * NB, NB, w.panel, ld, rem, 1, NB, 1.0, 0.0, false, s);
-        cudaMemcpy2DAsync(diag(k) + NB, sizeof(double) * ld, w.panel, sizeof(double) * ld,
-                          sizeof(double) * (size_t)rem * NB, NB, cudaMemcpyDeviceToDevice, s);
+        // in place: each CTA owns 32 whole rows of the panel
+        gemm_nt_small<32, 128>(diag(k) + NB, ld, w.invL + (size_t)k * NB * NB, NB, diag(k) + NB, ld,
+                               rem * NB, NB, NB, 1.0, 0.0, s);
     };
     // Steps are taken in pairs so that the bulk of the trailing matrix is updated with K = 256
     // (half the C traffic and epilogues of two K = 128 updates):
@@ -825,7 +843,7 @@ static void chol_factor_body(CholWork& w, double* A, cudaStream_t st) {
         for (int k = 0; k + 1 < nb; ++k) {
             const int rem = nb - k - 1;
             double* Apanel = diag(k) + NB;
-            gemm_nt(Apanel, ld, Apanel, ld, diag(k + 1), ld, rem, 1, NB, -1.0, 1.0, false, st);
+            gemm_nt_small<64, 64>(Apanel, ld, Apanel, ld, diag(k + 1), ld, rem * NB, NB, NB, -1.0, 1.0, st);
             cudaEventRecord(g_evA, st);
             cudaStreamWaitEvent(g_aux, g_evA, 0);
             panel_step(k + 1, g_aux);
