@@ -384,6 +384,43 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
         AL(P.ptaux, (size_t)std::max(1, nOP) * DBAT_PTAUX_STRIDE);
         AL(P.shPart, (size_t)((nOP + DBAT_SHCHUNK - 1) / DBAT_SHCHUNK + 1) * DBAT_NSLOT * DBAT_SHCOLS);
     }
+    {   // grouped Schur index: estimated points sorted by (ray count, image list)
+        std::vector<int> cand, big;
+        cand.reserve(nOP);
+        for (int j = 0; j < nOP; ++j) {
+            const int k = h->h_pt_start[j + 1] - h->h_pt_start[j];
+            const int* oc = &h->h_op_col[3 * (size_t)j];
+            if (k == 0 || (oc[0] < 0 && oc[1] < 0 && oc[2] < 0)) continue;
+            (k <= DBAT_GRP_MAXM ? cand : big).push_back(j);
+        }
+        const int* ps = h->h_pt_start.data();
+        const int* im = img_pm.data();
+        auto cmp3 = [&](int a, int b) {          // <0, 0, >0
+            const int ka = ps[a + 1] - ps[a], kb = ps[b + 1] - ps[b];
+            if (ka != kb) return ka < kb ? -1 : 1;
+            const int* la = im + ps[a]; const int* lb = im + ps[b];
+            for (int t = 0; t < ka; ++t) if (la[t] != lb[t]) return la[t] < lb[t] ? -1 : 1;
+            return 0;
+        };
+        std::sort(cand.begin(), cand.end(), [&](int a, int b) { const int c = cmp3(a, b); return c != 0 ? c < 0 : a < b; });
+        const int gcap = std::max(1, std::min(32, (int)(cand.size() / (148 * 8))));
+        std::vector<int> gstart;
+        gstart.push_back(0);
+        for (size_t i = 1; i <= cand.size(); ++i) {
+            const bool cut = i == cand.size() || cmp3(cand[i - 1], cand[i]) != 0 || (int)(i - gstart.back()) >= gcap;
+            if (cut) gstart.push_back((int)i);
+        }
+        const bool noCand = cand.empty();
+        if (noCand) { cand.push_back(0); gstart.assign(1, 0); }
+        if (big.empty()) big.push_back(0); else P.nBig = (int)big.size();
+        P.nGrp = (int)gstart.size() - 1;
+        P.grpMaxRays = 1;
+        for (size_t i = 0; i + 1 < gstart.size(); ++i) P.grpMaxRays = std::max(P.grpMaxRays, ps[cand[gstart[i]] + 1] - ps[cand[gstart[i]]]);
+        int *d_gp, *d_gs, *d_big;
+        UP(d_gp, cand); UP(d_gs, gstart); UP(d_big, big);
+        P.grp_pt = d_gp; P.grp_start = d_gs; P.big_pt = d_big;
+        AL(P.vinv, (size_t)std::max(1, nOP) * 8);
+    }
     AL(h->d_tmpG, (size_t)64 * DBAT_GSZ);
     const int nPartial = 2 * ((std::max(nObs, P.n) + 255) / 256) + 64;
     AL(h->d_partial, nPartial);

@@ -31,27 +31,30 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N)); }
 
 // C(tile) = beta*C + alpha * A(rows of tile, 0:K) * B(rows of tile col, 0:K)'
-// CTA tile BM x BN, one warp per 32 x 32 sub-tile (BM/32 warps along M, BN/32 along N), 3-stage
-// cp.async pipeline.  Smem strides BM+4 / BN+4 (= 4 mod 16): the 8-byte fragment loads of a
-// half-warp (addresses (lane&3)*stride + lane/4) fall into 16 distinct banks.
-//   <128, 64>  trailing update (two CTAs per SM: one CTA's C read-modify-write epilogue overlaps
-//              the other's main loop)
-//   < 64, 64>  the look-ahead column update on the critical path (4x the CTAs, 1/4 the latency)
-//   < 32,128>  panel solve on the critical path; the CTA owns whole rows and K spans the whole
-//              panel, so C may alias A (every A slice is in shared memory before the epilogue)
+// CTA tile BM x BN, one warp per WTM x WTN sub-tile, STAGES-deep cp.async pipeline over 16-wide
+// k-slices.  Smem strides BM+4 / BN+4 (= 4 mod 16): the 8-byte fragment loads of a half-warp
+// (addresses (lane&3)*stride + lane/4) fall into 16 distinct banks.
+//   <128, 64, 64x32 | 32x32, 3 stages, 2 CTAs/SM>  trailing update (one CTA's C read-modify-write
+//              epilogue overlaps the other's main loop)
+//   < 64, 64, 32x32, 8 stages>  the look-ahead column update on the critical path: 4x the CTAs of
+//              the big tile, and with K = 128 every slice is in flight from the start
+//   < 32,128, 32x32, 8 stages>  panel solve on the critical path; the CTA owns whole rows and K
+//              spans the whole panel, so C may alias A (every A slice is in shared memory before
+//              the epilogue)
 // tile list: if tri != 0 the 1-D grid enumerates the tiles (ti, tj) with BN*tj <= BM*ti + BM-1 of
 // the lower triangle (BM = 2 BN only); otherwise blockIdx.x = ti, blockIdx.y = tj.
-template <int BM, int BN>
-__global__ void __launch_bounds__(BM * BN / 32, (BM * BN >= 8192) ? 2 : 3)
+template <int BM, int BN, int WTM, int WTN, int STAGES, int MINB>
+__global__ void __launch_bounds__((BM / WTM) * (BN / WTN) * 32, MINB)
 k_gemm_nt(const double* A, int lda, const double* __restrict__ B, int ldb,
           double* C, int ldc, int K, double alpha, double beta, int tri) {
-    constexpr int NT = BM * BN / 32;              // threads
-    constexpr int WM = BM / 32;                   // warps along M
+    constexpr int NT = (BM / WTM) * (BN / WTN) * 32;   // threads
+    constexpr int WM = BM / WTM;                  // warps along M
+    constexpr int MI = WTM / 8, NJ = WTN / 8;     // 8x8 DMMA tiles per warp
     constexpr int LA = BM + 4, LB = BN + 4;
     constexpr int STAGE = KS * (LA + LB);
     extern __shared__ __align__(16) double sm[];
     int ti, tj;
-    if (tri) {
+    if (tri & 1) {
         const int t = blockIdx.x;
         ti = (int)((sqrt(4.0 * t + 1.0) - 1.0) * 0.5);
         while ((ti + 1) * (ti + 2) <= t) ++ti;
@@ -63,13 +66,20 @@ k_gemm_nt(const double* A, int lda, const double* __restrict__ B, int ldb,
     double* Cg = C + (size_t)tj * BN * ldc + (size_t)ti * BM;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = (warp % WM) * 32;
-    const int wn = (warp / WM) * 32;
-    double acc[4][4][2];
+    if (tri & 2) {                                // pull the C tile towards L2 for the epilogue
+        for (int l = tid; l < BN * (BM / 16); l += NT) {
+            const double* pc = Cg + (size_t)(l / (BM / 16)) * ldc + (l % (BM / 16)) * 16;
+            asm volatile("prefetch.global.L2 [%0];" :: "l"(pc));
+        }
+    }
+    if ((tri >> 8) && ((blockIdx.x / gridDim.y == 0 ? blockIdx.x : blockIdx.x) / 148 & 1)) __nanosleep((tri >> 8) * 256);
+    const int wm = (warp % WM) * WTM;
+    const int wn = (warp / WM) * WTN;
+    double acc[MI][NJ][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < MI; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        for (int j = 0; j < NJ; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
 
     const int nk = K / KS;
     auto load_stage = [&](int stage, int kt) {
@@ -89,82 +99,97 @@ k_gemm_nt(const double* A, int lda, const double* __restrict__ B, int ldb,
         }
     };
 #pragma unroll
-    for (int s = 0; s < GEMM_STAGES - 1; ++s) { if (s < nk) load_stage(s, s); cp_async_commit(); }
+    for (int s = 0; s < STAGES - 1; ++s) { if (s < nk) load_stage(s, s); cp_async_commit(); }
     for (int kt = 0; kt < nk; ++kt) {
-        cp_async_wait<GEMM_STAGES - 2>();
+        cp_async_wait<STAGES - 2>();
         __syncthreads();
-        if (kt + GEMM_STAGES - 1 < nk) load_stage((kt + GEMM_STAGES - 1) % GEMM_STAGES, kt + GEMM_STAGES - 1);
+        if (kt + STAGES - 1 < nk) load_stage((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
         cp_async_commit();
-        const double* As = sm + (size_t)(kt % GEMM_STAGES) * STAGE;
+        const double* As = sm + (size_t)(kt % STAGES) * STAGE;
         const double* Bs = As + KS * LA;
 #pragma unroll
         for (int k0 = 0; k0 < KS; k0 += 4) {
-            double af[4], bf[4];
+            double af[MI], bf[NJ];
             const double* ap = As + (k0 + (lane & 3)) * LA + wm + (lane >> 2);
             const double* bp = Bs + (k0 + (lane & 3)) * LB + wn + (lane >> 2);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) af[i] = ap[8 * i];
+            for (int i = 0; i < MI; ++i) af[i] = ap[8 * i];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = bp[8 * j];
+            for (int j = 0; j < NJ; ++j) bf[j] = bp[8 * j];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < MI; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < NJ; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
     }
     cp_async_wait<0>();
     // epilogue: C fragment (row = lane/4, cols 2*(lane%4)+{0,1}) per 8x8 tile
     if (beta == 0.0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < MI; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
+            for (int j = 0; j < NJ; ++j) {
                 double* p0 = Cg + (size_t)(wn + 8 * j + 2 * (lane & 3)) * ldc + wm + 8 * i + (lane >> 2);
                 p0[0] = alpha * acc[i][j][0]; p0[ldc] = alpha * acc[i][j][1];
             }
     } else {
-        double cv[4][4][2];
+        constexpr int IC = MI > 4 ? 4 : MI;           // row tiles per read-modify-write batch
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i0 = 0; i0 < MI; i0 += IC) {
+            double cv[IC][NJ][2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const double* p0 = Cg + (size_t)(wn + 8 * j + 2 * (lane & 3)) * ldc + wm + 8 * i + (lane >> 2);
-                cv[i][j][0] = p0[0]; cv[i][j][1] = p0[ldc];
-            }
+            for (int i = 0; i < IC; ++i)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+                for (int j = 0; j < NJ; ++j) {
+                    const double* p0 = Cg + (size_t)(wn + 8 * j + 2 * (lane & 3)) * ldc + wm + 8 * (i0 + i) + (lane >> 2);
+                    cv[i][j][0] = p0[0]; cv[i][j][1] = p0[ldc];
+                }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                double* p0 = Cg + (size_t)(wn + 8 * j + 2 * (lane & 3)) * ldc + wm + 8 * i + (lane >> 2);
-                p0[0] = beta * cv[i][j][0] + alpha * acc[i][j][0];
-                p0[ldc] = beta * cv[i][j][1] + alpha * acc[i][j][1];
-            }
+            for (int i = 0; i < IC; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    double* p0 = Cg + (size_t)(wn + 8 * j + 2 * (lane & 3)) * ldc + wm + 8 * (i0 + i) + (lane >> 2);
+                    p0[0] = beta * cv[i][j][0] + alpha * acc[i0 + i][j][0];
+                    p0[ldc] = beta * cv[i][j][1] + alpha * acc[i0 + i][j][1];
+                }
+        }
     }
 }
 
-template <int BM, int BN> constexpr int gemm_smem() { return GEMM_STAGES * KS * (BM + 4 + BN + 4) * 8; }
-template <int BM, int BN> static void gemm_attr() {
-    static bool done = false;
-    if (!done) { cudaFuncSetAttribute(k_gemm_nt<BM, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, gemm_smem<BM, BN>()); done = true; }
-}
+template <int BM, int BN, int WTM, int WTN, int STAGES, int MINB>
+struct GemmCfg {
+    static constexpr int threads = (BM / WTM) * (BN / WTN) * 32;
+    static constexpr int smem = STAGES * KS * (BM + 4 + BN + 4) * 8;
+    static void launch(dim3 grid, cudaStream_t st, const double* A, int lda, const double* B, int ldb,
+                       double* C, int ldc, int K, double alpha, double beta, int tri) {
+        static bool done = false;
+        if (!done) {
+            cudaFuncSetAttribute(k_gemm_nt<BM, BN, WTM, WTN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            done = true;
+        }
+        k_gemm_nt<BM, BN, WTM, WTN, STAGES, MINB><<<grid, threads, smem, st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, tri);
+        count_launch();
+    }
+};
+typedef GemmCfg<128, 64, 32, 32, 3, 2> GemmBig32;     // 8 warps
+typedef GemmCfg<128, 64, 64, 32, 3, 2> GemmBig64;     // 4 warps, 64 x 32 per warp
+typedef GemmCfg<64, 64, 32, 32, 8, 1> GemmCol;
+typedef GemmCfg<32, 128, 32, 32, 8, 1> GemmPanel;
 
 // mt = number of 128-row tiles, nt = number of 128-column blocks (two 64-wide tiles each)
 static void gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc,
                     int mt, int nt, int K, double alpha, double beta, bool tri, cudaStream_t st) {
-    gemm_attr<128, 64>();
+    static int wt64 = -1, flags = 0;
+    if (wt64 < 0) {
+        const char* e = getenv("DBAT_GEMM_WT"); wt64 = (e && e[0] == '1') ? 1 : 0;
+        e = getenv("DBAT_GEMM_PREFETCH"); if (e && e[0] == '1') flags |= 2;
+        e = getenv("DBAT_GEMM_STAGGER"); if (e) flags |= (atoi(e) & 0xffff) << 8;
+    }
     if (mt <= 0 || nt <= 0) return;
-    if (tri) k_gemm_nt<128, 64><<<mt * (mt + 1), 256, gemm_smem<128, 64>(), st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, 1);
-    else     k_gemm_nt<128, 64><<<dim3(mt, 2 * nt), 256, gemm_smem<128, 64>(), st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, 0);
-    count_launch();
-}
-// Latency-oriented variants for the critical path: rows x cols in units of BM x BN tiles.
-template <int BM, int BN>
-static void gemm_nt_small(const double* A, int lda, const double* B, int ldb, double* C, int ldc,
-                          int rows, int cols, int K, double alpha, double beta, cudaStream_t st) {
-    gemm_attr<BM, BN>();
-    if (rows <= 0 || cols <= 0) return;
-    k_gemm_nt<BM, BN><<<dim3(rows / BM, cols / BN), BM * BN / 32, gemm_smem<BM, BN>(), st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, 0);
-    count_launch();
+    const dim3 grid = tri ? dim3(mt * (mt + 1)) : dim3(mt, 2 * nt);
+    const int f = (tri ? 1 : 0) | (beta != 0.0 ? flags : 0);
+    if (wt64) GemmBig64::launch(grid, st, A, lda, B, ldb, C, ldc, K, alpha, beta, f);
+    else GemmBig32::launch(grid, st, A, lda, B, ldb, C, ldc, K, alpha, beta, f);
 }
 
 // Cholesky of one 128x128 diagonal block in shared memory + inverse of its factor.
@@ -824,8 +849,8 @@ static void chol_factor_body(CholWork& w, double* A, cudaStream_t st) {
         const int rem = nb - k - 1;
         if (rem <= 0) return;
         // in place: each CTA owns 32 whole rows of the panel
-        gemm_nt_small<32, 128>(diag(k) + NB, ld, w.invL + (size_t)k * NB * NB, NB, diag(k) + NB, ld,
-                               rem * NB, NB, NB, 1.0, 0.0, s);
+        GemmPanel::launch(dim3(rem * NB / 32, 1), s, diag(k) + NB, ld, w.invL + (size_t)k * NB * NB, NB,
+                          diag(k) + NB, ld, NB, 1.0, 0.0, 0);
     };
     // Steps are taken in pairs so that the bulk of the trailing matrix is updated with K = 256
     // (half the C traffic and epilogues of two K = 128 updates):
@@ -843,7 +868,7 @@ static void chol_factor_body(CholWork& w, double* A, cudaStream_t st) {
         for (int k = 0; k + 1 < nb; ++k) {
             const int rem = nb - k - 1;
             double* Apanel = diag(k) + NB;
-            gemm_nt_small<64, 64>(Apanel, ld, Apanel, ld, diag(k + 1), ld, rem * NB, NB, NB, -1.0, 1.0, st);
+            GemmCol::launch(dim3(rem * NB / 64, NB / 64), st, Apanel, ld, Apanel, ld, diag(k + 1), ld, NB, -1.0, 1.0, 0);
             cudaEventRecord(g_evA, st);
             cudaStreamWaitEvent(g_aux, g_evA, 0);
             panel_step(k + 1, g_aux);

@@ -6,6 +6,7 @@
 //   p_j = (V_j + lambda*I)^-1 (-g_j - W~_j' p_c)
 #include <cstdlib>
 #include "kernels.cuh"
+#include <algorithm>
 #include "launch.h"
 
 __device__ __forceinline__ double gram_at(const double* __restrict__ G, int R, int C) {
@@ -332,7 +333,8 @@ __global__ void k_schur_sh_final(DevProblem P, int nPart) {
 // DBAT_SCHUR=det to use the pair-index kernels above instead.
 // ---------------------------------------------------------------------------------------------
 // Schur update, one warp per object point (v1: FP64 atomics into the dense lower triangle).
-__global__ void __launch_bounds__(256) k_schur_atomic(DevProblem P, double lambda, double* __restrict__ shAcc) {
+__global__ void __launch_bounds__(256) k_schur_atomic(DevProblem P, double lambda, double* __restrict__ shAcc,
+                                                      const int* __restrict__ list, int nList) {
     const int lane = threadIdx.x & 31;
     const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
@@ -344,7 +346,9 @@ __global__ void __launch_bounds__(256) k_schur_atomic(DevProblem P, double lambd
 #pragma unroll
     for (int k = 0; k < NEL; ++k) accSh[k] = 0.0;
 
-    for (int j = warpGlobal; j < P.nOP; j += nWarps) {
+    const int nPts = list ? nList : P.nOP;
+    for (int jj = warpGlobal; jj < nPts; jj += nWarps) {
+        const int j = list ? list[jj] : jj;
         const double* rec = P.pt + (size_t)j * DBAT_PT_STRIDE;
         const int* opc = P.op_col + 3 * (size_t)j;
         if (opc[0] < 0 && opc[1] < 0 && opc[2] < 0) continue;
@@ -415,6 +419,165 @@ __global__ void __launch_bounds__(256) k_schur_atomic(DevProblem P, double lambd
         if (e < NE) atomicAdd(&shAcc[e], accSh[kk]);
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Grouped Schur update (default).  Points are sorted by their image list at create; a group is a
+// run of points seen by exactly the same m images.  One CTA per group: thread (slot, task) with
+//   task <  m(m+1)/2 : the 6x6 block  Y_o W_o2'  of the image pair (o >= o2),
+//   task >= m(m+1)/2 : 5 of the 15 columns  Y_o [Wsh | g]  of image o  (shared IO columns and rhs)
+// sums its block over the points slot, slot + nslot, ... of the group in registers (operands come
+// straight from L1/L2: W_o is read by the ~m tasks of the same point).  The slots are then added
+// in shared memory and flushed with one atomic per entry of S, 6 consecutive rows per 6 lanes.
+// With the 10-nearest-camera visibility of the synthetic blocks a group holds ~7 points, i.e. ~7x
+// fewer L2 atomics than one flush per point (the kernel this replaced was bound by exactly those).
+// ---------------------------------------------------------------------------------------------
+__global__ void k_point_vinv(DevProblem P, double lambda) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.nOP) return;
+    double Vi[6];
+    point_inverse(P.pt + (size_t)j * DBAT_PT_STRIDE, P.op_col + 3 * (size_t)j, lambda, Vi);
+    double2* o = reinterpret_cast<double2*>(P.vinv + (size_t)j * 8);
+    o[0] = make_double2(Vi[0], Vi[1]); o[1] = make_double2(Vi[2], Vi[3]); o[2] = make_double2(Vi[4], Vi[5]);
+}
+
+#define GRP_TH 192
+#define GRP_CAP 32            // max points per group (create-time cap)
+// tasks of 18 outputs (3 rows a = 3ah..3ah+2 of image o):
+//   id <  2 npair         : pair pr = id/2 (o >= o2), ah = id%2 : Y_o(a,:) . W_o2(b,:)   b = 0..5
+//   id >= 2 npair         : q = id - 2 npair, o = q/6, part = (q%6)/2, ah = q%2 :
+//                           Y_o(a,:) . [Wsh | g](s,:)   s = 6 part .. 6 part + 5 (s = 14: rhs, s = 15..17 unused)
+__global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double* __restrict__ shAcc) {
+    extern __shared__ __align__(16) double red[];           // [ntask * 18]
+    __shared__ int s_img[DBAT_GRP_MAXM], s_j[GRP_CAP], s_ob[GRP_CAP];
+    __shared__ double s_vi[GRP_CAP * 6];
+    __shared__ unsigned char s_po[DBAT_GRP_MAXM * (DBAT_GRP_MAXM + 1) / 2], s_po2[DBAT_GRP_MAXM * (DBAT_GRP_MAXM + 1) / 2];
+    const int t = threadIdx.x;
+    const size_t ld = P.ldS;
+    constexpr int NE = DBAT_NSLOT * (DBAT_NSLOT + 1);
+    double accSh[2] = {0.0, 0.0};                // entries t and t + GRP_TH of the shared x shared table
+    int mPrev = -1;
+    for (int grp = blockIdx.x; grp < P.nGrp; grp += gridDim.x) {
+        const int g0 = P.grp_start[grp], ng = P.grp_start[grp + 1] - g0;
+        if (t < ng) {                             // group header: point ids, observation offsets, V^-1
+            const int j = P.grp_pt[g0 + t];
+            s_j[t] = j; s_ob[t] = P.pt_start[j];
+            const double2* vp = reinterpret_cast<const double2*>(P.vinv + (size_t)j * 8);
+            const double2 v01 = vp[0], v23 = vp[1], v45 = vp[2];
+            double* sv = s_vi + 6 * t;
+            sv[0] = v01.x; sv[1] = v01.y; sv[2] = v23.x; sv[3] = v23.y; sv[4] = v45.x; sv[5] = v45.y;
+        }
+        const int j0 = P.grp_pt[g0];
+        const int o00 = P.pt_start[j0], m = P.pt_start[j0 + 1] - o00;
+        const int npair = m * (m + 1) / 2, ntask = 2 * npair + 6 * m;
+        if (m != mPrev) {                         // pair table (same for all groups with this m)
+            for (int pr = t; pr < npair; pr += GRP_TH) {
+                int o = (int)((sqrtf(8.0f * pr + 1.0f) - 1.0f) * 0.5f);
+                while ((o + 1) * (o + 2) / 2 <= pr) ++o;
+                while (o * (o + 1) / 2 > pr) --o;
+                s_po[pr] = (unsigned char)o; s_po2[pr] = (unsigned char)(pr - o * (o + 1) / 2);
+            }
+            mPrev = m;
+        }
+        if (t < m) s_img[t] = P.img_pm[o00 + t];
+        __syncthreads();
+        for (int task = t; task < ntask; task += GRP_TH) {
+            const bool isPair = task < 2 * npair;
+            int o, o2 = 0, part = 0, ah;
+            if (isPair) { const int pr = task >> 1; ah = task & 1; o = s_po[pr]; o2 = s_po2[pr]; }
+            else { const int q = task - 2 * npair; o = q / 6; const int r = q - 6 * o; part = r >> 1; ah = r & 1; }
+            double acc[18];
+#pragma unroll
+            for (int k = 0; k < 18; ++k) acc[k] = 0.0;
+#pragma unroll 2
+            for (int gi = 0; gi < ng; ++gi) {
+                const int ob = s_ob[gi];
+                const double* sv = s_vi + 6 * gi;
+                const double Vi[6] = {sv[0], sv[1], sv[2], sv[3], sv[4], sv[5]};
+                const double* Wo = P.W + (size_t)(ob + o) * DBAT_W_STRIDE + 9 * ah;
+                double Y[9];
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const double w3[3] = {Wo[3 * a], Wo[3 * a + 1], Wo[3 * a + 2]};
+                    symv3(Vi, w3, Y + 3 * a);
+                }
+                if (isPair) {
+                    const double2* Wb = reinterpret_cast<const double2*>(P.W + (size_t)(ob + o2) * DBAT_W_STRIDE);
+                    double w[18];
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) { const double2 v = Wb[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
+#pragma unroll
+                    for (int b = 0; b < 6; ++b)
+#pragma unroll
+                        for (int a = 0; a < 3; ++a)
+                            acc[3 * b + a] += Y[3 * a] * w[3 * b] + Y[3 * a + 1] * w[3 * b + 1] + Y[3 * a + 2] * w[3 * b + 2];
+                } else {
+                    const double* rec = P.pt + (size_t)s_j[gi] * DBAT_PT_STRIDE;
+#pragma unroll
+                    for (int si = 0; si < 6; ++si) {
+                        const int sidx = 6 * part + si;
+                        if (sidx <= DBAT_NSLOT) {
+                            const double* vs = sidx < DBAT_NSLOT ? rec + DBAT_PT_WSH + 3 * sidx : rec + 6;
+                            const double v0 = vs[0], v1 = vs[1], v2 = vs[2];
+#pragma unroll
+                            for (int a = 0; a < 3; ++a) acc[3 * si + a] += Y[3 * a] * v0 + Y[3 * a + 1] * v1 + Y[3 * a + 2] * v2;
+                        }
+                    }
+                }
+            }
+            double* r = red + task * 18;
+#pragma unroll
+            for (int k = 0; k < 18; ++k) r[k] = acc[k];
+        }
+        // shared x shared (+ rhs): entries of the NSLOT x (NSLOT+1) table, summed over the group
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int e = t + h * GRP_TH;
+            const int shA = e / (DBAT_NSLOT + 1), shB = e - shA * (DBAT_NSLOT + 1);
+            if (e < NE && (shB == DBAT_NSLOT || shB <= shA)) {
+#pragma unroll 4
+                for (int gi = 0; gi < ng; ++gi) {
+                    const double* rec = P.pt + (size_t)s_j[gi] * DBAT_PT_STRIDE;
+                    const double* sv = s_vi + 6 * gi;
+                    const double Vi[6] = {sv[0], sv[1], sv[2], sv[3], sv[4], sv[5]};
+                    const double* wa = rec + DBAT_PT_WSH + 3 * shA;
+                    const double* wb = shB < DBAT_NSLOT ? rec + DBAT_PT_WSH + 3 * shB : rec + 6;
+                    const double w3[3] = {wb[0], wb[1], wb[2]};
+                    double y[3];
+                    symv3(Vi, w3, y);
+                    accSh[h] += wa[0] * y[0] + wa[1] * y[1] + wa[2] * y[2];
+                }
+            }
+        }
+        __syncthreads();
+        // flush, consecutive lanes -> consecutive rows a of one column of S
+        for (int e = t; e < npair * 36; e += GRP_TH) {
+            const int pr = e / 36, k = e - pr * 36, b = k / 6, a = k - 6 * b;
+            const double v = red[(2 * pr + a / 3) * 18 + 3 * b + a % 3];
+            const int row = P.eo_col[6 * (size_t)s_img[s_po[pr]] + a];
+            const int col = P.eo_col[6 * (size_t)s_img[s_po2[pr]] + b];
+            if (row >= 0 && col >= 0 && col <= row) atomicAdd(&P.S[(size_t)col * ld + row], -v);
+        }
+        for (int e = t; e < m * 90; e += GRP_TH) {
+            const int oo = e / 90, k = e - oo * 90, sidx = k / 6, a = k - 6 * sidx;
+            const double v = red[(2 * npair + 6 * oo + 2 * (sidx / 6) + a / 3) * 18 + 3 * (sidx % 6) + a % 3];
+            const int row = P.eo_col[6 * (size_t)s_img[oo] + a];
+            if (row >= 0) {
+                if (sidx < DBAT_NSLOT) {
+                    const int col = P.sh_col[sidx];
+                    if (col >= 0) atomicAdd(&P.S[(size_t)col * ld + row], -v);
+                } else {
+                    atomicAdd(&P.rhs[row], v);
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int e = t + h * GRP_TH;
+        if (e < NE && accSh[h] != 0.0) atomicAdd(&shAcc[e], accSh[h]);
+    }
+}
 __global__ void k_schur_sh_apply(DevProblem P, const double* __restrict__ shAcc) {
     const size_t ld = P.ldS;
     for (int e = threadIdx.x; e < DBAT_NSLOT * (DBAT_NSLOT + 1); e += blockDim.x) {
@@ -431,22 +594,40 @@ __global__ void k_schur_sh_apply(DevProblem P, const double* __restrict__ shAcc)
     }
 }
 
-static int g_schur_mode = -1;       // 0 = atomic (default), 1 = deterministic
+static int g_schur_mode = -1;       // 0 = grouped atomic (default), 1 = deterministic, 2 = per-point atomic
 static double* g_shAcc = nullptr;
 void launch_schur(const DevProblem& P, double lambda, cudaStream_t st) {
     if (P.nOP <= 0) return;
     if (g_schur_mode < 0) {
         const char* e = getenv("DBAT_SCHUR");
-        g_schur_mode = (e && e[0] == 'd') ? 1 : 0;
+        g_schur_mode = (e && e[0] == 'd') ? 1 : (e && e[0] == 'p') ? 2 : 0;
     }
-    if (g_schur_mode == 0) {
+    if (g_schur_mode != 1) {
         if (!g_shAcc) cudaMalloc(&g_shAcc, sizeof(double) * DBAT_NSLOT * (DBAT_NSLOT + 1));
         cudaMemsetAsync(g_shAcc, 0, sizeof(double) * DBAT_NSLOT * (DBAT_NSLOT + 1), st);
-        int nb = (P.nOP + 7) / 8;
-        if (nb > 148 * 8) nb = 148 * 8;
-        k_schur_atomic<<<nb, 256, 0, st>>>(P, lambda, g_shAcc);
+        if (g_schur_mode == 2) {
+            int nb = (P.nOP + 7) / 8;
+            if (nb > 148 * 8) nb = 148 * 8;
+            k_schur_atomic<<<nb, 256, 0, st>>>(P, lambda, g_shAcc, nullptr, 0);
+            count_launch();
+        } else {
+            k_point_vinv<<<(P.nOP + 255) / 256, 256, 0, st>>>(P, lambda);
+            if (P.nGrp > 0) {
+                static bool attr = false;
+                const int smem = (DBAT_GRP_MAXM * (DBAT_GRP_MAXM + 1) + 6 * DBAT_GRP_MAXM) * 18 * 8;
+                if (!attr) { cudaFuncSetAttribute(k_schur_group, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+                const int mm = P.grpMaxRays;
+                k_schur_group<<<std::min(P.nGrp, 148 * 24), GRP_TH, (mm * (mm + 1) + 6 * mm) * 18 * 8, st>>>(P, g_shAcc);
+                count_launch();
+            }
+            if (P.nBig > 0) {
+                k_schur_atomic<<<std::min((P.nBig + 7) / 8, 148 * 8), 256, 0, st>>>(P, lambda, g_shAcc, P.big_pt, P.nBig);
+                count_launch();
+            }
+            count_launch();
+        }
         k_schur_sh_apply<<<1, 256, 0, st>>>(P, g_shAcc);
-        count_launch(2);
+        count_launch();
         return;
     }
     k_point_prep<<<(P.nOP + 127) / 128, 128, 0, st>>>(P, lambda);
