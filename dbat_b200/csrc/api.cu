@@ -403,7 +403,7 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
             return 0;
         };
         std::sort(cand.begin(), cand.end(), [&](int a, int b) { const int c = cmp3(a, b); return c != 0 ? c < 0 : a < b; });
-        const int gcap = std::max(1, std::min(32, (int)(cand.size() / (148 * 8))));
+        const int gcap = std::max(1, std::min(16, (int)(cand.size() / (148 * 8))));   // <= GRP_CAP of schur.cu
         std::vector<int> gstart;
         gstart.push_back(0);
         for (size_t i = 1; i <= cand.size(); ++i) {

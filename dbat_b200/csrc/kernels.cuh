@@ -76,4 +76,4 @@ struct DevProblem {
     int nBig;
     double* vinv;          // nOP x 8: (V_j + lambda I)^-1 (6 entries) of the current solve
 };
-#define DBAT_GRP_MAXM 24   // grouped path up to 24 rays per point (task results: 107 KB of shared memory)
+#define DBAT_GRP_MAXM 21   // grouped path up to 21 rays per point (header staging uses threads 64..64+6m of 192)

@@ -441,34 +441,79 @@ __global__ void k_point_vinv(DevProblem P, double lambda) {
 }
 
 #define GRP_TH 192
-#define GRP_CAP 32            // max points per group (create-time cap)
-// tasks of 18 outputs (3 rows a = 3ah..3ah+2 of image o):
-//   id <  2 npair         : pair pr = id/2 (o >= o2), ah = id%2 : Y_o(a,:) . W_o2(b,:)   b = 0..5
-//   id >= 2 npair         : q = id - 2 npair, o = q/6, part = (q%6)/2, ah = q%2 :
-//                           Y_o(a,:) . [Wsh | g](s,:)   s = 6 part .. 6 part + 5 (s = 14: rhs, s = 15..17 unused)
-__global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double* __restrict__ shAcc) {
-    extern __shared__ __align__(16) double red[];           // [ntask * 18]
-    __shared__ int s_img[DBAT_GRP_MAXM], s_j[GRP_CAP], s_ob[GRP_CAP];
-    __shared__ double s_vi[GRP_CAP * 6];
+#define GRP_CAP 16            // max points per group (create-time cap)
+#define GRP_YH 10             // doubles per half record of Y (9 + 1: keeps 16-byte alignment)
+struct GrpHeader {            // per-group data staged in shared memory (double-buffered)
+    int m, ng;
+    int j[GRP_CAP], ob[GRP_CAP];
+    int img[DBAT_GRP_MAXM];
+    int eoc[DBAT_GRP_MAXM * 6];                  // x column of every EO element of the group's images
+    double vi[GRP_CAP * 6];
+};
+// Registers of one thread's share of the next group's header (loaded early, stored late).
+struct GrpPrefetch { int j, ob, img, eoc; double2 v01, v23, v45; int m, ng; };
+
+__device__ __forceinline__ void grp_prefetch(const DevProblem& P, int grp, int t, GrpPrefetch& f) {
+    f.m = 0; f.ng = 0; f.j = 0; f.ob = 0; f.img = 0; f.eoc = -1;
+    if (grp >= P.nGrp) return;
+    const int g0 = P.grp_start[grp];
+    f.ng = P.grp_start[grp + 1] - g0;
+    const int j0 = P.grp_pt[g0];
+    const int o00 = P.pt_start[j0];
+    f.m = P.pt_start[j0 + 1] - o00;
+    if (t < f.ng) {
+        f.j = P.grp_pt[g0 + t];
+        f.ob = P.pt_start[f.j];
+        const double2* vp = reinterpret_cast<const double2*>(P.vinv + (size_t)f.j * 8);
+        f.v01 = vp[0]; f.v23 = vp[1]; f.v45 = vp[2];
+    }
+    if (t >= 32 && t - 32 < f.m) f.img = P.img_pm[o00 + t - 32];
+    if (t >= 64 && t - 64 < 6 * f.m) f.eoc = P.eo_col[6 * (size_t)P.img_pm[o00 + (t - 64) / 6] + (t - 64) % 6];
+}
+__device__ __forceinline__ void grp_store(GrpHeader& h, int t, const GrpPrefetch& f) {
+    if (t == 0) { h.m = f.m; h.ng = f.ng; }
+    if (t < f.ng) {
+        h.j[t] = f.j; h.ob[t] = f.ob;
+        double* sv = h.vi + 6 * t;
+        sv[0] = f.v01.x; sv[1] = f.v01.y; sv[2] = f.v23.x; sv[3] = f.v23.y; sv[4] = f.v45.x; sv[5] = f.v45.y;
+    }
+    if (t >= 32 && t - 32 < f.m) h.img[t - 32] = f.img;
+    if (t >= 64 && t - 64 < 6 * f.m) h.eoc[t - 64] = f.eoc;
+}
+
+// dynamic shared memory: red[ntask*18] | Wsm[GRP_CAP * m * 18] | Ysm[GRP_CAP * m * 2 * GRP_YH]
+__global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double* __restrict__ shAcc, int flags) {
+    extern __shared__ __align__(16) double dsm[];
+    __shared__ GrpHeader s_hdr[2];
     __shared__ unsigned char s_po[DBAT_GRP_MAXM * (DBAT_GRP_MAXM + 1) / 2], s_po2[DBAT_GRP_MAXM * (DBAT_GRP_MAXM + 1) / 2];
     const int t = threadIdx.x;
     const size_t ld = P.ldS;
     constexpr int NE = DBAT_NSLOT * (DBAT_NSLOT + 1);
+    const int mmax = P.grpMaxRays;
+    double* red = dsm;
+    double* Wsm = red + (mmax * (mmax + 1) + 6 * mmax) * 18;
+    double* Ysm = Wsm + GRP_CAP * mmax * 18;
     double accSh[2] = {0.0, 0.0};                // entries t and t + GRP_TH of the shared x shared table
-    int mPrev = -1;
-    for (int grp = blockIdx.x; grp < P.nGrp; grp += gridDim.x) {
-        const int g0 = P.grp_start[grp], ng = P.grp_start[grp + 1] - g0;
-        if (t < ng) {                             // group header: point ids, observation offsets, V^-1
-            const int j = P.grp_pt[g0 + t];
-            s_j[t] = j; s_ob[t] = P.pt_start[j];
-            const double2* vp = reinterpret_cast<const double2*>(P.vinv + (size_t)j * 8);
-            const double2 v01 = vp[0], v23 = vp[1], v45 = vp[2];
-            double* sv = s_vi + 6 * t;
-            sv[0] = v01.x; sv[1] = v01.y; sv[2] = v23.x; sv[3] = v23.y; sv[4] = v45.x; sv[5] = v45.y;
-        }
-        const int j0 = P.grp_pt[g0];
-        const int o00 = P.pt_start[j0], m = P.pt_start[j0 + 1] - o00;
+    int mPrev = -1, buf = 0;
+    {
+        GrpPrefetch f;
+        grp_prefetch(P, blockIdx.x, t, f);
+        grp_store(s_hdr[0], t, f);
+    }
+    __syncthreads();
+    for (int grp = blockIdx.x; grp < P.nGrp; grp += gridDim.x, buf ^= 1) {
+        GrpHeader& H = s_hdr[buf];
+        GrpPrefetch nxt;
+        grp_prefetch(P, grp + gridDim.x, t, nxt);            // in flight during this group's work
+        const int m = H.m, ng = H.ng;
         const int npair = m * (m + 1) / 2, ntask = 2 * npair + 6 * m;
+        const int recs = m * 18;                             // doubles of W per point (contiguous in global)
+        // stage W of every point of the group (coalesced 16-byte loads)
+        for (int idx = t; idx < ng * (recs / 2); idx += GRP_TH) {
+            const int gi = idx / (recs / 2), off = idx - gi * (recs / 2);
+            reinterpret_cast<double2*>(Wsm + gi * recs)[off] =
+                reinterpret_cast<const double2*>(P.W + (size_t)H.ob[gi] * DBAT_W_STRIDE)[off];
+        }
         if (m != mPrev) {                         // pair table (same for all groups with this m)
             for (int pr = t; pr < npair; pr += GRP_TH) {
                 int o = (int)((sqrtf(8.0f * pr + 1.0f) - 1.0f) * 0.5f);
@@ -478,7 +523,20 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
             }
             mPrev = m;
         }
-        if (t < m) s_img[t] = P.img_pm[o00 + t];
+        __syncthreads();
+        // Y = W (V + lambda I)^-1, one row (3 doubles) per thread
+        for (int idx = t; idx < ng * m * 6; idx += GRP_TH) {
+            const int gi = idx / (m * 6), r = idx - gi * (m * 6);       // r = 6 o + a
+            const double* sv = H.vi + 6 * gi;
+            const double Vi[6] = {sv[0], sv[1], sv[2], sv[3], sv[4], sv[5]};
+            const double* w = Wsm + gi * recs + 3 * r;
+            const double w3[3] = {w[0], w[1], w[2]};
+            double y[3];
+            symv3(Vi, w3, y);
+            const int o = r / 6, a = r - 6 * o;
+            double* yo = Ysm + ((gi * m + o) * 2 + a / 3) * GRP_YH + 3 * (a % 3);
+            yo[0] = y[0]; yo[1] = y[1]; yo[2] = y[2];
+        }
         __syncthreads();
         for (int task = t; task < ntask; task += GRP_TH) {
             const bool isPair = task < 2 * npair;
@@ -488,20 +546,13 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
             double acc[18];
 #pragma unroll
             for (int k = 0; k < 18; ++k) acc[k] = 0.0;
-#pragma unroll 2
             for (int gi = 0; gi < ng; ++gi) {
-                const int ob = s_ob[gi];
-                const double* sv = s_vi + 6 * gi;
-                const double Vi[6] = {sv[0], sv[1], sv[2], sv[3], sv[4], sv[5]};
-                const double* Wo = P.W + (size_t)(ob + o) * DBAT_W_STRIDE + 9 * ah;
-                double Y[9];
+                const double2* yp = reinterpret_cast<const double2*>(Ysm + ((gi * m + o) * 2 + ah) * GRP_YH);
+                double Y[10];
 #pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const double w3[3] = {Wo[3 * a], Wo[3 * a + 1], Wo[3 * a + 2]};
-                    symv3(Vi, w3, Y + 3 * a);
-                }
+                for (int k = 0; k < 5; ++k) { const double2 v = yp[k]; Y[2 * k] = v.x; Y[2 * k + 1] = v.y; }
                 if (isPair) {
-                    const double2* Wb = reinterpret_cast<const double2*>(P.W + (size_t)(ob + o2) * DBAT_W_STRIDE);
+                    const double2* Wb = reinterpret_cast<const double2*>(Wsm + gi * recs + o2 * 18);
                     double w[18];
 #pragma unroll
                     for (int k = 0; k < 9; ++k) { const double2 v = Wb[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
@@ -511,7 +562,7 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
                         for (int a = 0; a < 3; ++a)
                             acc[3 * b + a] += Y[3 * a] * w[3 * b] + Y[3 * a + 1] * w[3 * b + 1] + Y[3 * a + 2] * w[3 * b + 2];
                 } else {
-                    const double* rec = P.pt + (size_t)s_j[gi] * DBAT_PT_STRIDE;
+                    const double* rec = P.pt + (size_t)H.j[gi] * DBAT_PT_STRIDE;
 #pragma unroll
                     for (int si = 0; si < 6; ++si) {
                         const int sidx = 6 * part + si;
@@ -536,8 +587,8 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
             if (e < NE && (shB == DBAT_NSLOT || shB <= shA)) {
 #pragma unroll 4
                 for (int gi = 0; gi < ng; ++gi) {
-                    const double* rec = P.pt + (size_t)s_j[gi] * DBAT_PT_STRIDE;
-                    const double* sv = s_vi + 6 * gi;
+                    const double* rec = P.pt + (size_t)H.j[gi] * DBAT_PT_STRIDE;
+                    const double* sv = H.vi + 6 * gi;
                     const double Vi[6] = {sv[0], sv[1], sv[2], sv[3], sv[4], sv[5]};
                     const double* wa = rec + DBAT_PT_WSH + 3 * shA;
                     const double* wb = shB < DBAT_NSLOT ? rec + DBAT_PT_WSH + 3 * shB : rec + 6;
@@ -548,25 +599,28 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
                 }
             }
         }
+        grp_store(s_hdr[buf ^ 1], t, nxt);
         __syncthreads();
-        // flush, consecutive lanes -> consecutive rows a of one column of S
-        for (int e = t; e < npair * 36; e += GRP_TH) {
-            const int pr = e / 36, k = e - pr * 36, b = k / 6, a = k - 6 * b;
-            const double v = red[(2 * pr + a / 3) * 18 + 3 * b + a % 3];
-            const int row = P.eo_col[6 * (size_t)s_img[s_po[pr]] + a];
-            const int col = P.eo_col[6 * (size_t)s_img[s_po2[pr]] + b];
-            if (row >= 0 && col >= 0 && col <= row) atomicAdd(&P.S[(size_t)col * ld + row], -v);
-        }
-        for (int e = t; e < m * 90; e += GRP_TH) {
-            const int oo = e / 90, k = e - oo * 90, sidx = k / 6, a = k - 6 * sidx;
-            const double v = red[(2 * npair + 6 * oo + 2 * (sidx / 6) + a / 3) * 18 + 3 * (sidx % 6) + a % 3];
-            const int row = P.eo_col[6 * (size_t)s_img[oo] + a];
-            if (row >= 0) {
-                if (sidx < DBAT_NSLOT) {
-                    const int col = P.sh_col[sidx];
-                    if (col >= 0) atomicAdd(&P.S[(size_t)col * ld + row], -v);
-                } else {
-                    atomicAdd(&P.rhs[row], v);
+        // flush: threads 0..179 keep a fixed position inside the 6x6 block (36 | 180) resp. inside the
+        // 15x6 shared-column strip (90 | 180); consecutive lanes -> consecutive rows a of one column
+        if (t < 180 && !(flags & 1)) {
+            const int k = t % 36, b = k / 6, a = k - 6 * b;
+            const int srcoff = (a / 3) * 18 + 3 * b + a % 3;
+            for (int pr = t / 36; pr < npair; pr += 5) {
+                const double v = red[2 * pr * 18 + srcoff];
+                const int row = H.eoc[6 * s_po[pr] + a];
+                const int col = H.eoc[6 * s_po2[pr] + b];
+                if (row >= 0 && col >= 0 && col <= row) atomicAdd(&P.S[(size_t)col * ld + row], -v);
+            }
+            const int k2 = t % 90, sidx = k2 / 6, a2 = k2 - 6 * sidx;
+            const int srcoff2 = (2 * (sidx / 6) + a2 / 3) * 18 + 3 * (sidx % 6) + a2 % 3;
+            const int colsh = sidx < DBAT_NSLOT ? P.sh_col[sidx] : -2;
+            for (int oo = t / 90; oo < m; oo += 2) {
+                const double v = red[(2 * npair + 6 * oo) * 18 + srcoff2];
+                const int row = H.eoc[6 * oo + a2];
+                if (row >= 0) {
+                    if (colsh >= 0) atomicAdd(&P.S[(size_t)colsh * ld + row], -v);
+                    else if (colsh == -2) atomicAdd(&P.rhs[row], v);
                 }
             }
         }
@@ -614,10 +668,11 @@ void launch_schur(const DevProblem& P, double lambda, cudaStream_t st) {
             k_point_vinv<<<(P.nOP + 255) / 256, 256, 0, st>>>(P, lambda);
             if (P.nGrp > 0) {
                 static bool attr = false;
-                const int smem = (DBAT_GRP_MAXM * (DBAT_GRP_MAXM + 1) + 6 * DBAT_GRP_MAXM) * 18 * 8;
-                if (!attr) { cudaFuncSetAttribute(k_schur_group, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-                const int mm = P.grpMaxRays;
-                k_schur_group<<<std::min(P.nGrp, 148 * 24), GRP_TH, (mm * (mm + 1) + 6 * mm) * 18 * 8, st>>>(P, g_shAcc);
+                auto smem_for = [](int mm) { return ((mm * (mm + 1) + 6 * mm) * 18 + GRP_CAP * mm * 18 + GRP_CAP * mm * 2 * GRP_YH) * 8; };
+                if (!attr) { cudaFuncSetAttribute(k_schur_group, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(DBAT_GRP_MAXM)); attr = true; }
+                static int dbg = -1;
+                if (dbg < 0) { const char* e = getenv("DBAT_SCHUR_NOFLUSH"); dbg = (e && e[0] == '1') ? 1 : 0; }
+                k_schur_group<<<std::min(P.nGrp, 148 * 24), GRP_TH, smem_for(P.grpMaxRays), st>>>(P, g_shAcc, dbg);
                 count_launch();
             }
             if (P.nBig > 0) {
