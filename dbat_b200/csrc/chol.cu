@@ -56,23 +56,23 @@ k_gemm_nt(const double* A, int lda, const double* __restrict__ B, int ldb,
     int ti, tj;
     if (tri & 1) {
         const int t = blockIdx.x;
-        ti = (int)((sqrt(4.0 * t + 1.0) - 1.0) * 0.5);
-        while ((ti + 1) * (ti + 2) <= t) ++ti;
-        while (ti * (ti + 1) > t) --ti;
-        tj = t - ti * (ti + 1);
+        if (BM == 2 * BN) {                       // rows of 2 (ti + 1) tiles
+            ti = (int)((sqrtf(4.0f * t + 1.0f) - 1.0f) * 0.5f);
+            while ((ti + 1) * (ti + 2) <= t) ++ti;
+            while (ti * (ti + 1) > t) --ti;
+            tj = t - ti * (ti + 1);
+        } else {                                  // square tiles: rows of ti + 1 tiles
+            ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+            while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+            while (ti * (ti + 1) / 2 > t) --ti;
+            tj = t - ti * (ti + 1) / 2;
+        }
     } else { ti = blockIdx.x; tj = blockIdx.y; }
     const double* Ag = A + (size_t)ti * BM;
     const double* Bg = B + (size_t)tj * BN;
     double* Cg = C + (size_t)tj * BN * ldc + (size_t)ti * BM;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tri & 2) {                                // pull the C tile towards L2 for the epilogue
-        for (int l = tid; l < BN * (BM / 16); l += NT) {
-            const double* pc = Cg + (size_t)(l / (BM / 16)) * ldc + (l % (BM / 16)) * 16;
-            asm volatile("prefetch.global.L2 [%0];" :: "l"(pc));
-        }
-    }
-    if ((tri >> 8) && ((blockIdx.x / gridDim.y == 0 ? blockIdx.x : blockIdx.x) / 148 & 1)) __nanosleep((tri >> 8) * 256);
     const int wm = (warp % WM) * WTM;
     const int wn = (warp / WM) * WTN;
     double acc[MI][NJ][2];
@@ -173,23 +173,30 @@ struct GemmCfg {
 };
 typedef GemmCfg<128, 64, 32, 32, 3, 2> GemmBig32;     // 8 warps
 typedef GemmCfg<128, 64, 64, 32, 3, 2> GemmBig64;     // 4 warps, 64 x 32 per warp
+typedef GemmCfg<64, 64, 32, 32, 3, 3> GemmSq64;       // 4 warps, three CTAs per SM
+typedef GemmCfg<128, 128, 64, 32, 3, 1> GemmSq128;    // 8 warps, 64 x 32 per warp, one CTA per SM
+typedef GemmCfg<64, 64, 32, 32, 3, 4> GemmSq64x4;     // as GemmSq64 with a 128-register cap, four CTAs per SM
+typedef GemmCfg<64, 64, 32, 32, 4, 3> GemmSq64s4;     // four stages
+typedef GemmCfg<64, 32, 32, 32, 3, 6> GemmR6432;      // 2 warps
 typedef GemmCfg<64, 64, 32, 32, 8, 1> GemmCol;
 typedef GemmCfg<32, 128, 32, 32, 8, 1> GemmPanel;
 
-// mt = number of 128-row tiles, nt = number of 128-column blocks (two 64-wide tiles each)
+// mt = number of 128-row tiles, nt = number of 128-column blocks
 static void gemm_nt(const double* A, int lda, const double* B, int ldb, double* C, int ldc,
                     int mt, int nt, int K, double alpha, double beta, bool tri, cudaStream_t st) {
-    static int wt64 = -1, flags = 0;
-    if (wt64 < 0) {
-        const char* e = getenv("DBAT_GEMM_WT"); wt64 = (e && e[0] == '1') ? 1 : 0;
-        e = getenv("DBAT_GEMM_PREFETCH"); if (e && e[0] == '1') flags |= 2;
-        e = getenv("DBAT_GEMM_STAGGER"); if (e) flags |= (atoi(e) & 0xffff) << 8;
-    }
+    static int cfg = -1;
+    if (cfg < 0) { const char* e = getenv("DBAT_GEMM_CFG"); cfg = e ? atoi(e) : 2; }
     if (mt <= 0 || nt <= 0) return;
-    const dim3 grid = tri ? dim3(mt * (mt + 1)) : dim3(mt, 2 * nt);
-    const int f = (tri ? 1 : 0) | (beta != 0.0 ? flags : 0);
-    if (wt64) GemmBig64::launch(grid, st, A, lda, B, ldb, C, ldc, K, alpha, beta, f);
-    else GemmBig32::launch(grid, st, A, lda, B, ldb, C, ldc, K, alpha, beta, f);
+    const int f = tri ? 1 : 0;
+    switch (cfg) {
+    case 1: GemmBig64::launch(tri ? dim3(mt * (mt + 1)) : dim3(mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
+    case 2: GemmSq64::launch(tri ? dim3(mt * (2 * mt + 1)) : dim3(2 * mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
+    case 4: GemmSq64x4::launch(tri ? dim3(mt * (2 * mt + 1)) : dim3(2 * mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
+    case 5: GemmSq64s4::launch(tri ? dim3(mt * (2 * mt + 1)) : dim3(2 * mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
+    case 6: GemmR6432::launch(tri ? dim3(2 * mt * (2 * mt + 1)) : dim3(2 * mt, 4 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
+    case 3: GemmSq128::launch(tri ? dim3(mt * (mt + 1) / 2) : dim3(mt, nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
+    default: GemmBig32::launch(tri ? dim3(mt * (mt + 1)) : dim3(mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
+    }
 }
 
 // Cholesky of one 128x128 diagonal block in shared memory + inverse of its factor.
@@ -428,7 +435,7 @@ k_potrf128_v1(double* __restrict__ A, int lda, double* __restrict__ invL, int bl
 #define PLD2 132
 #define XLD 20
 #define TLD 12
-#define POTRF_SMEM_DOUBLES (NB * PLD2 + 8 * PB * XLD + 2 * PB + 32)
+#define POTRF_SMEM_DOUBLES (NB * PLD2 + 8 * PB * XLD + 3 * PB + 32)
 
 __device__ __forceinline__ double rsqrt_nr(double d) {
     double y;
@@ -464,6 +471,7 @@ __device__ __forceinline__ void bulk_store(double* gdst, const double* ssrc, int
 __device__ __forceinline__ void potrf_diag16(double* As, double* Xd, double* colb, int c0,
                                              int lane, int gcol0, int nvalid, double& lmin, double& lmax,
                                              int& bad) {
+    double* spd = colb + 2 * PB;                 // [16] pivots of this block
     const int r = lane & 15;
     const bool isX = lane >= 16;
     double v[PB];
@@ -497,11 +505,17 @@ __device__ __forceinline__ void potrf_diag16(double* As, double* Xd, double* col
         __syncwarp();
 #pragma unroll
         for (int c = j + 1; c < PB; ++c) v[c] = fma(-w, cb[c], v[c]);
-        // off the chain: scale column j
-        const double isd = rsqrt_nr(dj);
-        if (!(dj > 0.0)) bad = 1;
-        if (gcol0 + j < nvalid) { const double l = dj * isd; lmin = fmin(lmin, l); lmax = fmax(lmax, l); }
-        v[j] *= isd;
+        if (lane == 0) spd[j] = dj;              // pivot, for the scaling pass below
+    }
+    // off the chain: 1/sqrt(d_j) is computed once, by lane j, and broadcast for the column scaling
+    __syncwarp();
+    {
+        const double dr = spd[r];
+        const double isdr = rsqrt_nr(dr);
+        if (!(dr > 0.0)) bad = 1;
+        if (!isX && gcol0 + r < nvalid) { const double l = dr * isdr; lmin = fmin(lmin, l); lmax = fmax(lmax, l); }
+#pragma unroll
+        for (int j = 0; j < PB; ++j) v[j] *= __shfl_sync(0xffffffffu, isdr, j);
     }
     if (!isX) {
 #pragma unroll
@@ -640,18 +654,15 @@ __device__ __forceinline__ void potrf_x_task(double* As, const double* XdAll, in
     }
 }
 
-// W(p): the tasks of one round, handed out through a shared counter (X tasks first, they are longer).
-__device__ __forceinline__ void potrf_worker(double* As, const double* XdAll, const unsigned char* tij, int* ctr,
-                                             int p, int lane, double* __restrict__ out) {
+// W(p): the tasks of one round, dealt round-robin to the nW workers (X tasks first, they are longer;
+// the U groups continue the same round-robin so that the load stays even).
+__device__ __forceinline__ void potrf_worker(double* As, const double* XdAll, const unsigned char* tij,
+                                             int p, int wid, int nW, int lane, double* __restrict__ out) {
     const int m = 14 - 2 * p;
     const int ntile = m * (m + 1) / 2;
     const int nX = p < NB / PB - 1 ? 2 * (p + 1) : 2 * p;       // the last row block has nothing to propagate to
     const int nU = ntile > 3 ? (ntile - 3 + 3) / 4 : 0;
-    for (;;) {
-        int task = 0;
-        if (lane == 0) task = atomicAdd(ctr + p, 1);
-        task = __shfl_sync(0xffffffffu, task, 0);
-        if (task >= nX + nU) break;
+    for (int task = wid; task < nX + nU; task += nW) {
         if (task < nX) potrf_x_task(As, XdAll, p, task, lane, out);
         else potrf_update_group(As, tij, p, 3 + 4 * (task - nX), ntile, lane);
     }
@@ -685,7 +696,7 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
     double* As = sm;                          // [128 columns][PLD2]
     double* XdAll = As + NB * PLD2;           // [8][16][XLD]
     double* colb = XdAll + 8 * PB * XLD;      // [2][16]
-    unsigned char* tij = (unsigned char*)(colb + 2 * PB);   // [105][2] (ti, tj) of the lower-triangular tile list
+    unsigned char* tij = (unsigned char*)(colb + 3 * PB);   // [105][2] (ti, tj) of the lower-triangular tile list
     int* ctr = (int*)(tij + 224);             // [8] task counters
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     double* out = invL + (size_t)blk * NB * NB;
@@ -695,11 +706,18 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
     const long long tstart = clock64();
     double* ptrace = minmax + 16 + warp * 40;     // per warp: 4 stamps per panel
 #endif
-    // Roles (16 warps, 4 per scheduler).  Warp 0: pivots.  Warps 4, 8, 12 share its scheduler and
-    // FP64 pipe: warp 4 only moves data (write-backs), 8 and 12 only take part in the barriers.
-    // The other 12 warps are the DMMA workers.
+    // Roles (16 warps, 4 per scheduler).  Warp 0: pivots.  Warp 4 only moves data (write-backs).
+    // The other 14 warps are the DMMA workers (measured slightly faster than keeping warps 8 and 12,
+    // which share the pivot warp's scheduler, idle: -DPOTRF_W12).
+#ifndef POTRF_W12
+    const bool isPivot = warp == 0, isIO = warp == 4, isWorker = !isPivot && !isIO;
+    const int wid = warp < 4 ? warp - 1 : warp - 2;          // worker id 0..13
+#define POTRF_NW 14
+#else                                            // keep the pivot warp's scheduler free of DMMA work
     const bool isPivot = warp == 0, isIO = warp == 4, isWorker = (warp & 3) != 0;
     const int wid = (warp >> 2) * 3 + (warp & 3) - 1;        // worker id 0..11 (workers only)
+#define POTRF_NW 12
+#endif
     // ---- load the lower triangle (16-byte chunks).  The pivot warp fetches only the first
     //      diagonal block and starts as soon as that has landed.
     if (isPivot) {
@@ -733,7 +751,7 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
             potrf_diag16(As, XdAll + p * PB * XLD, colb, c0, lane, blk * NB + c0, nvalid, lmin, lmax, bad);
         } else if (p > 0) {
             if (isIO) potrf_io(As, XdAll, p - 1, lane, A, lda, out);
-            else if (isWorker) potrf_worker(As, XdAll, tij, ctr, p - 1, lane, out);
+            else if (isWorker) potrf_worker(As, XdAll, tij, p - 1, wid, POTRF_NW, lane, out);
         } else {
             cp_async_wait<0>();
         }
@@ -774,7 +792,7 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
             }
             PTRACE(4 * p + 2)
         } else {
-            if (isWorker && 2 + wid < m) {        // the other row tiles, one per worker
+            if (isWorker && 2 + wid < m) {        // the other row tiles, one per worker (at most 12)
                 double R[2][2][2];
                 potrf_rtiles<1>(As, XdAll + p * PB * XLD, c0, 2 + wid, 2 + wid, lane, R);
             }
@@ -787,8 +805,16 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
     if (isIO) {
         potrf_io(As, XdAll, NB / PB - 1, lane, A, lda, out);
         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    } else if (isWorker || isPivot) potrf_worker(As, XdAll, tij, ctr, NB / PB - 1, lane, out);
+    } else if (isWorker || isPivot) potrf_worker(As, XdAll, tij, NB / PB - 1, isPivot ? POTRF_NW : wid, POTRF_NW + 1, lane, out);
     PTRACE(4 * 8 + 0)
+    if (isPivot) {                               // per-lane pivot statistics -> lane 0
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+            lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        }
+        bad = __any_sync(0xffffffffu, bad);
+    }
     if (t == 0) {
         if (bad) atomicCAS(info, 0, blk + 1);
         double omin = minmax[0], omax = minmax[1];
@@ -1034,6 +1060,90 @@ __global__ void __launch_bounds__(256) k_bwd_coop(const double* __restrict__ A, 
     if (t == 0) atomicExch(&flags[j], 1);
 }
 
+// Pipelined backward substitution, one cooperative launch.  CTA j owns block j of the solution.
+// Its work list is the block column below the diagonal, bottom-up, then its own inverse block:
+//   L(nb-1, j), L(nb-2, j), ..., L(j+1, j), invL_j          (each 128 x 128, column-major)
+// streamed through a ring of three 64-row half-block buffers with cp.async, independent of the
+// flags - only the vector x_i a half-block is multiplied with has to be waited for.  The chain
+// x_i -> x_{i-1} therefore costs: flag + 1 KB vector load + two 64 x 128 shared-memory mat-vecs
+// for L(i, i-1)' + two for invL' + publish.
+#define BWD_LD 66             // half-block column stride in shared memory (64 rows + 2)
+#define BWD_BUF (NB * BWD_LD)
+__device__ __forceinline__ void bwd_issue_half(double* buf, const double* __restrict__ src, size_t lds, int half, int t) {
+    // 128 columns x 64 rows, 16-byte chunks: 32 chunks per column
+    for (int idx = t; idx < NB * 32; idx += 256) {
+        const int c = idx >> 5, r2 = (idx & 31) * 2;
+        cp_async16(buf + c * BWD_LD + r2, src + (size_t)c * lds + half * 64 + r2);
+    }
+}
+__global__ void __launch_bounds__(256, 1) k_bwd_pipe(const double* __restrict__ A, int ld,
+                                                     const double* __restrict__ invL, int nb,
+                                                     const double* __restrict__ y, double* x, int* flags) {
+    extern __shared__ __align__(16) double sm[];
+    double* ring = sm;                       // [3][BWD_BUF]
+    double* v = sm + 3 * BWD_BUF;            // [128] vector being multiplied
+    double* yj = v + NB;                     // [128] running right-hand side of block j
+    double* part = yj + NB;                  // [2][128] partial sums of the two row halves of a thread pair
+    const int t = threadIdx.x, j = blockIdx.x;
+    const int nItems = 2 * (nb - 1 - j) + 2; // half-blocks in the work list
+    auto item_src = [&](int it, const double*& src, size_t& lds, int& half) {
+        const int blk = it >> 1; half = it & 1;
+        if (blk < nb - 1 - j) { const int i = nb - 1 - blk; src = A + (size_t)j * NB * ld + (size_t)i * NB; lds = (size_t)ld; }
+        else { src = invL + (size_t)j * NB * NB; lds = NB; }
+    };
+    if (t < NB) yj[t] = y[(size_t)j * NB + t];
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        if (it < nItems) { const double* src; size_t lds; int half; item_src(it, src, lds, half); bwd_issue_half(ring + it * BWD_BUF, src, lds, half, t); }
+        cp_async_commit();
+    }
+    const int c = t & 127, hr = t >> 7;      // thread pair (c, hr): column c, rows 32 hr .. 32 hr + 31 of the half
+    for (int it = 0; it < nItems; ++it) {
+        // keep two half-blocks in flight beyond the current one
+        if (it + 2 < nItems) { const double* src; size_t lds; int half; item_src(it + 2, src, lds, half); bwd_issue_half(ring + ((it + 2) % 3) * BWD_BUF, src, lds, half, t); }
+        cp_async_commit();
+        const int blk = it >> 1, half = it & 1;
+        const bool isInv = blk >= nb - 1 - j;
+        if (half == 0) {                     // new vector
+            if (!isInv) {
+                const int i = nb - 1 - blk;
+                if (t == 0) { while (atomicAdd(&flags[i], 0) == 0) { } }
+                __syncthreads();
+                if (t < NB) v[t] = __ldcg(x + (size_t)i * NB + t);
+            } else {
+                __syncthreads();
+                if (t < NB) v[t] = yj[t];
+            }
+        }
+        cp_async_wait<2>();
+        __syncthreads();
+        const double* M = ring + (it % 3) * BWD_BUF + c * BWD_LD + 32 * hr;
+        const double* vv = v + 64 * half + 32 * hr;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int r = 0; r < 32; r += 2) {
+            const double2 m2 = *reinterpret_cast<const double2*>(M + r);
+            const double2 v2 = *reinterpret_cast<const double2*>(vv + r);
+            s0 = fma(m2.x, v2.x, s0); s1 = fma(m2.y, v2.y, s1);
+        }
+        part[hr * NB + c] = s0 + s1;
+        __syncthreads();
+        if (t < NB) {
+            const double s = part[t] + part[NB + t];
+            if (!isInv) yj[t] -= s;
+            else if (half == 0) yj[t] = s;   // x_j accumulates in place of yj (v holds the old yj)
+            else yj[t] += s;
+        }
+        // the buffer (it % 3) is refilled by the issue at the top of iteration it + 1: the
+        // barrier after its vector load / cp_async_wait orders that after these reads
+    }
+    __syncthreads();
+    if (t < NB) x[(size_t)j * NB + t] = yj[t];
+    __threadfence();
+    __syncthreads();
+    if (t == 0) atomicExch(&flags[j], 1);
+}
+
 static double* g_solve_tmp = nullptr;
 static int* g_solve_flags = nullptr;
 static int g_solve_tmp_n = 0;
@@ -1057,6 +1167,26 @@ void chol_solve(const CholWork& w, const double* A, double* x, cudaStream_t st) 
     double* y = g_solve_tmp;
     k_get_y_row<<<(w.ld + 255) / 256, 256, 0, st>>>(A, w.ld, y, w.n);
     count_launch();
+    static int pipe_ok = -1;
+    const int pipe_smem = (3 * BWD_BUF + 4 * NB) * 8;
+    if (pipe_ok < 0) {
+        const char* e = getenv("DBAT_BWD");
+        int dev = 0, coop = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        pipe_ok = (coop && !(e && e[0] == '0') &&
+                   cudaFuncSetAttribute(k_bwd_pipe, cudaFuncAttributeMaxDynamicSharedMemorySize, pipe_smem) == cudaSuccess) ? sms : 0;
+    }
+    if (w.nb <= pipe_ok) {
+        cudaMemsetAsync(g_solve_flags, 0, sizeof(int) * w.nb, st);
+        const double* Ac = A; const double* iL = w.invL; int ld = w.ld, nb = w.nb; const double* yc = y;
+        int* fl = g_solve_flags;
+        void* args[] = {(void*)&Ac, (void*)&ld, (void*)&iL, (void*)&nb, (void*)&yc, (void*)&x, (void*)&fl};
+        cudaLaunchCooperativeKernel((void*)k_bwd_pipe, dim3(w.nb), dim3(256), args, pipe_smem, st);
+        count_launch();
+        return;
+    }
     if (w.nb <= g_coop_max) {
         cudaMemsetAsync(g_solve_flags, 0, sizeof(int) * w.nb, st);
         const double* Ac = A; const double* iL = w.invL; int ld = w.ld, nb = w.nb; const double* yc = y;
