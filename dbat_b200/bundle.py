@@ -202,6 +202,11 @@ class Problem:
         elif w == 'cxx_cam':
             nC = self.n - len(s.bundle.serial.OP.dest)
             out = np.zeros((nC, nC))
+        elif w == 'cxx':
+            out = np.zeros((self.n, self.n))
+        elif w == 'cxx_op':
+            m3 = len(s.bundle.serial.OP.dest)
+            out = np.zeros((m3, m3))
         else:
             raise ValueError(which)
         self._check(L.dbat_cov(self._h, _lib.COV[w], float(s0), _lib.dptr(out)))
@@ -394,8 +399,9 @@ def _blockdiag(blocks):
 
 
 def bundle_cov(s, e, *varargin):
-    """bundle_cov.m:1-55: posterior covariances CIO/CEO/COP (block-diagonal, sparse) and
-    CIOF/CEOF (full), from the undamped factorisation on the device, times s0^2."""
+    """bundle_cov.m:1-55: posterior covariances CIO/CEO/COP (block-diagonal, sparse), CIOF/CEOF/COPF
+    (full) and CXX (all unknowns, x order), from the undamped factorisation on the device, times
+    s0^2.  CXX and COPF are dense on the device and refused above 2 GB."""
     P = e.problem
     out = []
     for w in varargin:
@@ -413,6 +419,16 @@ def bundle_cov(s, e, *varargin):
             Cf = np.zeros((N, N))
             Cf[np.ix_(des.dest, des.dest)] = Cc[np.ix_(des.src, des.src)]   # bundle_cov.m:148-196
             out.append(sp.csc_matrix(Cf))
+        elif lw == 'copf':
+            Cop = P.cov('cxx_op', e.s0)                    # OP x OP block of CXX, x order
+            des = s.bundle.deserial.OP
+            N = 3 * s.OP.val.shape[1]
+            nC = P.n - Cop.shape[0]
+            Cf = np.zeros((N, N))
+            Cf[np.ix_(des.dest, des.dest)] = Cop[np.ix_(des.src - nC, des.src - nC)]   # bundle_cov.m:148-196
+            out.append(sp.csc_matrix(Cf))
+        elif lw == 'cxx':
+            out.append(P.cov('cxx', e.s0))                 # bundle_cov.m:138-145
         else:
-            raise NotImplementedError("bundle_cov('%s') is not available on the device path" % w)
+            raise ValueError("bundle_cov: unknown covariance '%s'" % w)
     return out[0] if len(out) == 1 else out

@@ -77,6 +77,7 @@ struct dbat_handle {
     int *d_IOsrc = nullptr, *d_IOdst = nullptr, *d_EOsrc = nullptr, *d_EOdst = nullptr, *d_OPsrc = nullptr, *d_OPdst = nullptr;
     int nIOdes = 0, nEOdes = 0, nOPdes = 0;
     int *d_rep = nullptr, *d_img_chunk_start = nullptr, *d_col2pt = nullptr;
+    double* d_pack = nullptr;                 // packed lower triangle of S for the multi-rank allreduce
     double *d_tmpG = nullptr, *d_partial = nullptr, *d_scal = nullptr;
     double* h_scal = nullptr;           // pinned
     double *d_x = nullptr, *d_t = nullptr, *d_p = nullptr, *d_pgn = nullptr, *d_g = nullptr, *d_pc = nullptr;
@@ -560,6 +561,18 @@ static int dev_dot(dbat_handle* h, const double* a, const double* b, int n, doub
     return 0;
 }
 
+// Lower block-trapezoids of S (block column c: rows 128c..ld-1 of its 128 columns) <-> one contiguous
+// buffer of 8192 nb (nb+1) doubles: the multi-rank allreduce then moves half of the ld x ld square.
+__global__ void k_pack_lower(double* __restrict__ S, int ld, double* __restrict__ buf, int unpack) {
+    const int col = blockIdx.y, c = col >> 7;
+    const size_t off = (size_t)128 * c * ld - (size_t)8192 * c * (c - 1) + (size_t)(col - 128 * c) * (ld - 128 * c);
+    const int r0 = 128 * c;
+    for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < ld; r += gridDim.x * blockDim.x) {
+        if (unpack) S[(size_t)col * ld + r] = buf[off + r - r0];
+        else buf[off + r - r0] = S[(size_t)col * ld + r];
+    }
+}
+
 // Solve the (damped, optionally Jacobi-scaled) normal equations at d_x -> step in `pout`.
 // singular: 1 if the reduced system was not positive definite / numerically singular.
 static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, int* singular) {
@@ -573,7 +586,16 @@ static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, 
     }
     launch_schur(P, lambda, h->st);
     if (h->nranks > 1) {
-        int rc = allreduce(h, P.S, (size_t)P.ldS * P.ldS);
+        const size_t nbk = (size_t)P.ldS / 128, cnt = 8192 * nbk * (nbk + 1);
+        if (!h->d_pack) {
+            if (cudaMalloc(&h->d_pack, sizeof(double) * cnt) != cudaSuccess) { h->err = "out of memory for the allreduce buffer"; return DBAT_E_OOM; }
+            h->allocs.push_back(h->d_pack);
+        }
+        const dim3 grid((unsigned)std::min<size_t>(8, (P.ldS + 255) / 256), (unsigned)P.ldS);
+        k_pack_lower<<<grid, 256, 0, h->st>>>(P.S, P.ldS, h->d_pack, 0);
+        int rc = allreduce(h, h->d_pack, cnt);
+        k_pack_lower<<<grid, 256, 0, h->st>>>(P.S, P.ldS, h->d_pack, 1);
+        count_launch(2);
         if (!rc) rc = allreduce(h, P.rhs, P.ldS);
         if (rc) return rc;
     }
@@ -1085,6 +1107,82 @@ extern "C" int dbat_solve(dbat_handle* h, int method, const dbat_opts* opts, con
 __global__ void __launch_bounds__(128) k_cop(DevProblem P, const double* __restrict__ C, int ldc,
                                               const double* __restrict__ dsc, double s02, double* __restrict__ out);
 
+
+// ---- full point covariances (bundle_cov 'CXX' / 'COPF').  With T_j[a] = (V_j^-1 w_a) for the camera-side
+// rows a of point j (shared IO slots, then 6 per observation; w_a the 3-vector of the cross block):
+//   U  = Ccc (B V^-1)            U[r, xc]  = sum_a Ccc[r, col(a)] T_j[a][t]        (nCam x nOPcols)
+//   Cpp = V^-1 + (B V^-1)' U     Cpp[xc, xc'] = [j == j'] Vi[t][t'] + sum_a T_j[a][t] U[col(a), xc']
+//   Ccp = -U
+__global__ void k_cov_rows(DevProblem P, double* __restrict__ T, int* __restrict__ Tc) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.nOP) return;
+    const size_t r0 = (size_t)DBAT_NSLOT * j + 6 * (size_t)P.pt_start[j];
+    const int o0 = P.pt_start[j], k = P.pt_start[j + 1] - o0;
+    const double* rec = P.pt + (size_t)j * DBAT_PT_STRIDE;
+    const double* v = P.vinv + (size_t)j * 8;
+    const double Vi[6] = {v[0], v[1], v[2], v[3], v[4], v[5]};
+    for (int a = 0; a < DBAT_NSLOT + 6 * k; ++a) {
+        const double* w; int col;
+        if (a < DBAT_NSLOT) { w = rec + DBAT_PT_WSH + 3 * a; col = P.sh_col[a]; }
+        else {
+            const int o = (a - DBAT_NSLOT) / 6, e = (a - DBAT_NSLOT) % 6;
+            w = P.W + (size_t)(o0 + o) * DBAT_W_STRIDE + 3 * e;
+            col = P.eo_col[6 * (size_t)P.img_pm[o0 + o] + e];
+        }
+        double* t = T + 3 * (r0 + a);
+        t[0] = Vi[0] * w[0] + Vi[1] * w[1] + Vi[2] * w[2];
+        t[1] = Vi[1] * w[0] + Vi[3] * w[1] + Vi[4] * w[2];
+        t[2] = Vi[2] * w[0] + Vi[4] * w[1] + Vi[5] * w[2];
+        Tc[r0 + a] = col;
+    }
+}
+__global__ void k_cov_U(DevProblem P, const double* __restrict__ C, int ldc, const double* __restrict__ dsc,
+                        const double* __restrict__ T, const int* __restrict__ Tc, double* __restrict__ U) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (r >= P.nC) return;
+    const int* opc = P.op_col + 3 * (size_t)j;
+    if (opc[0] < 0 && opc[1] < 0 && opc[2] < 0) return;
+    const size_t r0 = (size_t)DBAT_NSLOT * j + 6 * (size_t)P.pt_start[j];
+    const int rows = DBAT_NSLOT + 6 * (P.pt_start[j + 1] - P.pt_start[j]);
+    double u[3] = {0.0, 0.0, 0.0};
+    const double dr = dsc[r];
+    for (int a = 0; a < rows; ++a) {
+        const int ca = Tc[r0 + a];
+        if (ca < 0) continue;
+        const double c = C[(size_t)ca * ldc + r] * dr * dsc[ca];
+        const double* t = T + 3 * (r0 + a);
+        u[0] += c * t[0]; u[1] += c * t[1]; u[2] += c * t[2];
+    }
+    for (int t = 0; t < 3; ++t) if (opc[t] >= 0) U[(size_t)(opc[t] - P.nC) * P.nC + r] = u[t];
+}
+__global__ void k_cov_pp(DevProblem P, const double* __restrict__ T, const int* __restrict__ Tc,
+                         const double* __restrict__ U, const int* __restrict__ col2pt, double* __restrict__ Cpp) {
+    const int m3 = P.n - P.nC;
+    const int xc = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;      // column xc (point j'), row point j
+    if (xc >= m3) return;
+    const int* opc = P.op_col + 3 * (size_t)j;
+    if (opc[0] < 0 && opc[1] < 0 && opc[2] < 0) return;
+    const size_t r0 = (size_t)DBAT_NSLOT * j + 6 * (size_t)P.pt_start[j];
+    const int rows = DBAT_NSLOT + 6 * (P.pt_start[j + 1] - P.pt_start[j]);
+    double acc[3] = {0.0, 0.0, 0.0};
+    const double* Uc = U + (size_t)xc * P.nC;
+    for (int a = 0; a < rows; ++a) {
+        const int ca = Tc[r0 + a];
+        if (ca < 0) continue;
+        const double u = Uc[ca];
+        const double* t = T + 3 * (r0 + a);
+        acc[0] += t[0] * u; acc[1] += t[1] * u; acc[2] += t[2] * u;
+    }
+    const int code = col2pt[xc];                          // 3 j' + t' of OP column nC + xc
+    if (code / 3 == j) {
+        const double* v = P.vinv + (size_t)j * 8;
+        const int tp = code % 3;
+        const double Vrow[3][3] = {{v[0], v[1], v[2]}, {v[1], v[3], v[4]}, {v[2], v[4], v[5]}};
+        acc[0] += Vrow[0][tp]; acc[1] += Vrow[1][tp]; acc[2] += Vrow[2][tp];
+    }
+    for (int t = 0; t < 3; ++t) if (opc[t] >= 0) Cpp[(size_t)xc * m3 + (opc[t] - P.nC)] = acc[t];
+}
+
 extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
     if (!h || !out) return DBAT_E_BADARG;
     if (h->nranks > 1) { h->err = "dbat_cov is single-rank only"; return DBAT_E_UNSUPPORTED; }
@@ -1111,7 +1209,56 @@ extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
     if (e != cudaSuccess) { cudaFree(Z); cudaFree(C); h->err = std::string("dbat_cov: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
     const double s02 = s0 * s0;
     const int nC = P.nC, ld = P.ldS;
-    if (which == DBAT_COV_COP) {
+    if (which == DBAT_COV_CXX || which == DBAT_COV_CXX_OP) {
+        const int m3 = P.n - nC;
+        const size_t limit = (size_t)1 << 28;                 // 2 GB of doubles per dense block
+        if ((size_t)m3 * m3 > limit || (size_t)nC * m3 > limit || (which == DBAT_COV_CXX && (size_t)P.n * P.n > limit)) {
+            cudaFree(Z); cudaFree(C);
+            h->err = "dense point covariance too large (more than 2 GB); use COP for the 3x3 blocks";
+            return DBAT_E_UNSUPPORTED;
+        }
+        const size_t nRows = (size_t)DBAT_NSLOT * P.nOP + 6 * (size_t)P.nObs;
+        double *T = nullptr, *U = nullptr, *Cpp = nullptr; int* Tc = nullptr;
+        if (cudaMalloc(&T, sizeof(double) * 3 * std::max<size_t>(1, nRows)) || cudaMalloc(&Tc, sizeof(int) * std::max<size_t>(1, nRows)) ||
+            cudaMalloc(&U, sizeof(double) * std::max<size_t>(1, (size_t)nC * m3)) || cudaMalloc(&Cpp, sizeof(double) * std::max<size_t>(1, (size_t)m3 * m3))) {
+            cudaFree(T); cudaFree(Tc); cudaFree(U); cudaFree(Cpp); cudaFree(Z); cudaFree(C);
+            h->err = "out of memory for the point covariance"; return DBAT_E_OOM;
+        }
+        cudaMemsetAsync(U, 0, sizeof(double) * std::max<size_t>(1, (size_t)nC * m3), h->st);
+        cudaMemsetAsync(Cpp, 0, sizeof(double) * std::max<size_t>(1, (size_t)m3 * m3), h->st);
+        if (P.nOP > 0 && m3 > 0) {
+            launch_point_vinv(P, 0.0, h->st);
+            k_cov_rows<<<(P.nOP + 127) / 128, 128, 0, h->st>>>(P, T, Tc);
+            k_cov_U<<<dim3((nC + 127) / 128, P.nOP), 128, 0, h->st>>>(P, C, ld, h->d_dscale, T, Tc, U);
+            k_cov_pp<<<dim3((m3 + 127) / 128, P.nOP), 128, 0, h->st>>>(P, T, Tc, U, h->d_col2pt, Cpp);
+            count_launch(3);
+        }
+        std::vector<double> hpp((size_t)m3 * m3), hu, hc, dsc;
+        cudaMemcpyAsync(hpp.data(), Cpp, sizeof(double) * hpp.size(), cudaMemcpyDeviceToHost, h->st);
+        if (which == DBAT_COV_CXX) {
+            hu.resize((size_t)nC * m3); hc.resize((size_t)ld * ld); dsc.resize(std::max(1, nC));
+            cudaMemcpyAsync(hu.data(), U, sizeof(double) * hu.size(), cudaMemcpyDeviceToHost, h->st);
+            cudaMemcpyAsync(hc.data(), C, sz, cudaMemcpyDeviceToHost, h->st);
+            cudaMemcpyAsync(dsc.data(), h->d_dscale, sizeof(double) * nC, cudaMemcpyDeviceToHost, h->st);
+        }
+        e = cudaStreamSynchronize(h->st);
+        cudaFree(T); cudaFree(Tc); cudaFree(U); cudaFree(Cpp);
+        const double nanv = NAN;
+        if (which == DBAT_COV_CXX_OP) {
+            for (size_t k = 0; k < hpp.size(); ++k) out[k] = info != 0 ? nanv : s02 * hpp[k];
+        } else {
+            const size_t n = (size_t)P.n;
+            for (size_t b = 0; b < n; ++b)
+                for (size_t a = 0; a < n; ++a) {
+                    double v;
+                    if (a < (size_t)nC && b < (size_t)nC) v = hc[b * ld + a] * dsc[a] * dsc[b];
+                    else if (a < (size_t)nC) v = -hu[(b - nC) * nC + a];
+                    else if (b < (size_t)nC) v = -hu[(a - nC) * nC + b];
+                    else v = hpp[(b - nC) * m3 + (a - nC)];
+                    out[b * n + a] = info != 0 ? nanv : s02 * v;
+                }
+        }
+    } else if (which == DBAT_COV_COP) {
         double* dOut = nullptr;
         cudaMalloc(&dOut, sizeof(double) * 9 * (size_t)std::max(1, P.nOP));
         cudaMemsetAsync(dOut, 0, sizeof(double) * 9 * (size_t)std::max(1, P.nOP), h->st);

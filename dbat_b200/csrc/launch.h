@@ -28,6 +28,7 @@ void launch_diag(const DevProblem& P, const double* camDiag, double* diagN, cuda
 void launch_build_S(const DevProblem& P, const double* camDiag, const double* camG, double lambda,
                     cudaStream_t st);
 void launch_schur(const DevProblem& P, double lambda, cudaStream_t st);
+void launch_point_vinv(const DevProblem& P, double lambda, cudaStream_t st);   // P.vinv = (V_j + lambda I)^-1
 void launch_scale_S(const DevProblem& P, const double* d, cudaStream_t st);
 void launch_backsub(const DevProblem& P, double lambda, const double* pc, double* p, cudaStream_t st);
 void launch_vec_ops_sum(const double* a, int n, double* partial, double* scal, int slot, cudaStream_t st);

@@ -648,6 +648,9 @@ __global__ void k_schur_sh_apply(DevProblem P, const double* __restrict__ shAcc)
     }
 }
 
+void launch_point_vinv(const DevProblem& P, double lambda, cudaStream_t st) {
+    if (P.nOP > 0) { k_point_vinv<<<(P.nOP + 255) / 256, 256, 0, st>>>(P, lambda); count_launch(); }
+}
 static int g_schur_mode = -1;       // 0 = grouped atomic (default), 1 = deterministic, 2 = per-point atomic
 static double* g_shAcc = nullptr;
 void launch_schur(const DevProblem& P, double lambda, cudaStream_t st) {

@@ -55,6 +55,9 @@ extern "C" {
 #define DBAT_COV_CEO  2   /* out: 6 x 6 x nImg */
 #define DBAT_COV_COP  3   /* out: 3 x 3 x nOP */
 #define DBAT_COV_CXX_CAM 4 /* out: nCam x nCam dense covariance of the IO+EO unknowns (x order) */
+#define DBAT_COV_CXX  5   /* out: n x n dense covariance of all unknowns, x order (bundle_cov.m:138-145);
+                             refused with DBAT_E_UNSUPPORTED when the dense result would exceed 2 GB */
+#define DBAT_COV_CXX_OP 6 /* out: (n - nCam) x (n - nCam): the OP x OP block of CXX (source of COPF) */
 
 typedef struct dbat_handle dbat_handle;
 

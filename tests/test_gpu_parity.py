@@ -202,8 +202,9 @@ def test_posterior_covariances(case):
     s1, ok, _, s0, E = dbat_b200.bundle(s1, 'gna')
     s2, oko, _, s0o, Eo = obundle(s2, 'gna')
     assert ok and oko
-    for w in ('CIO', 'CEO', 'COP', 'CIOF', 'CEOF'):
-        Cg = dbat_b200.bundle_cov(s1, E, w).toarray()
+    for w in ('CIO', 'CEO', 'COP', 'CIOF', 'CEOF', 'COPF', 'CXX'):
+        Cg = dbat_b200.bundle_cov(s1, E, w)
+        Cg = Cg.toarray() if hasattr(Cg, 'toarray') else Cg
         Co = ocov(s2, Eo, w)
         assert Cg.shape == Co.shape
         assert relmax(Cg, Co) < 1e-8, w
