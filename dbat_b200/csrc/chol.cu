@@ -697,7 +697,6 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
     double* XdAll = As + NB * PLD2;           // [8][16][XLD]
     double* colb = XdAll + 8 * PB * XLD;      // [2][16]
     unsigned char* tij = (unsigned char*)(colb + 3 * PB);   // [105][2] (ti, tj) of the lower-triangular tile list
-    int* ctr = (int*)(tij + 224);             // [8] task counters
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     double* out = invL + (size_t)blk * NB * NB;
     double lmin = 1e300, lmax = 0.0;
@@ -742,7 +741,6 @@ k_potrf128(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, 
             while (i * (i + 1) / 2 > u) --i;
             tij[2 * u] = (unsigned char)i; tij[2 * u + 1] = (unsigned char)(u - i * (i + 1) / 2);
         }
-        if (u >= 128 && u < 136) ctr[u - 128] = 0;
     }
     for (int p = 0; p < NB / PB; ++p) {
         const int c0 = PB * p;

@@ -482,7 +482,7 @@ __device__ __forceinline__ void grp_store(GrpHeader& h, int t, const GrpPrefetch
 }
 
 // dynamic shared memory: red[ntask*18] | Wsm[GRP_CAP * m * 18] | Ysm[GRP_CAP * m * 2 * GRP_YH]
-__global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double* __restrict__ shAcc, int flags) {
+__global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double* __restrict__ shAcc) {
     extern __shared__ __align__(16) double dsm[];
     __shared__ GrpHeader s_hdr[2];
     __shared__ unsigned char s_po[DBAT_GRP_MAXM * (DBAT_GRP_MAXM + 1) / 2], s_po2[DBAT_GRP_MAXM * (DBAT_GRP_MAXM + 1) / 2];
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
         __syncthreads();
         // flush: threads 0..179 keep a fixed position inside the 6x6 block (36 | 180) resp. inside the
         // 15x6 shared-column strip (90 | 180); consecutive lanes -> consecutive rows a of one column
-        if (t < 180 && !(flags & 1)) {
+        if (t < 180) {
             const int k = t % 36, b = k / 6, a = k - 6 * b;
             const int srcoff = (a / 3) * 18 + 3 * b + a % 3;
             for (int pr = t / 36; pr < npair; pr += 5) {
@@ -673,9 +673,7 @@ void launch_schur(const DevProblem& P, double lambda, cudaStream_t st) {
                 static bool attr = false;
                 auto smem_for = [](int mm) { return ((mm * (mm + 1) + 6 * mm) * 18 + GRP_CAP * mm * 18 + GRP_CAP * mm * 2 * GRP_YH) * 8; };
                 if (!attr) { cudaFuncSetAttribute(k_schur_group, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(DBAT_GRP_MAXM)); attr = true; }
-                static int dbg = -1;
-                if (dbg < 0) { const char* e = getenv("DBAT_SCHUR_NOFLUSH"); dbg = (e && e[0] == '1') ? 1 : 0; }
-                k_schur_group<<<std::min(P.nGrp, 148 * 24), GRP_TH, smem_for(P.grpMaxRays), st>>>(P, g_shAcc, dbg);
+                k_schur_group<<<std::min(P.nGrp, 148 * 24), GRP_TH, smem_for(P.grpMaxRays), st>>>(P, g_shAcc);
                 count_launch();
             }
             if (P.nBig > 0) {

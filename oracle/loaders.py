@@ -118,14 +118,18 @@ def load_camera_stations(path):
 
 
 # --------------------------------------------------------------------------- PhotoModeler text export
-def load_pm_export(path):
+def load_pm_export(path, imSz=None):
     """Subset of `code/file/loadpm.m:104-330`: 5 header lines, per-image 6-line blocks
     (id name; outer x y z kappa phi omega [deg]; std; cov (blank); inner f xp yp xs ys K1 K2 K3 P1 P2;
     std), control points `id x y z sx sy sz`, object points (same columns), mark points
     `photo(0-based) id x y sx sy`; sections end with a blank line."""
     lines = open(path).read().split('\n')
     hdr2 = lines[1].split()
-    job = {'imSz': np.array([float(hdr2[2]), float(hdr2[3])]),
+    # line 2 carries the image size only in newer exports; loadpm.m:8-9,117-120 then takes it from
+    # the caller (or reads the image files, which are not shipped)
+    if imSz is None:
+        imSz = [float(hdr2[2]), float(hdr2[3])]
+    job = {'imSz': np.array(imSz, float),
            'defCam': np.array([float(v) for v in lines[3].split()])}
     k = 5
     images = []
@@ -206,5 +210,61 @@ def prague_cam_struct(root, stub):
         fixed = np.all(cp_std[:, k] == 0)
         s.prior.OP.use[:, j] = not fixed
         s.bundle.est.OP[:, j] = not fixed
+        s.prior.OP.isCtrl[j] = True
+    return s
+
+
+def stpierre_struct(root, imSz=(6912, 5212)):
+    """StPierre `C5_reduced` PhotoModeler export (`data/hamburg2017/stpierre/pmexports`) set up like
+    `stpierrebundledemo_ps.m:100-111`: forward Brown model (-1), self-calibration of all camera
+    parameters except skew and aspect (`setcamest(s0,'all','not','sk','as')`), EO and OP start values
+    as loaded, datum from the weighted control points (prior observations, `setcpt.m`).  The export's
+    header has no image size and the images are not shipped; the size used here makes the pixels
+    square for the exported sensor (9.9658 x 7.5152 mm) and covers the largest measured coordinate
+    (6885.6, 5206.6) - there is no reference golden for this data set, it is an oracle-vs-device case."""
+    import os
+    prob = load_pm_export(os.path.join(root, 'C5_reduced-pmexport.txt'), imSz)
+    nImg = len(prob['images'])
+    ids = np.unique(np.concatenate([prob['ctrlPts'][:, 0], prob['objPts'][:, 0]])).astype(int)
+    op_of = {v: i for i, v in enumerate(ids)}
+    nK, nP = 3, 2
+    inner = prob['job']['defCam']
+    imSz = prob['job']['imSz']
+    IO = np.zeros((5 + nK + nP, nImg))
+    IO[0] = inner[0]
+    IO[1], IO[2] = inner[1], -inner[2]                     # prob2dbatstruct.m:226-236 sign conventions
+    IO[5:8] = -inner[5:8, None]
+    IO[8:10] = -inner[8:10, None]
+    px = inner[3:5] / imSz
+    IO[3] = 1 - px[0] / px[1]
+    pxSize = np.array([[px[1]], [px[1]]])
+    EO = np.zeros((6, nImg))
+    for i, im in enumerate(prob['images']):
+        EO[0:3, i] = im['outer'][0:3]
+        EO[3:6, i] = np.deg2rad(im['outer'][[5, 4, 3]])
+    OP = np.full((3, len(ids)), np.nan)
+    for r in np.vstack([prob['objPts'], prob['ctrlPts']]):
+        OP[:, op_of[int(r[0])]] = r[1:4]
+    mk = prob['markPts']
+    keep = np.array([int(r[1]) in op_of for r in mk])
+    mk = mk[keep]
+    order = np.lexsort((mk[:, 1], mk[:, 0]))               # columns sorted by (image, id), prob2dbatstruct.m:349-365
+    mk = mk[order]
+    mstd = mk[:, 4:6].copy()
+    if np.any(mstd == 0):                                  # prob2dbatstruct.m:367-373: any zero => all 1 px
+        mstd[:] = 1.0
+    s = new_struct(IO, EO, OP, mk[:, 2:4].T, mk[:, 0].astype(int), np.array([op_of[int(v)] for v in mk[:, 1]]),
+                   pxSize, imSz[:, None], -1, nK, nP, mstd.T)
+    s.OP.id = ids
+    s.bundle.est.IO[:] = True
+    s.bundle.est.IO[3:5, :] = False                        # not 'as', 'sk'
+    s.bundle.est.EO[:] = True
+    s.bundle.est.OP[:] = True
+    s.prior.OP.isCtrl = np.zeros(len(ids), bool)
+    for r in prob['ctrlPts']:                              # weighted control points: prior observations
+        j = op_of[int(r[0])]
+        s.prior.OP.val[:, j] = r[1:4]
+        s.prior.OP.std[:, j] = r[4:7]
+        s.prior.OP.use[:, j] = True
         s.prior.OP.isCtrl[j] = True
     return s

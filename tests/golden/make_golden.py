@@ -31,6 +31,9 @@ FILES = {
         'data/prague2016/cam/dbatexports/weighted-no-orient-dbatreport.txt',
         'data/prague2016/cam/dbatexports/fixed-no-orient-dbatreport.txt',
     ],
+    'stpierre': [
+        'data/hamburg2017/stpierre/pmexports/C5_reduced-pmexport.txt',
+    ],
     'dbatexports': [
         'data/dbat/dbatexports/camcal-dbatreport.txt',
         'data/dbat/dbatexports/camcal-dbatreport-model2.txt',
@@ -51,6 +54,8 @@ def main():
             rel = f.split(sub + '/', 1)[1] if sub + '/' in f else os.path.basename(f)
             if sub == 'prague2016cam':
                 rel = f.split('data/prague2016/cam/', 1)[1]
+            if sub == 'stpierre':
+                rel = os.path.basename(f)
             dst = os.path.join(HERE, sub, rel)
             os.makedirs(os.path.dirname(dst), exist_ok=True)
             shutil.copyfile(os.path.join(REF, f), dst)

@@ -334,6 +334,7 @@ print('DET-OK')
 
 
 PRAGUE = os.path.join(os.path.dirname(GOLD), 'prague2016cam')
+STPIERRE = os.path.join(os.path.dirname(GOLD), 'stpierre')
 
 
 @pytest.mark.parametrize('stub,sigma0,last', [('weighted', 1.60984, 98.3715), ('fixed', 1.78095, 108.827)])
@@ -372,6 +373,36 @@ def test_prague2016_selfcalibration(damping):
         np.testing.assert_allclose(E.x, Eo.x, rtol=EST_RTOL, atol=1e-12)
     else:
         np.testing.assert_allclose(E.x, Eo.x, rtol=1e-6, atol=1e-9)
+
+
+@pytest.mark.parametrize('damping', ['gna', 'lmp', 'lm'])
+def test_stpierre_selfcalibration(damping):
+    """BASELINE config 3 data (hamburg2017 StPierre, `C5_reduced` PhotoModeler export: 28 images, 2003
+    object points, 4331 image points, 4 weighted control points) set up like `stpierrebundledemo_ps.m`:
+    forward Brown model (-1), self-calibration of everything but skew/aspect, datum from the prior
+    observations of the control points; followed by bundle_cov.  The reference holds no golden for
+    this input (the demo's .psz is missing, the export has no image size): oracle vs CUDA."""
+    s = loaders.stpierre_struct(STPIERRE)
+    so = copy.deepcopy(s)
+    s, ok, iters, s0, E = dbat_b200.bundle(s, damping)
+    so, oko, iterso, s0o, Eo = obundle(so, damping)
+    assert ok and oko
+    np.testing.assert_allclose(s0, s0o, rtol=EST_RTOL)
+    assert abs(s0 - 1.0282960127) < 1e-8                   # value of the oracle at the time of writing
+    if damping != 'lm':
+        assert iters == iterso
+        np.testing.assert_allclose(E.x, Eo.x, rtol=EST_RTOL, atol=1e-12)
+        np.testing.assert_allclose(E.res, Eo.res, rtol=1e-9)
+    else:
+        np.testing.assert_allclose(E.x, Eo.x, rtol=1e-6, atol=1e-9)
+    if damping == 'gna':
+        for w in ('CIO', 'CEO', 'COP'):
+            Cg = dbat_b200.bundle_cov(s, E, w).toarray()
+            Co = ocov(so, Eo, w)
+            assert relmax(Cg, Co) < 1e-7, w
+            sg, sd = np.sqrt(np.diag(Cg)), np.sqrt(np.diag(Co))
+            m = sd > 0
+            np.testing.assert_allclose(sg[m], sd[m], rtol=1e-7)
 
 
 @pytest.mark.parametrize('seed', [1, 2, 3, 4, 5, 6])

@@ -167,3 +167,22 @@ def test_prague2016_cam_golden(stub, sigma0, nparams, nobs, last):
     assert (E.numParams, E.numObs) == (nparams, nobs)
     assert E.redundancy == 3734
     assert abs(E.res[-1] - last) < 6e-4
+
+
+def test_stpierre_oracle_converges():
+    """hamburg2017 StPierre C5_reduced export (BASELINE config 3 data; no reference golden exists for
+    this input): the oracle converges with every damping to the same sigma0 ~ 1 (a-priori mark point
+    sigma of 1 px, prob2dbatstruct.m:367-373) - a plausibility pin of loader + model -1 + prior
+    observations on real data."""
+    import copy, os
+    from oracle import loaders
+    from oracle.bundle import bundle as obundle
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'stpierre')
+    s = loaders.stpierre_struct(root)
+    assert s.EO.val.shape[1] == 28 and s.OP.val.shape[1] == 2003 and s.IP.val.shape[1] == 4331
+    vals = []
+    for damping, n in (('gna', 5), ('lmp', 5), ('lm', 6)):
+        s2, ok, iters, s0, E = obundle(copy.deepcopy(s), damping)
+        assert ok and iters == n
+        vals.append(s0)
+    assert max(vals) - min(vals) < 1e-9 and abs(vals[0] - 1.0282960127) < 1e-8
