@@ -302,8 +302,12 @@ def main():
     if dom == 'cholesky':
         fp64 = fp64_peak_tflops()
         ach = (nRed ** 3 / 3.0) / (ph_ms['cholesky'] * 1e-3) / 1e12
+        # DRAM bytes of one factorisation from the ncu capture profiles/chol_factor_n6002_dram.csv
+        # (dram__bytes_read.sum + dram__bytes_write.sum over its k_potrf128 / k_gemm_nt launches, cold
+        # caches): known for the config-4 size only
+        traffic = 3.306e9 if nRed == 6002 else None
         line['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': fp64, 'unit': 'TFLOP/s',
-                            'frac': ach / fp64, 'traffic': None,
+                            'frac': ach / fp64, 'traffic': traffic,
                             'kernel': 'k_gemm_nt (DMMA blocked Cholesky, %d^3/3 flop per factorisation)' % nRed,
                             'peak_source': 'cuBLAS DGEMM 8192^3 measured in this run (FP64; MEASURED_PEAKS.json '
                                            'holds no FP64 figure)'}
