@@ -55,9 +55,18 @@ class Result(C.Structure):
 EXPORTS = ['dbat_create', 'dbat_destroy', 'dbat_last_error', 'dbat_num_unknowns',
            'dbat_num_residuals', 'dbat_eval', 'dbat_jacobian_nnz', 'dbat_jacobian_csc',
            'dbat_default_opts', 'dbat_solve', 'dbat_normal_step', 'dbat_cov',
-           'dbat_comm_unique_id', 'dbat_comm_init', 'dbat_phase_times', 'dbat_dense_chol_solve']
+           'dbat_comm_unique_id', 'dbat_comm_init', 'dbat_phase_times', 'dbat_dense_chol_solve',
+           'dbat_forwintersect', 'dbat_forwintersect_error']
 
 _lib = None
+
+
+class FwiDesc(C.Structure):
+    _fields_ = [
+        ('nImg', C.c_int64), ('nOP', C.c_int64), ('nObs', C.c_int64), ('NC', C.c_int64), ('nK', C.c_int64), ('nP', C.c_int64),
+        ('IO', c_dp), ('EO', c_dp), ('pxSize', c_dp), ('IPval', c_dp),
+        ('obs_img', c_ip), ('obs_op', c_ip), ('pts', c_ip), ('nPts', C.c_int64),
+    ]
 
 
 def lib():
@@ -102,6 +111,10 @@ def lib():
     L.dbat_phase_times.restype = C.c_int
     L.dbat_dense_chol_solve.argtypes = [C.c_int64, c_dp, c_dp, c_dp, c_dp, C.c_int, c_dp]
     L.dbat_dense_chol_solve.restype = C.c_int
+    L.dbat_forwintersect.argtypes = [C.POINTER(FwiDesc), c_dp, c_dp, c_dp]
+    L.dbat_forwintersect.restype = C.c_int
+    L.dbat_forwintersect_error.argtypes = []
+    L.dbat_forwintersect_error.restype = C.c_char_p
     _lib = L
     return L
 

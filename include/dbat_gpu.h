@@ -167,6 +167,26 @@ int dbat_comm_init(dbat_handle *h, int nranks, int rank, const void *id128);
  * names[i] is a static string; returns the number of phases written (<= cap). */
 int dbat_phase_times(const dbat_handle *h, const char **names, double *ms, int64_t *count, int cap);
 
+/* ---- start values ------------------------------------------------------------
+ * Forward intersection of object points from known IO/EO.  Replaces
+ * code/photogrammetry/forwintersect.m:19-46 (pm_multiforwintersect.m:15-51, pm_forwintersect3.m:11-73,
+ * lens correction pm_multilenscorr1.m:36-69).  All arrays are host arrays in MATLAB layout
+ * (column-major doubles, 1-based int64 indices).  Points seen in fewer than two images get NaN. */
+typedef struct dbat_fwi_desc {
+    int64_t nImg, nOP, nObs, NC, nK, nP;
+    const double*  IO;        /* NC x nImg  [f; ppx; ppy; b1; b2; K(nK); P(nP)] (the struct's storage) */
+    const double*  EO;        /* 6 x nImg   [X;Y;Z;omega;phi;kappa] */
+    const double*  pxSize;    /* 2 x nImg   mm per pixel */
+    const double*  IPval;     /* 2 x nObs   measured pixel coordinates */
+    const int64_t* obs_img;   /* nObs, image of every observation (1-based) */
+    const int64_t* obs_op;    /* nObs, object point (column of OP) of every observation (1-based) */
+    const int64_t* pts;       /* nPts, object points to compute (1-based) */
+    int64_t nPts;
+} dbat_fwi_desc;
+/* OP: 3 x nPts out; res: nPts out or NULL (pm_forwintersect3's norm(b-Ax)/n); kernel_ms: device time or NULL */
+int dbat_forwintersect(const dbat_fwi_desc* desc, double* OP, double* res, double* kernel_ms);
+const char* dbat_forwintersect_error(void);
+
 #ifdef __cplusplus
 }
 #endif

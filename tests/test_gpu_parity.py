@@ -427,3 +427,54 @@ def test_structural_rank_matches_oracle_on_thin_networks(seed):
     so, oko, _, _, Eo = obundle(so, 'gna')
     assert (E.code == -4) == (Eo.code == -4), (E.code, Eo.code)
     assert E.code == Eo.code
+
+
+# ------------------------------------------------------------------ start values
+def test_forwintersect_matches_oracle_camcal():
+    """forwintersect(s,'all',true) as in camcaldemo.m:107 on the camcal project (golden EO, calibrated
+    camera): CUDA kernel vs the literal restatement of pm_multiforwintersect / pm_forwintersect3."""
+    from oracle.photogrammetry import forwintersect as ofwi
+    from camcal_fixture import camcal_struct
+    s = camcal_struct('golden', 0)
+    s.OP.val[:, s.bundle.est.OP.all(axis=0)] = np.nan          # unknown before the intersection
+    sg, idg, resg = dbat_b200.forwintersect(s, 'all', True)
+    so, ido, reso = ofwi(s, 'all', True)
+    assert np.array_equal(idg, ido) and len(idg) == 96
+    est = s.bundle.est.OP.all(axis=0)
+    np.testing.assert_allclose(sg.OP.val[:, est], so.OP.val[:, est], rtol=1e-9, atol=1e-9)
+    np.testing.assert_allclose(resg, reso, rtol=1e-6, atol=1e-10)
+    assert np.array_equal(sg.OP.val[:, ~est], s.OP.val[:, ~est])       # control points untouched
+
+
+@pytest.mark.parametrize('case', ['model3', 'ragged'])
+def test_forwintersect_matches_oracle_synthetic(case):
+    """Same on seeded synthetic blocks (ragged: points with different ray counts, incl. an explicit id list
+    and a point left with a single ray -> NaN)."""
+    from oracle.photogrammetry import forwintersect as ofwi
+    s, truth = scene(**CASES[case])
+    s.IO.val[5:10, :] = truth['IO'][5:10, None]                 # non-trivial lens correction
+    k = np.flatnonzero(s.IP.op == 3)
+    keep = np.ones(len(s.IP.op), bool)
+    keep[k[1:]] = False                                          # point 3 keeps one ray
+    for f in ('val', 'std'):
+        setattr(s.IP, f, getattr(s.IP, f)[:, keep])
+    for f in ('img', 'op', 'cam'):
+        setattr(s.IP, f, getattr(s.IP, f)[keep])
+    ids = np.arange(0, s.OP.val.shape[1], 2)
+    ids = np.union1d(ids, [3])
+    sg, idg, resg = dbat_b200.forwintersect(s, ids)
+    so, ido, reso = ofwi(s, ids)
+    assert np.array_equal(idg, ido)
+    assert np.isnan(sg.OP.val[:, 3]).all() and np.isnan(so.OP.val[:, 3]).all()
+    m = ~np.isnan(so.OP.val[0])
+    np.testing.assert_allclose(sg.OP.val[:, m], so.OP.val[:, m], rtol=1e-9, atol=1e-9)
+    mr = ~np.isnan(reso)
+    np.testing.assert_allclose(resg[mr], reso[mr], rtol=1e-6, atol=1e-10)
+    assert np.isnan(resg[~mr]).all()
+
+
+def test_forwintersect_refuses_bad_eo():
+    s, _ = scene(**CASES['model3'])
+    s.EO.val[0, 0] = np.nan
+    with pytest.raises(ValueError, match='EO'):
+        dbat_b200.forwintersect(s, 'all')

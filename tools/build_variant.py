@@ -5,7 +5,7 @@ def build(tag, extra):
     src = os.path.join(ROOT, 'dbat_b200', 'csrc')
     os.makedirs(os.path.join(ROOT, 'variants'), exist_ok=True)
     objs, procs = [], []
-    for f in ['eval', 'schur', 'schur_index', 'chol', 'api']:
+    for f in ['eval', 'schur', 'schur_index', 'chol', 'api', 'startval']:
         o = '/tmp/var_%s_%s.o' % (tag, f)
         cmd = ['/usr/local/cuda/bin/nvcc', '-Wno-deprecated-gpu-targets'] + extra.split() + [
             '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
