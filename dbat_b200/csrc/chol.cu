@@ -43,7 +43,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 //              the epilogue)
 // tile list: if tri != 0 the 1-D grid enumerates the tiles (ti, tj) with BN*tj <= BM*ti + BM-1 of
 // the lower triangle (BM = 2 BN only); otherwise blockIdx.x = ti, blockIdx.y = tj.
-template <int BM, int BN, int WTM, int WTN, int STAGES, int MINB>
+template <int BM, int BN, int WTM, int WTN, int STAGES, int MINB, bool PFC = false>
 __global__ void __launch_bounds__((BM / WTM) * (BN / WTN) * 32, MINB)
 k_gemm_nt(const double* A, int lda, const double* __restrict__ B, int ldb,
           double* C, int ldc, int K, double alpha, double beta, int tri) {
@@ -100,11 +100,23 @@ k_gemm_nt(const double* A, int lda, const double* __restrict__ B, int ldb,
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) { if (s < nk) load_stage(s, s); cp_async_commit(); }
+    // PFC: the C tile of a read-modify-write update is fetched into registers three k-slices before
+    // the end of the main loop, so that its DRAM latency is covered by DMMA work
+    double cpf[PFC ? MI : 1][PFC ? NJ : 1][2];
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         if (kt + STAGES - 1 < nk) load_stage((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
         cp_async_commit();
+        if (PFC && kt == (nk > 3 ? nk - 3 : 0)) {
+#pragma unroll
+            for (int i = 0; i < (PFC ? MI : 1); ++i)
+#pragma unroll
+                for (int j = 0; j < (PFC ? NJ : 1); ++j) {
+                    const double* p0 = Cg + (size_t)(wn + 8 * j + 2 * (lane & 3)) * ldc + wm + 8 * i + (lane >> 2);
+                    cpf[i][j][0] = p0[0]; cpf[i][j][1] = p0[ldc];
+                }
+        }
         const double* As = sm + (size_t)(kt % STAGES) * STAGE;
         const double* Bs = As + KS * LA;
 #pragma unroll
@@ -132,6 +144,15 @@ k_gemm_nt(const double* A, int lda, const double* __restrict__ B, int ldb,
                 double* p0 = Cg + (size_t)(wn + 8 * j + 2 * (lane & 3)) * ldc + wm + 8 * i + (lane >> 2);
                 p0[0] = alpha * acc[i][j][0]; p0[ldc] = alpha * acc[i][j][1];
             }
+    } else if (PFC) {
+#pragma unroll
+        for (int i = 0; i < (PFC ? MI : 1); ++i)
+#pragma unroll
+            for (int j = 0; j < (PFC ? NJ : 1); ++j) {
+                double* p0 = Cg + (size_t)(wn + 8 * j + 2 * (lane & 3)) * ldc + wm + 8 * i + (lane >> 2);
+                p0[0] = beta * cpf[i][j][0] + alpha * acc[i][j][0];
+                p0[ldc] = beta * cpf[i][j][1] + alpha * acc[i][j][1];
+            }
     } else {
         constexpr int IC = MI > 4 ? 4 : MI;           // row tiles per read-modify-write batch
 #pragma unroll
@@ -156,7 +177,7 @@ k_gemm_nt(const double* A, int lda, const double* __restrict__ B, int ldb,
     }
 }
 
-template <int BM, int BN, int WTM, int WTN, int STAGES, int MINB>
+template <int BM, int BN, int WTM, int WTN, int STAGES, int MINB, bool PFC = false>
 struct GemmCfg {
     static constexpr int threads = (BM / WTM) * (BN / WTN) * 32;
     static constexpr int smem = STAGES * KS * (BM + 4 + BN + 4) * 8;
@@ -164,16 +185,17 @@ struct GemmCfg {
                        double* C, int ldc, int K, double alpha, double beta, int tri) {
         static bool done = false;
         if (!done) {
-            cudaFuncSetAttribute(k_gemm_nt<BM, BN, WTM, WTN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(k_gemm_nt<BM, BN, WTM, WTN, STAGES, MINB, PFC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             done = true;
         }
-        k_gemm_nt<BM, BN, WTM, WTN, STAGES, MINB><<<grid, threads, smem, st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, tri);
+        k_gemm_nt<BM, BN, WTM, WTN, STAGES, MINB, PFC><<<grid, threads, smem, st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, tri);
         count_launch();
     }
 };
 typedef GemmCfg<128, 64, 32, 32, 3, 2> GemmBig32;     // 8 warps
 typedef GemmCfg<128, 64, 64, 32, 3, 2> GemmBig64;     // 4 warps, 64 x 32 per warp
 typedef GemmCfg<64, 64, 32, 32, 3, 3> GemmSq64;       // 4 warps, three CTAs per SM
+typedef GemmCfg<64, 64, 32, 32, 3, 3, true> GemmSq64P; // + C tile prefetched into registers (read-modify-write only)
 typedef GemmCfg<128, 128, 64, 32, 3, 1> GemmSq128;    // 8 warps, 64 x 32 per warp, one CTA per SM
 typedef GemmCfg<64, 64, 32, 32, 3, 4> GemmSq64x4;     // as GemmSq64 with a 128-register cap, four CTAs per SM
 typedef GemmCfg<64, 64, 32, 32, 4, 3> GemmSq64s4;     // four stages
@@ -193,6 +215,9 @@ static void gemm_nt(const double* A, int lda, const double* B, int ldb, double* 
     case 2: GemmSq64::launch(tri ? dim3(mt * (2 * mt + 1)) : dim3(2 * mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
     case 4: GemmSq64x4::launch(tri ? dim3(mt * (2 * mt + 1)) : dim3(2 * mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
     case 5: GemmSq64s4::launch(tri ? dim3(mt * (2 * mt + 1)) : dim3(2 * mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
+    case 7: if (beta != 0.0) GemmSq64P::launch(tri ? dim3(mt * (2 * mt + 1)) : dim3(2 * mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f);
+            else GemmSq64::launch(tri ? dim3(mt * (2 * mt + 1)) : dim3(2 * mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f);
+            break;
     case 6: GemmR6432::launch(tri ? dim3(2 * mt * (2 * mt + 1)) : dim3(2 * mt, 4 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
     case 3: GemmSq128::launch(tri ? dim3(mt * (mt + 1) / 2) : dim3(mt, nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
     default: GemmBig32::launch(tri ? dim3(mt * (mt + 1)) : dim3(mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;

@@ -90,6 +90,33 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         if (nHandles++ == 0) mexLock();
         return;
     }
+    if (!strcmp(cmd, "forwintersect")) {
+        /* [OP,res]=dbat_mex('forwintersect',IO,EO,pxSize,IPval,im,op,pts,nK,nP)  (forwintersect.m:28-41) */
+        if (nrhs != 10) ERR("nrhs", "forwintersect(IO,EO,pxSize,IPval,im,op,pts,nK,nP)");
+        for (int a = 5; a <= 7; ++a) if (!mxIsInt64(prhs[a])) ERR("badType", "im, op and pts must be int64.");
+        dbat_fwi_desc f;
+        memset(&f, 0, sizeof(f));
+        f.NC = (int64_t)mxGetM(prhs[1]); f.nImg = (int64_t)mxGetN(prhs[1]);
+        f.nObs = (int64_t)mxGetN(prhs[4]); f.nPts = (int64_t)mxGetNumberOfElements(prhs[7]);
+        f.nK = (int64_t)mxGetScalar(prhs[8]); f.nP = (int64_t)mxGetScalar(prhs[9]);
+        if (mxGetM(prhs[2]) != 6 || (int64_t)mxGetN(prhs[2]) != f.nImg) ERR("badSize", "EO must be 6-by-nImg.");
+        if (mxGetNumberOfElements(prhs[3]) != (mwSize)(2 * f.nImg)) ERR("badSize", "pxSize must be 2-by-nImg.");
+        if ((int64_t)mxGetNumberOfElements(prhs[5]) != f.nObs || (int64_t)mxGetNumberOfElements(prhs[6]) != f.nObs)
+            ERR("badSize", "im and op must have one element per image point.");
+        f.IO = mxGetDoubles(prhs[1]); f.EO = mxGetDoubles(prhs[2]); f.pxSize = mxGetDoubles(prhs[3]);
+        f.IPval = mxGetDoubles(prhs[4]);
+        f.obs_img = (const int64_t *)mxGetData(prhs[5]); f.obs_op = (const int64_t *)mxGetData(prhs[6]);
+        f.pts = (const int64_t *)mxGetData(prhs[7]);
+        f.nOP = 0;
+        for (int64_t k = 0; k < f.nObs; ++k) if (f.obs_op[k] > f.nOP) f.nOP = f.obs_op[k];
+        for (int64_t k = 0; k < f.nPts; ++k) if (f.pts[k] > f.nOP) f.nOP = f.pts[k];
+        plhs[0] = mxCreateDoubleMatrix(3, (mwSize)f.nPts, mxREAL);
+        mxArray *res = mxCreateDoubleMatrix(1, (mwSize)f.nPts, mxREAL);
+        int rc = dbat_forwintersect(&f, mxGetDoubles(plhs[0]), mxGetDoubles(res), NULL);
+        if (rc != DBAT_OK) mexErrMsgIdAndTxt("DBAT:dbat_mex:forwintersect", "%s (code %d)", dbat_forwintersect_error(), rc);
+        if (nlhs > 1) plhs[1] = res; else mxDestroyArray(res);
+        return;
+    }
     if (nrhs < 2) ERR("nrhs", "Handle required.");
     dbat_handle *h = get_handle(prhs[1]);
     const mwSize n = (mwSize)dbat_num_unknowns(h), m = (mwSize)dbat_num_residuals(h);
