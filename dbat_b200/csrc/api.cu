@@ -388,11 +388,13 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     {   // grouped Schur index: estimated points sorted by (ray count, image list)
         std::vector<int> cand, big;
         cand.reserve(nOP);
+        int maxm = DBAT_GRP_MAXM;                 // DBAT_GRP_MAXM=k lowers the threshold (tests of the per-point path)
+        if (const char* e = getenv("DBAT_GRP_MAXM")) maxm = std::max(1, std::min(DBAT_GRP_MAXM, atoi(e)));
         for (int j = 0; j < nOP; ++j) {
             const int k = h->h_pt_start[j + 1] - h->h_pt_start[j];
             const int* oc = &h->h_op_col[3 * (size_t)j];
             if (k == 0 || (oc[0] < 0 && oc[1] < 0 && oc[2] < 0)) continue;
-            (k <= DBAT_GRP_MAXM ? cand : big).push_back(j);
+            (k <= maxm ? cand : big).push_back(j);
         }
         const int* ps = h->h_pt_start.data();
         const int* im = img_pm.data();

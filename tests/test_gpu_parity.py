@@ -109,7 +109,7 @@ def test_value_dependent_sparsity_camcal_start():
     P.close()
 
 
-@pytest.mark.parametrize('case', ['model3', 'priors+fixed', 'model5'])
+@pytest.mark.parametrize('case', ['model3', 'priors+fixed', 'model5', 'ragged'])
 @pytest.mark.parametrize('lam,jacobi', [(0.0, False), (1e3, False), (0.0, True)])
 def test_damped_step(case, lam, jacobi):
     """Schur + dense Cholesky step equals the reference's full sparse solve
@@ -331,6 +331,38 @@ print('DET-OK')
     env = dict(os.environ, DBAT_SCHUR='det')
     out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
     assert 'DET-OK' in out.stdout, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize('mode', ['maxm', 'perpoint'])
+def test_schur_fallback_paths_subprocess(mode):
+    """The grouped Schur kernel hands points with more than 21 rays to the per-point kernel.  No small
+    scene has such points, so the threshold is lowered (DBAT_GRP_MAXM=6: the 10-ray points of the test
+    scene take the per-point kernel, the ragged 3-ray ones stay grouped); DBAT_SCHUR=perpoint runs the
+    per-point kernel for everything.  Same step as the oracle in both."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, copy, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import dbat_b200
+from test_gpu_parity import scene, CASES
+from oracle.cameramodel import brown_euler_cam4
+from oracle.dbatstruct import buildweightmatrix, serialize
+for case in ('priors+fixed', 'ragged'):
+    s, _ = scene(**CASES[case])
+    x0 = serialize(s); W = buildweightmatrix(s)
+    P = dbat_b200.Problem(copy.deepcopy(s))
+    p1, st1 = P.normal_step(x0, 10.0, False)
+    ro, Jo = brown_euler_cam4(x0, s, True)
+    Jw = Jo.multiply(np.sqrt(W)[:, None]).tocsc(); rw = ro * np.sqrt(W)
+    N = (Jw.T @ Jw).toarray()
+    po = np.linalg.solve(N + 10.0 * np.eye(N.shape[0]), -(Jw.T @ rw))
+    assert np.abs(p1 - po).max() / np.abs(po).max() < 5e-9, case
+print('FALLBACK-OK')
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, DBAT_GRP_MAXM='6') if mode == 'maxm' else dict(os.environ, DBAT_SCHUR='perpoint')
+    out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
+    assert 'FALLBACK-OK' in out.stdout, out.stdout + out.stderr
 
 
 PRAGUE = os.path.join(os.path.dirname(GOLD), 'prague2016cam')
