@@ -422,14 +422,19 @@ __global__ void __launch_bounds__(256) k_schur_atomic(DevProblem P, double lambd
 
 // ---------------------------------------------------------------------------------------------
 // Grouped Schur update (default).  Points are sorted by their image list at create; a group is a
-// run of points seen by exactly the same m images.  One CTA per group: thread (slot, task) with
-//   task <  m(m+1)/2 : the 6x6 block  Y_o W_o2'  of the image pair (o >= o2),
-//   task >= m(m+1)/2 : 5 of the 15 columns  Y_o [Wsh | g]  of image o  (shared IO columns and rhs)
-// sums its block over the points slot, slot + nslot, ... of the group in registers (operands come
-// straight from L1/L2: W_o is read by the ~m tasks of the same point).  The slots are then added
-// in shared memory and flushed with one atomic per entry of S, 6 consecutive rows per 6 lanes.
-// With the 10-nearest-camera visibility of the synthetic blocks a group holds ~7 points, i.e. ~7x
-// fewer L2 atomics than one flush per point (the kernel this replaced was bound by exactly those).
+// run of ng <= 16 points seen by exactly the same m images.  For one group the whole update is ONE
+// small dense contraction over k = (point, coordinate), K = 3 ng:
+//     What (6m x K)   rows: the EO x OP blocks W_o of all points side by side
+//     Wsh  (15 x K)   rows: the shared IO x OP slots and the gradient g_j
+//     Yhat = What (V + lambda I)^-1 per point,   Ysh likewise
+//     S[cams, cams] -= Yhat What'    S[shared, cams] -= Yhat Wsh'    rhs += Yhat g    shared x shared += Ysh Wsh'
+// One CTA per group stages What / Wsh with coalesced loads, forms Yhat once per row, and runs the
+// product on the FP64 tensor pipe (DMMA m8n8k4, 8x8 output tiles of the lower triangle dealt to the
+// warps).  Every C fragment goes to S with one `red.global.add` per entry (8 consecutive rows per
+// 8 lanes); the shared x shared tiles stay in registers across all groups of the CTA.
+// With the 10-nearest-camera visibility of the synthetic blocks a group holds ~5-7 points: that many
+// times fewer atomics than one flush per point (which bound the per-point kernel this replaced), and
+// ~3x fewer instructions and shared-memory bytes than the same sums with scalar FP64 FMAs.
 // ---------------------------------------------------------------------------------------------
 __global__ void k_point_vinv(DevProblem P, double lambda) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -440,9 +445,9 @@ __global__ void k_point_vinv(DevProblem P, double lambda) {
     o[0] = make_double2(Vi[0], Vi[1]); o[1] = make_double2(Vi[2], Vi[3]); o[2] = make_double2(Vi[4], Vi[5]);
 }
 
-#define GRP_TH 192
+#define GRP_TH 256
 #define GRP_CAP 16            // max points per group (create-time cap)
-#define GRP_YH 10             // doubles per half record of Y (9 + 1: keeps 16-byte alignment)
+#define GRP_LDK 52            // row stride of What / Yhat / Wsh: 3*GRP_CAP = 48 columns + 4 (= 4 mod 16: conflict-free fragments)
 struct GrpHeader {            // per-group data staged in shared memory (double-buffered)
     int m, ng;
     int j[GRP_CAP], ob[GRP_CAP];
@@ -481,20 +486,25 @@ __device__ __forceinline__ void grp_store(GrpHeader& h, int t, const GrpPrefetch
     if (t >= 64 && t - 64 < 6 * f.m) h.eoc[t - 64] = f.eoc;
 }
 
-// dynamic shared memory: red[ntask*18] | Wsm[GRP_CAP * m * 18] | Ysm[GRP_CAP * m * 2 * GRP_YH]
+__device__ __forceinline__ void dmma_s(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// dynamic shared memory (RW = 6m rounded up to 8, for the largest m of the problem):
+//   What[RW][LDK] | Yhat[RW + 16][LDK] (rows RW.. : Ysh) | Wsh[16][LDK]
 __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double* __restrict__ shAcc) {
     extern __shared__ __align__(16) double dsm[];
     __shared__ GrpHeader s_hdr[2];
-    __shared__ unsigned char s_po[DBAT_GRP_MAXM * (DBAT_GRP_MAXM + 1) / 2], s_po2[DBAT_GRP_MAXM * (DBAT_GRP_MAXM + 1) / 2];
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
     const size_t ld = P.ldS;
-    constexpr int NE = DBAT_NSLOT * (DBAT_NSLOT + 1);
-    const int mmax = P.grpMaxRays;
-    double* red = dsm;
-    double* Wsm = red + (mmax * (mmax + 1) + 6 * mmax) * 18;
-    double* Ysm = Wsm + GRP_CAP * mmax * 18;
-    double accSh[2] = {0.0, 0.0};                // entries t and t + GRP_TH of the shared x shared table
-    int mPrev = -1, buf = 0;
+    const int RWmax = (6 * P.grpMaxRays + 7) & ~7;
+    double* What = dsm;
+    double* Yhat = What + RWmax * GRP_LDK;
+    double* Wsh = Yhat + (RWmax + 16) * GRP_LDK;
+    for (int i = t; i < (2 * RWmax + 32) * GRP_LDK; i += GRP_TH) dsm[i] = 0.0;     // padding rows / columns stay zero
+    double accSh[2] = {0.0, 0.0};                // warps 0..3: one 8x8 tile of the shared x shared table each
+    int buf = 0;
     {
         GrpPrefetch f;
         grp_prefetch(P, blockIdx.x, t, f);
@@ -506,130 +516,111 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
         GrpPrefetch nxt;
         grp_prefetch(P, grp + gridDim.x, t, nxt);            // in flight during this group's work
         const int m = H.m, ng = H.ng;
-        const int npair = m * (m + 1) / 2, ntask = 2 * npair + 6 * m;
-        const int recs = m * 18;                             // doubles of W per point (contiguous in global)
-        // stage W of every point of the group (coalesced 16-byte loads)
-        for (int idx = t; idx < ng * (recs / 2); idx += GRP_TH) {
-            const int gi = idx / (recs / 2), off = idx - gi * (recs / 2);
-            reinterpret_cast<double2*>(Wsm + gi * recs)[off] =
-                reinterpret_cast<const double2*>(P.W + (size_t)H.ob[gi] * DBAT_W_STRIDE)[off];
+        const int R = 6 * m, RT = (R + 7) >> 3;              // camera rows, 8-row tiles
+        const int K = 3 * ng, Kp = (K + 3) & ~3;
+        // ---- stage What (coalesced: 18 m contiguous doubles per point) and Wsh
+        for (int idx = t; idx < ng * 3 * R; idx += GRP_TH) {
+            const int gi = idx / (3 * R), e = idx - gi * 3 * R;            // e = 3 r + c
+            const int r = e / 3, c = e - 3 * r;
+            What[r * GRP_LDK + 3 * gi + c] = P.W[(size_t)H.ob[gi] * DBAT_W_STRIDE + e];
         }
-        if (m != mPrev) {                         // pair table (same for all groups with this m)
-            for (int pr = t; pr < npair; pr += GRP_TH) {
-                int o = (int)((sqrtf(8.0f * pr + 1.0f) - 1.0f) * 0.5f);
-                while ((o + 1) * (o + 2) / 2 <= pr) ++o;
-                while (o * (o + 1) / 2 > pr) --o;
-                s_po[pr] = (unsigned char)o; s_po2[pr] = (unsigned char)(pr - o * (o + 1) / 2);
+        for (int idx = t; idx < ng * 45; idx += GRP_TH) {
+            const int gi = idx / 45, e = idx - gi * 45, sidx = e / 3, c = e - 3 * sidx;
+            const double* rec = P.pt + (size_t)H.j[gi] * DBAT_PT_STRIDE;
+            Wsh[sidx * GRP_LDK + 3 * gi + c] = sidx < DBAT_NSLOT ? rec[DBAT_PT_WSH + 3 * sidx + c] : rec[6 + c];
+        }
+        if (Kp > K) {                                        // k padding may hold a previous group's data
+            for (int idx = t; idx < (2 * RT * 8 + 32) * (Kp - K); idx += GRP_TH) {
+                const int row = idx / (Kp - K), k = K + idx - row * (Kp - K);
+                // rows: What [0, 8RT), Yhat [0, 8RT) and its 16 shared rows, Wsh 16 rows
+                double* base = row < 8 * RT ? What + row * GRP_LDK
+                             : row < 16 * RT ? Yhat + (row - 8 * RT) * GRP_LDK
+                             : row < 16 * RT + 16 ? Yhat + (RWmax + row - 16 * RT) * GRP_LDK
+                             : Wsh + (row - 16 * RT - 16) * GRP_LDK;
+                base[k] = 0.0;
             }
-            mPrev = m;
         }
         __syncthreads();
-        // Y = W (V + lambda I)^-1, one row (3 doubles) per thread
-        for (int idx = t; idx < ng * m * 6; idx += GRP_TH) {
-            const int gi = idx / (m * 6), r = idx - gi * (m * 6);       // r = 6 o + a
+        // ---- Yhat = What V^-1 (camera rows), Ysh = Wsh V^-1: one (row, point) per thread
+        for (int idx = t; idx < ng * (R + 15); idx += GRP_TH) {
+            const int gi = idx / (R + 15), r = idx - gi * (R + 15);
             const double* sv = H.vi + 6 * gi;
             const double Vi[6] = {sv[0], sv[1], sv[2], sv[3], sv[4], sv[5]};
-            const double* w = Wsm + gi * recs + 3 * r;
+            const double* w = (r < R ? What + r * GRP_LDK : Wsh + (r - R) * GRP_LDK) + 3 * gi;
             const double w3[3] = {w[0], w[1], w[2]};
             double y[3];
             symv3(Vi, w3, y);
-            const int o = r / 6, a = r - 6 * o;
-            double* yo = Ysm + ((gi * m + o) * 2 + a / 3) * GRP_YH + 3 * (a % 3);
+            double* yo = (r < R ? Yhat + r * GRP_LDK : Yhat + (RWmax + r - R) * GRP_LDK) + 3 * gi;
             yo[0] = y[0]; yo[1] = y[1]; yo[2] = y[2];
         }
+        grp_store(s_hdr[buf ^ 1], t, nxt);
         __syncthreads();
-        for (int task = t; task < ntask; task += GRP_TH) {
-            const bool isPair = task < 2 * npair;
-            int o, o2 = 0, part = 0, ah;
-            if (isPair) { const int pr = task >> 1; ah = task & 1; o = s_po[pr]; o2 = s_po2[pr]; }
-            else { const int q = task - 2 * npair; o = q / 6; const int r = q - 6 * o; part = r >> 1; ah = r & 1; }
-            double acc[18];
+        // ---- tiles: pair tiles (ti >= tj) of Yhat What', then RT x 2 tiles of Yhat Wsh'
+        const int nPair = RT * (RT + 1) / 2, nTile = nPair + 2 * RT;
+        for (int tile = warp; tile < nTile; tile += GRP_TH / 32) {
+            int ti, tj; const double* Bm;
+            if (tile < nPair) {
+                ti = (int)((sqrtf(8.0f * tile + 1.0f) - 1.0f) * 0.5f);
+                while ((ti + 1) * (ti + 2) / 2 <= tile) ++ti;
+                while (ti * (ti + 1) / 2 > tile) --ti;
+                tj = tile - ti * (ti + 1) / 2;
+                Bm = What;
+            } else { ti = (tile - nPair) >> 1; tj = (tile - nPair) & 1; Bm = Wsh; }
+            const double* pa = Yhat + (8 * ti + fr) * GRP_LDK + fk;
+            const double* pb = Bm + (8 * tj + fr) * GRP_LDK + fk;
+            double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+            for (int k0 = 0; k0 < Kp; k0 += 8) {             // two accumulator pairs: shorter dependent chains
+                dmma_s(c0, c1, pa[k0], pb[k0]);
+                if (k0 + 4 < Kp) dmma_s(d0, d1, pa[k0 + 4], pb[k0 + 4]);
+            }
+            c0 += d0; c1 += d1;
+            const int r = 8 * ti + fr;
+            if (r < R) {
+                const int row = H.eoc[r];
+                if (row >= 0) {
+                    if (tile < nPair) {
 #pragma unroll
-            for (int k = 0; k < 18; ++k) acc[k] = 0.0;
-            for (int gi = 0; gi < ng; ++gi) {
-                const double2* yp = reinterpret_cast<const double2*>(Ysm + ((gi * m + o) * 2 + ah) * GRP_YH);
-                double Y[10];
+                        for (int e = 0; e < 2; ++e) {
+                            const int c = 8 * tj + 2 * fk + e;
+                            if (c < R) {
+                                const int col = H.eoc[c];
+                                if (col >= 0 && col <= row) atomicAdd(&P.S[(size_t)col * ld + row], -(e ? c1 : c0));
+                            }
+                        }
+                    } else {
 #pragma unroll
-                for (int k = 0; k < 5; ++k) { const double2 v = yp[k]; Y[2 * k] = v.x; Y[2 * k + 1] = v.y; }
-                if (isPair) {
-                    const double2* Wb = reinterpret_cast<const double2*>(Wsm + gi * recs + o2 * 18);
-                    double w[18];
-#pragma unroll
-                    for (int k = 0; k < 9; ++k) { const double2 v = Wb[k]; w[2 * k] = v.x; w[2 * k + 1] = v.y; }
-#pragma unroll
-                    for (int b = 0; b < 6; ++b)
-#pragma unroll
-                        for (int a = 0; a < 3; ++a)
-                            acc[3 * b + a] += Y[3 * a] * w[3 * b] + Y[3 * a + 1] * w[3 * b + 1] + Y[3 * a + 2] * w[3 * b + 2];
-                } else {
-                    const double* rec = P.pt + (size_t)H.j[gi] * DBAT_PT_STRIDE;
-#pragma unroll
-                    for (int si = 0; si < 6; ++si) {
-                        const int sidx = 6 * part + si;
-                        if (sidx <= DBAT_NSLOT) {
-                            const double* vs = sidx < DBAT_NSLOT ? rec + DBAT_PT_WSH + 3 * sidx : rec + 6;
-                            const double v0 = vs[0], v1 = vs[1], v2 = vs[2];
-#pragma unroll
-                            for (int a = 0; a < 3; ++a) acc[3 * si + a] += Y[3 * a] * v0 + Y[3 * a + 1] * v1 + Y[3 * a + 2] * v2;
+                        for (int e = 0; e < 2; ++e) {
+                            const int sidx = 8 * tj + 2 * fk + e;
+                            if (sidx < DBAT_NSLOT) {
+                                const int col = P.sh_col[sidx];
+                                if (col >= 0) atomicAdd(&P.S[(size_t)col * ld + row], -(e ? c1 : c0));
+                            } else if (sidx == DBAT_NSLOT) {
+                                atomicAdd(&P.rhs[row], e ? c1 : c0);
+                            }
                         }
                     }
                 }
             }
-            double* r = red + task * 18;
-#pragma unroll
-            for (int k = 0; k < 18; ++k) r[k] = acc[k];
         }
-        // shared x shared (+ rhs): entries of the NSLOT x (NSLOT+1) table, summed over the group
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int e = t + h * GRP_TH;
-            const int shA = e / (DBAT_NSLOT + 1), shB = e - shA * (DBAT_NSLOT + 1);
-            if (e < NE && (shB == DBAT_NSLOT || shB <= shA)) {
-#pragma unroll 4
-                for (int gi = 0; gi < ng; ++gi) {
-                    const double* rec = P.pt + (size_t)H.j[gi] * DBAT_PT_STRIDE;
-                    const double* sv = H.vi + 6 * gi;
-                    const double Vi[6] = {sv[0], sv[1], sv[2], sv[3], sv[4], sv[5]};
-                    const double* wa = rec + DBAT_PT_WSH + 3 * shA;
-                    const double* wb = shB < DBAT_NSLOT ? rec + DBAT_PT_WSH + 3 * shB : rec + 6;
-                    const double w3[3] = {wb[0], wb[1], wb[2]};
-                    double y[3];
-                    symv3(Vi, w3, y);
-                    accSh[h] += wa[0] * y[0] + wa[1] * y[1] + wa[2] * y[2];
-                }
-            }
-        }
-        grp_store(s_hdr[buf ^ 1], t, nxt);
-        __syncthreads();
-        // flush: threads 0..179 keep a fixed position inside the 6x6 block (36 | 180) resp. inside the
-        // 15x6 shared-column strip (90 | 180); consecutive lanes -> consecutive rows a of one column
-        if (t < 180) {
-            const int k = t % 36, b = k / 6, a = k - 6 * b;
-            const int srcoff = (a / 3) * 18 + 3 * b + a % 3;
-            for (int pr = t / 36; pr < npair; pr += 5) {
-                const double v = red[2 * pr * 18 + srcoff];
-                const int row = H.eoc[6 * s_po[pr] + a];
-                const int col = H.eoc[6 * s_po2[pr] + b];
-                if (row >= 0 && col >= 0 && col <= row) atomicAdd(&P.S[(size_t)col * ld + row], -v);
-            }
-            const int k2 = t % 90, sidx = k2 / 6, a2 = k2 - 6 * sidx;
-            const int srcoff2 = (2 * (sidx / 6) + a2 / 3) * 18 + 3 * (sidx % 6) + a2 % 3;
-            const int colsh = sidx < DBAT_NSLOT ? P.sh_col[sidx] : -2;
-            for (int oo = t / 90; oo < m; oo += 2) {
-                const double v = red[(2 * npair + 6 * oo) * 18 + srcoff2];
-                const int row = H.eoc[6 * oo + a2];
-                if (row >= 0) {
-                    if (colsh >= 0) atomicAdd(&P.S[(size_t)colsh * ld + row], -v);
-                    else if (colsh == -2) atomicAdd(&P.rhs[row], v);
-                }
-            }
+        // ---- shared x shared (+ rhs column): Ysh Wsh', 2 x 2 tiles kept in registers by warps 0..3
+        if (warp < 4) {
+            const int ta = warp >> 1, tb = warp & 1;
+            const double* pa = Yhat + (RWmax + 8 * ta + fr) * GRP_LDK + fk;
+            const double* pb = Wsh + (8 * tb + fr) * GRP_LDK + fk;
+            for (int k0 = 0; k0 < Kp; k0 += 4) dmma_s(accSh[0], accSh[1], pa[k0], pb[k0]);
         }
         __syncthreads();
     }
+    if (warp < 4) {
+        const int a = 8 * (warp >> 1) + fr;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-        const int e = t + h * GRP_TH;
-        if (e < NE && accSh[h] != 0.0) atomicAdd(&shAcc[e], accSh[h]);
+        for (int e = 0; e < 2; ++e) {
+            const int b = 8 * (warp & 1) + 2 * fk + e;
+            if (a < DBAT_NSLOT && (b == DBAT_NSLOT || b <= a) && b <= DBAT_NSLOT) {
+                const double v = e ? accSh[1] : accSh[0];
+                if (v != 0.0) atomicAdd(&shAcc[a * (DBAT_NSLOT + 1) + b], v);
+            }
+        }
     }
 }
 __global__ void k_schur_sh_apply(DevProblem P, const double* __restrict__ shAcc) {
@@ -671,7 +662,7 @@ void launch_schur(const DevProblem& P, double lambda, cudaStream_t st) {
             k_point_vinv<<<(P.nOP + 255) / 256, 256, 0, st>>>(P, lambda);
             if (P.nGrp > 0) {
                 static bool attr = false;
-                auto smem_for = [](int mm) { return ((mm * (mm + 1) + 6 * mm) * 18 + GRP_CAP * mm * 18 + GRP_CAP * mm * 2 * GRP_YH) * 8; };
+                auto smem_for = [](int mm) { return (2 * ((6 * mm + 7) & ~7) + 32) * GRP_LDK * 8; };
                 if (!attr) { cudaFuncSetAttribute(k_schur_group, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(DBAT_GRP_MAXM)); attr = true; }
                 k_schur_group<<<std::min(P.nGrp, 148 * 24), GRP_TH, smem_for(P.grpMaxRays), st>>>(P, g_shAcc);
                 count_launch();
