@@ -4,20 +4,16 @@
 // code/bundle/lsa/levenberg_marquardt.m:119, gauss_newton_armijo.m:172,
 // code/bundle/bundle_cov.m:87.
 //
-// Right-looking, block size 128:  for k: L_kk = chol(A_kk) (+ inv(L_kk)) ;
+// Right-looking, block size 128:  for k: L_kk = chol(A_kk) (+ inv(L_kk))  (k_potrf128) ;
 //   A_ik <- A_ik inv(L_kk)'  (GEMM) ;  A_ij -= L_ik L_jk'  for i>=j>k (GEMM, lower tiles only).
-// The two GEMM shapes share one 128x128x16 double-buffered cp.async kernel ("NT": both
-// operands column-major, C = beta*C + alpha*A*B').
+// All GEMMs are instances of one templated cp.async + DMMA kernel ("NT": both operands
+// column-major, C = beta*C + alpha*A*B').
 #include <cstdio>
 #include <cstdlib>
 #include "launch.h"
 
 #define NB 128
 #define KS 16                 // k-slice per pipeline stage
-#ifndef SLD
-#define SLD 132               // smem row stride (doubles) = 4 mod 16: the 8-byte fragment loads of a half-warp
-#endif                        // (addresses (lane&3)*SLD + lane/4) fall into 16 distinct 8-byte banks
-#define GEMM_STAGES 3
 
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -43,7 +39,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 //              the epilogue)
 // tile list: if tri != 0 the 1-D grid enumerates the tiles (ti, tj) with BN*tj <= BM*ti + BM-1 of
 // the lower triangle (BM = 2 BN only); otherwise blockIdx.x = ti, blockIdx.y = tj.
-template <int BM, int BN, int WTM, int WTN, int STAGES, int MINB, bool PFC = false>
+template <int BM, int BN, int WTM, int WTN, int STAGES, int MINB>
 __global__ void __launch_bounds__((BM / WTM) * (BN / WTN) * 32, MINB)
 k_gemm_nt(const double* A, int lda, const double* __restrict__ B, int ldb,
           double* C, int ldc, int K, double alpha, double beta, int tri) {
@@ -100,23 +96,11 @@ k_gemm_nt(const double* A, int lda, const double* __restrict__ B, int ldb,
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) { if (s < nk) load_stage(s, s); cp_async_commit(); }
-    // PFC: the C tile of a read-modify-write update is fetched into registers three k-slices before
-    // the end of the main loop, so that its DRAM latency is covered by DMMA work
-    double cpf[PFC ? MI : 1][PFC ? NJ : 1][2];
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
         if (kt + STAGES - 1 < nk) load_stage((kt + STAGES - 1) % STAGES, kt + STAGES - 1);
         cp_async_commit();
-        if (PFC && kt == (nk > 3 ? nk - 3 : 0)) {
-#pragma unroll
-            for (int i = 0; i < (PFC ? MI : 1); ++i)
-#pragma unroll
-                for (int j = 0; j < (PFC ? NJ : 1); ++j) {
-                    const double* p0 = Cg + (size_t)(wn + 8 * j + 2 * (lane & 3)) * ldc + wm + 8 * i + (lane >> 2);
-                    cpf[i][j][0] = p0[0]; cpf[i][j][1] = p0[ldc];
-                }
-        }
         const double* As = sm + (size_t)(kt % STAGES) * STAGE;
         const double* Bs = As + KS * LA;
 #pragma unroll
@@ -144,15 +128,6 @@ k_gemm_nt(const double* A, int lda, const double* __restrict__ B, int ldb,
                 double* p0 = Cg + (size_t)(wn + 8 * j + 2 * (lane & 3)) * ldc + wm + 8 * i + (lane >> 2);
                 p0[0] = alpha * acc[i][j][0]; p0[ldc] = alpha * acc[i][j][1];
             }
-    } else if (PFC) {
-#pragma unroll
-        for (int i = 0; i < (PFC ? MI : 1); ++i)
-#pragma unroll
-            for (int j = 0; j < (PFC ? NJ : 1); ++j) {
-                double* p0 = Cg + (size_t)(wn + 8 * j + 2 * (lane & 3)) * ldc + wm + 8 * i + (lane >> 2);
-                p0[0] = beta * cpf[i][j][0] + alpha * acc[i][j][0];
-                p0[ldc] = beta * cpf[i][j][1] + alpha * acc[i][j][1];
-            }
     } else {
         constexpr int IC = MI > 4 ? 4 : MI;           // row tiles per read-modify-write batch
 #pragma unroll
@@ -177,7 +152,7 @@ k_gemm_nt(const double* A, int lda, const double* __restrict__ B, int ldb,
     }
 }
 
-template <int BM, int BN, int WTM, int WTN, int STAGES, int MINB, bool PFC = false>
+template <int BM, int BN, int WTM, int WTN, int STAGES, int MINB>
 struct GemmCfg {
     static constexpr int threads = (BM / WTM) * (BN / WTN) * 32;
     static constexpr int smem = STAGES * KS * (BM + 4 + BN + 4) * 8;
@@ -185,21 +160,17 @@ struct GemmCfg {
                        double* C, int ldc, int K, double alpha, double beta, int tri) {
         static bool done = false;
         if (!done) {
-            cudaFuncSetAttribute(k_gemm_nt<BM, BN, WTM, WTN, STAGES, MINB, PFC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            cudaFuncSetAttribute(k_gemm_nt<BM, BN, WTM, WTN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             done = true;
         }
-        k_gemm_nt<BM, BN, WTM, WTN, STAGES, MINB, PFC><<<grid, threads, smem, st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, tri);
+        k_gemm_nt<BM, BN, WTM, WTN, STAGES, MINB><<<grid, threads, smem, st>>>(A, lda, B, ldb, C, ldc, K, alpha, beta, tri);
         count_launch();
     }
 };
-typedef GemmCfg<128, 64, 32, 32, 3, 2> GemmBig32;     // 8 warps
-typedef GemmCfg<128, 64, 64, 32, 3, 2> GemmBig64;     // 4 warps, 64 x 32 per warp
-typedef GemmCfg<64, 64, 32, 32, 3, 3> GemmSq64;       // 4 warps, three CTAs per SM
-typedef GemmCfg<64, 64, 32, 32, 3, 3, true> GemmSq64P; // + C tile prefetched into registers (read-modify-write only)
-typedef GemmCfg<128, 128, 64, 32, 3, 1> GemmSq128;    // 8 warps, 64 x 32 per warp, one CTA per SM
-typedef GemmCfg<64, 64, 32, 32, 3, 4> GemmSq64x4;     // as GemmSq64 with a 128-register cap, four CTAs per SM
-typedef GemmCfg<64, 64, 32, 32, 4, 3> GemmSq64s4;     // four stages
-typedef GemmCfg<64, 32, 32, 32, 3, 6> GemmR6432;      // 2 warps
+typedef GemmCfg<128, 64, 32, 32, 3, 2> GemmBig32;     // 8 warps, two CTAs per SM (DBAT_GEMM_CFG=0)
+typedef GemmCfg<64, 64, 32, 32, 3, 3> GemmSq64;       // 4 warps, three CTAs per SM (default)
+// Other shapes were timed and dropped (profiles/README.md): 128x64 with 64x32 warp tiles, 128x128,
+// 64x64 at four CTAs per SM or four stages, 64x32, and 64x64 with the C tile prefetched into registers.
 typedef GemmCfg<64, 64, 32, 32, 8, 1> GemmCol;
 typedef GemmCfg<32, 128, 32, 32, 8, 1> GemmPanel;
 
@@ -210,234 +181,11 @@ static void gemm_nt(const double* A, int lda, const double* B, int ldb, double* 
     if (cfg < 0) { const char* e = getenv("DBAT_GEMM_CFG"); cfg = e ? atoi(e) : 2; }
     if (mt <= 0 || nt <= 0) return;
     const int f = tri ? 1 : 0;
-    switch (cfg) {
-    case 1: GemmBig64::launch(tri ? dim3(mt * (mt + 1)) : dim3(mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
-    case 2: GemmSq64::launch(tri ? dim3(mt * (2 * mt + 1)) : dim3(2 * mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
-    case 4: GemmSq64x4::launch(tri ? dim3(mt * (2 * mt + 1)) : dim3(2 * mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
-    case 5: GemmSq64s4::launch(tri ? dim3(mt * (2 * mt + 1)) : dim3(2 * mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
-    case 7: if (beta != 0.0) GemmSq64P::launch(tri ? dim3(mt * (2 * mt + 1)) : dim3(2 * mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f);
-            else GemmSq64::launch(tri ? dim3(mt * (2 * mt + 1)) : dim3(2 * mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f);
-            break;
-    case 6: GemmR6432::launch(tri ? dim3(2 * mt * (2 * mt + 1)) : dim3(2 * mt, 4 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
-    case 3: GemmSq128::launch(tri ? dim3(mt * (mt + 1) / 2) : dim3(mt, nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
-    default: GemmBig32::launch(tri ? dim3(mt * (mt + 1)) : dim3(mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f); break;
-    }
+    if (cfg == 0) GemmBig32::launch(tri ? dim3(mt * (mt + 1)) : dim3(mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f);
+    else GemmSq64::launch(tri ? dim3(mt * (2 * mt + 1)) : dim3(2 * mt, 2 * nt), st, A, lda, B, ldb, C, ldc, K, alpha, beta, f);
 }
 
-// Cholesky of one 128x128 diagonal block in shared memory + inverse of its factor.
-// 256 threads, left-looking over 16-column panels:  (1) panel -= L(:,0:c0) L(panel,0:c0)'
-// (2) warp 0 factors the 16x16 diagonal block  (3) one thread per row solves the rows below.
-// inv(L) is then built block-wise (16x16 blocks, all blocks of one sub-diagonal in parallel)
-// into the strictly upper triangle of the same tile (transposed), its diagonal in dg[].
-#define PLD 129
-#define PB 16
-__global__ void __launch_bounds__(256, 1)
-k_potrf128_v1(double* __restrict__ A, int lda, double* __restrict__ invL, int blk, int nvalid,
-              int* __restrict__ info, double* __restrict__ minmax) {
-    extern __shared__ __align__(16) double sm[];
-    double* As = sm;                    // [128][PLD] row-major
-    double* dg = sm + NB * PLD;         // [128] diagonal of inv(L)
-    double* rd = dg + NB;               // [16] reciprocal pivots of the current diagonal block (+ pad to 16*17)
-    double* Tb = rd + PB * 17;          // [7][16][17] scratch for the inverse
-    double* colb = Tb + 7 * PB * 17;    // [2][16] column exchange buffer of the diagonal-block factorisation
-    double* XdAll = colb + 2 * PB;      // [8][16][17] inverses of all diagonal blocks, zero above the diagonal
-    __shared__ int s_bad;
-    __shared__ double s_min, s_max;
-    const int t = threadIdx.x;
-#ifdef POTRF_PROFILE
-    long long tk[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tl = clock64();
-#define TICK(k) { __syncthreads(); const long long n_ = clock64(); tk[k] += n_ - tl; tl = n_; }
-#else
-#define TICK(k)
-#endif
-    {
-        const int i = t & 127, h = t >> 7;
-        const double* src = A + i;
-#pragma unroll 16
-        for (int c = h * 64; c < h * 64 + 64; ++c) As[i * PLD + c] = (c <= i) ? src[(size_t)c * lda] : 0.0;
-    }
-    if (t == 0) { s_bad = 0; s_min = 1e300; s_max = 0.0; }
-    __syncthreads();
-    TICK(0)
-    for (int c0 = 0; c0 < NB; c0 += PB) {
-        if (c0 > 0) {                                   // (1) left-looking update of the panel (DMMA)
-            // P(i, j) -= sum_k L(i,k) L(j,k), i in [c0,128), j in [c0,c0+16), k < c0.
-            // warp w owns the 8-row tiles c0/8 + w, + w+8 ; two 8-column tiles each.
-            const int lane = t & 31, warp = t >> 5;
-            const int fr = lane >> 2, fk = lane & 3;
-            const double* Bp0 = As + (c0 + fr) * PLD + fk;          // B(k,n) = L(c0+n, k)
-            const double* Bp1 = Bp0 + 8 * PLD;
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int i0 = c0 + 8 * (warp + 8 * half);
-                if (i0 < NB) {
-                    double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;     // two independent accumulator sets:
-                    double e00 = 0.0, e01 = 0.0, e10 = 0.0, e11 = 0.0;     // halves the dependent DMMA chain
-                    const double* Ap = As + (i0 + fr) * PLD + fk;
-#pragma unroll 2
-                    for (int k0 = 0; k0 < c0; k0 += 8) {
-                        const double a = Ap[k0], b0 = Bp0[k0], b1 = Bp1[k0];
-                        const double a2 = Ap[k0 + 4], b02 = Bp0[k0 + 4], b12 = Bp1[k0 + 4];
-                        dmma(c00, c01, a, b0);
-                        dmma(c10, c11, a, b1);
-                        dmma(e00, e01, a2, b02);
-                        dmma(e10, e11, a2, b12);
-                    }
-                    c00 += e00; c01 += e01; c10 += e10; c11 += e11;
-                    double* Cp = As + (i0 + fr) * PLD + c0 + 2 * fk;
-                    Cp[0] -= c00; Cp[1] -= c01; Cp[8] -= c10; Cp[9] -= c11;
-                }
-            }
-        }
-        __syncthreads();
-        TICK(1)
-        if (t < 32) {                                   // (2) 16x16 diagonal block, lane = row
-            // Row r lives in registers; the finished column j travels through a small double-
-            // buffered shared array.  The next pivot is taken from lane j+1's own registers
-            // (cand), so the pivot chain does not wait for the shared-memory exchange.
-            const int r = t & 15;
-            double row[PB];
-#pragma unroll
-            for (int c = 0; c < PB; ++c) row[c] = As[(c0 + r) * PLD + c0 + c];
-            double d = __shfl_sync(0xffffffffu, row[0], 0);
-#pragma unroll
-            for (int j = 0; j < PB; ++j) {
-                const double inv = rsqrt(d);
-                const double l = d * inv;
-                if (t == 0) {
-                    if (!(d > 0.0)) s_bad = 1;
-                    if (blk * NB + c0 + j < nvalid) { s_min = fmin(s_min, l); s_max = fmax(s_max, l); }
-                    rd[j] = inv;
-                }
-                row[j] = (r == j) ? l : (r > j ? row[j] * inv : 0.0);
-                if (j + 1 < PB) {
-                    const double cand = row[j + 1] - row[j] * row[j];      // exact for lane j+1
-                    d = __shfl_sync(0xffffffffu, cand, j + 1);
-                }
-                double* cb = colb + (j & 1) * PB;
-                if (t < PB) cb[r] = row[j];
-                __syncwarp();
-#pragma unroll
-                for (int c = j + 1; c < PB; ++c) {
-                    row[c] -= row[j] * cb[c];           // entries above the diagonal are scratch
-                }
-            }
-            if (t < PB) {
-#pragma unroll
-                for (int cc = 0; cc < PB; ++cc) if (cc <= r) As[(c0 + r) * PLD + c0 + cc] = row[cc];
-            }
-        }
-        __syncthreads();
-        TICK(2)
-        if (t < NB) {
-            if (t >= c0 + PB) {                         // (3) rows below: solve x L_dd' = a (right-looking)
-                double* rowp = As + t * PLD + c0;
-                double a[PB];
-#pragma unroll
-                for (int k = 0; k < PB; ++k) a[k] = rowp[k];
-#pragma unroll
-                for (int j = 0; j < PB; ++j) {
-                    a[j] *= rd[j];
-#pragma unroll
-                    for (int k = j + 1; k < PB; ++k) a[k] -= a[j] * As[(c0 + k) * PLD + c0 + j];
-                }
-#pragma unroll
-                for (int j = 0; j < PB; ++j) rowp[j] = a[j];
-            }
-        } else if (t < NB + 32) {
-            // concurrently (warp 4): inverse of the diagonal block for the X phase; lane c builds
-            // column c of X = L_dd^-1 (rows of L are broadcast reads)
-            const int c = t & 15;
-            double x[PB];
-#pragma unroll
-            for (int rr = 0; rr < PB; ++rr) {
-                double s0 = (rr == c) ? 1.0 : 0.0, s1 = 0.0;
-                const double* Lr = As + (c0 + rr) * PLD + c0;
-#pragma unroll
-                for (int k = 0; k < rr; ++k) {
-                    if (k & 1) s1 -= Lr[k] * x[k]; else s0 -= Lr[k] * x[k];
-                }
-                x[rr] = (rr >= c) ? (s0 + s1) * rd[rr] : 0.0;
-            }
-            if (t < NB + PB) {
-                double* Xa = XdAll + (c0 / PB) * PB * 17;
-#pragma unroll
-                for (int rr = 0; rr < PB; ++rr) {
-                    Xa[rr * 17 + c] = x[rr];                          // zero above the diagonal
-                    if (rr > c) As[(c0 + c) * PLD + c0 + rr] = x[rr];  // transposed, for the X phase
-                }
-                dg[c0 + c] = x[c];
-            }
-        }
-        __syncthreads();
-        TICK(3)
-    }
-    if (t == 0) {
-        if (s_bad) atomicCAS(info, 0, blk + 1);
-        double omin = minmax[0], omax = minmax[1];
-        if (blk == 0) { omin = 1e300; omax = 0.0; }
-        minmax[0] = fmin(omin, s_min); minmax[1] = fmax(omax, s_max);
-    }
-    {   // write L back (lower triangle): thread pair per row
-        const int i = t & 127, h = t >> 7;
-        for (int c = h * 64; c < h * 64 + 64; ++c) if (c <= i) A[(size_t)c * lda + i] = As[i * PLD + c];
-    }
-    TICK(4)
-    // ---- inverse.  X(r,c), r>c is stored at As[c][r]; X(c,c) in dg[c].
-    {
-        // X(ib,jb) = -inv(L_ib,ib) * sum_{kb=jb}^{ib-1} L(ib,kb) X(kb,jb), one sub-diagonal d = ib-jb
-        // at a time; every 16x16 block is 2x2 DMMA tiles, tile tasks are dealt round-robin to warps.
-        const int lane = t & 31, warp = t >> 5;
-        const int fr = lane >> 2, fk = lane & 3;
-        for (int d = 1; d < NB / PB; ++d) {
-            const int ntask = (NB / PB - d) * 4;
-            for (int task = warp; task < ntask; task += 8) {
-                const int q = task >> 2, tm = (task >> 1) & 1, tn = task & 1;
-                const int jb = q, ib = q + d;
-                double c0v = 0.0, c1v = 0.0;
-                const double* Ap = As + (ib * PB + 8 * tm + fr) * PLD + fk;              // L(ib rows, k)
-                {   // kb = jb: B(k,n) = Xd_jb(k, 8tn+n) (zero padded)
-                    const double* Bx = XdAll + jb * PB * 17 + fk * 17 + 8 * tn + fr;
-#pragma unroll
-                    for (int k0 = 0; k0 < PB; k0 += 4) dmma(c0v, c1v, Ap[jb * PB + k0], Bx[k0 * 17]);
-                }
-                const double* Bp = As + (jb * PB + 8 * tn + fr) * PLD + fk;              // X(k, j) = As[j][k]
-                for (int kb = jb + 1; kb < ib; ++kb) {
-#pragma unroll
-                    for (int k0 = 0; k0 < PB; k0 += 4) dmma(c0v, c1v, Ap[kb * PB + k0], Bp[kb * PB + k0]);
-                }
-                double* Tq = Tb + (q * PB + 8 * tm + fr) * 17 + 8 * tn + 2 * fk;
-                Tq[0] = c0v; Tq[1] = c1v;
-            }
-            __syncthreads();
-            for (int task = warp; task < ntask; task += 8) {
-                const int q = task >> 2, tm = (task >> 1) & 1, tn = task & 1;
-                const int jb = q, ib = q + d;
-                double c0v = 0.0, c1v = 0.0;
-                const double* Ax = XdAll + ib * PB * 17 + (8 * tm + fr) * 17 + fk;       // Xd_ib(i, m)
-                const double* Bt = Tb + (q * PB + fk) * 17 + 8 * tn + fr;                // T(m, n)
-#pragma unroll
-                for (int k0 = 0; k0 < PB; k0 += 4) dmma(c0v, c1v, Ax[k0], Bt[k0 * 17]);
-                // X(ib*16 + 8tm + fr, jb*16 + 8tn + 2fk + {0,1}) stored transposed
-                double* Xo = As + (jb * PB + 8 * tn + 2 * fk) * PLD + ib * PB + 8 * tm + fr;
-                Xo[0] = -c0v; Xo[PLD] = -c1v;
-            }
-            __syncthreads();
-        }
-    }
-    TICK(5)
-    double* out = invL + (size_t)blk * NB * NB;          // column-major 128x128, lower triangular
-    {
-        const int i = t & 127, h = t >> 7;
-        for (int cc = h * 64; cc < h * 64 + 64; ++cc)
-            out[(size_t)cc * NB + i] = (i > cc) ? As[cc * PLD + i] : (i == cc ? dg[cc] : 0.0);
-    }
-    TICK(6)
-#ifdef POTRF_PROFILE
-    if (t == 0 && blk == 1) for (int k = 0; k < 8; ++k) minmax[2 + k] = (double)tk[k];
-#endif
-}
-
+#define PB 16                 // panel width inside the 128x128 diagonal block
 // ---------------------------------------------------------------------------------------------
 // k_potrf128: Cholesky of one 128x128 diagonal block + inverse of its factor, organised around
 // the only inherently serial part, the 128 pivots.
@@ -852,13 +600,11 @@ void chol_alloc(CholWork& w, int n, int ld) {
     cudaMemset(w.invL, 0, sizeof(double) * (size_t)w.nb * NB * NB);   // k_potrf128 never writes the zeros above the diagonal
     cudaMalloc(&w.info, sizeof(int));
     cudaMalloc(&w.minmax, sizeof(double) * (16 + 16 * 40));
-    cudaMalloc(&w.panel, sizeof(double) * (size_t)ld * NB);
 }
 void chol_free(CholWork& w) {
     if (w.invL) cudaFree(w.invL);
     if (w.info) cudaFree(w.info);
     if (w.minmax) cudaFree(w.minmax);
-    if (w.panel) cudaFree(w.panel);
     if (w.graphExec) cudaGraphExecDestroy((cudaGraphExec_t)w.graphExec);
     w = CholWork();
 }
@@ -871,13 +617,9 @@ static cudaEvent_t g_evA = nullptr, g_evB = nullptr;
 // stream finishes the rest of the trailing update of step k.
 static void chol_factor_body(CholWork& w, double* A, cudaStream_t st) {
     static bool attr = false;
-    const int psmem1 = (NB * PLD + NB + PB * 17 + 7 * PB * 17 + 2 * PB + 8 * PB * 17) * 8;
     const int psmem = POTRF_SMEM_DOUBLES * 8;
-    static int potrf_v1 = 0;
     if (!attr) {
-        { const char* e = getenv("DBAT_POTRF"); potrf_v1 = (e && e[0] == '1') ? 1 : 0; }
         cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
-        cudaFuncSetAttribute(k_potrf128_v1, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem1);
         {   // the look-ahead stream carries the critical path: its CTAs must be dispatched ahead of the
             // remaining CTAs of the trailing update running on the main stream
             int lo = 0, hi = 0;
@@ -892,8 +634,7 @@ static void chol_factor_body(CholWork& w, double* A, cudaStream_t st) {
     const int ld = w.ld, nb = w.nb;
     auto diag = [&](int k) { return A + (size_t)k * NB * ld + (size_t)k * NB; };
     auto panel_step = [&](int k, cudaStream_t s) {        // potrf(k) + L_ik = A_ik inv(L_kk)' (in place)
-        if (potrf_v1) k_potrf128_v1<<<1, 256, psmem1, s>>>(diag(k), ld, w.invL, k, w.n, w.info, w.minmax);
-        else k_potrf128<<<1, POTRF_THREADS, psmem, s>>>(diag(k), ld, w.invL, k, w.n, w.info, w.minmax);
+        k_potrf128<<<1, POTRF_THREADS, psmem, s>>>(diag(k), ld, w.invL, k, w.n, w.info, w.minmax);
         count_launch();
         const int rem = nb - k - 1;
         if (rem <= 0) return;
@@ -901,51 +642,22 @@ static void chol_factor_body(CholWork& w, double* A, cudaStream_t st) {
         GemmPanel::launch(dim3(rem * NB / 32, 1), s, diag(k) + NB, ld, w.invL + (size_t)k * NB * NB, NB,
                           diag(k) + NB, ld, NB, 1.0, 0.0, 0);
     };
-    // Steps are taken in pairs so that the bulk of the trailing matrix is updated with K = 256
-    // (half the C traffic and epilogues of two K = 128 updates):
-    //   k   : potrf + panel solve (arrives through the look-ahead of the previous pair)
-    //   k+1 : column block k+1 -= L(:,k) L(k+1,k)'  (K=128), potrf + panel solve
-    //   k+2 : column block k+2 -= L(:,k:k+1) L(k+2,k:k+1)'  (K=256), then potrf + panel solve on the
-    //         aux stream while the main stream updates the remaining columns >= k+3 with K=256.
+    // every potrf + panel solve runs on the aux stream under the trailing update (K = 128) of the
+    // previous step.  (Taking the steps in pairs, with K = 256 trailing updates, halves the C traffic
+    // but leaves every second panel step without anything to overlap with: measured slower.)
     panel_step(0, st);
-    static int pair_mode = -1;
-    // default: single-step look-ahead (measured 6.7 ms vs 7.3 ms for the pair-step variant at n = 6002)
-    if (pair_mode < 0) { const char* e = getenv("DBAT_CHOL_PAIR"); pair_mode = (e && e[0] == '1') ? 1 : 0; }
-    if (!pair_mode) {
-        // single-step look-ahead: every potrf + panel solve runs on the aux stream under the
-        // trailing update (K = 128) of the previous step
-        for (int k = 0; k + 1 < nb; ++k) {
-            const int rem = nb - k - 1;
-            double* Apanel = diag(k) + NB;
-            GemmCol::launch(dim3(rem * NB / 64, NB / 64), st, Apanel, ld, Apanel, ld, diag(k + 1), ld, NB, -1.0, 1.0, 0);
-            cudaEventRecord(g_evA, st);
-            cudaStreamWaitEvent(g_aux, g_evA, 0);
-            panel_step(k + 1, g_aux);
-            cudaEventRecord(g_evB, g_aux);
-            if (rem > 1) gemm_nt(Apanel + NB, ld, Apanel + NB, ld, diag(k + 2), ld, rem - 1, rem - 1, NB, -1.0, 1.0, true, st);
-            cudaStreamWaitEvent(st, g_evB, 0);
-        }
-        return;
-    }
-    int k = 0;
-    for (; k + 1 < nb; k += 2) {
-        const int rem1 = nb - k - 1;                       // row blocks below block k
-        gemm_nt(diag(k) + NB, ld, diag(k) + NB, ld, diag(k + 1), ld, rem1, 1, NB, -1.0, 1.0, false, st);
-        panel_step(k + 1, st);
-        const int rem2 = nb - k - 2;                       // row blocks below block k+1
-        if (rem2 <= 0) break;
-        const double* P2 = A + (size_t)k * NB * ld + (size_t)(k + 2) * NB;       // L(k+2:, k:k+1), 256 columns
-        gemm_nt(P2, ld, P2, ld, diag(k + 2), ld, rem2, 1, 2 * NB, -1.0, 1.0, false, st);
+    for (int k = 0; k + 1 < nb; ++k) {
+        const int rem = nb - k - 1;
+        double* Apanel = diag(k) + NB;
+        GemmCol::launch(dim3(rem * NB / 64, NB / 64), st, Apanel, ld, Apanel, ld, diag(k + 1), ld, NB, -1.0, 1.0, 0);
         cudaEventRecord(g_evA, st);
         cudaStreamWaitEvent(g_aux, g_evA, 0);
-        panel_step(k + 2, g_aux);
+        panel_step(k + 1, g_aux);
         cudaEventRecord(g_evB, g_aux);
-        if (rem2 > 1)
-            gemm_nt(P2 + NB, ld, P2 + NB, ld, diag(k + 3), ld, rem2 - 1, rem2 - 1, 2 * NB, -1.0, 1.0, true, st);
+        if (rem > 1) gemm_nt(Apanel + NB, ld, Apanel + NB, ld, diag(k + 2), ld, rem - 1, rem - 1, NB, -1.0, 1.0, true, st);
         cudaStreamWaitEvent(st, g_evB, 0);
     }
 }
-
 
 // The launch sequence of a factorisation is static for a given (matrix, size): it is captured into
 // a CUDA graph on its second use and replayed afterwards, which removes most of the host launch

@@ -48,7 +48,6 @@ struct CholWork {
     double* invL = nullptr;         // nb x 128 x 128 inverses of the diagonal blocks
     int* info = nullptr;            // device flag: 0 ok, k>0 = first non-positive pivot (1-based)
     double* minmax = nullptr;       // device: [0]=min pivot, [1]=max pivot (of L's diagonal)
-    double* panel = nullptr;        // ld x 128 workspace for the panel solve
     void* graphExec = nullptr;      // captured launch sequence of chol_factor (cudaGraphExec_t)
     const double* graphA = nullptr; const double* seen = nullptr; cudaStream_t graphStream = nullptr;
     int graphLaunches = 0;
