@@ -10,6 +10,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <iterator>
 #include <vector>
 #include <dlfcn.h>
 
@@ -398,27 +399,56 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
         }
         const int* ps = h->h_pt_start.data();
         const int* im = img_pm.data();
-        auto cmp3 = [&](int a, int b) {          // <0, 0, >0
+        // lexicographic order of the (ascending) image lists: points with similar lists become neighbours
+        std::sort(cand.begin(), cand.end(), [&](int a, int b) {
             const int ka = ps[a + 1] - ps[a], kb = ps[b + 1] - ps[b];
-            if (ka != kb) return ka < kb ? -1 : 1;
             const int* la = im + ps[a]; const int* lb = im + ps[b];
-            for (int t = 0; t < ka; ++t) if (la[t] != lb[t]) return la[t] < lb[t] ? -1 : 1;
-            return 0;
-        };
-        std::sort(cand.begin(), cand.end(), [&](int a, int b) { const int c = cmp3(a, b); return c != 0 ? c < 0 : a < b; });
+            for (int t = 0; t < std::min(ka, kb); ++t) if (la[t] != lb[t]) return la[t] < lb[t];
+            return ka != kb ? ka < kb : a < b;
+        });
+        // greedy groups of consecutive points: at most gcap points, union of their image lists at most
+        // `mu` images (a single point always fits).  A point that lacks an image of the union simply
+        // has zero rows there.
         const int gcap = std::max(1, std::min(16, (int)(cand.size() / (148 * 8))));   // <= GRP_CAP of schur.cu
-        std::vector<int> gstart;
-        gstart.push_back(0);
-        for (size_t i = 1; i <= cand.size(); ++i) {
-            const bool cut = i == cand.size() || cmp3(cand[i - 1], cand[i]) != 0 || (int)(i - gstart.back()) >= gcap;
-            if (cut) gstart.push_back((int)i);
+        int mu = 12;
+        if (const char* e = getenv("DBAT_GRP_MU")) mu = std::max(1, std::min(DBAT_GRP_MAXM, atoi(e)));
+        std::vector<int> gstart, gimg_off, gimg, uni, tmp;
+        std::vector<unsigned char> slot(std::max(1, nObs), 0);
+        gstart.push_back(0); gimg_off.push_back(0);
+        auto close_group = [&](size_t end) {
+            for (size_t i = gstart.back(); i < end; ++i) {
+                const int j = cand[i];
+                for (int o = ps[j]; o < ps[j + 1]; ++o)
+                    slot[o] = (unsigned char)(std::lower_bound(uni.begin(), uni.end(), im[o]) - uni.begin());
+            }
+            gimg.insert(gimg.end(), uni.begin(), uni.end());
+            gimg_off.push_back((int)gimg.size());
+            gstart.push_back((int)end);
+            P.grpMaxRays = std::max(P.grpMaxRays, (int)uni.size());
+        };
+        P.grpMaxRays = 1;
+        for (size_t i = 0; i < cand.size(); ++i) {
+            const int j = cand[i];
+            tmp.clear();
+            std::set_union(uni.begin(), uni.end(), im + ps[j], im + ps[j + 1], std::back_inserter(tmp));
+            const int cnt = (int)(i - gstart.back());
+            if (cnt > 0 && ((int)tmp.size() > mu || cnt >= gcap)) {
+                close_group(i);
+                uni.assign(im + ps[j], im + ps[j + 1]);
+            } else {
+                uni.swap(tmp);
+            }
         }
+        if (!cand.empty()) close_group(cand.size());
         const bool noCand = cand.empty();
-        if (noCand) { cand.push_back(0); gstart.assign(1, 0); }
+        if (noCand) { cand.push_back(0); gstart.assign(1, 0); gimg_off.assign(1, 0); gimg.push_back(0); }
         if (big.empty()) big.push_back(0); else P.nBig = (int)big.size();
         P.nGrp = (int)gstart.size() - 1;
-        P.grpMaxRays = 1;
-        for (size_t i = 0; i + 1 < gstart.size(); ++i) P.grpMaxRays = std::max(P.grpMaxRays, ps[cand[gstart[i]] + 1] - ps[cand[gstart[i]]]);
+        {
+            int *d_go, *d_gi; unsigned char* d_sl;
+            UP(d_go, gimg_off); UP(d_gi, gimg); UP(d_sl, slot);
+            P.grp_img_off = d_go; P.grp_img = d_gi; P.obs_slot = d_sl;
+        }
         int *d_gp, *d_gs, *d_big;
         UP(d_gp, cand); UP(d_gs, gstart); UP(d_big, big);
         P.grp_pt = d_gp; P.grp_start = d_gs; P.big_pt = d_big;

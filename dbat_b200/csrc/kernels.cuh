@@ -65,13 +65,16 @@ struct DevProblem {
     const long long* blk_off;    // nBlk+1 offsets into pairs
     int nBlk;
     double* shPart;        // per-CTA partials of the shared x shared reduction
-    // grouped Schur update (default): points sorted by their image list; a group is a run of points
-    // seen by exactly the same images (capped in length), so the camera x camera blocks of a whole
-    // group are summed on chip and reach S with one atomic per entry
+    // grouped Schur update (default): points sorted by their image list; a group is a run of <= 16
+    // neighbouring points whose image lists have a small union, so the camera x camera blocks of a
+    // whole group are summed on chip and reach S with one atomic per entry
     const int* grp_pt;     // point ids, grouped
     const int* grp_start;  // nGrp+1 offsets into grp_pt
+    const int* grp_img_off;      // nGrp+1 offsets into grp_img
+    const int* grp_img;          // ascending union of the image lists of every group
+    const unsigned char* obs_slot;   // per point-major observation: position of its image in the group's union
     int nGrp;
-    int grpMaxRays;        // largest ray count among grouped points
+    int grpMaxRays;        // largest union among the groups (sizes the kernel's shared memory)
     const int* big_pt;     // points with more than DBAT_GRP_MAXM rays (per-point kernel)
     int nBig;
     double* vinv;          // nOP x 8: (V_j + lambda I)^-1 (6 entries) of the current solve

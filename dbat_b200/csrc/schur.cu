@@ -449,40 +449,43 @@ __global__ void k_point_vinv(DevProblem P, double lambda) {
 #define GRP_CAP 16            // max points per group (create-time cap)
 #define GRP_LDK 52            // row stride of What / Yhat / Wsh: 3*GRP_CAP = 48 columns + 4 (= 4 mod 16: conflict-free fragments)
 struct GrpHeader {            // per-group data staged in shared memory (double-buffered)
-    int m, ng;
-    int j[GRP_CAP], ob[GRP_CAP];
-    int img[DBAT_GRP_MAXM];
-    int eoc[DBAT_GRP_MAXM * 6];                  // x column of every EO element of the group's images
+    int m, ng, maxobs;                           // images in the union, points, largest ray count of a point
+    int j[GRP_CAP], ob[GRP_CAP], nob[GRP_CAP];   // point id, first point-major observation, ray count
+    int eoc[DBAT_GRP_MAXM * 6];                  // x column of every EO element of the union's images
     double vi[GRP_CAP * 6];
 };
 // Registers of one thread's share of the next group's header (loaded early, stored late).
-struct GrpPrefetch { int j, ob, img, eoc; double2 v01, v23, v45; int m, ng; };
+struct GrpPrefetch { int j, ob, nob, eoc; double2 v01, v23, v45; int m, ng; };
 
 __device__ __forceinline__ void grp_prefetch(const DevProblem& P, int grp, int t, GrpPrefetch& f) {
-    f.m = 0; f.ng = 0; f.j = 0; f.ob = 0; f.img = 0; f.eoc = -1;
+    f.m = 0; f.ng = 0; f.j = 0; f.ob = 0; f.nob = 0; f.eoc = -1;
     if (grp >= P.nGrp) return;
     const int g0 = P.grp_start[grp];
     f.ng = P.grp_start[grp + 1] - g0;
-    const int j0 = P.grp_pt[g0];
-    const int o00 = P.pt_start[j0];
-    f.m = P.pt_start[j0 + 1] - o00;
+    const int i0 = P.grp_img_off[grp];
+    f.m = P.grp_img_off[grp + 1] - i0;
     if (t < f.ng) {
         f.j = P.grp_pt[g0 + t];
         f.ob = P.pt_start[f.j];
+        f.nob = P.pt_start[f.j + 1] - f.ob;
         const double2* vp = reinterpret_cast<const double2*>(P.vinv + (size_t)f.j * 8);
         f.v01 = vp[0]; f.v23 = vp[1]; f.v45 = vp[2];
     }
-    if (t >= 32 && t - 32 < f.m) f.img = P.img_pm[o00 + t - 32];
-    if (t >= 64 && t - 64 < 6 * f.m) f.eoc = P.eo_col[6 * (size_t)P.img_pm[o00 + (t - 64) / 6] + (t - 64) % 6];
+    if (t >= 64 && t - 64 < 6 * f.m) f.eoc = P.eo_col[6 * (size_t)P.grp_img[i0 + (t - 64) / 6] + (t - 64) % 6];
 }
 __device__ __forceinline__ void grp_store(GrpHeader& h, int t, const GrpPrefetch& f) {
     if (t == 0) { h.m = f.m; h.ng = f.ng; }
+    if (t < 32) {                                            // largest ray count of the group (warp 0)
+        int mo = t < f.ng ? f.nob : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mo = max(mo, __shfl_xor_sync(0xffffffffu, mo, o));
+        if (t == 0) h.maxobs = mo;
+    }
     if (t < f.ng) {
-        h.j[t] = f.j; h.ob[t] = f.ob;
+        h.j[t] = f.j; h.ob[t] = f.ob; h.nob[t] = f.nob;
         double* sv = h.vi + 6 * t;
         sv[0] = f.v01.x; sv[1] = f.v01.y; sv[2] = f.v23.x; sv[3] = f.v23.y; sv[4] = f.v45.x; sv[5] = f.v45.y;
     }
-    if (t >= 32 && t - 32 < f.m) h.img[t - 32] = f.img;
     if (t >= 64 && t - 64 < 6 * f.m) h.eoc[t - 64] = f.eoc;
 }
 
@@ -518,11 +521,18 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
         const int m = H.m, ng = H.ng;
         const int R = 6 * m, RT = (R + 7) >> 3;              // camera rows, 8-row tiles
         const int K = 3 * ng, Kp = (K + 3) & ~3;
-        // ---- stage What (coalesced: 18 m contiguous doubles per point) and Wsh
-        for (int idx = t; idx < ng * 3 * R; idx += GRP_TH) {
-            const int gi = idx / (3 * R), e = idx - gi * 3 * R;            // e = 3 r + c
-            const int r = e / 3, c = e - 3 * r;
-            What[r * GRP_LDK + 3 * gi + c] = P.W[(size_t)H.ob[gi] * DBAT_W_STRIDE + e];
+        // ---- stage What: the 6x3 block of observation o of point gi goes to the rows of its image's
+        //      position in the union (obs_slot); rows of images a point does not see stay zero
+        {
+            const int per = 18 * H.maxobs;
+            for (int idx = t; idx < ng * per; idx += GRP_TH) {
+                const int gi = idx / per, e18 = idx - gi * per, o = e18 / 18, e = e18 - 18 * o;   // e = 3 a + c
+                if (o < H.nob[gi]) {
+                    const int ob = H.ob[gi] + o;
+                    const int a = e / 3, c = e - 3 * a;
+                    What[(6 * P.obs_slot[ob] + a) * GRP_LDK + 3 * gi + c] = P.W[(size_t)ob * DBAT_W_STRIDE + e];
+                }
+            }
         }
         for (int idx = t; idx < ng * 45; idx += GRP_TH) {
             const int gi = idx / 45, e = idx - gi * 45, sidx = e / 3, c = e - 3 * sidx;
@@ -584,7 +594,8 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
                             const int c = 8 * tj + 2 * fk + e;
                             if (c < R) {
                                 const int col = H.eoc[c];
-                                if (col >= 0 && col <= row) atomicAdd(&P.S[(size_t)col * ld + row], -(e ? c1 : c0));
+                                const double v = e ? c1 : c0;                 // exact zero: image pair not shared by any point
+                                if (col >= 0 && col <= row && v != 0.0) atomicAdd(&P.S[(size_t)col * ld + row], -v);
                             }
                         }
                     } else {
@@ -608,6 +619,12 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
             const double* pa = Yhat + (RWmax + 8 * ta + fr) * GRP_LDK + fk;
             const double* pb = Wsh + (8 * tb + fr) * GRP_LDK + fk;
             for (int k0 = 0; k0 < Kp; k0 += 4) dmma_s(accSh[0], accSh[1], pa[k0], pb[k0]);
+        }
+        __syncthreads();
+        // What must be all zero where the next group does not write (images a point does not see)
+        for (int i = t; i < 8 * RT * (Kp / 2); i += GRP_TH) {
+            const int row = i / (Kp / 2), k2 = i - row * (Kp / 2);
+            *reinterpret_cast<double2*>(What + row * GRP_LDK + 2 * k2) = make_double2(0.0, 0.0);
         }
         __syncthreads();
     }
