@@ -186,3 +186,36 @@ def test_stpierre_oracle_converges():
         assert ok and iters == n
         vals.append(s0)
     assert max(vals) - min(vals) < 1e-9 and abs(vals[0] - 1.0282960127) < 1e-8
+
+
+def test_forwintersect_oracle_known_answer():
+    """Restatement of forwintersect.m / pm_multiforwintersect.m / pm_forwintersect3.m: with the true
+    IO/EO and noise-free image points of a seeded synthetic block (no affine term) the intersection
+    returns the true object points (the generator projects with the modular model 3, the intersection
+    removes the distortion with pm_lens1 - both sides of the same Brown polynomial), residuals are ~0,
+    and a point left with one ray comes back as NaN."""
+    import numpy as np
+    from dbat_b200 import synth
+    from oracle.photogrammetry import forwintersect
+    saved = synth.IO_TRUE.copy()
+    synth.IO_TRUE[3] = 0.0            # pm_multilenscorr1 has no affine term ("a: not implemented yet", :155-158)
+    try:
+        s, truth = synth.make_scene(21, 60, rays=6, seed=3, noise_px=0.0, build_indices=False)
+    finally:
+        synth.IO_TRUE[:] = saved
+    s.IO.val[:] = truth['IO'][:, None]
+    s.EO.val[:] = truth['EO']
+    k = np.flatnonzero(s.IP.op == 5)
+    keep = np.ones(len(s.IP.op), bool)
+    keep[k[1:]] = False
+    for f in ('val', 'std'):
+        setattr(s.IP, f, getattr(s.IP, f)[:, keep])
+    for f in ('img', 'op', 'cam'):
+        setattr(s.IP, f, getattr(s.IP, f)[keep])
+    s.OP.val[:] = np.nan
+    s2, ids, res = forwintersect(s, 'all')
+    m = np.arange(60) != 5
+    assert np.isnan(s2.OP.val[:, 5]).all() and np.isnan(res[5])
+    # model 3 applies the distortion on the measured side (backward), as pm_multilenscorr1 does
+    assert np.abs(s2.OP.val[:, m] - truth['OP'][:, m]).max() < 1e-6
+    assert np.nanmax(res) < 1e-7
