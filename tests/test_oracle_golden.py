@@ -219,3 +219,29 @@ def test_forwintersect_oracle_known_answer():
     # model 3 applies the distortion on the measured side (backward), as pm_multilenscorr1 does
     assert np.abs(s2.OP.val[:, m] - truth['OP'][:, m]).max() < 1e-6
     assert np.nanmax(res) < 1e-7
+
+
+def test_camcal_script_pipeline_matches_golden_report():
+    """The whole script pipeline of data/script/camcaldemo/camcaldemo.xml - default camera values,
+    spatial_resection (resect.m, 3-point Grunert from the 4 control points), forward_intersection
+    (forwintersect.m), bundle_adjustment (GNA) - reproduces the reference's own report.txt:
+    8 iterations, first error 28805.9, last error 98.556, sigma0 1.6148.  This pins the restatements of
+    resect / pm_resect_3pt / largesttriangle / forwintersect on a reference golden: the first error is a
+    function of the start values only."""
+    import copy, os
+    import numpy as np
+    from oracle.loaders import load_camcal_script
+    from oracle.photogrammetry import resect, forwintersect
+    from oracle.bundle import bundle as obundle
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'camcaldemo')
+    s = load_camcal_script(root)
+    assert np.isnan(s.EO.val).all()
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, rms, fail = resect(s, 'all', cpId, 1, 0, cpId)
+    assert not fail and np.isfinite(s1.EO.val).all() and rms.max() < 0.2      # normalised image units, default camera
+    s2, ids, res = forwintersect(s1, 'all', True)
+    assert np.isfinite(s2.OP.val).all() and len(ids) == 96
+    s3, ok, iters, sigma0, E = obundle(copy.deepcopy(s2), 'gna')
+    assert ok and iters == 8
+    assert abs(E.res[0] - 28805.9) < 0.06 and abs(E.res[-1] - 98.556) < 6e-4
+    assert abs(sigma0 - 1.6148) < 6e-5
