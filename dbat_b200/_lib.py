@@ -56,7 +56,7 @@ EXPORTS = ['dbat_create', 'dbat_destroy', 'dbat_last_error', 'dbat_num_unknowns'
            'dbat_num_residuals', 'dbat_eval', 'dbat_jacobian_nnz', 'dbat_jacobian_csc',
            'dbat_default_opts', 'dbat_solve', 'dbat_normal_step', 'dbat_cov',
            'dbat_comm_unique_id', 'dbat_comm_init', 'dbat_phase_times', 'dbat_dense_chol_solve',
-           'dbat_forwintersect', 'dbat_forwintersect_error']
+           'dbat_forwintersect', 'dbat_forwintersect_error', 'dbat_resect3']
 
 _lib = None
 
@@ -66,6 +66,13 @@ class FwiDesc(C.Structure):
         ('nImg', C.c_int64), ('nOP', C.c_int64), ('nObs', C.c_int64), ('NC', C.c_int64), ('nK', C.c_int64), ('nP', C.c_int64),
         ('IO', c_dp), ('EO', c_dp), ('pxSize', c_dp), ('IPval', c_dp),
         ('obs_img', c_ip), ('obs_op', c_ip), ('pts', c_ip), ('nPts', C.c_int64),
+    ]
+
+
+class ResectDesc(C.Structure):
+    _fields_ = [
+        ('nCam', C.c_int64), ('X3', c_dp), ('x3', c_dp), ('test_start', c_ip), ('XT', c_dp), ('xT', c_dp),
+        ('behind', C.c_int32),
     ]
 
 
@@ -115,6 +122,8 @@ def lib():
     L.dbat_forwintersect.restype = C.c_int
     L.dbat_forwintersect_error.argtypes = []
     L.dbat_forwintersect_error.restype = C.c_char_p
+    L.dbat_resect3.argtypes = [C.POINTER(ResectDesc), c_dp, c_dp]
+    L.dbat_resect3.restype = C.c_int
     _lib = L
     return L
 

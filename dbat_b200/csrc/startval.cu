@@ -169,3 +169,193 @@ extern "C" int dbat_forwintersect(const dbat_fwi_desc* d, double* OP, double* re
     for (void* p : allocs) cudaFree(p);
     return rc;
 }
+
+
+// ---------------------------------------------------------------------------------------------
+// Batched 3-point spatial resection with residual test, one thread per camera.
+// Replaces the per-camera body of code/photogrammetry/resect.m:96-129 -> pm_resect_3pt.m:38-147
+// (Grunert's quartic, absolute orientation of every admissible root, mean reprojection residual over
+// the camera's test points, best root) and the conversion of the best camera matrix to EO
+// (euclidean(null(P)), derotmat3d.m:19-21).  The choice of the three points (largesttriangle.m) and
+// the lens correction of the few control-point measurements stay on the host.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct Cplx { double re, im; };
+__device__ __forceinline__ Cplx cmul(Cplx a, Cplx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+__device__ __forceinline__ Cplx csub(Cplx a, Cplx b) { return {a.re - b.re, a.im - b.im}; }
+__device__ __forceinline__ Cplx cdiv(Cplx a, Cplx b) {
+    const double d = b.re * b.re + b.im * b.im;
+    return {(a.re * b.re + a.im * b.im) / d, (a.im * b.re - a.re * b.im) / d};
+}
+// all four roots of c4 z^4 + ... + c0 (MATLAB `roots`): Durand-Kerner on the monic polynomial
+__device__ void quartic_roots(const double c[5], Cplx z[4]) {
+    const double a3 = c[3] / c[4], a2 = c[2] / c[4], a1 = c[1] / c[4], a0 = c[0] / c[4];
+    const double bound = 1.0 + fmax(fmax(fabs(a3), fabs(a2)), fmax(fabs(a1), fabs(a0)));
+    Cplx w = {0.4, 0.9}, pw = {1.0, 0.0};
+    for (int i = 0; i < 4; ++i) { z[i] = {pw.re * bound * 0.5, pw.im * bound * 0.5}; pw = cmul(pw, w); }
+    for (int it = 0; it < 200; ++it) {
+        double moved = 0.0;
+        for (int i = 0; i < 4; ++i) {
+            // p(z_i) by Horner
+            Cplx p = {1.0, 0.0};
+            p = cmul(p, z[i]); p.re += a3;
+            p = cmul(p, z[i]); p.re += a2;
+            p = cmul(p, z[i]); p.re += a1;
+            p = cmul(p, z[i]); p.re += a0;
+            Cplx q = {1.0, 0.0};
+            for (int j = 0; j < 4; ++j) if (j != i) q = cmul(q, csub(z[i], z[j]));
+            const Cplx d = cdiv(p, q);
+            z[i] = csub(z[i], d);
+            moved = fmax(moved, fabs(d.re) + fabs(d.im));
+        }
+        if (moved < 1e-15 * bound) break;
+    }
+}
+__device__ __forceinline__ void cross3(const double a[3], const double b[3], double c[3]) {
+    c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+__device__ __forceinline__ void unit3(double a[3]) {
+    const double n = 1.0 / sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    a[0] *= n; a[1] *= n; a[2] *= n;
+}
+// columns r1 = ob/|ob|, r2 = (ob x oc)/|.|, r3 = (ob x (ob x oc))/|.|   (pm_resect_3pt.m:103-118)
+__device__ void tri_frame(const double p0[3], const double p1[3], const double p2[3], double R[3][3]) {
+    double ob[3] = {p2[0] - p0[0], p2[1] - p0[1], p2[2] - p0[2]};
+    double oc[3] = {p1[0] - p0[0], p1[1] - p0[1], p1[2] - p0[2]};
+    double r2[3], r3[3];
+    cross3(ob, oc, r2);
+    cross3(ob, r2, r3);
+    unit3(ob); unit3(r2); unit3(r3);
+    for (int i = 0; i < 3; ++i) { R[i][0] = ob[i]; R[i][1] = r2[i]; R[i][2] = r3[i]; }
+}
+
+struct ResectDev {
+    int nCam, behind;
+    const double* X3; const double* x3; const int* tstart; const double* XT; const double* xT;
+    double* EO; double* res;
+};
+__global__ void __launch_bounds__(64) k_resect3(ResectDev D) {
+    const int cam = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cam >= D.nCam) return;
+    const double* X = D.X3 + 9 * (size_t)cam;          // 3 object points, column-major 3x3
+    const double* xi = D.x3 + 6 * (size_t)cam;         // 3 normalised image points, 2x3
+    double x[3][3];                                    // unit rays
+    for (int k = 0; k < 3; ++k) {
+        x[k][0] = xi[2 * k]; x[k][1] = xi[2 * k + 1]; x[k][2] = 1.0;
+        unit3(x[k]);
+    }
+    auto dist = [&](int i, int j) {
+        const double d0 = X[3 * i] - X[3 * j], d1 = X[3 * i + 1] - X[3 * j + 1], d2 = X[3 * i + 2] - X[3 * j + 2];
+        return sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+    };
+    auto cosang = [&](int i, int j) { return fabs(x[i][0] * x[j][0] + x[i][1] * x[j][1] + x[i][2] * x[j][2]); };   // subspace(): acute
+    const double a = dist(1, 2), b = dist(0, 2), c = dist(0, 1);
+    const double ca = cosang(1, 2), cb = cosang(0, 2), cg = cosang(0, 1);
+    const double b2 = b * b;
+    const double q1 = (a * a - c * c) / b2, q2 = (a * a + c * c) / b2, q3 = (b2 - c * c) / b2, q4 = (b2 - a * a) / b2;
+    double co[5];
+    co[4] = (q1 - 1) * (q1 - 1) - 4 * c * c / b2 * ca * ca;
+    co[3] = 4 * (q1 * (1 - q1) * cb + 2 * c * c / b2 * ca * ca * cb - (1 - q2) * ca * cg);
+    co[2] = 2 * (q1 * q1 + 2 * q1 * q1 * cb * cb + 2 * q3 * ca * ca + 2 * q4 * cg * cg - 4 * q2 * ca * cb * cg - 1);
+    co[1] = 4 * (-q1 * (1 + q1) * cb + 2 * a * a / b2 * cg * cg * cb - (1 - q2) * ca * cg);
+    co[0] = (1 + q1) * (1 + q1) - 4 * a * a / b2 * cg * cg;
+    Cplx z[4];
+    quartic_roots(co, z);
+    const int t0 = D.tstart[cam], t1 = D.tstart[cam + 1];
+    double best = 1e300, bestR[3][3], bestC[3];
+    bool found = false;
+    double oR[3][3];
+    tri_frame(X, X + 3, X + 6, oR);
+    for (int r = 0; r < 4; ++r) {
+        const double mag = sqrt(z[r].re * z[r].re + z[r].im * z[r].im);
+        if (!(fabs(z[r].im) / mag < 1e-3)) continue;   // pm_resect_3pt.m:74: real roots only
+        const double v = z[r].re;
+        const double u = ((-1 + q1) * v * v - 2 * q1 * cb * v + 1 + q1) / (2 * (cg - v * ca));
+        const double s1 = sqrt(b2 / (1 + v * v - 2 * v * cb));
+        const double s3 = v * s1, s2 = u * s1;
+        if (!(s1 >= 0 && s2 >= 0 && s3 >= 0)) continue;
+        const double sgn = D.behind ? -1.0 : 1.0;
+        double cx[3][3];
+        const double ss[3] = {s1, s2, s3};
+        for (int k = 0; k < 3; ++k) for (int i = 0; i < 3; ++i) cx[k][i] = sgn * ss[k] * x[k][i];
+        double cRd[3][3];
+        tri_frame(cx[0], cx[1], cx[2], cRd);
+        double R[3][3];                                 // cRo = cRdelta * oRdelta'
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[i][j] = cRd[i][0] * oR[j][0] + cRd[i][1] * oR[j][1] + cRd[i][2] * oR[j][2];
+        double C[3];                                    // oxO = X1 - cRo' * cx1
+        for (int i = 0; i < 3; ++i) C[i] = X[i] - (R[0][i] * cx[0][0] + R[1][i] * cx[0][1] + R[2][i] * cx[0][2]);
+        double ssq = 0.0;
+        for (int t = t0; t < t1; ++t) {
+            const double d0 = D.XT[3 * (size_t)t] - C[0], d1 = D.XT[3 * (size_t)t + 1] - C[1], d2 = D.XT[3 * (size_t)t + 2] - C[2];
+            const double p0 = R[0][0] * d0 + R[0][1] * d1 + R[0][2] * d2;
+            const double p1 = R[1][0] * d0 + R[1][1] * d1 + R[1][2] * d2;
+            const double p2 = R[2][0] * d0 + R[2][1] * d1 + R[2][2] * d2;
+            const double e0 = p0 / p2 - D.xT[2 * (size_t)t], e1 = p1 / p2 - D.xT[2 * (size_t)t + 1];
+            ssq += e0 * e0 + e1 * e1;
+        }
+        const double rr = sqrt(ssq / (t1 - t0));
+        if (rr < best) {
+            best = rr; found = true;
+            for (int i = 0; i < 3; ++i) { bestC[i] = C[i]; for (int j = 0; j < 3; ++j) bestR[i][j] = R[i][j]; }
+        }
+    }
+    double* eo = D.EO + 6 * (size_t)cam;
+    const double nanv = __longlong_as_double(0x7ff8000000000000LL);
+    if (found) {
+        eo[0] = bestC[0]; eo[1] = bestC[1]; eo[2] = bestC[2];
+        eo[3] = atan2(-bestR[2][1], bestR[2][2]);       // derotmat3d.m:19-21
+        eo[4] = asin(bestR[2][0]);
+        eo[5] = atan2(-bestR[1][0], bestR[0][0]);
+        D.res[cam] = best;
+    } else {
+        for (int i = 0; i < 6; ++i) eo[i] = nanv;
+        D.res[cam] = nanv;                              // resect.m:120 reports inf/fail; the host mirror maps NaN to failure
+    }
+}
+}  // namespace
+
+extern "C" int dbat_resect3(const dbat_resect_desc* d, double* EO, double* res) {
+    if (!d || !EO || !res || d->nCam < 0 || (d->nCam > 0 && (!d->X3 || !d->x3 || !d->test_start))) {
+        g_fwi_err = "dbat_resect3: bad argument"; return DBAT_E_BADARG;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_fwi_err = "dbat_resect3: no CUDA device"; return DBAT_E_CUDA; }
+    const int nCam = (int)d->nCam;
+    if (nCam == 0) return DBAT_OK;
+    std::vector<int> ts(nCam + 1);
+    for (int k = 0; k <= nCam; ++k) {
+        ts[k] = (int)d->test_start[k];
+        if (ts[k] < 0 || (k > 0 && ts[k] < ts[k - 1])) { g_fwi_err = "dbat_resect3: test_start must be non-decreasing"; return DBAT_E_BADARG; }
+    }
+    const int nT = ts[nCam];
+    if (nT > 0 && (!d->XT || !d->xT)) { g_fwi_err = "dbat_resect3: bad argument"; return DBAT_E_BADARG; }
+    std::vector<void*> allocs;
+    auto up = [&](const void* h, size_t bytes) -> void* {
+        void* p = nullptr;
+        if (cudaMalloc(&p, std::max<size_t>(bytes, 16)) != cudaSuccess) return nullptr;
+        allocs.push_back(p);
+        if (h && bytes) cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice);
+        return p;
+    };
+    ResectDev D{};
+    D.nCam = nCam; D.behind = d->behind ? 1 : 0;
+    D.X3 = (const double*)up(d->X3, sizeof(double) * 9 * nCam);
+    D.x3 = (const double*)up(d->x3, sizeof(double) * 6 * nCam);
+    D.tstart = (const int*)up(ts.data(), sizeof(int) * (nCam + 1));
+    D.XT = (const double*)up(d->XT, sizeof(double) * 3 * nT);
+    D.xT = (const double*)up(d->xT, sizeof(double) * 2 * nT);
+    D.EO = (double*)up(nullptr, sizeof(double) * 6 * nCam);
+    D.res = (double*)up(nullptr, sizeof(double) * nCam);
+    int rc = DBAT_OK;
+    if (!D.X3 || !D.x3 || !D.tstart || !D.XT || !D.xT || !D.EO || !D.res) { g_fwi_err = "dbat_resect3: out of device memory"; rc = DBAT_E_OOM; }
+    else {
+        k_resect3<<<(nCam + 63) / 64, 64>>>(D);
+        count_launch();
+        cudaMemcpy(EO, D.EO, sizeof(double) * 6 * nCam, cudaMemcpyDeviceToHost);
+        cudaMemcpy(res, D.res, sizeof(double) * nCam, cudaMemcpyDeviceToHost);
+        const cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { g_fwi_err = std::string("dbat_resect3: ") + cudaGetErrorString(e); rc = DBAT_E_CUDA; }
+    }
+    for (void* p : allocs) cudaFree(p);
+    return rc;
+}

@@ -187,6 +187,24 @@ typedef struct dbat_fwi_desc {
 int dbat_forwintersect(const dbat_fwi_desc* desc, double* OP, double* res, double* kernel_ms);
 const char* dbat_forwintersect_error(void);
 
+/* Batched 3-point spatial resection with residual test, one problem per camera.  Replaces the
+ * per-camera body of code/photogrammetry/resect.m:96-129 (pm_resect_3pt.m:38-147: Grunert's quartic,
+ * absolute orientation per admissible root, mean reprojection residual over the test points, best
+ * root; then EO = [euclidean(null(P)); derotmat3d(P(:,1:3))]).  The caller chooses the three points
+ * (largesttriangle.m) and passes lens-corrected, normalised image coordinates (K\[x;y;1]). */
+typedef struct dbat_resect_desc {
+    int64_t nCam;
+    const double*  X3;          /* 3 x 3 x nCam  object coordinates of the three points (columns) */
+    const double*  x3;          /* 2 x 3 x nCam  their normalised image coordinates */
+    const int64_t* test_start;  /* nCam+1, 0-based offsets of every camera's test points in XT / xT */
+    const double*  XT;          /* 3 x nTest     object coordinates of the test points */
+    const double*  xT;          /* 2 x nTest     normalised image coordinates of the test points */
+    int32_t behind;             /* pm_resect_3pt's `behind` flag (resect.m passes true) */
+} dbat_resect_desc;
+/* EO: 6 x nCam out ([X;Y;Z;omega;phi;kappa], NaN when no admissible root); res: nCam out (best mean residual).
+ * Errors are reported through dbat_forwintersect_error(). */
+int dbat_resect3(const dbat_resect_desc* desc, double* EO, double* res);
+
 #ifdef __cplusplus
 }
 #endif

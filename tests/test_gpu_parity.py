@@ -510,3 +510,45 @@ def test_forwintersect_refuses_bad_eo():
     s.EO.val[0, 0] = np.nan
     with pytest.raises(ValueError, match='EO'):
         dbat_b200.forwintersect(s, 'all')
+
+
+def test_resect_matches_oracle_camcal():
+    """resect(s0,'all',cpId,1,0,cpId) as in camcaldemo.m:102 / parseops.m:38 on the camcal script project
+    (default camera, EO unknown): batched 3-point resection kernel vs the restatement of resect.m /
+    pm_resect_3pt.m."""
+    from oracle.photogrammetry import resect as oresect
+    s = loaders.load_camcal_script(os.path.join(os.path.dirname(GOLD), 'camcaldemo'))
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    sg, rmsg, failg = dbat_b200.resect(s, 'all', cpId, 1, 0, cpId)
+    so, rmso, failo = oresect(s, 'all', cpId, 1, 0, cpId)
+    assert not failg and not failo
+    np.testing.assert_allclose(sg.EO.val, so.EO.val, rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(rmsg, rmso, rtol=1e-6, atol=1e-12)
+    # two candidate triangles per camera (n = 2): same winner
+    sg2, rmsg2, _ = dbat_b200.resect(s, [0, 5, 20], cpId, 2, 0.5, cpId)
+    so2, rmso2, _ = oresect(s, [0, 5, 20], cpId, 2, 0.5, cpId)
+    np.testing.assert_allclose(sg2.EO.val[:, [0, 5, 20]], so2.EO.val[:, [0, 5, 20]], rtol=1e-7, atol=1e-8)
+    np.testing.assert_allclose(rmsg2, rmso2, rtol=1e-6, atol=1e-12)
+
+
+def test_camcal_script_pipeline_on_device_matches_golden_report():
+    """The camcal script's operations on the device - spatial_resection, forward_intersection,
+    bundle_adjustment - against the reference's report.txt: 8 iterations, first error 28805.9, last error
+    98.556, sigma0 1.6148 (the first error depends on the start values only)."""
+    s = loaders.load_camcal_script(os.path.join(os.path.dirname(GOLD), 'camcaldemo'))
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, rms, fail = dbat_b200.resect(s, 'all', cpId, 1, 0, cpId)
+    assert not fail
+    s2, ids, res = dbat_b200.forwintersect(s1, 'all', True)
+    assert np.isfinite(s2.OP.val).all()
+    s3, ok, iters, sigma0, E = dbat_b200.bundle(s2, 'gna')
+    assert ok and iters == 8
+    assert abs(E.res[0] - 28805.9) < 0.06 and abs(E.res[-1] - 98.556) < 6e-4
+    assert abs(sigma0 - 1.6148) < 6e-5
+
+
+def test_resect_reports_failure_with_two_control_points():
+    s = loaders.load_camcal_script(os.path.join(os.path.dirname(GOLD), 'camcaldemo'))
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl][:2]
+    sg, rms, fail = dbat_b200.resect(s, [0, 1], cpId, 1, 0, cpId)
+    assert fail and np.isnan(sg.EO.val[:, [0, 1]]).all() and np.isinf(rms).all()
