@@ -117,6 +117,28 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         if (nlhs > 1) plhs[1] = res; else mxDestroyArray(res);
         return;
     }
+    if (!strcmp(cmd, "resect3")) {
+        /* [EO,res]=dbat_mex('resect3',X3,x3,testStart,XT,xT,behind)  (resect.m:96-129, pm_resect_3pt.m) */
+        if (nrhs != 7) ERR("nrhs", "resect3(X3,x3,testStart,XT,xT,behind)");
+        if (!mxIsInt64(prhs[3])) ERR("badType", "testStart must be int64 (0-based offsets).");
+        dbat_resect_desc r;
+        memset(&r, 0, sizeof(r));
+        r.nCam = (int64_t)(mxGetNumberOfElements(prhs[1]) / 9);
+        if (mxGetNumberOfElements(prhs[2]) != (mwSize)(6 * r.nCam) || mxGetNumberOfElements(prhs[3]) != (mwSize)(r.nCam + 1))
+            ERR("badSize", "X3 is 3x3xN, x3 is 2x3xN, testStart has N+1 elements.");
+        r.X3 = mxGetDoubles(prhs[1]); r.x3 = mxGetDoubles(prhs[2]);
+        r.test_start = (const int64_t *)mxGetData(prhs[3]);
+        r.XT = mxGetDoubles(prhs[4]); r.xT = mxGetDoubles(prhs[5]);
+        r.behind = mxIsLogicalScalarTrue(prhs[6]) || mxGetScalar(prhs[6]) != 0;
+        if (mxGetNumberOfElements(prhs[4]) != (mwSize)(3 * r.test_start[r.nCam]) ||
+            mxGetNumberOfElements(prhs[5]) != (mwSize)(2 * r.test_start[r.nCam])) ERR("badSize", "XT is 3xT, xT is 2xT.");
+        plhs[0] = mxCreateDoubleMatrix(6, (mwSize)r.nCam, mxREAL);
+        mxArray *res = mxCreateDoubleMatrix(1, (mwSize)r.nCam, mxREAL);
+        int rc = dbat_resect3(&r, mxGetDoubles(plhs[0]), mxGetDoubles(res));
+        if (rc != DBAT_OK) mexErrMsgIdAndTxt("DBAT:dbat_mex:resect3", "%s (code %d)", dbat_forwintersect_error(), rc);
+        if (nlhs > 1) plhs[1] = res; else mxDestroyArray(res);
+        return;
+    }
     if (nrhs < 2) ERR("nrhs", "Handle required.");
     dbat_handle *h = get_handle(prhs[1]);
     const mwSize n = (mwSize)dbat_num_unknowns(h), m = (mwSize)dbat_num_residuals(h);
