@@ -5,12 +5,12 @@ bundle, levenberg_marquardt, levenberg_marquardt_powell, gauss_newton_armijo, bu
 and the start-value steps that precede them in every demo, resect and forwintersect.
 All numerical work runs in libdbatgpu.so (hand-written sm_100a CUDA, include/dbat_gpu.h).
 """
-from .bundle import (Problem, bundle, bundle_cov, gauss_newton_armijo, levenberg_marquardt,
+from .bundle import (Problem, bundle, bundle_cov, gauss_markov, gauss_newton_armijo, levenberg_marquardt,
                      levenberg_marquardt_powell, make_termfun)
 from .photogrammetry import forwintersect, resect
 from .dbatstruct import (buildserialindices, buildweightmatrix, deserialize, new_struct,
                          serialize, seteoest_depend)
 
-__all__ = ['Problem', 'bundle', 'bundle_cov', 'gauss_newton_armijo', 'levenberg_marquardt',
+__all__ = ['Problem', 'bundle', 'bundle_cov', 'gauss_markov', 'gauss_newton_armijo', 'levenberg_marquardt',
            'levenberg_marquardt_powell', 'make_termfun', 'forwintersect', 'resect', 'buildserialindices',
            'buildweightmatrix', 'deserialize', 'new_struct', 'serialize', 'seteoest_depend']

@@ -283,6 +283,18 @@ def levenberg_marquardt_powell(resFun, vetoFun, x0, W, maxIter, termFun, doTrace
     return o.x, o.code, o.n, final, o.T, o.rr, o.damping, o.rhos, o.steps
 
 
+def gauss_markov(resFun, x0, W, maxIter, convTol, trace, sTest):
+    """gauss_markov.m:1: [x,code,n,final,T,rr]=gauss_markov(resFun,x0,W,maxIter,convTol,trace,sTest) -
+    undamped Gauss-Newton with the relative termination test norm(J p) <= convTol norm(r).  (Through
+    `bundle(s,'gm')` the reference passes a function handle as convTol, bundle.m:273, which fails; the
+    direct call works and is what this mirrors.)"""
+    P = _need_problem(resFun)
+    o = P.solve('gm', x0, maxIter, float(convTol), False, trace, sTest)
+    final = _Final(P, o.r_u, o.r_w, o.p)
+    P.last = o
+    return o.x, o.code, o.n, final, o.T, o.rr
+
+
 def gauss_newton_armijo(resFun, vetoFun, x0, W, maxIter, termFun, trace, sTest, mu, alphaMin):
     """gauss_newton_armijo.m:1-2: [x,code,n,final,T,rr,alphas]."""
     P = _need_problem(resFun)

@@ -989,6 +989,40 @@ static int solve_gna(dbat_handle* h, const dbat_opts* o, dbat_result* res, Trace
     return 0;
 }
 
+static int solve_gm(dbat_handle* h, const dbat_opts* o, dbat_result* res, TraceOut& T) {
+    // gauss_markov.m:35-110: undamped Gauss-Newton, p = (J'J)\(-J'r), x = x + p; terminates on
+    // norm(J p) <= convTol norm(r) (always the relative test, :86); no structural-rank test.
+    DevProblem& P = h->P;
+    const int nn = P.n;
+    int n = 0, code = 0, rc;
+    const int cap = o->maxIter + 2;
+    res->nDamping = 0; res->nRr = 0;
+    T.store_x(h, 0);                                                  // :42
+    while (true) {
+        if ((rc = eval_full(h))) return rc;                           // :58-61
+        const double rr = h->h_scal[SC_RR];
+        if (res->nRr < cap + 1) res->rr[res->nRr++] = std::sqrt(rr);  // :63
+        if (o->doTrace) printf("Gauss-Markov: iteration %d, residual norm=%.2g\n", n, std::sqrt(rr));
+        int sing = 0;
+        // :69.  Solved with Jacobi column scaling (the same step p = D (D N D)^-1 D (-g)): the pivot-ratio
+        // test that stands in for MATLAB's singular-matrix warning is only meaningful on the scaled system
+        if ((rc = solve_step(h, 0.0, true, h->d_p, &sing))) return rc;
+        if (o->singularTest && sing) { code = -2; break; }            // :71-79
+        double jp2 = 0, rjp = 0;
+        if ((rc = eval_jp(h, h->d_p, &jp2, &rjp))) return rc;
+        if (std::sqrt(jp2) <= o->convTol * std::sqrt(rr)) break;      // :86
+        n++;                                                          // :92
+        launch_axpy(1.0, h->d_p, h->d_x, h->d_t, nn, h->st);          // :95
+        std::swap(h->d_x, h->d_t);
+        h->params_valid = false; h->normal_valid = false;
+        T.store_x(h, n);                                              // :97-104
+        if (n > o->maxIter) { code = -1; break; }                     // :107-110
+    }
+    res->code = code; res->iters = n;
+    res->nTrace = std::min(n + 1, cap);
+    return 0;
+}
+
 __global__ void k_gradient(DevProblem P, const double* __restrict__ camG, double* __restrict__ g) {
     // g = J'r : shared IO from the summed Gram, EO from the per-image Grams, OP from the records
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1091,7 +1125,6 @@ static int solve_lmp(dbat_handle* h, const dbat_opts* o, dbat_result* res, Trace
 
 extern "C" int dbat_solve(dbat_handle* h, int method, const dbat_opts* opts, const double* x0, dbat_result* res) {
     if (!h || !opts || !x0 || !res || !res->x || !res->rr || !res->damping) return DBAT_E_BADARG;
-    if (method == DBAT_METHOD_GM) { h->err = "gauss_markov is broken via bundle() in the reference (bundle.m:273); not provided"; return DBAT_E_UNSUPPORTED; }
     const int nn = h->P.n;
     CK(cudaMemcpyAsync(h->d_x, x0, sizeof(double) * nn, cudaMemcpyHostToDevice, h->st));
     CK(cudaMemsetAsync(h->d_p, 0, sizeof(double) * nn, h->st));
@@ -1103,6 +1136,7 @@ extern "C" int dbat_solve(dbat_handle* h, int method, const dbat_opts* opts, con
     auto t0 = std::chrono::steady_clock::now();
     int rc;
     switch (method) {
+        case DBAT_METHOD_GM: rc = solve_gm(h, opts, res, T); break;
         case DBAT_METHOD_LM: rc = solve_lm(h, opts, res, T); break;
         case DBAT_METHOD_GNA: rc = solve_gna(h, opts, res, T); break;
         case DBAT_METHOD_LMP: rc = solve_lmp(h, opts, res, T); break;

@@ -149,6 +149,36 @@ def _scaled_gn(J, r):
     return D * q, sing, D, Js, Hs, gs, Jn, Jn2
 
 
+def gauss_markov(resFun, x0, W, maxIter, convTol, trace, sTest):
+    """gauss_markov.m:35-121: undamped Gauss-Newton.  (bundle.m:273 passes a function handle as convTol,
+    so the method is only usable by a direct call; it is restated as written.)"""
+    x = x0.copy()
+    T = [x0.copy()]
+    n = 0
+    code = 0
+    rr = []
+    R = np.sqrt(W)
+    while True:
+        s, K, r, J = _weighted(resFun, R, x, True)               # :58-61
+        rr.append(np.sqrt(r @ r))                                # :63
+        if trace:
+            print('Gauss-Markov: iteration %d, residual norm=%.2g' % (n, rr[-1]))
+        p, sing = _solve_spd((J.T @ J).tocsc(), -(J.T @ r))      # :69
+        if sTest and sing:                                       # :71-79
+            code = -2
+            break
+        if np.linalg.norm(J @ p) <= convTol * np.linalg.norm(r): # :86
+            break
+        n += 1                                                   # :92
+        x = x + p                                                # :95
+        T.append(x.copy())                                       # :97-104
+        if n > maxIter:                                          # :107-110
+            code = -1
+            break
+    final = NS(unweighted=NS(r=s, J=K), weighted=NS(r=r, J=J))   # :113-116
+    return x, code, n, final, np.array(T).T[:, :n + 1], np.array(rr)
+
+
 def gauss_newton_armijo(resFun, vetoFun, x0, W, maxIter, termFun, trace, sTest, mu, alphaMin):
     """gauss_newton_armijo.m:75-290."""
     x = x0.copy()

@@ -245,3 +245,24 @@ def test_camcal_script_pipeline_matches_golden_report():
     assert ok and iters == 8
     assert abs(E.res[0] - 28805.9) < 0.06 and abs(E.res[-1] - 98.556) < 6e-4
     assert abs(sigma0 - 1.6148) < 6e-5
+
+
+def test_gauss_markov_oracle_reaches_golden_solution():
+    """gauss_markov.m restated (undamped Gauss-Newton): from the start values of the camcal fixture it
+    reaches the same estimates as the golden GNA run."""
+    import copy
+    import numpy as np
+    from camcal_fixture import camcal_struct
+    from oracle.cameramodel import brown_euler_cam4
+    from oracle.dbatstruct import buildserialindices, buildweightmatrix, serialize
+    from oracle.lsa import gauss_markov
+    from oracle.bundle import bundle as obundle
+    s = camcal_struct('default', seed=1)
+    buildserialindices(s)
+    x0, W = serialize(s), buildweightmatrix(s)
+    x, code, n, final, T, rr = gauss_markov(lambda xx, j: brown_euler_cam4(xx, s, j), x0, W, 20, 1e-6, False, True)
+    assert code == 0 and T.shape[1] == n + 1 and len(rr) == n + 1
+    s2, ok, iters, s0, E = obundle(copy.deepcopy(s), 'gna')
+    assert ok
+    np.testing.assert_allclose(x, E.x, rtol=1e-6, atol=1e-8)
+    assert abs(rr[-1] - 98.556) < 6e-4
