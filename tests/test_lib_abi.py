@@ -27,14 +27,15 @@ def test_struct_layouts_match_header():
     import tempfile
     from dbat_b200 import _lib
     import ctypes
-    src = '#include <stdio.h>\n#include "dbat_gpu.h"\nint main(){printf("%zu %zu %zu\\n", sizeof(dbat_problem_desc), sizeof(dbat_opts), sizeof(dbat_result));return 0;}\n'
+    src = '#include <stdio.h>\n#include "dbat_gpu.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(dbat_problem_desc), sizeof(dbat_opts), sizeof(dbat_result), sizeof(dbat_fwi_desc), sizeof(dbat_resect_desc));return 0;}\n'
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, 't.c')
         open(c, 'w').write(src)
         exe = os.path.join(d, 't')
         subprocess.check_call(['gcc', '-I', os.path.join(ROOT, 'include'), c, '-o', exe])
         sizes = [int(v) for v in subprocess.check_output([exe]).split()]
-    assert sizes == [ctypes.sizeof(_lib.ProblemDesc), ctypes.sizeof(_lib.Opts), ctypes.sizeof(_lib.Result)]
+    assert sizes == [ctypes.sizeof(_lib.ProblemDesc), ctypes.sizeof(_lib.Opts), ctypes.sizeof(_lib.Result),
+                     ctypes.sizeof(_lib.FwiDesc), ctypes.sizeof(_lib.ResectDesc)]
 
 
 def test_no_cpu_fallback_without_device(built_lib):
