@@ -141,17 +141,17 @@ def load_pm_export(path, imSz=None):
         inner = np.array([float(v) for v in lines[k + 4].split()[1:]])
         images.append({'id': int(tok[0]), 'name': tok[1], 'outer': outer, 'inner': inner})
         k += 6
-    def table(k):
-        while k < len(lines) and not lines[k].strip():
-            k += 1
+    def table(k, ncol):
+        """Rows up to the next blank line (loadpm.m:230-333); an empty section is just its blank line."""
         rows = []
         while k < len(lines) and lines[k].strip():
             rows.append([float(v) for v in lines[k].split()])
             k += 1
-        return np.array(rows), k
-    ctrl, k = table(k)
-    obj, k = table(k)
-    mark, k = table(k)
+        return (np.array(rows) if rows else np.zeros((0, ncol))), k + 1
+    k += 1                                                 # blank line that ends the image blocks
+    ctrl, k = table(k, 7)
+    obj, k = table(k, 7)
+    mark, k = table(k, 6)
     return {'job': job, 'images': images, 'ctrlPts': ctrl, 'objPts': obj, 'markPts': mark}
 
 
@@ -267,4 +267,56 @@ def stpierre_struct(root, imSz=(6912, 5212)):
         s.prior.OP.std[:, j] = r[4:7]
         s.prior.OP.use[:, j] = True
         s.prior.OP.isCtrl[j] = True
+    return s
+
+
+def camcal_pm_struct(pmfile, cptfile=None, focal=7.3, keep_loaded=False):
+    """The PhotoModeler-export camcal demos (`camcaldemo.m:30-98`, `camcaldemo2.m`, `camcaldemo_1ray.m`,
+    `camcaldemo_missing_obs.m`; with keep_loaded `camcaldemo_no_datum.m:36-52`): `loadpm` +
+    `prob2dbatstruct` (`misc/prob2dbatstruct.m:198-420`), distortion model 3, `setcamvals(s0,'default',7.3)`
+    (`setcamvals.m:40-48`: cc = 7.3, pp at the sensor centre, everything else 0), everything but skew
+    estimated.  Default (the demos with control points): EO and non-control OP cleared (NaN) - start
+    values come from `resect` / `forwintersect` - and the points with id > 1000 fixed at the coordinates
+    of `ref/camcal-fixed.txt` (`setcpt`, std 0).  keep_loaded: EO/OP start values as loaded, nothing fixed."""
+    prob = load_pm_export(pmfile)
+    nImg = len(prob['images'])
+    ids = np.unique(np.concatenate([prob['ctrlPts'][:, 0], prob['objPts'][:, 0]])).astype(int)
+    op_of = {v: i for i, v in enumerate(ids)}
+    nK, nP = 3, 2
+    inner = prob['job']['defCam']
+    imSz = prob['job']['imSz']
+    ss = inner[3:5]
+    px = ss / imSz
+    pxSize = np.array([[px[1]], [px[1]]])                  # prob2dbatstruct.m:238-242
+    IO = np.zeros((5 + nK + nP, nImg))
+    IO[0] = focal
+    IO[1], IO[2] = 0.5 * ss[0], -0.5 * ss[1]               # setcamvals.m:44
+    EO = np.full((6, nImg), np.nan)
+    OP = np.full((3, len(ids)), np.nan)
+    if keep_loaded:
+        for i, im in enumerate(prob['images']):
+            EO[0:3, i] = im['outer'][0:3]
+            EO[3:6, i] = np.deg2rad(im['outer'][[5, 4, 3]])
+        for r in np.vstack([prob['objPts'], prob['ctrlPts']]) if len(prob['ctrlPts']) else prob['objPts']:
+            OP[:, op_of[int(r[0])]] = r[1:4]
+    mk = prob['markPts']
+    keep = np.array([int(r[1]) in op_of for r in mk])
+    mk = mk[keep]
+    mk = mk[np.lexsort((mk[:, 1], mk[:, 0]))]
+    mstd = mk[:, 4:6].copy()
+    if np.any(mstd == 0):                                  # prob2dbatstruct.m:367-373
+        mstd[:] = 1.0
+    s = new_struct(IO, EO, OP, mk[:, 2:4].T, mk[:, 0].astype(int), np.array([op_of[int(v)] for v in mk[:, 1]]),
+                   pxSize, imSz[:, None], 3, nK, nP, mstd.T)
+    s.OP.id = ids
+    s.bundle.est.IO[:] = True
+    s.bundle.est.IO[4, :] = False
+    s.bundle.est.EO[:] = True
+    s.bundle.est.OP[:] = True
+    s.prior.OP.isCtrl = ids > 1000                         # camcaldemo.m:74-78
+    if not keep_loaded:
+        cp = {int(r[0]): [float(v) for v in r[2:5]] for r in load_table(cptfile)}
+        for j in np.flatnonzero(s.prior.OP.isCtrl):
+            s.OP.val[:, j] = cp[int(ids[j])]
+            s.bundle.est.OP[:, j] = False
     return s

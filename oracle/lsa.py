@@ -50,10 +50,29 @@ def _solve_spd(A, b):
             return np.full(len(b), np.nan), True
     if not np.all(np.isfinite(x)):
         return x, True
-    # MATLAB warns (singular / nearlySingular) when rcond < eps: cheap estimate from U's diagonal
+    # MATLAB warns (singular / nearlySingular) when its reciprocal condition estimate is below eps.
+    # Cheap screen on U's diagonal first; in the suspicious band the 1-norm estimate itself
+    # (Hager/Higham, what rcond/condest do) decides.  Pinned by camcal-dbatreport-no-datum.txt
+    # (datum-free network: code -2 at iteration 0).
+    eps = np.finfo(float).eps
     d = np.abs(lu.U.diagonal())
-    if d.min() <= np.finfo(float).eps * d.max() * 1e-2:
+    ratio = d.min() / d.max()
+    if ratio <= eps * 1e-2:
         return x, True
+    if ratio < 1e-12:
+        n = A.shape[0]
+        if perm is not None:
+            def solve(v):
+                out = np.empty(n)
+                out[perm] = lu.solve(np.asarray(v, dtype=float).reshape(-1)[perm])
+                return out
+        else:
+            def solve(v):
+                return lu.solve(np.asarray(v, dtype=float).reshape(-1))
+        Ainv = spla.LinearOperator((n, n), matvec=solve, rmatvec=solve, dtype=float)
+        rcond = 1.0 / (spla.onenormest(A) * spla.onenormest(Ainv))
+        if rcond < eps:
+            return x, True
     return x, False
 
 

@@ -34,6 +34,17 @@ FILES = {
     'stpierre': [
         'data/hamburg2017/stpierre/pmexports/C5_reduced-pmexport.txt',
     ],
+    'camcalpm': [
+        'data/dbat/pmexports/camcal-pmexport.txt',
+        'data/dbat/pmexports/camcal-pmexport-1ray.txt',
+        'data/dbat/pmexports/camcal-pmexport-missing-obs.txt',
+        'data/dbat/pmexports/camcal-pmexport5.txt',
+        'data/dbat/ref/camcal-fixed.txt',
+        'data/dbat/dbatexports/camcal-dbatreport-1ray.txt',
+        'data/dbat/dbatexports/camcal-dbatreport-missing-obs.txt',
+        'data/dbat/dbatexports/camcal-dbatreport-no-datum.txt',
+        'data/dbat/dbatexports/camcal-dbatreport5.txt',
+    ],
     'dbatexports': [
         'data/dbat/dbatexports/camcal-dbatreport.txt',
         'data/dbat/dbatexports/camcal-dbatreport-model2.txt',
@@ -54,7 +65,7 @@ def main():
             rel = f.split(sub + '/', 1)[1] if sub + '/' in f else os.path.basename(f)
             if sub == 'prague2016cam':
                 rel = f.split('data/prague2016/cam/', 1)[1]
-            if sub == 'stpierre':
+            if sub in ('stpierre', 'camcalpm'):
                 rel = os.path.basename(f)
             dst = os.path.join(HERE, sub, rel)
             os.makedirs(os.path.dirname(dst), exist_ok=True)

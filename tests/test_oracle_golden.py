@@ -260,9 +260,73 @@ def test_gauss_markov_oracle_reaches_golden_solution():
     s = camcal_struct('default', seed=1)
     buildserialindices(s)
     x0, W = serialize(s), buildweightmatrix(s)
-    x, code, n, final, T, rr = gauss_markov(lambda xx, j: brown_euler_cam4(xx, s, j), x0, W, 20, 1e-6, False, True)
+    x, code, n, final, T, rr = gauss_markov(lambda xx, j: brown_euler_cam4(xx, s, j), x0, W, 20, 1e-6, False, False)
     assert code == 0 and T.shape[1] == n + 1 and len(rr) == n + 1
     s2, ok, iters, s0, E = obundle(copy.deepcopy(s), 'gna')
     assert ok
     np.testing.assert_allclose(x, E.x, rtol=1e-6, atol=1e-8)
     assert abs(rr[-1] - 98.556) < 6e-4
+
+
+@pytest.mark.parametrize('pm,iters,first,last,sigma0,nparams', [
+    ('camcal-pmexport.txt', 9, 30873.9, 98.556, 1.6148, 423),
+    ('camcal-pmexport5.txt', 6, 254.75, 18.4099, 2.80749, 57)])
+def test_camcal_pm_demo_pipeline_matches_golden_reports(pm, iters, first, last, sigma0, nparams):
+    """camcaldemo.m / camcaldemo2.m end to end (loadpm, prob2dbatstruct, default camera 7.3 mm, fixed
+    control points, resect, forwintersect, bundle GNA) against data/dbat/dbatexports/camcal-dbatreport.txt
+    and camcal-dbatreport5.txt: iteration count, first and last error, sigma0, number of parameters."""
+    import copy, os
+    import numpy as np
+    from oracle.loaders import camcal_pm_struct
+    from oracle.photogrammetry import resect, forwintersect
+    from oracle.bundle import bundle as obundle
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'camcalpm')
+    s = camcal_pm_struct(os.path.join(G, pm), os.path.join(G, 'camcal-fixed.txt'))
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, _, fail = resect(s, 'all', cpId, 1, 0, cpId)
+    assert not fail
+    s2, _, _ = forwintersect(s1, 'all', True)
+    s3, ok, it, s0, E = obundle(copy.deepcopy(s2), 'gna')
+    assert ok and it == iters and E.numParams == nparams
+    assert abs(E.res[0] - first) < 0.6 * 10 ** (np.floor(np.log10(first)) - 5)      # 6 printed digits
+    assert abs(E.res[-1] - last) < 0.6 * 10 ** (np.floor(np.log10(last)) - 5)
+    assert abs(s0 - sigma0) < 0.6 * 10 ** (np.floor(np.log10(sigma0)) - 5)
+
+
+@pytest.mark.parametrize('pm,code,first,sigma0', [
+    ('camcal-pmexport-missing-obs.txt', -4, 30118.6, 499.142),
+    ('camcal-pmexport-1ray.txt', -4, None, None)])
+def test_camcal_pm_failure_demos_match_golden_reports(pm, code, first, sigma0):
+    """camcaldemo_missing_obs.m / camcaldemo_1ray.m: the reference's reports record failure code -4
+    (structurally rank-deficient normal matrix) at iteration 0, with first error 30118.6 / sigma0 499.142
+    for the missing-observations project and NaN for the single-ray one."""
+    import copy, os
+    import numpy as np
+    from oracle.loaders import camcal_pm_struct
+    from oracle.photogrammetry import resect, forwintersect
+    from oracle.bundle import bundle as obundle
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'camcalpm')
+    s = camcal_pm_struct(os.path.join(G, pm), os.path.join(G, 'camcal-fixed.txt'))
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, _, fail = resect(s, 'all', cpId, 1, 0, cpId)
+    s2, _, _ = forwintersect(s1, 'all', True)
+    s3, ok, it, s0, E = obundle(copy.deepcopy(s2), 'gna')
+    assert not ok and it == 0 and E.code == code and E.numParams == 423
+    if first is None:
+        assert np.isnan(s0) and np.isnan(E.res[0])
+    else:
+        assert abs(E.res[0] - first) < 0.06 and abs(s0 - sigma0) < 6e-4
+
+
+def test_camcal_no_datum_demo_matches_golden_report():
+    """camcaldemo_no_datum.m: start values as loaded, no control points (435 parameters, 7-dimensional
+    gauge freedom).  The reference reports code -2 (singular normal matrix: MATLAB's rcond warning) at
+    iteration 0, first error 15772.8, sigma0 258.848."""
+    import copy, os
+    from oracle.loaders import camcal_pm_struct
+    from oracle.bundle import bundle as obundle
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'camcalpm')
+    s = camcal_pm_struct(os.path.join(G, 'camcal-pmexport.txt'), None, keep_loaded=True)
+    s3, ok, it, s0, E = obundle(copy.deepcopy(s), 'gna')
+    assert not ok and it == 0 and E.code == -2 and E.numParams == 435
+    assert abs(E.res[0] - 15772.8) < 0.06 and abs(s0 - 258.848) < 6e-4
