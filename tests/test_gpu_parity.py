@@ -573,3 +573,40 @@ def test_gauss_markov_direct_call(case):
     np.testing.assert_allclose(T, To, rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(final.weighted.r, finalo.weighted.r, rtol=1e-9, atol=1e-11)
     P.close()
+
+
+CAMCALPM = os.path.join(os.path.dirname(GOLD), 'camcalpm')
+
+
+@pytest.mark.parametrize('pm,iters,first,last,sigma0,nparams', [
+    ('camcal-pmexport.txt', 9, 30873.9, 98.556, 1.6148, 423),
+    ('camcal-pmexport5.txt', 6, 254.75, 18.4099, 2.80749, 57)])
+def test_camcal_pm_demo_pipeline_on_device(pm, iters, first, last, sigma0, nparams):
+    """camcaldemo.m / camcaldemo2.m end to end on the device (resect, forwintersect, bundle GNA) against
+    the reference's reports: iteration count, last error, sigma0, number of parameters to the printed
+    digits; the first error (a function of the start values only) to 1e-5: the Grunert quartic of image 21
+    has a nearly double root, where the device's polynomial solver and MATLAB's eigenvalue-based `roots`
+    (which the restatement reproduces: 30873.87) differ by 4e-6 in the resected pose."""
+    s = loaders.camcal_pm_struct(os.path.join(CAMCALPM, pm), os.path.join(CAMCALPM, 'camcal-fixed.txt'))
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, _, fail = dbat_b200.resect(s, 'all', cpId, 1, 0, cpId)
+    assert not fail
+    s2, _, _ = dbat_b200.forwintersect(s1, 'all', True)
+    s3, ok, it, s0, E = dbat_b200.bundle(s2, 'gna')
+    assert ok and it == iters and E.numParams == nparams
+    assert abs(E.res[0] - first) < 1e-5 * first
+    assert abs(E.res[-1] - last) < 0.6 * 10 ** (np.floor(np.log10(last)) - 5)
+    assert abs(s0 - sigma0) < 0.6 * 10 ** (np.floor(np.log10(sigma0)) - 5)
+
+
+def test_camcal_missing_obs_demo_on_device():
+    """camcaldemo_missing_obs.m on the device: failure code -4 at iteration 0, first error 30118.6,
+    sigma0 499.142 as in the reference's report."""
+    s = loaders.camcal_pm_struct(os.path.join(CAMCALPM, 'camcal-pmexport-missing-obs.txt'),
+                                 os.path.join(CAMCALPM, 'camcal-fixed.txt'))
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, _, fail = dbat_b200.resect(s, 'all', cpId, 1, 0, cpId)
+    s2, _, _ = dbat_b200.forwintersect(s1, 'all', True)
+    s3, ok, it, s0, E = dbat_b200.bundle(s2, 'gna')
+    assert not ok and it == 0 and E.code == -4 and E.numParams == 423
+    assert abs(E.res[0] - 30118.6) < 1e-5 * 30118.6 and abs(s0 - 499.142) < 1e-5 * 499.142
