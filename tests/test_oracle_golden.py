@@ -330,3 +330,28 @@ def test_camcal_no_datum_demo_matches_golden_report():
     s3, ok, it, s0, E = obundle(copy.deepcopy(s), 'gna')
     assert not ok and it == 0 and E.code == -2 and E.numParams == 435
     assert abs(E.res[0] - 15772.8) < 0.06 and abs(s0 - 258.848) < 6e-4
+
+
+@pytest.mark.parametrize('stub,sigma0,last,nparams', [('fixed', 1.78095, 108.827, 414), ('weighted', 1.60984, 98.3715, 426)])
+def test_prague2016_cam_demo_pipeline_matches_golden_reports(stub, sigma0, last, nparams):
+    """prague2016_pm('c1'|'c2') end to end as the demo runs it (`prague2016_pm.m:100-215`): fixed
+    camera, control points fixed / weighted, EO and OP cleared, start values by resect + forwintersect,
+    GNA.  The reference's reports (`{fixed,weighted}-{no,with}-orient-dbatreport.txt`, all four agree)
+    give 3 iterations, first error 460.624 (a function of the start values only), last error, sigma0 and
+    the parameter count."""
+    import copy, os
+    import numpy as np
+    from oracle.loaders import prague_cam_struct
+    from oracle.photogrammetry import resect, forwintersect
+    from oracle.bundle import bundle as obundle
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'prague2016cam')
+    s = prague_cam_struct(root, stub)
+    s.EO.val[:] = np.nan                                   # cleareo / clearop (prague2016_pm.m:194-195)
+    s.OP.val[:, ~s.prior.OP.isCtrl] = np.nan
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, _, fail = resect(s, 'all', cpId, 1, 0, cpId)
+    assert not fail
+    s2, _, _ = forwintersect(s1, 'all', True)
+    s3, ok, it, s0, E = obundle(copy.deepcopy(s2), 'gna')
+    assert ok and it == 3 and E.numParams == nparams
+    assert abs(E.res[0] - 460.624) < 6e-4 and abs(E.res[-1] - last) < 6e-4 and abs(s0 - sigma0) < 6e-6
