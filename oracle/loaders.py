@@ -152,10 +152,22 @@ def load_pm_export(path, imSz=None):
     ctrl, k = table(k, 7)
     obj, k = table(k, 7)
     mark, k = table(k, 6)
+    # normal and "smart" points numbered from overlapping ranges: shift the smart ids above the
+    # normal ones (loadpm.m:385-404; smart mark points are the ones exported with zero std)
+    if len(mark) and len(obj):
+        smart = np.all(mark[:, 4:6] == 0, axis=1)
+        normId, smartId = np.unique(mark[~smart, 1]), np.unique(mark[smart, 1])
+        split = np.flatnonzero(np.diff(obj[:, 0]) < 0)
+        if len(split) and len(normId) and len(smartId):
+            shift = normId.max() + 1 - smartId.min()
+            mark[smart, 1] += shift
+            isSmartObj = np.isin(obj[:, 0], smartId)
+            isSmartObj[:split[0] + 1] = False
+            obj[isSmartObj, 0] += shift
     return {'job': job, 'images': images, 'ctrlPts': ctrl, 'objPts': obj, 'markPts': mark}
 
 
-def prague_cam_struct(root, stub):
+def prague_cam_struct(root, stub, cpfile=None):
     """The prague2016 'cam' projects C1 ('fixed') / C2 ('weighted') as `prague2016_pm.m:100-215` sets
     them up: `prob2dbatstruct` (`misc/prob2dbatstruct.m:198-420`: model 1, square pixels from the sensor
     height, py/K/P sign flips, angles = outer([6,5,4]) deg), fixed camera (`setcamest(s,'not','all')`),
@@ -189,13 +201,16 @@ def prague_cam_struct(root, stub):
     mk = prob['markPts']
     keep = np.array([int(r[1]) in op_of for r in mk])
     mk = mk[keep]
+    mstd = mk[:, 4:6].copy()
+    if np.any(mstd == 0):                                  # prob2dbatstruct.m:367-373: any zero => all 1 px
+        mstd[:] = 1.0
     s = new_struct(IO, EO, OP, mk[:, 2:4].T, mk[:, 0].astype(int), np.array([op_of[int(v)] for v in mk[:, 1]]),
-                   pxSize, imSz[:, None], 1, nK, nP, mk[:, 4:6].T)
+                   pxSize, imSz[:, None], 1, nK, nP, mstd.T)
     s.OP.id = ids
     s.bundle.est.IO[:] = False
     s.bundle.est.EO[:] = True
     s.bundle.est.OP[:] = True
-    cp = load_table(os.path.join(root, 'ref', 'ctrlpts-%s.txt' % stub))
+    cp = load_table(os.path.join(root, 'ref', cpfile or 'ctrlpts-%s.txt' % stub))
     cp_id = [int(r[0]) for r in cp]
     cp_pos = np.array([[float(v) for v in r[2:5]] for r in cp]).T
     cp_std = np.array([[float(v) for v in r[5:8]] if len(r) >= 8 else [0.0, 0.0, 0.0] for r in cp]).T

@@ -45,6 +45,18 @@ FILES = {
         'data/dbat/dbatexports/camcal-dbatreport-no-datum.txt',
         'data/dbat/dbatexports/camcal-dbatreport5.txt',
     ],
+    'prague2016sxb': [
+        'data/prague2016/sxb/pmexports/f-op0-no-orient-pmexport.txt',
+        'data/prague2016/sxb/pmexports/w-op0-no-orient-pmexport.txt',
+        'data/prague2016/sxb/pmexports/w-op1-no-orient-pmexport.txt',
+        'data/prague2016/sxb/pmexports/wsmart-no-orient-pmexport.txt',
+        'data/prague2016/sxb/ref/ctrlpts-fixed.txt',
+        'data/prague2016/sxb/ref/ctrlpts-weighted.txt',
+        'data/prague2016/sxb/dbatexports/f-op0-no-orient-dbatreport.txt',
+        'data/prague2016/sxb/dbatexports/w-op0-no-orient-dbatreport.txt',
+        'data/prague2016/sxb/dbatexports/w-op1-no-orient-dbatreport.txt',
+        'data/prague2016/sxb/dbatexports/wsmart-no-orient-dbatreport.txt',
+    ],
     'dbatexports': [
         'data/dbat/dbatexports/camcal-dbatreport.txt',
         'data/dbat/dbatexports/camcal-dbatreport-model2.txt',
@@ -65,6 +77,8 @@ def main():
             rel = f.split(sub + '/', 1)[1] if sub + '/' in f else os.path.basename(f)
             if sub == 'prague2016cam':
                 rel = f.split('data/prague2016/cam/', 1)[1]
+            if sub == 'prague2016sxb':
+                rel = f.split('data/prague2016/sxb/', 1)[1]
             if sub in ('stpierre', 'camcalpm'):
                 rel = os.path.basename(f)
             dst = os.path.join(HERE, sub, rel)

@@ -355,3 +355,33 @@ def test_prague2016_cam_demo_pipeline_matches_golden_reports(stub, sigma0, last,
     s3, ok, it, s0, E = obundle(copy.deepcopy(s2), 'gna')
     assert ok and it == 3 and E.numParams == nparams
     assert abs(E.res[0] - 460.624) < 6e-4 and abs(E.res[-1] - last) < 6e-4 and abs(s0 - sigma0) < 6e-6
+
+
+@pytest.mark.parametrize('stub,cps,first,last,sigma0,nparams', [
+    ('f-op0', 'fixed', 10.4471, 8.33522, 1.0419, 30),
+    ('w-op0', 'weighted', 10.4471, 7.87923, 0.984904, 78),
+    ('w-op1', 'weighted', 10.6748, 8.01901, 0.965375, 81),
+    ('wsmart', 'weighted', 60.1091, 38.2456, 1.07447, 1173)])
+def test_prague2016_sxb_demo_pipelines_match_golden_reports(stub, cps, first, last, sigma0, nparams):
+    """prague2016_pm('s1'..'s4') (`prague2016_pm.m`, StereoBox data: 5 images; fixed or weighted control
+    points; s3 adds a check point, s4 1100 "smart" points whose zero export sigmas make prob2dbatstruct
+    fall back to 1 px for every image point): resect + forwintersect start, GNA.  Reports
+    `data/prague2016/sxb/dbatexports/<stub>-no-orient-dbatreport.txt`: 4 iterations, first / last error,
+    sigma0, parameter count."""
+    import copy, os
+    import numpy as np
+    from oracle.loaders import prague_cam_struct
+    from oracle.photogrammetry import resect, forwintersect
+    from oracle.bundle import bundle as obundle
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'prague2016sxb')
+    s = prague_cam_struct(root, stub, 'ctrlpts-%s.txt' % cps)
+    s.EO.val[:] = np.nan
+    s.OP.val[:, ~s.prior.OP.isCtrl] = np.nan
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, _, fail = resect(s, 'all', cpId, 1, 0, cpId)
+    assert not fail
+    s2, _, _ = forwintersect(s1, 'all', True)
+    s3, ok, it, s0, E = obundle(copy.deepcopy(s2), 'gna')
+    assert ok and it == 4 and E.numParams == nparams
+    tol = lambda v: 0.6 * 10 ** (np.floor(np.log10(v)) - 5)
+    assert abs(E.res[0] - first) < tol(first) and abs(E.res[-1] - last) < tol(last) and abs(s0 - sigma0) < tol(sigma0)
