@@ -167,7 +167,7 @@ def load_pm_export(path, imSz=None):
     return {'job': job, 'images': images, 'ctrlPts': ctrl, 'objPts': obj, 'markPts': mark}
 
 
-def prague_cam_struct(root, stub, cpfile=None):
+def prague_cam_struct(root, stub, cpfile=None, shift_cp=True, orient='no'):
     """The prague2016 'cam' projects C1 ('fixed') / C2 ('weighted') as `prague2016_pm.m:100-215` sets
     them up: `prob2dbatstruct` (`misc/prob2dbatstruct.m:198-420`: model 1, square pixels from the sensor
     height, py/K/P sign flips, angles = outer([6,5,4]) deg), fixed camera (`setcamest(s,'not','all')`),
@@ -176,7 +176,7 @@ def prague_cam_struct(root, stub, cpfile=None):
     values are PhotoModeler's own estimates from the export (the demo recomputes them by resection /
     intersection; the converged result does not depend on that)."""
     import os
-    prob = load_pm_export(os.path.join(root, 'pmexports', '%s-no-orient-pmexport.txt' % stub))
+    prob = load_pm_export(os.path.join(root, 'pmexports', '%s-%s-orient-pmexport.txt' % (stub, orient)))
     nImg = len(prob['images'])
     ids = np.unique(np.concatenate([prob['ctrlPts'][:, 0], prob['objPts'][:, 0]])).astype(int)
     op_of = {v: i for i, v in enumerate(ids)}
@@ -215,7 +215,8 @@ def prague_cam_struct(root, stub, cpfile=None):
     cp_pos = np.array([[float(v) for v in r[2:5]] for r in cp]).T
     cp_std = np.array([[float(v) for v in r[5:8]] if len(r) >= 8 else [0.0, 0.0, 0.0] for r in cp]).T
     pm_pos = np.array([prob['ctrlPts'][prob['ctrlPts'][:, 0] == i, 1:4][0] for i in cp_id]).T
-    cp_pos = cp_pos + np.mean(pm_pos - cp_pos, axis=1, keepdims=True)     # prague2016_pm.m:174-190
+    if shift_cp:                                                           # sxb_prior_eo.m sets them unshifted
+        cp_pos = cp_pos + np.mean(pm_pos - cp_pos, axis=1, keepdims=True)  # prague2016_pm.m:174-190
     s.prior.OP.isCtrl = np.zeros(len(ids), bool)
     for k, i in enumerate(cp_id):                                          # setcpt.m
         j = op_of[i]
@@ -334,4 +335,17 @@ def camcal_pm_struct(pmfile, cptfile=None, focal=7.3, keep_loaded=False):
         for j in np.flatnonzero(s.prior.OP.isCtrl):
             s.OP.val[:, j] = cp[int(ids[j])]
             s.bundle.est.OP[:, j] = False
+    return s
+
+
+def set_prior_eo_positions(s, prob, path):
+    """`legacyloadeotable` + `matcheo` (by image label) + `setprioreo.m:20-42` for a table
+    `label,X,Y,Z,std`: prior observations of the camera positions."""
+    names = [im['name'].replace('\\', '/').split('/')[-1].lower() for im in prob['images']]
+    for r in load_table(path):
+        i = names.index(r[0].lower())
+        s.prior.EO.val[0:3, i] = [float(v) for v in r[1:4]]
+        s.prior.EO.std[0:3, i] = float(r[4])
+        s.prior.EO.use[0:3, i] = float(r[4]) != 0
+        s.bundle.est.EO[0:3, i] = float(r[4]) != 0
     return s

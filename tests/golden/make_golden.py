@@ -50,6 +50,10 @@ FILES = {
         'data/prague2016/sxb/pmexports/w-op0-no-orient-pmexport.txt',
         'data/prague2016/sxb/pmexports/w-op1-no-orient-pmexport.txt',
         'data/prague2016/sxb/pmexports/wsmart-no-orient-pmexport.txt',
+        'data/prague2016/sxb/pmexports/wsmart-with-orient-pmexport.txt',
+        'data/prague2016/sxb/ref/fake-camera-positions.txt',
+        'data/prague2016/sxb/dbatexports/sxb-prior-eo-dbatreport.txt',
+        'data/prague2016/sxb/dbatexports/sxb-no-prior-eo-dbatreport.txt',
         'data/prague2016/sxb/ref/ctrlpts-fixed.txt',
         'data/prague2016/sxb/ref/ctrlpts-weighted.txt',
         'data/prague2016/sxb/dbatexports/f-op0-no-orient-dbatreport.txt',

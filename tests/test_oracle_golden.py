@@ -385,3 +385,34 @@ def test_prague2016_sxb_demo_pipelines_match_golden_reports(stub, cps, first, la
     assert ok and it == 4 and E.numParams == nparams
     tol = lambda v: 0.6 * 10 ** (np.floor(np.log10(v)) - 5)
     assert abs(E.res[0] - first) < tol(first) and abs(E.res[-1] - last) < tol(last) and abs(s0 - sigma0) < tol(sigma0)
+
+
+@pytest.mark.parametrize('use_prior,iters,first,last,sigma0,nobs', [
+    (True, 3, 86.8008, 38.2458, 1.06942, 2452), (False, 4, 60.1122, 38.2456, 1.07447, 2440)])
+def test_sxb_prior_eo_demo_matches_golden_reports(use_prior, iters, first, last, sigma0, nobs):
+    """sxb_prior_eo.m (`code/demo/sxb_prior_eo.m:30-100`): the StereoBox project with smart points,
+    unshifted weighted control points and - with use_prior - prior observations of four camera positions
+    (`ref/fake-camera-positions.txt`, sigma 5 cm; `setprioreo.m`).  Reports `sxb-prior-eo-dbatreport.txt`
+    / `sxb-no-prior-eo-dbatreport.txt`: iterations, last error, sigma0 and the observation count (12 EO
+    observations) to the printed digits; the first error to 2e-5 (the resection start values of this
+    project sit on an ill-conditioned quartic, cf. the device test of the camcal demo)."""
+    import copy, os
+    import numpy as np
+    from oracle.loaders import prague_cam_struct, load_pm_export, set_prior_eo_positions
+    from oracle.photogrammetry import resect, forwintersect
+    from oracle.bundle import bundle as obundle
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'prague2016sxb')
+    s = prague_cam_struct(root, 'wsmart', 'ctrlpts-weighted.txt', shift_cp=False, orient='with')
+    if use_prior:
+        prob = load_pm_export(os.path.join(root, 'pmexports', 'wsmart-with-orient-pmexport.txt'))
+        set_prior_eo_positions(s, prob, os.path.join(root, 'ref', 'fake-camera-positions.txt'))
+    s.EO.val[:] = np.nan
+    s.OP.val[:, ~s.prior.OP.isCtrl] = np.nan
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, _, fail = resect(s, 'all', cpId, 1, 0, cpId)
+    assert not fail
+    s2, _, _ = forwintersect(s1, 'all', True)
+    s3, ok, it, s0, E = obundle(copy.deepcopy(s2), 'gna')
+    assert ok and it == iters and E.numParams == 1173 and len(E.final.weighted.r) == nobs
+    assert abs(E.res[0] - first) < 2e-5 * first
+    assert abs(E.res[-1] - last) < 6e-4 and abs(s0 - sigma0) < 6e-6
