@@ -15,7 +15,8 @@ import numpy as np
 import scipy.sparse as sp
 
 from . import _lib
-from .dbatstruct import buildserialindices, buildweightmatrix, deserialize, serialize
+from .dbatstruct import (buildserialindices, buildweightmatrix, column_matching, deserialize, paramtypes,
+                         serialize)
 
 _lin = lambda a: np.asarray(a).reshape(-1, order='F')
 
@@ -398,7 +399,22 @@ def bundle(s, *varargin):
     s0 = float(np.sqrt((r @ r) / dof))
     s.post.sigmas = s0 * s.IP.sigmas
     E.numObs, E.numParams, E.redundancy, E.s0, E.sigmas = len(r), len(x), dof, s0, s.post.sigmas
+    E.paramTypes = paramtypes(s)                                       # bundle.m:162,368
+    E.weakness = structural_weakness(final.weighted.J, E.paramTypes) if code == -4 \
+        else NS(structural=None, numerical=NS(rank=len(x), deficiency=0))
     return s, ok, iters, s0, E
+
+
+def structural_weakness(J, paramTypes):
+    """bundle.m:431-446: on code -4 record which parameters a maximum matching of the Jacobian's
+    pattern leaves out (`dmperm`), the structural rank and its deficiency; the numerical rank is
+    marked unchecked.  (The numerical null-space analysis of code -2, bundle.m:373-428, needs `eigs`
+    on the scaled Jacobian and is not provided.)"""
+    dm = column_matching(J)
+    rank = int(np.count_nonzero(dm))
+    return NS(structural=NS(dmperm=dm, rank=rank, deficiency=len(dm) - rank,
+                            suspectedParams=list(np.asarray(paramTypes, dtype=object)[dm == 0])),
+              numerical=NS(rank=float('nan'), deficiency=float('nan')))
 
 
 def _blockdiag(blocks):

@@ -167,3 +167,94 @@ def seteoest_depend(s, camNo=0):
     s.bundle.est.EO[:, camNo] = False
     s.bundle.est.EO[i, j] = False
     return s
+
+
+def buildparamtypes(s):
+    """buildparamtypes.m:22-104 for one IO block: the type string of every IO, EO and OP element
+    ('cc', 'K1', 'EX-3', 'om-21(7)', 'OX-12/13', control points 'CX-..', check points 'HX-..')."""
+    NC, nImg = s.IO.val.shape
+    nK, nP = int(s.IO.model.nK), int(s.IO.model.nP)
+    io = ['cc', 'px', 'py', 'as', 'sk'] + ['K%d' % (k + 1) for k in range(nK)] + ['P%d' % (k + 1) for k in range(nP)]
+    IOt = np.array([io] * nImg, dtype=object).T
+    eo_id = getattr(s.EO, 'id', None)
+    seq = np.arange(1, nImg + 1)
+    with_id = eo_id is not None and nImg > 1 and bool(np.any(np.asarray(eo_id) != seq))
+    EOt = np.empty((6, nImg), dtype=object)
+    for i in range(nImg):
+        tail = '' if nImg == 1 else '-%d' % (i + 1) + ('(%d)' % eo_id[i] if with_id else '')
+        for k, nm in enumerate(('EX', 'EY', 'EZ', 'om', 'ph', 'ka')):
+            EOt[k, i] = nm + tail
+    nOP = s.OP.val.shape[1]
+    op_id = getattr(s.OP, 'id', None)
+    ctrl = getattr(s.prior.OP, 'isCtrl', None)
+    check = getattr(s.prior.OP, 'isCheck', None)
+    OPt = np.empty((3, nOP), dtype=object)
+    for j in range(nOP):
+        lead = 'H' if (check is not None and check[j]) else ('C' if (ctrl is not None and ctrl[j]) else 'O')
+        tail = ''
+        if nOP > 1 and op_id is not None:
+            tail = '-%d' % (j + 1) + ('/%d' % op_id[j] if op_id[j] != j + 1 else '')
+        for k, ax in enumerate('XYZ'):
+            OPt[k, j] = lead + ax + tail
+    return IOt, EOt, OPt
+
+
+def paramtypes(s):
+    """[x,t]=serialize(s) (serialize.m:20-25): the type string of every unknown, in x order."""
+    IOt, EOt, OPt = buildparamtypes(s)
+    ser = s.bundle.serial
+    t = np.empty(ser.n, dtype=object)
+    for blk, T in ((ser.IO, IOt), (ser.EO, EOt), (ser.OP, OPt)):
+        t[blk.dest] = T.reshape(-1, order='F')[blk.src]
+    return t
+
+
+def column_matching(J):
+    """p = dmperm(J) for a tall sparse J: p[j] = 1-based row matched to column j, 0 if unmatched.
+    Columns are taken in order (cheap assignment, then augmenting depth-first search), as MATLAB's
+    dmperm / CSparse cs_maxtrans does, so an over-determined column set loses its last columns."""
+    import scipy.sparse as sps
+    A = sps.csc_matrix(J)
+    A.eliminate_zeros()
+    A.sort_indices()
+    m, n = A.shape
+    Ap, Ai = A.indptr, A.indices
+    row_of = np.full(n, -1, dtype=np.int64)
+    col_of = np.full(m, -1, dtype=np.int64)
+    nxt = Ap[:-1].copy()                                   # cheap-assignment cursor of every column
+    for k in range(n):
+        path = [k]                                         # columns on the current DFS path
+        via = {}                                           # column -> row through which it was reached
+        cur = {k: Ap[k]}
+        seen = {k}
+        free_row = -1
+        while path:
+            j = path[-1]
+            while nxt[j] < Ap[j + 1] and free_row < 0:
+                i = Ai[nxt[j]]
+                nxt[j] += 1
+                if col_of[i] < 0:
+                    free_row = i
+            if free_row >= 0:
+                break
+            moved = False
+            while cur[j] < Ap[j + 1]:
+                i = Ai[cur[j]]
+                cur[j] += 1
+                j2 = col_of[i]
+                if j2 >= 0 and j2 not in seen:
+                    seen.add(j2)
+                    via[j2] = i
+                    cur[j2] = Ap[j2]
+                    path.append(j2)
+                    moved = True
+                    break
+            if not moved:
+                path.pop()
+        if free_row >= 0:                                  # flip the matching along the path
+            i = free_row
+            for j in reversed(path):
+                row_of[j] = i
+                col_of[i] = j
+                i = via.get(j, -1)
+    return np.where(row_of >= 0, row_of + 1, 0)

@@ -13,7 +13,8 @@ import scipy.sparse as sp
 
 from . import lsa
 from .cameramodel import brown_euler_cam4
-from .dbatstruct import buildserialindices, buildweightmatrix, deserialize, serialize
+from .dbatstruct import (buildserialindices, buildweightmatrix, deserialize, dmperm_match, paramtypes,
+                         serialize)
 
 
 def bundle(s, damping='gna', maxIter=20, convTol=1e-6, absTerm=False, doTrace=False,
@@ -80,6 +81,15 @@ def bundle(s, damping='gna', maxIter=20, convTol=1e-6, absTerm=False, doTrace=Fa
     s0 = np.sqrt((r @ r) / dof)
     s.post.sigmas = s0 * s.IP.sigmas
     E.numObs, E.numParams, E.redundancy, E.s0 = len(r), len(x), dof, s0
+    # bundle.m:368-446: parameter type of every unknown; on code -4 the structural analysis
+    E.paramTypes = paramtypes(s)
+    E.weakness = NS(structural=None, numerical=None)
+    if code == -4:
+        dm = dmperm_match(E.final.weighted.J)                        # :433
+        rank = int(np.count_nonzero(dm))
+        E.weakness.structural = NS(dmperm=dm, rank=rank, deficiency=len(x) - rank,
+                                   suspectedParams=list(E.paramTypes[dm == 0]))
+        E.weakness.numerical = NS(rank=np.nan, deficiency=np.nan)    # :444-445
     return s, ok, iters, s0, E
 
 

@@ -191,3 +191,111 @@ def seteoest_depend(s, camNo=0):
     s.bundle.est.EO[:, camNo] = False
     s.bundle.est.EO[i, j] = False
     return s
+
+
+def buildparamtypes(s):
+    """buildparamtypes.m:22-104 (single IO block): type strings of every IO / EO / OP element, e.g.
+    'cc', 'K1', 'EX-3', 'om-21', 'OX-12/13' (index/id), 'CX-97/1001' for control points."""
+    NC, nImg = s.IO.val.shape
+    nK, nP = int(s.IO.model.nK), int(s.IO.model.nP)
+    base = ['cc', 'px', 'py', 'as', 'sk'] + ['K%d' % k for k in range(1, nK + 1)] + ['P%d' % k for k in range(1, nP + 1)]
+    IOt = np.empty((NC, nImg), dtype=object)
+    for i in range(nImg):
+        IOt[:, i] = base
+    names = ['EX', 'EY', 'EZ', 'om', 'ph', 'ka']
+    eo_id = getattr(s.EO, 'id', None)
+    EOt = np.empty((6, nImg), dtype=object)
+    useIds = eo_id is not None and nImg > 1 and np.any(np.arange(1, nImg + 1) != np.asarray(eo_id))
+    for i in range(nImg):
+        suf = '' if nImg == 1 else ('-%d(%d)' % (i + 1, eo_id[i]) if useIds else '-%d' % (i + 1))
+        EOt[:, i] = [n + suf for n in names]
+    nOP = s.OP.val.shape[1]
+    op_id = getattr(s.OP, 'id', None)
+    isCtrl = getattr(s.prior.OP, 'isCtrl', None)
+    isCheck = getattr(s.prior.OP, 'isCheck', None)
+    OPt = np.empty((3, nOP), dtype=object)
+    for j in range(nOP):
+        pre = 'O'
+        if isCtrl is not None and isCtrl[j]:
+            pre = 'C'
+        if isCheck is not None and isCheck[j]:
+            pre = 'H'
+        suf = ''
+        if nOP > 1 and op_id is not None:
+            suf = '-%d' % (j + 1)
+            if op_id[j] != j + 1:
+                suf += '/%d' % op_id[j]
+        OPt[:, j] = [pre + c + suf for c in 'XYZ']
+    return IOt, EOt, OPt
+
+
+def paramtypes(s):
+    """Second output of serialize.m:20-25: the type string of every element of x."""
+    IOt, EOt, OPt = buildparamtypes(s)
+    ser = s.bundle.serial
+    t = np.empty(ser.n, dtype=object)
+    t[ser.IO.dest] = IOt.reshape(-1, order='F')[ser.IO.src]
+    t[ser.EO.dest] = EOt.reshape(-1, order='F')[ser.EO.src]
+    t[ser.OP.dest] = OPt.reshape(-1, order='F')[ser.OP.src]
+    return t
+
+
+def dmperm_match(J):
+    """`p = dmperm(A)` for a tall sparse matrix: p[j] = row matched to column j (1-based) or 0.
+    CSparse's cs_maxtrans as MATLAB runs it: columns in order, cheap assignment first, then an
+    augmenting depth-first search - so when a column set cannot be matched completely it is the LAST
+    columns of the set that stay unmatched (bundle.m:433-442 reports exactly those parameters)."""
+    import scipy.sparse as sp
+    A = sp.csc_matrix(J)
+    A.eliminate_zeros()
+    A.sort_indices()
+    m, n = A.shape
+    Ap, Ai = A.indptr, A.indices
+    rowmatch = -np.ones(m, dtype=np.int64)            # column matched to each row
+    colmatch = -np.ones(n, dtype=np.int64)
+    cheap = Ap[:-1].copy()
+    for k in range(n):
+        # depth-first search for an augmenting path starting at column k
+        stack = [k]
+        ptr = {k: Ap[k]}
+        parent_row = {}
+        found = -1
+        visited = set([k])
+        while stack:
+            j = stack[-1]
+            # cheap assignment: first unmatched row in column j
+            hit = -1
+            while cheap[j] < Ap[j + 1]:
+                i = Ai[cheap[j]]
+                cheap[j] += 1
+                if rowmatch[i] < 0:
+                    hit = i
+                    break
+            if hit >= 0:
+                found = hit
+                break
+            advanced = False
+            while ptr[j] < Ap[j + 1]:
+                i = Ai[ptr[j]]
+                ptr[j] += 1
+                j2 = rowmatch[i]
+                if j2 >= 0 and j2 not in visited:
+                    visited.add(j2)
+                    parent_row[j2] = i
+                    ptr[j2] = Ap[j2]
+                    stack.append(j2)
+                    advanced = True
+                    break
+            if not advanced:
+                stack.pop()
+        if found >= 0:
+            # augment along the stack
+            i = found
+            for j in reversed(stack):
+                prev = colmatch[j]
+                colmatch[j] = i
+                rowmatch[i] = j
+                i = prev if j != k else -1
+                if j != k:
+                    i = parent_row[j]
+    return np.where(colmatch >= 0, colmatch + 1, 0)

@@ -416,3 +416,34 @@ def test_sxb_prior_eo_demo_matches_golden_reports(use_prior, iters, first, last,
     assert ok and it == iters and E.numParams == 1173 and len(E.final.weighted.r) == nobs
     assert abs(E.res[0] - first) < 2e-5 * first
     assert abs(E.res[-1] - last) < 6e-4 and abs(s0 - sigma0) < 6e-6
+
+
+@pytest.mark.parametrize('pm,rank,suspects', [
+    ('camcal-pmexport-1ray.txt', 422, ['OZ-87/88']),
+    ('camcal-pmexport-missing-obs.txt', 417, ['OX-12/13', 'OY-12/13', 'OZ-12/13', 'OX-59/60', 'OY-59/60', 'OZ-59/60'])])
+def test_structural_weakness_matches_golden_reports(pm, rank, suspects):
+    """bundle.m:431-446 on the two structurally deficient camcal projects: the reports list
+    "Structural rank: 422 (deficiency: 1) ... OZ-87/88" and "Structural rank: 417 (deficiency: 6) ...
+    OX/OY/OZ-12/13, OX/OY/OZ-59/60" (parameter types from buildparamtypes.m, unmatched columns from
+    dmperm).  Checked for the restatement and for the product's host-side helpers on the same Jacobian."""
+    import copy, os
+    import numpy as np
+    from oracle.loaders import camcal_pm_struct
+    from oracle.photogrammetry import resect, forwintersect
+    from oracle.bundle import bundle as obundle
+    from dbat_b200.bundle import structural_weakness
+    from dbat_b200.dbatstruct import paramtypes as product_paramtypes
+    G = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'camcalpm')
+    s = camcal_pm_struct(os.path.join(G, pm), os.path.join(G, 'camcal-fixed.txt'))
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, _, _ = resect(s, 'all', cpId, 1, 0, cpId)
+    s2, _, _ = forwintersect(s1, 'all', True)
+    s3, ok, it, s0, E = obundle(copy.deepcopy(s2), 'gna')
+    w = E.weakness.structural
+    assert E.code == -4 and w.rank == rank and w.deficiency == 423 - rank and w.suspectedParams == suspects
+    assert list(E.paramTypes[:9]) == ['cc', 'px', 'py', 'as', 'K1', 'K2', 'K3', 'P1', 'P2'] and E.paramTypes[9] == 'EX-1'
+    pt = product_paramtypes(s3)
+    assert list(pt) == list(E.paramTypes)
+    wp = structural_weakness(E.final.weighted.J, pt)
+    assert wp.structural.rank == rank and wp.structural.suspectedParams == suspects
+    assert np.array_equal(wp.structural.dmperm == 0, w.dmperm == 0)
