@@ -223,6 +223,17 @@ class _Final:
         self.unweighted = _RJ(problem, r_u, False)
         self.weighted = _RJ(problem, r_w, True)
         self.factorized = None
+        self._scaled = None
+
+    @property
+    def scaled(self):
+        """gauss_newton_armijo.m:166-174,249: column scaling D = 1/||J(:,j)|| and J*diag(D)."""
+        if self._scaled is None:
+            J = self.weighted.J
+            with np.errstate(divide='ignore'):
+                D = 1.0 / np.sqrt(np.asarray(J.multiply(J).sum(axis=0)).ravel())
+            self._scaled = NS(D=D, J=(J @ sp.diags(D)).tocsc())
+        return self._scaled
 
 
 class _RJ:
@@ -400,21 +411,65 @@ def bundle(s, *varargin):
     s.post.sigmas = s0 * s.IP.sigmas
     E.numObs, E.numParams, E.redundancy, E.s0, E.sigmas = len(r), len(x), dof, s0, s.post.sigmas
     E.paramTypes = paramtypes(s)                                       # bundle.m:162,368
-    E.weakness = structural_weakness(final.weighted.J, E.paramTypes) if code == -4 \
-        else NS(structural=None, numerical=NS(rank=len(x), deficiency=0))
+    if code == -4:
+        E.weakness = structural_weakness(final.weighted.J, E.paramTypes)
+    elif code == -2:
+        E.weakness = NS(structural=None, numerical=numerical_weakness(final.scaled.J, E.paramTypes))
+    else:
+        E.weakness = NS(structural=None, numerical=NS(rank=len(x), deficiency=0))
     return s, ok, iters, s0, E
 
 
 def structural_weakness(J, paramTypes):
     """bundle.m:431-446: on code -4 record which parameters a maximum matching of the Jacobian's
     pattern leaves out (`dmperm`), the structural rank and its deficiency; the numerical rank is
-    marked unchecked.  (The numerical null-space analysis of code -2, bundle.m:373-428, needs `eigs`
-    on the scaled Jacobian and is not provided.)"""
+    marked unchecked."""
     dm = column_matching(J)
     rank = int(np.count_nonzero(dm))
     return NS(structural=NS(dmperm=dm, rank=rank, deficiency=len(dm) - rank,
                             suspectedParams=list(np.asarray(paramTypes, dtype=object)[dm == 0])),
               numerical=NS(rank=float('nan'), deficiency=float('nan')))
+
+
+NUMRANK_MAX_N = 6000       # dense SVD of the scaled Jacobian's Gram matrix; above it the rank is NaN
+
+
+def numerical_weakness(Js, paramTypes):
+    """bundle.m:373-428: on code -2, the numerical rank of the column-scaled Jacobian
+    (spnrank.m:166-178: singular values above max(size)*eps(smax)), its deficiency and, when
+    deficient, an orthonormal basis V of the null-space with eigenvalues d of Js'Js, trace (of the
+    sqrt(eps)-shifted Js'Js, as the reference leaves it) and per vector the parameters whose
+    entry exceeds the mean of the largest entry and sqrt(1/n).  A post-mortem diagnostic, done on the
+    host like the reference's; beyond NUMRANK_MAX_N unknowns rank and deficiency are NaN, which is what
+    the reference records when spnrank gives up (:384-387)."""
+    m, n = Js.shape
+    if n > NUMRANK_MAX_N:
+        return NS(rank=float('nan'), deficiency=float('nan'))
+    G = (Js.T @ Js).toarray()
+    d, V = np.linalg.eigh(G)
+    smax = np.sqrt(max(d[-1], 0.0))
+    # singular values are sqrt(d), but squaring loses the small ones: re-measure ||Js v|| for every
+    # eigenvector whose eigenvalue is within rounding of the squared tolerance
+    tol = max(m, n) * np.spacing(smax)
+    sv = np.sqrt(np.maximum(d, 0.0))
+    doubt = sv < 1e4 * np.sqrt(np.finfo(float).eps) * smax
+    if doubt.any():
+        sv[doubt] = np.linalg.norm(Js @ V[:, doubt], axis=0)
+    rank = int(np.count_nonzero(sv > tol))
+    W = NS(rank=rank, deficiency=n - rank)
+    if W.deficiency > 0:
+        k = np.argsort(np.abs(d), kind='stable')[:W.deficiency]      # :405-407
+        W.V, W.d = V[:, k], d[k]
+        W.trace = float(np.trace(G) + np.sqrt(np.finfo(float).eps) * n)
+        pt = np.asarray(paramTypes, dtype=object)
+        avg = np.sqrt(1.0 / n)
+        W.suspectedParams = []
+        for j in range(W.deficiency):                                # :412-422
+            o = np.argsort(-np.abs(W.V[:, j]), kind='stable')
+            v = W.V[o, j]
+            keep = np.abs(v) > 0.5 * (avg + abs(v[0]))
+            W.suspectedParams.append(NS(values=v[keep], indices=o[keep], params=list(pt[o[keep]])))
+    return W
 
 
 def _blockdiag(blocks):

@@ -90,7 +90,40 @@ def bundle(s, damping='gna', maxIter=20, convTol=1e-6, absTerm=False, doTrace=Fa
         E.weakness.structural = NS(dmperm=dm, rank=rank, deficiency=len(x) - rank,
                                    suspectedParams=list(E.paramTypes[dm == 0]))
         E.weakness.numerical = NS(rank=np.nan, deficiency=np.nan)    # :444-445
+    elif code == -2 and hasattr(E.final, 'scaled'):                  # :373-428
+        E.weakness.numerical = numerical_weakness(E.final.scaled.J, E.paramTypes)
+    else:                                                            # :429-432
+        E.weakness.numerical = NS(rank=len(x), deficiency=0)
     return s, ok, iters, s0, E
+
+
+def numerical_weakness(Js, paramTypes):
+    """bundle.m:373-428: numerical rank of the column-scaled Jacobian and the parameters that carry
+    its null-space.  The rank follows spnrank.m:166-178 (singular values above
+    max(size)*eps(smax)); dense SVD / eigh stand in for the sparse eigs calls, so the null-space
+    basis V is one orthonormal basis of the same invariant subspace, ordered by |eigenvalue|."""
+    A = Js.toarray() if sp.issparse(Js) else np.asarray(Js)
+    n = A.shape[1]
+    sv = np.linalg.svd(A, compute_uv=False)
+    tol = max(A.shape) * np.spacing(sv[0])                           # spnrank.m:177
+    rank = int(np.count_nonzero(sv > tol))
+    W = NS(rank=rank, deficiency=n - rank)
+    if W.deficiency > 0:
+        JTJ = A.T @ A
+        d, V = np.linalg.eigh(JTJ)                                   # :398-402 (shift cancels)
+        k = np.argsort(np.abs(d), kind='stable')[:W.deficiency]      # :405-407
+        d, V = d[k], V[:, k]
+        W.V, W.d = V, d
+        W.trace = float(np.trace(JTJ) + np.sqrt(np.finfo(float).eps) * n)   # :410 (shifted JTJ)
+        W.suspectedParams = []
+        pt = np.asarray(paramTypes, dtype=object)
+        avg = np.sqrt(1.0 / n)
+        for j in range(V.shape[1]):                                  # :412-422
+            o = np.argsort(-np.abs(V[:, j]), kind='stable')
+            v = V[o, j]
+            keep = np.abs(v) > 0.5 * (avg + abs(v[0]))
+            W.suspectedParams.append(NS(values=v[keep], indices=o[keep], params=list(pt[o[keep]])))
+    return W
 
 
 # --------------------------------------------------------------------------- bundle_cov

@@ -330,6 +330,40 @@ def test_camcal_no_datum_demo_matches_golden_report():
     s3, ok, it, s0, E = obundle(copy.deepcopy(s), 'gna')
     assert not ok and it == 0 and E.code == -2 and E.numParams == 435
     assert abs(E.res[0] - 15772.8) < 0.06 and abs(s0 - 258.848) < 6e-4
+    # bundle.m:373-428 — report: "Numerical rank: 428 (deficiency: 7)" and seven null-space vectors
+    # with eigenvalues ~1e-17.  A basis of a 7-dimensional eigenspace is not unique, so every vector
+    # the report prints (its largest entries, 3 digits) must lie in the span of ours: the least-squares
+    # fit over the printed entries leaves only print rounding and needs coefficients of norm <= 1.
+    import re
+    import numpy as np
+    w = E.weakness.numerical
+    assert E.weakness.structural is None and (w.rank, w.deficiency) == (428, 7)
+    assert w.V.shape == (435, 7) and np.abs(w.d).max() < 1e-12 and abs(w.trace - 435) < 1e-4
+    assert np.linalg.norm(E.final.scaled.J @ w.V) < 1e-10
+    vecs = []
+    for line in open(os.path.join(G, 'camcal-dbatreport-no-datum.txt')):
+        if re.match(r'\s+Vector \d+', line):
+            vecs.append([])
+        m = re.match(r'\s+\(([A-Za-z0-9]+-\d+), (-?[\d.e-]+)\)', line)
+        if m and vecs:
+            vecs[-1].append((m.group(1), float(m.group(2))))
+        if 'Problems related' in line:
+            break
+    assert len(vecs) == 7
+    ix = {p: i for i, p in enumerate(E.paramTypes)}
+    for v in vecs:
+        K = [ix[p] for p, _ in v]
+        g = np.array([x for _, x in v])
+        c = np.linalg.lstsq(w.V[K], g, rcond=1e-2)[0]
+        assert np.abs(w.V[K] @ c - g).max() < 1e-3 and np.linalg.norm(c) < 1.001
+    for sp_ in w.suspectedParams:                    # IO parameters take no part in a gauge freedom
+        assert all(p[:2] in ('EX', 'EY', 'EZ', 'om', 'ph', 'ka', 'OX', 'OY', 'OZ') for p in sp_.params)
+    # the package's host-side analysis (Gram-matrix route) on the same Jacobian: same rank, same space
+    from dbat_b200.bundle import numerical_weakness
+    wp = numerical_weakness(E.final.scaled.J, E.paramTypes)
+    assert (wp.rank, wp.deficiency) == (428, 7) and abs(wp.trace - w.trace) < 1e-9
+    assert np.linalg.norm(wp.V - w.V @ (w.V.T @ wp.V)) < 1e-8
+    assert len(wp.suspectedParams) == 7
 
 
 @pytest.mark.parametrize('stub,sigma0,last,nparams', [('fixed', 1.78095, 108.827, 414), ('weighted', 1.60984, 98.3715, 426)])
