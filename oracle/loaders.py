@@ -8,6 +8,7 @@ internal py = -user py, internal K,P = -user K,P, internal `as` = 1 - user aspec
 square pixel size = sensor height / image height (`sensor="auto,h"`).
 """
 import re
+from types import SimpleNamespace as NS
 
 import numpy as np
 
@@ -129,7 +130,7 @@ def load_pm_export(path, imSz=None):
     # the caller (or reads the image files, which are not shipped)
     if imSz is None:
         imSz = [float(hdr2[2]), float(hdr2[3])]
-    job = {'imSz': np.array(imSz, float),
+    job = {'imSz': np.array(imSz, float), 'title': lines[0].strip(), 'fileName': path,
            'defCam': np.array([float(v) for v in lines[3].split()])}
     k = 5
     images = []
@@ -325,15 +326,24 @@ def camcal_pm_struct(pmfile, cptfile=None, focal=7.3, keep_loaded=False):
     s = new_struct(IO, EO, OP, mk[:, 2:4].T, mk[:, 0].astype(int), np.array([op_of[int(v)] for v in mk[:, 1]]),
                    pxSize, imSz[:, None], 3, nK, nP, mstd.T)
     s.OP.id = ids
+    s.OP.label = [''] * len(ids)
+    s.IP.sigmas = np.unique(mstd)                          # prob2dbatstruct.m:367
+    s.EO.name = [im['name'].replace('\\', '/').split('/')[-1] for im in prob['images']]
+    s.IO.model.camUnit = 'mm'                              # prob2dbatstruct.m:393-405
+    s.proj = NS(objUnit='m', x0desc='', title=prob['job']['title'], fileName=pmfile, cptFile=cptfile or '',
+                EOfile='', UUID='')
     s.bundle.est.IO[:] = True
     s.bundle.est.IO[4, :] = False
     s.bundle.est.EO[:] = True
     s.bundle.est.OP[:] = True
     s.prior.OP.isCtrl = ids > 1000                         # camcaldemo.m:74-78
+    s.prior.OP.isCheck = np.zeros(len(ids), bool)
     if not keep_loaded:
-        cp = {int(r[0]): [float(v) for v in r[2:5]] for r in load_table(cptfile)}
-        for j in np.flatnonzero(s.prior.OP.isCtrl):
-            s.OP.val[:, j] = cp[int(ids[j])]
+        cp = {int(r[0]): (r[1], [float(v) for v in r[2:5]]) for r in load_table(cptfile)}
+        for j in np.flatnonzero(s.prior.OP.isCtrl):        # setcpt.m:24-51 (fixed: std 0, not observed)
+            s.OP.label[j], s.OP.val[:, j] = cp[int(ids[j])]
+            s.prior.OP.val[:, j] = s.OP.val[:, j]
+            s.prior.OP.std[:, j] = 0.0
             s.bundle.est.OP[:, j] = False
     return s
 
