@@ -21,6 +21,7 @@ reference's, line for line, so that a result file can be diffed against one the 
 import math
 import os
 import platform
+import re
 import time
 
 import numpy as np
@@ -295,6 +296,9 @@ def _ray_counts(s):
 
 
 # ----------------------------------------------------------------------------- the result file
+_NONFINITE = re.compile(r'\b(nan|inf)\b')      # MATLAB spells them NaN / Inf
+
+
 class _Out:
     """Indented line writer; `table` is the reference's pretty_print (bundle_result_file.m:928-944)."""
 
@@ -302,7 +306,7 @@ class _Out:
         self.lines = []
 
     def __call__(self, level, text):
-        self.lines.append('   ' * level + text)
+        self.lines.append('   ' * level + _NONFINITE.sub(lambda m: {'nan': 'NaN', 'inf': 'Inf'}[m.group(0)], text))
 
     def table(self, level, rows, minLen=math.inf, maxLen=-math.inf):
         longest = max(len(r[0]) for r in rows)

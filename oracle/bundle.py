@@ -142,6 +142,8 @@ def _prepare(s, e):
     p = p[p >= 0]                                                    # :83-84
     nOP = np.count_nonzero(bOP >= 0)
     try:
+        if not np.all(np.isfinite(JTJ)):
+            raise np.linalg.LinAlgError
         L = np.linalg.cholesky(JTJ[np.ix_(p, p)])                    # :87
         fail = False
     except np.linalg.LinAlgError:
@@ -158,7 +160,7 @@ def _invblock_sqrt(L, p, ix):
     n = L.shape[0]
     rhs = np.zeros((n, len(ix)))
     rhs[invP[ix], np.arange(len(ix))] = 1.0
-    v2 = sla.solve_triangular(L, rhs, lower=True)
+    v2 = sla.solve_triangular(L, rhs, lower=True, check_finite=False)
     return v2.T @ v2
 
 

@@ -336,7 +336,7 @@ def camcal_pm_struct(pmfile, cptfile=None, focal=7.3, keep_loaded=False):
     s.bundle.est.IO[4, :] = False
     s.bundle.est.EO[:] = True
     s.bundle.est.OP[:] = True
-    s.prior.OP.isCtrl = ids > 1000                         # camcaldemo.m:74-78
+    s.prior.OP.isCtrl = (ids > 1000) & (not keep_loaded)   # camcaldemo.m:74-78; no setcpt in the no-datum demo
     s.prior.OP.isCheck = np.zeros(len(ids), bool)
     if not keep_loaded:
         cp = {int(r[0]): (r[1], [float(v) for v in r[2:5]]) for r in load_table(cptfile)}
