@@ -287,7 +287,7 @@ def stpierre_struct(root, imSz=(6912, 5212)):
     return s
 
 
-def camcal_pm_struct(pmfile, cptfile=None, focal=7.3, keep_loaded=False):
+def camcal_pm_struct(pmfile, cptfile=None, focal=7.3, keep_loaded=False, model=3):
     """The PhotoModeler-export camcal demos (`camcaldemo.m:30-98`, `camcaldemo2.m`, `camcaldemo_1ray.m`,
     `camcaldemo_missing_obs.m`; with keep_loaded `camcaldemo_no_datum.m:36-52`): `loadpm` +
     `prob2dbatstruct` (`misc/prob2dbatstruct.m:198-420`), distortion model 3, `setcamvals(s0,'default',7.3)`
@@ -324,7 +324,7 @@ def camcal_pm_struct(pmfile, cptfile=None, focal=7.3, keep_loaded=False):
     if np.any(mstd == 0):                                  # prob2dbatstruct.m:367-373
         mstd[:] = 1.0
     s = new_struct(IO, EO, OP, mk[:, 2:4].T, mk[:, 0].astype(int), np.array([op_of[int(v)] for v in mk[:, 1]]),
-                   pxSize, imSz[:, None], 3, nK, nP, mstd.T)
+                   pxSize, imSz[:, None], model, nK, nP, mstd.T)
     s.OP.id = ids
     s.OP.label = [''] * len(ids)
     s.IP.sigmas = np.unique(mstd)                          # prob2dbatstruct.m:367
@@ -334,6 +334,8 @@ def camcal_pm_struct(pmfile, cptfile=None, focal=7.3, keep_loaded=False):
                 EOfile='', UUID='')
     s.bundle.est.IO[:] = True
     s.bundle.est.IO[4, :] = False
+    if abs(model) < 3:                                     # setcamest.m:46-58: no affine terms in models 1, 2
+        s.bundle.est.IO[3, :] = False
     s.bundle.est.EO[:] = True
     s.bundle.est.OP[:] = True
     s.prior.OP.isCtrl = (ids > 1000) & (not keep_loaded)   # camcaldemo.m:74-78; no setcpt in the no-datum demo

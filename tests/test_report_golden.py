@@ -65,12 +65,12 @@ def report_diff(lines, golden_path, rtol=0.0):
     return bad
 
 
-def camcal_pm_run(pm, x0desc='Camera calibration from EXIF value'):
+def camcal_pm_run(pm, x0desc='Camera calibration from EXIF value', model=3):
     from oracle.loaders import camcal_pm_struct
     from oracle.photogrammetry import resect, forwintersect
     from oracle.bundle import bundle as obundle
     G = os.path.join(GOLD, 'camcalpm')
-    s = camcal_pm_struct(os.path.join(G, pm), os.path.join(G, 'camcal-fixed.txt'))
+    s = camcal_pm_struct(os.path.join(G, pm), os.path.join(G, 'camcal-fixed.txt'), model=model)
     cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
     s1, _, fail = resect(s, 'all', cpId, 1, 0, cpId)
     s2, _, _ = forwintersect(s1, 'all', True)
@@ -123,3 +123,15 @@ def test_no_datum_result_file_reproduces_the_reference_report():
     assert '         Numerical rank: 428 (deficiency: 7)' in lines
     assert sum('Vector ' in l for l in lines) == 7
     assert report_diff(lines, os.path.join(G, 'camcal-dbatreport-no-datum.txt')) == []
+
+
+@pytest.mark.parametrize('model', [-1, 1, 2, 3, 4, 5])
+def test_all_distortion_models_result_files_reproduce_the_reference_reports(model):
+    """camcaldemo_allmodels.m: the same project under every lens distortion model (the forward model -1,
+    the legacy backward models 1-2 without affine terms, 3-5): six 608/610-line result files, exactly."""
+    from oracle.bundle import bundle_cov as ocov
+    from dbat_b200.report import bundle_result_file
+    s, ok, it, s0, E = camcal_pm_run('camcal-pmexport.txt', model=model)
+    assert ok and it == 9
+    s, lines = bundle_result_file(s, E, None, cov=ocov)
+    assert report_diff(lines, os.path.join(GOLD, 'dbatexports', 'camcal-dbatreport-model%d.txt' % model)) == []
