@@ -763,7 +763,9 @@ def bundle_result_file(s, e, f=None, cov=_device_cov):
         lim = min(srt[min(3, len(srt)) - 1] * 1.1 + 0.1, 80)
         nPts = min(max(int(np.count_nonzero(srt < lim)), 3), len(srt))
         for n in range(nPts):
-            cams = np.sort(s.IP.img[s.IP.op == opIx[o[n]]]) + 1
+            # :805 indexes IP.vis with the position inside the OP subset, not the point's own row;
+            # kept, so that a result file diffs clean against the reference's
+            cams = np.sort(s.IP.img[s.IP.op == o[n]]) + 1
             out(5, '%6d: %5.2f (%s)' % (idOP[o[n]], srt[n], ' '.join('%4d' % c for c in cams)))
     else:
         for t in ('Minimum', 'Maximum', 'Average'):

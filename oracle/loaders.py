@@ -97,16 +97,27 @@ def load_camcal_script(root, calibrated_cam_xml=None):
                    ip_img, ip_op, pxSize[:, None], imSize[:, None], model, nK, nP, IPstd)
     s.OP.id = np.array(op_ids)
     s.EO.id = np.array(img_ids)
-    s.EO.name = [r[1] for r in imgs]
+    s.EO.name = [r[1].replace('\\', '/').split('/')[-1] for r in imgs]
     s.bundle.est.IO[:] = True
     s.bundle.est.IO[4, :] = False                        # <skew>false</skew>
     s.bundle.est.EO[:] = True
     s.bundle.est.OP[:] = True
-    for r in ctrl:                                       # fixed control points
+    s.OP.label = [''] * nOP
+    for r in ctrl:                                       # fixed control points (setcpt.m:24-51)
         j = op_of[int(r[0])]
         s.OP.val[:, j] = [float(r[2]), float(r[3]), float(r[4])]
+        s.OP.label[j] = r[1]
+        s.prior.OP.val[:, j] = s.OP.val[:, j]
+        s.prior.OP.std[:, j] = 0.0
         s.bundle.est.OP[:, j] = False
     s.prior.OP.isCtrl = ~s.bundle.est.OP.all(axis=0)
+    s.prior.OP.isCheck = np.zeros(nOP, bool)
+    s.IP.sigmas = np.unique(IPstd)
+    s.IO.model.camUnit = 'mm'
+    m = re.search(r'<name>\s*([^<]*?)\s*</name>', xml)
+    s.proj = NS(objUnit='m', x0desc='', title=m.group(1) if m else '', UUID='', EOfile='',
+                fileName=os.path.join(root, 'camcaldemo.xml'),
+                cptFile=os.path.join(root, 'reference', 'camcal-fixed.txt'))
     return s
 
 
@@ -130,7 +141,7 @@ def load_pm_export(path, imSz=None):
     # the caller (or reads the image files, which are not shipped)
     if imSz is None:
         imSz = [float(hdr2[2]), float(hdr2[3])]
-    job = {'imSz': np.array(imSz, float), 'title': lines[0].strip(), 'fileName': path,
+    job = {'imSz': np.array(imSz, float), 'title': lines[0].rstrip('\r'), 'fileName': path,
            'defCam': np.array([float(v) for v in lines[3].split()])}
     k = 5
     images = []
@@ -219,8 +230,16 @@ def prague_cam_struct(root, stub, cpfile=None, shift_cp=True, orient='no'):
     if shift_cp:                                                           # sxb_prior_eo.m sets them unshifted
         cp_pos = cp_pos + np.mean(pm_pos - cp_pos, axis=1, keepdims=True)  # prague2016_pm.m:174-190
     s.prior.OP.isCtrl = np.zeros(len(ids), bool)
+    s.prior.OP.isCheck = np.zeros(len(ids), bool)
+    s.OP.label = [''] * len(ids)
+    s.IP.sigmas = np.unique(mstd)                                          # prob2dbatstruct.m:367
+    s.EO.name = [im['name'].replace('\\', '/').split('/')[-1] for im in prob['images']]
+    s.IO.model.camUnit = 'mm'
+    s.proj = NS(objUnit='m', x0desc='', title=prob['job']['title'], UUID='', EOfile='',
+                fileName=prob['job']['fileName'], cptFile=os.path.join(root, 'ref', cpfile or 'ctrlpts-%s.txt' % stub))
     for k, i in enumerate(cp_id):                                          # setcpt.m
         j = op_of[i]
+        s.OP.label[j] = cp[k][1]
         s.prior.OP.val[:, j] = cp_pos[:, k]
         s.OP.val[:, j] = cp_pos[:, k]
         s.prior.OP.std[:, j] = cp_std[:, k]
@@ -360,4 +379,6 @@ def set_prior_eo_positions(s, prob, path):
         s.prior.EO.std[0:3, i] = float(r[4])
         s.prior.EO.use[0:3, i] = float(r[4]) != 0
         s.bundle.est.EO[0:3, i] = float(r[4]) != 0
+    if getattr(s, 'proj', None) is not None:
+        s.proj.EOfile = path
     return s

@@ -135,3 +135,70 @@ def test_all_distortion_models_result_files_reproduce_the_reference_reports(mode
     assert ok and it == 9
     s, lines = bundle_result_file(s, E, None, cov=ocov)
     assert report_diff(lines, os.path.join(GOLD, 'dbatexports', 'camcal-dbatreport-model%d.txt' % model)) == []
+
+
+def test_script_pipeline_result_file_reproduces_the_reference_report():
+    """data/script/camcaldemo (camcaldemo.xml run by the reference's script runner): its result/report.txt."""
+    from oracle.loaders import load_camcal_script
+    from oracle.photogrammetry import resect, forwintersect
+    from oracle.bundle import bundle as obundle, bundle_cov as ocov
+    from dbat_b200.report import bundle_result_file
+    root = os.path.join(GOLD, 'camcaldemo')
+    s = load_camcal_script(root)
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, _, fail = resect(s, 'all', cpId, 1, 0, cpId)
+    s2, _, _ = forwintersect(s1, 'all', True)
+    s3, ok, it, s0, E = obundle(copy.deepcopy(s2), 'gna')
+    s3, lines = bundle_result_file(s3, E, None, cov=ocov)
+    assert report_diff(lines, os.path.join(root, 'result', 'report.txt')) == []
+
+
+def prague_run(root, stub, cpfile=None, prior_eo=False, **kw):
+    from oracle.loaders import prague_cam_struct, load_pm_export, set_prior_eo_positions
+    from oracle.photogrammetry import resect, forwintersect
+    from oracle.bundle import bundle as obundle
+    s = prague_cam_struct(root, stub, cpfile, **kw)
+    if prior_eo:
+        prob = load_pm_export(os.path.join(root, 'pmexports', 'wsmart-with-orient-pmexport.txt'))
+        set_prior_eo_positions(s, prob, os.path.join(root, 'ref', 'fake-camera-positions.txt'))
+    s.EO.val[:] = np.nan                                     # cleareo / clearop (prague2016_pm.m:194-195)
+    s.OP.val[:, ~s.prior.OP.isCtrl] = np.nan
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, _, fail = resect(s, 'all', cpId, 1, 0, cpId)
+    assert not fail
+    s2, _, _ = forwintersect(s1, 'all', True)
+    return obundle(copy.deepcopy(s2), 'gna')
+
+
+@pytest.mark.parametrize('project,stub,cps', [
+    ('prague2016cam', 'fixed', None), ('prague2016cam', 'weighted', None),
+    ('prague2016sxb', 'f-op0', 'fixed'), ('prague2016sxb', 'w-op0', 'weighted'),
+    ('prague2016sxb', 'w-op1', 'weighted'), ('prague2016sxb', 'wsmart', 'weighted')])
+def test_prague2016_result_files_reproduce_the_reference_reports(project, stub, cps):
+    """prague2016_pm('c1','c2','s1'..'s4'): fixed camera (legacy model 1), fixed or weighted control
+    points (prior OP observations, so the Ctrl measurements tables carry real prior/posterior/diff
+    numbers), a check point (s3) and 1100 smart points (s4) - six result files, exactly."""
+    from oracle.bundle import bundle_cov as ocov
+    from dbat_b200.report import bundle_result_file
+    root = os.path.join(GOLD, project)
+    s, ok, it, s0, E = prague_run(root, stub, 'ctrlpts-%s.txt' % cps if cps else None)
+    assert ok
+    s, lines = bundle_result_file(s, E, None, cov=ocov)
+    assert report_diff(lines, os.path.join(root, 'dbatexports', '%s-no-orient-dbatreport.txt' % stub)) == []
+
+
+@pytest.mark.parametrize('use_prior', [True, False])
+def test_sxb_prior_eo_result_files_reproduce_the_reference_reports(use_prior):
+    """sxb_prior_eo.m: with / without prior observations of four camera positions.  Exact but for the
+    'First error' line, which is a function of the resection start values only (ill-conditioned quartic,
+    6e-6 and 1e-5 relative, cf. test_sxb_prior_eo_demo_matches_golden_reports): 2e-5 on that line."""
+    from oracle.bundle import bundle_cov as ocov
+    from dbat_b200.report import bundle_result_file
+    root = os.path.join(GOLD, 'prague2016sxb')
+    s, ok, it, s0, E = prague_run(root, 'wsmart', 'ctrlpts-weighted.txt', use_prior, shift_cp=False, orient='with')
+    assert ok
+    s, lines = bundle_result_file(s, E, None, cov=ocov)
+    rep = os.path.join(root, 'dbatexports', 'sxb-%sprior-eo-dbatreport.txt' % ('' if use_prior else 'no-'))
+    exact = report_diff(lines, rep)
+    assert len(exact) == 1 and 'First error' in exact[0][1]
+    assert report_diff(lines, rep, rtol=2e-5) == []
