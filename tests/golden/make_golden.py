@@ -30,6 +30,10 @@ FILES = {
         'data/prague2016/cam/ref/ctrlpts-fixed.txt',
         'data/prague2016/cam/dbatexports/weighted-no-orient-dbatreport.txt',
         'data/prague2016/cam/dbatexports/fixed-no-orient-dbatreport.txt',
+        'data/prague2016/cam/pmexports/weighted-with-orient-pmexport.txt',
+        'data/prague2016/cam/pmexports/fixed-with-orient-pmexport.txt',
+        'data/prague2016/cam/dbatexports/weighted-with-orient-dbatreport.txt',
+        'data/prague2016/cam/dbatexports/fixed-with-orient-dbatreport.txt',
     ],
     'stpierre': [
         'data/hamburg2017/stpierre/pmexports/C5_reduced-pmexport.txt',
@@ -60,6 +64,13 @@ FILES = {
         'data/prague2016/sxb/dbatexports/w-op0-no-orient-dbatreport.txt',
         'data/prague2016/sxb/dbatexports/w-op1-no-orient-dbatreport.txt',
         'data/prague2016/sxb/dbatexports/wsmart-no-orient-dbatreport.txt',
+        'data/prague2016/sxb/pmexports/f-op0-with-orient-pmexport.txt',
+        'data/prague2016/sxb/pmexports/w-op0-with-orient-pmexport.txt',
+        'data/prague2016/sxb/pmexports/w-op1-with-orient-pmexport.txt',
+        'data/prague2016/sxb/dbatexports/f-op0-with-orient-dbatreport.txt',
+        'data/prague2016/sxb/dbatexports/w-op0-with-orient-dbatreport.txt',
+        'data/prague2016/sxb/dbatexports/w-op1-with-orient-dbatreport.txt',
+        'data/prague2016/sxb/dbatexports/wsmart-with-orient-dbatreport.txt',
     ],
     'dbatexports': [
         'data/dbat/dbatexports/camcal-dbatreport.txt',

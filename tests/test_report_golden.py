@@ -170,21 +170,23 @@ def prague_run(root, stub, cpfile=None, prior_eo=False, **kw):
     return obundle(copy.deepcopy(s2), 'gna')
 
 
+@pytest.mark.parametrize('orient', ['no', 'with'])
 @pytest.mark.parametrize('project,stub,cps', [
     ('prague2016cam', 'fixed', None), ('prague2016cam', 'weighted', None),
     ('prague2016sxb', 'f-op0', 'fixed'), ('prague2016sxb', 'w-op0', 'weighted'),
     ('prague2016sxb', 'w-op1', 'weighted'), ('prague2016sxb', 'wsmart', 'weighted')])
-def test_prague2016_result_files_reproduce_the_reference_reports(project, stub, cps):
+def test_prague2016_result_files_reproduce_the_reference_reports(project, stub, cps, orient):
     """prague2016_pm('c1','c2','s1'..'s4'): fixed camera (legacy model 1), fixed or weighted control
     points (prior OP observations, so the Ctrl measurements tables carry real prior/posterior/diff
-    numbers), a check point (s3) and 1100 smart points (s4) - six result files, exactly."""
+    numbers), a check point (s3) and 1100 smart points (s4), each from the export PhotoModeler wrote
+    without and with its own orientation stage - twelve result files, exactly."""
     from oracle.bundle import bundle_cov as ocov
     from dbat_b200.report import bundle_result_file
     root = os.path.join(GOLD, project)
-    s, ok, it, s0, E = prague_run(root, stub, 'ctrlpts-%s.txt' % cps if cps else None)
+    s, ok, it, s0, E = prague_run(root, stub, 'ctrlpts-%s.txt' % cps if cps else None, orient=orient)
     assert ok
     s, lines = bundle_result_file(s, E, None, cov=ocov)
-    assert report_diff(lines, os.path.join(root, 'dbatexports', '%s-no-orient-dbatreport.txt' % stub)) == []
+    assert report_diff(lines, os.path.join(root, 'dbatexports', '%s-%s-orient-dbatreport.txt' % (stub, orient))) == []
 
 
 @pytest.mark.parametrize('use_prior', [True, False])
