@@ -204,3 +204,77 @@ def test_sxb_prior_eo_result_files_reproduce_the_reference_reports(use_prior):
     exact = report_diff(lines, rep)
     assert len(exact) == 1 and 'First error' in exact[0][1]
     assert report_diff(lines, rep, rtol=2e-5) == []
+
+
+# ----------------------------------------------------------------------------- device twins
+def _device_pipeline(s):
+    import dbat_b200
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, _, fail = dbat_b200.resect(s, 'all', cpId, 1, 0, cpId)
+    assert not fail
+    s2, _, _ = dbat_b200.forwintersect(s1, 'all', True)
+    return dbat_b200.bundle(s2, 'gna')
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('pm,report', [
+    ('camcal-pmexport.txt', 'dbatexports/camcal-dbatreport.txt'),
+    ('camcal-pmexport5.txt', 'camcalpm/camcal-dbatreport5.txt')])
+def test_camcal_result_files_from_the_device(pm, report):
+    """The camcal demos with every number from the device: start values (resect, forwintersect), bundle,
+    and CIOF / CEO / COP from the device factorisation through the default `bundle_cov`.  The result file
+    is the reference's to the printed digits; 1e-5 relative covers the 'First error' line (device
+    resection of image 21, see test_gpu_parity) and last-digit rounding."""
+    from oracle.loaders import camcal_pm_struct
+    from dbat_b200.report import bundle_result_file
+    G = os.path.join(GOLD, 'camcalpm')
+    s = camcal_pm_struct(os.path.join(G, pm), os.path.join(G, 'camcal-fixed.txt'))
+    s.proj.x0desc = 'Camera calibration from EXIF value'
+    s, ok, it, s0, E = _device_pipeline(s)
+    assert ok
+    s, lines = bundle_result_file(s, E)
+    assert report_diff(lines, os.path.join(GOLD, report), rtol=1e-5) == []
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('stub', ['fixed', 'weighted'])
+def test_prague2016_result_files_from_the_device(stub):
+    """prague2016_pm('c1'|'c2') on the device: legacy model 1, fixed camera, fixed / weighted control
+    points (prior OP observations enter the posterior covariances and the Ctrl measurement tables)."""
+    from oracle.loaders import prague_cam_struct
+    from dbat_b200.report import bundle_result_file
+    root = os.path.join(GOLD, 'prague2016cam')
+    s = prague_cam_struct(root, stub)
+    s.EO.val[:] = np.nan
+    s.OP.val[:, ~s.prior.OP.isCtrl] = np.nan
+    s, ok, it, s0, E = _device_pipeline(s)
+    assert ok
+    s, lines = bundle_result_file(s, E)
+    assert report_diff(lines, os.path.join(root, 'dbatexports', '%s-no-orient-dbatreport.txt' % stub), rtol=1e-5) == []
+
+
+def test_result_file_through_the_device_covariance_interface():
+    """The default covariance provider is `dbat_b200.bundle_cov`, which assembles sparse block-diagonal
+    CEO / COP and CIOF from what the device returns (`Problem.cov`: (N,k,k) blocks, camera part of CXX).
+    Here a stand-in Problem serves those arrays from the oracle, so the whole host path of the device
+    twins above - sparse block extraction included - is exercised without a GPU."""
+    from types import SimpleNamespace as NS
+    from oracle.bundle import bundle_cov as ocov
+    from dbat_b200.report import bundle_result_file, _diag_blocks
+
+    s, ok, it, s0, E = camcal_pm_run('camcal-pmexport5.txt')
+
+    class StandIn:
+        n = E.numParams
+
+        def cov(self, which, s0_):
+            assert s0_ == E.s0
+            if which == 'cxx_cam':
+                nC = self.n - len(s.bundle.serial.OP.dest)
+                return np.asarray(ocov(s, E, 'CXX'))[:nC, :nC]
+            k = {'cio': s.IO.val.shape[0], 'ceo': 6, 'cop': 3}[which]
+            return _diag_blocks(np.asarray(ocov(s, E, which.upper())), k)
+
+    E.problem = StandIn()
+    s, lines = bundle_result_file(s, E)
+    assert report_diff(lines, os.path.join(GOLD, 'camcalpm', 'camcal-dbatreport5.txt')) == []
