@@ -121,6 +121,62 @@ def load_camcal_script(root, calibrated_cam_xml=None):
     return s
 
 
+def load_sxb_script(root):
+    """The DBAT struct of `data/script/sxb/sxb.xml` after its input section and the operations up to
+    `set_bundle_estimate_params`: one calibrated aerial camera (IO loaded, not estimated), control points
+    with prior standard deviations (weighted: estimated and observed, `setcpt.m:40-51`), ids 351 and 410
+    filtered out of the control set and kept as check points (prior kept for the report, not observed),
+    two image-point files with their own sigmas (`sxy` 0.5 / 1.0 px), EO estimated.  OP start values
+    'loaded': control and check points at their prior position, the rest NaN until forward intersection."""
+    import os
+    xml = open(os.path.join(root, 'sxb.xml')).read()
+    cam = parse_camera_xml(xml)
+    cam['nK'], cam['nP'] = len(cam['K'].split(',')), len(cam['P'].split(','))
+    io, pxSize, imSize, model, nK, nP = camera_internal(cam, True)
+    ref = load_table(os.path.join(root, 'reference', 'sxb-control.txt'))
+    check_ids = {351, 410}                                   # <filter id="351,410">
+    imgs = load_table(os.path.join(root, 'images', 'images.txt'))
+    pts = []
+    for fname, sxy in (('markpts.txt', 0.5), ('smartpts.txt', 1.0)):
+        pts += [(int(r[1]), int(r[0]), float(r[2]), float(r[3]), sxy)
+                for r in load_table(os.path.join(root, 'measurements', fname))]
+    img_ids = [int(r[0]) for r in imgs]
+    im_of = {v: i for i, v in enumerate(img_ids)}
+    op_ids = sorted({p[1] for p in pts} | {int(r[0]) for r in ref})
+    op_of = {v: i for i, v in enumerate(op_ids)}
+    nImg, nOP = len(img_ids), len(op_ids)
+    s = new_struct(np.tile(io[:, None], (1, nImg)), np.full((6, nImg), np.nan), np.full((3, nOP), np.nan),
+                   np.array([[p[2], p[3]] for p in pts]).T, np.array([im_of[p[0]] for p in pts]),
+                   np.array([op_of[p[1]] for p in pts]), pxSize[:, None], imSize[:, None], model, nK, nP,
+                   np.array([[p[4], p[4]] for p in pts]).T)
+    s.OP.id = np.array(op_ids)
+    s.OP.label = [''] * nOP
+    s.EO.id = np.array(img_ids)
+    s.EO.name = [r[1].replace('\\', '/').split('/')[-1] for r in imgs]
+    s.bundle.est.IO[:] = False
+    s.bundle.est.EO[:] = True
+    s.bundle.est.OP[:] = True
+    s.prior.OP.isCtrl = np.zeros(nOP, bool)
+    s.prior.OP.isCheck = np.zeros(nOP, bool)
+    for r in ref:
+        j = op_of[int(r[0])]
+        s.OP.label[j] = r[1]
+        s.prior.OP.val[:, j] = [float(v) for v in r[2:5]]
+        s.prior.OP.std[:, j] = [float(v) for v in r[5:8]]
+        s.OP.val[:, j] = s.prior.OP.val[:, j]
+        if int(r[0]) in check_ids:
+            s.prior.OP.isCheck[j] = True
+        else:
+            s.prior.OP.isCtrl[j] = True
+            s.prior.OP.use[:, j] = True
+    s.IP.sigmas = np.unique(s.IP.std)
+    s.IO.model.camUnit = 'mm'
+    m = re.search(r'<name>\s*([^<]*?)\s*</name>', xml)
+    s.proj = NS(objUnit='m', x0desc='', title=m.group(1) if m else '', UUID='', EOfile='',
+                fileName=os.path.join(root, 'sxb.xml'), cptFile=os.path.join(root, 'reference', 'sxb-control.txt'))
+    return s
+
+
 def load_camera_stations(path):
     """result/camera_stations.txt → (ids, EO 6xN [radians], std 6xN as printed)."""
     rows = load_table(path)

@@ -23,6 +23,14 @@ FILES = {
         'data/script/camcaldemo/result/report.txt',
         'data/script/camcaldemo/result/top_residuals.txt',
     ],
+    'sxb': [
+        'data/script/sxb/sxb.xml',
+        'data/script/sxb/images/images.txt',
+        'data/script/sxb/measurements/markpts.txt',
+        'data/script/sxb/measurements/smartpts.txt',
+        'data/script/sxb/reference/sxb-control.txt',
+        'data/script/sxb/result/report.txt',
+    ],
     'prague2016cam': [
         'data/prague2016/cam/pmexports/weighted-no-orient-pmexport.txt',
         'data/prague2016/cam/pmexports/fixed-no-orient-pmexport.txt',

@@ -278,3 +278,27 @@ def test_result_file_through_the_device_covariance_interface():
     E.problem = StandIn()
     s, lines = bundle_result_file(s, E)
     assert report_diff(lines, os.path.join(GOLD, 'camcalpm', 'camcal-dbatreport5.txt')) == []
+
+
+def test_sxb_script_result_file_reproduces_the_reference_report():
+    """data/script/sxb (sxb.xml): aerial block with object coordinates of 1e6 m, calibrated camera, 14
+    weighted control points, 2 check points (Check measurements tables), two image-point files with
+    different sigmas.  Exact but for 'First error' (start values from a resection at 1e6 m: 6e-5)."""
+    from oracle.loaders import load_sxb_script
+    from oracle.photogrammetry import resect, forwintersect
+    from oracle.bundle import bundle as obundle, bundle_cov as ocov
+    from dbat_b200.report import bundle_result_file
+    root = os.path.join(GOLD, 'sxb')
+    s = load_sxb_script(root)
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, _, fail = resect(s, 'all', cpId, 1, 0, cpId)
+    assert not fail
+    s2, _, _ = forwintersect(s1, 'all', True)
+    s3, ok, it, s0, E = obundle(copy.deepcopy(s2), 'gna')
+    assert ok and it == 4 and (E.numParams, E.numObs) == (1173, 2434)
+    s3, lines = bundle_result_file(s3, E, None, cov=ocov)
+    rep = os.path.join(root, 'result', 'report.txt')
+    exact = report_diff(lines, rep)
+    assert len(exact) == 1 and 'First error' in exact[0][1]
+    assert report_diff(lines, rep, rtol=1e-4) == []
+    assert sum('Check point delta' in l for l in lines) == 1
