@@ -164,14 +164,125 @@ def _invblock_sqrt(L, p, ix):
     return v2.T @ v2
 
 
-def bundle_cov(s, e, *which):
+BLOCK_PATH_ABOVE = 6000        # unknowns; beyond it the dense n x n factor does not fit
+
+
+def _prepare_blocks(s, e):
+    """bundle_cov.m:87-101 and VectorizedCOP (:330-478) for problems too large for a dense factor: the
+    same elimination order [OP; EO; IO], carried out on the blocks.  With N = [A B'; B D] (A the
+    block-diagonal OP part), L = [LA 0; LB LC] gives LC*LC' = D - B*inv(A)*B' and
+    inv(N) = [inv(A) + Y'*Cc*Y, -Y'*Cc; -Cc*Y, Cc],  Y = B*inv(A), Cc = inv(LC*LC')."""
+    J = e.final.weighted.J.tocsc()
+    N = (J.T @ J).tocsc()
+    opx = np.asarray(s.bundle.serial.OP.dest)
+    src = np.asarray(s.bundle.serial.OP.src)
+    pt, comp = src // 3, src % 3
+    camx = np.concatenate([np.asarray(s.bundle.serial.EO.dest), np.asarray(s.bundle.serial.IO.dest)])
+    nOP = s.OP.val.shape[1]
+    A = N[opx][:, opx].tocoo()
+    assert np.all(pt[A.row] == pt[A.col])
+    Ab = np.tile(np.eye(3), (nOP, 1, 1))
+    Ab[pt, comp, comp] = 0.0
+    np.add.at(Ab, (pt[A.row], comp[A.row], comp[A.col]), A.data)
+    try:
+        Ai = np.linalg.inv(Ab)
+        Aix = sp.csc_matrix(_gather_blockdiag(Ai, pt, comp), shape=(len(opx), len(opx)))
+        B = N[camx][:, opx].tocsc()
+        Y = (B @ Aix).tocsc()
+        S = N[camx][:, camx].toarray() - (Y @ B.T).toarray()
+        Lc = np.linalg.cholesky(S)
+        Li = sla.solve_triangular(Lc, np.eye(len(camx)), lower=True)
+        Cc = Li.T @ Li
+        fail = False
+    except np.linalg.LinAlgError:
+        Ai, Y, Cc, fail = None, None, None, True
+    e.final.factorized = NS(blocks=True, fail=fail, Ai=Ai, Y=Y, Cc=Cc, camx=camx, opx=opx, pt=pt, comp=comp)
+    return e
+
+
+def _gather_blockdiag(Ai, pt, comp):
+    """(data, (row, col)) of the block-diagonal matrix whose x-ordered rows are (pt, comp)."""
+    order = np.argsort(pt, kind='stable')
+    start = np.searchsorted(pt[order], np.arange(Ai.shape[0] + 1))
+    rows, cols = [], []
+    size = np.diff(start)
+    for k in (1, 2, 3):
+        for j0 in [np.flatnonzero(size == k)]:
+            if len(j0) == 0:
+                continue
+            idx = order[start[j0][:, None] + np.arange(k)[None, :]]          # (n, k) x-positions
+            rows.append(np.repeat(idx, k, axis=1).ravel())
+            cols.append(np.tile(idx, (1, k)).ravel())
+    r, c = np.concatenate(rows), np.concatenate(cols)
+    return Ai[pt[r], comp[r], comp[c]], (r, c)
+
+
+def _cov_blocks(s, e, w):
+    F = e.final.factorized
+    key = w[1:3].upper()
+    shape = getattr(s.bundle.est, key).shape
+    Nel = shape[0] * shape[1]
+    if key in ('IO', 'EO'):
+        des = getattr(s.bundle.deserial, key)
+        C = np.zeros((Nel, Nel))
+        if F.fail:
+            C[np.ix_(des.dest, des.dest)] = np.nan
+        else:
+            pos = np.full(int(max(F.camx.max(), F.opx.max())) + 1, -1)
+            pos[F.camx] = np.arange(len(F.camx))
+            ix = pos[des.src]
+            C[np.ix_(des.dest, des.dest)] = F.Cc[np.ix_(ix, ix)]
+        if len(w) == 3:
+            C = C * np.kron(np.eye(shape[1]), np.ones((shape[0], shape[0])))
+        return C
+    if w != 'cop':
+        raise ValueError("bundle_cov: '%s' needs the dense factor (n > %d)" % (w, BLOCK_PATH_ABOVE))
+    nOP = shape[1]
+    Cb = np.zeros((nOP, 3, 3))
+    if F.fail:
+        Cb[F.pt[:, None], F.comp[:, None], F.comp[None, :]] = np.nan
+    else:
+        Cb[:] = F.Ai
+        edges = np.searchsorted(F.pt, np.arange(0, nOP + 3000, 3000))   # chunks end on point boundaries
+        for c0, c1 in zip(edges[:-1], edges[1:]):                    # Y'*Cc*Y, diagonal blocks only
+            if c1 == c0:
+                continue
+            cols = np.arange(c0, c1)
+            Yc = F.Y[:, cols].toarray()
+            T = F.Cc @ Yc
+            for d in (-2, -1, 0, 1, 2):                              # neighbours in x order share a point
+                a = cols[max(0, -d):len(cols) - max(0, d)]
+                b = a + d
+                same = F.pt[a] == F.pt[b]
+                v = np.einsum('ij,ij->j', Yc[:, a[same] - c0], T[:, b[same] - c0])
+                Cb[F.pt[a[same]], F.comp[a[same]], F.comp[b[same]]] += v
+        fixed = np.ones((nOP, 3), bool)
+        fixed[F.pt, F.comp] = False
+        Cb[fixed] = 0.0
+        Cb[np.broadcast_to(fixed[:, None, :], Cb.shape)] = 0.0
+    base = np.repeat(np.arange(nOP) * 3, 9)
+    rr = base + np.tile(np.repeat(np.arange(3), 3), nOP)
+    cc = base + np.tile(np.tile(np.arange(3), 3), nOP)
+    return sp.csc_matrix((Cb.ravel(), (rr, cc)), shape=(3 * nOP, 3 * nOP))
+
+
+def bundle_cov(s, e, *which, blocks=None):
     """bundle_cov.m:1-214.  which ∈ {'CXX','CIO','CEO','COP','CIOF','CEOF','COPF'}.
 
     Returns dense arrays (the reference returns sparse matrices of the same shape):
     CIOF (NC*nImg)^2, CEOF (6*nImg)^2, COPF (3*nOP)^2, CIO/CEO/COP block-diagonal of
-    those, CXX n x n — each scaled by s0^2 (:213).
+    those, CXX n x n — each scaled by s0^2 (:213).  Above BLOCK_PATH_ABOVE unknowns (or with
+    blocks=True) the factorisation is done on the blocks (`_prepare_blocks`): same numbers, COP comes
+    back as a sparse block-diagonal matrix, COPF / CXX are not available.
     """
-    if e.final.factorized is None:
+    if blocks is None:
+        blocks = len(e.x) > BLOCK_PATH_ABOVE
+    if blocks:
+        if e.final.factorized is None or not getattr(e.final.factorized, 'blocks', False):
+            _prepare_blocks(s, e)
+        out = [e.s0 ** 2 * _cov_blocks(s, e, w.lower()) for w in which]
+        return out[0] if len(out) == 1 else out
+    if e.final.factorized is None or getattr(e.final.factorized, 'blocks', False):
         _prepare(s, e)
     F = e.final.factorized
     out = []

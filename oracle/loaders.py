@@ -177,6 +177,52 @@ def load_sxb_script(root):
     return s
 
 
+def load_roma_script(root):
+    """The DBAT struct of `data/script/romabundledemo/romabundledemo.xml` up to (not including) its
+    forward_intersection: 60 images of one calibrated camera (IO loaded; cc, px, py, K1, K2 estimated),
+    EO start values from `prior/initial_eo.txt` (degrees), 26321 object points without start values,
+    90561 image points at sigma 1 px, no control points.  The datum (`set_datum depend`, ref_cam 1) is
+    set by the caller after the intersection, as the script does.  markpts.txt is stored xz-compressed."""
+    import lzma
+    import os
+    xml = open(os.path.join(root, 'romabundledemo.xml')).read()
+    cam = parse_camera_xml(open(os.path.join(root, 'cameras', 'EOS5DMarkII.xml')).read())
+    io, pxSize, imSize, model, nK, nP = camera_internal(cam, True)
+    imgs = load_table(os.path.join(root, 'images', 'images.txt'))
+    eo = load_table(os.path.join(root, 'prior', 'initial_eo.txt'))
+    with lzma.open(os.path.join(root, 'measurements', 'markpts.txt.xz'), 'rt') as fh:
+        mk = np.loadtxt(fh, delimiter=',', comments='#')
+    img_ids = [int(r[0]) for r in imgs]
+    im_of = {v: i for i, v in enumerate(img_ids)}
+    op_ids, ip_op = np.unique(mk[:, 1].astype(np.int64), return_inverse=True)
+    nImg, nOP = len(img_ids), len(op_ids)
+    EO = np.full((6, nImg), np.nan)
+    for r in eo:
+        i = im_of[int(r[0])]
+        EO[0:3, i] = [float(v) for v in r[1:4]]
+        EO[3:6, i] = np.deg2rad([float(v) for v in r[4:7]])
+    s = new_struct(np.tile(io[:, None], (1, nImg)), EO, np.full((3, nOP), np.nan), mk[:, 2:4].T,
+                   np.array([im_of[int(v)] for v in mk[:, 0]]), ip_op, pxSize[:, None], imSize[:, None],
+                   model, nK, nP, 1.0)
+    s.OP.id = op_ids
+    s.OP.label = [''] * nOP
+    s.EO.id = np.array(img_ids)
+    s.EO.name = [r[1].replace('\\', '/').split('/')[-1] for r in imgs]
+    s.bundle.est.IO[:] = False
+    s.bundle.est.IO[[0, 1, 2, 5, 6], :] = True               # all but aspect, skew, P, K3
+    s.bundle.est.EO[:] = True
+    s.bundle.est.OP[:] = True
+    s.prior.OP.isCtrl = np.zeros(nOP, bool)
+    s.prior.OP.isCheck = np.zeros(nOP, bool)
+    s.IP.sigmas = np.array([1.0])
+    s.IO.model.camUnit = 'mm'
+    m = re.search(r'<name>\s*([^<]*?)\s*</name>', xml)
+    s.proj = NS(objUnit='m', x0desc='', title=m.group(1) if m else '', UUID='', cptFile='',
+                fileName=os.path.join(root, 'romabundledemo.xml'),
+                EOfile=os.path.join(root, 'prior', 'initial_eo.txt'))
+    return s
+
+
 def load_camera_stations(path):
     """result/camera_stations.txt → (ids, EO 6xN [radians], std 6xN as printed)."""
     rows = load_table(path)

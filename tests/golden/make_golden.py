@@ -31,6 +31,15 @@ FILES = {
         'data/script/sxb/reference/sxb-control.txt',
         'data/script/sxb/result/report.txt',
     ],
+    'romabundledemo': [                                     # markpts.txt (2.6 MB) is stored xz-compressed
+        'data/script/romabundledemo/romabundledemo.xml',
+        'data/script/romabundledemo/cameras/EOS5DMarkII.xml',
+        'data/script/romabundledemo/images/images.txt',
+        'data/script/romabundledemo/prior/initial_eo.txt',
+        'data/script/romabundledemo/measurements/markpts.txt',
+        'data/script/romabundledemo/result/report.txt',
+        'data/script/romabundledemo/result/EOS5DMarkII.xml',
+    ],
     'prague2016cam': [
         'data/prague2016/cam/pmexports/weighted-no-orient-pmexport.txt',
         'data/prague2016/cam/pmexports/fixed-no-orient-pmexport.txt',
@@ -106,7 +115,13 @@ def main():
                 rel = os.path.basename(f)
             dst = os.path.join(HERE, sub, rel)
             os.makedirs(os.path.dirname(dst), exist_ok=True)
-            shutil.copyfile(os.path.join(REF, f), dst)
+            if os.path.getsize(os.path.join(REF, f)) > (1 << 20):
+                import lzma
+                dst += '.xz'
+                with open(os.path.join(REF, f), 'rb') as src, lzma.open(dst, 'wb', preset=9) as out:
+                    shutil.copyfileobj(src, out)
+            else:
+                shutil.copyfile(os.path.join(REF, f), dst)
             print('copied', f, '->', os.path.relpath(dst, HERE))
 
 

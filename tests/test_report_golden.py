@@ -302,3 +302,77 @@ def test_sxb_script_result_file_reproduces_the_reference_report():
     assert len(exact) == 1 and 'First error' in exact[0][1]
     assert report_diff(lines, rep, rtol=1e-4) == []
     assert sum('Check point delta' in l for l in lines) == 1
+
+
+def roma_struct():
+    from oracle.loaders import load_roma_script
+    return load_roma_script(os.path.join(GOLD, 'romabundledemo'))
+
+
+ROMA_CAMERA = dict(cc=24.5425002994450807, px=18.0816295411089882, py=12.0164475994770967,
+                   K1=0.000221523347553201198, K2=-1.86984852928280264e-07)      # result/EOS5DMarkII.xml
+
+
+def test_roma_script_result_file_reproduces_the_reference_report():
+    """data/script/romabundledemo: the reference's mid-size benchmark (7.28 s / 5 iterations in
+    MATLAB) - 60 images, 26321 object points, 90561 image points, n = 79321, self-calibration of cc, pp, K1,
+    K2, no control points, datum by `seteoest(s,'depend',1)`, i.e. the datum and problem shape of the
+    north-star workload.  Forward intersection from the prior EO, GNA: 5 iterations, 8641.39 -> 185.94,
+    sigma0 0.582769, and the whole 800-line result file - every camera station with deviations and
+    correlations, coverage, 26321-point statistics - exactly; the calibrated camera agrees with the
+    18-digit values of result/EOS5DMarkII.xml to 1e-13.  The posterior covariances of this size come from the
+    oracle's block path (`oracle/bundle.py:_prepare_blocks`, checked against the dense factor below)."""
+    from oracle.photogrammetry import forwintersect
+    from oracle.dbatstruct import seteoest_depend
+    from oracle.bundle import bundle as obundle, bundle_cov as ocov
+    from dbat_b200.report import bundle_result_file
+    s = roma_struct()
+    s, ids, _ = forwintersect(s, 'all', True)
+    assert len(ids) == 26321
+    seteoest_depend(s, 0)
+    s, ok, it, s0, E = obundle(s, 'gna')
+    assert ok and it == 5 and (E.numParams, E.numObs, E.redundancy) == (79321, 181122, 101801)
+    assert abs(s0 - 0.582769) < 6e-7 and abs(E.res[0] - 8641.39) < 6e-3 and abs(E.res[-1] - 185.94) < 6e-4
+    io = s.IO.val[:, 0]
+    got = dict(cc=io[0], px=io[1], py=-io[2], K1=-io[5], K2=-io[6])
+    for k, v in ROMA_CAMERA.items():
+        assert abs(got[k] - v) < 1e-13 * abs(v) + 1e-20, k
+    s, lines = bundle_result_file(s, E, None, cov=ocov)
+    assert report_diff(lines, os.path.join(GOLD, 'romabundledemo', 'result', 'report.txt')) == []
+
+
+def test_oracle_block_covariance_path_equals_the_dense_factor():
+    """oracle/bundle.py: `bundle_cov(..., blocks=True)` (what large problems use) against the literal
+    dense restatement of bundle_cov.m, on a self-calibrating project and on one with prior OP observations
+    and partly fixed points."""
+    from oracle.bundle import bundle_cov as ocov
+    for run in (lambda: camcal_pm_run('camcal-pmexport.txt'),
+                lambda: prague_run(os.path.join(GOLD, 'prague2016sxb'), 'w-op1', 'ctrlpts-weighted.txt')):
+        s, ok, it, s0, E = run()
+        dense = {w: np.asarray(ocov(s, E, w)) for w in ('CIOF', 'CEOF', 'CIO', 'CEO', 'COP')}
+        E.final.factorized = None
+        for w, D in dense.items():
+            B = ocov(s, E, w, blocks=True)
+            B = B.toarray() if hasattr(B, 'toarray') else B
+            assert np.abs(B - D).max() <= 1e-9 * max(np.abs(D).max(), 1e-300), w
+
+
+@pytest.mark.gpu
+def test_roma_result_file_from_the_device():
+    """The roma script project on the device: forward intersection, dependent datum, GNA self-calibration
+    (n = 79321, reduced camera system of order 358), covariances and result file.  5 iterations and the
+    reference's report to the printed digits (1e-5 relative, one unit of the last digit); the calibrated
+    camera to 1e-9 of the reference's 18-digit values (the north-star tolerance)."""
+    import dbat_b200
+    from dbat_b200.report import bundle_result_file
+    s = roma_struct()
+    s, ids, _ = dbat_b200.forwintersect(s, 'all', True)
+    dbat_b200.seteoest_depend(s, 0)
+    s, ok, it, s0, E = dbat_b200.bundle(s, 'gna')
+    assert ok and it == 5 and (E.numParams, E.numObs) == (79321, 181122)
+    io = s.IO.val[:, 0]
+    got = dict(cc=io[0], px=io[1], py=-io[2], K1=-io[5], K2=-io[6])
+    for k, v in ROMA_CAMERA.items():
+        assert abs(got[k] - v) < 1e-9 * abs(v), k
+    s, lines = bundle_result_file(s, E)
+    assert report_diff(lines, os.path.join(GOLD, 'romabundledemo', 'result', 'report.txt'), rtol=1e-5) == []
