@@ -1,0 +1,384 @@
+"""Ingest: project files -> the flat DBAT struct the device path consumes.
+
+Host mirror of the functions every reference demo calls between the file and `bundle`:
+
+  loadpm            `code/file/loadpm.m:104-404`       PhotoModeler text export -> prob
+  prob2dbatstruct   `code/misc/prob2dbatstruct.m:198-520`  prob -> struct (shared camera)
+  loadcpt           `code/file/loadcpt.m:23-112`       control point table
+  matchcpt          `code/misc/matchcpt.m:24-98`
+  setcpt            `code/misc/setcpt.m:20-52`
+  setcamvals        `code/misc/setcamvals.m:21-148`
+  setcamest         `code/misc/setcamest.m:28-125`
+  seteoest          `code/misc/seteoest.m:26-128`      (including the 'depend' datum)
+  cleareo, clearop  `code/misc/cleareo.m`, `clearop.m`
+
+The reference builds the struct with per-image loops and sparse `vis` / `ix` matrices
+(`prob2dbatstruct.m:349-365`); here the image points are sorted once by (image, object point) and kept
+as flat index vectors (`IP.img`, `IP.op`), which is the layout `dbat_create` uploads.  Indices are
+0-based; ids are the file's.  Image-variant cameras (`individualCameras`) are not supported by the
+device path and are refused.
+"""
+import os
+import uuid as _uuid
+from types import SimpleNamespace as NS
+
+import numpy as np
+
+from .dbatstruct import new_struct, seteoest_depend
+
+IO_ROWS = ('cc', 'px', 'py', 'as', 'sk')
+
+
+def _numbers(lines, ncol):
+    if not lines:
+        return np.zeros((0, ncol))
+    return np.array(' '.join(lines).split(), dtype=float).reshape(len(lines), -1)
+
+
+def loadpm(name, imSz=None):
+    """loadpm.m: parse a PhotoModeler text export.  Five header lines (title; tolerance, iterations and
+    - in newer exports - image size; default std; default camera; its std), one six-line block per image
+    up to a blank line, then control points, object points and mark points, each up to a blank line.
+    "Smart" points (exported with zero sigma) numbered from a range that overlaps the normal points are
+    shifted above them (:385-404).  Returns prob with job / images / ctrlPts / objPts / markPts /
+    rawOPids / OPlabels as the reference names them."""
+    with open(name) as fh:
+        lines = fh.read().split('\n')
+    tol = [float(v) for v in lines[1].split()]
+    if imSz is None:
+        imSz = tol[2:4] if len(tol) > 2 else [np.nan, np.nan]
+    job = NS(fileName=name, title=lines[0].rstrip('\r'), tol=tol[0], maxIter=tol[1],
+             defStd=np.array(lines[2].split(), float), defCam=np.array(lines[3].split(), float),
+             defCamStd=np.array(lines[4].split(), float), imSz=np.array(imSz, float))
+    k = 5
+    images = []
+    while k < len(lines) and lines[k].split() and lines[k].split()[0].lstrip('-').isdigit():
+        head = lines[k].split(None, 1)
+        num = lambda t: np.array(t.split()[1:], float)
+        cov = num(lines[k + 3]) if lines[k + 3].split() else np.full(3, np.nan)
+        images.append(NS(imName=head[1].strip() if len(head) > 1 else '', outer=num(lines[k + 1]),
+                         outerStd=num(lines[k + 2]), outerCov=cov, inner=num(lines[k + 4]),
+                         innerStd=num(lines[k + 5]), imSz=job.imSz, id=len(images) + 1))
+        k += 6
+    # image labels: names without their common directory (:196-211)
+    names = [im.imName.replace('\\', '/') for im in images]
+    common = os.path.commonpath([os.path.dirname(n) for n in names]) if names and all('/' in n for n in names) else ''
+    for im, n in zip(images, names):
+        im.label = n[len(common) + 1:] if common else n
+
+    def section(k):
+        e = k
+        while e < len(lines) and lines[e].strip():
+            e += 1
+        return lines[k:e], e + 1
+    k += 1
+    rows, k = section(k)
+    ctrlPts = _numbers(rows, 7)
+    rows, k = section(k)
+    objPts = _numbers(rows, 7)
+    rows, k = section(k)
+    markPts = _numbers(rows, 6)
+    rawOPids = objPts[:, 0].copy()
+    isCtrl = np.isin(objPts[:, 0], ctrlPts[:, 0])
+    OPlabels = [('%d' % i) if c else '' for i, c in zip(rawOPids, isCtrl)]
+    if len(markPts) and len(objPts):
+        smart = np.all(markPts[:, 4:6] == 0, axis=1)
+        normId, smartId = np.unique(markPts[~smart, 1]), np.unique(markPts[smart, 1])
+        split = np.flatnonzero(np.diff(objPts[:, 0]) < 0)
+        if len(split) and len(normId) and len(smartId):
+            shift = normId.max() + 1 - smartId.min()
+            markPts[smart, 1] += shift
+            isSmartObj = np.isin(objPts[:, 0], smartId)
+            isSmartObj[:split[0] + 1] = False
+            objPts[isSmartObj, 0] += shift
+    return NS(job=job, images=images, ctrlPts=ctrlPts, cptFile='', checkPts=np.zeros((0, 7)), objPts=objPts,
+              priorCamPos=np.zeros((0, 7)), rawOPids=rawOPids, OPlabels=OPlabels, markPts=markPts)
+
+
+def prob2dbatstruct(prob, individualCameras=False):
+    """prob2dbatstruct.m: the DBAT struct of a loaded project.  One camera shared by all images, taken
+    from the export's default camera with the sign conventions of :222-232 (py, K, P negated), square
+    pixels from the sensor height and the aspect folded into IO row 4 (:236-247); EO angles from the
+    export's kappa, phi, omega in degrees (:262-265); legacy distortion model 1; IO fixed, EO free, OP
+    free except control points with zero prior sigma; image points sorted by (image, point id); if any
+    exported image sigma is zero all are set to 1 px (:367-374)."""
+    if individualCameras:
+        raise NotImplementedError('image-variant cameras are not supported by the device path')
+    nImg = len(prob.images)
+    nK, nP = 3, 2
+    inner, innerStd = np.asarray(prob.job.defCam, float), np.asarray(prob.job.defCamStd, float)
+    imSz = np.asarray(prob.job.imSz, float)
+    IO = np.zeros(5 + nK + nP)
+    IOstd = np.full(5 + nK + nP, np.nan)
+    IO[0], IO[1], IO[2] = inner[0], inner[1], -inner[2]
+    IOstd[0:3] = innerStd[0:3]
+    IO[5:5 + nK + nP] = -inner[5:5 + nK + nP]
+    IOstd[5:5 + nK + nP] = innerStd[5:5 + nK + nP]
+    ssSize = inner[3:5]
+    px = ssSize / imSz
+    IO[3] = 1 - px[0] / px[1]
+    pxSize = np.array([px[1], px[1]])
+    outer = np.array([im.outer for im in prob.images]).T
+    outerStd = np.array([im.outerStd for im in prob.images]).T
+    EO = np.vstack([outer[0:3], np.deg2rad(outer[[5, 4, 3]])])
+    EOstd = np.vstack([outerStd[0:3], np.deg2rad(outerStd[[5, 4, 3]])])
+    order = np.argsort(prob.objPts[:, 0], kind='stable')
+    OPid = prob.objPts[order, 0].astype(np.int64)
+    nOP = len(OPid)
+    OP = prob.objPts[order, 1:4].T.copy()
+    priorCP = np.full((3, nOP), np.nan)
+    priorCPstd = np.full((3, nOP), np.nan)
+    for tab in (prob.ctrlPts, prob.checkPts):
+        hit = np.isin(tab[:, 0], OPid)
+        col = np.searchsorted(OPid, tab[hit, 0])
+        priorCP[:, col] = tab[hit, 1:4].T
+        priorCPstd[:, col] = tab[hit, 4:7].T
+    isCtrl = np.isin(OPid, prob.ctrlPts[:, 0])
+    isCheck = np.isin(OPid, prob.checkPts[:, 0])
+    mk = prob.markPts[np.isin(prob.markPts[:, 1], OPid)]
+    mstd = mk[:, 4:6].copy()
+    sigmas = np.unique(mstd)
+    if np.any(sigmas == 0):
+        mstd[:] = 1.0
+        sigmas = np.array([1.0])
+    s = new_struct(np.tile(IO[:, None], (1, nImg)), EO, OP, mk[:, 2:4].T, mk[:, 0].astype(np.int64),
+                   np.searchsorted(OPid, mk[:, 1]), pxSize[:, None], imSz[:, None], 1, nK, nP, mstd.T)
+    names = [im.imName.replace('\\', '/') for im in prob.images]
+    imDir = os.path.commonpath([os.path.dirname(n) for n in names]) if names and all('/' in n for n in names) else ''
+    s.proj = NS(objUnit='m', x0desc='', title=prob.job.title, imDir=imDir + '/' if imDir else '',
+                fileName=prob.job.fileName, cptFile=prob.cptFile, EOfile='', UUID=str(_uuid.uuid4()))
+    s.IO.model.camUnit = 'mm'
+    s.IO.sensor.ssSize = np.tile(ssSize[:, None], (1, nImg))
+    s.EO.name = [n[len(imDir) + 1:] if imDir else n for n in names]
+    s.EO.label = [im.label.replace('\\', '/') for im in prob.images]
+    s.EO.id = np.array([im.id for im in prob.images])
+    s.OP.id = OPid
+    s.OP.rawId = prob.rawOPids[order].astype(np.int64)
+    s.OP.label = [prob.OPlabels[i] for i in order]
+    s.IP.sigmas = sigmas
+    s.prior.IO.val[:] = s.IO.val
+    s.prior.IO.std[:] = IOstd[:, None]
+    s.prior.EO.val[:] = EO
+    s.prior.EO.std[:] = EOstd
+    s.prior.OP.val, s.prior.OP.std = priorCP, priorCPstd
+    s.prior.OP.isCtrl, s.prior.OP.isCheck = isCtrl, isCheck
+    s.prior.OP.use = np.tile(isCtrl & ~np.all(priorCPstd == 0, axis=0), (3, 1))
+    s.bundle.est.IO[:] = False
+    s.bundle.est.EO[:] = True
+    s.bundle.est.OP = ~(priorCPstd == 0)
+    return s
+
+
+def loadcpt(fName, has=(True, True)):
+    """loadcpt.m: control point table `id,name,x,y,z[,std...]`; 0, 1, 2 or 3 sigmas per line mean fixed,
+    sigma_xyz, (sigma_xy, sigma_z), (sigma_x, sigma_y, sigma_z)."""
+    hasId, hasName = has
+    ids, names, pos, std = [], [], [], []
+    with open(fName) as fh:
+        for line in fh:
+            line = line.strip()
+            if not line or line[0] == '#':
+                continue
+            tok = [t.strip() for t in line.split(',')]
+            ids.append(int(tok.pop(0)) if hasId else np.nan)
+            names.append(tok.pop(0) if hasName else '')
+            a = [float(t) for t in tok if t != '']
+            pos.append(a[0:3])
+            if len(a) == 3:
+                std.append([0.0, 0.0, 0.0])
+            elif len(a) == 4:
+                std.append([a[3]] * 3)
+            elif len(a) == 5:
+                std.append([a[3], a[3], a[4]])
+            elif len(a) == 6:
+                std.append(a[3:6])
+            else:
+                raise ValueError('Bad number of items on CP line.')
+    return NS(id=np.array(ids), name=names, pos=np.array(pos, float).reshape(-1, 3).T,
+              std=np.array(std, float).reshape(-1, 3).T, cov=None, fileName=fName)
+
+
+def matchcpt(s, pts, match='auto', check=False):
+    """matchcpt.m: (i, j) - struct points i (control points, or check points with check=True) and the
+    rows j of the table they match, by label, by raw id, or both ('auto': whatever the table carries)."""
+    byId = match in ('id', 'both') or (match == 'auto' and np.any(~np.isnan(np.asarray(pts.id, float))))
+    byLabel = match in ('label', 'both') or (match == 'auto' and any(pts.name))
+    sel = np.flatnonzero(s.prior.OP.isCheck if check else s.prior.OP.isCtrl)
+
+    def by(keys_s, keys_p):
+        common, a, b = np.intersect1d(np.asarray(keys_s), np.asarray(keys_p), return_indices=True)
+        return sel[a], b
+    il = jl = ii = ji = None
+    if byLabel:
+        il, jl = by([s.OP.label[c] for c in sel], pts.name)
+    if byId:
+        ii, ji = by(np.asarray(s.OP.rawId)[sel], pts.id)
+    if byLabel and byId:
+        if len(il):
+            if not (np.array_equal(il, ii) and np.array_equal(jl, ji)):
+                raise ValueError('Inconsistent match')
+            return il, jl
+        return ii, ji
+    if byLabel:
+        return il, jl
+    if byId:
+        return ii, ji
+    raise ValueError('Neither match-by-id nor match-by-label possible.')
+
+
+def setcpt(s, pts, i, j, isCtrl=True):
+    """setcpt.m: copy prior position / sigma / label of table rows j to points i; control points with zero
+    sigma become fixed, with non-zero sigma estimated and observed; check points are estimated, not observed."""
+    s.proj.cptFile = pts.fileName
+    s.prior.OP.val[:, i] = pts.pos[:, j]
+    s.OP.val[:, i] = pts.pos[:, j]
+    s.prior.OP.std[:, i] = pts.std[:, j]
+    for a, b in zip(i, j):
+        if pts.name[b]:
+            s.OP.label[a] = pts.name[b]
+    s.prior.OP.isCtrl[i] = isCtrl
+    s.prior.OP.isCheck[i] = not isCtrl
+    if isCtrl:
+        free = ~np.all(pts.std[:, j] == 0, axis=0)
+        s.prior.OP.use[:, i] = free
+        s.bundle.est.OP[:, i] = free
+    else:
+        s.prior.OP.use[:, i] = False
+        s.bundle.est.OP[:, i] = True
+    return s
+
+
+def _io_rows(s, name, est=None):
+    """Rows of IO.val addressed by a parameter name of setcamvals / setcamest."""
+    nK, nP = s.IO.model.nK, s.IO.model.nP
+    if name in IO_ROWS:
+        return [IO_ROWS.index(name)]
+    if name == 'lin' or name == 'af':
+        return list(range(5))
+    if name == 'pp':
+        return [1, 2]
+    if name == 'K':
+        return list(range(5, 5 + nK))
+    if name == 'P':
+        return list(range(5 + nK, 5 + nK + nP))
+    if name and name[0] in 'KP' and name[1:].isdigit():
+        n = int(name[1:])
+        if name[0] == 'K':
+            if not 1 <= n <= nK:
+                raise ValueError('K number out of range')
+            if est is None:
+                return [4 + n]
+            return list(range(5, 5 + n)) if est else list(range(4 + n, 5 + nK))      # setcamest.m:84-88
+        if not 1 <= n <= nP:
+            raise ValueError('P number out of range')
+        if est is None:
+            return [4 + nK + n]
+        if est:                                                                       # setcamest.m:95-101
+            return list(range(5 + nK, 5 + nK + max(n, 2)))                            # P1 brings P2 along
+        return list(range(4 + nK + (1 if n == 2 else n), 5 + nK + nP))                # and P2 takes P1 out
+    raise ValueError("Bad parameter '%s'" % name)
+
+
+def setcamvals(s, *args):
+    """setcamvals.m: setcamvals(s[, 'prior'][, cams|'all'][, 'loaded'][, 'default', cc][, name, value ...])."""
+    args = list(args)
+    prior = bool(args) and isinstance(args[0], str) and args[0] == 'prior'
+    if prior:
+        args.pop(0)
+    IO = s.prior.IO if prior else s.IO
+    ix = slice(None)
+    if args and not isinstance(args[0], str):
+        ix = np.atleast_1d(args.pop(0))
+    elif args and args[0] == 'all':
+        args.pop(0)
+    if args and args[0] == 'loaded':
+        args.pop(0)
+        IO.val[:, ix] = s.prior.IO.val[:, ix]
+    if args and args[0] == 'default':
+        args.pop(0)
+        if not args or isinstance(args[0], str):
+            raise ValueError('SETCAMVALS: CC must be numeric')
+        ss = getattr(s.IO.sensor, 'ssSize', None)
+        ss = s.IO.sensor.imSize * s.IO.sensor.pxSize if ss is None else ss
+        IO.val[0, ix] = args.pop(0)
+        IO.val[1, ix] = 0.5 * ss[0, ix]
+        IO.val[2, ix] = -0.5 * ss[1, ix]
+        IO.val[3:, ix] = 0
+    if len(args) % 2:
+        raise ValueError('SETCAMVALS: Trailing arguments must come in pairs')
+    for name, val in zip(args[0::2], args[1::2]):
+        rows = _io_rows(s, name)
+        if set(rows) & {3, 4} and np.any(np.abs(s.IO.model.distModel[ix]) < 3) and np.any(np.asarray(val) != 0):
+            raise ValueError('SETCAMVALS: Camera model only supports zero %s' % name)
+        IO.val[np.ix_(rows, np.arange(IO.val.shape[1])[ix])] = np.reshape(val, (-1, 1)) if np.ndim(val) else val
+    return s
+
+
+def setcamest(s, *args):
+    """setcamest.m: setcamest(s[, cams], names...) with 'not' switching the names after it off; 'all' and
+    'af' leave aspect and skew off for models 1, 2 and -1, which have no affine terms."""
+    args = list(args)
+    cams = np.arange(s.IO.val.shape[1])
+    if args and not isinstance(args[0], str):
+        cams = np.atleast_1d(args.pop(0))
+    affine = np.abs(s.IO.model.distModel[cams]) >= 3
+    doEst = True
+    for a in args:
+        if a == 'not':
+            if not doEst:
+                raise ValueError('SETCAMEST: Cannot specify not twice')
+            doEst = False
+            continue
+        if a in ('all', 'af'):
+            rows = list(range(s.bundle.est.IO.shape[0])) if a == 'all' else list(range(5))
+            val = np.full((len(rows), len(cams)), doEst)
+            val[3:5] &= affine
+            s.bundle.est.IO[np.ix_(rows, cams)] = val
+            continue
+        rows = _io_rows(s, a, doEst) if (a and a[0] in 'KP' and a[1:].isdigit()) else _io_rows(s, a)
+        if doEst and set(rows) & {3, 4} and np.any(~affine) and a in ('as', 'sk'):
+            raise ValueError('SETCAMEST: Model does not support skew, aspect.')
+        s.bundle.est.IO[np.ix_(rows, cams)] = doEst
+    return s
+
+
+_EO_ROWS = {'x': [0], 'y': [1], 'z': [2], 'pos': [0, 1, 2], 'om': [3], 'ph': [4], 'ka': [5],
+            'ang': [3, 4, 5], 'all': list(range(6))}
+
+
+def seteoest(s, *args):
+    """seteoest.m: seteoest(s[, cams], names...) ('not' as in setcamest, 'none' = nothing estimated), or
+    seteoest(s, 'depend'[, camNo]) for the dependent-pair datum (camNo 1-based as in the reference)."""
+    args = list(args)
+    if args and isinstance(args[0], str) and args[0] == 'depend':
+        if len(args) > 2:
+            raise NotImplementedError("seteoest 'depend' with a fixed axis")
+        return seteoest_depend(s, int(args[1]) - 1 if len(args) > 1 else 0)
+    cams = np.arange(s.EO.val.shape[1])
+    doEst = True
+    for a in args:
+        if not isinstance(a, str):
+            cams = np.atleast_1d(a)
+        elif a == 'not':
+            if not doEst:
+                raise ValueError('SETEOEST: Cannot specify not twice')
+            doEst = False
+        elif a == 'none':
+            s.bundle.est.EO[np.ix_(range(6), cams)] = False
+        elif a in _EO_ROWS:
+            s.bundle.est.EO[np.ix_(_EO_ROWS[a], cams)] = doEst
+        else:
+            raise ValueError('SETEOEST: Bad argument string %s' % a)
+    return s
+
+
+def cleareo(s):
+    """cleareo.m: NaN every EO element that is estimated and has no prior observation."""
+    s.EO.val[s.bundle.est.EO & ~s.prior.EO.use] = np.nan
+    return s
+
+
+def clearop(s):
+    """clearop.m: the same for the object points."""
+    s.OP.val[s.bundle.est.OP & ~s.prior.OP.use] = np.nan
+    return s

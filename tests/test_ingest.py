@@ -1,0 +1,147 @@
+"""dbat_b200/ingest.py (loadpm, prob2dbatstruct, loadcpt / matchcpt / setcpt, setcamvals, setcamest,
+seteoest, cleareo, clearop) against the oracle's project loaders and, end to end, against the reference's
+result files: the demo scripts below are the reference's demos, call for call."""
+import copy
+import os
+
+import numpy as np
+import pytest
+
+from dbat_b200 import ingest
+from test_report_golden import GOLD, report_diff
+
+CAMCAL = os.path.join(GOLD, 'camcalpm')
+
+
+def camcaldemo(pm, model=3):
+    """code/demo/camcaldemo.m:40-98 (camcaldemo_allmodels.m for the other models)."""
+    prob = ingest.loadpm(os.path.join(CAMCAL, pm))
+    s0 = ingest.prob2dbatstruct(prob)
+    if not s0.prior.OP.isCtrl.any():
+        s0.prior.OP.isCtrl = np.asarray(s0.OP.id) > 1000
+    pts = ingest.loadcpt(os.path.join(CAMCAL, 'camcal-fixed.txt'))
+    i, j = ingest.matchcpt(s0, pts)
+    s0 = ingest.setcpt(s0, pts, i, j)
+    s0.IO.model.distModel[:] = model
+    s0 = ingest.setcamvals(s0, 'default', 7.3)
+    s0 = ingest.setcamest(s0, 'all', 'not', 'sk')
+    s0 = ingest.seteoest(s0, 'all')
+    s0 = ingest.cleareo(s0)
+    return ingest.clearop(s0)
+
+
+def assert_same_struct(a, b):
+    for path in ('IO.val', 'EO.val', 'OP.val', 'IP.val', 'IP.std', 'IP.img', 'IP.op', 'IP.sigmas', 'OP.id',
+                 'IO.sensor.pxSize', 'IO.sensor.imSize', 'IO.model.distModel', 'bundle.est.IO', 'bundle.est.EO',
+                 'bundle.est.OP', 'prior.OP.use', 'prior.OP.isCtrl', 'prior.OP.isCheck', 'prior.EO.use', 'prior.IO.use'):
+        x, y = a, b
+        for k in path.split('.'):
+            x, y = getattr(x, k), getattr(y, k)
+        if path == 'OP.val':        # the demo's mean control-point offset is summed in a different order
+            np.testing.assert_allclose(np.asarray(x), np.asarray(y), rtol=1e-12, atol=1e-9, err_msg=path)
+        else:
+            np.testing.assert_array_equal(np.asarray(x), np.asarray(y), err_msg=path)
+    ctrl = a.prior.OP.isCtrl
+    np.testing.assert_allclose(a.prior.OP.val[:, ctrl], b.prior.OP.val[:, ctrl], rtol=1e-12, atol=1e-9)
+    np.testing.assert_array_equal(a.prior.OP.std[:, ctrl], b.prior.OP.std[:, ctrl])
+    assert list(a.OP.label) == list(b.OP.label) and list(a.EO.name) == list(b.EO.name)
+    assert a.proj.title == b.proj.title and (a.IO.model.nK, a.IO.model.nP) == (b.IO.model.nK, b.IO.model.nP)
+
+
+@pytest.mark.parametrize('pm', ['camcal-pmexport.txt', 'camcal-pmexport5.txt', 'camcal-pmexport-1ray.txt',
+                                'camcal-pmexport-missing-obs.txt'])
+@pytest.mark.parametrize('model', [3, 1, -1])
+def test_camcaldemo_ingest_equals_the_oracle_loader(pm, model):
+    from oracle.loaders import camcal_pm_struct
+    s = camcaldemo(pm, model)
+    o = camcal_pm_struct(os.path.join(CAMCAL, pm), os.path.join(CAMCAL, 'camcal-fixed.txt'), model=model)
+    assert_same_struct(s, o)
+
+
+def prague2016_pm(root, stub, cps, orient='no'):
+    """code/demo/prague2016_pm.m:140-195: loaded (fixed) camera, control points from the reference file
+    moved by the mean offset to PhotoModeler's frame, EO and OP cleared."""
+    prob = ingest.loadpm(os.path.join(root, 'pmexports', '%s-%s-orient-pmexport.txt' % (stub, orient)))
+    s0 = ingest.prob2dbatstruct(prob)
+    s0 = ingest.setcamvals(s0, 'loaded')
+    s0 = ingest.setcamest(s0, 'not', 'all')
+    ctrlPts = ingest.loadcpt(os.path.join(root, 'ref', 'ctrlpts-%s.txt' % cps))
+    assert np.all(np.isin(prob.ctrlPts[:, 0], ctrlPts.id))
+    _, ia, ib = np.intersect1d(prob.ctrlPts[:, 0], ctrlPts.id, return_indices=True)
+    ctrlPts.pos = ctrlPts.pos + np.mean(prob.ctrlPts[ia, 1:4].T - ctrlPts.pos[:, ib], axis=1, keepdims=True)
+    i, j = ingest.matchcpt(s0, ctrlPts, 'id')
+    s0 = ingest.setcpt(s0, ctrlPts, i, j)
+    s0 = ingest.cleareo(s0)
+    return ingest.clearop(s0)
+
+
+PRAGUE_CASES = [('prague2016cam', 'fixed', 'fixed'), ('prague2016cam', 'weighted', 'weighted'),
+                ('prague2016sxb', 'f-op0', 'fixed'), ('prague2016sxb', 'w-op0', 'weighted'),
+                ('prague2016sxb', 'w-op1', 'weighted'), ('prague2016sxb', 'wsmart', 'weighted')]
+
+
+@pytest.mark.parametrize('project,stub,cps', PRAGUE_CASES)
+def test_prague2016_ingest_equals_the_oracle_loader(project, stub, cps):
+    from oracle.loaders import prague_cam_struct
+    root = os.path.join(GOLD, project)
+    s = prague2016_pm(root, stub, cps)
+    o = prague_cam_struct(root, stub, 'ctrlpts-%s.txt' % cps)
+    o.EO.val[:] = np.nan
+    o.OP.val[:, ~o.prior.OP.isCtrl] = np.nan
+    assert_same_struct(s, o)
+
+
+def _solve_and_report(s):
+    """resect -> forwintersect -> bundle (oracle, CPU) -> result file, as every demo continues."""
+    from oracle.photogrammetry import resect, forwintersect
+    from oracle.bundle import bundle as obundle, bundle_cov as ocov
+    from dbat_b200.report import bundle_result_file
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, _, fail = resect(s, 'all', cpId, 1, 0, cpId)
+    assert not fail
+    s2, _, _ = forwintersect(s1, 'all', True)
+    s3, ok, it, s0, E = obundle(copy.deepcopy(s2), 'gna')
+    assert ok
+    return bundle_result_file(s3, E, None, cov=ocov)[1]
+
+
+def test_camcaldemo_from_file_to_result_file():
+    """camcaldemo.m with this package's ingest in front of the solver: the reference's 610-line report."""
+    s = camcaldemo('camcal-pmexport.txt')
+    s.proj.x0desc = 'Camera calibration from EXIF value'
+    assert report_diff(_solve_and_report(s), os.path.join(GOLD, 'dbatexports', 'camcal-dbatreport.txt')) == []
+
+
+@pytest.mark.parametrize('project,stub,cps', [PRAGUE_CASES[1], PRAGUE_CASES[4], PRAGUE_CASES[5]])
+def test_prague2016_from_file_to_result_file(project, stub, cps):
+    root = os.path.join(GOLD, project)
+    lines = _solve_and_report(prague2016_pm(root, stub, cps))
+    assert report_diff(lines, os.path.join(root, 'dbatexports', '%s-no-orient-dbatreport.txt' % stub)) == []
+
+
+def test_setters_follow_the_reference_argument_rules():
+    s = camcaldemo('camcal-pmexport5.txt')
+    s = ingest.setcamest(s, 'not', 'all')
+    assert not s.bundle.est.IO.any()
+    s = ingest.setcamest(s, 'cc', 'pp', 'K2')                       # K2 brings K1 (setcamest.m:84-86)
+    assert list(np.flatnonzero(s.bundle.est.IO[:, 0])) == [0, 1, 2, 5, 6]
+    s = ingest.setcamest(s, 'P1')                                   # P1 brings P2 (setcamest.m:95-98)
+    assert s.bundle.est.IO[8:10].all()
+    s = ingest.setcamest(s, 'not', 'K2')                            # not K2 takes K2 and K3 (:87-88)
+    assert list(np.flatnonzero(s.bundle.est.IO[:, 0])) == [0, 1, 2, 5, 8, 9]
+    s.IO.model.distModel[:] = 2
+    with pytest.raises(ValueError):
+        ingest.setcamest(s, 'as')                                   # no affine terms below model 3
+    s = ingest.setcamest(s, 'all')
+    assert not s.bundle.est.IO[3:5].any() and s.bundle.est.IO[[0, 1, 2, 5, 6, 7, 8, 9]].all()
+    s = ingest.setcamvals(s, 'default', 7.3, 'K1', 1e-3, 'pp', [3.5, -2.5])
+    assert s.IO.val[0, 0] == 7.3 and s.IO.val[5, 2] == 1e-3 and list(s.IO.val[1:3, 4]) == [3.5, -2.5]
+    s = ingest.seteoest(s, 'none')
+    assert not s.bundle.est.EO.any()
+    s = ingest.seteoest(s, [1, 2], 'pos')
+    assert s.bundle.est.EO[0:3, 1:3].all() and s.bundle.est.EO.sum() == 6
+    s.EO.val[:] = np.arange(30.0).reshape(6, 5) * [[1], [2], [-1], [1], [1], [1]]
+    s = ingest.seteoest(s, 'depend', 1)
+    assert not s.bundle.est.EO[:, 0].any() and s.bundle.est.EO.sum() == 30 - 7 and not s.bundle.est.EO[1, 4]
+    with pytest.raises(NotImplementedError):
+        ingest.prob2dbatstruct(ingest.loadpm(os.path.join(CAMCAL, 'camcal-pmexport5.txt')), True)
