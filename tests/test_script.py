@@ -1,0 +1,74 @@
+"""dbat_b200/script.py (`rundbatscript`) on the three script projects the reference ships, with the oracle
+as numerical backend on CPU and the device in the `-m gpu` twin: the XML is parsed, the struct built and the
+operations run by the package; the result file must be the reference's."""
+import os
+from types import SimpleNamespace as NS
+
+import numpy as np
+import pytest
+
+from dbat_b200.script import rundbatscript
+from test_report_golden import GOLD, report_diff
+
+
+def oracle_backend():
+    from oracle.photogrammetry import resect, forwintersect
+    from oracle.bundle import bundle, bundle_cov
+    return NS(resect=resect, forwintersect=forwintersect, bundle=bundle, bundle_cov=bundle_cov)
+
+
+@pytest.mark.parametrize('name,rtol', [('camcaldemo', 0.0), ('sxb', 1e-4), ('romabundledemo', 0.0)])
+def test_script_projects_reproduce_the_reference_reports(name, rtol):
+    root = os.path.join(GOLD, name)
+    s, E, lines = rundbatscript(os.path.join(root, name + '.xml'), backend=oracle_backend(), write=False)
+    assert E.code == 0
+    d = report_diff(lines, os.path.join(root, 'result', 'report.txt'))
+    if rtol:                              # sxb: start values from a resection at 1e6 m (see test_report_golden)
+        assert len(d) == 1 and 'First error' in d[0][1]
+        d = report_diff(lines, os.path.join(root, 'result', 'report.txt'), rtol=rtol)
+    assert d == []
+
+
+def test_script_writes_report_and_camera_files(tmp_path):
+    """Output section: the report goes to the path the script names, the calibrated camera to the io file
+    in the user's sign conventions with 18 significant digits (result/c4040z.xml of the reference)."""
+    import re
+    import shutil
+    root = tmp_path / 'camcaldemo'
+    shutil.copytree(os.path.join(GOLD, 'camcaldemo'), root)
+    shutil.rmtree(root / 'result')
+    os.makedirs(root / 'result')
+    s, E, lines = rundbatscript(str(root / 'camcaldemo.xml'), backend=oracle_backend())
+    assert open(root / 'result' / 'report.txt').read().split('\n')[:-1] == lines
+    got = open(root / 'result' / 'c4040z.xml').read()
+    ref = open(os.path.join(GOLD, 'camcaldemo', 'result', 'c4040z.xml')).read()
+    num = lambda tag, txt: [float(v) for v in re.search(r'<%s>([^<]*)</%s>' % (tag, tag), txt).group(1).split(',')]
+    for tag in ('cc', 'pp', 'K', 'P', 'aspect', 'skew', 'sensor', 'image'):
+        np.testing.assert_allclose(num(tag, got), num(tag, ref), rtol=1e-9 if tag != 'sensor' else 1e-5, atol=1e-14,
+                                   err_msg=tag)
+
+
+def test_script_errors_are_loud(tmp_path):
+    bad = tmp_path / 'bad.xml'
+    bad.write_text('<document dbat_script_version="2.0"><input/><operations/><output/></document>')
+    with pytest.raises(ValueError):
+        rundbatscript(str(bad), backend=oracle_backend())
+    src = open(os.path.join(GOLD, 'camcaldemo', 'camcaldemo.xml')).read()
+    for old, new in (('<operation>spatial_resection</operation>', '<operation>levitate</operation>'),
+                     ('min_rays="2"', 'min_rays="30"')):
+        root = tmp_path / ('case%d' % len(new))
+        import shutil
+        shutil.copytree(os.path.join(GOLD, 'camcaldemo'), root)
+        (root / 'camcaldemo.xml').write_text(src.replace(old, new))
+        with pytest.raises(ValueError):
+            rundbatscript(str(root / 'camcaldemo.xml'), backend=oracle_backend(), write=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', ['camcaldemo', 'sxb', 'romabundledemo'])
+def test_script_projects_on_the_device(name):
+    """`python -m dbat_b200.script project.xml` as a user runs it: everything numerical on the device."""
+    root = os.path.join(GOLD, name)
+    s, E, lines = rundbatscript(os.path.join(root, name + '.xml'), write=False)
+    assert E.code == 0
+    assert report_diff(lines, os.path.join(root, 'result', 'report.txt'), rtol=1e-4 if name == 'sxb' else 1e-5) == []
