@@ -52,15 +52,18 @@ def _drop_nullspace(lines):
     return out
 
 
-def report_diff(lines, golden_path, rtol=0.0):
-    """Lines that differ between a generated report and a golden one, run-specific lines aside."""
+def report_diff(lines, golden_path, rtol=0.0, first_error_rtol=None):
+    """Lines that differ between a generated report and a golden one, run-specific lines aside.
+    first_error_rtol: separate tolerance for the 'First error' line, which depends on the start values
+    only (resection of an ill-conditioned quartic: solver and LAPACK-build dependent)."""
     gold = _drop_nullspace([l.rstrip('\n') for l in open(golden_path)])
     lines = _drop_nullspace(lines)
     bad = []
     if len(gold) != len(lines):
         bad.append(('length', len(gold), len(lines)))
     for n, (a, b) in enumerate(zip(gold, lines)):
-        if not _same(a, b, rtol) and not (RUN_SPECIFIC.match(a) and RUN_SPECIFIC.match(b)):
+        tol = first_error_rtol if first_error_rtol is not None and 'First error:' in a else rtol
+        if not _same(a, b, tol) and not (RUN_SPECIFIC.match(a) and RUN_SPECIFIC.match(b)):
             bad.append((n + 1, a, b))
     return bad
 
@@ -233,7 +236,7 @@ def test_camcal_result_files_from_the_device(pm, report):
     s, ok, it, s0, E = _device_pipeline(s)
     assert ok
     s, lines = bundle_result_file(s, E)
-    assert report_diff(lines, os.path.join(GOLD, report), rtol=1e-5) == []
+    assert report_diff(lines, os.path.join(GOLD, report), rtol=1e-5, first_error_rtol=1e-4) == []
 
 
 @pytest.mark.gpu
@@ -250,7 +253,8 @@ def test_prague2016_result_files_from_the_device(stub):
     s, ok, it, s0, E = _device_pipeline(s)
     assert ok
     s, lines = bundle_result_file(s, E)
-    assert report_diff(lines, os.path.join(root, 'dbatexports', '%s-no-orient-dbatreport.txt' % stub), rtol=1e-5) == []
+    assert report_diff(lines, os.path.join(root, 'dbatexports', '%s-no-orient-dbatreport.txt' % stub), rtol=1e-5,
+                       first_error_rtol=1e-4) == []
 
 
 def test_result_file_through_the_device_covariance_interface():

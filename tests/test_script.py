@@ -71,4 +71,4 @@ def test_script_projects_on_the_device(name):
     root = os.path.join(GOLD, name)
     s, E, lines = rundbatscript(os.path.join(root, name + '.xml'), write=False)
     assert E.code == 0
-    assert report_diff(lines, os.path.join(root, 'result', 'report.txt'), rtol=1e-4 if name == 'sxb' else 1e-5) == []
+    assert report_diff(lines, os.path.join(root, 'result', 'report.txt'), rtol=1e-5, first_error_rtol=1e-3) == []
