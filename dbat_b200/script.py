@@ -14,7 +14,7 @@ output files (report, io) - builds the flat DBAT struct and runs the operations 
                            table readers `file/loadimagepts.m`, `loadctrlpts.m`, `loadeotable.m`, `loadimagetable.m`
   _run_operations          `script/parseops.m:30-116`, `parsesetinitialvalues.m`, `parsesetbundleest.m`,
                            `parsesetdatum.m` and `script/private/parseset*.m`
-  _write_outputs           `script/parseoutputfiles.m:29-120` (report and io files; plots are not produced)
+  _write_outputs           `script/parseoutputfiles.m:29-218` (report, io, eo and image_residuals files; plots are not produced)
 
 `backend` is a namespace with resect / forwintersect / bundle / bundle_cov; the default is this package
 (the device).  Tests hand in the oracle so the runner itself is checked on CPU against the three script
@@ -363,7 +363,46 @@ def _write_outputs(s, E, out, docFile, backend, write):
         elif node.tag == 'io' and write and E.code == 0:
             with open(_path(node.find('file').text, base, here), 'wt') as fh:
                 fh.write(_camera_xml(s, s.prior.IO.cams[0]))
+        elif node.tag == 'eo' and write:
+            with open(_path(node.find('file').text, base, here), 'wt') as fh:
+                fh.write('\n'.join(_eo_listing(s, E, docFile, backend)) + '\n')
+        elif node.tag == 'image_residuals' and write:
+            with open(_path(node.find('file').text, base, here), 'wt') as fh:
+                fh.write('\n'.join(_residual_listing(s, docFile, int(node.get('top_count', 1000)))) + '\n')
     return s, lines
+
+
+def _listing_head(s, what, docFile):
+    return ['# %s for dbat script file' % what, '# %s.' % docFile, '# Generated by dbat_b200.',
+            '# Execution UUID: %s.' % s.proj.UUID]
+
+
+def _eo_listing(s, E, docFile, backend):
+    """parseoutputfiles.m WritePostEOFile: one line per image - number, id, EO (angles in radians), the six
+    posterior standard deviations times 180/pi (positions included, as the reference writes them), label."""
+    sd = getattr(s.post.std, 'EO', None)
+    if sd is None:
+        from .report import _diag_blocks
+        sd = np.sqrt(np.diagonal(_diag_blocks(backend.bundle_cov(s, E, 'CEO'), 6), axis1=1, axis2=2)).T
+    out = _listing_head(s, 'EO listing', docFile)
+    out.append('# Format: EO number, EO id, x, y, z, omega, phi, kappa, sx, sy, sz, so, sk, label. Unit: degrees.')
+    for i in range(s.EO.val.shape[1]):
+        nums = list(s.EO.val[:, i]) + list(sd[:, i] * 180 / np.pi)
+        out.append('%d, %d, ' % (i + 1, s.EO.id[i]) + ''.join('%.18g, ' % v for v in nums) + s.EO.label[i])
+    return out
+
+
+def _residual_listing(s, docFile, topCount):
+    """parseoutputfiles.m WriteImageResidualsFile: the topCount largest image residuals (pixels)."""
+    res = s.post.res.IP
+    nrm = np.sqrt((res ** 2).sum(axis=0))
+    top = np.argsort(-nrm, kind='stable')[:topCount]
+    out = _listing_head(s, 'Top residual listing', docFile)
+    out += ['# Listing top %d residuals.' % topCount, '# Format: OP id, image id, x, y, resx, resy, resTot']
+    for k in top:
+        out.append('%d, %d, %g, %g, %g, %g, %g' % (s.OP.id[s.IP.op[k]], s.EO.id[s.IP.img[k]], s.IP.val[0, k],
+                                                   s.IP.val[1, k], res[0, k], res[1, k], nrm[k]))
+    return out
 
 
 def rundbatscript(f, verbose=False, backend=None, write=True):

@@ -46,6 +46,21 @@ def test_script_writes_report_and_camera_files(tmp_path):
     for tag in ('cc', 'pp', 'K', 'P', 'aspect', 'skew', 'sensor', 'image'):
         np.testing.assert_allclose(num(tag, got), num(tag, ref), rtol=1e-9 if tag != 'sensor' else 1e-5, atol=1e-14,
                                    err_msg=tag)
+    # eo file: 18-digit EO values and deviations; residual file: the 50 largest image residuals
+    body = lambda path: [l.rstrip('\n') for l in open(path) if not l.startswith('#')]
+    got, ref = body(root / 'result' / 'camera_stations.txt'), body(os.path.join(GOLD, 'camcaldemo', 'result', 'camera_stations.txt'))
+    assert len(got) == len(ref) == 21
+    for a, b in zip(got, ref):
+        ta, tb = a.split(', '), b.split(', ')
+        assert ta[:2] == tb[:2] and ta[-1] == tb[-1]
+        np.testing.assert_allclose([float(v) for v in ta[2:8]], [float(v) for v in tb[2:8]], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose([float(v) for v in ta[8:14]], [float(v) for v in tb[8:14]], rtol=1e-6)
+    got, ref = body(root / 'result' / 'top_residuals.txt'), body(os.path.join(GOLD, 'camcaldemo', 'result', 'top_residuals.txt'))
+    assert len(got) == len(ref) == 50
+    for a, b in zip(got, ref):
+        ta, tb = a.split(', '), b.split(', ')
+        assert ta[:4] == tb[:4]
+        np.testing.assert_allclose([float(v) for v in ta[4:]], [float(v) for v in tb[4:]], rtol=2e-5, atol=2e-6)
 
 
 def test_script_errors_are_loud(tmp_path):
