@@ -214,8 +214,10 @@ def coverage(s, ix=None, union=False):
     c = np.full(len(ix), np.nan)
     cr = np.full(len(ix), np.nan)
     crr = np.full(len(ix), np.nan)
+    order = np.argsort(s.IP.img, kind='stable')
+    start = np.searchsorted(np.asarray(s.IP.img)[order], np.arange(nImg + 1))
     for n, i in enumerate(ix):
-        pts = s.IP.val[:, s.IP.img == i]
+        pts = s.IP.val[:, order[start[i]:start[i + 1]]]
         if pts.shape[1] == 0:
             continue
         tot = np.prod(s.IO.sensor.imSize[:, i])
@@ -227,23 +229,25 @@ def coverage(s, ix=None, union=False):
 
 def angles(s):
     """angles.m: per object point the largest angle (rad, folded to [0, pi/2]) between any two of its
-    rays; 0 for one ray, NaN for none."""
+    rays; 0 for one ray, NaN for none.  Points are processed in groups of equal ray count instead of the
+    reference's per-point loop."""
     nOP = s.OP.val.shape[1]
     a = np.full(nOP, np.nan)
-    order = np.argsort(s.IP.op, kind='stable')
-    op = s.IP.op[order]
-    img = s.IP.img[order]
-    start = np.searchsorted(op, np.arange(nOP + 1))
-    for j in range(nOP):
-        cams = img[start[j]:start[j + 1]]
-        if len(cams) == 0:
-            continue
-        if len(cams) == 1:
-            a[j] = 0.0
-            continue
-        d = s.OP.val[:, j:j + 1] - s.EO.val[0:3, np.sort(cams)]
-        dn = d / np.sqrt((d ** 2).sum(axis=0))
-        a[j] = np.max(np.arccos(np.abs(np.clip(dn.T @ dn, -1, 1))))
+    order = np.lexsort((s.IP.img, s.IP.op))
+    img = np.asarray(s.IP.img)[order]
+    start = np.searchsorted(np.asarray(s.IP.op)[order], np.arange(nOP + 1))
+    cnt = np.diff(start)
+    a[cnt == 1] = 0.0
+    for k in np.unique(cnt[cnt > 1]):
+        grp = np.flatnonzero(cnt == k)
+        step = max(1, int(4e6 // (k * k)))
+        for g0 in range(0, len(grp), step):
+            pts = grp[g0:g0 + step]
+            cams = img[start[pts][:, None] + np.arange(k)[None, :]]              # (n, k)
+            d = s.OP.val[:, pts][:, :, None] - s.EO.val[0:3][:, cams]            # (3, n, k)
+            dn = d / np.sqrt((d ** 2).sum(axis=0))
+            ip = np.clip(np.einsum('cnk,cnl->nkl', dn, dn), -1, 1)
+            a[pts] = np.arccos(np.abs(ip).reshape(len(pts), -1).min(axis=1))     # max acos = acos of the min
     return a
 
 
