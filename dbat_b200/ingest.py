@@ -11,6 +11,7 @@ Host mirror of the functions every reference demo calls between the file and `bu
   setcamest         `code/misc/setcamest.m:28-125`
   seteoest          `code/misc/seteoest.m:26-128`      (including the 'depend' datum)
   cleareo, clearop  `code/misc/cleareo.m`, `clearop.m`
+  legacyloadeotable, matcheo, setprioreo   `code/file/legacyloadeotable.m`, `misc/matcheo.m`, `setprioreo.m`
 
 The reference builds the struct with per-image loops and sparse `vis` / `ix` matrices
 (`prob2dbatstruct.m:349-365`); here the image points are sorted once by (image, object point) and kept
@@ -245,6 +246,48 @@ def setcpt(s, pts, i, j, isCtrl=True):
     else:
         s.prior.OP.use[:, i] = False
         s.bundle.est.OP[:, i] = True
+    return s
+
+
+def legacyloadeotable(fName, has=(True, True)):
+    """legacyloadeotable.m: a camera-station table in the control-point format (`loadcpt`)."""
+    return loadcpt(fName, has)
+
+
+def matcheo(s, tbl, match='auto'):
+    """matcheo.m: (i, j) - images i and the table rows j they match, by label, by id, or both."""
+    byId = match in ('id', 'both') or (match == 'auto' and np.any(~np.isnan(np.asarray(tbl.id, float))))
+    byLabel = match in ('label', 'both') or (match == 'auto' and any(tbl.name))
+    il = jl = ii = ji = None
+    if byLabel:
+        _, il, jl = np.intersect1d(np.asarray(s.EO.label), np.asarray(tbl.name), return_indices=True)
+    if byId:
+        _, ii, ji = np.intersect1d(np.asarray(s.EO.id), np.asarray(tbl.id), return_indices=True)
+    if byLabel and byId:
+        if len(il):
+            if not (np.array_equal(il, ii) and np.array_equal(jl, ji)):
+                raise ValueError('Inconsistent match')
+            return il, jl
+        return ii, ji
+    if byLabel:
+        return il, jl
+    if byId:
+        return ii, ji
+    raise ValueError('Neither match-by-id nor match-by-label possible.')
+
+
+def setprioreo(s, tbl, i, j):
+    """setprioreo.m: prior observations of camera positions; zero sigma fixes the coordinate."""
+    s.proj.EOfile = tbl.fileName
+    s.prior.EO.val[0:3, i] = tbl.pos[:, j]
+    s.EO.val[0:3, i] = tbl.pos[:, j]
+    s.prior.EO.std[0:3, i] = tbl.std[:, j]
+    for a, b in zip(i, j):
+        if tbl.name[b]:
+            s.EO.label[a] = tbl.name[b]
+    free = tbl.std[:, j] != 0
+    s.prior.EO.use[0:3, i] = free
+    s.bundle.est.EO[0:3, i] = free
     return s
 
 

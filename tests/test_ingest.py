@@ -145,3 +145,28 @@ def test_setters_follow_the_reference_argument_rules():
     assert not s.bundle.est.EO[:, 0].any() and s.bundle.est.EO.sum() == 30 - 7 and not s.bundle.est.EO[1, 4]
     with pytest.raises(NotImplementedError):
         ingest.prob2dbatstruct(ingest.loadpm(os.path.join(CAMCAL, 'camcal-pmexport5.txt')), True)
+
+
+@pytest.mark.parametrize('usePriorEO', [True, False])
+def test_sxb_prior_eo_demo_from_file_to_result_file(usePriorEO):
+    """code/demo/sxb_prior_eo.m:30-75 call for call (prior observations of four camera positions matched
+    by image label), then resect / forwintersect / bundle / result file against the reference's report."""
+    root = os.path.join(GOLD, 'prague2016sxb')
+    prob = ingest.loadpm(os.path.join(root, 'pmexports', 'wsmart-with-orient-pmexport.txt'))
+    s0 = ingest.prob2dbatstruct(prob)
+    s0 = ingest.setcamvals(s0, 'loaded')
+    s0 = ingest.setcamest(s0, 'not', 'all')
+    ctrlPts = ingest.loadcpt(os.path.join(root, 'ref', 'ctrlpts-weighted.txt'))
+    i, j = ingest.matchcpt(s0, ctrlPts, 'id')
+    s0 = ingest.setcpt(s0, ctrlPts, i, j)
+    if usePriorEO:
+        EOtbl = ingest.legacyloadeotable(os.path.join(root, 'ref', 'fake-camera-positions.txt'), (False, True))
+        i, j = ingest.matcheo(s0, EOtbl)
+        assert len(i) == 4
+        s0 = ingest.setprioreo(s0, EOtbl, i, j)
+    s0 = ingest.cleareo(s0)
+    s0 = ingest.clearop(s0)
+    assert np.isnan(s0.EO.val).sum() == (30 - 12 if usePriorEO else 30)
+    lines = _solve_and_report(s0)
+    rep = os.path.join(root, 'dbatexports', 'sxb-%sprior-eo-dbatreport.txt' % ('' if usePriorEO else 'no-'))
+    assert report_diff(lines, rep, first_error_rtol=2e-5) == []
