@@ -14,7 +14,8 @@ from .photogrammetry import forwintersect, resect
 from .report import (angles, bundle_residuals, bundle_result_file, corrmat, coverage, cumchi2,
                      high_eo_correlations, high_io_correlations, high_op_correlations,
                      test_distortion_params)
-from .ingest import (cleareo, clearop, legacyloadeotable, loadcpt, loadpm, matchcpt, matcheo, prob2dbatstruct,
+from .ingest import (cleareo, clearop, legacyloadeotable, loadcpt, loadctrlpts, loadeotable, loadimagepts,
+                     loadimagetable, loadpm, matchcpt, matcheo, prob2dbatstruct,
                      setcamest, setcamvals, setcpt, seteoest, setprioreo)
 from .script import rundbatscript
 from .dbatstruct import (buildserialindices, buildweightmatrix, deserialize, new_struct,
@@ -24,5 +25,6 @@ __all__ = ['Problem', 'bundle', 'bundle_cov', 'gauss_markov', 'gauss_newton_armi
            'levenberg_marquardt_powell', 'make_termfun', 'forwintersect', 'resect', 'bundle_result_file', 'corrmat', 'cumchi2',
            'high_io_correlations', 'high_eo_correlations', 'high_op_correlations', 'test_distortion_params',
            'bundle_residuals', 'coverage', 'angles', 'loadpm', 'prob2dbatstruct', 'loadcpt', 'matchcpt', 'setcpt',
-           'setcamvals', 'setcamest', 'seteoest', 'cleareo', 'clearop', 'legacyloadeotable', 'matcheo', 'setprioreo', 'rundbatscript', 'buildserialindices',
+           'setcamvals', 'setcamest', 'seteoest', 'cleareo', 'clearop', 'legacyloadeotable', 'matcheo', 'setprioreo', 'loadimagepts', 'loadctrlpts',
+           'loadimagetable', 'loadeotable', 'rundbatscript', 'buildserialindices',
            'buildweightmatrix', 'deserialize', 'new_struct', 'serialize', 'seteoest_depend']

@@ -12,6 +12,7 @@ Host mirror of the functions every reference demo calls between the file and `bu
   seteoest          `code/misc/seteoest.m:26-128`      (including the 'depend' datum)
   cleareo, clearop  `code/misc/cleareo.m`, `clearop.m`
   legacyloadeotable, matcheo, setprioreo   `code/file/legacyloadeotable.m`, `misc/matcheo.m`, `setprioreo.m`
+  loadimagepts, loadctrlpts, loadimagetable, loadeotable   `code/file/*.m` (format-string table readers)
 
 The reference builds the struct with per-image loops and sparse `vis` / `ix` matrices
 (`prob2dbatstruct.m:349-365`); here the image points are sorted once by (image, object point) and kept
@@ -247,6 +248,81 @@ def setcpt(s, pts, i, j, isCtrl=True):
         s.prior.OP.use[:, i] = False
         s.bundle.est.OP[:, i] = True
     return s
+
+
+def _table(path, fmt, sep=',', cmt='#'):
+    """Rows of a delimited text table as dicts keyed by the format's part names."""
+    parts = [p.strip() for p in fmt.split(sep)]
+    rows = []
+    if not os.path.exists(path) and os.path.exists(path + '.xz'):       # large tables may be stored compressed
+        import lzma
+        opener = lambda: lzma.open(path + '.xz', 'rt')
+    else:
+        opener = lambda: open(path)
+    with opener() as fh:
+        for n, line in enumerate(fh, 1):
+            line = line.strip()
+            if not line or line[0] == cmt:
+                continue
+            tok = [t.strip() for t in line.split(sep)]
+            if len(tok) != len(parts):
+                raise ValueError('%s, line %d: Wrong number of elements (got %d, expected %d)'
+                                 % (path, n, len(tok), len(parts)))
+            rows.append(dict(zip(parts, tok)))
+    return parts, rows
+
+
+def loadimagepts(fName, fmt, sep=',', cmt='#'):
+    """loadimagepts.m: image measurement table; fmt lists the columns (id, im, x, y, sx, sy, sxy, ignored)."""
+    parts, rows = _table(fName, fmt, sep, cmt)
+    n = len(rows)
+    col = lambda k: np.array([float(r[k]) for r in rows]) if k in parts else np.full(n, np.nan)
+    sx, sy = (col('sxy'), col('sxy')) if 'sxy' in parts else (col('sx'), col('sy'))
+    return NS(id=col('id').astype(np.int64), im=col('im').astype(np.int64), pos=np.vstack([col('x'), col('y')]),
+              std=np.vstack([sx, sy]), fileName=fName)
+
+
+def loadctrlpts(fName, fmt, sep=',', cmt='#'):
+    """loadctrlpts.m: control point table; fmt lists the columns (id, label, x, y, z, sx, sy, sz, sxy, sxyz,
+    ignored); a missing sigma is 0 (fixed)."""
+    parts, rows = _table(fName, fmt, sep, cmt)
+    ids = np.array([int(r['id']) for r in rows], dtype=np.int64) if 'id' in parts else np.full(len(rows), -1)
+    pos = np.array([[float(r[k]) if k in r else np.nan for k in 'xyz'] for r in rows]).T.reshape(3, -1)
+    std = np.zeros((3, len(rows)))
+    for n, r in enumerate(rows):
+        for k, v in r.items():
+            if k in ('sx', 'sy', 'sz'):
+                std['xyz'.index(k[1]), n] = float(v)
+            elif k == 'sxy':
+                std[0:2, n] = float(v)
+            elif k == 'sxyz':
+                std[:, n] = float(v)
+    return NS(id=ids, name=[r.get('label', '') for r in rows], pos=pos, std=std, cov=None, fileName=fName)
+
+
+def loadimagetable(fName, fmt, sep=',', cmt='#'):
+    """loadimagetable.m: image list (id, cam, label, path, ignored); cam defaults to 1."""
+    parts, rows = _table(fName, fmt, sep, cmt)
+    return NS(id=np.array([int(r['id']) for r in rows], dtype=np.int64),
+              cam=np.array([int(r['cam']) if 'cam' in r else 1 for r in rows]),
+              name=[r.get('label', '') for r in rows], path=[r.get('path', '') for r in rows], fileName=fName)
+
+
+def loadeotable(fName, fmt, sep=',', cmt='#'):
+    """loadeotable.m: camera station table (id, label, x, y, z, omega, phi, kappa, sx, sy, sz, sxyz, so, sp,
+    sk, sang, ignored); angles are returned in the file's unit."""
+    parts, rows = _table(fName, fmt, sep, cmt)
+    n = len(rows)
+    num = lambda k: np.array([float(r[k]) for r in rows]) if k in parts else np.full(n, np.nan)
+    std = np.vstack([num('sx'), num('sy'), num('sz')])
+    if 'sxyz' in parts:
+        std[:] = num('sxyz')
+    angStd = np.vstack([num('so'), num('sp'), num('sk')])
+    if 'sang' in parts:
+        angStd[:] = num('sang')
+    return NS(id=np.array([int(r['id']) for r in rows], dtype=np.int64) if 'id' in parts else np.full(n, -1),
+              name=[r.get('label', '') for r in rows], pos=np.vstack([num('x'), num('y'), num('z')]),
+              ang=np.vstack([num('omega'), num('phi'), num('kappa')]), std=std, angStd=angStd, fileName=fName)
 
 
 def legacyloadeotable(fName, has=(True, True)):

@@ -30,6 +30,7 @@ from types import SimpleNamespace as NS
 import numpy as np
 
 from . import ingest
+from .ingest import _table
 from .dbatstruct import new_struct
 
 
@@ -40,28 +41,6 @@ def _text(node, tag, default=None):
 
 def _floats(txt):
     return [float(v) for v in txt.split(',') if v.strip()]
-
-
-def _table(path, fmt, sep=',', cmt='#'):
-    """Rows of a delimited text table as dicts keyed by the format's part names."""
-    parts = [p.strip() for p in fmt.split(sep)]
-    rows = []
-    if not os.path.exists(path) and os.path.exists(path + '.xz'):       # large tables may be stored compressed
-        import lzma
-        opener = lambda: lzma.open(path + '.xz', 'rt')
-    else:
-        opener = lambda: open(path)
-    with opener() as fh:
-        for n, line in enumerate(fh, 1):
-            line = line.strip()
-            if not line or line[0] == cmt:
-                continue
-            tok = [t.strip() for t in line.split(sep)]
-            if len(tok) != len(parts):
-                raise ValueError('%s, line %d: Wrong number of elements (got %d, expected %d)'
-                                 % (path, n, len(tok), len(parts)))
-            rows.append(dict(zip(parts, tok)))
-    return parts, rows
 
 
 def _path(txt, base, here):
@@ -98,29 +77,18 @@ def _camera(node):
 
 
 def _ctrl_pts(node, base, here):
+    """parsectrlpts.m: the table, then the keep / remove id filters."""
     f = node.find('file')
-    fname = _path(f.text, base, here)
-    parts, rows = _table(fname, f.get('format'))
-    ids = np.array([int(r['id']) for r in rows], dtype=np.int64)
-    pos = np.array([[float(r[k]) for k in 'xyz'] for r in rows]).T.reshape(3, -1)
-    std = np.zeros((3, len(rows)))
-    for n, r in enumerate(rows):
-        for k, v in r.items():
-            if k in ('sx', 'sy', 'sz'):
-                std['xyz'.index(k[1]), n] = float(v)
-            elif k == 'sxy':
-                std[0:2, n] = float(v)
-            elif k == 'sxyz':
-                std[:, n] = float(v)
-    names = [r.get('label', '') for r in rows]
+    pts = ingest.loadctrlpts(_path(f.text, base, here), f.get('format'))
     for flt in node.findall('filter'):
-        sel = np.isin(ids, [int(v) for v in flt.get('id').split(',') if v.strip()])
+        sel = np.isin(pts.id, [int(v) for v in flt.get('id').split(',') if v.strip()])
         what = flt.text.strip()
         if what not in ('keep', 'remove'):
             raise ValueError('DBAT XML input/ctrl_pts/filter error: Unknown filter %s' % what)
         keep = sel if what == 'keep' else ~sel
-        ids, pos, std, names = ids[keep], pos[:, keep], std[:, keep], [n for n, k in zip(names, keep) if k]
-    return NS(id=ids, name=names, pos=pos, std=std, fileName=fname)
+        pts.id, pts.pos, pts.std = pts.id[keep], pts.pos[:, keep], pts.std[:, keep]
+        pts.name = [n for n, k in zip(pts.name, keep) if k]
+    return pts
 
 
 def _parse_input(inp, docFile):
@@ -134,23 +102,19 @@ def _parse_input(inp, docFile):
         raise NotImplementedError('exactly one camera is supported by the device path (got %d)' % len(cams))
     cam = cams[0]
     f = inp.find('images').find('file')
-    _, rows = _table(_path(f.text, base, here), f.get('format'))
-    imId = np.array([int(r['id']) for r in rows], dtype=np.int64)
-    imPath = [r['path'].replace('\\', '/') for r in rows]
+    ims = ingest.loadimagetable(_path(f.text, base, here), f.get('format'))
+    imId, imPath = ims.id, [p.replace('\\', '/') for p in ims.path]
     imDir = os.path.commonpath([os.path.dirname(p) for p in imPath]) if all('/' in p for p in imPath) else ''
     ip = {'id': [], 'im': [], 'x': [], 'y': [], 'sx': [], 'sy': []}
     for f in inp.find('image_pts').findall('file'):
-        parts, rows = _table(_path(f.text, base, here), f.get('format'))
-        n = len(rows)
-        col = lambda k: np.array([float(r[k]) for r in rows]) if k in parts else np.full(n, np.nan)
-        sx, sy = (col('sxy'), col('sxy')) if 'sxy' in parts else (col('sx'), col('sy'))
-        if f.get('sxy') is not None:
-            sx = sy = np.full(n, float(f.get('sxy')))
+        pts = ingest.loadimagepts(_path(f.text, base, here), f.get('format'))
+        if f.get('sxy') is not None:                                    # parseimagepts.m:52-63
+            pts.std[:] = float(f.get('sxy'))
         if f.get('sx') is not None:
-            sx = np.full(n, float(f.get('sx')))
+            pts.std[0] = float(f.get('sx'))
         if f.get('sy') is not None:
-            sy = np.full(n, float(f.get('sy')))
-        for k, v in (('id', col('id')), ('im', col('im')), ('x', col('x')), ('y', col('y')), ('sx', sx), ('sy', sy)):
+            pts.std[1] = float(f.get('sy'))
+        for k, v in (('id', pts.id), ('im', pts.im), ('x', pts.pos[0]), ('y', pts.pos[1]), ('sx', pts.std[0]), ('sy', pts.std[1])):
             ip[k].append(v)
     ip = {k: np.concatenate(v) for k, v in ip.items()}
     none = NS(id=np.zeros(0, np.int64), name=[], pos=np.zeros((3, 0)), std=np.zeros((3, 0)), fileName='')
@@ -193,18 +157,15 @@ def _parse_input(inp, docFile):
     if inp.find('prior_eo') is not None:
         f = inp.find('prior_eo').find('file')
         EOfile = _path(f.text, base, here)
-        parts, rows = _table(EOfile, f.get('format'))
+        tbl = ingest.loadeotable(EOfile, f.get('format'))
         scale = {'radian': 1.0, 'degrees': np.pi / 180, 'gon': np.pi / 200}.get(f.get('units'))
-        for r in rows:
-            i = im_of[int(r['id'])]
-            for k, row in (('x', 0), ('y', 1), ('z', 2)):
-                if k in r:
-                    s.prior.EO.val[row, i] = float(r[k])
-            for k, row in (('omega', 3), ('phi', 4), ('kappa', 5)):
-                if k in r:
-                    if scale is None:
-                        raise ValueError('DBAT XML input/prior_eo: angles need a units attribute')
-                    s.prior.EO.val[row, i] = float(r[k]) * scale
+        if np.any(~np.isnan(tbl.ang)) and scale is None:
+            raise ValueError('DBAT XML input/prior_eo: angles need a units attribute')
+        col = np.array([im_of[int(v)] for v in tbl.id])
+        s.prior.EO.val[0:3, col] = tbl.pos
+        s.prior.EO.val[3:6, col] = tbl.ang * (scale or 1.0)
+        s.prior.EO.std[0:3, col] = tbl.std
+        s.prior.EO.std[3:6, col] = tbl.angStd * (scale or 1.0)
     return s, imDir, ctrl.fileName, EOfile
 
 

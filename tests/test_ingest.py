@@ -170,3 +170,23 @@ def test_sxb_prior_eo_demo_from_file_to_result_file(usePriorEO):
     lines = _solve_and_report(s0)
     rep = os.path.join(root, 'dbatexports', 'sxb-%sprior-eo-dbatreport.txt' % ('' if usePriorEO else 'no-'))
     assert report_diff(lines, rep, first_error_rtol=2e-5) == []
+
+
+def test_format_string_table_readers():
+    """loadimagepts / loadctrlpts / loadimagetable / loadeotable on the script projects' tables."""
+    sxb = os.path.join(GOLD, 'sxb')
+    pts = ingest.loadimagepts(os.path.join(sxb, 'measurements', 'markpts.txt'), 'id,im,x,y')
+    assert pts.pos.shape == (2, 47) and (pts.id[0], pts.im[0]) == (317, 1) and np.isnan(pts.std).all()
+    assert pts.pos[0, 0] == 5007.6667 and pts.pos[1, 0] == 7275.6667
+    cal = ingest.loadimagepts(os.path.join(GOLD, 'camcaldemo', 'measurements', 'markpts.txt'), 'im,id,x,y,sxy')
+    assert np.all(cal.std == 0.1) and cal.pos.shape[1] == 2074
+    cp = ingest.loadctrlpts(os.path.join(sxb, 'reference', 'sxb-control.txt'), 'id,label,x,y,z,sx,sy,sz')
+    assert len(cp.id) == 16 and cp.name[0] == 'B2.16' and list(cp.std[:, 0]) == [0.02, 0.02, 0.04]
+    fx = ingest.loadctrlpts(os.path.join(GOLD, 'camcaldemo', 'reference', 'camcal-fixed.txt'), 'id,label,x,y,z')
+    assert np.all(fx.std == 0) and list(fx.pos[:, 1]) == [1.0, 1.0, 0.0]
+    ims = ingest.loadimagetable(os.path.join(sxb, 'images', 'images.txt'), 'id,path')
+    assert list(ims.id) == [1, 2, 3, 4, 5] and ims.path[0].endswith('8811.jpg') and np.all(ims.cam == 1)
+    eo = ingest.loadeotable(os.path.join(GOLD, 'romabundledemo', 'prior', 'initial_eo.txt'), 'id,x,y,z,omega,phi,kappa')
+    assert eo.pos.shape == (3, 60) and list(eo.ang[:, 0]) == [39.43, 7.46, 99.59] and np.isnan(eo.std).all()
+    with pytest.raises(ValueError):
+        ingest.loadimagepts(os.path.join(sxb, 'measurements', 'markpts.txt'), 'id,im,x')
