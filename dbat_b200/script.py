@@ -21,7 +21,6 @@ output files (report, io) - builds the flat DBAT struct and runs the operations 
 projects the reference ships with their result files.
 """
 import os
-import re
 import sys
 import uuid as _uuid
 import xml.etree.ElementTree as ET
@@ -30,7 +29,6 @@ from types import SimpleNamespace as NS
 import numpy as np
 
 from . import ingest
-from .ingest import _table
 from .dbatstruct import new_struct
 
 

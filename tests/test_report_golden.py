@@ -262,7 +262,6 @@ def test_result_file_through_the_device_covariance_interface():
     CEO / COP and CIOF from what the device returns (`Problem.cov`: (N,k,k) blocks, camera part of CXX).
     Here a stand-in Problem serves those arrays from the oracle, so the whole host path of the device
     twins above - sparse block extraction included - is exercised without a GPU."""
-    from types import SimpleNamespace as NS
     from oracle.bundle import bundle_cov as ocov
     from dbat_b200.report import bundle_result_file, _diag_blocks
 
