@@ -493,6 +493,12 @@ def bundle_cov(s, e, *varargin):
             out.append(e)
         elif lw in ('cio', 'ceo', 'cop'):
             out.append(_blockdiag(P.cov(lw, e.s0)))
+        elif lw == 'ciof' and np.all(np.asarray(s.IO.struct.block) == np.asarray(s.IO.struct.block)[:, :1]):
+            # one shared camera (all the device path supports): every image carries the same NC x NC block
+            # (bundle_cov.m:148-160 with deserial fanning one x element out to all images), so the full matrix
+            # is that block tiled - no need for the dense camera-system inverse
+            nImg = s.IO.val.shape[1]
+            out.append(sp.csc_matrix(np.tile(P.cov('cio', e.s0)[0], (nImg, nImg))))
         elif lw in ('ciof', 'ceof'):
             Cc = P.cov('cxx_cam', e.s0)
             key = lw[1:3].upper()

@@ -279,6 +279,9 @@ def test_result_file_through_the_device_covariance_interface():
             return _diag_blocks(np.asarray(ocov(s, E, which.upper())), k)
 
     E.problem = StandIn()
+    import dbat_b200
+    for w in ('CIOF', 'CEOF', 'CIO', 'CEO', 'COP'):             # the assembled matrices equal the oracle's
+        np.testing.assert_allclose(dbat_b200.bundle_cov(s, E, w).toarray(), np.asarray(ocov(s, E, w)), rtol=0, atol=1e-18)
     s, lines = bundle_result_file(s, E)
     assert report_diff(lines, os.path.join(GOLD, 'camcalpm', 'camcal-dbatreport5.txt')) == []
 
