@@ -13,6 +13,7 @@ Host mirror of the functions every reference demo calls between the file and `bu
   cleareo, clearop  `code/misc/cleareo.m`, `clearop.m`
   legacyloadeotable, matcheo, setprioreo   `code/file/legacyloadeotable.m`, `misc/matcheo.m`, `setprioreo.m`
   loadimagepts, loadctrlpts, loadimagetable, loadeotable   `code/file/*.m` (format-string table readers)
+  loadpm3dtbl       `code/file/loadpm3dtbl.m`          PhotoModeler's 3-D point table (external verification)
 
 The reference builds the struct with per-image loops and sparse `vis` / `ix` matrices
 (`prob2dbatstruct.m:349-365`); here the image points are sorted once by (image, object point) and kept
@@ -323,6 +324,37 @@ def loadeotable(fName, fmt, sep=',', cmt='#'):
     return NS(id=np.array([int(r['id']) for r in rows], dtype=np.int64) if 'id' in parts else np.full(n, -1),
               name=[r.get('label', '') for r in rows], pos=np.vstack([num('x'), num('y'), num('z')]),
               ang=np.vstack([num('omega'), num('phi'), num('kappa')]), std=std, angStd=angStd, fileName=fName)
+
+
+def loadpm3dtbl(fName):
+    """loadpm3dtbl.m (normal point table): PhotoModeler's exported 3-D point table - id, name, the photos
+    a point is used in, position and precision (`fixed` precisions read as 0)."""
+    import re
+    ids, names, vis, pos, std = [], [], [], [], []
+    with open(fName) as fh:
+        for line in fh:
+            m = re.match(r'^\s*(\d+)\s*,\s*"([^"]*)"\s*,\s*"([^"]*)"\s*,(.*)$', line.strip())
+            if not m:
+                continue
+            nums = []
+            for tok in m.group(4).split(','):
+                tok = tok.strip()
+                if tok == 'fixed':
+                    nums.append(0.0)
+                    continue
+                try:
+                    nums.append(float(tok))
+                except ValueError:
+                    break
+            if len(nums) < 6:
+                raise ValueError('Could not parse position part of string: %s' % m.group(4))
+            ids.append(int(m.group(1)))
+            names.append(m.group(2).strip())
+            vis.append([int(v) for v in m.group(3).split(',') if v.strip()])
+            pos.append(nums[0:3])
+            std.append(nums[3:6])
+    return NS(id=np.array(ids, dtype=np.int64), name=names, vis=vis, pos=np.array(pos).T.reshape(3, -1),
+              std=np.array(std).T.reshape(3, -1), fileName=fName)
 
 
 def legacyloadeotable(fName, has=(True, True)):

@@ -50,6 +50,8 @@ FILES = {
         'data/prague2016/cam/pmexports/weighted-with-orient-pmexport.txt',
         'data/prague2016/cam/pmexports/fixed-with-orient-pmexport.txt',
         'data/prague2016/cam/dbatexports/weighted-with-orient-dbatreport.txt',
+        'data/prague2016/cam/pmexports/weighted-no-orient-3dpts.txt',      # PhotoModeler's own result tables
+        'data/prague2016/cam/pmexports/fixed-no-orient-3dpts.txt',
         'data/prague2016/cam/dbatexports/fixed-with-orient-dbatreport.txt',
     ],
     'stpierre': [

@@ -190,3 +190,31 @@ def test_format_string_table_readers():
     assert eo.pos.shape == (3, 60) and list(eo.ang[:, 0]) == [39.43, 7.46, 99.59] and np.isnan(eo.std).all()
     with pytest.raises(ValueError):
         ingest.loadimagepts(os.path.join(sxb, 'measurements', 'markpts.txt'), 'id,im,x')
+
+
+@pytest.mark.parametrize('stub', ['fixed', 'weighted'])
+def test_external_verification_against_photomodeler(stub):
+    """prague2016_pm.m:255-300, the reference's cross-software check: the adjusted object points and their
+    posterior standard deviations against PhotoModeler's own 3-D point table for the same project
+    (`pmexports/<stub>-no-orient-3dpts.txt`, printed to 1e-6 m).  They agree to that printing resolution -
+    positions (after undoing the demo's mean control-point offset) to 1.5e-6 m, standard deviations to 1e-6 m."""
+    from oracle.photogrammetry import resect, forwintersect
+    from oracle.bundle import bundle as obundle, bundle_cov as ocov
+    from dbat_b200.report import bundle_result_file
+    root = os.path.join(GOLD, 'prague2016cam')
+    s0 = prague2016_pm(root, stub, stub)
+    prob = ingest.loadpm(os.path.join(root, 'pmexports', '%s-no-orient-pmexport.txt' % stub))
+    ctrlPts = ingest.loadcpt(os.path.join(root, 'ref', 'ctrlpts-%s.txt' % stub))
+    _, ia, ib = np.intersect1d(prob.ctrlPts[:, 0], ctrlPts.id, return_indices=True)
+    meanOffset = np.mean(prob.ctrlPts[ia, 1:4].T - ctrlPts.pos[:, ib], axis=1, keepdims=True)
+    cpId = np.asarray(s0.OP.id)[s0.prior.OP.isCtrl]
+    s1, _, fail = resect(s0, 'all', cpId, 1, 0, cpId)
+    s2, _, _ = forwintersect(s1, 'all', True)
+    s3, ok, it, sig0, E = obundle(copy.deepcopy(s2), 'gna')
+    s3, _ = bundle_result_file(s3, E, None, cov=ocov)
+    pts3d = ingest.loadpm3dtbl(os.path.join(root, 'pmexports', '%s-no-orient-3dpts.txt' % stub))
+    _, i, j = np.intersect1d(pts3d.id, s3.OP.id, return_indices=True)
+    assert len(i) == len(pts3d.id) == 100
+    assert np.abs(s3.OP.val[:, j] - meanOffset - pts3d.pos[:, i]).max() < 1.5e-6
+    assert np.abs(s3.post.std.OP[:, j] - pts3d.std[:, i]).max() < 1e-6
+    assert [len(v) for v in pts3d.vis][:2] == [21, 21] and max(len(v) for v in pts3d.vis) == 21
