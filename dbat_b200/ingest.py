@@ -14,6 +14,7 @@ Host mirror of the functions every reference demo calls between the file and `bu
   legacyloadeotable, matcheo, setprioreo   `code/file/legacyloadeotable.m`, `misc/matcheo.m`, `setprioreo.m`
   loadimagepts, loadctrlpts, loadimagetable, loadeotable   `code/file/*.m` (format-string table readers)
   loadpm3dtbl       `code/file/loadpm3dtbl.m`          PhotoModeler's 3-D point table (external verification)
+  loadpsz, ps2pmstruct   `code/file/loadpsz.m`, `misc/ps2pmstruct.m`   PhotoScan .psz archives
 
 The reference builds the struct with per-image loops and sparse `vis` / `ix` matrices
 (`prob2dbatstruct.m:349-365`); here the image points are sorted once by (image, object point) and kept
@@ -533,3 +534,204 @@ def clearop(s):
     """clearop.m: the same for the object points."""
     s.OP.val[s.bundle.est.OP & ~s.prior.OP.use] = np.nan
     return s
+
+
+# ----------------------------------------------------------------------------- PhotoScan archives
+def _ply_vertices(data):
+    """Vertex table of a binary little-endian PLY file (what a .psz stores) as a dict of arrays."""
+    head, _, body = data.partition(b'end_header\n')
+    types = {'float': '<f4', 'double': '<f8', 'uint': '<u4', 'int': '<i4', 'uchar': 'u1', 'char': 'i1',
+             'ushort': '<u2', 'short': '<i2'}
+    n, fields, seen_vertex = 0, [], False
+    for line in head.decode('ascii', 'replace').split('\n'):
+        tok = line.split()
+        if tok[:1] == ['format'] and tok[1] != 'binary_little_endian':
+            raise ValueError('PLY format %s not supported' % tok[1])
+        if tok[:1] == ['element']:
+            seen_vertex = tok[1] == 'vertex'
+            if seen_vertex:
+                n = int(tok[2])
+        elif tok[:1] == ['property'] and seen_vertex:
+            fields.append((tok[2], types[tok[1]]))
+    rec = np.frombuffer(body, dtype=np.dtype(fields), count=n)
+    return {k: rec[k] for k, _ in fields}
+
+
+def loadpsz(psFile):
+    """loadpsz.m (the parts a bundle needs; document version 1.2, one chunk, one frame sensor): cameras
+    with their chunk-local transforms, the chunk's local-to-global similarity (:203-226), markers with
+    reference positions and image measurements, the sparse point cloud and its projections, the default
+    accuracies (:1021-1056), the camera calibration in DBAT units (:700-868).  Positions are returned in
+    the global frame: P_local = [I 0]/(T diag(1,-1,-1,1)) (:277-290), P_global = P_local/L2G (:341).
+    DBAT point ids: markers 1..nCP in document order, cloud point i -> i+1+nCP (:451-470)."""
+    import xml.etree.ElementTree as ET
+    import zipfile
+    z = zipfile.ZipFile(psFile)
+    chunk = ET.fromstring(z.read('doc.xml')).find('chunks').find('chunk')
+    tf = lambda txt: {'1': True, 'true': True, '0': False, 'false': False}[txt]
+    vec = lambda node: np.array(node.text.split(), float)
+    prop = lambda node: {p.get('name'): p.get('value') for p in node.findall('property')}
+    defStd = {'tiePoints': np.nan, 'projections': np.nan, 'markers': np.nan, 'camPos': np.nan}
+    st = prop(chunk.find('settings')) if chunk.find('settings') is not None else {}
+    for key, name in (('tiepoints', 'tiePoints'), ('cameras', 'camPos'), ('markers', 'markers'), ('projections', 'projections')):
+        if 'accuracy_' + key in st:
+            defStd[name] = float(st['accuracy_' + key])
+    R, T, S = np.eye(4), np.eye(4), np.eye(4)
+    xf = chunk.find('transform')
+    if xf is not None:
+        if xf.find('rotation') is not None:
+            R[:3, :3] = vec(xf.find('rotation')).reshape(3, 3)
+        if xf.find('translation') is not None:
+            T[:3, 3] = vec(xf.find('translation'))
+        if xf.find('scale') is not None:
+            S[:3, :3] *= float(xf.find('scale').text)
+    L2G = T @ S @ R
+    cams = [c for c in chunk.find('cameras').findall('camera')]
+    keep = [c for c in cams if tf(c.get('enabled')) and c.find('transform') is not None]
+    if len({c.get('sensor_id') for c in keep}) > 1:
+        raise NotImplementedError('Handling of cameras for multiple sensor ids not implemented')
+    camIds = [int(c.get('id')) for c in keep]
+    cam_of = {v: i for i, v in enumerate(camIds)}
+    CC = np.zeros((3, len(keep)))
+    Rg = np.zeros((3, 3, len(keep)))
+    for i, c in enumerate(keep):
+        Tc = vec(c.find('transform')).reshape(4, 4)
+        Pl = np.eye(3, 4) @ np.linalg.inv(Tc @ np.diag([1.0, -1.0, -1.0, 1.0]))
+        Pg = Pl @ np.linalg.inv(L2G)
+        CC[:, i] = -np.linalg.solve(Pg[:, :3], Pg[:, 3])           # null(P), euclidean
+        Rg[:, :, i] = Pg[:, :3] / np.cbrt(np.linalg.det(Pg[:, :3]))
+    # markers (control points)
+    markers = chunk.find('markers').findall('marker') if chunk.find('markers') is not None else []
+    rawCP = [int(m.get('id')) for m in markers]
+    cp_of = {v: i + 1 for i, v in enumerate(rawCP)}
+    cpPos = np.full((3, len(markers)), np.nan)
+    cpStd = np.full((3, len(markers)), np.nan)
+    cpEnabled = np.zeros(len(markers), bool)
+    for i, m in enumerate(markers):
+        ref = m.find('reference')
+        cpStd[:, i] = defStd['markers']
+        if ref is not None:
+            for k, axis in enumerate('xyz'):
+                if ref.get(axis) is not None:
+                    cpPos[k, i] = float(ref.get(axis))
+            if ref.get('sxyz') is not None:
+                cpStd[:, i] = float(ref.get('sxyz'))
+            elif ref.get('sxy') is not None:
+                cpStd[0:2, i] = float(ref.get('sxy'))
+            for k, axis in enumerate(('sx', 'sy', 'sz')):
+                if ref.get(axis) is not None:
+                    cpStd[k, i] = float(ref.get(axis))
+            if ref.get('enabled') is not None:
+                cpEnabled[i] = tf(ref.get('enabled'))
+    nCP = len(markers)
+    frame = chunk.find('frames').find('frame')
+    # sparse cloud and its projections
+    pc = frame.find('point_cloud')
+    objPts = np.zeros((0, 4))
+    objMark = np.zeros((0, 4))
+    if pc is not None:
+        pts = _ply_vertices(z.read(pc.find('points').get('path')))
+        local = np.vstack([pts['x'], pts['y'], pts['z'], np.ones(len(pts['x']))]).astype(float)
+        glob = L2G @ local
+        objPts = np.column_stack([pts['id'].astype(float) + 1 + nCP, (glob[:3] / glob[3]).T])
+        rows = []
+        for pr in pc.findall('projections'):
+            if int(pr.get('camera_id')) not in cam_of:
+                continue
+            v = _ply_vertices(z.read(pr.get('path')))
+            rows.append(np.column_stack([np.full(len(v['id']), cam_of[int(pr.get('camera_id'))] + 1.0),
+                                         v['id'].astype(float) + 1 + nCP, v['x'].astype(float), v['y'].astype(float)]))
+        if rows:
+            objMark = np.vstack(rows)
+            objMark = objMark[np.lexsort((objMark[:, 1], objMark[:, 0]))]
+    rows = []
+    fm = frame.find('markers')
+    for m in (fm.findall('marker') if fm is not None else []):
+        for loc in m.findall('location'):
+            if int(loc.get('camera_id')) in cam_of:
+                rows.append([cam_of[int(loc.get('camera_id'))] + 1.0, cp_of[int(m.get('marker_id'))],
+                             float(loc.get('x')), float(loc.get('y'))])
+    ctrlMark = np.array(rows).reshape(-1, 4)
+    ctrlMark = ctrlMark[np.lexsort((ctrlMark[:, 1], ctrlMark[:, 0]))]
+    # image names
+    psDir = os.path.dirname(os.path.abspath(psFile))
+    imNames = [''] * len(keep)
+    for c in frame.find('cameras').findall('camera'):
+        if int(c.get('camera_id')) in cam_of:
+            p = c.find('photo').get('path')
+            absolute = (not p) or p[0] in '/\\' or (len(p) > 1 and p[1] == ':')
+            imNames[cam_of[int(c.get('camera_id'))]] = p if absolute else os.path.normpath(os.path.join(psDir, p))
+    # camera (:700-868)
+    sid = keep[0].get('sensor_id')
+    sensor = [x for x in chunk.find('sensors').findall('sensor') if x.get('id') == sid][0]
+    cals = sensor.findall('calibration')
+    cal = ([c for c in cals if c.get('class') == 'adjusted'] or cals)[0]
+    num = lambda tag, d=None: float(cal.find(tag).text) if cal.find(tag) is not None else d
+    imSz = np.array([float(sensor.find('resolution').get('width')), float(sensor.find('resolution').get('height'))])
+    ppIsAbsolute = cal.find('fx') is not None or cal.find('fy') is not None
+    fx, fy = num('fx', np.nan), num('fy', np.nan)
+    if cal.find('f') is not None:
+        ppIsAbsolute = False
+        fy = num('f')
+        fx = fy + num('b1', 0.0)
+    cx, cy = num('cx', 0.0), num('cy', 0.0)
+    if not ppIsAbsolute:
+        cx, cy = cx + imSz[0] / 2, cy + imSz[1] / 2
+    k = [num('k%d' % n) for n in range(1, 5) if cal.find('k%d' % n) is not None]
+    p = [num('p%d' % n) for n in range(1, 5) if cal.find('p%d' % n) is not None]
+    sp_ = prop(sensor)
+    pixelSz = np.array([float(sp_.get('pixel_width', 1)), float(sp_.get('pixel_height', 1))])
+    focal = fx * pixelSz[0]
+    kk = np.array([-v * focal ** (-2 * (n + 1)) for n, v in enumerate(k)])
+    pp_ = np.array(p, float)
+    if len(pp_) >= 2:
+        pp_[0:2] = pp_[0:2] / focal
+        pp_[1] = -pp_[1]
+        pp_[0:2] = pp_[[1, 0]]
+    camera = NS(name=sensor.get('label'), imSz=imSz, pixelSz=pixelSz, sensorFormat=imSz * pixelSz, focal=focal,
+                pp=np.array([cx, cy]) * pixelSz, k=kk, p=pp_, isFixed=tf(sp_.get('fixed', 'true')),
+                isAdjusted=cal.get('class') == 'adjusted')
+    return NS(fileName=psFile, camera=camera, cameraIds=np.array(camIds), cameraLabels=[c.get('label') for c in keep],
+              imNames=imNames, defStd=NS(**defStd), L2G=L2G,
+              glob=NS(CC=CC, R=Rg, objPts=objPts,
+                      controlPts=NS(id=np.arange(1, nCP + 1), rawId=np.array(rawCP), pos=cpPos, std=cpStd,
+                                    enabled=cpEnabled, labels=[m.get('label', '') for m in markers])),
+              markPts=NS(ctrl=ctrlMark, obj=objMark))
+
+
+def ps2pmstruct(psz):
+    """ps2pmstruct.m (global frame): a loaded PhotoScan project in the shape `loadpm` returns, so that
+    `prob2dbatstruct` applies - camera in PhotoModeler conventions, EO angles by `derotmat3d` of the global
+    rotation (:36-41), enabled markers as control points and the others as check points (:51-66), marker
+    measurements at the 'projections' accuracy and tie points at the 'tiePoints' accuracy (:86-91)."""
+    cam = psz.camera
+    k1k3, p1p2 = np.zeros(3), np.zeros(2)
+    k1k3[:min(3, len(cam.k))] = cam.k[:3]
+    p1p2[:min(2, len(cam.p))] = cam.p[:2]
+    defCam = np.concatenate([[cam.focal], cam.pp, cam.sensorFormat, k1k3, p1p2])
+    job = NS(fileName=psz.fileName, title='Photoscan import', defCam=defCam, defCamStd=np.zeros(10), imSz=cam.imSz)
+    g = psz.glob
+    images = []
+    for i in range(g.CC.shape[1]):
+        M = g.R[:, :, i]
+        ang = np.array([np.arctan2(-M[2, 1], M[2, 2]), np.arcsin(M[2, 0]), np.arctan2(-M[1, 0], M[0, 0])])   # derotmat3d.m
+        images.append(NS(imName=psz.imNames[i], outer=np.concatenate([g.CC[:, i], np.rad2deg(ang[[2, 1, 0]])]),
+                         outerStd=np.zeros(6), imSz=cam.imSz, id=int(psz.cameraIds[i]), label=psz.cameraLabels[i]))
+    cp = g.controlPts
+    tab = lambda sel: np.column_stack([cp.id[sel], cp.pos[:, sel].T, cp.std[:, sel].T]).reshape(-1, 7)
+    ctrlPts, checkPts = tab(cp.enabled), tab(~cp.enabled)
+    ok = np.array([np.count_nonzero(psz.markPts.ctrl[:, 1] == i) >= 2 for i in checkPts[:, 0]], bool)
+    checkPts = checkPts[ok]
+    cPts = np.vstack([ctrlPts, checkPts])
+    order = np.argsort(cPts[:, 0], kind='stable')
+    cPts = cPts[order]
+    objPts = np.vstack([cPts, np.column_stack([g.objPts, np.full((len(g.objPts), 3), np.nan)])])
+    rawOPids = np.concatenate([cp.rawId[cPts[:, 0].astype(int) - 1], g.objPts[:, 0] - 1 - len(cp.id)])
+    OPlabels = [cp.labels[int(i) - 1] for i in cPts[:, 0]] + [''] * len(g.objPts)
+    markPts = np.vstack([np.column_stack([psz.markPts.ctrl, np.full((len(psz.markPts.ctrl), 2), psz.defStd.projections)]),
+                         np.column_stack([psz.markPts.obj, np.full((len(psz.markPts.obj), 2), psz.defStd.tiePoints)])])
+    markPts = markPts[np.lexsort((markPts[:, 1], markPts[:, 0]))]
+    markPts = markPts[np.isin(markPts[:, 1], objPts[:, 0])]
+    markPts[:, 0] -= 1
+    return NS(job=job, images=images, ctrlPts=ctrlPts, cptFile='', checkPts=checkPts, objPts=objPts,
+              priorCamPos=np.zeros((0, 7)), rawOPids=rawOPids, OPlabels=OPlabels, markPts=markPts)

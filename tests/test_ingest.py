@@ -218,3 +218,47 @@ def test_external_verification_against_photomodeler(stub):
     assert np.abs(s3.OP.val[:, j] - meanOffset - pts3d.pos[:, i]).max() < 1.5e-6
     assert np.abs(s3.post.std.OP[:, j] - pts3d.std[:, i]).max() < 1e-6
     assert [len(v) for v in pts3d.vis][:2] == [21, 21] and max(len(v) for v in pts3d.vis) == 21
+
+
+def ps_postproc(psFile):
+    """code/demo/ps_postproc.m:30-105 (no point filtering): PhotoScan project -> PhotoModeler-shaped prob ->
+    struct, forward lens model, camera fixed unless PhotoScan adjusted it, EO / OP start values as
+    PhotoScan estimated them."""
+    psz = ingest.loadpsz(psFile)
+    prob = ingest.ps2pmstruct(psz)
+    s0 = ingest.prob2dbatstruct(prob)
+    s0.IO.model.distModel[:] = -1
+    assert not psz.camera.isAdjusted
+    return s0, psz
+
+
+def test_photoscan_project_from_archive_to_result_file():
+    """ps_postproc('') on data/prague2016/sxb/psprojects/sxb.psz (zip of doc.xml + binary PLY tables): 5
+    cameras placed by the chunk's similarity transform, 16 markers as weighted control points, 1166 tie
+    points with 4018 projections at 1 px and 48 marker measurements at 0.1 px.  Starting from PhotoScan's
+    own estimates the bundle needs 3 iterations (93.8342 -> 48.1954, sigma0 0.710294) and the result file
+    is the reference's `sxb-dbatreport.txt`, iteration count and first error included - which pins the
+    transform chain of loadpsz (camera-to-chunk, axis flip, chunk-to-world) as well."""
+    from oracle.bundle import bundle as obundle, bundle_cov as ocov
+    from dbat_b200.report import bundle_result_file
+    root = os.path.join(GOLD, 'prague2016sxb')
+    s0, psz = ps_postproc(os.path.join(root, 'psprojects', 'sxb.psz'))
+    assert s0.IP.val.shape[1] == 4066 and list(s0.IP.sigmas) == [0.1, 1.0]
+    assert s0.prior.OP.isCtrl.sum() == 16 and s0.prior.OP.use.sum() == 48 and s0.OP.val.shape[1] == 1182
+    assert np.isfinite(s0.EO.val).all() and np.isfinite(s0.OP.val).all()
+    s, ok, it, sig0, E = obundle(copy.deepcopy(s0), 'gna', 20)
+    assert ok and it == 3 and (E.numParams, E.numObs) == (3576, 8180)
+    s, lines = bundle_result_file(s, E, None, cov=ocov)
+    assert report_diff(lines, os.path.join(root, 'psprojects', 'sxb-dbatreport.txt')) == []
+
+
+@pytest.mark.gpu
+def test_photoscan_project_on_the_device():
+    """The same on the device: forward (computer vision) lens model -1, fixed camera, weighted control points."""
+    import dbat_b200
+    root = os.path.join(GOLD, 'prague2016sxb')
+    s0, psz = ps_postproc(os.path.join(root, 'psprojects', 'sxb.psz'))
+    s, ok, it, sig0, E = dbat_b200.bundle(s0, 'gna', 20)
+    assert ok and it == 3
+    s, lines = dbat_b200.bundle_result_file(s, E)
+    assert report_diff(lines, os.path.join(root, 'psprojects', 'sxb-dbatreport.txt'), rtol=1e-5) == []
