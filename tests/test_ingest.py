@@ -262,3 +262,25 @@ def test_photoscan_project_on_the_device():
     assert ok and it == 3
     s, lines = dbat_b200.bundle_result_file(s, E)
     assert report_diff(lines, os.path.join(root, 'psprojects', 'sxb-dbatreport.txt'), rtol=1e-5) == []
+
+
+def test_prague2016_ps_demo_from_archive_to_result_file():
+    """code/demo/prague2016_ps.m ('s5'): the PhotoScan project with the control points of
+    `ref/ctrlpts-weighted-raw.txt` (matched by PhotoScan's marker ids), EO / OP cleared and recomputed by
+    resection and intersection, legacy backward model: `dbatexports/sxb-dbatreport.txt`, exact but for the
+    start-value dependent first error (resection at 1e6 m coordinates: 2e-4)."""
+    root = os.path.join(GOLD, 'prague2016sxb')
+    psz = ingest.loadpsz(os.path.join(root, 'psprojects', 'sxb.psz'))
+    ctrlPts = ingest.loadcpt(os.path.join(root, 'ref', 'ctrlpts-weighted-raw.txt'))
+    s0 = ingest.prob2dbatstruct(ingest.ps2pmstruct(psz))
+    s0 = ingest.setcamvals(s0, 'loaded')
+    s0 = ingest.setcamest(s0, 'not', 'all')
+    i, j = ingest.matchcpt(s0, ctrlPts)
+    assert len(i) == 15
+    s0 = ingest.setcpt(s0, ctrlPts, i, j)
+    s0 = ingest.clearop(ingest.cleareo(s0))
+    lines = _solve_and_report(s0)
+    rep = os.path.join(root, 'dbatexports', 'sxb-dbatreport.txt')
+    exact = report_diff(lines, rep)
+    assert len(exact) == 1 and 'First error' in exact[0][1]
+    assert report_diff(lines, rep, first_error_rtol=5e-4) == []
