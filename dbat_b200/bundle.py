@@ -319,6 +319,9 @@ def gauss_newton_armijo(resFun, vetoFun, x0, W, maxIter, termFun, trace, sTest, 
     return o.x, o.code, o.n, final, o.T, o.rr, o.damping
 
 
+VERSION = 'dbat_b200 0.1 (B200 device path)'
+
+
 def bundle(s, *varargin):
     """bundle.m:1-76: [s,ok,iters,s0,E]=bundle(s[,maxIter|tol][,damping][,'trace'][,...])."""
     maxIter, damping, veto, singularTest = 20, 'gna', False, True      # bundle.m:78-87
@@ -365,7 +368,7 @@ def bundle(s, *varargin):
     W = buildweightmatrix(s)                                           # bundle.m:175
     termFun = make_termfun(convTol, absTerm)                           # bundle.m:186-192
     E = NS(maxIter=maxIter, convTol=convTol, absTerm=absTerm, singularTest=singularTest,
-           chirality=veto)
+           chirality=veto, dateStamp=time.strftime('%d-%b-%Y %H:%M:%S'), version=VERSION)   # bundle.m:263-265
     t0 = time.process_time()
     if damping in ('none', 'gm'):
         raise NotImplementedError("'gm' is broken via bundle() in the reference (bundle.m:273-274)")
