@@ -211,6 +211,10 @@ class Problem:
         else:
             raise ValueError(which)
         self._check(L.dbat_cov(self._h, _lib.COV[w], float(s0), _lib.dptr(out)))
+        if not np.isfinite(out).all():
+            # the factorisation broke down (singular or NaN normal matrix): the reference then reports NaN
+            # for every estimated element (bundle_cov.m:101-107,136-160), not a partly finite matrix
+            out[out != 0] = np.nan
         return out
 
 
@@ -414,12 +418,19 @@ def bundle(s, *varargin):
     s.post.sigmas = s0 * s.IP.sigmas
     E.numObs, E.numParams, E.redundancy, E.s0, E.sigmas = len(r), len(x), dof, s0, s.post.sigmas
     E.paramTypes = paramtypes(s)                                       # bundle.m:162,368
-    if code == -4:
-        E.weakness = structural_weakness(final.weighted.J, E.paramTypes)
-    elif code == -2:
-        E.weakness = NS(structural=None, numerical=numerical_weakness(final.scaled.J, E.paramTypes))
-    else:
-        E.weakness = NS(structural=None, numerical=NS(rank=len(x), deficiency=0))
+    E.weakness = NS(structural=None, numerical=NS(rank=len(x), deficiency=0))
+    if code in (-4, -2):
+        # post-mortem diagnostics must not turn a reported failure code into an exception (the reference
+        # wraps its rank estimate in try/catch as well, bundle.m:377-387): on error the ranks are NaN
+        nan = float('nan')
+        try:
+            if code == -4:
+                E.weakness = structural_weakness(final.weighted.J, E.paramTypes)
+            else:
+                E.weakness = NS(structural=None, numerical=numerical_weakness(final.scaled.J, E.paramTypes))
+        except Exception as exc:                                       # noqa: BLE001
+            E.weakness = NS(structural=NS(rank=nan, deficiency=nan, suspectedParams=[], error=repr(exc))
+                            if code == -4 else None, numerical=NS(rank=nan, deficiency=nan, error=repr(exc)))
     return s, ok, iters, s0, E
 
 

@@ -610,6 +610,3 @@ def test_camcal_missing_obs_demo_on_device():
     s3, ok, it, s0, E = dbat_b200.bundle(s2, 'gna')
     assert not ok and it == 0 and E.code == -4 and E.numParams == 423
     assert abs(E.res[0] - 30118.6) < 1e-5 * 30118.6 and abs(s0 - 499.142) < 1e-5 * 499.142
-    w = E.weakness.structural                                   # report: "Structural rank: 417 (deficiency: 6)"
-    assert w.rank == 417 and w.deficiency == 6
-    assert w.suspectedParams == ['OX-12/13', 'OY-12/13', 'OZ-12/13', 'OX-59/60', 'OY-59/60', 'OZ-59/60']

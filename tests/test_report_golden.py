@@ -382,3 +382,26 @@ def test_roma_result_file_from_the_device():
         assert abs(got[k] - v) < 1e-9 * abs(v), k
     s, lines = bundle_result_file(s, E)
     assert report_diff(lines, os.path.join(GOLD, 'romabundledemo', 'result', 'report.txt'), rtol=1e-5) == []
+
+
+@pytest.mark.gpu
+def test_failed_run_result_file_from_the_device():
+    """camcaldemo_missing_obs.m on the device: code -4, and the post-mortem on the device-exported Jacobian -
+    "Structural rank: 417 (deficiency: 6)" with the six suspected parameters - then the result file of the
+    failed run (NaN deviations, start values) against the reference's."""
+    import dbat_b200
+    from oracle.loaders import camcal_pm_struct
+    G = os.path.join(GOLD, 'camcalpm')
+    s = camcal_pm_struct(os.path.join(G, 'camcal-pmexport-missing-obs.txt'), os.path.join(G, 'camcal-fixed.txt'))
+    s.proj.x0desc = 'Camera calibration from EXIF value'
+    cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+    s1, _, fail = dbat_b200.resect(s, 'all', cpId, 1, 0, cpId)
+    s2, _, _ = dbat_b200.forwintersect(s1, 'all', True)
+    s3, ok, it, s0, E = dbat_b200.bundle(s2, 'gna')
+    assert E.code == -4
+    w = E.weakness.structural
+    assert not hasattr(w, 'error'), w.error
+    assert w.rank == 417 and w.deficiency == 6
+    assert w.suspectedParams == ['OX-12/13', 'OY-12/13', 'OZ-12/13', 'OX-59/60', 'OY-59/60', 'OZ-59/60']
+    s3, lines = dbat_b200.bundle_result_file(s3, E)
+    assert report_diff(lines, os.path.join(G, 'camcal-dbatreport-missing-obs.txt'), rtol=1e-4) == []
