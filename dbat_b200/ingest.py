@@ -502,10 +502,19 @@ def seteoest(s, *args):
     """seteoest.m: seteoest(s[, cams], names...) ('not' as in setcamest, 'none' = nothing estimated), or
     seteoest(s, 'depend'[, camNo]) for the dependent-pair datum (camNo 1-based as in the reference)."""
     args = list(args)
-    if args and isinstance(args[0], str) and args[0] == 'depend':
-        if len(args) > 2:
-            raise NotImplementedError("seteoest 'depend' with a fixed axis")
-        return seteoest_depend(s, int(args[1]) - 1 if len(args) > 1 else 0)
+    if args and isinstance(args[0], str) and args[0] == 'depend':          # setdepend, seteoest.m:90-128
+        rest = args[1:]
+        camNo = int(rest.pop(0)) - 1 if rest and not isinstance(rest[0], str) else 0
+        if not rest or rest[0] == 'pos':
+            return seteoest_depend(s, camNo)
+        if rest[0] not in ('x', 'y', 'z'):
+            raise ValueError('SETEOEST: Bad position argument for depend.')
+        row = 'xyz'.index(rest[0])                                         # longest baseline along one axis
+        offset = s.EO.val[row] - s.EO.val[row, camNo]
+        s.bundle.est.EO[:] = True
+        s.bundle.est.EO[:, camNo] = False
+        s.bundle.est.EO[row, int(np.argmax(offset))] = False
+        return s
     cams = np.arange(s.EO.val.shape[1])
     doEst = True
     for a in args:

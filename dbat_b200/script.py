@@ -282,9 +282,13 @@ def _run_operations(s, ops, backend, log):
         elif node.tag == 'set_datum':
             if (node.text or '').strip() != 'depend':
                 raise ValueError('DBAT XML operation set_datum error: Unknown datum %s' % node.text)
-            if node.get('ref_base', 'longest') != 'longest':
-                raise NotImplementedError("set_datum ref_base '%s'" % node.get('ref_base'))
-            ingest.seteoest(s, 'depend', int(node.get('ref_cam', 1)))
+            base = node.get('ref_base', 'longest')
+            if base == 'longest':
+                ingest.seteoest(s, 'depend', int(node.get('ref_cam', 1)))
+            elif base in ('x', 'y', 'z'):
+                ingest.seteoest(s, 'depend', int(node.get('ref_cam', 1)), base)
+            else:
+                raise ValueError("DBAT XML operation set_datum error: Unknown reference base '%s'" % base)
         else:
             raise ValueError('DBAT XML script operations error: Unknown operation %s' % node.tag)
     return s, E

@@ -143,6 +143,10 @@ def test_setters_follow_the_reference_argument_rules():
     s.EO.val[:] = np.arange(30.0).reshape(6, 5) * [[1], [2], [-1], [1], [1], [1]]
     s = ingest.seteoest(s, 'depend', 1)
     assert not s.bundle.est.EO[:, 0].any() and s.bundle.est.EO.sum() == 30 - 7 and not s.bundle.est.EO[1, 4]
+    s = ingest.seteoest(s, 'depend', 2, 'z')                        # base camera 2, longest baseline along z
+    assert not s.bundle.est.EO[:, 1].any() and s.bundle.est.EO.sum() == 30 - 7 and not s.bundle.est.EO[2, 0]
+    with pytest.raises(ValueError):
+        ingest.seteoest(s, 'depend', 1, 'w')
     with pytest.raises(NotImplementedError):
         ingest.prob2dbatstruct(ingest.loadpm(os.path.join(CAMCAL, 'camcal-pmexport5.txt')), True)
 
