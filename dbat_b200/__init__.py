@@ -11,9 +11,9 @@ All numerical work runs in libdbatgpu.so (hand-written sm_100a CUDA, include/dba
 from .bundle import (Problem, bundle, bundle_cov, gauss_markov, gauss_newton_armijo, levenberg_marquardt,
                      levenberg_marquardt_powell, make_termfun)
 from .photogrammetry import forwintersect, resect
-from .report import (angles, bundle_residuals, bundle_result_file, corrmat, coverage, cumchi2,
+from .report import (angles, bundle_residuals, bundle_result_file, camangles, corrmat, coverage, cumchi2,
                      high_eo_correlations, high_io_correlations, high_op_correlations,
-                     test_distortion_params)
+                     test_distortion_params, writestats)
 from .ingest import (cleareo, clearop, legacyloadeotable, loadcpt, loadctrlpts, loadeotable, loadimagepts,
                      loadimagetable, loadpm, loadpm3dtbl, loadpsz, ps2pmstruct, matchcpt, matcheo, prob2dbatstruct,
                      setcamest, setcamvals, setcpt, seteoest, setprioreo)
@@ -24,7 +24,7 @@ from .dbatstruct import (buildserialindices, buildweightmatrix, deserialize, new
 __all__ = ['Problem', 'bundle', 'bundle_cov', 'gauss_markov', 'gauss_newton_armijo', 'levenberg_marquardt',
            'levenberg_marquardt_powell', 'make_termfun', 'forwintersect', 'resect', 'bundle_result_file', 'corrmat', 'cumchi2',
            'high_io_correlations', 'high_eo_correlations', 'high_op_correlations', 'test_distortion_params',
-           'bundle_residuals', 'coverage', 'angles', 'loadpm', 'prob2dbatstruct', 'loadcpt', 'matchcpt', 'setcpt',
+           'bundle_residuals', 'coverage', 'angles', 'camangles', 'writestats', 'loadpm', 'prob2dbatstruct', 'loadcpt', 'matchcpt', 'setcpt',
            'setcamvals', 'setcamest', 'seteoest', 'cleareo', 'clearop', 'legacyloadeotable', 'matcheo', 'setprioreo', 'loadimagepts', 'loadctrlpts',
            'loadimagetable', 'loadeotable', 'loadpm3dtbl', 'loadpsz', 'ps2pmstruct', 'rundbatscript', 'buildserialindices',
            'buildweightmatrix', 'deserialize', 'new_struct', 'serialize', 'seteoest_depend']

@@ -12,6 +12,7 @@ Host mirror of the reference's `bundle_result_file` and the statistics it is bui
   coverage                 `code/photogrammetry/coverage.m`
   angles                   `code/photogrammetry/angles.m`
   bundle_result_file       `code/bundle/bundle_result_file.m`
+  writestats, camangles    `code/file/writestats.m`, `code/photogrammetry/camangles.m` (pre-bundle statistics)
 
 The covariances come from `bundle_cov`, i.e. from the factorisation that lives on the device; what is
 done here is O(unknowns) post-processing and text layout.  Everything is written against the block
@@ -791,3 +792,203 @@ def bundle_result_file(s, e, f=None, cov=_device_cov):
         with open(f, 'wt') as fid:
             fid.write('\n'.join(out.lines) + '\n')
     return s, out.lines
+
+
+# ----------------------------------------------------------------------------- pre-bundle statistics
+def camangles(s):
+    """camangles.m: per image the largest angle (rad, folded to [0, pi/2]) between any two of its rays."""
+    nImg = s.EO.val.shape[1]
+    a = np.zeros(nImg)
+    for i in range(nImg):
+        pp = s.OP.val[:, np.asarray(s.IP.op)[np.asarray(s.IP.img) == i]]
+        if pp.shape[1] < 2:
+            continue
+        d = s.EO.val[0:3, i:i + 1] - pp
+        dn = d / np.sqrt((d ** 2).sum(axis=0))
+        lo = 1.0
+        for c0 in range(0, dn.shape[1], 2048):                   # min |cos| over all pairs, in row blocks
+            lo = min(lo, float(np.abs(np.clip(dn[:, c0:c0 + 2048].T @ dn, -1, 1)).min()))
+        a[i] = np.arccos(lo)
+    return a
+
+
+def _sturges_edges(x):
+    """Bin edges of MATLAB's histcounts(x,'BinMethod','sturges'): ceil(log2(n)+1) bins widened to a 'nice'
+    width (1, 2, 3, 5 or 10 times a power of ten) with the left edge on a multiple of it."""
+    x = np.asarray(x, float)
+    nbins = max(int(np.ceil(np.log2(len(x)) + 1)), 1)
+    xmin, xmax = x.min(), x.max()
+    rng = xmax - xmin
+    scale = max(abs(xmin), abs(xmax))
+    raw = max(rng / nbins, np.spacing(scale))
+    if rng <= max(np.sqrt(np.spacing(scale)), np.finfo(float).tiny):
+        return np.array([np.floor(xmin) - 0.5 * 0 + 0.0, np.floor(xmin) + 1.0])
+    p10 = 10.0 ** np.floor(np.log10(raw))
+    rel = raw / p10
+    width = p10 * (1 if rel < 1.5 else 2 if rel < 2.5 else 3 if rel < 4 else 5 if rel < 7.5 else 10)
+    left = min(width * np.floor(xmin / width), xmin)
+    n = max(1, int(np.ceil((xmax - left) / width)))
+    return left + width * np.arange(n + 1)
+
+
+def _hist_centers(x, centers):
+    """MATLAB hist(x, centers): bins split at the midpoints, open-ended at both ends."""
+    mid = (centers[:-1] + centers[1:]) / 2
+    return np.bincount(np.digitize(x, mid, right=True), minlength=len(centers))
+
+
+def writestats(s, fName=None, desc=''):
+    """writestats.m: pre-bundle statistics of a project - image ray counts and ray angles, control and
+    object point ray counts and angles with their histograms and worst cases.  Returns (s, lines) with
+    s.camRayAng / s.rayAng (degrees) stored like the reference does."""
+    digits = lambda v: int(np.floor(np.log10(v))) + 1 if v > 0 else 1
+    L = []
+    w = L.append
+    nImg, nOP = s.EO.val.shape[1], s.OP.val.shape[1]
+    isCtrl = np.asarray(s.prior.OP.isCtrl, bool)
+    nCp = int(isCtrl.sum())
+    w(desc)
+    w('')
+    w('Project file: %s' % _get(s, 'proj.fileName', ''))
+    w('')
+    w('Execution time stamp: %s' % time.strftime('%Y-%m-%d %H:%M:%S'))
+    w('')
+    w('Total # OP          : %d' % (nOP - nCp))
+    w('Total # CP          : %d' % nCp)
+    w('Total # cams        : %d' % nImg)
+    w('Total # image marks : %d' % s.IP.val.shape[1])
+    w('Project units       : %s' % _get(s, 'proj.objUnit', 'm'))
+    w('')
+    w('Project images: no (id), shortened label, name:')
+    labels = list(_get(s, 'EO.label', None) or s.EO.name)
+    labelLen = max(len(l) for l in labels)
+    if labelLen > 8:                                              # drop the common leading part of long labels
+        shortest = min(len(l) for l in labels)
+        mat = np.array([list(l.ljust(labelLen)) for l in labels])
+        diff = np.flatnonzero(~np.all(mat == mat[0], axis=0))
+        neq = (diff[0] + 1) if len(diff) else labelLen + 1
+        if shortest < neq:
+            cut = shortest - 4
+        else:
+            cut = neq - 4
+            if cut > 0:
+                na = [k for k, ch in enumerate(labels[0][cut:cut + 3]) if not ch.isalnum()]
+                if na:
+                    cut += na[-1] + 1
+        if cut > 4:
+            labels = [l[cut:] for l in labels]
+            labelLen = max(len(l) for l in labels)
+    eid = np.asarray(_get(s, 'EO.id', np.arange(1, nImg + 1)))
+    dNo, dId = digits(nImg), digits(max(int(eid.max()), 1))
+    imDir = _get(s, 'proj.imDir', '')
+    for i in range(nImg):
+        w('  %-*d (%-*d), %-*s, %s' % (dNo, i + 1, dId, eid[i], labelLen, labels[i], os.path.join(imDir, s.EO.name[i])))
+    w('')
+    w('')
+    w('IMAGE STATISTICS')
+    cnt = np.bincount(s.IP.img, minlength=nImg)
+    dC = digits(cnt.max())
+    w('')
+    w('Image ray count:')
+    w('  min : %*d' % (dC, cnt.min()))
+    w('  max : %*d' % (dC, cnt.max()))
+    w('  mean: %*d' % (dC, int(np.floor(cnt.mean() + 0.5))))
+    edges = _sturges_edges(cnt)
+    n = np.histogram(cnt, edges)[0]
+    edges = edges.copy()
+    edges[-1] += 1
+    dE = digits(edges.max())
+    w('')
+    w('Image with lowest ray count: cam no (id), label, count')
+    o = np.argsort(cnt, kind='stable')
+    srt = cnt[o]
+    for j in range(int(np.count_nonzero(srt < srt[min(3, len(srt)) - 1] * 1.1 + 0.1))):
+        w('  %*d (%*d), %-*s, %*d' % (dNo, o[j] + 1, dId, eid[o[j]], labelLen, labels[o[j]], dE, srt[j]))
+    w('')
+    w('Image ray count histogram: nRays, nCams')
+    for i in range(len(n)):
+        w('  %*d-%*d: %d' % (dE, edges[i], dE, edges[i + 1] - 1, n[i]))
+    if getattr(s, 'camRayAng', None) is None:
+        s.camRayAng = camangles(s) * 180 / np.pi
+    ca = s.camRayAng
+    w('')
+    w('Image ray angles (deg):')
+    w('  min : %4.1f' % ca.min())
+    w('  max : %4.1f' % ca.max())
+    w('  mean: %4.1f' % ca.mean())
+    w('')
+    w('Smallest image ray angles: cam no (id), label, nRays, angle')
+    o = np.argsort(ca, kind='stable')
+    srt = ca[o]
+    for j in range(int(np.count_nonzero(srt < srt[min(3, len(srt)) - 1] * 1.1 + 0.1))):
+        w('  %*d (%*d), %-*s, %*d, %4.1f' % (dNo, o[j] + 1, dId, eid[o[j]], labelLen, labels[o[j]], dE, cnt[o[j]], srt[j]))
+    aa = np.arange(0.0, 91.0, 5.0)
+
+    def angle_hist(vals):
+        h = _hist_centers(vals, aa)
+        d = digits(h.max())
+        for a_, c_ in zip(aa, h):
+            w('  %2d, %*d' % (a_, d, c_))
+    w('')
+    w('Image ray angle histogram: angle, count')
+    angle_hist(ca)
+    rays = _ray_counts(s)
+    if getattr(s, 'rayAng', None) is None:
+        s.rayAng = angles(s) * 180 / np.pi
+    ra = s.rayAng
+    rawId = np.asarray(_get(s, 'OP.rawId', s.OP.id))
+    oplab = _get(s, 'OP.label', None) or [''] * nOP
+    vis_of = lambda j: ', '.join(labels[i] for i in np.sort(np.asarray(s.IP.img)[np.asarray(s.IP.op) == j]))
+    for ix, title, tag in ((np.flatnonzero(isCtrl), 'CONTROL POINT STATISTICS', 'CP'),
+                           (np.flatnonzero(~isCtrl), 'OBJECT POINT STATISTICS', 'OP')):
+        w('')
+        w('')
+        w(title)
+        if not np.any(ix):                                       # (`~any(ix)`: also skips a lone point with index 0)
+            continue
+        r = rays[ix]
+        dR = digits(r.max())
+        w('')
+        w('%s ray count:' % tag)
+        w('  min : %*d' % (dR, r.min()))
+        w('  max : %*d' % (dR, r.max()))
+        w('  mean: %*.1f' % (dR + 2, r.mean()))
+        w('')
+        w('%s ray count histogram: nRays, count' % tag)
+        h = np.bincount(r)
+        nz = np.flatnonzero(h)
+        dn_, dc_ = digits(nz.max() + 1), digits(h.max())
+        for k in nz:
+            w('  %*d, %*d' % (dn_, k, dc_, h[k]))
+
+        def worst(vals, with_angle):
+            o = np.argsort(vals, kind='stable')
+            srt = vals[o]
+            cut = int(np.count_nonzero(srt < srt[min(3, len(srt)) - 1] * 1.1 + 0.1))
+            sel = ix[o[:cut]]
+            ll = max(len(oplab[j]) for j in sel)
+            d1, d2 = digits(sel.max() + 1), digits(max(int(rawId[sel].max()), 1))
+            d3 = digits(max(int(rays[sel].max()), 1)) if with_angle else digits(max(int(srt[cut - 1]), 1))
+            w('')
+            if with_angle:
+                w('Smallest %s ray angles: %s no (id), %snRays, angle, (images with rays)' % (tag, tag, 'label, ' if ll else ''))
+            else:
+                w('%s with lowest ray count: %s no (id), %snRays, (images with rays)' % (tag, tag, 'label, ' if ll else ''))
+            for j, v in zip(sel, srt[:cut]):
+                head = '  %*d (%*d), ' % (d1, j + 1, d2, rawId[j]) + ('%-*s, ' % (ll, oplab[j]) if ll else '')
+                body = '%*d, %4.1f, ' % (d3, rays[j], v) if with_angle else '%*d, ' % (d3, rays[j])
+                w(head + body + '(%s)' % vis_of(j))
+        worst(r.astype(float), False)
+        w('')
+        w('%s ray angles:' % tag)
+        w('  min : %4.1f' % np.min(ra[ix]))
+        w('  max : %4.1f' % np.max(ra[ix]))
+        w('  mean: %4.1f' % np.mean(ra[ix]))
+        worst(ra[ix], True)
+        w('')
+        w('%s ray angle histogram: angle, count' % tag)
+        angle_hist(ra[ix])
+    if fName is not None:
+        with open(fName, 'wt') as fh:
+            fh.write('\n'.join(L) + '\n')
+    return s, L

@@ -93,6 +93,7 @@ FILES = {
         'data/prague2016/sxb/psprojects/sxb.psz',                       # PhotoScan archive (XML + PLY), 150 kB
         'data/prague2016/sxb/psprojects/sxb-dbatreport.txt',
         'data/prague2016/sxb/dbatexports/sxb-dbatreport.txt',
+        'data/prague2016/sxb/psprojects/sxb-psstats-prefilt.txt',
         'data/prague2016/sxb/ref/ctrlpts-weighted-raw.txt',
     ],
     'dbatexports': [

@@ -288,3 +288,19 @@ def test_prague2016_ps_demo_from_archive_to_result_file():
     exact = report_diff(lines, rep)
     assert len(exact) == 1 and 'First error' in exact[0][1]
     assert report_diff(lines, rep, first_error_rtol=5e-4) == []
+
+
+def test_photoscan_project_statistics_file():
+    """ps_postproc.m:70-76 -> writestats.m: the 1101-line pre-bundle statistics of the PhotoScan project
+    (image / control point / object point ray counts and ray angles, MATLAB-style histograms, worst cases)
+    against `psprojects/sxb-psstats-prefilt.txt`; only the path and time stamp lines differ."""
+    from dbat_b200.report import writestats
+    root = os.path.join(GOLD, 'prague2016sxb')
+    s0, psz = ps_postproc(os.path.join(root, 'psprojects', 'sxb.psz'))
+    s0, lines = writestats(s0, None, 'Initial, unfiltered statitistics')
+    gold = [l.rstrip('\n') for l in open(os.path.join(root, 'psprojects', 'sxb-psstats-prefilt.txt'))]
+    assert len(lines) == len(gold) == 1101
+    bad = [(n + 1, a, b) for n, (a, b) in enumerate(zip(gold, lines)) if a != b]
+    assert [n for n, _, _ in bad] == [3, 5, 14, 15, 16, 17, 18]          # project file, time stamp, image paths
+    assert all(a.split(', ')[:2] == b.split(', ')[:2] for n, a, b in bad if n >= 14)
+    assert s0.camRayAng.shape == (5,) and s0.rayAng.shape == (1182,)
