@@ -137,13 +137,37 @@ def serialize(s):
     return x
 
 
-def deserialize(s, x):
-    """deserialize.m:28-30 (two-argument form): returns the struct updated in place."""
+def deserialize(s, x, i=None, what=None):
+    """deserialize.m:20-100.
+    deserialize(s, x): the struct updated in place from the vector of unknowns x (:28-30).
+    deserialize(s, E, i): the same from column i of the iteration trace E.trace (0 = start values,
+    np.inf = last), i.e. a rewind to that iteration (:31-46).
+    deserialize(s, E, v, 'IO'|'EO'|'OP'): an array with one layer per iteration in v ('all' = every
+    iteration) of that parameter group; s is left alone (:47-100)."""
+    if i is None:
+        cols = {None: np.asarray(x)}
+    else:
+        E = x
+        if E is None or getattr(E, 'trace', None) is None:
+            raise ValueError('Empty bundle iteration struct')
+        T = np.asarray(E.trace)
+        if what is None:
+            cols = {None: T[:, T.shape[1] - 1 if i == np.inf else int(i)]}
+        else:
+            v = np.arange(T.shape[1]) if isinstance(i, str) and i == 'all' else np.atleast_1d(i).astype(int)
+            fld = getattr(s, what)
+            des = getattr(s.bundle.deserial, what)
+            out = np.repeat(fld.val[:, :, None], len(v), axis=2)
+            r, c = np.unravel_index(des.dest, fld.val.shape, order='F')
+            for k, it in enumerate(v):
+                out[r, c, k] = T[des.src, it]
+            return out
+    xv = cols[None]
     for name in ('IO', 'EO', 'OP'):
         fld = getattr(s, name)
         des = getattr(s.bundle.deserial, name)
         v = _lin(fld.val).copy()
-        v[des.dest] = x[des.src]
+        v[des.dest] = xv[des.src]
         fld.val = v.reshape(fld.val.shape, order='F')
     return s
 

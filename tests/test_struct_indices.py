@@ -101,3 +101,30 @@ def test_depend_datum():
     orc.seteoest_depend(so, 0)
     assert np.array_equal(s.bundle.est.EO, so.bundle.est.EO)
     assert s.bundle.est.EO.size - s.bundle.est.EO.sum() == 7      # seteoest.m:125-128
+
+
+def test_deserialize_rewinds_to_an_iteration_of_the_trace():
+    """deserialize.m:31-100: deserialize(s,E,i) puts iteration i of E.trace back into the struct (the
+    reference's only resume mechanism); deserialize(s,E,v,'EO') stacks a parameter group over iterations."""
+    from types import SimpleNamespace as NS
+    rng = np.random.default_rng(5)
+    s = _random_struct(rng, shared_io=True)
+    prod.buildserialindices(s)
+    x0 = prod.serialize(s)
+    trace = np.stack([x0 + k for k in range(4)], axis=1)          # 4 iterations, every unknown +k
+    E = NS(trace=trace)
+    fixedEO = s.EO.val.copy()
+    for i, col in ((0, 0), (2, 2), (np.inf, 3)):
+        t = prod.deserialize(copy.deepcopy(s), E, i)
+        assert np.array_equal(prod.serialize(t), trace[:, col])
+        est = s.bundle.est.EO
+        assert np.array_equal(t.EO.val[~est], fixedEO[~est])       # what is not estimated keeps its value
+    EO = prod.deserialize(s, E, 'all', 'EO')
+    assert EO.shape == s.EO.val.shape + (4,)
+    for k in range(4):
+        np.testing.assert_array_equal(EO[:, :, k], prod.deserialize(copy.deepcopy(s), E, k).EO.val)
+    IO = prod.deserialize(s, E, [1, 3], 'IO')
+    assert IO.shape[2] == 2 and np.array_equal(IO[:, :, 1], prod.deserialize(copy.deepcopy(s), E, 3).IO.val)
+    assert np.array_equal(prod.serialize(s), x0)                   # the 4-argument form leaves s alone
+    with pytest.raises(ValueError):
+        prod.deserialize(s, None, 1)
