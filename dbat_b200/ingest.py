@@ -358,6 +358,35 @@ def loadpm3dtbl(fName):
               std=np.array(std).T.reshape(3, -1), fileName=fName)
 
 
+def loadpmreport(fName):
+    """loadpmreport.m (the parts the external verification uses): PhotoModeler's status report - per photo
+    the EO values and standard deviations [omega, phi, kappa (rad), X, Y, Z], and the processing summary
+    (iterations, first / last total error)."""
+    import re
+    EO, STD, info = [], [], {}
+    with open(fName) as fh:
+        for line in fh:
+            t = line.strip()
+            m = re.match(r'(Number of Processing Iterations|First Error|Last Error): ([-\d.eE+]+)', t)
+            if m:
+                info[m.group(1)] = float(m.group(2))
+            elif re.match(r'Photo \d+:', t):
+                EO.append([])
+                STD.append([])
+            elif EO and len(STD[-1]) < 6:
+                m = re.match(r'Value: ([-\d.eE+]+)', t)
+                if m:
+                    EO[-1].append(float(m.group(1)))
+                m = re.match(r'Deviation: \w+: ([-\d.eE+]+)', t)
+                if m:
+                    STD[-1].append(float(m.group(1)))
+    EO, STD = np.array([e[:6] for e in EO]).T, np.array(STD).T
+    toRad = np.array([[np.pi / 180]] * 3 + [[1.0]] * 3)
+    return NS(EO=(EO * toRad)[[3, 4, 5, 0, 1, 2]], EOstd=(STD * toRad)[[3, 4, 5, 0, 1, 2]],
+              iterations=info.get('Number of Processing Iterations'), firstError=info.get('First Error'),
+              lastError=info.get('Last Error'), fileName=fName)
+
+
 def legacyloadeotable(fName, has=(True, True)):
     """legacyloadeotable.m: a camera-station table in the control-point format (`loadcpt`)."""
     return loadcpt(fName, has)

@@ -52,6 +52,8 @@ FILES = {
         'data/prague2016/cam/dbatexports/weighted-with-orient-dbatreport.txt',
         'data/prague2016/cam/pmexports/weighted-no-orient-3dpts.txt',      # PhotoModeler's own result tables
         'data/prague2016/cam/pmexports/fixed-no-orient-3dpts.txt',
+        'data/prague2016/cam/pmexports/weighted-no-orient-pmreport.txt',
+        'data/prague2016/cam/pmexports/fixed-no-orient-pmreport.txt',
         'data/prague2016/cam/dbatexports/fixed-with-orient-dbatreport.txt',
     ],
     'stpierre': [

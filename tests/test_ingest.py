@@ -221,6 +221,14 @@ def test_external_verification_against_photomodeler(stub):
     assert len(i) == len(pts3d.id) == 100
     assert np.abs(s3.OP.val[:, j] - meanOffset - pts3d.pos[:, i]).max() < 1.5e-6
     assert np.abs(s3.post.std.OP[:, j] - pts3d.std[:, i]).max() < 1e-6
+    # camera stations and total error against PhotoModeler's status report (values printed to 1e-6, deviations
+    # to 1e-3): its own adjustment stopped a little short of the minimum, as the reference's paper reports
+    pm = ingest.loadpmreport(os.path.join(root, 'pmexports', '%s-no-orient-pmreport.txt' % stub))
+    assert pm.EO.shape == (6, 21)
+    assert np.abs(s3.EO.val[0:3] - pm.EO[0:3]).max() < 5e-5 and np.abs(s3.EO.val[3:6] - pm.EO[3:6]).max() < np.deg2rad(1e-3)
+    assert np.abs(s3.post.std.EO[0:3] - pm.EOstd[0:3]).max() < 6e-4
+    assert np.abs(s3.post.std.EO[3:6] - pm.EOstd[3:6]).max() < np.deg2rad(6e-4)
+    assert abs(sig0 / pm.lastError - 1) < 2e-3
     assert [len(v) for v in pts3d.vis][:2] == [21, 21] and max(len(v) for v in pts3d.vis) == 21
 
 
