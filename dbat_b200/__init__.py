@@ -14,7 +14,7 @@ from .photogrammetry import forwintersect, resect
 from .report import (angles, bundle_residuals, bundle_result_file, camangles, corrmat, coverage, cumchi2,
                      high_eo_correlations, high_io_correlations, high_op_correlations,
                      test_distortion_params, writestats)
-from .ingest import (cleareo, clearop, legacyloadeotable, loadcpt, loadctrlpts, loadeotable, loadimagepts,
+from .ingest import (cleareo, clearop, filterprob, legacyloadeotable, loadcpt, loadctrlpts, loadeotable, loadimagepts,
                      loadimagetable, loadpm, loadpm3dtbl, loadpmreport, loadpsz, ps2pmstruct, matchcpt, matcheo, prob2dbatstruct,
                      setcamest, setcamvals, setcpt, seteoest, setprioreo)
 from .script import rundbatscript
@@ -26,5 +26,5 @@ __all__ = ['Problem', 'bundle', 'bundle_cov', 'gauss_markov', 'gauss_newton_armi
            'high_io_correlations', 'high_eo_correlations', 'high_op_correlations', 'test_distortion_params',
            'bundle_residuals', 'coverage', 'angles', 'camangles', 'writestats', 'loadpm', 'prob2dbatstruct', 'loadcpt', 'matchcpt', 'setcpt',
            'setcamvals', 'setcamest', 'seteoest', 'cleareo', 'clearop', 'legacyloadeotable', 'matcheo', 'setprioreo', 'loadimagepts', 'loadctrlpts',
-           'loadimagetable', 'loadeotable', 'loadpm3dtbl', 'loadpmreport', 'loadpsz', 'ps2pmstruct', 'rundbatscript', 'buildserialindices',
+           'loadimagetable', 'loadeotable', 'loadpm3dtbl', 'loadpmreport', 'filterprob', 'loadpsz', 'ps2pmstruct', 'rundbatscript', 'buildserialindices',
            'buildweightmatrix', 'deserialize', 'new_struct', 'serialize', 'seteoest_depend']

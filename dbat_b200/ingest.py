@@ -773,3 +773,25 @@ def ps2pmstruct(psz):
     markPts[:, 0] -= 1
     return NS(job=job, images=images, ctrlPts=ctrlPts, cptFile='', checkPts=checkPts, objPts=objPts,
               priorCamPos=np.zeros((0, 7)), rawOPids=rawOPids, OPlabels=OPlabels, markPts=markPts)
+
+
+def filterprob(prob, s0, minRays=0, minAngle=0.0):
+    """loadplotpsz.m:58-90: drop the object points (never control points) seen in fewer than minRays images
+    or whose largest ray intersection angle is below minAngle degrees, from prob; returns (prob, removed ids).
+    Rebuild the struct with prob2dbatstruct afterwards, as the reference does."""
+    from .report import angles
+    isCtrl = np.asarray(s0.prior.OP.isCtrl, bool)
+    bad = np.zeros(len(isCtrl), bool)
+    if minRays > 0:
+        bad |= (np.bincount(s0.IP.op, minlength=len(isCtrl)) < minRays) & ~isCtrl
+    if minAngle > 0:
+        with np.errstate(invalid='ignore'):
+            bad |= (np.rad2deg(angles(s0)) < minAngle) & ~isCtrl
+    ids = np.asarray(s0.OP.id)[bad]
+    keepObj = ~np.isin(prob.objPts[:, 0], ids)
+    out = NS(**vars(prob))
+    out.objPts = prob.objPts[keepObj]
+    out.rawOPids = np.asarray(prob.rawOPids)[keepObj]
+    out.OPlabels = [l for l, k in zip(prob.OPlabels, keepObj) if k]
+    out.markPts = prob.markPts[~np.isin(prob.markPts[:, 1], ids)]
+    return out, ids

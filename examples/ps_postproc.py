@@ -1,6 +1,6 @@
 """The reference's `code/demo/ps_postproc.m` on the device path.
 
-    python examples/ps_postproc.py [project.psz [report.txt]]
+    python examples/ps_postproc.py [project.psz [report.txt [minRays [minAngle]]]]
 
 Loads a PhotoScan archive, keeps PhotoScan's own orientation and tie points as start values, uses the
 enabled markers as weighted control points and runs the bundle with the forward (computer vision) lens
@@ -19,6 +19,12 @@ reportFile = sys.argv[2] if len(sys.argv) > 2 else os.path.splitext(os.path.base
 psz = dbat.loadpsz(fileName)                                                 # ps_postproc.m:56
 prob = dbat.ps2pmstruct(psz)                                                 # loadplotpsz.m:48
 s0 = dbat.prob2dbatstruct(prob)                                              # loadplotpsz.m:52
+minRays = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+minAngle = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0
+if minRays > 0 or minAngle > 0:                                              # loadplotpsz.m:58-90
+    prob, removed = dbat.filterprob(prob, s0, minRays, minAngle)
+    s0 = dbat.prob2dbatstruct(prob)
+    print('Filtered %d object points.' % len(removed))
 s0.IO.model.distModel[:] = -1                                                # ps_postproc.m:69
 if psz.camera.isAdjusted:                                                    # :86-110: estimate what PhotoScan adjusted
     s0 = dbat.setcamest(s0, 'not', 'all')

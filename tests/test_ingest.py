@@ -312,3 +312,26 @@ def test_photoscan_project_statistics_file():
     assert [n for n, _, _ in bad] == [3, 5, 14, 15, 16, 17, 18]          # project file, time stamp, image paths
     assert all(a.split(', ')[:2] == b.split(', ')[:2] for n, a, b in bad if n >= 14)
     assert s0.camRayAng.shape == (5,) and s0.rayAng.shape == (1182,)
+
+
+def test_point_filter_of_the_photoscan_demo():
+    """loadplotpsz.m:58-90 (ps_postproc's minRays / minAngle arguments): filtered points disappear with their
+    measurements, control points stay whatever their ray count."""
+    root = os.path.join(GOLD, 'prague2016sxb')
+    psz = ingest.loadpsz(os.path.join(root, 'psprojects', 'sxb.psz'))
+    prob = ingest.ps2pmstruct(psz)
+    s0 = ingest.prob2dbatstruct(prob)
+    rays = np.bincount(s0.IP.op, minlength=s0.OP.val.shape[1])
+    prob4, gone = ingest.filterprob(prob, s0, minRays=4)
+    s4 = ingest.prob2dbatstruct(prob4)
+    assert len(gone) == np.count_nonzero((rays < 4) & ~s0.prior.OP.isCtrl) > 0
+    assert s4.OP.val.shape[1] == s0.OP.val.shape[1] - len(gone) and s4.prior.OP.isCtrl.sum() == 16
+    r4 = np.bincount(s4.IP.op, minlength=s4.OP.val.shape[1])
+    assert r4[~s4.prior.OP.isCtrl].min() >= 4 and r4[s4.prior.OP.isCtrl].min() == 1
+    assert s4.IP.val.shape[1] == s0.IP.val.shape[1] - rays[np.isin(s0.OP.id, gone)].sum()
+    from dbat_b200.report import angles
+    probA, goneA = ingest.filterprob(prob, s0, minAngle=15.0)
+    sA = ingest.prob2dbatstruct(probA)
+    assert len(goneA) > 0 and np.rad2deg(angles(sA))[~sA.prior.OP.isCtrl].min() >= 15.0
+    same, none = ingest.filterprob(prob, s0)
+    assert len(none) == 0 and same.objPts.shape == prob.objPts.shape
