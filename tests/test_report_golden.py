@@ -349,12 +349,25 @@ def test_roma_script_result_file_reproduces_the_reference_report():
 
 def test_oracle_block_covariance_path_equals_the_dense_factor():
     """oracle/bundle.py: `bundle_cov(..., blocks=True)` (what large problems use) against the literal
-    dense restatement of bundle_cov.m, on a self-calibrating project and on one with prior OP observations
-    and partly fixed points."""
-    from oracle.bundle import bundle_cov as ocov
-    for run in (lambda: camcal_pm_run('camcal-pmexport.txt'),
+    dense restatement of bundle_cov.m, on a self-calibrating project, on one with single coordinates of some
+    points held fixed, and on one with prior OP observations."""
+    from oracle.bundle import bundle as obundle, bundle_cov as ocov
+
+    def partly_fixed_points():
+        from oracle.loaders import camcal_pm_struct
+        from oracle.photogrammetry import resect, forwintersect
+        G = os.path.join(GOLD, 'camcalpm')
+        s = camcal_pm_struct(os.path.join(G, 'camcal-pmexport.txt'), os.path.join(G, 'camcal-fixed.txt'))
+        cpId = np.asarray(s.OP.id)[s.prior.OP.isCtrl]
+        s = forwintersect(resect(s, 'all', cpId, 1, 0, cpId)[0], 'all', True)[0]
+        s.bundle.est.OP[2, 5:9] = False                        # z of four points fixed: 2 x 2 point blocks
+        s.bundle.est.OP[0:2, 20] = False                       # x, y of one point fixed: a 1 x 1 block
+        return obundle(s, 'gna')
+
+    for run in (lambda: camcal_pm_run('camcal-pmexport.txt'), partly_fixed_points,
                 lambda: prague_run(os.path.join(GOLD, 'prague2016sxb'), 'w-op1', 'ctrlpts-weighted.txt')):
         s, ok, it, s0, E = run()
+        assert ok
         dense = {w: np.asarray(ocov(s, E, w)) for w in ('CIOF', 'CEOF', 'CIO', 'CEO', 'COP')}
         E.final.factorized = None
         for w, D in dense.items():
