@@ -92,6 +92,16 @@ def _ctrl_pts(node, base, here):
 def _parse_input(inp, docFile):
     here = os.path.dirname(os.path.abspath(docFile))
     base = inp.get('base_dir', '').replace('$HERE', here)
+    known = {'ctrl_pts', 'check_pts', 'images', 'prior_eo', 'image_pts', 'cameras', 'c'}
+    unknown = [c.tag for c in inp if c.tag not in known]
+    missing = [t for t in ('images', 'image_pts', 'cameras') if inp.find(t) is None]
+    if unknown or missing:                                              # parseinput.m:24-28 (checkxmlfields)
+        raise ValueError('DBAT XML script input error: %s' % '; '.join(
+            (['unknown field(s) ' + ', '.join(unknown)] if unknown else []) +
+            (['missing field(s) ' + ', '.join(missing)] if missing else [])))
+    for t in ('images', 'image_pts', 'ctrl_pts', 'check_pts', 'prior_eo'):
+        if inp.find(t) is not None and inp.find(t).find('file') is None:
+            raise ValueError('DBAT XML input/%s error: missing file' % t)
     camsNode = inp.find('cameras')
     cams = [_camera(c) for c in camsNode.findall('camera')]
     for f in camsNode.findall('file'):

@@ -69,12 +69,19 @@ def test_script_errors_are_loud(tmp_path):
     with pytest.raises(ValueError):
         rundbatscript(str(bad), backend=oracle_backend())
     src = open(os.path.join(GOLD, 'camcaldemo', 'camcaldemo.xml')).read()
-    for old, new in (('<operation>spatial_resection</operation>', '<operation>levitate</operation>'),
-                     ('min_rays="2"', 'min_rays="30"')):
-        root = tmp_path / ('case%d' % len(new))
-        import shutil
+    import shutil
+    cases = ([('<operation>spatial_resection</operation>', '<operation>levitate</operation>')],   # unknown operation
+             [('min_rays="2"', 'min_rays="30"')],                                                  # ray count check
+             [('<image_pts>', '<image_points>'), ('</image_pts>', '</image_points>')],             # unknown / missing field
+             [('format="id,label,x,y,z"', 'format="id,label,x,y"')])                               # table / format mismatch
+    for n, edits in enumerate(cases):
+        root = tmp_path / ('case%d' % n)
         shutil.copytree(os.path.join(GOLD, 'camcaldemo'), root)
-        (root / 'camcaldemo.xml').write_text(src.replace(old, new))
+        txt = src
+        for old, new in edits:
+            assert old in txt
+            txt = txt.replace(old, new)
+        (root / 'camcaldemo.xml').write_text(txt)
         with pytest.raises(ValueError):
             rundbatscript(str(root / 'camcaldemo.xml'), backend=oracle_backend(), write=False)
 
