@@ -86,10 +86,15 @@ def main():
     dense_flops = (6.0 * nImg) ** 3 / 3
     out = {'project': name, 'images': nImg, 'observations': int(s.IP.val.shape[1]),
            'S_block_density': round(nnzb / nImg ** 2, 4), 'dense_cholesky_gflop': round(dense_flops / 1e9, 3)}
+    coo = G.tocoo()
     for label, perm in (('natural', np.arange(nImg)), ('rcm', np.asarray(reverse_cuthill_mckee(G.tocsr(), symmetric_mode=True))),
                         ('minimum_degree', minimum_degree(G))):
         cnt = symbolic_cholesky(G, perm)
-        out[label] = {'L_block_density': round(float((cnt.sum() + nImg) / (nImg * (nImg + 1) / 2)), 4),
+        inv = np.empty(nImg, np.int64)
+        inv[perm] = np.arange(nImg)
+        band = int(np.abs(inv[coo.row] - inv[coo.col]).max())
+        out[label] = {'bandwidth_blocks': band, 'band_cholesky_gflop': round(6.0 * nImg * (6.0 * band) ** 2 / 1e9, 3),
+                      'L_block_density': round(float((cnt.sum() + nImg) / (nImg * (nImg + 1) / 2)), 4),
                       'gflop': round(work(cnt) / 1e9, 3), 'vs_dense': round(work(cnt) / dense_flops, 4),
                       'largest_front_blocks': int(cnt.max())}
     print(json.dumps(out))
