@@ -65,3 +65,27 @@ def test_band_of_the_reduced_system_survives_only_with_the_io_block_last():
     # (3) x order (IO first, today's layout of S): the arrowhead fills the whole factor
     L0 = np.linalg.cholesky(S)
     assert np.count_nonzero(np.abs(L0) > 1e-13) > 0.98 * nC * (nC + 1) / 2
+
+
+def test_banded_tile_cholesky_prototype_equals_the_dense_factor():
+    """tools/band_cholesky_proto.py: the tile loop restricted to band + border tiles gives the dense factor
+    on a band-plus-border SPD matrix, with the predicted number of tile operations."""
+    from band_cholesky_proto import band_tile_cholesky, dense_counts
+    rng = np.random.default_rng(1)
+    NB, nb, bt, nborder = 8, 12, 3, 2
+    n = NB * nb
+    ne = nb - nborder
+    M = rng.standard_normal((n, n))
+    keep = np.zeros((nb, nb), bool)
+    for i in range(nb):
+        for j in range(nb):
+            keep[i, j] = abs(i - j) <= bt or i >= ne or j >= ne
+    M = M * np.kron(keep, np.ones((NB, NB)))
+    A = M @ M.T                                            # band 2*bt in tiles ... so use it as the pattern source
+    A = A * np.kron(keep, np.ones((NB, NB))) + n * np.eye(n)   # SPD, band bt + dense border
+    L, cnt = band_tile_cholesky(A, NB, bt, nborder)
+    np.testing.assert_allclose(L, np.linalg.cholesky(A), rtol=1e-10, atol=1e-12)
+    assert cnt['gemm_tiles'] < dense_counts(nb)['gemm_tiles'] and cnt['potrf'] == nb
+    # one tile less of band is not enough: the factor is then wrong
+    Lbad, _ = band_tile_cholesky(A, NB, bt - 1, nborder)
+    assert np.abs(Lbad - np.linalg.cholesky(A)).max() > 1e-6
