@@ -56,7 +56,7 @@ EXPORTS = ['dbat_create', 'dbat_destroy', 'dbat_last_error', 'dbat_num_unknowns'
            'dbat_num_residuals', 'dbat_eval', 'dbat_jacobian_nnz', 'dbat_jacobian_csc',
            'dbat_default_opts', 'dbat_solve', 'dbat_normal_step', 'dbat_cov',
            'dbat_comm_unique_id', 'dbat_comm_init', 'dbat_phase_times', 'dbat_dense_chol_solve',
-           'dbat_forwintersect', 'dbat_forwintersect_error', 'dbat_resect3']
+           'dbat_forwintersect', 'dbat_forwintersect_error', 'dbat_resect3', 'dbat_camera_order']
 
 _lib = None
 
@@ -124,6 +124,8 @@ def lib():
     L.dbat_forwintersect_error.restype = C.c_char_p
     L.dbat_resect3.argtypes = [C.POINTER(ResectDesc), c_dp, c_dp]
     L.dbat_resect3.restype = C.c_int
+    L.dbat_camera_order.argtypes = [C.c_int64, C.c_int64, C.c_int64, c_ip, c_ip, c_ip, C.POINTER(C.c_int64)]
+    L.dbat_camera_order.restype = C.c_int
     _lib = L
     return L
 
@@ -163,3 +165,15 @@ def dense_chol_solve(A, b, want_inverse=False, repeat=1):
     if rc != 0:
         raise DbatError(rc, lib().dbat_last_error(None).decode())
     return x, Ainv, ms.value
+
+
+def camera_order(img, op, nImg, nOP):
+    """Reverse Cuthill-McKee order of the images on the co-visibility graph (host code in the library):
+    returns (perm, bandwidth) with perm 0-based."""
+    img1, op1 = i64(np.asarray(img) + 1), i64(np.asarray(op) + 1)
+    perm = np.empty(nImg, dtype=np.int64)
+    bw = C.c_int64()
+    rc = lib().dbat_camera_order(nImg, nOP, len(img1), iptr(img1), iptr(op1), iptr(perm), C.byref(bw))
+    if rc != 0:
+        raise DbatError(rc, 'dbat_camera_order: bad argument')
+    return perm - 1, int(bw.value)

@@ -151,6 +151,16 @@ int dbat_normal_step(dbat_handle *h, const double *x, double lambda, int flags,
 /* Posterior covariances from the undamped factorisation at the current x, times s0^2. */
 int dbat_cov(dbat_handle *h, int which, double s0, double *out);
 
+/* Elimination order of the images for a banded factorisation of the reduced camera system (host only, no
+ * device needed): reverse Cuthill-McKee on the co-visibility graph - images i, j are adjacent when they
+ * observe a common object point, which is exactly when S has a non-zero 6x6 block (i, j).  obs_img / obs_op
+ * are 1-based as in dbat_problem_desc; perm (nImg, 1-based) lists the images in elimination order and
+ * *bandwidth (may be NULL) is the largest distance, in images, between two adjacent images under it.  The
+ * reference has no counterpart on its solver path (it factors the camera block densely, bundle_cov.m:97);
+ * its ordering experiments are private/blkcolperm.m and test/postcov/reorder_test.m. */
+int dbat_camera_order(int64_t nImg, int64_t nOP, int64_t nObs, const int64_t *obs_img,
+                      const int64_t *obs_op, int64_t *perm, int64_t *bandwidth);
+
 /* The dense solver on its own (unit tests / profiling): x = A^-1 b for a symmetric positive
  * definite column-major n x n matrix through the same blocked FP64 Cholesky the reduced camera
  * system uses; Ainv (n x n, may be NULL) receives the explicit inverse used by dbat_cov.

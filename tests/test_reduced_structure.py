@@ -89,3 +89,37 @@ def test_banded_tile_cholesky_prototype_equals_the_dense_factor():
     # one tile less of band is not enough: the factor is then wrong
     Lbad, _ = band_tile_cholesky(A, NB, bt - 1, nborder)
     assert np.abs(Lbad - np.linalg.cholesky(A)).max() > 1e-6
+
+
+def test_library_camera_order_is_a_valid_rcm_order():
+    """`dbat_camera_order` (host code in libdbatgpu.so, no device needed): a permutation whose bandwidth on
+    the co-visibility graph is reported correctly, is far below the natural one for a shuffled block and
+    comparable to SciPy's reverse Cuthill-McKee; isolated images and empty input are handled."""
+    from dbat_b200 import _lib
+    from dbat_b200.synth import make_scene
+    from reduced_sparsity import covisibility
+    s, _ = make_scene(196, 6000, rays=8, seed=5, build_indices=False)
+    nImg, nOP = s.EO.val.shape[1], s.OP.val.shape[1]
+    rng = np.random.default_rng(0)
+    shuffle = rng.permutation(nImg)                               # destroy the generator's strip order
+    img, op = shuffle[np.asarray(s.IP.img)], np.asarray(s.IP.op)
+    perm, bw = _lib.camera_order(img, op, nImg, nOP)
+    assert sorted(perm) == list(range(nImg))
+    G = covisibility(img, op, nImg).tocoo()
+    pos = np.empty(nImg, int)
+    pos[perm] = np.arange(nImg)
+    assert bw == np.abs(pos[G.row] - pos[G.col]).max()
+    natural = np.abs(G.row - G.col).max()
+    ref = np.asarray(reverse_cuthill_mckee(G.tocsr(), symmetric_mode=True))
+    rpos = np.empty(nImg, int)
+    rpos[ref] = np.arange(nImg)
+    scipy_bw = np.abs(rpos[G.row] - rpos[G.col]).max()
+    assert bw < 0.5 * natural and bw <= 1.3 * scipy_bw
+    # two images that see nothing in common with the rest, and no observations at all
+    perm2, bw2 = _lib.camera_order(np.array([0, 1, 0, 1]), np.array([0, 0, 1, 1]), 4, 2)
+    assert sorted(perm2) == [0, 1, 2, 3] and bw2 == 1
+    perm3, bw3 = _lib.camera_order(np.zeros(0, int), np.zeros(0, int), 3, 0)
+    assert sorted(perm3) == [0, 1, 2] and bw3 == 0
+    import pytest
+    with pytest.raises(_lib.DbatError):
+        _lib.camera_order(np.array([5]), np.array([0]), 3, 1)
