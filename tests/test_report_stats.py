@@ -113,3 +113,56 @@ def test_angles_and_coverage_on_a_toy_block():
     np.testing.assert_allclose(crr[0], np.hypot(40, 15) / np.hypot(50.5, 25.5))
     uc, ucr, ucrr = report.coverage(s, np.arange(3), True)
     np.testing.assert_allclose([uc, ucr], [80 * 30 / 5000, 80 * 30 / 5000])
+
+
+def test_result_file_branches_the_goldens_do_not_reach():
+    """A small synthetic project with a control point nobody observes, a labelled check point and an object
+    point seen in one image only: the report must come out (no exception) with the reference's wording for
+    those cases (`bundle_result_file.m:580-586,735-738,768-790`)."""
+    import copy
+    from dbat_b200.synth import make_scene
+    from oracle.bundle import bundle as obundle, bundle_cov as ocov
+    s, truth = make_scene(6, 40, rays=4, seed=11, build_indices=False)
+    nOP = s.OP.val.shape[1]
+    s.IO.val[:] = truth['IO'][:, None]
+    s.EO.val[:] = truth['EO']
+    s.OP.val[:] = truth['OP']
+    s.OP.id = np.arange(1, nOP + 1)
+    s.OP.label = [''] * nOP
+    s.EO.name = ['img%d.jpg' % i for i in range(6)]
+    s.proj = NS(title='toy', UUID='', fileName='', cptFile='', EOfile='', objUnit='m', x0desc='')
+    s.IO.model.camUnit = 'mm'
+    s.IP.sigmas = np.array([1.0])
+    s.bundle.est.IO[:] = False
+    s.prior.OP.isCtrl = np.zeros(nOP, bool)
+    s.prior.OP.isCheck = np.zeros(nOP, bool)
+    for j in range(5):                                            # five control points, fixed at the truth
+        s.prior.OP.isCtrl[j] = True
+        s.prior.OP.val[:, j] = truth['OP'][:, j]
+        s.prior.OP.std[:, j] = 0.0
+        s.bundle.est.OP[:, j] = False
+        s.OP.label[j] = 'CP%d' % j
+    drop = np.asarray(s.IP.op) == 4                               # control point 5 is never observed
+    lone = np.flatnonzero(np.asarray(s.IP.op) == 20)[1:]          # object point 21 keeps a single ray
+    keep = ~drop
+    keep[lone] = False
+    for k in ('val', 'std'):
+        setattr(s.IP, k, getattr(s.IP, k)[:, keep])
+    for k in ('img', 'op', 'cam'):
+        setattr(s.IP, k, np.asarray(getattr(s.IP, k))[keep])
+    s.bundle.est.OP[:, 20] = False                                # a one-ray point cannot be estimated
+    s.prior.OP.isCheck[7] = True                                  # a check point with a label
+    s.prior.OP.val[:, 7] = truth['OP'][:, 7] + 0.01
+    s.prior.OP.std[:, 7] = 0.02
+    s.OP.label[7] = 'CHK'
+    s, ok, it, s0, E = obundle(copy.deepcopy(s), 'gna')
+    assert ok
+    s, lines = report.bundle_result_file(s, E, None, cov=ocov)
+    text = '\n'.join(lines)
+    assert 'CP ray count: 1x0, ' in text and '1 points with 0 rays.' in text
+    assert 'Ignoring 1 CP with 0 rays.' in text
+    assert 'Number of check pts: 1' in text and 'Check point delta' in text and '(CHK, pt 8)' in text
+    assert 'CCP ray count: ' in text and ', label CHK)' in text
+    assert '1 points with 1 rays.' in text and lines[-1] == 'End of result file'
+    s, stats = report.writestats(s, None, 'toy')
+    assert any(l.startswith('CP with lowest ray count') for l in stats)
