@@ -94,3 +94,24 @@ def test_script_projects_on_the_device(name):
     s, E, lines = rundbatscript(os.path.join(root, name + '.xml'), write=False)
     assert E.code == 0
     assert report_diff(lines, os.path.join(root, 'result', 'report.txt'), rtol=1e-5, first_error_rtol=1e-3) == []
+
+
+def test_script_initial_value_fields(tmp_path):
+    """set_initial_values/io field by field (parsesetinitialiovalues.m): with cc = 7.3 written out, default
+    principal point and zero distortion, the camcal script becomes the PhotoModeler demo `camcaldemo.m`
+    (EXIF focal length 7.3 instead of the script's 7.5) up to the sensor width - the script derives it from the
+    pixel size ('auto'), the export states 7.25319 mm, which moves the default principal point by 1.5 um - and
+    lands on that demo's numbers: 9 iterations instead of the script's 8, first error 30873.9 to 0.05 %,
+    sigma0 1.6148."""
+    import shutil
+    root = tmp_path / 'camcaldemo'
+    shutil.copytree(os.path.join(GOLD, 'camcaldemo'), root)
+    src = open(root / 'camcaldemo.xml').read()
+    old = '<io>\n          <all>default</all>\n        </io>'
+    assert old in src
+    new = ('<io><all>default</all><cc>7.3</cc><pp>default</pp><K>0,0,0</K><P>default</P>'
+           '<aspect>1</aspect><skew>0</skew></io>')
+    (root / 'camcaldemo.xml').write_text(src.replace(old, new))
+    s, E, lines = rundbatscript(str(root / 'camcaldemo.xml'), backend=oracle_backend(), write=False)
+    assert E.code == 0 and E.usedIters == 9
+    assert abs(E.res[0] / 30873.9 - 1) < 5e-4 and abs(E.s0 - 1.6148) < 6e-5
