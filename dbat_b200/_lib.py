@@ -12,6 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('DBAT_LIB', os.path.join(_HERE, 'libdbatgpu.so'))   # DBAT_LIB: tuning builds
 
 METHOD = {'gm': 0, 'gna': 1, 'lm': 2, 'lmp': 3}
+E_NOTSPD = -105        # DBAT_E_NOTSPD (include/dbat_gpu.h)
 COV = {'cio': 1, 'ceo': 2, 'cop': 3, 'cxx_cam': 4, 'cxx': 5, 'cxx_op': 6}
 
 c_dp = C.POINTER(C.c_double)

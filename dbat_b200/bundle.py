@@ -210,8 +210,10 @@ class Problem:
             out = np.zeros((m3, m3))
         else:
             raise ValueError(which)
-        self._check(L.dbat_cov(self._h, _lib.COV[w], float(s0), _lib.dptr(out)))
-        if not np.isfinite(out).all():
+        rc = L.dbat_cov(self._h, _lib.COV[w], float(s0), _lib.dptr(out))
+        if rc != _lib.E_NOTSPD:          # a failed factorisation is an outcome (NaN deviations), not an API error
+            self._check(rc)
+        if rc == _lib.E_NOTSPD or not np.isfinite(out).all():
             # the factorisation broke down (singular or NaN normal matrix): the reference then reports NaN
             # for every estimated element (bundle_cov.m:101-107,136-160), not a partly finite matrix
             out[out != 0] = np.nan
