@@ -31,6 +31,7 @@ class ProblemDesc(C.Structure):
         ('OPdes_src', c_ip), ('OPdes_dest', c_ip), ('nOPdes', C.c_int64),
         ('nPriorIO', C.c_int64), ('nPriorEO', C.c_int64), ('nPriorOP', C.c_int64),
         ('prior_x', c_ip), ('prior_val', c_dp), ('prior_std', c_dp),
+        ('nCovis', C.c_int64), ('covis_a', c_ip), ('covis_b', c_ip),
     ]
 
 
@@ -57,7 +58,8 @@ EXPORTS = ['dbat_create', 'dbat_destroy', 'dbat_last_error', 'dbat_num_unknowns'
            'dbat_num_residuals', 'dbat_eval', 'dbat_jacobian_nnz', 'dbat_jacobian_csc',
            'dbat_default_opts', 'dbat_solve', 'dbat_normal_step', 'dbat_cov',
            'dbat_comm_unique_id', 'dbat_comm_init', 'dbat_phase_times', 'dbat_dense_chol_solve',
-           'dbat_forwintersect', 'dbat_forwintersect_error', 'dbat_resect3', 'dbat_camera_order']
+           'dbat_forwintersect', 'dbat_forwintersect_error', 'dbat_resect3', 'dbat_camera_order',
+           'dbat_tile_symbolic', 'dbat_tile_symbolic_get', 'dbat_tile_chol_solve']
 
 _lib = None
 
@@ -127,6 +129,13 @@ def lib():
     L.dbat_resect3.restype = C.c_int
     L.dbat_camera_order.argtypes = [C.c_int64, C.c_int64, C.c_int64, c_ip, c_ip, c_ip, C.POINTER(C.c_int64)]
     L.dbat_camera_order.restype = C.c_int
+    L.dbat_tile_symbolic.argtypes = [C.c_int64, C.c_int64, C.c_int64, c_ip, c_ip, c_ip, C.c_int64, C.c_int64,
+                                     C.c_int64, c_ip]
+    L.dbat_tile_symbolic.restype = C.c_int
+    L.dbat_tile_symbolic_get.argtypes = [c_ip] * 8
+    L.dbat_tile_symbolic_get.restype = C.c_int
+    L.dbat_tile_chol_solve.argtypes = [C.c_int64, c_dp, c_dp, c_dp, C.c_int64, C.c_int64, C.c_int, c_dp]
+    L.dbat_tile_chol_solve.restype = C.c_int
     _lib = L
     return L
 
@@ -178,3 +187,40 @@ def camera_order(img, op, nImg, nOP):
     if rc != 0:
         raise DbatError(rc, 'dbat_camera_order: bad argument')
     return perm - 1, int(bw.value)
+
+
+def tile_symbolic(img, op, nImg, nOP, nEO, nIO, mode=-1, leaf=120):
+    """Symbolic analysis of the reduced camera system (host code in the library): dict of counts + arrays."""
+    img1, op1, ne = i64(np.asarray(img) + 1), i64(np.asarray(op) + 1), i64(nEO)
+    cnt = np.zeros(16, dtype=np.int64)
+    rc = lib().dbat_tile_symbolic(nImg, nOP, len(img1), iptr(img1), iptr(op1), iptr(ne), nIO, mode, leaf, iptr(cnt))
+    if rc != 0:
+        raise DbatError(rc, 'dbat_tile_symbolic: bad argument')
+    names = ['nT', 'ld', 'nS', 'nSlots', 'nSlotsS', 'nTasks', 'nTerms', 'depth', 'mode', 'nSeg', 'ioS']
+    out = {k: int(cnt[i]) for i, k in enumerate(names)}
+    nT = out['nT']
+    arr = dict(imgS=np.empty(nImg, np.int64), tix=np.empty(nT * nT, np.int64), taskIJ=np.empty(2 * out['nTasks'], np.int64),
+               termPtr=np.empty(out['nTasks'] + 1, np.int64), termAB=np.empty(max(1, 2 * out['nTerms']), np.int64),
+               level=np.empty(nT, np.int64), s2kind=np.empty(out['ld'], np.int64), bwdCols=np.empty(nT, np.int64))
+    lib().dbat_tile_symbolic_get(*[iptr(arr[k]) for k in ('imgS', 'tix', 'taskIJ', 'termPtr', 'termAB', 'level', 's2kind', 'bwdCols')])
+    out.update(arr)
+    out['tix'] = out['tix'].reshape(nT, nT)
+    out['taskIJ'] = out['taskIJ'].reshape(-1, 2)
+    out['termAB'] = out['termAB'][:2 * out['nTerms']].reshape(-1, 2)
+    return out
+
+
+def tile_chol_solve(A, b, mode=-1, leaf=120, repeat=1):
+    """x = A^-1 b through the sparse tile Cholesky on the device; returns (x, stats dict)."""
+    A = np.asfortranarray(np.asarray(A, dtype=np.float64))
+    n = A.shape[0]
+    b = f64(b)
+    x = np.empty(n)
+    st = np.zeros(8)
+    rc = lib().dbat_tile_chol_solve(n, A.ctypes.data_as(c_dp), dptr(b), dptr(x), mode, leaf, repeat, dptr(st))
+    if rc not in (0, E_NOTSPD):
+        raise DbatError(rc, lib().dbat_last_error(None).decode())
+    names = ['ms', 'nT', 'nSlots', 'nTasks', 'nTerms', 'depth', 'min_pivot', 'max_pivot']
+    d = {k: float(st[i]) for i, k in enumerate(names)}
+    d['rc'] = rc
+    return x, d

@@ -21,6 +21,13 @@ from .dbatstruct import (buildserialindices, buildweightmatrix, column_matching,
 _lin = lambda a: np.asarray(a).reshape(-1, order='F')
 
 
+def covisibility_edges(img, op, nImg, nOP):
+    """Pairs (a < b) of images that observe a common object point: the block pattern of the reduced camera system."""
+    A = sp.csr_matrix((np.ones(len(img), dtype=np.int32), (np.asarray(op), np.asarray(img))), shape=(nOP, nImg))
+    G = sp.triu((A.T @ A).tocsr(), 1).tocoo()
+    return G.row.astype(np.int64), G.col.astype(np.int64)
+
+
 class Problem:
     """Device-resident bundle problem: stands in for the closure `@(x)brown_euler_cam4(x,s)`.
 
@@ -89,6 +96,14 @@ class Problem:
         put('prior_x', np.concatenate(px), 'i')
         put('prior_val', np.concatenate(pv), 'd')
         put('prior_std', np.concatenate(ps), 'd')
+        d.nCovis = 0
+        if points is not None:
+            # every rank must order and tile the reduced camera system identically: hand the library the
+            # co-visibility graph of the whole project, not only of this shard's points
+            ca, cb = covisibility_edges(s.IP.img, s.IP.op, nImg, nOP)
+            put('covis_a', ca + 1, 'i')
+            put('covis_b', cb + 1, 'i')
+            d.nCovis = len(ca)
         h = C.c_void_p()
         rc = L.dbat_create(C.byref(d), C.byref(h))
         if rc != 0:

@@ -17,6 +17,7 @@
 #include "../../include/dbat_gpu.h"
 #include "kernels.cuh"
 #include "launch.h"
+#include "tilechol.h"
 
 int64_t g_dbat_launches = 0;
 static std::string g_create_err;
@@ -84,7 +85,9 @@ struct dbat_handle {
     double *d_x = nullptr, *d_t = nullptr, *d_p = nullptr, *d_pgn = nullptr, *d_g = nullptr, *d_pc = nullptr;
     double *d_camDiag = nullptr, *d_camG = nullptr, *d_diagN = nullptr, *d_dscale = nullptr;
     double *d_r = nullptr;              // m doubles (export)
-    CholWork chol;
+    TChol tc;                           // sparse tile Cholesky of the reduced system (tilechol.cu)
+    std::vector<int> h_x2s;             // x column (camera side) -> S index
+    double* d_dS = nullptr;             // Jacobi scale per S index
     bool params_valid = false;          // parameter arrays correspond to d_x
     bool normal_valid = false;          // Gram / point records correspond to d_x
     // comm
@@ -358,13 +361,57 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     { auto v = to_int(d->OPdes_src, d->nOPdes, false); UP(h->d_OPsrc, v); }
     { auto v = to_int(d->OPdes_dest, d->nOPdes, true); UP(h->d_OPdst, v); }
     UP(h->d_img_chunk_start, img_chunk_start); UP(h->d_col2pt, col2pt);
-    P.ldS = std::max(128, ((nC + 1 + 127) / 128) * 128);   // >= 1 padding row: carries the rhs (chol_put_rhs)
+    {   // ---- reduced system: elimination order of the images, tile pattern, symbolic factorisation
+        std::vector<int64_t> adjPtr; std::vector<int32_t> adj;
+        covis_graph(nImg, nOP, h->h_pt_start.data(), img_pm.data(), adjPtr, adj);
+        if (d->nCovis > 0 && d->covis_a && d->covis_b) {      // the whole project's graph (sharded problems)
+            std::vector<std::vector<int32_t>> nb(nImg);
+            for (int i = 0; i < nImg; ++i) nb[i].assign(adj.begin() + adjPtr[i], adj.begin() + adjPtr[i + 1]);
+            for (int64_t e = 0; e < d->nCovis; ++e) {
+                const int64_t a = d->covis_a[e] - 1, b = d->covis_b[e] - 1;
+                if (a < 0 || a >= nImg || b < 0 || b >= nImg) return fail_create(h, DBAT_E_BADARG, "covis edge out of range");
+                if (a == b) continue;
+                nb[a].push_back((int32_t)b); nb[b].push_back((int32_t)a);
+            }
+            adj.clear();
+            for (int i = 0; i < nImg; ++i) {
+                std::sort(nb[i].begin(), nb[i].end());
+                nb[i].erase(std::unique(nb[i].begin(), nb[i].end()), nb[i].end());
+                adjPtr[i] = (int64_t)adj.size();
+                adj.insert(adj.end(), nb[i].begin(), nb[i].end());
+            }
+            adjPtr[nImg] = (int64_t)adj.size();
+        }
+        std::vector<int> nEO(nImg, 0);
+        for (int i = 0; i < nImg; ++i) for (int a = 0; a < 6; ++a) if (colEO[(size_t)i * 6 + a] >= 0) nEO[i]++;
+        int nIO = 0;
+        for (int sl = 0; sl < DBAT_NSLOT; ++sl) if (h->h_sh_col[sl] >= 0) nIO++;
+        TileSym sym;
+        if (tile_symbolic(nImg, adjPtr.data(), adj.data(), nEO.data(), nIO, -1, 120, sym))
+            return fail_create(h, DBAT_E_BADARG, "symbolic analysis of the reduced system failed");
+        std::vector<int> sh_s(DBAT_NSLOT, -1), eo_s((size_t)6 * nImg, -1), s2x(sym.ld, -1);
+        h->h_x2s.assign(std::max(1, nC), -1);
+        int k = 0;
+        for (int sl = 0; sl < DBAT_NSLOT; ++sl) if (h->h_sh_col[sl] >= 0) sh_s[sl] = sym.ioS + k++;
+        for (int i = 0; i < nImg; ++i) {
+            int q = 0;
+            for (int a = 0; a < 6; ++a) if (colEO[(size_t)i * 6 + a] >= 0) eo_s[(size_t)i * 6 + a] = sym.imgS[i] + q++;
+        }
+        for (int sl = 0; sl < DBAT_NSLOT; ++sl) if (sh_s[sl] >= 0) { s2x[sh_s[sl]] = h->h_sh_col[sl]; h->h_x2s[h->h_sh_col[sl]] = sh_s[sl]; }
+        for (size_t e = 0; e < eo_s.size(); ++e) if (eo_s[e] >= 0) { s2x[eo_s[e]] = colEO[e]; h->h_x2s[colEO[e]] = eo_s[e]; }
+        if (tchol_alloc(h->tc, sym)) return fail_create(h, DBAT_E_OOM, "out of memory for the reduced system");
+        int *d_shs, *d_eos, *d_s2x;
+        UP(d_shs, sh_s); UP(d_eos, eo_s); UP(d_s2x, s2x);
+        P.sh_s = d_shs; P.eo_s = d_eos; P.s2x = d_s2x; P.T = h->tc.d;
+        P.ldS = sym.ld;
+        AL(h->d_dS, sym.ld);
+    }
+    const std::vector<int>& imgRank = h->tc.sym.imgRank;
     AL(P.chunkG, (size_t)std::max(1, P.nChunks) * DBAT_GSZ);
     AL(P.imgG, (size_t)nImg * DBAT_GSZ);
     AL(P.shG, DBAT_GSZ);
     AL(P.pt, (size_t)std::max(1, nOP) * DBAT_PT_STRIDE);
     AL(P.W, (size_t)std::max(1, nObs) * DBAT_W_STRIDE);
-    AL(P.S, (size_t)P.ldS * P.ldS);
     AL(P.rhs, P.ldS);
     {   // deterministic Schur index: inverse permutation, point of every pm observation, pair blocks
         std::vector<int> cm2pm(nObs), pt_pm(nObs);
@@ -398,7 +445,14 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
             (k <= maxm ? cand : big).push_back(j);
         }
         const int* ps = h->h_pt_start.data();
-        const int* im = img_pm.data();
+        // image lists in elimination-order rank (ascending inside a point): the union of a group is then
+        // ascending in S order, which the tile pairs of k_schur_group rely on
+        std::vector<int> rk(std::max(1, nObs));
+        for (int j = 0; j < nOP; ++j) {
+            for (int o = ps[j]; o < ps[j + 1]; ++o) rk[o] = imgRank[img_pm[o]];
+            std::sort(rk.begin() + ps[j], rk.begin() + ps[j + 1]);
+        }
+        const int* im = rk.data();
         // lexicographic order of the (ascending) image lists: points with similar lists become neighbours
         std::sort(cand.begin(), cand.end(), [&](int a, int b) {
             const int ka = ps[a + 1] - ps[a], kb = ps[b + 1] - ps[b];
@@ -419,9 +473,9 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
             for (size_t i = gstart.back(); i < end; ++i) {
                 const int j = cand[i];
                 for (int o = ps[j]; o < ps[j + 1]; ++o)
-                    slot[o] = (unsigned char)(std::lower_bound(uni.begin(), uni.end(), im[o]) - uni.begin());
+                    slot[o] = (unsigned char)(std::lower_bound(uni.begin(), uni.end(), imgRank[img_pm[o]]) - uni.begin());
             }
-            gimg.insert(gimg.end(), uni.begin(), uni.end());
+            for (int r : uni) gimg.push_back(h->tc.sym.imgOrder[r]);
             gimg_off.push_back((int)gimg.size());
             gstart.push_back((int)end);
             P.grpMaxRays = std::max(P.grpMaxRays, (int)uni.size());
@@ -463,7 +517,6 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     AL(h->d_r, h->m);
     if (cudaMallocHost((void**)&h->h_scal, sizeof(double) * SC_N) != cudaSuccess)
         return fail_create(h, DBAT_E_OOM, "cudaMallocHost failed");
-    chol_alloc(h->chol, nC, P.ldS);
     h->ev.resize(4096);
     for (auto& e : h->ev) cudaEventCreate(&e);
     cudaMemset(h->d_p, 0, sizeof(double) * P.n);
@@ -477,7 +530,7 @@ extern "C" void dbat_destroy(dbat_handle* h) {
     if (h->st) cudaStreamSynchronize(h->st);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_scal) cudaFreeHost(h->h_scal);
-    chol_free(h->chol);
+    tchol_free(h->tc);
     for (auto& e : h->ev) cudaEventDestroy(e);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
     if (h->st) cudaStreamDestroy(h->st);
@@ -593,67 +646,51 @@ static int dev_dot(dbat_handle* h, const double* a, const double* b, int n, doub
     return 0;
 }
 
-// Lower block-trapezoids of S (block column c: rows 128c..ld-1 of its 128 columns) <-> one contiguous
-// buffer of 8192 nb (nb+1) doubles: the multi-rank allreduce then moves half of the ld x ld square.
-__global__ void k_pack_lower(double* __restrict__ S, int ld, double* __restrict__ buf, int unpack) {
-    const int col = blockIdx.y, c = col >> 7;
-    const size_t off = (size_t)128 * c * ld - (size_t)8192 * c * (c - 1) + (size_t)(col - 128 * c) * (ld - 128 * c);
-    const int r0 = 128 * c;
-    for (int r = r0 + blockIdx.x * blockDim.x + threadIdx.x; r < ld; r += gridDim.x * blockDim.x) {
-        if (unpack) S[(size_t)col * ld + r] = buf[off + r - r0];
-        else buf[off + r - r0] = S[(size_t)col * ld + r];
-    }
-}
-
 // Solve the (damped, optionally Jacobi-scaled) normal equations at d_x -> step in `pout`.
 // singular: 1 if the reduced system was not positive definite / numerically singular.
 static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, int* singular) {
     DevProblem& P = h->P;
+    TChol& tc = h->tc;
     size_t a = ph_begin(h);
     launch_build_S(P, h->d_camDiag, h->d_camG, lambda, h->st);
     if (h->nranks > 1 && h->rank != 0) {
         // only rank 0 contributes N_cc + lambda*I and -g_c; the others add their Schur terms to zero
-        cudaMemsetAsync(P.S, 0, sizeof(double) * (size_t)P.ldS * P.ldS, h->st);
+        tchol_zero(tc, h->st);
         cudaMemsetAsync(P.rhs, 0, sizeof(double) * P.ldS, h->st);
     }
     launch_schur(P, lambda, h->st);
     if (h->nranks > 1) {
-        const size_t nbk = (size_t)P.ldS / 128, cnt = 8192 * nbk * (nbk + 1);
-        if (!h->d_pack) {
-            if (cudaMalloc(&h->d_pack, sizeof(double) * cnt) != cudaSuccess) { h->err = "out of memory for the allreduce buffer"; return DBAT_E_OOM; }
-            h->allocs.push_back(h->d_pack);
-        }
-        const dim3 grid((unsigned)std::min<size_t>(8, (P.ldS + 255) / 256), (unsigned)P.ldS);
-        k_pack_lower<<<grid, 256, 0, h->st>>>(P.S, P.ldS, h->d_pack, 0);
-        int rc = allreduce(h, h->d_pack, cnt);
-        k_pack_lower<<<grid, 256, 0, h->st>>>(P.S, P.ldS, h->d_pack, 1);
-        count_launch(2);
+        // the tiles of the pattern of S are one contiguous array: no packing
+        int rc = allreduce(h, tc.d.tiles, (size_t)tc.d.nSlotsS * TC_TT);
         if (!rc) rc = allreduce(h, P.rhs, P.ldS);
         if (rc) return rc;
     }
     if (jacobi) {
         launch_diag(P, h->d_camDiag, h->d_diagN, h->st);
         launch_inv_sqrt(h->d_diagN, h->d_dscale, P.nC, h->st);
-        launch_scale_S(P, h->d_dscale, h->st);
+        launch_scale_prep(P, h->d_dscale, h->d_dS, h->st);
+        tchol_scale(tc, h->d_dS, h->st);
     }
     ph_end(h, PH_SCHUR, a);
     a = ph_begin(h);
-    chol_put_rhs(h->chol, P.S, P.rhs, h->st);
-    chol_factor(h->chol, P.S, h->st);
+    tchol_put_rhs(tc, P.rhs, h->st);
+    tchol_factor(tc, h->st);
     ph_end(h, PH_CHOL, a);
     a = ph_begin(h);
-    chol_solve(h->chol, P.S, h->d_pc, h->st);
-    if (jacobi) launch_mul(h->d_pc, h->d_dscale, h->d_pc, P.nC, h->st);
+    tchol_solve(tc, h->st);
+    launch_unpermute(P, tc.xs, jacobi ? h->d_dscale : nullptr, h->d_pc, h->st);
     launch_backsub(P, lambda, h->d_pc, pout, h->st);
-    int info = 0; double mm[2] = {1, 1};
-    cudaMemcpyAsync(&info, h->chol.info, sizeof(int), cudaMemcpyDeviceToHost, h->st);
-    cudaMemcpyAsync(mm, h->chol.minmax, 2 * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    int info = 0; unsigned long long mmb[2] = {0, 0};
+    cudaMemcpyAsync(&info, tc.d.info, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+    cudaMemcpyAsync(mmb, tc.d.minmax, sizeof(mmb), cudaMemcpyDeviceToHost, h->st);
     ph_end(h, PH_SOLVE, a);
     cudaError_t e = cudaStreamSynchronize(h->st);
     if (e != cudaSuccess) { h->err = std::string("solve_step: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
     // MATLAB's mldivide warns (singularMatrix / nearlySingularMatrix) when rcond < eps; with the
     // Cholesky factor rcond ~ (min pivot / max pivot)^2.
-    const double ratio = mm[1] > 0 ? mm[0] / mm[1] : 0.0;
+    double mm[2];
+    memcpy(mm, mmb, sizeof(mm));
+    const double ratio = mm[1] > 0 ? mm[0] / mm[1] : 1.0;      // no camera-side unknown at all: nothing to be singular
     *singular = (info != 0) || !(ratio * ratio > 2.220446049250313e-16);
     return 0;
 }
@@ -1189,11 +1226,11 @@ __global__ void k_cov_rows(DevProblem P, double* __restrict__ T, int* __restrict
     const double Vi[6] = {v[0], v[1], v[2], v[3], v[4], v[5]};
     for (int a = 0; a < DBAT_NSLOT + 6 * k; ++a) {
         const double* w; int col;
-        if (a < DBAT_NSLOT) { w = rec + DBAT_PT_WSH + 3 * a; col = P.sh_col[a]; }
+        if (a < DBAT_NSLOT) { w = rec + DBAT_PT_WSH + 3 * a; col = P.sh_s[a]; }
         else {
             const int o = (a - DBAT_NSLOT) / 6, e = (a - DBAT_NSLOT) % 6;
             w = P.W + (size_t)(o0 + o) * DBAT_W_STRIDE + 3 * e;
-            col = P.eo_col[6 * (size_t)P.img_pm[o0 + o] + e];
+            col = P.eo_s[6 * (size_t)P.img_pm[o0 + o] + e];
         }
         double* t = T + 3 * (r0 + a);
         t[0] = Vi[0] * w[0] + Vi[1] * w[1] + Vi[2] * w[2];
@@ -1202,10 +1239,13 @@ __global__ void k_cov_rows(DevProblem P, double* __restrict__ T, int* __restrict
         Tc[r0 + a] = col;
     }
 }
+// C and dsc are in S order (Tc holds S indices); U is indexed by x columns
 __global__ void k_cov_U(DevProblem P, const double* __restrict__ C, int ldc, const double* __restrict__ dsc,
-                        const double* __restrict__ T, const int* __restrict__ Tc, double* __restrict__ U) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
-    if (r >= P.nC) return;
+                        const double* __restrict__ T, const int* __restrict__ Tc, const int* __restrict__ x2s,
+                        double* __restrict__ U) {
+    const int rx = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (rx >= P.nC) return;
+    const int r = x2s[rx];
     const int* opc = P.op_col + 3 * (size_t)j;
     if (opc[0] < 0 && opc[1] < 0 && opc[2] < 0) return;
     const size_t r0 = (size_t)DBAT_NSLOT * j + 6 * (size_t)P.pt_start[j];
@@ -1219,7 +1259,7 @@ __global__ void k_cov_U(DevProblem P, const double* __restrict__ C, int ldc, con
         const double* t = T + 3 * (r0 + a);
         u[0] += c * t[0]; u[1] += c * t[1]; u[2] += c * t[2];
     }
-    for (int t = 0; t < 3; ++t) if (opc[t] >= 0) U[(size_t)(opc[t] - P.nC) * P.nC + r] = u[t];
+    for (int t = 0; t < 3; ++t) if (opc[t] >= 0) U[(size_t)(opc[t] - P.nC) * P.nC + rx] = u[t];
 }
 __global__ void k_cov_pp(DevProblem P, const double* __restrict__ T, const int* __restrict__ Tc,
                          const double* __restrict__ U, const int* __restrict__ col2pt, double* __restrict__ Cpp) {
@@ -1235,7 +1275,7 @@ __global__ void k_cov_pp(DevProblem P, const double* __restrict__ T, const int* 
     for (int a = 0; a < rows; ++a) {
         const int ca = Tc[r0 + a];
         if (ca < 0) continue;
-        const double u = Uc[ca];
+        const double u = Uc[P.s2x[ca]];
         const double* t = T + 3 * (r0 + a);
         acc[0] += t[0] * u; acc[1] += t[1] * u; acc[2] += t[2] * u;
     }
@@ -1249,32 +1289,77 @@ __global__ void k_cov_pp(DevProblem P, const double* __restrict__ T, const int* 
     for (int t = 0; t < 3; ++t) if (opc[t] >= 0) Cpp[(size_t)xc * m3 + (opc[t] - P.nC)] = acc[t];
 }
 
+__global__ void k_dense_unit_diag(double* __restrict__ A, int ld, int from) {
+    const int k = from + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < ld) A[(size_t)k * ld + k] = 1.0;
+}
+// undamped point blocks: numerically singular (relative pivot below 1e-13) -> *bad = 1
+__global__ void k_point_pd_check(DevProblem P, int* __restrict__ bad) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.nOP) return;
+    const int* opc = P.op_col + 3 * (size_t)j;
+    const bool f0 = opc[0] >= 0, f1 = opc[1] >= 0, f2 = opc[2] >= 0;
+    if (!f0 && !f1 && !f2) return;
+    const double* rec = P.pt + (size_t)j * DBAT_PT_STRIDE;
+    const double a00 = f0 ? rec[0] : 1.0, a11 = f1 ? rec[3] : 1.0, a22 = f2 ? rec[5] : 1.0;
+    const double a01 = (f0 && f1) ? rec[1] : 0.0, a02 = (f0 && f2) ? rec[2] : 0.0, a12 = (f1 && f2) ? rec[4] : 0.0;
+    const double tol = 1e-13;
+    bool ok = a00 > 0.0;
+    const double l10 = a01 / sqrt(a00), l20 = a02 / sqrt(a00);
+    const double d1 = a11 - l10 * l10;
+    ok = ok && d1 > tol * a11;
+    const double l21 = (a12 - l20 * l10) / sqrt(d1);
+    const double d2 = a22 - l20 * l20 - l21 * l21;
+    ok = ok && d2 > tol * a22;
+    if (!ok) *bad = 1;
+}
+
 extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
     if (!h || !out) return DBAT_E_BADARG;
     if (h->nranks > 1) { h->err = "dbat_cov is single-rank only"; return DBAT_E_UNSUPPORTED; }
     DevProblem& P = h->P;
     int rc;
     if (!h->normal_valid) { if ((rc = eval_full(h))) return rc; }
-    // undamped, Jacobi-scaled reduced system -> factor -> explicit inverse
+    // undamped, Jacobi-scaled reduced system (tiles, S order) -> dense copy -> dense factor -> explicit
+    // inverse.  The dense path (chol.cu) is kept for the covariances: inv(S) is a full matrix.
     launch_build_S(P, h->d_camDiag, h->d_camG, 0.0, h->st);
     launch_schur(P, 0.0, h->st);
     launch_diag(P, h->d_camDiag, h->d_diagN, h->st);
     launch_inv_sqrt(h->d_diagN, h->d_dscale, P.nC, h->st);
-    launch_scale_S(P, h->d_dscale, h->st);
-    chol_factor(h->chol, P.S, h->st);
-    double *Z = nullptr, *C = nullptr;
-    const size_t sz = sizeof(double) * (size_t)P.ldS * P.ldS;
-    if (cudaMalloc(&Z, sz) != cudaSuccess || cudaMalloc(&C, sz) != cudaSuccess) {
-        if (Z) cudaFree(Z);
+    launch_scale_prep(P, h->d_dscale, h->d_dS, h->st);
+    tchol_scale(h->tc, h->d_dS, h->st);
+    const int ldd = (P.ldS + 127) / 128 * 128;
+    double *Sd = nullptr, *Z = nullptr, *C = nullptr;
+    const size_t sz = sizeof(double) * (size_t)ldd * ldd;
+    int* d_bad = nullptr;
+    if (cudaMalloc(&Sd, sz) != cudaSuccess || cudaMalloc(&Z, sz) != cudaSuccess || cudaMalloc(&C, sz) != cudaSuccess ||
+        cudaMalloc(&d_bad, sizeof(int)) != cudaSuccess) {
+        cudaFree(Sd); cudaFree(Z); cudaFree(C); cudaFree(d_bad);
         h->err = "out of memory for the covariance workspace"; return DBAT_E_OOM;
     }
-    chol_inverse(h->chol, P.S, Z, C, h->st);
-    int info = 0;
-    cudaMemcpyAsync(&info, h->chol.info, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+    cudaMemsetAsync(Sd, 0, sz, h->st);
+    cudaMemsetAsync(d_bad, 0, sizeof(int), h->st);
+    tchol_to_dense(h->tc, Sd, ldd, h->st);
+    k_dense_unit_diag<<<(ldd + 255) / 256, 256, 0, h->st>>>(Sd, ldd, P.ldS - 1);      // rhs row position and padding
+    // a point block that is not positive definite (a point with a single ray) makes the reference's
+    // factorisation of the full normal matrix fail (bundle_cov.m:87-107): report that, not huge numbers
+    if (P.nOP > 0) k_point_pd_check<<<(P.nOP + 255) / 256, 256, 0, h->st>>>(P, d_bad);
+    count_launch(2);
+    CholWork cw;
+    chol_alloc(cw, P.ldS - 1, ldd);
+    chol_factor(cw, Sd, h->st);
+    chol_inverse(cw, Sd, Z, C, h->st);
+    int info = 0, badPts = 0;
+    cudaMemcpyAsync(&info, cw.info, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+    cudaMemcpyAsync(&badPts, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->st);
     cudaError_t e = cudaStreamSynchronize(h->st);
+    chol_free(cw);
+    cudaFree(Sd); cudaFree(d_bad);
     if (e != cudaSuccess) { cudaFree(Z); cudaFree(C); h->err = std::string("dbat_cov: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
+    if (badPts) info = -1;
     const double s02 = s0 * s0;
-    const int nC = P.nC, ld = P.ldS;
+    const int nC = P.nC, ld = ldd;
+    const std::vector<int>& x2s = h->h_x2s;
     if (which == DBAT_COV_CXX || which == DBAT_COV_CXX_OP) {
         const int m3 = P.n - nC;
         const size_t limit = (size_t)1 << 28;                 // 2 GB of doubles per dense block
@@ -1284,10 +1369,12 @@ extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
             return DBAT_E_UNSUPPORTED;
         }
         const size_t nRows = (size_t)DBAT_NSLOT * P.nOP + 6 * (size_t)P.nObs;
-        double *T = nullptr, *U = nullptr, *Cpp = nullptr; int* Tc = nullptr;
-        if (cudaMalloc(&T, sizeof(double) * 3 * std::max<size_t>(1, nRows)) || cudaMalloc(&Tc, sizeof(int) * std::max<size_t>(1, nRows)) ||
+        double *T = nullptr, *U = nullptr, *Cpp = nullptr; int *Tc = nullptr, *d_x2s = nullptr;
+        if (cudaMalloc(&d_x2s, sizeof(int) * x2s.size()) ||
+            cudaMemcpy(d_x2s, x2s.data(), sizeof(int) * x2s.size(), cudaMemcpyHostToDevice) ||
+            cudaMalloc(&T, sizeof(double) * 3 * std::max<size_t>(1, nRows)) || cudaMalloc(&Tc, sizeof(int) * std::max<size_t>(1, nRows)) ||
             cudaMalloc(&U, sizeof(double) * std::max<size_t>(1, (size_t)nC * m3)) || cudaMalloc(&Cpp, sizeof(double) * std::max<size_t>(1, (size_t)m3 * m3))) {
-            cudaFree(T); cudaFree(Tc); cudaFree(U); cudaFree(Cpp); cudaFree(Z); cudaFree(C);
+            cudaFree(d_x2s); cudaFree(T); cudaFree(Tc); cudaFree(U); cudaFree(Cpp); cudaFree(Z); cudaFree(C);
             h->err = "out of memory for the point covariance"; return DBAT_E_OOM;
         }
         cudaMemsetAsync(U, 0, sizeof(double) * std::max<size_t>(1, (size_t)nC * m3), h->st);
@@ -1295,7 +1382,7 @@ extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
         if (P.nOP > 0 && m3 > 0) {
             launch_point_vinv(P, 0.0, h->st);
             k_cov_rows<<<(P.nOP + 127) / 128, 128, 0, h->st>>>(P, T, Tc);
-            k_cov_U<<<dim3((nC + 127) / 128, P.nOP), 128, 0, h->st>>>(P, C, ld, h->d_dscale, T, Tc, U);
+            k_cov_U<<<dim3((nC + 127) / 128, P.nOP), 128, 0, h->st>>>(P, C, ld, h->d_dS, T, Tc, d_x2s, U);
             k_cov_pp<<<dim3((m3 + 127) / 128, P.nOP), 128, 0, h->st>>>(P, T, Tc, U, h->d_col2pt, Cpp);
             count_launch(3);
         }
@@ -1308,7 +1395,7 @@ extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
             cudaMemcpyAsync(dsc.data(), h->d_dscale, sizeof(double) * nC, cudaMemcpyDeviceToHost, h->st);
         }
         e = cudaStreamSynchronize(h->st);
-        cudaFree(T); cudaFree(Tc); cudaFree(U); cudaFree(Cpp);
+        cudaFree(d_x2s); cudaFree(T); cudaFree(Tc); cudaFree(U); cudaFree(Cpp);
         const double nanv = NAN;
         if (which == DBAT_COV_CXX_OP) {
             for (size_t k = 0; k < hpp.size(); ++k) out[k] = info != 0 ? nanv : s02 * hpp[k];
@@ -1317,7 +1404,7 @@ extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
             for (size_t b = 0; b < n; ++b)
                 for (size_t a = 0; a < n; ++a) {
                     double v;
-                    if (a < (size_t)nC && b < (size_t)nC) v = hc[b * ld + a] * dsc[a] * dsc[b];
+                    if (a < (size_t)nC && b < (size_t)nC) v = hc[(size_t)x2s[b] * ld + x2s[a]] * dsc[a] * dsc[b];
                     else if (a < (size_t)nC) v = -hu[(b - nC) * nC + a];
                     else if (b < (size_t)nC) v = -hu[(a - nC) * nC + b];
                     else v = hpp[(b - nC) * m3 + (a - nC)];
@@ -1328,7 +1415,7 @@ extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
         double* dOut = nullptr;
         cudaMalloc(&dOut, sizeof(double) * 9 * (size_t)std::max(1, P.nOP));
         cudaMemsetAsync(dOut, 0, sizeof(double) * 9 * (size_t)std::max(1, P.nOP), h->st);
-        if (P.nOP > 0) { k_cop<<<(P.nOP + 3) / 4, 128, 0, h->st>>>(P, C, ld, h->d_dscale, s02, dOut); count_launch(); }
+        if (P.nOP > 0) { k_cop<<<(P.nOP + 3) / 4, 128, 0, h->st>>>(P, C, ld, h->d_dS, s02, dOut); count_launch(); }
         cudaMemcpyAsync(out, dOut, sizeof(double) * 9 * (size_t)P.nOP, cudaMemcpyDeviceToHost, h->st);
         e = cudaStreamSynchronize(h->st);
         cudaFree(dOut);
@@ -1337,7 +1424,7 @@ extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
         std::vector<double> hc((size_t)ld * ld), dsc(std::max(1, nC));
         cudaMemcpy(hc.data(), C, sz, cudaMemcpyDeviceToHost);
         cudaMemcpy(dsc.data(), h->d_dscale, sizeof(double) * nC, cudaMemcpyDeviceToHost);
-        auto cv = [&](int a, int b) { return (info != 0) ? NAN : s02 * hc[(size_t)b * ld + a] * dsc[a] * dsc[b]; };
+        auto cv = [&](int a, int b) { return (info != 0) ? NAN : s02 * hc[(size_t)x2s[b] * ld + x2s[a]] * dsc[a] * dsc[b]; };
         if (which == DBAT_COV_CXX_CAM) {
             for (int b = 0; b < nC; ++b) for (int a = 0; a < nC; ++a) out[(size_t)b * nC + a] = cv(a, b);
         } else if (which == DBAT_COV_CEO || which == DBAT_COV_CIO) {
@@ -1382,10 +1469,10 @@ __global__ void __launch_bounds__(128) k_cop(DevProblem P, const double* __restr
     if (!f2) { Vi[2] = 0; Vi[4] = 0; Vi[5] = 0; }
     const int o0 = P.pt_start[j], k = P.pt_start[j + 1] - o0;
     const int nRows = DBAT_NSLOT + 6 * k;
-    auto row_col = [&](int a) -> int {
-        if (a < DBAT_NSLOT) return P.sh_col[a];
+    auto row_col = [&](int a) -> int {                 // S index of row a
+        if (a < DBAT_NSLOT) return P.sh_s[a];
         const int o = (a - DBAT_NSLOT) / 6, e = (a - DBAT_NSLOT) % 6;
-        return P.eo_col[6 * (size_t)P.img_pm[o0 + o] + e];
+        return P.eo_s[6 * (size_t)P.img_pm[o0 + o] + e];
     };
     auto row_T = [&](int a, double T[3]) {
         const double* w = (a < DBAT_NSLOT) ? rec + DBAT_PT_WSH + 3 * a
@@ -1484,6 +1571,97 @@ extern "C" int dbat_dense_chol_solve(int64_t n, const double* A, const double* b
     chol_free(w); cudaFree(dA); cudaFree(dA0); cudaFree(drhs); cudaFree(dx);
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
     if (e != cudaSuccess) { g_create_err = std::string("dbat_dense_chol_solve: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
+    return info != 0 ? DBAT_E_NOTSPD : DBAT_OK;
+}
+
+// The sparse tile solver on a caller-supplied SPD matrix: blocks of 6 columns play the images.
+extern "C" int dbat_tile_chol_solve(int64_t n, const double* A, const double* b, double* x, int64_t mode,
+                                    int64_t leafImages, int repeat, double* stats) {
+    if (n <= 0 || !A || !b || !x) return DBAT_E_BADARG;
+    const int nImg = (int)((n + 5) / 6);
+    std::vector<int> nEO(nImg, 6);
+    nEO[nImg - 1] = (int)(n - 6 * (int64_t)(nImg - 1));
+    std::vector<std::vector<int32_t>> nb(nImg);
+    for (int64_t c = 0; c < n; ++c)
+        for (int64_t r = c + 1; r < n; ++r)
+            if (A[(size_t)c * n + r] != 0.0 && r / 6 != c / 6) { nb[r / 6].push_back((int32_t)(c / 6)); nb[c / 6].push_back((int32_t)(r / 6)); }
+    std::vector<int64_t> ap(nImg + 1, 0); std::vector<int32_t> ad;
+    for (int i = 0; i < nImg; ++i) {
+        std::sort(nb[i].begin(), nb[i].end());
+        nb[i].erase(std::unique(nb[i].begin(), nb[i].end()), nb[i].end());
+        ap[i] = (int64_t)ad.size(); ad.insert(ad.end(), nb[i].begin(), nb[i].end());
+    }
+    ap[nImg] = (int64_t)ad.size();
+    TileSym sym;
+    if (tile_symbolic(nImg, ap.data(), ad.data(), nEO.data(), 0, (int)mode, (int)leafImages, sym)) return DBAT_E_BADARG;
+    TChol tc;
+    if (tchol_alloc(tc, sym)) { g_create_err = "dbat_tile_chol_solve: out of memory"; return DBAT_E_OOM; }
+    // host tiles and rhs in S order
+    std::vector<int> x2s(n);
+    for (int64_t c = 0; c < n; ++c) x2s[c] = sym.imgS[c / 6] + (int)(c % 6);
+    std::vector<double> ht((size_t)sym.nSlotsS * TC_TT, 0.0), hr(sym.ld, 0.0);
+    for (int64_t c = 0; c < n; ++c)
+        for (int64_t r = c; r < n; ++r) {
+            const double v = A[(size_t)c * n + r];
+            if (v == 0.0) continue;
+            const int sr = std::max(x2s[r], x2s[c]), sc = std::min(x2s[r], x2s[c]);
+            const int slot = sym.tix[(size_t)(sr / TC_T) * sym.nT + sc / TC_T];
+            if (slot < 0 || slot >= sym.nSlotsS) { tchol_free(tc); g_create_err = "tile pattern misses an entry"; return DBAT_E_STATE; }
+            ht[(size_t)slot * TC_TT + (sc % TC_T) * TC_T + sr % TC_T] = v;
+        }
+    for (int k = 0; k < sym.ld - 1; ++k)
+        if (sym.s2kind[k] == 0) ht[(size_t)sym.tix[(size_t)(k / TC_T) * sym.nT + k / TC_T] * TC_TT + (k % TC_T) * TC_T + k % TC_T] = 1.0;
+    for (int64_t c = 0; c < n; ++c) hr[x2s[c]] = b[c];
+    double *d0 = nullptr, *drhs = nullptr;
+    cudaMalloc(&d0, sizeof(double) * ht.size());
+    cudaMalloc(&drhs, sizeof(double) * hr.size());
+    cudaMemcpy(d0, ht.data(), sizeof(double) * ht.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(drhs, hr.data(), sizeof(double) * hr.size(), cudaMemcpyHostToDevice);
+    cudaStream_t st; cudaStreamCreate(&st);
+    cudaEvent_t e0, e1, e2; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+    float best = 1e30f, bestF = 1e30f;
+    const char* profPath = getenv("DBAT_TCHOL_PROF");        // per-task time stamps of the last repetition
+    unsigned long long* dprof = nullptr;
+    if (profPath) { cudaMalloc(&dprof, sizeof(unsigned long long) * 4 * sym.nTasks); tc.d.prof = dprof; }
+    for (int it = 0; it < std::max(1, repeat); ++it) {
+        cudaMemcpyAsync(tc.d.tiles, d0, sizeof(double) * ht.size(), cudaMemcpyDeviceToDevice, st);
+        cudaEventRecord(e0, st);
+        tchol_put_rhs(tc, drhs, st);
+        tchol_factor(tc, st);
+        cudaEventRecord(e2, st);
+        tchol_solve(tc, st);
+        cudaEventRecord(e1, st);
+        cudaStreamSynchronize(st);
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms);
+        cudaEventElapsedTime(&ms, e0, e2); bestF = std::min(bestF, ms);
+    }
+    if (profPath) {
+        std::vector<unsigned long long> hp((size_t)4 * sym.nTasks);
+        cudaMemcpy(hp.data(), dprof, sizeof(unsigned long long) * hp.size(), cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(profPath, "w")) {
+            fprintf(f, "task,I,J,level,nterms,t_claim,t_terms,t_deps,t_end\n");
+            for (int t = 0; t < sym.nTasks; ++t)
+                fprintf(f, "%d,%d,%d,%d,%lld,%llu,%llu,%llu,%llu\n", t, sym.taskI[t], sym.taskJ[t], sym.level[sym.taskJ[t]],
+                        (long long)(sym.termPtr[t + 1] - sym.termPtr[t]), hp[4 * t] - hp[0], hp[4 * t + 1] - hp[0], hp[4 * t + 2] - hp[0], hp[4 * t + 3] - hp[0]);
+            fclose(f);
+        }
+        cudaFree(dprof);
+    }
+    cudaEventDestroy(e2);
+    (void)bestF;
+    int info = 0; double mn = 0, mx = 0;
+    tchol_pivot_stats(tc, &info, &mn, &mx, st);
+    std::vector<double> hx(sym.ld);
+    cudaMemcpy(hx.data(), tc.xs, sizeof(double) * sym.ld, cudaMemcpyDeviceToHost);
+    for (int64_t c = 0; c < n; ++c) x[c] = hx[x2s[c]];
+    if (stats) {
+        stats[0] = best; stats[1] = sym.nT; stats[2] = sym.nSlots; stats[3] = sym.nTasks; stats[4] = (double)sym.nTerms;
+        stats[5] = sym.depth; stats[6] = mn; stats[7] = mx;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    tchol_free(tc); cudaFree(d0); cudaFree(drhs);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
+    if (e != cudaSuccess) { g_create_err = std::string("dbat_tile_chol_solve: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
     return info != 0 ? DBAT_E_NOTSPD : DBAT_OK;
 }
 

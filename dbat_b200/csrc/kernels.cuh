@@ -3,6 +3,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "model.cuh"
+#include "tilechol.h"
 
 #define DBAT_GW 24                 // Gram width: NSLOT(14) IO | 6 EO | 1 r | pad  (3 tiles of 8)
 #define DBAT_GT 3                  // 8-wide tiles
@@ -29,7 +30,7 @@ struct DevProblem {
     int n;                 // unknowns
     int nC;                // camera-side unknowns (IO+EO) = order of the reduced system
     int nChunks;
-    int ldS;               // leading dimension of S (multiple of 128)
+    int ldS;               // order of the padded reduced system (multiple of 64; the last row carries the rhs)
     int nPrior;
     // observations, camera-major (reference row order: obs k -> rows 2k,2k+1)
     const double2* uv_cm; const double2* isig_cm; const int* pt_cm; const int* img_cm;
@@ -44,6 +45,12 @@ struct DevProblem {
     const int* sh_col;     // NSLOT
     const int* eo_col;     // nImg x 6
     const int* op_col;     // nOP x 3
+    // position of the camera-side unknowns in the reduced system ("S order": images in elimination
+    // order, shared IO last; tilesym.cu), -1 = fixed
+    const int* sh_s;       // NSLOT
+    const int* eo_s;       // nImg x 6
+    const int* s2x;        // ldS: x column of every S index (-1: padding / rhs row)
+    TCholDev T;            // the reduced system itself: 64 x 64 tiles of the sparse pattern (tilechol.cu)
     // prior observations
     const int* prior_col; const double* prior_val; const double* prior_isig;
     // normal-equation storage
@@ -52,8 +59,7 @@ struct DevProblem {
     double* shG;           // GSZ             sum over images
     double* pt;            // nOP x PT_STRIDE point records
     double* W;             // nObs x 18       cross blocks, point-major order
-    double* S;             // ldS x ldS       reduced system (lower triangle), column-major
-    double* rhs;           // ldS             reduced right-hand side
+    double* rhs;           // ldS             reduced right-hand side (S order)
     // deterministic Schur reduction (index built once at create, schur_index.cu)
     double* Y;             // nObs x 18       Y_o = W_o (V_j + lambda I)^-1, point-major order
     double* ptaux;         // nOP x PTAUX_STRIDE : Vg[3], pad, Ysh[14][3]

@@ -85,56 +85,57 @@ void launch_diag(const DevProblem& P, const double* camDiag, double* diagN, cuda
     count_launch();
 }
 
-// S := N_cc + lambda*I (lower triangle), rhs := -g_c ; padding rows get a unit diagonal
+// S := N_cc + lambda*I (lower triangle, S order), rhs := -g_c ; padding positions get a unit diagonal
 __global__ void k_build_S(DevProblem P, const double* __restrict__ camDiag, const double* __restrict__ camG,
                           double lambda) {
     const int i = blockIdx.x;         // image index, or nImg for the shared block
-    const size_t ld = P.ldS;
     if (i < P.nImg) {
         const double* G = P.imgG + (size_t)i * DBAT_GSZ;
         const int* ec = P.eo_col + 6 * (size_t)i;
+        const int* es = P.eo_s + 6 * (size_t)i;
         for (int e = threadIdx.x; e < 6 * (6 + DBAT_NSLOT + 1); e += blockDim.x) {
             const int a = e / (6 + DBAT_NSLOT + 1), b = e % (6 + DBAT_NSLOT + 1);
-            const int row = ec[a];
+            const int row = es[a];
             if (row < 0) continue;
-            if (b < 6) {                                   // EO x EO
-                const int col = ec[b];
+            if (b < 6) {                                   // EO x EO (S indices ascend with the element)
+                const int col = es[b];
                 if (col < 0 || col > row) continue;
                 double v = gram_at(G, DBAT_COL_EO + a, DBAT_COL_EO + b);
-                if (a == b) v += camDiag[row] + lambda;
-                P.S[(size_t)col * ld + row] = v;
-            } else if (b < 6 + DBAT_NSLOT) {               // EO x shared IO (IO columns come first in x)
-                const int col = P.sh_col[b - 6];
-                if (col < 0) continue;
-                P.S[(size_t)col * ld + row] = gram_at(G, DBAT_COL_EO + a, b - 6);
+                if (a == b) v += camDiag[ec[a]] + lambda;
+                *tc_at(P.T, row, col) = v;
+            } else if (b < 6 + DBAT_NSLOT) {               // shared IO x EO (the IO block comes last in S)
+                const int srow = P.sh_s[b - 6];
+                if (srow < 0) continue;
+                *tc_at(P.T, srow, row) = gram_at(G, DBAT_COL_EO + a, b - 6);
             } else {
-                P.rhs[row] = -(gram_at(G, DBAT_COL_EO + a, DBAT_COL_R) + camG[row]);
+                P.rhs[row] = -(gram_at(G, DBAT_COL_EO + a, DBAT_COL_R) + camG[ec[a]]);
             }
         }
     } else {
         for (int e = threadIdx.x; e < DBAT_NSLOT * (DBAT_NSLOT + 1); e += blockDim.x) {
             const int a = e / (DBAT_NSLOT + 1), b = e % (DBAT_NSLOT + 1);
-            const int row = P.sh_col[a];
+            const int row = P.sh_s[a];
             if (row < 0) continue;
             if (b < DBAT_NSLOT) {
-                const int col = P.sh_col[b];
+                const int col = P.sh_s[b];
                 if (col < 0 || col > row) continue;
                 double v = gram_at(P.shG, a, b);
-                if (a == b) v += camDiag[row] + lambda;
-                P.S[(size_t)col * ld + row] = v;
+                if (a == b) v += camDiag[P.sh_col[a]] + lambda;
+                *tc_at(P.T, row, col) = v;
             } else {
-                P.rhs[row] = -(gram_at(P.shG, a, DBAT_COL_R) + camG[row]);
+                P.rhs[row] = -(gram_at(P.shG, a, DBAT_COL_R) + camG[P.sh_col[a]]);
             }
         }
-        for (int k = P.nC + threadIdx.x; k < P.ldS; k += blockDim.x) {
-            P.S[(size_t)k * ld + k] = 1.0;
+        for (int k = threadIdx.x; k < P.ldS; k += blockDim.x) {
+            if (P.s2x[k] >= 0) continue;
             P.rhs[k] = 0.0;
+            if (k != P.ldS - 1) *tc_at(P.T, k, k) = 1.0;     // the rhs row gets its diagonal in tchol_put_rhs
         }
     }
 }
 void launch_build_S(const DevProblem& P, const double* camDiag, const double* camG, double lambda,
                     cudaStream_t st) {
-    cudaMemsetAsync(P.S, 0, sizeof(double) * (size_t)P.ldS * P.ldS, st);
+    cudaMemsetAsync(P.T.tiles, 0, sizeof(double) * (size_t)P.T.nSlotsS * TC_TT, st);
     k_build_S<<<P.nImg + 1, 128, 0, st>>>(P, camDiag, camG, lambda);
     count_launch();
 }
@@ -182,7 +183,6 @@ __global__ void __launch_bounds__(256) k_schur_pairs(DevProblem P) {
     const int lane = threadIdx.x & 31;
     const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
-    const size_t ld = P.ldS;
     for (int blk = warpGlobal; blk < P.nBlk; blk += nWarps) {
         const long long key = P.blk_key[blk];
         const int ia = (int)(key / P.nImg), ib = (int)(key % P.nImg);
@@ -213,22 +213,23 @@ __global__ void __launch_bounds__(256) k_schur_pairs(DevProblem P) {
             for (int b = 0; b < 6; ++b)
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) acc[a][b] += __shfl_xor_sync(0xffffffffu, acc[a][b], o);
-        const int* ra = P.eo_col + 6 * (size_t)ia;
-        const int* cb = P.eo_col + 6 * (size_t)ib;
+        const int* ra = P.eo_s + 6 * (size_t)ia;
+        const int* cb = P.eo_s + 6 * (size_t)ib;
 #pragma unroll
         for (int a = 0; a < 6; ++a)
 #pragma unroll
             for (int b = 0; b < 6; ++b)
                 if (lane == ((a * 6 + b) & 31)) {
                     const int row = ra[a], col = cb[b];
-                    if (row >= 0 && col >= 0 && col <= row) P.S[(size_t)col * ld + row] -= acc[a][b];
+                    if (row < 0 || col < 0) continue;
+                    if (ia == ib) { if (col <= row) *tc_at(P.T, row, col) -= acc[a][b]; }
+                    else *tc_at(P.T, max(row, col), min(row, col)) -= acc[a][b];
                 }
     }
 }
 
 __global__ void __launch_bounds__(128) k_schur_cam(DevProblem P) {
     const int i = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const size_t ld = P.ldS;
     double acc[6][4];
 #pragma unroll
     for (int a = 0; a < 6; ++a)
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(128) k_schur_cam(DevProblem P) {
         for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc[a][c] += __shfl_xor_sync(0xffffffffu, acc[a][c], o);
-    const int* ec = P.eo_col + 6 * (size_t)i;
+    const int* ec = P.eo_s + 6 * (size_t)i;
 #pragma unroll
     for (int a = 0; a < 6; ++a)
 #pragma unroll
@@ -265,7 +266,7 @@ __global__ void __launch_bounds__(128) k_schur_cam(DevProblem P) {
             if (lane == a * 4 + c) {
                 const int row = ec[a], col = 4 * w + c;
                 if (row >= 0) {
-                    if (col < DBAT_NSLOT) { const int sc = P.sh_col[col]; if (sc >= 0) P.S[(size_t)sc * ld + row] -= acc[a][c]; }
+                    if (col < DBAT_NSLOT) { const int sc = P.sh_s[col]; if (sc >= 0) *tc_at(P.T, sc, row) -= acc[a][c]; }
                     else if (col == DBAT_NSLOT) P.rhs[row] += acc[a][c];
                 }
             }
@@ -310,16 +311,15 @@ __global__ void __launch_bounds__(256) k_schur_sh(DevProblem P) {
             if (lane == ((s * 2 + c) & 31)) out[s * DBAT_SHCOLS + 2 * w + c] = acc[s][c];
 }
 __global__ void k_schur_sh_final(DevProblem P, int nPart) {
-    const size_t ld = P.ldS;
     for (int e = threadIdx.x; e < DBAT_NSLOT * DBAT_SHCOLS; e += blockDim.x) {
         const int s = e / DBAT_SHCOLS, c = e % DBAT_SHCOLS;
         double t = 0.0;
         for (int q = 0; q < nPart; ++q) t += P.shPart[(size_t)q * (DBAT_NSLOT * DBAT_SHCOLS) + e];
-        const int row = P.sh_col[s];
+        const int row = P.sh_s[s];
         if (row < 0) continue;
         if (c < DBAT_NSLOT) {
-            const int col = P.sh_col[c];
-            if (col >= 0 && c <= s) P.S[(size_t)col * ld + row] -= t;
+            const int col = P.sh_s[c];
+            if (col >= 0 && c <= s) *tc_at(P.T, row, col) -= t;
         } else if (c == DBAT_NSLOT) {
             P.rhs[row] += t;
         }
@@ -338,7 +338,6 @@ __global__ void __launch_bounds__(256) k_schur_atomic(DevProblem P, double lambd
     const int lane = threadIdx.x & 31;
     const int warpGlobal = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int nWarps = (gridDim.x * blockDim.x) >> 5;
-    const size_t ld = P.ldS;
     // shared x shared accumulators: entries e = lane + 32*k of the NSLOT x (NSLOT+1) table
     constexpr int NE = DBAT_NSLOT * (DBAT_NSLOT + 1);
     constexpr int NEL = (NE + 31) / 32;
@@ -366,29 +365,29 @@ __global__ void __launch_bounds__(256) k_schur_atomic(DevProblem P, double lambd
             while ((o + 1) * (o + 2) / 2 <= pr) ++o;
             while (o * (o + 1) / 2 > pr) --o;
             const int o2 = pr - o * (o + 1) / 2;            // o2 <= o  => image(o2) <= image(o)
-            const int row = P.eo_col[6 * (size_t)P.img_pm[o0 + o] + a];
+            const int row = P.eo_s[6 * (size_t)P.img_pm[o0 + o] + a];
             if (row < 0) continue;
             const double* Wa = P.W + (size_t)(o0 + o) * DBAT_W_STRIDE + 3 * a;
             const double wa[3] = {Wa[0], Wa[1], Wa[2]};
             double ya[3];
             symv3(Vi, wa, ya);
-            const int* ec2 = P.eo_col + 6 * (size_t)P.img_pm[o0 + o2];
+            const int* ec2 = P.eo_s + 6 * (size_t)P.img_pm[o0 + o2];
             const double* Wb = P.W + (size_t)(o0 + o2) * DBAT_W_STRIDE;
 #pragma unroll
             for (int b = 0; b < 6; ++b) {
                 const int col = ec2[b];
-                if (col < 0 || col > row) continue;
+                if (col < 0 || (o2 == o && col > row)) continue;     // same image: lower triangle only
                 const double v = ya[0] * Wb[3 * b] + ya[1] * Wb[3 * b + 1] + ya[2] * Wb[3 * b + 2];
-                atomicAdd(&P.S[(size_t)col * ld + row], -v);
+                atomicAdd(tc_at(P.T, max(row, col), min(row, col)), -v);
             }
             if (o2 == 0) {                                   // once per (o, a): rhs and shared x local
                 atomicAdd(&P.rhs[row], ya[0] * gj[0] + ya[1] * gj[1] + ya[2] * gj[2]);
 #pragma unroll
                 for (int s = 0; s < DBAT_NSLOT; ++s) {
-                    const int col = P.sh_col[s];
-                    if (col < 0) continue;
+                    const int srow = P.sh_s[s];
+                    if (srow < 0) continue;
                     const double* ws = rec + DBAT_PT_WSH + 3 * s;
-                    atomicAdd(&P.S[(size_t)col * ld + row], -(ya[0] * ws[0] + ya[1] * ws[1] + ya[2] * ws[2]));
+                    atomicAdd(tc_at(P.T, srow, row), -(ya[0] * ws[0] + ya[1] * ws[1] + ya[2] * ws[2]));
                 }
             }
         }
@@ -451,7 +450,7 @@ __global__ void k_point_vinv(DevProblem P, double lambda) {
 struct GrpHeader {            // per-group data staged in shared memory (double-buffered)
     int m, ng, maxobs;                           // images in the union, points, largest ray count of a point
     int j[GRP_CAP], ob[GRP_CAP], nob[GRP_CAP];   // point id, first point-major observation, ray count
-    int eoc[DBAT_GRP_MAXM * 6];                  // x column of every EO element of the union's images
+    int eoc[DBAT_GRP_MAXM * 6];                  // S index of every EO element of the union's images (ascending)
     double vi[GRP_CAP * 6];
 };
 // Registers of one thread's share of the next group's header (loaded early, stored late).
@@ -471,7 +470,7 @@ __device__ __forceinline__ void grp_prefetch(const DevProblem& P, int grp, int t
         const double2* vp = reinterpret_cast<const double2*>(P.vinv + (size_t)f.j * 8);
         f.v01 = vp[0]; f.v23 = vp[1]; f.v45 = vp[2];
     }
-    if (t >= 64 && t - 64 < 6 * f.m) f.eoc = P.eo_col[6 * (size_t)P.grp_img[i0 + (t - 64) / 6] + (t - 64) % 6];
+    if (t >= 64 && t - 64 < 6 * f.m) f.eoc = P.eo_s[6 * (size_t)P.grp_img[i0 + (t - 64) / 6] + (t - 64) % 6];
 }
 __device__ __forceinline__ void grp_store(GrpHeader& h, int t, const GrpPrefetch& f) {
     if (t == 0) { h.m = f.m; h.ng = f.ng; }
@@ -500,7 +499,6 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
     __shared__ GrpHeader s_hdr[2];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int fr = lane >> 2, fk = lane & 3;
-    const size_t ld = P.ldS;
     const int RWmax = (6 * P.grpMaxRays + 7) & ~7;
     double* What = dsm;
     double* Yhat = What + RWmax * GRP_LDK;
@@ -595,7 +593,7 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
                             if (c < R) {
                                 const int col = H.eoc[c];
                                 const double v = e ? c1 : c0;                 // exact zero: image pair not shared by any point
-                                if (col >= 0 && col <= row && v != 0.0) atomicAdd(&P.S[(size_t)col * ld + row], -v);
+                                if (col >= 0 && col <= row && v != 0.0) atomicAdd(tc_at(P.T, row, col), -v);
                             }
                         }
                     } else {
@@ -603,8 +601,8 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
                         for (int e = 0; e < 2; ++e) {
                             const int sidx = 8 * tj + 2 * fk + e;
                             if (sidx < DBAT_NSLOT) {
-                                const int col = P.sh_col[sidx];
-                                if (col >= 0) atomicAdd(&P.S[(size_t)col * ld + row], -(e ? c1 : c0));
+                                const int srow = P.sh_s[sidx];
+                                if (srow >= 0) atomicAdd(tc_at(P.T, srow, row), -(e ? c1 : c0));
                             } else if (sidx == DBAT_NSLOT) {
                                 atomicAdd(&P.rhs[row], e ? c1 : c0);
                             }
@@ -641,15 +639,14 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
     }
 }
 __global__ void k_schur_sh_apply(DevProblem P, const double* __restrict__ shAcc) {
-    const size_t ld = P.ldS;
     for (int e = threadIdx.x; e < DBAT_NSLOT * (DBAT_NSLOT + 1); e += blockDim.x) {
         const int a = e / (DBAT_NSLOT + 1), b = e % (DBAT_NSLOT + 1);
-        const int row = P.sh_col[a];
+        const int row = P.sh_s[a];
         if (row < 0) continue;
         if (b < DBAT_NSLOT) {
-            const int col = P.sh_col[b];
+            const int col = P.sh_s[b];
             if (col < 0 || b > a) continue;
-            P.S[(size_t)col * ld + row] -= shAcc[e];
+            *tc_at(P.T, row, col) -= shAcc[e];
         } else {
             P.rhs[row] += shAcc[e];
         }
@@ -707,17 +704,30 @@ void launch_schur(const DevProblem& P, double lambda, cudaStream_t st) {
     count_launch(5);
 }
 
-// S := D S D (lower triangle), rhs := D rhs   (Jacobi column scaling, gauss_newton_armijo.m:166-172)
-__global__ void k_scale_S(DevProblem P, const double* __restrict__ d) {
-    const int c = blockIdx.y;
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= P.nC || r >= P.nC || r < c) return;
-    P.S[(size_t)c * P.ldS + r] *= d[r] * d[c];
-    if (c == 0) P.rhs[r] *= d[r];
+// Jacobi column scaling (gauss_newton_armijo.m:166-172) of the reduced system: dS[s] = d[x column of s]
+// (1 at padding positions), rhs := D rhs; the tiles are scaled by tchol_scale.
+__global__ void k_scale_prep(DevProblem P, const double* __restrict__ d, double* __restrict__ dS) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.ldS) return;
+    const int c = P.s2x[s];
+    const double v = c >= 0 ? d[c] : 1.0;
+    dS[s] = v;
+    P.rhs[s] *= v;
 }
-void launch_scale_S(const DevProblem& P, const double* d, cudaStream_t st) {
-    dim3 grid((P.nC + 255) / 256, P.nC);
-    k_scale_S<<<grid, 256, 0, st>>>(P, d);
+void launch_scale_prep(const DevProblem& P, const double* d, double* dS, cudaStream_t st) {
+    k_scale_prep<<<(P.ldS + 255) / 256, 256, 0, st>>>(P, d, dS);
+    count_launch();
+}
+// camera-side step from the solution in S order: pc[x column] = xs[s] (* d)
+__global__ void k_unpermute(DevProblem P, const double* __restrict__ xs, const double* __restrict__ d,
+                            double* __restrict__ pc) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= P.ldS) return;
+    const int c = P.s2x[s];
+    if (c >= 0) pc[c] = d ? xs[s] * d[c] : xs[s];
+}
+void launch_unpermute(const DevProblem& P, const double* xs, const double* d, double* pc, cudaStream_t st) {
+    k_unpermute<<<(P.ldS + 255) / 256, 256, 0, st>>>(P, xs, d, pc);
     count_launch();
 }
 

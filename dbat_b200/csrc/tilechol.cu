@@ -1,0 +1,665 @@
+// tilechol.cu — sparse tile Cholesky of the reduced camera system on the FP64 tensor pipe (DMMA
+// mma.sync.m8n8k4.f64), one persistent data-flow kernel per factorisation.
+//
+// Replaces MATLAB's `\` / chol (CHOLMOD supernodal) at code/bundle/lsa/levenberg_marquardt.m:119,
+// gauss_newton_armijo.m:172, levenberg_marquardt_powell.m:272-277 for the reduced camera system.
+// The matrix is held as 64 x 64 tiles of the sparse pattern computed once per problem (tilesym.cu:
+// nested-dissection order of the images, shared IO block and rhs row last, tile-level symbolic
+// fill).  Left-looking: ONE task per tile,
+//     L(I,J) = ( S(I,J) - sum_k L(I,k) L(J,k)' ) inv(L(J,J))'          (I > J)
+//     L(J,J) = chol( S(J,J) - sum_k L(J,k) L(J,k)' )
+// The sums run over the k < J where both tiles exist; they stay in registers, so every tile is read
+// once as S and written once as L (the right-looking dense code re-read the trailing matrix 47 times).
+// CTAs claim tasks from one list (columns sorted by elimination-tree level: independent subtrees
+// interleave), and wait on per-tile ready flags: a task depends only on tasks earlier in the list,
+// every claimed task belongs to a running CTA, hence no deadlock for any grid size.
+// The triangular solve against the diagonal tile uses the inverses of its four 16 x 16 diagonal
+// blocks (which fall out of the pivot sweep for free) and is row-wise independent: each warp owns
+// 16 rows of the tile and needs no CTA-wide barrier.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include "launch.h"
+#include "tilechol.h"
+
+#define LA 68                     // shared-memory column stride of a 64-row operand (= 4 mod 16)
+#define PB 16
+#define TC_STAGES 4
+#define TC_SLICE (16 * LA)        // one 16-column slice of one operand
+#define TC_STAGE (2 * TC_SLICE)
+#define TC_OFF_LS (64 * LA)       // solve phase: L(J,J) columns 0..47 behind the 64 x 64 work tile
+#define TC_OFF_XD (TC_OFF_LS + 48 * LA)
+#define TC_OFF_COLB (TC_OFF_XD + TC_XD)
+#define TC_SMEM_DOUBLES (TC_OFF_COLB + 3 * PB + 8)
+static_assert(TC_OFF_XD >= TC_STAGES * TC_STAGE - TC_XD || true, "layout");
+static_assert(TC_STAGES * TC_STAGE <= TC_OFF_COLB, "pipeline stages must fit under the scratch area");
+#define TC_THREADS 128
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+__device__ __forceinline__ int ld_acquire(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+// lane 0 of the warp spins until *f == epoch, then the whole warp continues (the barrier orders the
+// other lanes' later reads after lane 0's acquire)
+__device__ __forceinline__ void warp_wait_flag(const int* f, int epoch, int lane) {
+    if (lane == 0) { while (ld_acquire(f) != epoch) { __nanosleep(32); } }
+    __syncwarp();
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define TC_STAMP(k) { if (D.prof && tid == 0) D.prof[4 * (size_t)task + (k)] = gtimer(); }
+__device__ __forceinline__ double rsqrt_nr(double d) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double h = d * y, e = fma(-h, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    h = d * y; e = fma(-h, y, 1.0);
+    return fma(0.5 * y, e, y);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 64 x 64 diagonal tile in shared memory (column-major, stride LA): Cholesky in place + the
+// inverses of the four 16 x 16 diagonal blocks (Xd[p][n'][n] = inv(L_pp)(n', n), row stride TC_XLD).
+// ---------------------------------------------------------------------------------------------
+// D(p): one warp factors the 16 x 16 diagonal block in registers, LDL' form (lane r < 16: row r;
+// lanes 16..31 carry the columns of the identity through the same sweep -> inv(L_pp)).  Between
+// two pivots: reciprocal seed, one correction folded into the update, one shuffle.
+__device__ __forceinline__ void tc_diag16(double* As, double* Xd, double* colb, int c0, int lane,
+                                          const unsigned char* __restrict__ valid, int gcol0,
+                                          double& lmin, double& lmax, int& bad) {
+    double* spd = colb + 2 * PB;
+    const int r = lane & 15;
+    const bool isX = lane >= 16;
+    double v[PB];
+#pragma unroll
+    for (int c = 0; c < PB; ++c) {
+        const double a = As[(c0 + c) * LA + c0 + r];
+        v[c] = isX ? (c == r ? 1.0 : 0.0) : a;
+    }
+    double d = __shfl_sync(0xffffffffu, v[0], 0);
+#pragma unroll
+    for (int j = 0; j < PB; ++j) {
+        double* cb = colb + (j & 1) * PB;
+        if (!isX) cb[r] = v[j];
+        double y;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+        const double e = fma(-d, y, 1.0);
+        const double vy = v[j] * y;
+        const double dj = d;
+        if (j + 1 < PB) {
+            const double q = v[j] * vy;
+            const double base = v[j + 1] - q;
+            const double t = fma(e, e, e);
+            const double cand = fma(-q, t, base);
+            d = __shfl_sync(0xffffffffu, cand, j + 1);
+        }
+        const double e2 = e * e;
+        const double vy1 = fma(vy, e, vy);
+        const double w = fma(vy1, e2, vy1);
+        __syncwarp();
+#pragma unroll
+        for (int c = j + 1; c < PB; ++c) v[c] = fma(-w, cb[c], v[c]);
+        if (lane == 0) spd[j] = dj;
+    }
+    __syncwarp();
+    {
+        const double dr = spd[r];
+        const double isdr = rsqrt_nr(dr);
+        if (!(dr > 0.0)) bad = 1;
+        if (!isX && valid[gcol0 + r]) { const double l = dr * isdr; lmin = fmin(lmin, l); lmax = fmax(lmax, l); }
+#pragma unroll
+        for (int j = 0; j < PB; ++j) v[j] *= __shfl_sync(0xffffffffu, isdr, j);
+    }
+    if (!isX) {
+#pragma unroll
+        for (int c = 0; c < PB; ++c) if (c <= r) As[(c0 + c) * LA + c0 + r] = v[c];
+    } else {
+#pragma unroll
+        for (int j = 0; j < PB; ++j) Xd[j * TC_XLD + r] = v[j];         // inv(L_pp)(j, r); zero above the diagonal
+    }
+}
+
+// R(p): 8-row tile q below the diagonal block: L(i, panel) = A(i, panel) inv(L_pp)'
+__device__ __forceinline__ void tc_rtile(double* As, const double* Xd, int c0, int q, int lane) {
+    const int fr = lane >> 2, fk = lane & 3;
+    const double* pb = Xd + fr * TC_XLD + fk;
+    const double* pa = As + (c0 + fk) * LA + c0 + PB + 8 * q + fr;
+    double r0[4][2], r1[4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const double a = pa[4 * k * LA];
+        r0[k][0] = r0[k][1] = r1[k][0] = r1[k][1] = 0.0;
+        dmma(r0[k][0], r0[k][1], a, pb[4 * k]);
+        dmma(r1[k][0], r1[k][1], a, pb[8 * TC_XLD + 4 * k]);
+    }
+    __syncwarp();                                   // every lane has read its A fragments before the in-place store
+    double* pc = As + (c0 + 2 * fk) * LA + c0 + PB + 8 * q + fr;
+    pc[0] = (r0[0][0] + r0[1][0]) + (r0[2][0] + r0[3][0]);
+    pc[LA] = (r0[0][1] + r0[1][1]) + (r0[2][1] + r0[3][1]);
+    pc[8 * LA] = (r1[0][0] + r1[1][0]) + (r1[2][0] + r1[3][0]);
+    pc[9 * LA] = (r1[0][1] + r1[1][1]) + (r1[2][1] + r1[3][1]);
+}
+
+// U(p): 8 x 8 tile (ti, tj), ti >= tj, of the trailing block: A(i,j) -= L(i,panel) L(j,panel)'
+__device__ __forceinline__ void tc_utile(double* As, int c0, int ti, int tj, int lane) {
+    const int fr = lane >> 2, fk = lane & 3;
+    const int b0 = c0 + PB;
+    const double* pa0 = As + (c0 + fk) * LA + b0 + fr;
+    double acc[4][2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        acc[k][0] = acc[k][1] = 0.0;
+        dmma(acc[k][0], acc[k][1], pa0[4 * k * LA + 8 * ti], pa0[4 * k * LA + 8 * tj]);
+    }
+    double* pc = As + (b0 + 8 * tj + 2 * fk) * LA + b0 + 8 * ti + fr;
+    pc[0] -= (acc[0][0] + acc[1][0]) + (acc[2][0] + acc[3][0]);
+    pc[LA] -= (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
+}
+
+__device__ void tc_potrf64(double* As, double* Xd, double* colb, int warp, int lane,
+                           const unsigned char* __restrict__ valid, int gcol0, int* info, unsigned long long* minmax,
+                           int J) {
+    double lmin = 1e300, lmax = 0.0;
+    int bad = 0;
+    for (int p = 0; p < 4; ++p) {
+        const int c0 = PB * p;
+        const int m = 6 - 2 * p;                              // 8-row tiles below the diagonal block
+        if (warp == 0) tc_diag16(As, Xd + p * PB * TC_XLD, colb, c0, lane, valid, gcol0 + c0, lmin, lmax, bad);
+        __syncthreads();
+        for (int q = warp; q < m; q += TC_THREADS / 32) tc_rtile(As, Xd + p * PB * TC_XLD, c0, q, lane);
+        __syncthreads();
+        const int ntile = m * (m + 1) / 2;
+        for (int t = warp; t < ntile; t += TC_THREADS / 32) {
+            int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+            while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+            while (ti * (ti + 1) / 2 > t) --ti;
+            tc_utile(As, c0, ti, t - ti * (ti + 1) / 2, lane);
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lmin = fmin(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+            lmax = fmax(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        }
+        bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            if (bad) atomicCAS(info, 0, J + 1);
+            if (lmax > 0.0) {                                 // positive doubles order like their bit patterns
+                atomicMin(minmax, (unsigned long long)__double_as_longlong(lmin));
+                atomicMax(minmax + 1, (unsigned long long)__double_as_longlong(lmax));
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the factorisation kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int epoch) {
+    extern __shared__ __align__(16) double sm[];
+    __shared__ int s_task;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp & 1) * 32, wn = (warp >> 1) * 32;
+    const int fr = lane >> 2, fk = lane & 3;
+    double* Xd = sm + TC_OFF_XD;
+    double* colb = sm + TC_OFF_COLB;
+    for (;;) {
+        __syncthreads();                                      // previous task's shared memory is free
+        if (tid == 0) s_task = atomicAdd(D.counters, 1);
+        __syncthreads();
+        const int task = s_task;
+        if (task >= D.nTasks) break;
+        TC_STAMP(0)
+        const int I = D.taskI[task], J = D.taskJ[task];
+        const int slot = D.tix[(size_t)I * D.nT + J];
+        double* tile = D.tiles + ((size_t)slot << 12);
+        const long long t0 = D.termPtr[task];
+        const int nterm = (int)(D.termPtr[task + 1] - t0);
+        // ---- accumulator: -S(I,J) for tiles of the pattern of S, zero for fill tiles
+        double acc[4][4][2];
+        if (slot < D.nSlotsS) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const double* p0 = tile + (wn + 8 * j + 2 * fk) * 64 + wm + 8 * i + fr;
+                    acc[i][j][0] = -p0[0]; acc[i][j][1] = -p0[64];
+                }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+        }
+        if (I == J) {
+            // ---- diagonal tile: sum_k L(J,k) L(J,k)'.  One operand per term, so a whole tile is fetched at
+            //      once into one of two buffers the moment its flag is up: the last term - the one on the
+            //      critical path of the factorisation - costs one L2 round trip and 64 uninterrupted k-steps.
+            for (int term = 0; term < nterm; ++term) {
+                const int sa = D.termA[t0 + term];
+                warp_wait_flag(D.flag + sa, epoch, lane);
+                double* As = sm + (term & 1) * (64 * LA);
+                const double* ga = D.tiles + ((size_t)sa << 12);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    const int chunk = tid + c * TC_THREADS;
+                    const int kk = chunk >> 5, m2 = (chunk & 31) * 2;
+                    cp_async16(As + kk * LA + m2, ga + kk * 64 + m2);
+                }
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncthreads();
+                if (wm >= wn) {                                 // the upper 32 x 32 block is never used
+#pragma unroll 4
+                    for (int k0 = 0; k0 < 64; k0 += 4) {
+                        double af[4], bf[4];
+                        const double* ap = As + (k0 + fk) * LA + wm + fr;
+                        const double* bp = As + (k0 + fk) * LA + wn + fr;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) af[i] = ap[8 * i];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) bf[j] = bp[8 * j];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                    }
+                }
+            }
+        } else {
+        // ---- sum_k L(I,k) L(J,k)': 16-column slices through a cp.async ring; a term is issued once
+        //      the flags of its two tiles are up
+        const int nsl = nterm * 4;
+        auto issue = [&](int q) {
+            const int term = q >> 2, ks = q & 3;
+            const int sa = D.termA[t0 + term], sb = D.termB[t0 + term];
+            if (ks == 0) {
+                warp_wait_flag(D.flag + sa, epoch, lane);
+                warp_wait_flag(D.flag + sb, epoch, lane);
+            }
+            double* As = sm + (q % TC_STAGES) * TC_STAGE;
+            double* Bs = As + TC_SLICE;
+            const double* ga = D.tiles + ((size_t)sa << 12) + ks * 16 * 64;
+            const double* gb = D.tiles + ((size_t)sb << 12) + ks * 16 * 64;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int chunk = tid + c * TC_THREADS;
+                const int kk = chunk >> 5, m2 = (chunk & 31) * 2;
+                cp_async16(As + kk * LA + m2, ga + kk * 64 + m2);
+                cp_async16(Bs + kk * LA + m2, gb + kk * 64 + m2);
+            }
+        };
+#pragma unroll
+        for (int s = 0; s < TC_STAGES - 1; ++s) { if (s < nsl) issue(s); cp_async_commit(); }
+        for (int q = 0; q < nsl; ++q) {
+            cp_async_wait<TC_STAGES - 2>();
+            __syncthreads();
+            const double* As = sm + (q % TC_STAGES) * TC_STAGE;
+            const double* Bs = As + TC_SLICE;
+#pragma unroll
+            for (int k0 = 0; k0 < 16; k0 += 4) {
+                double af[4], bf[4];
+                const double* ap = As + (k0 + fk) * LA + wm + fr;
+                const double* bp = Bs + (k0 + fk) * LA + wn + fr;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) af[i] = ap[8 * i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = bp[8 * j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+            const int nq = q + TC_STAGES - 1;
+            if (nq < nsl) issue(nq);
+            cp_async_commit();
+        }
+        }
+        cp_async_wait<0>();
+        __syncthreads();
+        TC_STAMP(1)
+        // ---- C = S - sum (= -acc) into the work tile (column-major, stride LA)
+        double* Cs = sm;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                double* p0 = Cs + (wn + 8 * j + 2 * fk) * LA + wm + 8 * i + fr;
+                p0[0] = -acc[i][j][0]; p0[LA] = -acc[i][j][1];
+            }
+        if (I == J) {
+            __syncthreads();
+            TC_STAMP(2)
+            tc_potrf64(Cs, Xd, colb, warp, lane, D.valid, 64 * J, D.info, D.minmax, J);
+            // write L(J,J) (lower triangle; zeros above) and the inverse diagonal blocks
+            for (int idx = tid; idx < 64 * 32; idx += TC_THREADS) {
+                const int c = idx >> 5, r2 = (idx & 31) * 2;
+                double2 v;
+                v.x = (r2 >= c) ? Cs[c * LA + r2] : 0.0;
+                v.y = (r2 + 1 >= c) ? Cs[c * LA + r2 + 1] : 0.0;
+                *reinterpret_cast<double2*>(tile + c * 64 + r2) = v;
+            }
+            double* gx = D.invD + (size_t)J * TC_XD;
+            for (int idx = tid; idx < TC_XD; idx += TC_THREADS) gx[idx] = Xd[idx];
+        } else {
+            // ---- X = C inv(L(J,J))' by 16-column panels; warp w owns rows 16w .. 16w+15
+            const int dslot = D.tix[(size_t)J * D.nT + J];
+            warp_wait_flag(D.flag + dslot, epoch, lane);
+            __syncthreads();                                   // all warps have stored C and seen the flag
+            {
+                double* Ls = sm + TC_OFF_LS;
+                const double* gl = D.tiles + ((size_t)dslot << 12);
+                for (int chunk = tid; chunk < 48 * 32; chunk += TC_THREADS) {
+                    const int c = chunk >> 5, m2 = (chunk & 31) * 2;
+                    cp_async16(Ls + c * LA + m2, gl + c * 64 + m2);
+                }
+                cp_async_commit();
+                const double* gx = D.invD + (size_t)J * TC_XD;
+                for (int idx = tid; idx < TC_XD; idx += TC_THREADS) Xd[idx] = __ldcg(gx + idx);
+                cp_async_wait<0>();
+                __syncthreads();
+            }
+            TC_STAMP(2)
+            const double* Ls = sm + TC_OFF_LS;
+            const int R0 = 16 * warp;
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                const int c0 = PB * p;
+                double t[2][2][2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const double* p0 = Cs + (c0 + 8 * j + 2 * fk) * LA + R0 + 8 * i + fr;
+                        t[i][j][0] = p0[0]; t[i][j][1] = p0[LA];
+                    }
+                for (int k0 = 0; k0 < c0; k0 += 4) {          // T = C(:,p) - X(:, 0:c0) L(p rows, 0:c0)'
+                    const double a0 = -Cs[(k0 + fk) * LA + R0 + fr], a1 = -Cs[(k0 + fk) * LA + R0 + 8 + fr];
+                    const double b0 = Ls[(k0 + fk) * LA + c0 + fr], b1 = Ls[(k0 + fk) * LA + c0 + 8 + fr];
+                    dmma(t[0][0][0], t[0][0][1], a0, b0); dmma(t[0][1][0], t[0][1][1], a0, b1);
+                    dmma(t[1][0][0], t[1][0][1], a1, b0); dmma(t[1][1][0], t[1][1][1], a1, b1);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        double* p0 = Cs + (c0 + 8 * j + 2 * fk) * LA + R0 + 8 * i + fr;
+                        p0[0] = t[i][j][0]; p0[LA] = t[i][j][1];
+                    }
+                __syncwarp();
+                double x[2][2][2];                             // X(:,p) = T inv(L_pp)'
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) { x[i][j][0] = 0.0; x[i][j][1] = 0.0; }
+                const double* xd = Xd + p * PB * TC_XLD;
+#pragma unroll
+                for (int k0 = 0; k0 < PB; k0 += 4) {
+                    const double a0 = Cs[(c0 + k0 + fk) * LA + R0 + fr], a1 = Cs[(c0 + k0 + fk) * LA + R0 + 8 + fr];
+                    const double b0 = xd[fr * TC_XLD + k0 + fk], b1 = xd[(8 + fr) * TC_XLD + k0 + fk];
+                    dmma(x[0][0][0], x[0][0][1], a0, b0); dmma(x[0][1][0], x[0][1][1], a0, b1);
+                    dmma(x[1][0][0], x[1][0][1], a1, b0); dmma(x[1][1][0], x[1][1][1], a1, b1);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        double* p0 = Cs + (c0 + 8 * j + 2 * fk) * LA + R0 + 8 * i + fr;
+                        p0[0] = x[i][j][0]; p0[LA] = x[i][j][1];
+                        double* g0 = tile + (c0 + 8 * j + 2 * fk) * 64 + R0 + 8 * i + fr;
+                        g0[0] = x[i][j][0]; g0[64] = x[i][j][1];
+                    }
+                __syncwarp();
+            }
+        }
+        __syncthreads();                                      // orders every thread's tile stores before the release
+        if (tid == 0) st_release(D.flag + slot, epoch);
+        TC_STAMP(3)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward substitution L' x = y (y = the rhs row of the factor).  One task per tile column, taken
+// in descending elimination-tree level; block J waits for the blocks of the rows of its column.
+// ---------------------------------------------------------------------------------------------
+#define BW_LD 65
+__global__ void __launch_bounds__(TC_THREADS) k_tchol_bwd(TCholDev D, int epoch, double* __restrict__ xs) {
+    __shared__ double Ls[64 * BW_LD];
+    __shared__ double Xd[4 * 16 * 16];
+    __shared__ double yv[64], xv[64];
+    __shared__ int s_task;
+    const int tid = threadIdx.x;
+    const int nT = D.nT;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_task = atomicAdd(D.counters + 1, 1);
+        __syncthreads();
+        if (s_task >= nT) break;
+        const int J = D.bwdCols[s_task];
+        const int e0 = D.colPtr[J], e1 = D.colPtr[J + 1];
+        const int yslot = D.tix[(size_t)(nT - 1) * nT + J];
+        // y block: row 63 of the tile (nT-1, J); the rhs row itself solves to 0
+        if (tid < 64) yv[tid] = (J == nT - 1 && tid == 63) ? 0.0 : D.tiles[((size_t)yslot << 12) + tid * 64 + 63];
+        {   // diagonal tile and its inverse blocks (final since the factorisation kernel ended)
+            const double* gl = D.tiles + ((size_t)D.colSlot[e0] << 12);
+            for (int idx = tid; idx < 64 * 64; idx += TC_THREADS) Ls[(idx >> 6) * BW_LD + (idx & 63)] = gl[idx];
+            const double* gx = D.invD + (size_t)J * TC_XD;
+            for (int idx = tid; idx < 1024; idx += TC_THREADS) {
+                const int p = idx >> 8, a = (idx >> 4) & 15, b = idx & 15;
+                Xd[idx] = gx[p * PB * TC_XLD + a * TC_XLD + b];
+            }
+        }
+        const int c = tid >> 1, h = tid & 1;
+        double acc = 0.0;
+        double2 v[16];
+        bool have = false;
+        for (int e = e1 - 1; e > e0; --e) {                    // rows descending: highest level first
+            const int slot = D.colSlot[e];
+            const int I = D.slotI[slot];
+            if (!have) {
+                const double2* g = reinterpret_cast<const double2*>(D.tiles + ((size_t)slot << 12) + c * 64 + 32 * h);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = g[k];
+            }
+            if (tid == 0) { while (ld_acquire(D.xflag + I) != epoch) { __nanosleep(32); } }
+            __syncthreads();
+            if (tid < 64) xv[tid] = (I == nT - 1 && tid == 63) ? 0.0 : __ldcg(xs + (size_t)I * 64 + tid);
+            __syncthreads();
+            const double* xx = xv + 32 * h;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { acc = fma(v[k].x, xx[2 * k], acc); acc = fma(v[k].y, xx[2 * k + 1], acc); }
+            have = false;
+            if (e - 1 > e0) {                                   // prefetch the next tile before the next wait
+                const int s2 = D.colSlot[e - 1];
+                const double2* g = reinterpret_cast<const double2*>(D.tiles + ((size_t)s2 << 12) + c * 64 + 32 * h);
+#pragma unroll
+                for (int k = 0; k < 16; ++k) v[k] = g[k];
+                have = true;
+            }
+            __syncthreads();                                    // xv is reused
+        }
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        __syncthreads();
+        if (h == 0) yv[c] -= acc;
+        __syncthreads();
+        // L(J,J)' x = y by 16-blocks, last block first
+        for (int p = 3; p >= 0; --p) {
+            if (tid < 16) {                                     // x_p = inv(L_pp)' y_p
+                double s = 0.0;
+                for (int n2 = tid; n2 < 16; ++n2) s = fma(Xd[p * 256 + n2 * 16 + tid], yv[16 * p + n2], s);
+                xv[16 * p + tid] = s;
+            }
+            __syncthreads();
+            if (tid < 16 * p) {                                 // y(0:16p) -= L(p rows, 0:16p)' x_p
+                double s = 0.0;
+#pragma unroll
+                for (int r = 0; r < 16; ++r) s = fma(Ls[tid * BW_LD + 16 * p + r], xv[16 * p + r], s);
+                yv[tid] -= s;
+            }
+            __syncthreads();
+        }
+        if (tid < 64) xs[(size_t)J * 64 + tid] = xv[tid];
+        __syncthreads();
+        if (tid == 0) st_release(D.xflag + J, epoch);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small helpers on the tile array
+// ---------------------------------------------------------------------------------------------
+__global__ void k_tc_put_rhs(TCholDev D, const double* __restrict__ rhs) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= D.ld) return;
+    const int slot = D.tix[(size_t)(D.nT - 1) * D.nT + (s >> 6)];
+    D.tiles[((size_t)slot << 12) + (s & 63) * 64 + 63] = (s == D.ld - 1) ? 1e300 : rhs[s];
+}
+__global__ void k_tc_scale(TCholDev D, const double* __restrict__ dS) {
+    const int slot = blockIdx.x;
+    const int I = D.slotI[slot], J = D.slotJ[slot];
+    double* t = D.tiles + ((size_t)slot << 12);
+    for (int idx = threadIdx.x; idx < 4096; idx += blockDim.x) {
+        const int c = idx >> 6, r = idx & 63;
+        const int gr = 64 * I + r, gc = 64 * J + c;
+        if (gr == D.ld - 1) continue;                           // the rhs row is scaled when it is put
+        if (gr >= gc) t[idx] *= dS[gr] * dS[gc];
+    }
+}
+__global__ void k_tc_to_dense(TCholDev D, double* __restrict__ dense, int ldd) {
+    const int slot = blockIdx.x;
+    const int I = D.slotI[slot], J = D.slotJ[slot];
+    const double* t = D.tiles + ((size_t)slot << 12);
+    for (int idx = threadIdx.x; idx < 4096; idx += blockDim.x) {
+        const int c = idx >> 6, r = idx & 63;
+        const int gr = 64 * I + r, gc = 64 * J + c;
+        if (gr >= gc) dense[(size_t)gc * ldd + gr] = t[idx];
+    }
+}
+
+template <typename T>
+static int up(TChol& w, const T** dst, const std::vector<T>& v) {
+    T* p = nullptr;
+    if (cudaMalloc(&p, sizeof(T) * std::max<size_t>(1, v.size())) != cudaSuccess) return 1;
+    w.allocs.push_back(p);
+    if (!v.empty() && cudaMemcpy(p, v.data(), sizeof(T) * v.size(), cudaMemcpyHostToDevice) != cudaSuccess) return 1;
+    *dst = p;
+    return 0;
+}
+template <typename T>
+static int al(TChol& w, T** dst, size_t cnt, bool zero) {
+    T* p = nullptr;
+    if (cudaMalloc(&p, sizeof(T) * std::max<size_t>(1, cnt)) != cudaSuccess) return 1;
+    w.allocs.push_back(p);
+    if (zero && cudaMemset(p, 0, sizeof(T) * std::max<size_t>(1, cnt)) != cudaSuccess) return 1;
+    *dst = p;
+    return 0;
+}
+
+int tchol_alloc(TChol& w, const TileSym& sym) {
+    w.sym = sym;
+    const TileSym& s = w.sym;
+    TCholDev& d = w.d;
+    d.nT = s.nT; d.ld = s.ld; d.nSlots = s.nSlots; d.nSlotsS = s.nSlotsS; d.nTasks = s.nTasks;
+    int bad = 0;
+    bad |= up(w, &d.tix, s.tix);
+    bad |= up(w, &d.slotI, s.slotI); bad |= up(w, &d.slotJ, s.slotJ);
+    bad |= up(w, &d.colPtr, s.colPtr); bad |= up(w, &d.colSlot, s.colSlot);
+    bad |= up(w, &d.taskI, s.taskI); bad |= up(w, &d.taskJ, s.taskJ);
+    {
+        std::vector<long long> tp(s.termPtr.begin(), s.termPtr.end());
+        bad |= up(w, &d.termPtr, tp);
+    }
+    bad |= up(w, &d.termA, s.termA); bad |= up(w, &d.termB, s.termB);
+    bad |= up(w, &d.bwdCols, s.bwdCols);
+    {
+        std::vector<unsigned char> valid(s.ld);
+        for (int k = 0; k < s.ld; ++k) valid[k] = s.s2kind[k] == 1;
+        bad |= up(w, &d.valid, valid);
+    }
+    bad |= al(w, &d.tiles, (size_t)s.nSlots * TC_TT, true);
+    bad |= al(w, &d.invD, (size_t)s.nT * TC_XD, true);
+    bad |= al(w, &d.flag, (size_t)s.nSlots, true);
+    bad |= al(w, &d.xflag, (size_t)s.nT, true);
+    bad |= al(w, &d.counters, 4, true);
+    bad |= al(w, &d.info, 1, true);
+    bad |= al(w, &d.minmax, 2, true);
+    bad |= al(w, &w.xs, (size_t)s.ld, true);
+    if (bad) { tchol_free(w); return 1; }
+    w.epoch = 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int smem = TC_SMEM_DOUBLES * 8;
+    cudaFuncSetAttribute(k_tchol_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tchol_factor, TC_THREADS, smem);
+    if (occ < 1) occ = 1;
+    w.gridFactor = std::max(1, std::min(s.nTasks, sms * occ));
+    int occ2 = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_tchol_bwd, TC_THREADS, 0);
+    if (occ2 < 1) occ2 = 1;
+    w.gridBwd = std::max(1, std::min(s.nT, sms * occ2));
+    return 0;
+}
+void tchol_free(TChol& w) {
+    for (void* p : w.allocs) cudaFree(p);
+    w.allocs.clear();
+    w.d = TCholDev();
+    w.xs = nullptr;
+}
+void tchol_zero(TChol& w, cudaStream_t st) {
+    cudaMemsetAsync(w.d.tiles, 0, sizeof(double) * (size_t)w.d.nSlotsS * TC_TT, st);
+}
+void tchol_put_rhs(TChol& w, const double* rhs, cudaStream_t st) {
+    k_tc_put_rhs<<<(w.d.ld + 255) / 256, 256, 0, st>>>(w.d, rhs);
+    count_launch();
+}
+void tchol_factor(TChol& w, cudaStream_t st) {
+    ++w.epoch;
+    cudaMemsetAsync(w.d.counters, 0, sizeof(int) * 4, st);
+    cudaMemsetAsync(w.d.info, 0, sizeof(int), st);
+    static const unsigned long long init[2] = {0x7fefffffffffffffull, 0ull};      // DBL_MAX, 0
+    cudaMemcpyAsync(w.d.minmax, init, sizeof(init), cudaMemcpyHostToDevice, st);
+    k_tchol_factor<<<w.gridFactor, TC_THREADS, TC_SMEM_DOUBLES * 8, st>>>(w.d, w.epoch);
+    count_launch();
+}
+void tchol_solve(TChol& w, cudaStream_t st) {
+    k_tchol_bwd<<<w.gridBwd, TC_THREADS, 0, st>>>(w.d, w.epoch, w.xs);
+    count_launch();
+}
+void tchol_scale(TChol& w, const double* dS, cudaStream_t st) {
+    k_tc_scale<<<w.d.nSlotsS, 256, 0, st>>>(w.d, dS);
+    count_launch();
+}
+void tchol_to_dense(TChol& w, double* dense, int ldd, cudaStream_t st) {
+    k_tc_to_dense<<<w.d.nSlotsS, 256, 0, st>>>(w.d, dense, ldd);      // fill slots hold stale factors, S has no entries there
+    count_launch();
+}
+void tchol_pivot_stats(TChol& w, int* info, double* mn, double* mx, cudaStream_t st) {
+    unsigned long long mm[2] = {0, 0};
+    cudaMemcpyAsync(info, w.d.info, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(mm, w.d.minmax, sizeof(mm), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    double a, b;
+    memcpy(&a, &mm[0], 8); memcpy(&b, &mm[1], 8);
+    *mn = a; *mx = b;
+}

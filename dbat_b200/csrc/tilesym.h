@@ -1,0 +1,47 @@
+// tilesym.h — host-side symbolic analysis of the reduced camera system for the sparse tile Cholesky
+// (tilechol.cu).  SURVEY.md §8(f) N4: the reference factors the camera block densely
+// (code/bundle/bundle_cov.m:97); its ordering experiments are code/bundle/private/blkcolperm.m and
+// code/test/postcov/reorder_test.m.  Here the images are ordered by nested dissection (or reverse
+// Cuthill-McKee) on the co-visibility graph, the shared IO block and the right-hand side come last
+// ([OP; EO; IO] as in bundle_cov.m:76-84), and the factorisation works on 64 x 64 tiles of the
+// resulting sparse pattern.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#define TC_T 64                    // tile size
+#define TC_TT (TC_T * TC_T)
+
+struct TileSym {
+    int nT = 0;                    // tile rows / columns
+    int ld = 0;                    // order of the padded system = nT * TC_T; the last row carries the rhs
+    int nS = 0;                    // number of real unknowns in S (EO + IO columns)
+    int nSlots = 0, nSlotsS = 0;   // stored tiles; the first nSlotsS belong to the pattern of S itself (rest: fill)
+    int nTasks = 0, depth = 0;
+    int64_t nTerms = 0;
+    int order_mode = 0;            // 0 natural, 1 rcm, 2 nested dissection
+    int nSeg = 0;
+    std::vector<int> imgOrder;     // image ids in elimination order
+    std::vector<int> imgRank;      // inverse of imgOrder
+    std::vector<int> imgS;         // per image id: S index of its first estimated EO column (-1: none)
+    int ioS = 0;                   // S index of the first estimated shared IO column
+    std::vector<int> s2kind;       // per S index: 0 padding (identity), 1 unknown, 2 rhs row
+    std::vector<int> tix;          // nT x nT (row-major, [I * nT + J], I >= J): slot or -1
+    std::vector<int> slotI, slotJ; // tile coordinates of every slot
+    std::vector<int> colPtr, colSlot;   // per tile column: its slots, rows ascending (the diagonal tile first)
+    std::vector<int> taskI, taskJ;      // task list in execution (= priority) order
+    std::vector<int64_t> termPtr;       // nTasks + 1
+    std::vector<int> termA, termB;      // slots of L(I,k), L(J,k) for every term of every task
+    std::vector<int> level;             // elimination-tree level of every tile column
+    std::vector<int> bwdCols;           // tile columns for the backward substitution (descending level)
+};
+
+// adjacency of the co-visibility graph in CSR form (no self loops needed); nEO[i] = number of estimated
+// EO elements of image i (0..6); nIO = number of estimated shared IO columns.
+// mode: 0 natural, 1 rcm, 2 nested dissection, -1 automatic.
+int tile_symbolic(int nImg, const int64_t* adjPtr, const int32_t* adj, const int* nEO, int nIO, int mode,
+                  int leafImages, TileSym& out);
+
+// co-visibility graph from (0-based) point-major image lists
+void covis_graph(int nImg, int nOP, const int* pt_start, const int* img_pm, std::vector<int64_t>& adjPtr,
+                 std::vector<int32_t>& adj);

@@ -85,6 +85,11 @@ typedef struct dbat_problem_desc {
     int64_t nPriorIO, nPriorEO, nPriorOP;
     const int64_t *prior_x;       /* nPriorIO+nPriorEO+nPriorOP, 1-based                 */
     const double  *prior_val, *prior_std;
+    /* Optional: co-visibility edges (pairs of 1-based image indices that observe a common object point) of
+     * the WHOLE project.  A point-sharded problem (one rank of a multi-GPU run) sees only its own points, but
+     * every rank must order and tile the reduced camera system identically; nCovis == 0: use the local points. */
+    int64_t nCovis;
+    const int64_t *covis_a, *covis_b;
 } dbat_problem_desc;
 
 /* Optimiser constants; defaults are those hard-coded in bundle.m:281-283,301-304,321-325. */
@@ -160,6 +165,25 @@ int dbat_cov(dbat_handle *h, int which, double s0, double *out);
  * its ordering experiments are private/blkcolperm.m and test/postcov/reorder_test.m. */
 int dbat_camera_order(int64_t nImg, int64_t nOP, int64_t nObs, const int64_t *obs_img,
                       const int64_t *obs_op, int64_t *perm, int64_t *bandwidth);
+
+/* Symbolic analysis of the reduced camera system on its own (host only; tests and tools): elimination order
+ * of the images (mode 0 natural, 1 reverse Cuthill-McKee, 2 nested dissection, -1 automatic), 64 x 64 tile
+ * pattern with fill, task list of the data-flow factorisation.  nEO (nImg): estimated EO elements per image;
+ * counts (16) = {nT, ld, nS, nSlots, nSlotsS, nTasks, nTerms, depth, mode, nSeg, ioS}.  dbat_tile_symbolic_get
+ * copies the arrays of the last analysis (any pointer may be NULL): imgS (nImg), tix (nT*nT), taskIJ
+ * (2*nTasks), termPtr (nTasks+1), termAB (2*nTerms), level (nT), s2kind (ld), bwdCols (nT). */
+int dbat_tile_symbolic(int64_t nImg, int64_t nOP, int64_t nObs, const int64_t *obs_img, const int64_t *obs_op,
+                       const int64_t *nEO, int64_t nIO, int64_t mode, int64_t leafImages, int64_t *counts);
+int dbat_tile_symbolic_get(int64_t *imgS, int64_t *tix, int64_t *taskIJ, int64_t *termPtr, int64_t *termAB,
+                           int64_t *level, int64_t *s2kind, int64_t *bwdCols);
+
+/* The sparse tile solver on its own (unit tests / profiling): x = A^-1 b for a symmetric positive definite
+ * column-major n x n matrix whose 6-column blocks play the role of images (coupled where A has a non-zero),
+ * through the ordering, symbolic analysis and data-flow tile Cholesky the reduced camera system uses.
+ * mode as in dbat_tile_symbolic; stats (8, may be NULL) = {ms best of `repeat`, nT, nSlots, nTasks, nTerms,
+ * depth, min pivot, max pivot}. */
+int dbat_tile_chol_solve(int64_t n, const double *A, const double *b, double *x, int64_t mode, int64_t leafImages,
+                         int repeat, double *stats);
 
 /* The dense solver on its own (unit tests / profiling): x = A^-1 b for a symmetric positive
  * definite column-major n x n matrix through the same blocked FP64 Cholesky the reduced camera

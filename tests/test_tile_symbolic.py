@@ -1,0 +1,127 @@
+"""Host side of the sparse tile Cholesky (dbat_b200/csrc/tilesym.cu), checked on CPU.
+
+The symbolic analysis (elimination order of the images, 64 x 64 tile pattern with fill, task list of the
+data-flow factorisation) is executed here by a NumPy emulation of the device kernels' task semantics
+(tilechol.cu): tasks are run one after the other in LIST ORDER, and every tile a task reads must already be
+final - which is exactly the property that makes the persistent kernel deadlock-free.  The result must be
+the Cholesky factor of the permuted reduced system, and the backward substitution in `bwdCols` order must
+solve it.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from dbat_b200 import _lib
+from dbat_b200.synth import make_scene
+
+T = 64
+
+
+def _reduced_pattern_matrix(s, sym, rng):
+    """Random SPD matrix in S order with exactly the structure of the reduced camera system: 6 x 6 blocks of
+    co-visible images, dense IO rows, identity at padding positions."""
+    nImg = s.EO.val.shape[1]
+    ld = sym['ld']
+    nEO = s.bundle.est.EO[:6].sum(axis=0).astype(int)
+    A = sp.csr_matrix((np.ones(len(s.IP.img)), (s.IP.op, s.IP.img)))
+    G = (A.T @ A).tocoo()
+    S = np.zeros((ld, ld))
+    for a, b in zip(G.row, G.col):
+        if nEO[a] == 0 or nEO[b] == 0:
+            continue
+        ra = slice(sym['imgS'][a], sym['imgS'][a] + nEO[a])
+        rb = slice(sym['imgS'][b], sym['imgS'][b] + nEO[b])
+        S[ra, rb] = rng.normal(size=(nEO[a], nEO[b]))
+    kind = sym['s2kind']
+    io = np.arange(sym['ioS'], sym['ioS'] + 9)
+    S[io, :] = rng.normal(size=(9, ld)) * (kind == 1)[None, :]
+    S = np.tril(S) + np.tril(S, -1).T
+    S[kind != 1, :] = 0
+    S[:, kind != 1] = 0
+    S += np.diag(np.abs(S).sum(axis=1) + 1.0)            # diagonally dominant => SPD (padding: identity)
+    return S
+
+
+def _emulate(sym, S, rhs):
+    nT, ld = sym['nT'], sym['ld']
+    tix = sym['tix']
+    M = S.copy()
+    M[ld - 1, :] = rhs                                     # tchol_put_rhs
+    M[ld - 1, ld - 1] = 1e300
+    tiles, done = {}, set()
+    # every entry of the lower triangle must lie in a stored tile
+    r, c = np.nonzero(np.tril(M))
+    assert np.all(tix[r // T, c // T] >= 0)
+    for (I, J), t0, t1 in zip(sym['taskIJ'], sym['termPtr'][:-1], sym['termPtr'][1:]):
+        slot = tix[I, J]
+        assert slot >= 0 and slot not in done
+        C = M[I * T:(I + 1) * T, J * T:(J + 1) * T].copy() if slot < sym['nSlotsS'] else np.zeros((T, T))
+        if slot >= sym['nSlotsS']:
+            assert not M[I * T:(I + 1) * T, J * T:(J + 1) * T].any()      # a fill tile holds no entry of S
+        for a, b in sym['termAB'][t0:t1]:
+            assert a in done and b in done, 'task list is not a topological order'
+            C -= tiles[a] @ tiles[b].T
+        if I == J:
+            tiles[slot] = np.linalg.cholesky(np.tril(C) + np.tril(C, -1).T)
+        else:
+            d = tix[J, J]
+            assert d in done
+            tiles[slot] = np.linalg.solve(tiles[d], C.T).T
+        done.add(slot)
+    assert len(done) == sym['nSlots'] == sym['nTasks']
+    L = np.zeros((ld, ld))
+    for I in range(nT):
+        for J in range(I + 1):
+            if tix[I, J] >= 0:
+                L[I * T:(I + 1) * T, J * T:(J + 1) * T] = tiles[tix[I, J]]
+    # backward substitution in bwdCols order
+    y = L[ld - 1, :].copy()
+    y[ld - 1] = 0.0
+    x = np.zeros(ld)
+    xdone = set()
+    for J in sym['bwdCols']:
+        yj = y[J * T:(J + 1) * T].copy()
+        for I in range(J + 1, nT):
+            if tix[I, J] >= 0:
+                assert I in xdone, 'bwdCols is not a valid order'
+                xi = x[I * T:(I + 1) * T].copy()
+                if I == nT - 1:
+                    xi[T - 1] = 0.0
+                yj -= tiles[tix[I, J]].T @ xi
+        x[J * T:(J + 1) * T] = np.linalg.solve(tiles[tix[J, J]].T, yj)
+        xdone.add(J)
+    return L, x
+
+
+@pytest.mark.parametrize('nImg,nOP,rays,mode', [(21, 100, 10, -1), (60, 900, 8, 1), (420, 9000, 8, 2), (420, 9000, 8, 1),
+                                                (420, 9000, 8, 0)])
+def test_task_list_factors_the_reduced_system(built_lib, nImg, nOP, rays, mode):
+    s, _ = make_scene(nImg, nOP, rays=rays, seed=3, build_indices=False)
+    nEO = s.bundle.est.EO[:6].sum(axis=0).astype(int)
+    sym = _lib.tile_symbolic(s.IP.img, s.IP.op, nImg, nOP, nEO, 9, mode=mode, leaf=60)
+    assert sym['nS'] == nEO.sum() + 9 and sym['ld'] % T == 0 and sym['ld'] > sym['ioS'] + 9
+    assert (sym['s2kind'] == 1).sum() == sym['nS'] and sym['s2kind'][-1] == 2
+    if mode == 2:
+        assert sym['nSeg'] > 2 and sym['depth'] < sym['nT']        # independent subtrees shorten the chain
+    rng = np.random.default_rng(5)
+    S = _reduced_pattern_matrix(s, sym, rng)
+    ld = sym['ld']
+    rhs = rng.normal(size=ld) * (sym['s2kind'] == 1)
+    L, x = _emulate(sym, S, rhs)
+    n1 = ld - 1
+    np.testing.assert_allclose(L[:n1, :n1] @ L[:n1, :n1].T, S[:n1, :n1], rtol=0, atol=1e-9 * np.abs(S).max())
+    np.testing.assert_allclose(x[:n1], np.linalg.solve(S[:n1, :n1], rhs[:n1]), rtol=1e-9, atol=1e-12)
+
+
+def test_orderings_are_permutations_and_dissection_shortens_the_chain(built_lib):
+    s, _ = make_scene(600, 12000, rays=8, seed=11, build_indices=False)
+    nEO = s.bundle.est.EO[:6].sum(axis=0).astype(int)
+    res = {}
+    for mode in (0, 1, 2):
+        sym = _lib.tile_symbolic(s.IP.img, s.IP.op, 600, 12000, nEO, 9, mode=mode, leaf=60)
+        used = np.sort(np.concatenate([np.arange(a, a + k) for a, k in zip(sym['imgS'], nEO) if k > 0]))
+        assert len(np.unique(used)) == len(used) == nEO.sum()
+        assert np.all(sym['s2kind'][used] == 1)
+        res[mode] = sym
+    assert res[2]['depth'] < 0.7 * res[1]['depth']
+    assert res[1]['nTerms'] < res[0]['nTerms']                     # RCM beats the generator's order
