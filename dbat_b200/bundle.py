@@ -35,10 +35,11 @@ class Problem:
     sparse Jacobian) exactly like `[f,J]=feval(resFun,x)`.
     """
 
-    def __init__(self, s, points=None, cam_priors=True):
+    def __init__(self, s, points=None, cam_priors=True, covis=None):
         """points=(lo,hi): keep only object points lo..hi-1 and their observations (one shard of
         a point-partitioned multi-GPU run; x stays the global vector).  cam_priors=False drops
-        the IO/EO prior observations (they are counted on rank 0 only)."""
+        the IO/EO prior observations (they are counted on rank 0 only).  covis=(a, b): co-visibility edges
+        (0-based image pairs) of the whole project when `s` itself holds only one rank's points."""
         if s.bundle.serial is None or s.bundle.deserial is None:
             buildserialindices(s)
         L = _lib.lib()
@@ -97,12 +98,12 @@ class Problem:
         put('prior_val', np.concatenate(pv), 'd')
         put('prior_std', np.concatenate(ps), 'd')
         d.nCovis = 0
-        if points is not None:
+        if points is not None or covis is not None:
             # every rank must order and tile the reduced camera system identically: hand the library the
             # co-visibility graph of the whole project, not only of this shard's points
-            ca, cb = covisibility_edges(s.IP.img, s.IP.op, nImg, nOP)
-            put('covis_a', ca + 1, 'i')
-            put('covis_b', cb + 1, 'i')
+            ca, cb = covis if covis is not None else covisibility_edges(s.IP.img, s.IP.op, nImg, nOP)
+            put('covis_a', np.asarray(ca) + 1, 'i')
+            put('covis_b', np.asarray(cb) + 1, 'i')
             d.nCovis = len(ca)
         h = C.c_void_p()
         rc = L.dbat_create(C.byref(d), C.byref(h))
@@ -162,6 +163,15 @@ class Problem:
                                                 _lib.dptr(p), _lib.dptr(st)))
         return p, dict(f=st[0], jp2=st[1], rjp=st[2], singular=bool(st[3]), launches=int(st[4]),
                        f_new=st[5], device_ms=st[6])
+
+    def reduced_info(self):
+        """Structure of the reduced camera system (tile counts, factorisation work, chain depth)."""
+        v = np.zeros(16, dtype=np.int64)
+        self._check(_lib.lib().dbat_reduced_info(self._h, _lib.iptr(v)))
+        names = ['nT', 'ld', 'nS', 'nSlots', 'nSlotsS', 'nTasks', 'nTerms', 'depth', 'order_mode', 'nSeg', 'gridFactor', 'gridBwd']
+        d = {k: int(v[i]) for i, k in enumerate(names)}
+        d['flops'] = 2.0 * 64 ** 3 * d['nTerms'] + 64.0 ** 3 * (d['nSlots'] - d['nT']) + d['nT'] * 64.0 ** 3 / 3
+        return d
 
     def phase_times(self):
         names = (C.c_char_p * 16)()

@@ -82,8 +82,10 @@ struct dbat_handle {
     double* d_pack = nullptr;                 // packed lower triangle of S for the multi-rank allreduce
     double *d_tmpG = nullptr, *d_partial = nullptr, *d_scal = nullptr;
     double* h_scal = nullptr;           // pinned
+    double* h_G = nullptr;              // pinned: summed Gram of the last evaluation
     double *d_x = nullptr, *d_t = nullptr, *d_p = nullptr, *d_pgn = nullptr, *d_g = nullptr, *d_pc = nullptr;
     double *d_camDiag = nullptr, *d_camG = nullptr, *d_diagN = nullptr, *d_dscale = nullptr;
+    double *d_evalRed = nullptr, *d_prr = nullptr; size_t nEvalRed = 0;
     double *d_r = nullptr;              // m doubles (export)
     TChol tc;                           // sparse tile Cholesky of the reduced system (tilechol.cu)
     std::vector<int> h_x2s;             // x column (camera side) -> S index
@@ -408,8 +410,17 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     }
     const std::vector<int>& imgRank = h->tc.sym.imgRank;
     AL(P.chunkG, (size_t)std::max(1, P.nChunks) * DBAT_GSZ);
-    AL(P.imgG, (size_t)nImg * DBAT_GSZ);
-    AL(P.shG, DBAT_GSZ);
+    {   // per-image Grams, their sum, camera-side prior terms and the prior r'r in ONE buffer: a multi-rank
+        // evaluation sums it with a single allreduce
+        const size_t nCp = (size_t)std::max(1, nC);
+        h->nEvalRed = (size_t)nImg * DBAT_GSZ + DBAT_GSZ + 2 * nCp + 8;
+        AL(h->d_evalRed, h->nEvalRed);
+        P.imgG = h->d_evalRed;
+        P.shG = P.imgG + (size_t)nImg * DBAT_GSZ;
+        h->d_camDiag = P.shG + DBAT_GSZ;
+        h->d_camG = h->d_camDiag + nCp;
+        h->d_prr = h->d_camG + nCp;
+    }
     AL(P.pt, (size_t)std::max(1, nOP) * DBAT_PT_STRIDE);
     AL(P.W, (size_t)std::max(1, nObs) * DBAT_W_STRIDE);
     AL(P.rhs, P.ldS);
@@ -513,9 +524,10 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     AL(h->d_partial, nPartial);
     AL(h->d_scal, SC_N);
     AL(h->d_x, P.n); AL(h->d_t, P.n); AL(h->d_p, P.n); AL(h->d_pgn, P.n); AL(h->d_g, P.n); AL(h->d_pc, P.ldS);
-    AL(h->d_camDiag, std::max(1, nC)); AL(h->d_camG, std::max(1, nC)); AL(h->d_diagN, P.n); AL(h->d_dscale, P.n);
+    AL(h->d_diagN, P.n); AL(h->d_dscale, P.n);
     AL(h->d_r, h->m);
-    if (cudaMallocHost((void**)&h->h_scal, sizeof(double) * SC_N) != cudaSuccess)
+    if (cudaMallocHost((void**)&h->h_scal, sizeof(double) * SC_N) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_G, sizeof(double) * DBAT_GSZ) != cudaSuccess)
         return fail_create(h, DBAT_E_OOM, "cudaMallocHost failed");
     h->ev.resize(4096);
     for (auto& e : h->ev) cudaEventCreate(&e);
@@ -530,6 +542,7 @@ extern "C" void dbat_destroy(dbat_handle* h) {
     if (h->st) cudaStreamSynchronize(h->st);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_scal) cudaFreeHost(h->h_scal);
+    if (h->h_G) cudaFreeHost(h->h_G);
     tchol_free(h->tc);
     for (auto& e : h->ev) cudaEventDestroy(e);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -539,6 +552,14 @@ extern "C" void dbat_destroy(dbat_handle* h) {
 extern "C" const char* dbat_last_error(const dbat_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
 extern "C" int64_t dbat_num_unknowns(const dbat_handle* h) { return h ? h->P.n : 0; }
 extern "C" int64_t dbat_num_residuals(const dbat_handle* h) { return h ? h->m : 0; }
+extern "C" int dbat_reduced_info(const dbat_handle* h, int64_t* info) {
+    if (!h || !info) return DBAT_E_BADARG;
+    const TileSym& s = h->tc.sym;
+    const int64_t v[16] = {s.nT, s.ld, s.nS, s.nSlots, s.nSlotsS, s.nTasks, s.nTerms, s.depth, s.order_mode, s.nSeg,
+                           h->tc.gridFactor, h->tc.gridBwd, 0, 0, 0, 0};
+    memcpy(info, v, sizeof(v));
+    return DBAT_OK;
+}
 
 // --------------------------------------------------------------------------------------------
 // evaluation building blocks
@@ -574,19 +595,15 @@ static int eval_full(dbat_handle* h) {
     launch_point_side(h->P, h->st);
     launch_prior_apply(h->P, h->d_x, h->d_camDiag, h->d_camG, h->d_col2pt, h->st);
     // r'r = Gram(r,r) + prior rows
-    static double hG[DBAT_GSZ];
-    launch_prior_rr(h->P, h->d_x, h->d_partial, h->d_scal, SC_PRR, h->st);
+    double* hG = h->h_G;
+    launch_prior_rr(h->P, h->d_x, h->d_partial, h->d_prr, 0, h->st);
     if (h->nranks > 1) {
-        // camera-side sums are partial per rank (each rank holds a subset of the points)
-        int rc = allreduce(h, h->P.imgG, (size_t)h->P.nImg * DBAT_GSZ);
-        if (!rc) rc = allreduce(h, h->P.shG, DBAT_GSZ);
-        if (!rc) rc = allreduce(h, h->d_camDiag, h->P.nC);
-        if (!rc) rc = allreduce(h, h->d_camG, h->P.nC);
-        if (!rc) rc = allreduce(h, h->d_scal + SC_PRR, 1);
+        // camera-side sums are partial per rank (each rank holds a subset of the points): one allreduce
+        int rc = allreduce(h, h->d_evalRed, h->nEvalRed);
         if (rc) return rc;
     }
     cudaMemcpyAsync(hG, h->P.shG, sizeof(double) * DBAT_GSZ, cudaMemcpyDeviceToHost, h->st);
-    cudaMemcpyAsync(h->h_scal + SC_PRR, h->d_scal + SC_PRR, sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    cudaMemcpyAsync(h->h_scal + SC_PRR, h->d_prr, sizeof(double), cudaMemcpyDeviceToHost, h->st);
     ph_end(h, PH_EVAL, a);
     cudaStreamSynchronize(h->st);
     h->h_scal[SC_RR] = gram_host(hG, DBAT_COL_R, DBAT_COL_R) + h->h_scal[SC_PRR];
@@ -644,6 +661,18 @@ static int dev_dot(dbat_handle* h, const double* a, const double* b, int n, doub
     if (cudaStreamSynchronize(h->st) != cudaSuccess) { h->err = "dot failed"; return DBAT_E_CUDA; }
     *out = h->h_scal[SC_A];
     return 0;
+}
+
+// With several ranks a rank owns the camera part of x and its own points; the entries of other ranks' points in an
+// uploaded vector are zeroed so that norms and dot products add up over the ranks.
+__global__ void k_mask_unowned(double* __restrict__ x, const int* __restrict__ col2pt, int nC, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (nC + k < n && col2pt[k] < 0) x[nC + k] = 0.0;
+}
+static void mask_unowned(dbat_handle* h, double* x) {
+    if (h->nranks <= 1 || h->P.n <= h->P.nC) return;
+    k_mask_unowned<<<(h->P.n - h->P.nC + 255) / 256, 256, 0, h->st>>>(x, h->d_col2pt, h->P.nC, h->P.n);
+    count_launch();
 }
 
 // Solve the (damped, optionally Jacobi-scaled) normal equations at d_x -> step in `pout`.
@@ -792,7 +821,7 @@ extern "C" int dbat_normal_step(dbat_handle* h, const double* x, double lambda, 
     if (!h) return DBAT_E_BADARG;
     ph_reset(h);
     const size_t tot = ph_begin(h);
-    if (x) { CK(cudaMemcpyAsync(h->d_x, x, sizeof(double) * h->P.n, cudaMemcpyHostToDevice, h->st)); h->cscWeighted = -1; }
+    if (x) { CK(cudaMemcpyAsync(h->d_x, x, sizeof(double) * h->P.n, cudaMemcpyHostToDevice, h->st)); h->cscWeighted = -1; mask_unowned(h, h->d_x); }
     const int64_t l0 = g_dbat_launches;
     int rc = eval_full(h);
     if (rc) return rc;
@@ -949,7 +978,9 @@ static int solve_lm(dbat_handle* h, const dbat_opts* o, dbat_result* res, TraceO
             int sing = 0;
             if ((rc = solve_step(h, lambda, false, h->d_p, &sing))) return rc;   // :119
             if (res->nRr < cap + 1) res->rr[res->nRr++] = std::sqrt(rr);      // :122
-            if (n == 0 && structurally_deficient(h)) { code = -4; break; }   // :126-135
+            if (n == 0 && structurally_deficient(h)) {                // :126-135 (p = NaN)
+                code = -4; cudaMemsetAsync(h->d_p, 0xff, sizeof(double) * nn, h->st); break;
+            }
             if (res->nDamping < cap + 1) res->damping[res->nDamping++] = lambda;   // :136
             if (o->doTrace) printf("Levenberg-Marquardt: iteration %d, residual norm=%.2g, lambda=%.2g\n", n, std::sqrt(rr), lambda);
             T.store_x(h, n);                                          // :149-156
@@ -1090,7 +1121,9 @@ static int solve_lmp(dbat_handle* h, const dbat_opts* o, dbat_result* res, Trace
     int ntr = 0;
     while (true) {
         if (res->nRr < cap + 1) res->rr[res->nRr++] = std::sqrt(rr);  // :109
-        if (n == 0 && structurally_deficient(h)) { code = -4; break; }   // :113-122
+        if (n == 0 && structurally_deficient(h)) {                    // :113-122 (p = NaN)
+            code = -4; cudaMemsetAsync(h->d_p, 0xff, sizeof(double) * nn, h->st); break;
+        }
         // dogleg (:232-335)
         int sing = 0, step = 0;
         if ((rc = solve_step(h, 0.0, true, h->d_pgn, &sing))) return rc;
@@ -1140,7 +1173,7 @@ static int solve_lmp(dbat_handle* h, const dbat_opts* o, dbat_result* res, Trace
         if (res->rhos && res->nRhos < cap) res->rhos[res->nRhos] = rho;
         res->nRhos++;
         if (o->doTrace) printf("Levenberg-Marquardt-Powell: iteration %d, residual norm=%.2g, delta=%.2g, step=%d, rho=%.1f\n", n, std::sqrt(rr), delta, step, rho);
-        if (rho <= o->mu || !(rho == rho)) {                          // :166-179
+        if (rho <= o->mu) {                                           // :166-179 (a NaN rho is not <= mu: accepted, like the reference)
             delta = delta / 2;
             if (delta > npGN) delta = delta / std::exp2(std::ceil(std::log2(delta / npGN)));
         } else {                                                      // :180-195
@@ -1164,7 +1197,11 @@ extern "C" int dbat_solve(dbat_handle* h, int method, const dbat_opts* opts, con
     if (!h || !opts || !x0 || !res || !res->x || !res->rr || !res->damping) return DBAT_E_BADARG;
     const int nn = h->P.n;
     CK(cudaMemcpyAsync(h->d_x, x0, sizeof(double) * nn, cudaMemcpyHostToDevice, h->st));
+    mask_unowned(h, h->d_x);
     CK(cudaMemsetAsync(h->d_p, 0, sizeof(double) * nn, h->st));
+    CK(cudaMemsetAsync(h->d_pgn, 0, sizeof(double) * nn, h->st));
+    CK(cudaMemsetAsync(h->d_g, 0, sizeof(double) * nn, h->st));
+    CK(cudaMemsetAsync(h->d_t, 0, sizeof(double) * nn, h->st));
     h->cscWeighted = -1; h->params_valid = false; h->normal_valid = false;
     ph_reset(h);
     const int64_t l0 = g_dbat_launches;

@@ -40,6 +40,26 @@ def exchange_unique_id(rank, make_id, dist=None):
     return bytes(buf.cpu().numpy().tobytes())
 
 
+def gather_unique_keys(keys, dist=None):
+    """Sorted union over all ranks of an int64 key array (variable length per rank)."""
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    world = dist.get_world_size()
+    dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' else torch.device('cpu')
+    keys = np.unique(np.asarray(keys, dtype=np.int64))
+    cnt = torch.tensor([len(keys)], dtype=torch.int64, device=dev)
+    cnts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    m = int(max(int(c.item()) for c in cnts))
+    buf = torch.full((max(1, m),), -1, dtype=torch.int64, device=dev)
+    buf[:len(keys)] = torch.from_numpy(keys).to(dev)
+    bufs = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf)
+    allk = torch.cat(bufs).cpu().numpy()
+    return np.unique(allk[allk >= 0])
+
+
 class ShardedProblem(Problem):
     """Rank-local shard of a point-partitioned problem; x/p vectors keep the global layout.
 
@@ -47,11 +67,23 @@ class ShardedProblem(Problem):
     rank; `gather` merges them.
     """
 
-    def __init__(self, s, rank, world):
+    def __init__(self, s, rank, world, local=False):
+        """local=False: `s` is the whole project, this rank takes its share of the object points.
+        local=True: `s` already holds only this rank's object points and observations (cameras and IO are
+        the same on every rank; x is [IO; EO; this rank's OP]): nothing of the whole project ever has to
+        exist on one host.  The co-visibility graph is then gathered over the ranks."""
         import torch.distributed as dist
-        self.rank, self.world = rank, world
-        parts = partition_points(s.IP.op, s.OP.val.shape[1], world)
-        super().__init__(s, points=parts[rank], cam_priors=(rank == 0))
+        self.rank, self.world, self.local = rank, world, local
+        if local:
+            from .bundle import covisibility_edges
+            nImg, nOP = s.EO.val.shape[1], s.OP.val.shape[1]
+            ca, cb = covisibility_edges(s.IP.img, s.IP.op, nImg, nOP)
+            key = gather_unique_keys(ca * nImg + cb, dist)
+            super().__init__(s, cam_priors=(rank == 0), covis=(key // nImg, key % nImg))
+            parts = None
+        else:
+            parts = partition_points(s.IP.op, s.OP.val.shape[1], world)
+            super().__init__(s, points=parts[rank], cam_priors=(rank == 0))
         self.parts = parts
         L = _lib.lib()
 
@@ -65,8 +97,11 @@ class ShardedProblem(Problem):
         uid = exchange_unique_id(rank, make_id, dist)
         self._check(L.dbat_comm_init(self._h, world, rank, C.create_string_buffer(uid, 128)))
         des = s.bundle.deserial.OP
-        lo, hi = parts[rank]
-        self.own_cols = des.src[(des.dest >= 3 * lo) & (des.dest < 3 * hi)]
+        if local:
+            self.own_cols = des.src
+        else:
+            lo, hi = parts[rank]
+            self.own_cols = des.src[(des.dest >= 3 * lo) & (des.dest < 3 * hi)]
 
     def gather(self, v):
         """Merge a per-rank vector in x layout: camera part from any rank, point part from owners."""

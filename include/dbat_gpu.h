@@ -166,6 +166,11 @@ int dbat_cov(dbat_handle *h, int which, double s0, double *out);
 int dbat_camera_order(int64_t nImg, int64_t nOP, int64_t nObs, const int64_t *obs_img,
                       const int64_t *obs_op, int64_t *perm, int64_t *bandwidth);
 
+/* Structure of the reduced camera system of a problem: info (16) = {nT (64 x 64 tile rows), ld, nS (camera-side
+ * unknowns), nSlots (stored tiles incl. fill), nSlotsS (tiles of S itself), nTasks, nTerms (tile products per
+ * factorisation), depth (longest dependency chain in tile columns), order mode, segments, ...}. */
+int dbat_reduced_info(const dbat_handle *h, int64_t *info);
+
 /* Symbolic analysis of the reduced camera system on its own (host only; tests and tools): elimination order
  * of the images (mode 0 natural, 1 reverse Cuthill-McKee, 2 nested dissection, -1 automatic), 64 x 64 tile
  * pattern with fill, task list of the data-flow factorisation.  nEO (nImg): estimated EO elements per image;
