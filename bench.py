@@ -1,18 +1,18 @@
 #!/usr/bin/env python
 """bench.py — LM iterations/s of the bundle-adjustment hot path on B200 (BASELINE.json metric).
 
-A "step" is one Levenberg-Marquardt iteration (levenberg_marquardt.m:117-206) on the
-synthetic self-calibration scene of BASELINE config 4 (1000 cameras x 200k points x 2M
-observations, shared Brown IO, depend datum): residual + Jacobian + normal-equation
-assembly, damped Schur reduction, dense FP64 Cholesky of the 6002-order reduced system,
-back-substitution, |Jp| statistics and the trial-point residual.  Accepted trial points are
-taken, so successive steps walk the real LM path.
+A "step" is one Levenberg-Marquardt iteration (levenberg_marquardt.m:117-206): residual + Jacobian +
+normal-equation assembly, damped Schur reduction onto the camera system, sparse tile Cholesky of the
+reduced system (FP64 DMMA), back-substitution, |Jp| statistics and the trial-point residual.  Accepted
+trial points are taken, so successive steps walk the real LM path.
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-N>1 (torchrun, one rank per GPU): points are sharded across ranks (weak scaling: 200k points
-and 2M observations per rank over the same 1000 cameras), reduced system combined by NCCL
-allreduce; value counts 2M-observation equivalents so it aggregates over ranks.
+N = 1: BASELINE config 4 (1000 cameras x 200k points x 2M observations, shared Brown IO, depend datum).
+N > 1 (torchrun, one rank per GPU): the block grows with N like BASELINE config 5 - 1000 cameras, 200k
+points and 2M observations PER RANK (N = 8: 8000 x 1.6M x 16M; config 5 itself is 10k x 4M x 40M) - so the
+reduced camera system and its collective grow with N; every rank generates only its own points.  `value`
+counts 2M-observation equivalents, i.e. it aggregates over ranks (weak scaling).
 """
 import argparse
 import json
@@ -28,11 +28,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 C4 = dict(nImg=1000, nOP=200000, rays=10)
-ALG_BYTES = {   # algorithmic HBM bytes per observation (DESIGN.md "Kernels")
-    'k_cam_side': 64.0,      # uv 16 + isig 16 + pt idx 4 + (img via chunk) + point gather 24 + chunk partials ~4
-    'k_point_side': 64.0 + 144.0 + 41.6,   # reads as above, writes W_o 144 B/obs + point record 416 B/pt (10 rays)
-    'k_resid': 64.0,
-    'k_jp': 64.0 + 24.0,
+UNIT = 'LM iterations/s (2M-observation equivalents)'
+# algorithmic HBM bytes per observation: what the kernel has to move at least
+ALG_BYTES = {
+    'cam_side': 64.0,                       # uv 16 + 1/sigma 16 + indices 8 + point gather 24
+    'point_side': 64.0 + 144.0 + 41.6,      # reads as above; writes W_o 144 B/obs + point record 416 B/point
+    'resid': 64.0,
+    'jp': 64.0 + 24.0,
+    'schur': 144.0 + 41.6,                  # W_o + point records read once
+    'backsub': 144.0 + 41.6 + 2.4,          # W_o + records read, 24 B/point written
 }
 
 
@@ -42,9 +46,10 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
-    ap.add_argument('--nimg', type=int, default=C4['nImg'])
-    ap.add_argument('--nop', type=int, default=C4['nOP'])
+    ap.add_argument('--nimg', type=int, default=0, help='cameras (default 1000 per rank)')
+    ap.add_argument('--nop', type=int, default=C4['nOP'], help='object points per rank')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ref-budget', type=float, default=420.0, help='wall seconds for the reference arm')
     return ap.parse_args()
 
 
@@ -97,73 +102,85 @@ class ClockSampler(threading.Thread):
                 'reasons': reasons, 'samples': len(rows)}
 
 
-def cpu_lm_iteration_sample(nImg=100, nOP=20000, iters=2):
-    """Reference CPU path (oracle port of levenberg_marquardt.m: sparse J, J'J, sparse solve of the
-    FULL damped system) on a bounded 1/10-scale sample of the workload.  Returns (it/s, desc)."""
+# ------------------------------------------------------------------------------------------------
+# reference CPU path
+# ------------------------------------------------------------------------------------------------
+CPU_DESC = ("oracle port of levenberg_marquardt.m:76-82,117-206 on the host cores: sparse Jacobian as multi_res.m "
+            "builds it (SciPy CSC), J'J by sparse product, (J'J+lambda I)\\(-J'r) as MATLAB's CHOLMOD would order it "
+            "(3x3 point blocks first, dense LAPACK Cholesky of the camera front: oracle.lsa.solve_spd_pointfirst), "
+            "trial residual; no MATLAB/Octave exists in this image")
+
+
+def cpu_lm_iterations(s, max_iters, budget_s):
+    """LM iterations of the reference CPU algorithm on scene `s` until `max_iters` or the wall budget.
+    Returns (iterations done, seconds)."""
     import scipy.sparse as sp
-    from dbat_b200.synth import make_scene
     from oracle import lsa
     from oracle.cameramodel import brown_euler_cam4
     from oracle.dbatstruct import buildweightmatrix, serialize
-    s, _ = make_scene(nImg, nOP, rays=10)
     x = serialize(s)
     R = np.sqrt(buildweightmatrix(s))
-    nOPx = len(s.bundle.serial.OP.dest)
-    lsa.set_ordering(np.concatenate([np.arange(len(x) - nOPx, len(x)), np.arange(len(x) - nOPx)[::-1]]))
-    I = sp.identity(len(x), format='csc')
+    n = len(x)
+    nC = n - len(s.bundle.serial.OP.dest)
+    I = sp.identity(n, format='csc')
+    done = 0
     t0 = time.perf_counter()
-    for _ in range(iters):
+    while done < max_iters:
         f, J = brown_euler_cam4(x, s, True)
         r = R * f
         Jw = (sp.diags(R) @ J).tocsc()
         N = (Jw.T @ Jw).tocsc()
         g = Jw.T @ r
-        p, _ = lsa._solve_spd(N + 1e-10 * N.diagonal().sum() / len(x) * I, -g)
-        Jp = Jw @ p
+        lam = 1e-10 * N.diagonal().sum() / n if done == 0 else 0.0          # levenberg_marquardt.m:88-106,181
+        p = lsa.solve_spd_pointfirst(N + lam * I, -g, nC)
+        Jp = Jw @ p                                                          # :162
         fNew = brown_euler_cam4(x + p, s, False)[0]
         if np.sum((R * fNew) ** 2) < r @ r:
             x = x + p
-    dt = time.perf_counter() - t0
-    nobs = len(s.IP.img)
-    return iters / dt, nobs, ('%d LM iterations of the oracle (SciPy sparse J, J\'J, SuperLU solve of the full '
-                              'damped system) on a %d-camera x %d-point x %d-observation scene of the same '
-                              'generator' % (iters, nImg, nOP, nobs))
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    return done, time.perf_counter() - t0
+
+
+def workload_name(nImg, nOP, nObs, n, nRed):
+    return ('BASELINE config 4: synthetic %d cameras x %d points x %d observations, shared IO + Brown '
+            'self-calibration (model 3), LM iteration; n=%d unknowns, reduced order %d' % (nImg, nOP, nObs, n, nRed))
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU algorithm (oracle port; no MATLAB/Octave exists
-    here) on the host cores, bounded sample of the same workload."""
+    """--impl reference: the reference's own CPU algorithm on THE SAME scene as the GPU arm at N=1 (config 4
+    itself, no scaled-down sample).  One LM iteration costs tens of seconds on the host, so the arm runs as many
+    of the K requested iterations as fit a wall budget (at least one) and reports how many it timed."""
     if rank != 0:
         return
-    steps = max(1, args.steps)
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_lm_iteration_sample(20, 2000, 1)
-    nI, nP = (100, 20000) if args.nimg >= 100 else (args.nimg, args.nop)
-    t0 = time.perf_counter()
-    its, nobs, desc = cpu_lm_iteration_sample(nI, nP, steps)
-    dt = time.perf_counter() - t0
-    # 2M-observation equivalents, same unit as the GPU arm
+    from dbat_b200.synth import make_scene
+    nImg = args.nimg or C4['nImg']
+    s, _ = make_scene(nImg, args.nop, rays=C4['rays'], cache_dir=os.environ.get('DBAT_SCENE_CACHE', '/tmp'))
+    nobs = len(s.IP.img)
+    n = s.bundle.serial.n
+    done, dt = cpu_lm_iterations(s, max(1, args.steps), args.ref_budget)
+    its = done / dt
     value = its * nobs / 2.0e6
     cores = os.cpu_count() or 1
     line = {
-        'impl': 'reference', 'metric': 'lm_iterations_per_s', 'value': value,
-        'unit': 'LM iterations/s (2M-observation equivalents)', 'n_gpus': 0, 'steps': steps,
-        'warmup': args.warmup, 'ms_per_step': 1e3 / its, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'synthetic self-calibration LM, 1/10-scale sample of BASELINE config 4 '
-                               '(%d cameras x %d points x %d observations); value scaled by observations/2M'
-                               % (nI, nP, nobs)},
-        'cpu_baseline': {'value': value, 'unit': 'LM iterations/s (2M-observation equivalents)',
-                         'cores': cores, 'kind': 'port', 'sample': desc},
-        'e2e': {'value': value, 'unit': 'LM iterations/s (2M-observation equivalents)',
-                'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'impl': 'reference', 'metric': 'lm_iterations_per_s', 'value': value, 'unit': UNIT, 'n_gpus': 0,
+        'steps': done, 'steps_requested': args.steps, 'warmup': 0, 'ms_per_step': 1e3 / its,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': workload_name(nImg, args.nop, nobs, n, n - 3 * args.nop),
+                   'same_config': True,
+                   'note': 'full config, %d of %d requested iterations inside the %.0f s budget' % (done, args.steps, args.ref_budget)},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '%d full LM iterations on the config itself; %s' % (done, CPU_DESC)},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0, 'seconds': dt,
     }
     print(json.dumps(line), flush=True)
 
 
 def fp64_peak_tflops():
-    """cuBLAS DGEMM yardstick for the FP64 tensor pipe (MEASURED_PEAKS.json has no FP64 figure)."""
+    """cuBLAS DGEMM yardstick for the FP64 tensor pipe (MEASURED_PEAKS.json has no FP64 figure): best of 3
+    runs of an 8192^3 torch.matmul, the method fixed since round 1 so that fractions stay comparable."""
     import torch
     n = 8192
     a = torch.randn(n, n, dtype=torch.float64, device='cuda')
@@ -203,18 +220,27 @@ def main():
         dist.barrier()
     import dbat_b200
     from dbat_b200.parallel import ShardedProblem
-    from dbat_b200.synth import make_scene
+    from dbat_b200.synth import make_scene, make_scene_shard
 
-    # scene: config 4 per rank (weak scaling over points; the same 1000 stations)
-    nImg, nOP = args.nimg, args.nop * world
-    s, _ = make_scene(nImg, nOP, rays=C4['rays'], cache_dir=os.environ.get('DBAT_SCENE_CACHE', '/tmp'))
-    nObsGlobal = len(s.IP.img)
-    x0 = dbat_b200.serialize(s)
+    nImg = args.nimg or C4['nImg'] * world
+    nOP = args.nop * world
     if world > 1:
-        P = ShardedProblem(s, rank, world)
+        # every rank generates its own share of the points; the cameras are the same everywhere
+        s, _ = make_scene_shard(nImg, nOP, rank, world, rays=C4['rays'])
+        P = ShardedProblem(s, rank, world, local=True)
+        nObsLocal = len(s.IP.img)
+        t = torch.tensor([nObsLocal], dtype=torch.float64, device='cuda')
+        dist.all_reduce(t)
+        nObsGlobal = int(t.item())
     else:
+        s, _ = make_scene(nImg, nOP, rays=C4['rays'], cache_dir=os.environ.get('DBAT_SCENE_CACHE', '/tmp'))
         P = dbat_b200.Problem(s)
+        nObsLocal = nObsGlobal = len(s.IP.img)
+    x0 = dbat_b200.serialize(s)
     n = P.n
+    nRed = n - 3 * s.OP.val.shape[1]
+    nGlobal = nRed + 3 * nOP
+    info = P.reduced_info()
 
     # pinned host buffers for the end-to-end leg
     xh = torch.empty(n, dtype=torch.float64).pin_memory()
@@ -271,69 +297,71 @@ def main():
     its = args.steps / (dev_total * 1e-3)
     value = its * equiv
     e2e_value = args.steps / wall_e2e * equiv
+    if world == 1:
+        wl = workload_name(nImg, nOP, nObsGlobal, n, nRed)
+    else:
+        wl = ('BASELINE config 5 shape at %d/10 scale per axis: synthetic %d cameras x %d points x %d observations '
+              '(1000 x 200k x 2M per rank), shared IO + Brown self-calibration (model 3), LM iteration; n=%d '
+              'unknowns, reduced order %d' % (world, nImg, nOP, nObsGlobal, nGlobal, nRed))
+    sbytes = info['nSlotsS'] * 4096 * 8
     line = {
-        'metric': 'lm_iterations_per_s', 'value': value,
-        'unit': 'LM iterations/s (2M-observation equivalents)', 'n_gpus': world, 'steps': args.steps,
+        'metric': 'lm_iterations_per_s', 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': dev_total / args.steps, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE config 4: synthetic %d cameras x %d points x %d observations, shared IO '
-                               '+ Brown self-calibration (model 3), LM iteration; n=%d unknowns, reduced order %d'
-                               % (nImg, nOP, nObsGlobal, n, n - 3 * nOP),
-                   'l2': 'inputs (>600 MB of observation, cross-block and reduced-system arrays) exceed the 126 MB L2',
+        'config': {'workload': wl,
+                   'l2': 'inputs (>600 MB of observation, cross-block and reduced-system arrays per rank) exceed the 126 MB L2',
                    'timing': 'CUDA events on the library stream around each step (max over ranks); wall '
                              'clock %.3f ms/step' % (1e3 * wall / args.steps),
-                   'parallelism': 'points sharded over %d rank(s), NCCL allreduce of the reduced system' % world},
-        'e2e': {'value': e2e_value, 'unit': 'LM iterations/s (2M-observation equivalents)',
-                'h2d_bytes_per_step': 8 * n, 'd2h_bytes_per_step': 8 * n + 64},
+                   'parallelism': ('single GPU' if world == 1 else
+                                   'points sharded over %d ranks; per solve one ncclAllReduce of the %d tiles of the '
+                                   'reduced system (%.1f MB) + rhs, per evaluation one of the per-image Grams; '
+                                   'factorisation replicated' % (world, info['nSlotsS'], sbytes / 1e6)),
+                   'reduced_system': {k: info[k] for k in ('nT', 'nSlots', 'nSlotsS', 'nTasks', 'nTerms', 'depth', 'order_mode', 'nSeg')}},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 8 * n * world, 'd2h_bytes_per_step': (8 * n + 64) * world},
         'gpu_launches': int(launches),
         'clocks': sampler.summary(),
         'phases_ms_last_step': {k: v[0] for k, v in phases.items()},
     }
-    # roofline of the dominant kernel family of the step
+    # rooflines: every kernel family of the step against its bound; the dominant one is the headline entry
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        hbm_peak, peak_src = float(peaks['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        hbm_peak, peak_src = float(peaks['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
     except Exception:
         hbm_peak, peak_src = 6650.0, 'fallback (B200_PROFILING.md)'
-    nRed = n - 3 * nOP
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'r2_dram_traffic.json')))
+    except Exception:
+        traffic = {}
     ph_ms = {k: v[0] for k, v in phases.items() if k != 'total'}
+    fp64 = fp64_peak_tflops()
+    roofs = {}
+    if ph_ms.get('cholesky', 0) > 0:
+        ach = info['flops'] / (ph_ms['cholesky'] * 1e-3) / 1e12
+        roofs['cholesky'] = {'bound': 'tensor', 'achieved': ach, 'peak': fp64, 'unit': 'TFLOP/s', 'frac': ach / fp64,
+                             'traffic': traffic.get('k_tchol_factor') if world == 1 else None,
+                             'kernel': 'k_tchol_factor (sparse tile Cholesky, DMMA; %.2f useful GFLOP per factorisation: '
+                                       '%d tile products + %d triangular solves + %d 64x64 factorisations; the dense '
+                                       'factorisation of the same system would be %.1f GFLOP)'
+                                       % (info['flops'] / 1e9, info['nTerms'], info['nSlots'] - info['nT'], info['nT'], nRed ** 3 / 3e9),
+                             'peak_source': 'cuBLAS DGEMM 8192^3 measured in this run (FP64; MEASURED_PEAKS.json holds no FP64 figure)',
+                             'limit': 'dependency chain of %d tile columns, not the tensor pipe' % info['depth']}
+    for phn, (b, kern) in {'eval_jac_assembly': (ALG_BYTES['cam_side'] + ALG_BYTES['point_side'], 'k_cam_side+k_point_side'),
+                           'trial_residual': (ALG_BYTES['resid'], 'k_resid'),
+                           'jp_stats': (ALG_BYTES['jp'], 'k_jp'),
+                           'build_schur': (ALG_BYTES['schur'], 'k_schur_group')}.items():
+        if ph_ms.get(phn, 0) > 0:
+            g = b * nObsLocal / (ph_ms[phn] * 1e-3) / 1e9
+            roofs[phn] = {'bound': 'hbm', 'achieved': g, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': g / hbm_peak,
+                          'traffic': traffic.get(kern) if world == 1 else None, 'kernel': kern, 'bytes_per_obs': b,
+                          'ms': ph_ms[phn], 'peak_source': peak_src}
     dom = max(ph_ms, key=ph_ms.get) if ph_ms else 'cholesky'
     line['dominant_phase'] = dom
-    if dom == 'cholesky':
-        fp64 = fp64_peak_tflops()
-        ach = (nRed ** 3 / 3.0) / (ph_ms['cholesky'] * 1e-3) / 1e12
-        # DRAM bytes of one factorisation from the ncu capture profiles/chol_factor_n6002_dram.csv
-        # (dram__bytes_read.sum + dram__bytes_write.sum over its k_potrf128 / k_gemm_nt launches, cold
-        # caches): known for the config-4 size only
-        traffic = 3.306e9 if nRed == 6002 else None
-        line['roofline'] = {'bound': 'tensor', 'achieved': ach, 'peak': fp64, 'unit': 'TFLOP/s',
-                            'frac': ach / fp64, 'traffic': traffic,
-                            'kernel': 'k_gemm_nt (DMMA blocked Cholesky, %d^3/3 flop per factorisation)' % nRed,
-                            'peak_source': 'cuBLAS DGEMM 8192^3 measured in this run (FP64; MEASURED_PEAKS.json '
-                                           'holds no FP64 figure)'}
-    else:
-        nobs_rank = nObsGlobal / world
-        key, kern = {'eval_jac_assembly': (ALG_BYTES['k_cam_side'] + ALG_BYTES['k_point_side'], 'k_cam_side+k_point_side'),
-                     'trial_residual': (ALG_BYTES['k_resid'], 'k_resid'),
-                     'jp_stats': (ALG_BYTES['k_jp'], 'k_jp')}.get(dom, (144.0 + 41.6, 'k_schur'))
-        ach = key * nobs_rank / (ph_ms.get(dom, 1.0) * 1e-3) / 1e9
-        line['roofline'] = {'bound': 'hbm', 'achieved': ach, 'peak': hbm_peak, 'unit': 'GB/s',
-                            'frac': ach / hbm_peak, 'traffic': None, 'kernel': kern, 'peak_source': peak_src}
-    # HBM view of the streaming kernels (explains the step; algorithmic bytes per observation)
-    nobs_rank = nObsGlobal / world
-    hbm = {}
-    for phn, (b, kern) in {'eval_jac_assembly': (ALG_BYTES['k_cam_side'] + ALG_BYTES['k_point_side'], 'k_cam_side+k_point_side'),
-                           'trial_residual': (ALG_BYTES['k_resid'], 'k_resid'),
-                           'jp_stats': (ALG_BYTES['k_jp'], 'k_jp')}.items():
-        if phn in ph_ms and ph_ms[phn] > 0:
-            g = b * nobs_rank / (ph_ms[phn] * 1e-3) / 1e9
-            hbm[kern] = {'GB/s': g, 'frac_of_measured_hbm': g / hbm_peak, 'ms': ph_ms[phn], 'bytes_per_obs': b}
-    line['hbm_streams'] = hbm
+    line['roofline'] = roofs.get(dom, roofs.get('cholesky'))
+    line['rooflines'] = roofs
     if world == 1 and not args.no_cpu_baseline:
-        nI, nPt = (100, 20000) if nImg >= 100 else (nImg, nOP)
-        cits, cobs, desc = cpu_lm_iteration_sample(nI, nPt, 2)
-        line['cpu_baseline'] = {'value': cits * cobs / 2.0e6, 'unit': 'LM iterations/s (2M-observation equivalents)',
-                                'cores': os.cpu_count() or 1, 'kind': 'port', 'sample': desc}
+        done, dt = cpu_lm_iterations(s, 1, 1.0)
+        line['cpu_baseline'] = {'value': done / dt * nObsGlobal / 2.0e6, 'unit': UNIT, 'cores': os.cpu_count() or 1,
+                                'kind': 'port', 'sample': '%d full LM iteration(s) on the config itself (%.1f s); %s' % (done, dt, CPU_DESC)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

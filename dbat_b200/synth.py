@@ -169,3 +169,80 @@ def make_scene(nImg=1000, nOP=200000, rays=10, seed=SEED, noise_px=0.5, start_no
         buildserialindices(s)
     truth = dict(IO=IO_TRUE.copy(), EO=EO, OP=OP, L=L)
     return s, truth
+
+
+def make_scene_shard(nImg, nOP_total, rank, world, rays=10, seed=SEED, noise_px=0.5, start_noise=1.0):
+    """One rank's share of a synthetic block for a point-sharded multi-GPU run: the stations (and their start
+    values) are generated identically on every rank from `seed`; this rank's nOP_total/world object points, their
+    observations and start values come from an independent stream (seed, rank).  Nothing of the whole block
+    ever exists on one host.  Same recipe as make_scene (the station re-orientation pass for starved stations
+    is replaced by a check: at the densities of BASELINE configs 4/5 it never triggers).
+
+    Returns (s, truth) with s.OP / s.IP holding only this rank's points; x = [IO; EO; this rank's OP]."""
+    rng = np.random.default_rng(seed)
+    H = 110.0
+    A_fp = (H * 24 / 24) * (H * 16 / 24)
+    L = np.sqrt(nImg * A_fp / 12)
+    g = int(np.ceil(np.sqrt(nImg)))
+    gi, gj = np.meshgrid(np.arange(g), np.arange(g), indexing='ij')
+    cells = np.stack([gi.ravel(), gj.ravel()], axis=1)[:nImg]
+    edge = min(55.0, 0.2 * L)
+    cxy = edge + (cells + 0.5 + rng.uniform(-0.3, 0.3, cells.shape)) * ((L - 2 * edge) / g)
+    EO = np.empty((6, nImg))
+    EO[0:2] = cxy.T
+    EO[2] = rng.uniform(80, 140, nImg)
+    EO[3:5] = rng.normal(0, np.deg2rad(10), (2, nImg))
+    for _ in range(100):
+        hit_x = EO[0] - EO[2] * np.tan(EO[4]) / np.cos(EO[3])
+        hit_y = EO[1] + EO[2] * np.tan(EO[3])
+        out = np.flatnonzero((hit_x < 0) | (hit_x > L) | (hit_y < 0) | (hit_y > L))
+        if len(out) == 0:
+            break
+        EO[3:5, out] = rng.normal(0, np.deg2rad(10), (2, len(out)))
+    EO[5] = rng.uniform(-np.pi, np.pi, nImg)
+    EO0 = EO.copy()
+    EO0[0:3] += start_noise * rng.normal(0, 0.05, (3, nImg))
+    EO0[3:6] += start_noise * rng.normal(0, np.deg2rad(0.1), (3, nImg))
+    M = _rot(EO[3:6])
+    tree = cKDTree(cxy)
+    kq = min(nImg, max(4 * rays, 48))
+    lo, hi = (nOP_total * rank) // world, (nOP_total * (rank + 1)) // world
+    nOP = hi - lo
+    prng = np.random.default_rng([seed, 1 + rank, world])
+    OP = np.empty((3, nOP))
+    idx = np.empty((nOP, kq), dtype=np.int64)
+    take = np.zeros((nOP, kq), dtype=bool)
+    bad = np.arange(nOP)
+    for _ in range(1000):
+        OP[0:2, bad] = prng.uniform(0, L, (2, len(bad)))
+        OP[2, bad] = prng.uniform(0, 30, len(bad))
+        for b0 in range(0, len(bad), 100000):
+            bb = bad[b0:b0 + 100000]
+            Qb = OP.T[bb]
+            _, ib = tree.query(Qb[:, 0:2], k=kq)
+            ib = ib.reshape(len(Qb), -1)
+            ii = ib.ravel()
+            l, depth = _ideal(np.repeat(Qb, kq, axis=0), EO[0:3, ii].T, M[ii], IO_TRUE[0])
+            ok = (depth < 0) & (l[:, 0] > -11.9) & (l[:, 0] < 11.8) & (l[:, 1] > -7.9) & (l[:, 1] < 7.8)
+            ok = ok.reshape(len(Qb), kq)
+            idx[bb] = ib
+            take[bb] = ok & (np.cumsum(ok, axis=1) <= rays)
+        bad = bad[take[bad].sum(axis=1) < rays]
+        if len(bad) == 0:
+            break
+    else:
+        raise RuntimeError('could not place all object points')
+    pj, slot = np.nonzero(take)
+    ip_img = idx[pj, slot]
+    l, _ = _ideal(OP.T[pj], EO[0:3, ip_img].T, M[ip_img], IO_TRUE[0])
+    uv = _pixel_from_ideal(l, IO_TRUE) + prng.normal(0, noise_px, (len(pj), 2))
+    OP0 = OP + start_noise * prng.normal(0, 0.1, OP.shape)
+    s = new_struct(np.tile(IO_START[:, None], (1, nImg)), EO0, OP0, uv.T, ip_img, pj,
+                   np.array([[PX], [PX]]), np.array([[IM_W], [IM_H]]), 3, 3, 2, noise_px)
+    s.bundle.est.IO[:] = True
+    s.bundle.est.IO[4, :] = False
+    s.bundle.est.OP[:] = True
+    seteoest_depend(s, 0)
+    buildserialindices(s)
+    truth = dict(IO=IO_TRUE.copy(), EO=EO, OP=OP, L=L, op_range=(lo, hi))
+    return s, truth

@@ -76,6 +76,38 @@ def _solve_spd(A, b):
     return x, False
 
 
+def solve_spd_pointfirst(A, b, nC):
+    """`A\\b` (levenberg_marquardt.m:119) for the damped normal matrix of a bundle with x = [IO; EO; OP] and
+    every object point fully estimated: what MATLAB's mldivide -> CHOLMOD (supernodal, AMD ordering) does on this
+    matrix, spelled out - the 3 x 3 point blocks are eliminated first (AMD puts the low-degree point columns
+    first, as the reference itself orders them in bundle_cov.m:73-84), the camera front is a dense LAPACK
+    Cholesky.  Used by bench.py's CPU baseline at sizes where SuperLU (no supernodal BLAS-3 front) needs tens of
+    minutes; checked against `_solve_spd` in tests/test_oracle_golden.py."""
+    import scipy.linalg as sla
+    A = sp.csc_matrix(A)
+    n = A.shape[0]
+    m3 = n - nC
+    assert m3 % 3 == 0
+    nP = m3 // 3
+    D = A[:nC, :nC].toarray()
+    B = A[:nC, nC:].tocsc()                                   # camera x point
+    V = A[nC:, nC:].tocoo()
+    assert np.all(V.row // 3 == V.col // 3), 'point block is not 3 x 3 block diagonal'
+    Vb = np.zeros((nP, 3, 3))
+    np.add.at(Vb, (V.row // 3, V.row % 3, V.col % 3), V.data)
+    Vi = np.linalg.inv(Vb)
+    ii = (3 * np.arange(nP)[:, None, None] + np.arange(3)[None, :, None]) + np.zeros((1, 1, 3), dtype=np.int64)
+    jj = (3 * np.arange(nP)[:, None, None] + np.arange(3)[None, None, :]) + np.zeros((1, 3, 1), dtype=np.int64)
+    Vis = sp.csc_matrix((Vi.ravel(), (ii.ravel(), jj.ravel())), shape=(m3, m3))
+    Y = (B @ Vis).tocsr()                                     # B V^-1
+    S = D - (Y @ B.T).toarray()
+    rhs = b[:nC] - Y @ b[nC:]
+    c, low = sla.cho_factor(S, lower=True, check_finite=False)
+    pc = sla.cho_solve((c, low), rhs, check_finite=False)
+    pp = Vis @ (b[nC:] - B.T @ pc)
+    return np.concatenate([pc, pp])
+
+
 def _weighted(resFun, R, x, want_jac):
     s, K = resFun(x, want_jac)
     r = R * s

@@ -64,11 +64,13 @@ def test_bench_reference_arm_runs_without_gpu():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+    out = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '2', '--warmup', '0',
+                          '--nimg', '60', '--nop', '6000'],
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line['impl'] == 'reference' and line['metric'] == 'lm_iterations_per_s' and line['value'] > 0
     assert line['cpu_baseline']['kind'] == 'port' and line['cpu_baseline']['value'] == line['value']
     assert line['e2e']['h2d_bytes_per_step'] == 0 and line['e2e']['d2h_bytes_per_step'] == 0
-    assert line['gpu_launches'] == 0 and 'workload' in line['config']
+    assert line['gpu_launches'] == 0 and 'workload' in line['config'] and line['config']['same_config'] is True
+    assert line['steps'] == 2

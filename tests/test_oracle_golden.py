@@ -481,3 +481,28 @@ def test_structural_weakness_matches_golden_reports(pm, rank, suspects):
     wp = structural_weakness(E.final.weighted.J, pt)
     assert wp.structural.rank == rank and wp.structural.suspectedParams == suspects
     assert np.array_equal(wp.structural.dmperm == 0, w.dmperm == 0)
+
+
+def test_pointfirst_cpu_solver_equals_the_sparse_solve():
+    """bench.py's CPU baseline solves (J'J + lambda I) p = -J'r by eliminating the 3 x 3 point blocks first and
+    factoring the camera front densely (what CHOLMOD's supernodal factorisation does with an AMD ordering); it
+    must give the step of the oracle's general sparse solve (`_solve_spd`, MATLAB's backslash)."""
+    import scipy.sparse as sp
+    from dbat_b200.synth import make_scene
+    from oracle import lsa
+    from oracle.cameramodel import brown_euler_cam4
+    from oracle.dbatstruct import buildweightmatrix, serialize
+    s, _ = make_scene(30, 1500, rays=6, seed=9)
+    x = serialize(s)
+    R = np.sqrt(buildweightmatrix(s))
+    f, J = brown_euler_cam4(x, s, True)
+    Jw = (sp.diags(R) @ J).tocsc()
+    N = (Jw.T @ Jw).tocsc()
+    g = Jw.T @ (R * f)
+    n = len(x)
+    nC = n - len(s.bundle.serial.OP.dest)
+    A = (N + 1e-6 * N.diagonal().mean() * sp.identity(n, format='csc')).tocsc()
+    p1, sing = lsa._solve_spd(A, -g)
+    assert not sing
+    p2 = lsa.solve_spd_pointfirst(A, -g, nC)
+    np.testing.assert_allclose(p2, p1, rtol=1e-9, atol=1e-12 * np.abs(p1).max())
