@@ -59,7 +59,8 @@ EXPORTS = ['dbat_create', 'dbat_destroy', 'dbat_last_error', 'dbat_num_unknowns'
            'dbat_default_opts', 'dbat_solve', 'dbat_normal_step', 'dbat_cov',
            'dbat_comm_unique_id', 'dbat_comm_init', 'dbat_phase_times', 'dbat_dense_chol_solve',
            'dbat_forwintersect', 'dbat_forwintersect_error', 'dbat_resect3', 'dbat_camera_order',
-           'dbat_tile_symbolic', 'dbat_tile_symbolic_get', 'dbat_tile_chol_solve', 'dbat_reduced_info']
+           'dbat_tile_symbolic', 'dbat_tile_symbolic_get', 'dbat_tile_symbolic_get2', 'dbat_tile_chol_solve',
+           'dbat_reduced_info']
 
 _lib = None
 
@@ -136,6 +137,8 @@ def lib():
     L.dbat_tile_symbolic.restype = C.c_int
     L.dbat_tile_symbolic_get.argtypes = [c_ip] * 8
     L.dbat_tile_symbolic_get.restype = C.c_int
+    L.dbat_tile_symbolic_get2.argtypes = [c_ip] * 3
+    L.dbat_tile_symbolic_get2.restype = C.c_int
     L.dbat_tile_chol_solve.argtypes = [C.c_int64, c_dp, c_dp, c_dp, C.c_int64, C.c_int64, C.c_int, c_dp]
     L.dbat_tile_chol_solve.restype = C.c_int
     _lib = L
@@ -191,24 +194,33 @@ def camera_order(img, op, nImg, nOP):
     return perm - 1, int(bw.value)
 
 
-def tile_symbolic(img, op, nImg, nOP, nEO, nIO, mode=-1, leaf=120):
-    """Symbolic analysis of the reduced camera system (host code in the library): dict of counts + arrays."""
+def tile_symbolic(img, op, nImg, nOP, nEO, nIO, mode=-1, leaf=120, parts=1, part=0):
+    """Symbolic analysis of the reduced camera system (host code in the library): dict of counts + arrays.
+    parts / part: task lists of one part of a distributed factorisation."""
     img1, op1, ne = i64(np.asarray(img) + 1), i64(np.asarray(op) + 1), i64(nEO)
     cnt = np.zeros(16, dtype=np.int64)
+    cnt[14], cnt[15] = parts, part
     rc = lib().dbat_tile_symbolic(nImg, nOP, len(img1), iptr(img1), iptr(op1), iptr(ne), nIO, mode, leaf, iptr(cnt))
     if rc != 0:
-        raise DbatError(rc, 'dbat_tile_symbolic: bad argument')
-    names = ['nT', 'ld', 'nS', 'nSlots', 'nSlotsS', 'nTasks', 'nTerms', 'depth', 'mode', 'nSeg', 'ioS']
+        raise DbatError(rc, 'dbat_tile_symbolic failed')
+    names = ['nT', 'ld', 'nS', 'nSlots', 'nSlotsS', 'nTasks', 'nTerms', 'depth', 'mode', 'nSeg', 'ioS', 'nTasks1',
+             'nTopS', 'nTop', 'nParts', 'nOwnS']
     out = {k: int(cnt[i]) for i, k in enumerate(names)}
     nT = out['nT']
-    arr = dict(imgS=np.empty(nImg, np.int64), tix=np.empty(nT * nT, np.int64), taskIJ=np.empty(2 * out['nTasks'], np.int64),
+    arr = dict(imgS=np.empty(nImg, np.int64), tix=np.empty(nT * nT, np.int64), taskIJ=np.empty(max(1, 2 * out['nTasks']), np.int64),
                termPtr=np.empty(out['nTasks'] + 1, np.int64), termAB=np.empty(max(1, 2 * out['nTerms']), np.int64),
                level=np.empty(nT, np.int64), s2kind=np.empty(out['ld'], np.int64), bwdCols=np.empty(nT, np.int64))
     lib().dbat_tile_symbolic_get(*[iptr(arr[k]) for k in ('imgS', 'tix', 'taskIJ', 'termPtr', 'termAB', 'level', 's2kind', 'bwdCols')])
+    arr2 = dict(taskMode=np.empty(max(1, out['nTasks']), np.int64), colOwner=np.empty(nT, np.int64),
+                ownSBegin=np.empty(out['nParts'] + 1, np.int64))
+    lib().dbat_tile_symbolic_get2(*[iptr(arr2[k]) for k in ('taskMode', 'colOwner', 'ownSBegin')])
     out.update(arr)
+    out.update(arr2)
     out['tix'] = out['tix'].reshape(nT, nT)
-    out['taskIJ'] = out['taskIJ'].reshape(-1, 2)
+    out['taskIJ'] = out['taskIJ'][:2 * out['nTasks']].reshape(-1, 2)
+    out['taskMode'] = out['taskMode'][:out['nTasks']]
     out['termAB'] = out['termAB'][:2 * out['nTerms']].reshape(-1, 2)
+    out['bwdCols'] = out['bwdCols'][out['bwdCols'] >= 0]
     return out
 
 

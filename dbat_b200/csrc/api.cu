@@ -45,6 +45,9 @@ struct NcclApi {
     int (*GetUniqueId)(nccl_uid*) = nullptr;
     int (*CommInitRank)(void**, int, nccl_uid, int) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(void*) = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
 };
@@ -57,9 +60,12 @@ static bool nccl_load() {
     g_nccl.GetUniqueId = (int (*)(nccl_uid*))dlsym(g_nccl.lib, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(void**, int, nccl_uid, int))dlsym(g_nccl.lib, "ncclCommInitRank");
     g_nccl.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclAllReduce");
+    g_nccl.Reduce = (int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t))dlsym(g_nccl.lib, "ncclReduce");
+    g_nccl.GroupStart = (int (*)())dlsym(g_nccl.lib, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(g_nccl.lib, "ncclGroupEnd");
     g_nccl.CommDestroy = (int (*)(void*))dlsym(g_nccl.lib, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char* (*)(int))dlsym(g_nccl.lib, "ncclGetErrorString");
-    return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce;
+    return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.AllReduce && g_nccl.Reduce && g_nccl.GroupStart && g_nccl.GroupEnd;
 }
 
 // --------------------------------------------------------------------------------------------
@@ -90,6 +96,8 @@ struct dbat_handle {
     TChol tc;                           // sparse tile Cholesky of the reduced system (tilechol.cu)
     std::vector<int> h_x2s;             // x column (camera side) -> S index
     double* d_dS = nullptr;             // Jacobi scale per S index
+    unsigned long long* d_stats = nullptr;   // pivot statistics exchanged between the ranks
+    std::vector<int> h_nEO; int h_nIOest = 0; std::vector<int64_t> h_adjPtr; std::vector<int32_t> h_adj;   // for re-tiling in dbat_comm_init
     bool params_valid = false;          // parameter arrays correspond to d_x
     bool normal_valid = false;          // Gram / point records correspond to d_x
     // comm
@@ -155,6 +163,39 @@ static int fail_create(dbat_handle* h, int code, const std::string& msg) {
     g_create_err = msg;
     if (h) dbat_destroy(h);
     return code;
+}
+
+// (Re)build everything that depends on the tiling of the reduced system: symbolic analysis for nParts parts, the S
+// index maps, the tile storage and the S-ordered work vectors.  dbat_create calls it for one part; dbat_comm_init
+// again when the factorisation is distributed over the ranks.
+static int setup_reduced(dbat_handle* h, int nParts, int myPart) {
+    DevProblem& P = h->P;
+    const int nImg = P.nImg, nC = P.nC;
+    TileSym sym;
+    if (tile_symbolic(nImg, h->h_adjPtr.data(), h->h_adj.data(), h->h_nEO.data(), h->h_nIOest, -1, 120, sym, nParts, myPart)) {
+        h->err = "symbolic analysis of the reduced system failed"; return DBAT_E_STATE;
+    }
+    std::vector<int> sh_s(DBAT_NSLOT, -1), eo_s((size_t)6 * nImg, -1), s2x(sym.ld, -1);
+    h->h_x2s.assign(std::max(1, nC), -1);
+    int k = 0;
+    for (int sl = 0; sl < DBAT_NSLOT; ++sl) if (h->h_sh_col[sl] >= 0) sh_s[sl] = sym.ioS + k++;
+    for (int i = 0; i < nImg; ++i) {
+        int q = 0;
+        for (int a = 0; a < 6; ++a) if (h->h_eo_col[(size_t)i * 6 + a] >= 0) eo_s[(size_t)i * 6 + a] = sym.imgS[i] + q++;
+    }
+    for (int sl = 0; sl < DBAT_NSLOT; ++sl) if (sh_s[sl] >= 0) { s2x[sh_s[sl]] = h->h_sh_col[sl]; h->h_x2s[h->h_sh_col[sl]] = sh_s[sl]; }
+    for (size_t e = 0; e < eo_s.size(); ++e) if (eo_s[e] >= 0) { s2x[eo_s[e]] = h->h_eo_col[e]; h->h_x2s[h->h_eo_col[e]] = eo_s[e]; }
+    if (h->tc.d.tiles) tchol_free(h->tc);
+    if (tchol_alloc(h->tc, sym)) { h->err = "out of memory for the reduced system"; return DBAT_E_OOM; }
+    int rc = 0;
+    int *d_shs = nullptr, *d_eos = nullptr, *d_s2x = nullptr;
+    if ((rc = dev_upload(h, &d_shs, sh_s)) || (rc = dev_upload(h, &d_eos, eo_s)) || (rc = dev_upload(h, &d_s2x, s2x))) return rc;
+    P.sh_s = d_shs; P.eo_s = d_eos; P.s2x = d_s2x; P.T = h->tc.d;
+    P.ldS = sym.ld;
+    if ((rc = dev_alloc(h, &h->d_dS, (size_t)sym.ld)) || (rc = dev_alloc(h, &P.rhs, (size_t)sym.ld)) ||
+        (rc = dev_alloc(h, &h->d_pc, (size_t)sym.ld))) return rc;
+    if (!h->d_stats && (rc = dev_alloc(h, &h->d_stats, (size_t)4))) return rc;
+    return 0;
 }
 
 extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
@@ -364,8 +405,8 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     { auto v = to_int(d->OPdes_dest, d->nOPdes, true); UP(h->d_OPdst, v); }
     UP(h->d_img_chunk_start, img_chunk_start); UP(h->d_col2pt, col2pt);
     {   // ---- reduced system: elimination order of the images, tile pattern, symbolic factorisation
-        std::vector<int64_t> adjPtr; std::vector<int32_t> adj;
-        covis_graph(nImg, nOP, h->h_pt_start.data(), img_pm.data(), adjPtr, adj);
+        covis_graph(nImg, nOP, h->h_pt_start.data(), img_pm.data(), h->h_adjPtr, h->h_adj);
+        std::vector<int64_t>& adjPtr = h->h_adjPtr; std::vector<int32_t>& adj = h->h_adj;
         if (d->nCovis > 0 && d->covis_a && d->covis_b) {      // the whole project's graph (sharded problems)
             std::vector<std::vector<int32_t>> nb(nImg);
             for (int i = 0; i < nImg; ++i) nb[i].assign(adj.begin() + adjPtr[i], adj.begin() + adjPtr[i + 1]);
@@ -384,29 +425,11 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
             }
             adjPtr[nImg] = (int64_t)adj.size();
         }
-        std::vector<int> nEO(nImg, 0);
-        for (int i = 0; i < nImg; ++i) for (int a = 0; a < 6; ++a) if (colEO[(size_t)i * 6 + a] >= 0) nEO[i]++;
-        int nIO = 0;
-        for (int sl = 0; sl < DBAT_NSLOT; ++sl) if (h->h_sh_col[sl] >= 0) nIO++;
-        TileSym sym;
-        if (tile_symbolic(nImg, adjPtr.data(), adj.data(), nEO.data(), nIO, -1, 120, sym))
-            return fail_create(h, DBAT_E_BADARG, "symbolic analysis of the reduced system failed");
-        std::vector<int> sh_s(DBAT_NSLOT, -1), eo_s((size_t)6 * nImg, -1), s2x(sym.ld, -1);
-        h->h_x2s.assign(std::max(1, nC), -1);
-        int k = 0;
-        for (int sl = 0; sl < DBAT_NSLOT; ++sl) if (h->h_sh_col[sl] >= 0) sh_s[sl] = sym.ioS + k++;
-        for (int i = 0; i < nImg; ++i) {
-            int q = 0;
-            for (int a = 0; a < 6; ++a) if (colEO[(size_t)i * 6 + a] >= 0) eo_s[(size_t)i * 6 + a] = sym.imgS[i] + q++;
-        }
-        for (int sl = 0; sl < DBAT_NSLOT; ++sl) if (sh_s[sl] >= 0) { s2x[sh_s[sl]] = h->h_sh_col[sl]; h->h_x2s[h->h_sh_col[sl]] = sh_s[sl]; }
-        for (size_t e = 0; e < eo_s.size(); ++e) if (eo_s[e] >= 0) { s2x[eo_s[e]] = colEO[e]; h->h_x2s[colEO[e]] = eo_s[e]; }
-        if (tchol_alloc(h->tc, sym)) return fail_create(h, DBAT_E_OOM, "out of memory for the reduced system");
-        int *d_shs, *d_eos, *d_s2x;
-        UP(d_shs, sh_s); UP(d_eos, eo_s); UP(d_s2x, s2x);
-        P.sh_s = d_shs; P.eo_s = d_eos; P.s2x = d_s2x; P.T = h->tc.d;
-        P.ldS = sym.ld;
-        AL(h->d_dS, sym.ld);
+        h->h_nEO.assign(nImg, 0);
+        for (int i = 0; i < nImg; ++i) for (int a = 0; a < 6; ++a) if (colEO[(size_t)i * 6 + a] >= 0) h->h_nEO[i]++;
+        h->h_nIOest = 0;
+        for (int sl = 0; sl < DBAT_NSLOT; ++sl) if (h->h_sh_col[sl] >= 0) h->h_nIOest++;
+        if ((rc = setup_reduced(h, 1, 0))) return fail_create(h, rc, h->err);
     }
     const std::vector<int>& imgRank = h->tc.sym.imgRank;
     AL(P.chunkG, (size_t)std::max(1, P.nChunks) * DBAT_GSZ);
@@ -423,7 +446,6 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     }
     AL(P.pt, (size_t)std::max(1, nOP) * DBAT_PT_STRIDE);
     AL(P.W, (size_t)std::max(1, nObs) * DBAT_W_STRIDE);
-    AL(P.rhs, P.ldS);
     {   // deterministic Schur index: inverse permutation, point of every pm observation, pair blocks
         std::vector<int> cm2pm(nObs), pt_pm(nObs);
         for (int o = 0; o < nObs; ++o) { cm2pm[h->h_pm2cm[o]] = o; pt_pm[o] = h->h_pt_cm[h->h_pm2cm[o]]; }
@@ -523,7 +545,7 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     const int nPartial = 2 * ((std::max(nObs, P.n) + 255) / 256) + 64;
     AL(h->d_partial, nPartial);
     AL(h->d_scal, SC_N);
-    AL(h->d_x, P.n); AL(h->d_t, P.n); AL(h->d_p, P.n); AL(h->d_pgn, P.n); AL(h->d_g, P.n); AL(h->d_pc, P.ldS);
+    AL(h->d_x, P.n); AL(h->d_t, P.n); AL(h->d_p, P.n); AL(h->d_pgn, P.n); AL(h->d_g, P.n);
     AL(h->d_diagN, P.n); AL(h->d_dscale, P.n);
     AL(h->d_r, h->m);
     if (cudaMallocHost((void**)&h->h_scal, sizeof(double) * SC_N) != cudaSuccess ||
@@ -569,6 +591,29 @@ static int allreduce(dbat_handle* h, double* buf, size_t cnt) {
     int rc = g_nccl.AllReduce(buf, buf, cnt, /*ncclDouble*/ 8, /*ncclSum*/ 0, h->comm, h->st);
     if (rc != 0) { h->err = std::string("ncclAllReduce: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); return DBAT_E_NCCL; }
     return 0;
+}
+
+static int nccl_fail(dbat_handle* h, const char* what, int rc) {
+    h->err = std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?");
+    return DBAT_E_NCCL;
+}
+// every part's own tiles of S end up, summed over the ranks, on the rank that factors them
+static int reduce_owned_tiles(dbat_handle* h) {
+    TChol& tc = h->tc;
+    int rc = g_nccl.GroupStart();
+    if (rc) return nccl_fail(h, "ncclGroupStart", rc);
+    for (int g = 0; g < tc.sym.nParts && !rc; ++g) {
+        const size_t b = tc.sym.ownSBegin[g], e = tc.sym.ownSBegin[g + 1];
+        if (e > b) rc = g_nccl.Reduce(tc.d.tiles + b * TC_TT, tc.d.tiles + b * TC_TT, (e - b) * TC_TT, /*ncclDouble*/ 8, /*ncclSum*/ 0, g, h->comm, h->st);
+    }
+    const int rc2 = g_nccl.GroupEnd();
+    if (rc) return nccl_fail(h, "ncclReduce", rc);
+    if (rc2) return nccl_fail(h, "ncclGroupEnd", rc2);
+    return 0;
+}
+static int allreduce_max_u64(dbat_handle* h, unsigned long long* buf, size_t cnt) {
+    int rc = g_nccl.AllReduce(buf, buf, cnt, /*ncclUint64*/ 5, /*ncclMax*/ 2, h->comm, h->st);
+    return rc ? nccl_fail(h, "ncclAllReduce", rc) : 0;
 }
 
 // scatter device vector xdev into the parameter arrays and rebuild the per-image records
@@ -688,9 +733,11 @@ static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, 
         cudaMemsetAsync(P.rhs, 0, sizeof(double) * P.ldS, h->st);
     }
     launch_schur(P, lambda, h->st);
+    const bool dist = h->nranks > 1 && tc.sym.nParts > 1;
     if (h->nranks > 1) {
-        // the tiles of the pattern of S are one contiguous array: no packing
-        int rc = allreduce(h, tc.d.tiles, (size_t)tc.d.nSlotsS * TC_TT);
+        int rc;
+        if (dist) rc = reduce_owned_tiles(h);        // top tiles are summed later, together with the partial factor updates
+        else rc = allreduce(h, tc.d.tiles, (size_t)tc.d.nTopS * TC_TT);      // one contiguous array: no packing
         if (!rc) rc = allreduce(h, P.rhs, P.ldS);
         if (rc) return rc;
     }
@@ -702,11 +749,24 @@ static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, 
     }
     ph_end(h, PH_SCHUR, a);
     a = ph_begin(h);
-    tchol_put_rhs(tc, P.rhs, h->st);
-    tchol_factor(tc, h->st);
+    tchol_put_rhs(tc, P.rhs, h->st, !dist || h->rank == 0);
+    tchol_factor_begin(tc, h->st);
+    if (dist) {
+        // every rank has factored the columns of its own subtree and subtracted its subtree's contribution from the
+        // separator ("top") tiles: sum them, then everybody factors the top
+        int rc = allreduce(h, tc.d.tiles, (size_t)tc.d.nTop * TC_TT);
+        if (rc) return rc;
+    }
+    tchol_factor_end(tc, h->st);
     ph_end(h, PH_CHOL, a);
     a = ph_begin(h);
     tchol_solve(tc, h->st);
+    if (dist) {
+        tchol_solve_owned_mask(tc, h->rank == 0, h->st);
+        int rc = allreduce(h, tc.xs, P.ldS);
+        if (!rc) { tchol_pack_stats(tc, h->d_stats, false, h->st); rc = allreduce_max_u64(h, h->d_stats, 3); tchol_pack_stats(tc, h->d_stats, true, h->st); }
+        if (rc) return rc;
+    }
     launch_unpermute(P, tc.xs, jacobi ? h->d_dscale : nullptr, h->d_pc, h->st);
     launch_backsub(P, lambda, h->d_pc, pout, h->st);
     int info = 0; unsigned long long mmb[2] = {0, 0};
@@ -1721,5 +1781,7 @@ extern "C" int dbat_comm_init(dbat_handle* h, int nranks, int rank, const void* 
     int rc = g_nccl.CommInitRank(&h->comm, nranks, id, rank);
     if (rc != 0) { h->err = std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"); return DBAT_E_NCCL; }
     h->nranks = nranks; h->rank = rank;
+    // distribute the factorisation: cut the elimination tree into one subtree per rank (tilesym.cu)
+    if ((rc = setup_reduced(h, nranks, rank))) return rc;
     return DBAT_OK;
 }

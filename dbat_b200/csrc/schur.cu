@@ -135,7 +135,7 @@ __global__ void k_build_S(DevProblem P, const double* __restrict__ camDiag, cons
 }
 void launch_build_S(const DevProblem& P, const double* camDiag, const double* camG, double lambda,
                     cudaStream_t st) {
-    cudaMemsetAsync(P.T.tiles, 0, sizeof(double) * (size_t)P.T.nSlotsS * TC_TT, st);
+    tchol_zero_dev(P.T, st);
     k_build_S<<<P.nImg + 1, 128, 0, st>>>(P, camDiag, camG, lambda);
     count_launch();
 }

@@ -214,7 +214,7 @@ __device__ void tc_potrf64(double* As, double* Xd, double* colb, int warp, int l
 // ---------------------------------------------------------------------------------------------
 // the factorisation kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int epoch) {
+__global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int epoch, int taskBegin, int taskEnd, int counter) {
     extern __shared__ __align__(16) double sm[];
     __shared__ int s_task;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -224,10 +224,10 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int 
     double* colb = sm + TC_OFF_COLB;
     for (;;) {
         __syncthreads();                                      // previous task's shared memory is free
-        if (tid == 0) s_task = atomicAdd(D.counters, 1);
+        if (tid == 0) s_task = taskBegin + atomicAdd(D.counters + counter, 1);
         __syncthreads();
         const int task = s_task;
-        if (task >= D.nTasks) break;
+        if (task >= taskEnd) break;
         TC_STAMP(0)
         const int I = D.taskI[task], J = D.taskJ[task];
         const int slot = D.tix[(size_t)I * D.nT + J];
@@ -236,7 +236,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int 
         const int nterm = (int)(D.termPtr[task + 1] - t0);
         // ---- accumulator: -S(I,J) for tiles of the pattern of S, zero for fill tiles
         double acc[4][4][2];
-        if (slot < D.nSlotsS) {
+        if (D.inS(slot) || (D.taskMode[task] == 0 && slot < D.nTop && D.nTop < D.nSlots)) {
+            // tiles of S; in a distributed run also every top tile of phase 2 (it holds the summed partial results)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -337,6 +338,17 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int 
         cp_async_wait<0>();
         __syncthreads();
         TC_STAMP(1)
+        if (D.taskMode[task] == 1) {
+            // partial sum only: the tile := (local part of S) - sum over this subtree; summed over the ranks later
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    double* p0 = tile + (wn + 8 * j + 2 * fk) * 64 + wm + 8 * i + fr;
+                    p0[0] = -acc[i][j][0]; p0[64] = -acc[i][j][1];
+                }
+            continue;
+        }
         // ---- C = S - sum (= -acc) into the work tile (column-major, stride LA)
         double* Cs = sm;
 #pragma unroll
@@ -443,7 +455,7 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int 
 // in descending elimination-tree level; block J waits for the blocks of the rows of its column.
 // ---------------------------------------------------------------------------------------------
 #define BW_LD 65
-__global__ void __launch_bounds__(TC_THREADS) k_tchol_bwd(TCholDev D, int epoch, double* __restrict__ xs) {
+__global__ void __launch_bounds__(TC_THREADS) k_tchol_bwd(TCholDev D, int epoch, double* __restrict__ xs, int nCols) {
     __shared__ double Ls[64 * BW_LD];
     __shared__ double Xd[4 * 16 * 16];
     __shared__ double yv[64], xv[64];
@@ -454,7 +466,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tchol_bwd(TCholDev D, int epoch,
         __syncthreads();
         if (tid == 0) s_task = atomicAdd(D.counters + 1, 1);
         __syncthreads();
-        if (s_task >= nT) break;
+        if (s_task >= nCols) break;
         const int J = D.bwdCols[s_task];
         const int e0 = D.colPtr[J], e1 = D.colPtr[J + 1];
         const int yslot = D.tix[(size_t)(nT - 1) * nT + J];
@@ -527,14 +539,17 @@ __global__ void __launch_bounds__(TC_THREADS) k_tchol_bwd(TCholDev D, int epoch,
 // ---------------------------------------------------------------------------------------------
 // small helpers on the tile array
 // ---------------------------------------------------------------------------------------------
-__global__ void k_tc_put_rhs(TCholDev D, const double* __restrict__ rhs) {
+// putTop = 0: leave the top tile columns alone (distributed: their tiles are summed over the ranks, so only one
+// rank may contribute the rhs row and the 1e300 corner)
+__global__ void k_tc_put_rhs(TCholDev D, const double* __restrict__ rhs, const int* __restrict__ colOwner, int putTop) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= D.ld) return;
+    if (!putTop && colOwner[s >> 6] < 0) return;
     const int slot = D.tix[(size_t)(D.nT - 1) * D.nT + (s >> 6)];
     D.tiles[((size_t)slot << 12) + (s & 63) * 64 + 63] = (s == D.ld - 1) ? 1e300 : rhs[s];
 }
 __global__ void k_tc_scale(TCholDev D, const double* __restrict__ dS) {
-    const int slot = blockIdx.x;
+    const int slot = blockIdx.x < D.nTopS ? blockIdx.x : D.nTop + (blockIdx.x - D.nTopS);     // the tiles of S
     const int I = D.slotI[slot], J = D.slotJ[slot];
     double* t = D.tiles + ((size_t)slot << 12);
     for (int idx = threadIdx.x; idx < 4096; idx += blockDim.x) {
@@ -545,7 +560,7 @@ __global__ void k_tc_scale(TCholDev D, const double* __restrict__ dS) {
     }
 }
 __global__ void k_tc_to_dense(TCholDev D, double* __restrict__ dense, int ldd) {
-    const int slot = blockIdx.x;
+    const int slot = blockIdx.x < D.nTopS ? blockIdx.x : D.nTop + (blockIdx.x - D.nTopS);     // the tiles of S
     const int I = D.slotI[slot], J = D.slotJ[slot];
     const double* t = D.tiles + ((size_t)slot << 12);
     for (int idx = threadIdx.x; idx < 4096; idx += blockDim.x) {
@@ -583,13 +598,15 @@ int tchol_alloc(TChol& w, const TileSym& sym) {
     bad |= up(w, &d.tix, s.tix);
     bad |= up(w, &d.slotI, s.slotI); bad |= up(w, &d.slotJ, s.slotJ);
     bad |= up(w, &d.colPtr, s.colPtr); bad |= up(w, &d.colSlot, s.colSlot);
-    bad |= up(w, &d.taskI, s.taskI); bad |= up(w, &d.taskJ, s.taskJ);
+    bad |= up(w, &d.taskI, s.taskI); bad |= up(w, &d.taskJ, s.taskJ); bad |= up(w, &d.taskMode, s.taskMode);
+    d.nTopS = s.nTopS; d.nTop = s.nTop; d.nOwnS = s.nOwnS;
     {
         std::vector<long long> tp(s.termPtr.begin(), s.termPtr.end());
         bad |= up(w, &d.termPtr, tp);
     }
     bad |= up(w, &d.termA, s.termA); bad |= up(w, &d.termB, s.termB);
     bad |= up(w, &d.bwdCols, s.bwdCols);
+    bad |= up(w, &w.colOwnerDev, s.colOwner);
     {
         std::vector<unsigned char> valid(s.ld);
         for (int k = 0; k < s.ld; ++k) valid[k] = s.s2kind[k] == 1;
@@ -613,7 +630,7 @@ int tchol_alloc(TChol& w, const TileSym& sym) {
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tchol_factor, TC_THREADS, smem);
     if (occ < 1) occ = 1;
-    w.gridFactor = std::max(1, std::min(s.nTasks, sms * occ));
+    w.gridFactor = std::max(1, std::min(std::max(s.nTasks1, s.nTasks - s.nTasks1), sms * occ));
     int occ2 = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_tchol_bwd, TC_THREADS, 0);
     if (occ2 < 1) occ2 = 1;
@@ -626,24 +643,62 @@ void tchol_free(TChol& w) {
     w.d = TCholDev();
     w.xs = nullptr;
 }
-void tchol_zero(TChol& w, cudaStream_t st) {
-    cudaMemsetAsync(w.d.tiles, 0, sizeof(double) * (size_t)w.d.nSlotsS * TC_TT, st);
+void tchol_zero_dev(const TCholDev& d, cudaStream_t st) {
+    // one part: the S tiles [0, nTopS).  Distributed: every top tile (the fill tiles among them receive partial sums
+    // that are added up over the ranks, so they must not keep the previous factor) and the owned S tiles.
+    const size_t top = d.nTop < d.nSlots ? d.nTop : d.nTopS;
+    cudaMemsetAsync(d.tiles, 0, sizeof(double) * top * TC_TT, st);
+    if (d.nOwnS > 0) cudaMemsetAsync(d.tiles + (size_t)d.nTop * TC_TT, 0, sizeof(double) * (size_t)d.nOwnS * TC_TT, st);
 }
-void tchol_put_rhs(TChol& w, const double* rhs, cudaStream_t st) {
-    k_tc_put_rhs<<<(w.d.ld + 255) / 256, 256, 0, st>>>(w.d, rhs);
+void tchol_zero(TChol& w, cudaStream_t st) { tchol_zero_dev(w.d, st); }
+void tchol_put_rhs(TChol& w, const double* rhs, cudaStream_t st, bool putTop) {
+    k_tc_put_rhs<<<(w.d.ld + 255) / 256, 256, 0, st>>>(w.d, rhs, w.colOwnerDev, putTop ? 1 : 0);
     count_launch();
 }
-void tchol_factor(TChol& w, cudaStream_t st) {
+// [~min pivot bits, max pivot bits, info] as three uint64: one max-allreduce combines the statistics of all ranks
+__global__ void k_tc_pack_stats(TCholDev D, unsigned long long* __restrict__ out, int unpack) {
+    if (threadIdx.x != 0) return;
+    if (!unpack) { out[0] = ~D.minmax[0]; out[1] = D.minmax[1]; out[2] = (unsigned long long)(unsigned)(*D.info); }
+    else { D.minmax[0] = ~out[0]; D.minmax[1] = out[1]; *D.info = (int)out[2]; }
+}
+void tchol_pack_stats(TChol& w, unsigned long long* buf, bool unpack, cudaStream_t st) {
+    k_tc_pack_stats<<<1, 32, 0, st>>>(w.d, buf, unpack ? 1 : 0);
+    count_launch();
+}
+static void factor_launch(TChol& w, int t0, int t1, int counter, cudaStream_t st) {
+    if (t1 <= t0) return;
+    const int grid = std::max(1, std::min(w.gridFactor, t1 - t0));
+    k_tchol_factor<<<grid, TC_THREADS, TC_SMEM_DOUBLES * 8, st>>>(w.d, w.epoch, t0, t1, counter);
+    count_launch();
+}
+void tchol_factor_begin(TChol& w, cudaStream_t st) {
     ++w.epoch;
     cudaMemsetAsync(w.d.counters, 0, sizeof(int) * 4, st);
     cudaMemsetAsync(w.d.info, 0, sizeof(int), st);
     static const unsigned long long init[2] = {0x7fefffffffffffffull, 0ull};      // DBL_MAX, 0
     cudaMemcpyAsync(w.d.minmax, init, sizeof(init), cudaMemcpyHostToDevice, st);
-    k_tchol_factor<<<w.gridFactor, TC_THREADS, TC_SMEM_DOUBLES * 8, st>>>(w.d, w.epoch);
-    count_launch();
+    factor_launch(w, 0, w.sym.nTasks1, 0, st);
+}
+void tchol_factor_end(TChol& w, cudaStream_t st) {
+    factor_launch(w, w.sym.nTasks1, w.sym.nTasks, 2, st);
+}
+void tchol_factor(TChol& w, cudaStream_t st) {
+    tchol_factor_begin(w, st);
+    tchol_factor_end(w, st);
 }
 void tchol_solve(TChol& w, cudaStream_t st) {
-    k_tchol_bwd<<<w.gridBwd, TC_THREADS, 0, st>>>(w.d, w.epoch, w.xs);
+    const int nCols = (int)w.sym.bwdCols.size();
+    k_tchol_bwd<<<std::max(1, std::min(w.gridBwd, nCols)), TC_THREADS, 0, st>>>(w.d, w.epoch, w.xs, nCols);
+    count_launch();
+}
+__global__ void k_tc_mask_x(TCholDev D, const int* __restrict__ colOwner, int me, int keepTop, double* __restrict__ xs) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= D.ld) return;
+    const int ow = colOwner[s >> 6];
+    if (!((ow < 0 && keepTop) || (ow >= 0 && ow == me))) xs[s] = 0.0;
+}
+void tchol_solve_owned_mask(TChol& w, bool keepTop, cudaStream_t st) {
+    k_tc_mask_x<<<(w.d.ld + 255) / 256, 256, 0, st>>>(w.d, w.colOwnerDev, w.sym.myPart, keepTop ? 1 : 0, w.xs);
     count_launch();
 }
 void tchol_scale(TChol& w, const double* dS, cudaStream_t st) {

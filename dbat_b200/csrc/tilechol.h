@@ -20,12 +20,14 @@ struct TCholDev {
     const int* tix = nullptr;
     const int* slotI = nullptr; const int* slotJ = nullptr;
     const int* colPtr = nullptr; const int* colSlot = nullptr;
-    const int* taskI = nullptr; const int* taskJ = nullptr;
+    const int* taskI = nullptr; const int* taskJ = nullptr; const unsigned char* taskMode = nullptr;
     const long long* termPtr = nullptr; const int* termA = nullptr; const int* termB = nullptr;
     const int* bwdCols = nullptr;
     const unsigned char* valid = nullptr;   // per S index: 1 = real unknown (enters the pivot statistics)
     unsigned long long* prof = nullptr;     // optional: 4 globaltimer stamps per task (claim, terms done, deps done, end)
     int nT = 0, ld = 0, nSlots = 0, nSlotsS = 0, nTasks = 0;
+    int nTopS = 0, nTop = 0, nOwnS = 0;     // slot ranges: S tiles are [0, nTopS) and [nTop, nTop + nOwnS)
+    __host__ __device__ bool inS(int slot) const { return slot < nTopS || (slot >= nTop && slot < nTop + nOwnS); }
 };
 
 struct TChol {
@@ -34,6 +36,7 @@ struct TChol {
     int epoch = 0;
     int gridFactor = 0, gridBwd = 0;
     double* xs = nullptr;              // ld: solution in S order
+    const int* colOwnerDev = nullptr;  // nT: owning part of every tile column (-1 = top)
     std::vector<void*> allocs;
 };
 
@@ -41,12 +44,20 @@ int tchol_alloc(TChol& w, const TileSym& sym);           // uploads the symbolic
 void tchol_free(TChol& w);
 // zero the tiles of the pattern of S (fill tiles are never read before they are written)
 void tchol_zero(TChol& w, cudaStream_t st);
+void tchol_zero_dev(const TCholDev& d, cudaStream_t st);
 // row ld-1 := rhs (S order, length ld), S(ld-1, ld-1) := 1e300: forward substitution rides in the factorisation
-void tchol_put_rhs(TChol& w, const double* rhs, cudaStream_t st);
-// in-place factorisation; afterwards w.d.info / w.d.minmax hold the pivot statistics
+void tchol_put_rhs(TChol& w, const double* rhs, cudaStream_t st, bool putTop = true);
+void tchol_pack_stats(TChol& w, unsigned long long* buf3, bool unpack, cudaStream_t st);
+// in-place factorisation; afterwards w.d.info / w.d.minmax hold the pivot statistics.
+// Distributed (w.sym.nParts > 1): tchol_factor_begin runs phase 1 (this part's own columns and its partial sums
+// into the top tiles); the caller then sums the top tiles [0, nTop) over the ranks and calls tchol_factor_end.
 void tchol_factor(TChol& w, cudaStream_t st);
-// after tchol_put_rhs + tchol_factor: w.xs = S^-1 rhs (S order)
+void tchol_factor_begin(TChol& w, cudaStream_t st);
+void tchol_factor_end(TChol& w, cudaStream_t st);
+// after tchol_put_rhs + tchol_factor: w.xs = S^-1 rhs (S order).  Distributed: only the top blocks and this part's
+// own blocks of w.xs are computed (tchol_solve_owned_mask zeroes the rest so that a sum over the ranks completes it)
 void tchol_solve(TChol& w, cudaStream_t st);
+void tchol_solve_owned_mask(TChol& w, bool keepTop, cudaStream_t st);
 // S := D S D and rhs-row scaling with d given per S index (Jacobi scaling; padding entries must be 1)
 void tchol_scale(TChol& w, const double* dS, cudaStream_t st);
 // dense copy of S (before any factorisation touched the tiles: the slots of the pattern of S only; column-major,

@@ -94,10 +94,14 @@ struct Orderer {
     std::vector<int> mark, level;
     int nextTag = 1;
     std::vector<std::vector<int>> segs;       // elimination order as a list of segments
+    std::vector<int> segOwner;                // owning part of every segment, -1 = above the cut ("top")
+    int cutDepth = 0;                         // the tree is cut into 2^cutDepth parts
     Orderer(const Graph& gg, int lf) : g(gg), leaf(lf), mark(gg.n, 0), level(gg.n, -1) {}
 
-    // nodes: a node set (all currently marked with `tag`); nd = dissect, else one RCM segment
-    void run(std::vector<int> nodes, int tag, bool nd) {
+    // nodes: a node set (all currently marked with `tag`); nd = dissect, else one RCM segment.
+    // depth / path: position in the dissection tree (path = bits of the left/right choices so far)
+    void run(std::vector<int> nodes, int tag, bool nd, int depth = 0, int path = 0) {
+        const int ownerHere = depth >= cutDepth ? (path >> (depth - cutDepth)) : (path << (cutDepth - depth));
         // split into connected components first
         for (int v : nodes) level[v] = -1;
         std::vector<int> order;
@@ -114,6 +118,7 @@ struct Orderer {
             const int ecc = level[order.back()];
             if (!nd || (int)comp.size() <= leaf || ecc < 2) {
                 segs.emplace_back(order.rbegin(), order.rend());      // reverse Cuthill-McKee-like
+                segOwner.push_back(ownerHere);
                 continue;
             }
             // separator = one BFS level, chosen for balance among the interior levels; only its nodes
@@ -142,14 +147,15 @@ struct Orderer {
                     (touches ? S : A).push_back(v);
                 }
             }
-            if (A.empty() || B.empty()) { segs.emplace_back(order.rbegin(), order.rend()); continue; }
+            if (A.empty() || B.empty()) { segs.emplace_back(order.rbegin(), order.rend()); segOwner.push_back(ownerHere); continue; }
             const int ta = nextTag++, tb = nextTag++;
             for (int v : A) mark[v] = ta;
             for (int v : B) mark[v] = tb;
             for (int v : S) mark[v] = -1;
-            run(A, ta, true);
-            run(B, tb, true);
+            run(A, ta, true, depth + 1, 2 * path);
+            run(B, tb, true, depth + 1, 2 * path + 1);
             segs.push_back(S);
+            segOwner.push_back(depth >= cutDepth ? ownerHere : -1);   // a separator above the cut belongs to everybody
         }
     }
 };
@@ -157,7 +163,7 @@ struct Orderer {
 }  // namespace
 
 int tile_symbolic(int nImg, const int64_t* adjPtr, const int32_t* adj, const int* nEO, int nIO, int mode,
-                  int leafImages, TileSym& out) {
+                  int leafImages, TileSym& out, int nParts, int myPart) {
     const int T = TC_T;
     out = TileSym();
     int nCamCols = 0;
@@ -167,43 +173,74 @@ int tile_symbolic(int nImg, const int64_t* adjPtr, const int32_t* adj, const int
         if (!strcmp(e, "natural")) mode = 0; else if (!strcmp(e, "rcm")) mode = 1; else if (!strcmp(e, "nd")) mode = 2;
     }
     if (const char* e = getenv("DBAT_ND_LEAF")) leafImages = std::max(8, atoi(e));
+    // the tree can only be cut where it was dissected; parts = largest power of two <= nParts
+    int cutDepth = 0;
+    if (mode == 2) while ((2 << cutDepth) <= nParts) ++cutDepth;
+    if (getenv("DBAT_REPLICATED_CHOL")) cutDepth = 0;
+    out.nParts = 1 << cutDepth;
+    out.myPart = myPart < out.nParts ? myPart : -2;           // a rank beyond the parts owns nothing
     out.order_mode = mode;
     Graph g{nImg, adjPtr, adj};
     // ---- elimination order as segments; every segment starts on a tile boundary when dissecting
     std::vector<std::vector<int>> segs;
+    std::vector<int> segOwner;
     if (mode == 0) {
         segs.emplace_back(nImg);
         std::iota(segs[0].begin(), segs[0].end(), 0);
+        segOwner.push_back(-1);
     } else {
         Orderer o(g, leafImages);
+        o.cutDepth = cutDepth;
         std::vector<int> all(nImg);
         std::iota(all.begin(), all.end(), 0);
         for (int v : all) o.mark[v] = 0;
         o.nextTag = 1;
         o.run(all, 0, mode == 2);
         segs.swap(o.segs);
+        segOwner.swap(o.segOwner);
+        if (cutDepth == 0) std::fill(segOwner.begin(), segOwner.end(), -1);
     }
     out.nSeg = (int)segs.size();
     out.imgOrder.clear(); out.imgRank.assign(nImg, -1); out.imgS.assign(nImg, -1);
+    const bool align = mode == 2 && segs.size() > 1;
     int cur = 0;
-    for (auto& sg : segs) {
+    std::vector<int> colOwnerS;                       // owner of every S index handed out so far
+    for (size_t q = 0; q < segs.size(); ++q) {
+        auto& sg = segs[q];
         int cols = 0;
         for (int v : sg) cols += nEO[v];
         if (cols == 0) { for (int v : sg) { out.imgRank[v] = (int)out.imgOrder.size(); out.imgOrder.push_back(v); } continue; }
-        if (mode == 2 && segs.size() > 1) cur = (cur + T - 1) / T * T;
+        if (align) {
+            const int prevOwner = colOwnerS.empty() ? -1 : colOwnerS.back();
+            cur = (cur + T - 1) / T * T;
+            colOwnerS.resize(cur, prevOwner);         // the alignment padding stays with the segment before it
+        }
         for (int v : sg) {
             out.imgRank[v] = (int)out.imgOrder.size();
             out.imgOrder.push_back(v);
             if (nEO[v] > 0) { out.imgS[v] = cur; cur += nEO[v]; }
         }
+        colOwnerS.resize(cur, segOwner[q]);
     }
     if ((int)out.imgOrder.size() != nImg) return DBAT_E_BADARG;
+    if (cutDepth > 0) {                                   // the IO block and the rhs row never share a tile column with an owned segment
+        const int prevOwner = colOwnerS.empty() ? -1 : colOwnerS.back();
+        cur = (cur + T - 1) / T * T;
+        colOwnerS.resize(cur, prevOwner);
+    }
     out.ioS = cur;
     const int nEnd = cur + nIO;                       // unknowns occupy [0, nEnd) minus the alignment padding
     out.nS = nCamCols + nIO;
     out.ld = (nEnd + 1 + T - 1) / T * T;
     out.nT = out.ld / T;
     const int nT = out.nT;
+    colOwnerS.resize(out.ld, -1);
+    out.colOwner.assign(nT, -1);
+    for (int J = 0; J < nT; ++J) {
+        int ow = colOwnerS[(size_t)J * T];
+        for (int k = 1; k < T; ++k) if (colOwnerS[(size_t)J * T + k] != ow) ow = -1;      // mixed (cannot happen when aligned)
+        out.colOwner[J] = ow;
+    }
     out.s2kind.assign(out.ld, 0);
     for (int i = 0; i < nImg; ++i) for (int a = 0; a < nEO[i]; ++a) out.s2kind[out.imgS[i] + a] = 1;
     for (int a = 0; a < nIO; ++a) out.s2kind[out.ioS + a] = 1;
@@ -250,22 +287,37 @@ int tile_symbolic(int nImg, const int64_t* adjPtr, const int32_t* adj, const int
     for (int J = 0; J < nT; ++J) if (parent[J] >= 0) out.level[parent[J]] = std::max(out.level[parent[J]], out.level[J] + 1);
     out.depth = 0;
     for (int J = 0; J < nT; ++J) out.depth = std::max(out.depth, out.level[J] + 1);
+    // an owned column may only have rows in columns of the same owner or in top columns (guaranteed by the
+    // dissection; verified here because everything distributed rests on it)
+    for (int J = 0; J < nT; ++J) {
+        if (out.colOwner[J] < 0) continue;
+        for (int I = J + 1; I < nT; ++I)
+            if (getbit(colL, I, J) && out.colOwner[I] >= 0 && out.colOwner[I] != out.colOwner[J]) return DBAT_E_STATE;
+    }
 
-    // ---- slots: tiles of S first (column-major), then the fill tiles
+    // ---- slots: [top S | top fill | owned S by part | owned fill by part]
     out.tix.assign((size_t)nT * nT, -1);
     out.slotI.clear(); out.slotJ.clear();
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int J = 0; J < nT; ++J)
+    out.ownSBegin.assign(out.nParts + 1, 0);
+    auto add_tiles = [&](int owner, bool wantS) {
+        for (int J = 0; J < nT; ++J) {
+            if (out.colOwner[J] != owner) continue;
             for (int I = J; I < nT; ++I) {
                 if (!getbit(colL, I, J)) continue;
-                const bool inS = getbit(colS, I, J) != 0;
-                if ((pass == 0) != inS) continue;
+                if ((getbit(colS, I, J) != 0) != wantS) continue;
                 out.tix[(size_t)I * nT + J] = (int)out.slotI.size();
                 out.slotI.push_back(I); out.slotJ.push_back(J);
             }
-        if (pass == 0) out.nSlotsS = (int)out.slotI.size();
-    }
+        }
+    };
+    add_tiles(-1, true);  out.nTopS = (int)out.slotI.size();
+    add_tiles(-1, false); out.nTop = (int)out.slotI.size();
+    for (int gpart = 0; gpart < out.nParts; ++gpart) { out.ownSBegin[gpart] = (int)out.slotI.size(); add_tiles(gpart, true); }
+    out.ownSBegin[out.nParts] = (int)out.slotI.size();
+    out.nOwnS = (int)out.slotI.size() - out.nTop;
+    for (int gpart = 0; gpart < out.nParts; ++gpart) add_tiles(gpart, false);
     out.nSlots = (int)out.slotI.size();
+    out.nSlotsS = out.nTopS + out.nOwnS;
     out.colPtr.assign(nT + 1, 0); out.colSlot.clear();
     std::vector<std::vector<int>> rowCols(nT);                       // per tile row: its columns k < row, ascending
     for (int J = 0; J < nT; ++J) {
@@ -273,34 +325,83 @@ int tile_symbolic(int nImg, const int64_t* adjPtr, const int32_t* adj, const int
             if (getbit(colL, I, J)) { out.colSlot.push_back(out.tix[(size_t)I * nT + J]); if (I > J) rowCols[I].push_back(J); }
         out.colPtr[J + 1] = (int)out.colSlot.size();
     }
-    // ---- task list: columns by (level, index); within a column the diagonal tile first, then rows ascending
+    // ... and every column an owned column depends on must belong to the same part (a top column may only sit above)
+    for (int J = 0; J < nT; ++J) {
+        if (out.colOwner[J] < 0) continue;
+        for (int k : rowCols[J]) if (out.colOwner[k] != out.colOwner[J]) return DBAT_E_STATE;
+    }
+    // ---- task lists: columns by (level, index); within a column the diagonal tile first, then rows ascending.
+    //   phase 1: every tile of this part's own columns (all their terms lie in the same subtree), then one
+    //            partial-sum task per top tile that has terms in this part's subtree;
+    //   phase 2: every tile of the top columns with the terms that lie in top columns (after the partial sums of
+    //            all parts have been added up).  One part: everything is top, phase 1 is empty.
     std::vector<int> cols(nT);
     std::iota(cols.begin(), cols.end(), 0);
     std::stable_sort(cols.begin(), cols.end(), [&](int a, int b) { return out.level[a] < out.level[b]; });
-    out.taskI.clear(); out.taskJ.clear(); out.termPtr.assign(1, 0); out.termA.clear(); out.termB.clear();
-    for (int J : cols) {
-        for (int e = out.colPtr[J]; e < out.colPtr[J + 1]; ++e) {
-            const int I = out.slotI[out.colSlot[e]];
-            out.taskI.push_back(I); out.taskJ.push_back(J);
-            // terms: k < J present in both row I and row J
-            const std::vector<int>& ri = rowCols[I];
-            const std::vector<int>& rj = rowCols[J];
-            size_t a = 0, b = 0;
-            while (a < ri.size() && b < rj.size() && ri[a] < J && rj[b] < J) {
-                if (ri[a] < rj[b]) ++a;
-                else if (ri[a] > rj[b]) ++b;
-                else {
-                    out.termA.push_back(out.tix[(size_t)I * nT + ri[a]]);
-                    out.termB.push_back(out.tix[(size_t)J * nT + rj[b]]);
-                    ++a; ++b;
+    out.taskI.clear(); out.taskJ.clear(); out.taskMode.clear(); out.termPtr.assign(1, 0); out.termA.clear(); out.termB.clear();
+    const int me = out.myPart;
+    struct Tmp { double key; int I, J, mode; std::vector<int> a, b; };
+    auto collect = [&](int I, int J, int mode_, int termOwner, Tmp& t) -> bool {   // terms whose column k has owner termOwner
+        const std::vector<int>& ri = rowCols[I];
+        const std::vector<int>& rj = rowCols[J];
+        size_t a = 0, b = 0;
+        int maxLevel = -1;
+        t.I = I; t.J = J; t.mode = mode_; t.a.clear(); t.b.clear();
+        while (a < ri.size() && b < rj.size() && ri[a] < J && rj[b] < J) {
+            if (ri[a] < rj[b]) ++a;
+            else if (ri[a] > rj[b]) ++b;
+            else {
+                if (out.colOwner[ri[a]] == termOwner) {
+                    t.a.push_back(out.tix[(size_t)I * nT + ri[a]]);
+                    t.b.push_back(out.tix[(size_t)J * nT + rj[b]]);
+                    maxLevel = std::max(maxLevel, out.level[ri[a]]);
                 }
+                ++a; ++b;
             }
+        }
+        // a final task sorts with its column; a partial sum right after the last column it reads
+        t.key = mode_ == 0 ? (double)out.level[J] : maxLevel + 0.5;
+        return !(mode_ == 1 && t.a.empty());                       // nothing to add from this subtree: no task
+    };
+    auto flush = [&](std::vector<Tmp>& list) {
+        std::stable_sort(list.begin(), list.end(), [](const Tmp& x, const Tmp& y) { return x.key < y.key; });
+        for (const Tmp& t : list) {
+            out.taskI.push_back(t.I); out.taskJ.push_back(t.J); out.taskMode.push_back((unsigned char)t.mode);
+            out.termA.insert(out.termA.end(), t.a.begin(), t.a.end());
+            out.termB.insert(out.termB.end(), t.b.begin(), t.b.end());
             out.termPtr.push_back((int64_t)out.termA.size());
         }
+        list.clear();
+    };
+    std::vector<Tmp> list;
+    Tmp tmp;
+    if (out.nParts > 1 && me >= 0) {
+        for (int J : cols) {
+            if (out.colOwner[J] != me) continue;
+            for (int e = out.colPtr[J]; e < out.colPtr[J + 1]; ++e)
+                if (collect(out.slotI[out.colSlot[e]], J, 0, me, tmp)) list.push_back(tmp);
+        }
+        for (int J : cols) {
+            if (out.colOwner[J] >= 0) continue;
+            for (int e = out.colPtr[J]; e < out.colPtr[J + 1]; ++e)
+                if (collect(out.slotI[out.colSlot[e]], J, 1, me, tmp)) list.push_back(tmp);
+        }
+        flush(list);
     }
+    out.nTasks1 = (int)out.taskI.size();
+    for (int J : cols) {
+        if (out.colOwner[J] >= 0) continue;
+        for (int e = out.colPtr[J]; e < out.colPtr[J + 1]; ++e)
+            if (collect(out.slotI[out.colSlot[e]], J, 0, -1, tmp)) list.push_back(tmp);
+    }
+    flush(list);
     out.nTasks = (int)out.taskI.size();
     out.nTerms = (int64_t)out.termA.size();
-    out.bwdCols.assign(cols.rbegin(), cols.rend());
+    // backward substitution: top columns (descending level) first, then this part's own columns
+    out.bwdCols.clear();
+    for (auto it = cols.rbegin(); it != cols.rend(); ++it) if (out.colOwner[*it] < 0) out.bwdCols.push_back(*it);
+    out.nBwd1 = (int)out.bwdCols.size();
+    for (auto it = cols.rbegin(); it != cols.rend(); ++it) if (out.colOwner[*it] >= 0 && out.colOwner[*it] == me) out.bwdCols.push_back(*it);
     return DBAT_OK;
 }
 
@@ -313,6 +414,7 @@ static TileSym g_last_sym;
 extern "C" int dbat_tile_symbolic(int64_t nImg, int64_t nOP, int64_t nObs, const int64_t* obs_img,
                                   const int64_t* obs_op, const int64_t* nEO, int64_t nIO, int64_t mode,
                                   int64_t leafImages, int64_t* counts) {
+    // counts[14], counts[15] on entry: nParts, myPart of a distributed factorisation (0, 0 = one part)
     if (nImg <= 0 || !obs_img || !obs_op || !nEO || !counts) return DBAT_E_BADARG;
     std::vector<int> start((size_t)nOP + 1, 0), imgs((size_t)nObs);
     for (int64_t o = 0; o < nObs; ++o) {
@@ -328,12 +430,13 @@ extern "C" int dbat_tile_symbolic(int64_t nImg, int64_t nOP, int64_t nObs, const
     covis_graph((int)nImg, (int)nOP, start.data(), imgs.data(), ap, ad);
     std::vector<int> ne((size_t)nImg);
     for (int64_t i = 0; i < nImg; ++i) ne[(size_t)i] = (int)nEO[i];
-    int rc = tile_symbolic((int)nImg, ap.data(), ad.data(), ne.data(), (int)nIO, (int)mode, (int)leafImages, g_last_sym);
+    const int nParts = counts[14] > 0 ? (int)counts[14] : 1, myPart = (int)counts[15];
+    int rc = tile_symbolic((int)nImg, ap.data(), ad.data(), ne.data(), (int)nIO, (int)mode, (int)leafImages, g_last_sym, nParts, myPart);
     if (rc) return rc;
     const TileSym& s = g_last_sym;
     counts[0] = s.nT; counts[1] = s.ld; counts[2] = s.nS; counts[3] = s.nSlots; counts[4] = s.nSlotsS;
     counts[5] = s.nTasks; counts[6] = s.nTerms; counts[7] = s.depth; counts[8] = s.order_mode; counts[9] = s.nSeg;
-    counts[10] = s.ioS;
+    counts[10] = s.ioS; counts[11] = s.nTasks1; counts[12] = s.nTopS; counts[13] = s.nTop; counts[14] = s.nParts; counts[15] = s.nOwnS;
     return DBAT_OK;
 }
 extern "C" int dbat_tile_symbolic_get(int64_t* imgS, int64_t* tix, int64_t* taskIJ, int64_t* termPtr,
@@ -347,6 +450,15 @@ extern "C" int dbat_tile_symbolic_get(int64_t* imgS, int64_t* tix, int64_t* task
     if (termAB) for (int64_t t = 0; t < s.nTerms; ++t) { termAB[2 * t] = s.termA[t]; termAB[2 * t + 1] = s.termB[t]; }
     if (level) for (int J = 0; J < s.nT; ++J) level[J] = s.level[J];
     if (s2kind) for (int k = 0; k < s.ld; ++k) s2kind[k] = s.s2kind[k];
-    if (bwdCols) for (int J = 0; J < s.nT; ++J) bwdCols[J] = s.bwdCols[J];
+    if (bwdCols) { for (int J = 0; J < s.nT; ++J) bwdCols[J] = -1; for (size_t k = 0; k < s.bwdCols.size(); ++k) bwdCols[k] = s.bwdCols[k]; }
+    return DBAT_OK;
+}
+// taskMode (nTasks), colOwner (nT), ownSBegin (nParts+1) of the last analysis
+extern "C" int dbat_tile_symbolic_get2(int64_t* taskMode, int64_t* colOwner, int64_t* ownSBegin) {
+    const TileSym& s = g_last_sym;
+    if (s.nT == 0) return DBAT_E_BADARG;
+    if (taskMode) for (int t = 0; t < s.nTasks; ++t) taskMode[t] = s.taskMode[t];
+    if (colOwner) for (int J = 0; J < s.nT; ++J) colOwner[J] = s.colOwner[J];
+    if (ownSBegin) for (size_t k = 0; k < s.ownSBegin.size(); ++k) ownSBegin[k] = s.ownSBegin[k];
     return DBAT_OK;
 }

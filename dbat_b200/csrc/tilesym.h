@@ -16,8 +16,18 @@ struct TileSym {
     int nT = 0;                    // tile rows / columns
     int ld = 0;                    // order of the padded system = nT * TC_T; the last row carries the rhs
     int nS = 0;                    // number of real unknowns in S (EO + IO columns)
-    int nSlots = 0, nSlotsS = 0;   // stored tiles; the first nSlotsS belong to the pattern of S itself (rest: fill)
-    int nTasks = 0, depth = 0;
+    // stored tiles.  Slot order: [top S | top fill | owned-by-part-0 S | ... | owned-by-part-(nParts-1) S | owned fill ...]
+    // ("top" = tile columns every rank factors; with one part everything is top).  nSlotsS counts the tiles of
+    // the pattern of S itself: the ranges [0, nTopS) and [nTop, nTop + nOwnS).
+    int nSlots = 0, nSlotsS = 0;
+    int nTopS = 0, nTop = 0, nOwnS = 0;
+    int nParts = 1, myPart = 0;
+    std::vector<int> ownSBegin;    // nParts + 1: slot range of the S tiles owned by every part
+    std::vector<int> colOwner;     // per tile column: owning part, -1 = top
+    int nTasks = 0, nTasks1 = 0, depth = 0;   // tasks [0, nTasks1): phase 1 (own columns + partial sums into top tiles),
+                                              // [nTasks1, nTasks): phase 2 (top columns, after the partial sums are reduced)
+    std::vector<unsigned char> taskMode;      // 0 = final (factor / solve, sets the tile's flag), 1 = partial sum only
+    int nBwd1 = 0;                            // bwdCols[0, nBwd1): top columns; [nBwd1, ..): this part's own columns
     int64_t nTerms = 0;
     int order_mode = 0;            // 0 natural, 1 rcm, 2 nested dissection
     int nSeg = 0;
@@ -39,8 +49,10 @@ struct TileSym {
 // adjacency of the co-visibility graph in CSR form (no self loops needed); nEO[i] = number of estimated
 // EO elements of image i (0..6); nIO = number of estimated shared IO columns.
 // mode: 0 natural, 1 rcm, 2 nested dissection, -1 automatic.
+// nParts / myPart: distributed factorisation - the elimination tree is cut into nParts (a power of two) subtrees,
+// part g factors the columns of subtree g, everybody the separators above the cut (nParts = 1: everything local).
 int tile_symbolic(int nImg, const int64_t* adjPtr, const int32_t* adj, const int* nEO, int nIO, int mode,
-                  int leafImages, TileSym& out);
+                  int leafImages, TileSym& out, int nParts = 1, int myPart = 0);
 
 // co-visibility graph from (0-based) point-major image lists
 void covis_graph(int nImg, int nOP, const int* pt_start, const int* img_pm, std::vector<int64_t>& adjPtr,

@@ -181,6 +181,11 @@ int dbat_tile_symbolic(int64_t nImg, int64_t nOP, int64_t nObs, const int64_t *o
                        const int64_t *nEO, int64_t nIO, int64_t mode, int64_t leafImages, int64_t *counts);
 int dbat_tile_symbolic_get(int64_t *imgS, int64_t *tix, int64_t *taskIJ, int64_t *termPtr, int64_t *termAB,
                            int64_t *level, int64_t *s2kind, int64_t *bwdCols);
+/* Distributed factorisation: counts[14], counts[15] of dbat_tile_symbolic are, on entry, the number of parts the
+ * elimination tree is cut into and the part whose task lists are wanted (0, 0: one part); on return counts[11..15] =
+ * {nTasks1 (tasks of phase 1), nTopS, nTop (slots of the top tile columns), parts actually used, nOwnS}.
+ * dbat_tile_symbolic_get2: taskMode (nTasks; 1 = partial sum), colOwner (nT; -1 = top), ownSBegin (parts + 1). */
+int dbat_tile_symbolic_get2(int64_t *taskMode, int64_t *colOwner, int64_t *ownSBegin);
 
 /* The sparse tile solver on its own (unit tests / profiling): x = A^-1 b for a symmetric positive definite
  * column-major n x n matrix whose 6-column blocks play the role of images (coupled where A has a non-zero),
