@@ -59,7 +59,8 @@ EXPORTS = ['dbat_create', 'dbat_destroy', 'dbat_last_error', 'dbat_num_unknowns'
            'dbat_default_opts', 'dbat_solve', 'dbat_normal_step', 'dbat_cov',
            'dbat_comm_unique_id', 'dbat_comm_init', 'dbat_phase_times', 'dbat_dense_chol_solve',
            'dbat_forwintersect', 'dbat_forwintersect_error', 'dbat_resect3', 'dbat_camera_order',
-           'dbat_tile_symbolic', 'dbat_tile_symbolic_get', 'dbat_tile_symbolic_get2', 'dbat_tile_chol_solve',
+           'dbat_tile_symbolic', 'dbat_tile_symbolic_get', 'dbat_tile_symbolic_get2', 'dbat_tile_symbolic_coords',
+           'dbat_tile_chol_solve',
            'dbat_reduced_info']
 
 _lib = None
@@ -137,6 +138,8 @@ def lib():
     L.dbat_tile_symbolic.restype = C.c_int
     L.dbat_tile_symbolic_get.argtypes = [c_ip] * 8
     L.dbat_tile_symbolic_get.restype = C.c_int
+    L.dbat_tile_symbolic_coords.argtypes = [C.c_int64, c_dp]
+    L.dbat_tile_symbolic_coords.restype = C.c_int
     L.dbat_tile_symbolic_get2.argtypes = [c_ip] * 3
     L.dbat_tile_symbolic_get2.restype = C.c_int
     L.dbat_tile_chol_solve.argtypes = [C.c_int64, c_dp, c_dp, c_dp, C.c_int64, C.c_int64, C.c_int, c_dp]
@@ -194,12 +197,17 @@ def camera_order(img, op, nImg, nOP):
     return perm - 1, int(bw.value)
 
 
-def tile_symbolic(img, op, nImg, nOP, nEO, nIO, mode=-1, leaf=120, parts=1, part=0):
+def tile_symbolic(img, op, nImg, nOP, nEO, nIO, mode=-1, leaf=120, parts=1, part=0, xyz=None):
     """Symbolic analysis of the reduced camera system (host code in the library): dict of counts + arrays.
     parts / part: task lists of one part of a distributed factorisation."""
     img1, op1, ne = i64(np.asarray(img) + 1), i64(np.asarray(op) + 1), i64(nEO)
     cnt = np.zeros(16, dtype=np.int64)
     cnt[14], cnt[15] = parts, part
+    if xyz is not None:
+        c = np.ascontiguousarray(np.asarray(xyz, dtype=np.float64).T)      # 3 x nImg column-major = nImg x 3 C order
+        lib().dbat_tile_symbolic_coords(nImg, dptr(c))
+    else:
+        lib().dbat_tile_symbolic_coords(0, None)
     rc = lib().dbat_tile_symbolic(nImg, nOP, len(img1), iptr(img1), iptr(op1), iptr(ne), nIO, mode, leaf, iptr(cnt))
     if rc != 0:
         raise DbatError(rc, 'dbat_tile_symbolic failed')

@@ -97,7 +97,7 @@ struct dbat_handle {
     std::vector<int> h_x2s;             // x column (camera side) -> S index
     double* d_dS = nullptr;             // Jacobi scale per S index
     unsigned long long* d_stats = nullptr;   // pivot statistics exchanged between the ranks
-    std::vector<int> h_nEO; int h_nIOest = 0; std::vector<int64_t> h_adjPtr; std::vector<int32_t> h_adj;   // for re-tiling in dbat_comm_init
+    std::vector<double> h_xyz; std::vector<int> h_nEO; int h_nIOest = 0; std::vector<int64_t> h_adjPtr; std::vector<int32_t> h_adj;   // for re-tiling in dbat_comm_init
     bool params_valid = false;          // parameter arrays correspond to d_x
     bool normal_valid = false;          // Gram / point records correspond to d_x
     // comm
@@ -172,7 +172,8 @@ static int setup_reduced(dbat_handle* h, int nParts, int myPart) {
     DevProblem& P = h->P;
     const int nImg = P.nImg, nC = P.nC;
     TileSym sym;
-    if (tile_symbolic(nImg, h->h_adjPtr.data(), h->h_adj.data(), h->h_nEO.data(), h->h_nIOest, -1, 120, sym, nParts, myPart)) {
+    if (tile_symbolic(nImg, h->h_adjPtr.data(), h->h_adj.data(), h->h_nEO.data(), h->h_nIOest, -1, 120, sym, nParts, myPart,
+                      h->h_xyz.size() == 3 * (size_t)nImg ? h->h_xyz.data() : nullptr)) {
         h->err = "symbolic analysis of the reduced system failed"; return DBAT_E_STATE;
     }
     std::vector<int> sh_s(DBAT_NSLOT, -1), eo_s((size_t)6 * nImg, -1), s2x(sym.ld, -1);
@@ -425,6 +426,8 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
             }
             adjPtr[nImg] = (int64_t)adj.size();
         }
+        h->h_xyz.resize((size_t)3 * nImg);
+        for (int i = 0; i < nImg; ++i) for (int a = 0; a < 3; ++a) h->h_xyz[3 * (size_t)i + a] = d->EOval[6 * (size_t)i + a];
         h->h_nEO.assign(nImg, 0);
         for (int i = 0; i < nImg; ++i) for (int a = 0; a < 6; ++a) if (colEO[(size_t)i * 6 + a] >= 0) h->h_nEO[i]++;
         h->h_nIOest = 0;

@@ -186,6 +186,9 @@ int dbat_tile_symbolic_get(int64_t *imgS, int64_t *tix, int64_t *taskIJ, int64_t
  * {nTasks1 (tasks of phase 1), nTopS, nTop (slots of the top tile columns), parts actually used, nOwnS}.
  * dbat_tile_symbolic_get2: taskMode (nTasks; 1 = partial sum), colOwner (nT; -1 = top), ownSBegin (parts + 1). */
 int dbat_tile_symbolic_get2(int64_t *taskMode, int64_t *colOwner, int64_t *ownSBegin);
+/* Station coordinates (3 x nImg) for the next dbat_tile_symbolic call: the dissection then bisects geometrically
+ * (dbat_create takes them from EOval); nImg = 0 / NULL clears them. */
+int dbat_tile_symbolic_coords(int64_t nImg, const double *xyz);
 
 /* The sparse tile solver on its own (unit tests / profiling): x = A^-1 b for a symmetric positive definite
  * column-major n x n matrix whose 6-column blocks play the role of images (coupled where A has a non-zero),
