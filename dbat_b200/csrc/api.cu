@@ -31,7 +31,7 @@ static std::string g_create_err;
         }                                                                                          \
     } while (0)
 
-enum { SC_RR = 0, SC_JP2 = 1, SC_RJP = 2, SC_TRACE = 3, SC_A = 4, SC_B = 5, SC_C = 6, SC_PRR = 7, SC_N = 16 };
+enum { SC_RR = 0, SC_JP2 = 1, SC_RJP = 2, SC_TRACE = 3, SC_A = 4, SC_B = 5, SC_C = 6, SC_PRR = 7, SC_JPP = 8 /* 8..11 */, SC_N = 16 };
 enum { PH_EVAL = 0, PH_SCHUR, PH_CHOL, PH_SOLVE, PH_TRIAL, PH_JP, PH_TOTAL, PH_N };
 static const char* kPhaseNames[PH_N] = {"eval_jac_assembly", "build_schur", "cholesky", "solve_backsub",
                                         "trial_residual", "jp_stats", "total"};
@@ -98,6 +98,8 @@ struct dbat_handle {
     double* d_dS = nullptr;             // Jacobi scale per S index
     unsigned long long* d_stats = nullptr;   // pivot statistics exchanged between the ranks
     std::vector<double> h_xyz; std::vector<int> h_nEO; int h_nIOest = 0; std::vector<int64_t> h_adjPtr; std::vector<int32_t> h_adj;   // for re-tiling in dbat_comm_init
+    const double* jp_vec = nullptr;     // vector whose |Jp|^2, r'Jp came out of the last back-substitution (nullptr: none)
+    double jp_cache[2] = {0, 0};
     bool params_valid = false;          // parameter arrays correspond to d_x
     bool normal_valid = false;          // Gram / point records correspond to d_x
     // comm
@@ -393,6 +395,7 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
             recs[i].io = ioOfImg[i];
         }
         UP(P.img, recs);
+        { int* d_imgio; UP(d_imgio, ioOfImg); P.img_io = d_imgio; }
         AL(P.io, h->nIOrec);
         UP(h->d_rep, rep);
     }
@@ -468,6 +471,26 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
         AL(P.Y, (size_t)std::max(1, nObs) * DBAT_W_STRIDE);
         AL(P.ptaux, (size_t)std::max(1, nOP) * DBAT_PTAUX_STRIDE);
         AL(P.shPart, (size_t)((nOP + DBAT_SHCHUNK - 1) / DBAT_SHCHUNK + 1) * DBAT_NSLOT * DBAT_SHCOLS);
+    }
+    {   // point-side assembly blocks: runs [begin, end) of whole points with at most DBAT_PSB observations (and at most
+        // DBAT_PSB / 2 points); a point with more observations than that goes to the one-thread-per-point kernel
+        std::vector<int> pairs, bigp;
+        int begin = 0, cnt = 0;
+        auto close = [&](int end) { if (end > begin) { pairs.push_back(begin); pairs.push_back(end); } begin = end; cnt = 0; };
+        for (int j = 0; j < nOP; ++j) {
+            const int k = h->h_pt_start[j + 1] - h->h_pt_start[j];
+            if (k > DBAT_PSB) { close(j); bigp.push_back(j); begin = j + 1; continue; }
+            if (cnt + k > DBAT_PSB || j - begin >= DBAT_PSB / 2) close(j);
+            cnt += k;
+        }
+        close(nOP);
+        P.nPsb = (int)pairs.size() / 2;
+        P.nPsbig = (int)bigp.size();
+        if (pairs.empty()) pairs.assign(2, 0);
+        if (bigp.empty()) bigp.push_back(0);
+        int *d_pairs, *d_bigp;
+        UP(d_pairs, pairs); UP(d_bigp, bigp);
+        P.psb_pt = d_pairs; P.psbig = d_bigp;
     }
     {   // grouped Schur index: estimated points sorted by (ray count, image list)
         std::vector<int> cand, big;
@@ -545,7 +568,8 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
         AL(P.vinv, (size_t)std::max(1, nOP) * 8);
     }
     AL(h->d_tmpG, (size_t)64 * DBAT_GSZ);
-    const int nPartial = 2 * ((std::max(nObs, P.n) + 255) / 256) + 64;
+    const int nPartial = std::max(2 * ((std::max(nObs, P.n) + 255) / 256),
+                                  2 * (P.nPsb + (P.nPsbig + 127) / 128 + (nOP + 127) / 128 + 1) + 2 * ((nImg + 3) / 4 + 1)) + 64;
     AL(h->d_partial, nPartial);
     AL(h->d_scal, SC_N);
     AL(h->d_x, P.n); AL(h->d_t, P.n); AL(h->d_p, P.n); AL(h->d_pgn, P.n); AL(h->d_g, P.n);
@@ -637,6 +661,7 @@ static inline double gram_host(const double* G, int R, int C) {
 static int eval_full(dbat_handle* h) {
     size_t a = ph_begin(h);
     h->cscWeighted = -1;                    // any cached Jacobian export belongs to an older x
+    h->jp_vec = nullptr;
     set_params(h, h->d_x);
     h->params_valid = true;
     launch_cam_side(h->P, h->d_img_chunk_start, h->d_tmpG, h->st);
@@ -678,6 +703,7 @@ static int eval_rr(dbat_handle* h, const double* xdev, double* rr) {
 
 // |J v|^2 and r'(J v) with J, r at d_x
 static int eval_jp(dbat_handle* h, const double* v, double* jp2, double* rjp) {
+    if (v == h->jp_vec && v) { *jp2 = h->jp_cache[0]; *rjp = h->jp_cache[1]; return 0; }   // by-product of solve_step
     size_t a = ph_begin(h);
     if (!h->params_valid) { set_params(h, h->d_x); h->params_valid = true; }
     launch_jp(h->P, h->d_x, v, h->d_partial, h->d_scal, SC_JP2, SC_RJP, h->st);
@@ -771,7 +797,13 @@ static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, 
         if (rc) return rc;
     }
     launch_unpermute(P, tc.xs, jacobi ? h->d_dscale : nullptr, h->d_pc, h->st);
-    launch_backsub(P, lambda, h->d_pc, pout, h->st);
+    static const bool fusedJp = !getenv("DBAT_JP_SEPARATE");
+    double* jpOut = fusedJp ? h->d_scal + SC_JPP : nullptr;
+    launch_backsub(P, lambda, h->d_pc, pout, h->d_partial, h->d_camDiag, h->d_camG, jpOut, h->st);
+    if (jpOut) {
+        if (h->nranks > 1) { int rc = allreduce(h, jpOut, 2); if (rc) return rc; }     // point parts; the camera part is global already
+        cudaMemcpyAsync(h->h_scal + SC_JPP, jpOut, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    }
     int info = 0; unsigned long long mmb[2] = {0, 0};
     cudaMemcpyAsync(&info, tc.d.info, sizeof(int), cudaMemcpyDeviceToHost, h->st);
     cudaMemcpyAsync(mmb, tc.d.minmax, sizeof(mmb), cudaMemcpyDeviceToHost, h->st);
@@ -782,6 +814,12 @@ static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, 
     // Cholesky factor rcond ~ (min pivot / max pivot)^2.
     double mm[2];
     memcpy(mm, mmb, sizeof(mm));
+    h->jp_vec = nullptr;
+    if (jpOut) {
+        h->jp_cache[0] = h->h_scal[SC_JPP] + h->h_scal[SC_JPP + 2];
+        h->jp_cache[1] = h->h_scal[SC_JPP + 1] + h->h_scal[SC_JPP + 3];
+        h->jp_vec = pout;
+    }
     const double ratio = mm[1] > 0 ? mm[0] / mm[1] : 1.0;      // no camera-side unknown at all: nothing to be singular
     *singular = (info != 0) || !(ratio * ratio > 2.220446049250313e-16);
     return 0;

@@ -10,6 +10,7 @@
 //   k_point_side (point-major order, one thread per object point): V_j, g_j, the IO x OP
 //                cross block and the per-observation EO x OP cross blocks W_o.
 // Both are HBM-bound streams (48-52 B read per observation).
+#include <cstdlib>
 #include "kernels.cuh"
 #include "launch.h"
 
@@ -94,14 +95,42 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 #endif
 #define XT_LD 68   // 64 rows + 4: fragment loads (8 cols x 4 rows) hit 32 distinct bank pairs
 
+// One image and one IO record serve a whole chunk: they are staged in shared memory by two TMA bulk copies
+// (cp.async.bulk + mbarrier) instead of living in ~56 registers of every thread.
+__device__ __forceinline__ void tma_stage(void* sdst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(sdst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(d), "l"(gsrc), "r"(bytes), "r"(b) : "memory");
+}
 template <int MODEL>
-__global__ void __launch_bounds__(128, DBAT_EVAL_MINBLOCKS) k_cam_side(DevProblem P) {
+__global__ void __launch_bounds__(128, 3) k_cam_side(DevProblem P) {
     extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(16) ImgRec s_g;
+    __shared__ __align__(16) IORec s_io;
+    __shared__ __align__(8) unsigned long long s_bar;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* Xt = smem + (size_t)warp * DBAT_GW * XT_LD;    // [GW][XT_LD] per warp
     const Chunk ck = P.chunks[blockIdx.x];
-    const ImgRec g = P.img[ck.img];
-    const IORec io = P.io[g.io];
+    if (threadIdx.x == 0) {
+        const unsigned b = (unsigned)__cvta_generic_to_shared(&s_bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(b) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"((unsigned)(sizeof(ImgRec) + sizeof(IORec))) : "memory");
+        const ImgRec* gi = P.img + ck.img;
+        tma_stage(&s_g, gi, sizeof(ImgRec), &s_bar);
+        tma_stage(&s_io, P.io + P.img_io[ck.img], sizeof(IORec), &s_bar);
+    }
+    __syncthreads();
+    {
+        const unsigned b = (unsigned)__cvta_generic_to_shared(&s_bar);
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(b) : "memory");
+        }
+    }
+    const ImgRec& g = s_g;
+    const IORec& io = s_io;
 
     double acc[DBAT_GTP][2];
 #pragma unroll
@@ -187,22 +216,22 @@ __global__ void k_cam_reduce(DevProblem P, const int* __restrict__ img_chunk_sta
     }
 }
 
-// sum over images, two fixed levels (64 groups, then 1)
-__global__ void k_sh_reduce1(DevProblem P, double* __restrict__ tmp) {
-    const int gsz = (P.nImg + gridDim.x - 1) / gridDim.x;
-    const int i0 = blockIdx.x * gsz, i1 = min(P.nImg, i0 + gsz);
-    for (int e = threadIdx.x; e < DBAT_GSZ; e += blockDim.x) {
-        double s = 0.0;
-        for (int i = i0; i < i1; ++i) s += P.imgG[(size_t)i * DBAT_GSZ + e];
-        tmp[(size_t)blockIdx.x * DBAT_GSZ + e] = s;
+// sum over images in ONE launch: block b owns 64 Gram entries, its four thread groups a quarter of the images each
+// (fixed order: bit-reproducible)
+__global__ void __launch_bounds__(256) k_sh_reduce(DevProblem P) {
+    __shared__ double part[4][64];
+    const int e = blockIdx.x * 64 + (threadIdx.x & 63), q = threadIdx.x >> 6;
+    const int per = (P.nImg + 3) / 4, i0 = q * per, i1 = min(P.nImg, i0 + per);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int i = i0;
+    for (; i + 3 < i1; i += 4) {
+        s0 += P.imgG[(size_t)i * DBAT_GSZ + e]; s1 += P.imgG[(size_t)(i + 1) * DBAT_GSZ + e];
+        s2 += P.imgG[(size_t)(i + 2) * DBAT_GSZ + e]; s3 += P.imgG[(size_t)(i + 3) * DBAT_GSZ + e];
     }
-}
-__global__ void k_sh_reduce2(DevProblem P, const double* __restrict__ tmp, int ngroups) {
-    for (int e = threadIdx.x; e < DBAT_GSZ; e += blockDim.x) {
-        double s = 0.0;
-        for (int gI = 0; gI < ngroups; ++gI) s += tmp[(size_t)gI * DBAT_GSZ + e];
-        P.shG[e] = s;
-    }
+    for (; i < i1; ++i) s0 += P.imgG[(size_t)i * DBAT_GSZ + e];
+    part[q][threadIdx.x & 63] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (threadIdx.x < 64) P.shG[e] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
 }
 
 template <int MODEL>
@@ -216,9 +245,9 @@ static void launch_cam_side_t(const DevProblem& P, const int* img_chunk_start, d
     }
     if (P.nChunks > 0) k_cam_side<MODEL><<<P.nChunks, 128, smem, st>>>(P);
     k_cam_reduce<<<P.nImg, 128, 0, st>>>(P, img_chunk_start);
-    k_sh_reduce1<<<64, 128, 0, st>>>(P, tmp);
-    k_sh_reduce2<<<1, 128, 0, st>>>(P, tmp, 64);
-    count_launch(4);
+    k_sh_reduce<<<DBAT_GSZ / 64, 256, 0, st>>>(P);
+    (void)tmp;
+    count_launch(3);
 }
 
 void launch_cam_side(const DevProblem& P, const int* img_chunk_start, double* tmp, cudaStream_t st) {
@@ -235,9 +264,10 @@ void launch_cam_side(const DevProblem& P, const int* img_chunk_start, double* tm
 // point side: one thread per object point
 // ---------------------------------------------------------------------------------------------
 template <int MODEL>
-__global__ void __launch_bounds__(128, DBAT_EVAL_MINBLOCKS) k_point_side(DevProblem P) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.nOP) return;
+__global__ void __launch_bounds__(128, DBAT_EVAL_MINBLOCKS) k_point_side(DevProblem P, const int* __restrict__ list, int nList) {
+    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (jj >= (list ? nList : P.nOP)) return;
+    const int j = list ? list[jj] : jj;
     const double Q[3] = {P.OPval[3 * (size_t)j], P.OPval[3 * (size_t)j + 1], P.OPval[3 * (size_t)j + 2]};
     double m[3];
 #pragma unroll
@@ -319,10 +349,106 @@ __global__ void k_prior_apply(DevProblem P, const double* __restrict__ x,
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// point side, one thread per OBSERVATION (default).  A block takes a run of whole points with at most DBAT_PSB
+// observations.  Phase 1: every thread evaluates its observation once (residual + all partials), writes the
+// EO x OP cross block W_o straight to global memory (nine 16-byte stores) and leaves the weighted rows
+// [A_op | r | A_io] of its observation in shared memory.  Phase 2: one thread per (point, item) - 14 IO slots, V, g -
+// sums the products over the point's observations in image order (deterministic) and writes its piece of the
+// point record.  No accumulator lives across observations, so the kernel needs half the registers of the
+// one-thread-per-point version and runs at three to four times its occupancy.
+// ---------------------------------------------------------------------------------------------
+#define PS_ROW 37      // doubles per observation row in shared memory: A_op 6 | r 2 | A_io 28 (+1: odd stride)
+template <int MODEL>
+__global__ void __launch_bounds__(DBAT_PSB, 3) k_point_side_obs(DevProblem P) {
+    __shared__ double rows[DBAT_PSB * PS_ROW];
+    const int tid = threadIdx.x;
+    const int p0 = P.psb_pt[2 * blockIdx.x], p1 = P.psb_pt[2 * blockIdx.x + 1];
+    const int ob0 = P.pt_start[p0], nob = P.pt_start[p1] - ob0;
+    if (tid < nob) {
+        const int ob = ob0 + tid;
+        const int j = P.pt_pm[ob];
+        const double2 uv = P.uv_pm[ob];
+        const double2 is = P.isig_pm[ob];
+        const ImgRec g = P.img[P.img_pm[ob]];
+        const IORec io = P.io[g.io];
+        const double Q[3] = {P.OPval[3 * (size_t)j], P.OPval[3 * (size_t)j + 1], P.OPval[3 * (size_t)j + 2]};
+        ObsJac o;
+        obs_model<MODEL, true, true>(Q, g, io, P.nK, P.nP, uv.x, uv.y, o);
+        double* row = rows + tid * PS_ROW;
+        double A[2][3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const double m = P.op_col[3 * (size_t)j + t] >= 0 ? 1.0 : 0.0;
+            A[0][t] = o.dOP[0][t] * is.x * m; A[1][t] = o.dOP[1][t] * is.y * m;
+            row[t] = A[0][t]; row[3 + t] = A[1][t];
+        }
+        row[6] = o.r[0] * is.x; row[7] = o.r[1] * is.y;
+#pragma unroll
+        for (int s = 0; s < DBAT_NSLOT; ++s) { row[8 + 2 * s] = o.dIO[s][0] * is.x; row[9 + 2 * s] = o.dIO[s][1] * is.y; }
+        double w[18];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double a0 = o.dC[0][c] * is.x, a1 = o.dC[1][c] * is.y;
+            const double b0 = o.dA[0][c] * is.x, b1 = o.dA[1][c] * is.y;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                w[c * 3 + t] = a0 * A[0][t] + a1 * A[1][t];
+                w[(3 + c) * 3 + t] = b0 * A[0][t] + b1 * A[1][t];
+            }
+        }
+        double2* Wo = reinterpret_cast<double2*>(P.W + (size_t)ob * DBAT_W_STRIDE);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) Wo[q] = make_double2(w[2 * q], w[2 * q + 1]);
+    }
+    __syncthreads();
+    const int nItems = (p1 - p0) * 16;
+    for (int item = tid; item < nItems; item += DBAT_PSB) {
+        const int j = p0 + (item >> 4), it = item & 15;
+        const int r0 = P.pt_start[j] - ob0, r1 = P.pt_start[j + 1] - ob0;
+        double* rec = P.pt + (size_t)j * DBAT_PT_STRIDE;
+        if (it < DBAT_NSLOT) {                               // IO slot x OP cross block
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            for (int r = r0; r < r1; ++r) {
+                const double* row = rows + r * PS_ROW;
+                const double u0 = row[8 + 2 * it], u1 = row[9 + 2 * it];
+                a0 += u0 * row[0] + u1 * row[3]; a1 += u0 * row[1] + u1 * row[4]; a2 += u0 * row[2] + u1 * row[5];
+            }
+            rec[DBAT_PT_WSH + 3 * it] = a0; rec[DBAT_PT_WSH + 3 * it + 1] = a1; rec[DBAT_PT_WSH + 3 * it + 2] = a2;
+        } else if (it == 14) {                               // V_j (upper triangle, row-wise)
+            double V[6] = {0, 0, 0, 0, 0, 0};
+            for (int r = r0; r < r1; ++r) {
+                const double* row = rows + r * PS_ROW;
+                V[0] += row[0] * row[0] + row[3] * row[3];
+                V[1] += row[0] * row[1] + row[3] * row[4];
+                V[2] += row[0] * row[2] + row[3] * row[5];
+                V[3] += row[1] * row[1] + row[4] * row[4];
+                V[4] += row[1] * row[2] + row[4] * row[5];
+                V[5] += row[2] * row[2] + row[5] * row[5];
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) rec[k] = V[k];
+        } else {                                             // g_j
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+            for (int r = r0; r < r1; ++r) {
+                const double* row = rows + r * PS_ROW;
+                g0 += row[0] * row[6] + row[3] * row[7]; g1 += row[1] * row[6] + row[4] * row[7]; g2 += row[2] * row[6] + row[5] * row[7];
+            }
+            rec[6] = g0; rec[7] = g1; rec[8] = g2; rec[9] = 0.0;
+        }
+    }
+}
+
 template <int MODEL>
 static void launch_point_side_t(const DevProblem& P, cudaStream_t st) {
-    if (P.nOP > 0) k_point_side<MODEL><<<(P.nOP + 127) / 128, 128, 0, st>>>(P);
-    count_launch();
+    static const bool perPoint = getenv("DBAT_POINT_SIDE_PER_POINT") != nullptr;
+    if (perPoint || !P.psb_pt) {
+        if (P.nOP > 0) k_point_side<MODEL><<<(P.nOP + 127) / 128, 128, 0, st>>>(P, nullptr, 0);
+        count_launch();
+        return;
+    }
+    if (P.nPsb > 0) { k_point_side_obs<MODEL><<<P.nPsb, DBAT_PSB, 0, st>>>(P); count_launch(); }
+    if (P.nPsbig > 0) { k_point_side<MODEL><<<(P.nPsbig + 127) / 128, 128, 0, st>>>(P, P.psbig, P.nPsbig); count_launch(); }
 }
 void launch_point_side(const DevProblem& P, cudaStream_t st) {
     switch (P.model) {
@@ -403,7 +529,7 @@ static void launch_resid_t(const DevProblem& P, const double* x, double* partial
         if (r_out) k_resid<MODEL, true><<<nb, RES_BLOCK, 0, st>>>(P, partial, (double2*)r_out, weighted);
         else       k_resid<MODEL, false><<<nb, RES_BLOCK, 0, st>>>(P, partial, nullptr, weighted);
     }
-    k_final_sum<<<1, 256, 0, st>>>(partial, nb, scal, slot, 0);
+    k_final_sum<<<1, 1024, 0, st>>>(partial, nb, scal, slot, 0);
     count_launch(2);
     if (P.nPrior > 0) {
         k_prior_resid<<<1, 256, 0, st>>>(P, x, partial, r_out ? r_out + 2 * (size_t)P.nObs : nullptr, weighted);

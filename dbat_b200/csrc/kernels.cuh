@@ -11,6 +11,7 @@
 #define DBAT_GSZ (DBAT_GTP * 64)   // doubles per Gram in C-fragment tile layout
 #define DBAT_COL_EO DBAT_NSLOT     // first EO column in the Gram
 #define DBAT_COL_R (DBAT_NSLOT + 6)
+#define DBAT_PSB 128                // observations per block of the point-side assembly kernel
 #define DBAT_CHUNK 1024            // max observations per camera-side chunk (one CTA)
 #define DBAT_PT_STRIDE 52          // doubles per point record: V[6] g[3] pad Wsh[14][3]
 #define DBAT_PT_WSH 10
@@ -37,10 +38,17 @@ struct DevProblem {
     // observations, point-major
     const double2* uv_pm; const double2* isig_pm; const int* img_pm; const int* pm2cm;
     const int* pt_start;   // nOP+1
+    // point-side assembly: blocks of whole points with at most DBAT_PSB observations (one thread per observation);
+    // points with more observations than that go through the one-thread-per-point kernel
+    const int* psb_pt;     // nPsb pairs [first point, end point) of every block
+    int nPsb;
+    const int* psbig;      // points with more than DBAT_PSB observations
+    int nPsbig;
     const Chunk* chunks;
     // current parameter values
     double* IOval; double* EOval; double* OPval;   // NC x nImg, 6 x nImg, 3 x nOP
     ImgRec* img; IORec* io;
+    const int* img_io;     // nImg: index of every image's IO record (the io field of ImgRec, for the staging copy)
     // column maps (0-based x column, -1 = fixed)
     const int* sh_col;     // NSLOT
     const int* eo_col;     // nImg x 6

@@ -31,7 +31,8 @@ void launch_schur(const DevProblem& P, double lambda, cudaStream_t st);
 void launch_point_vinv(const DevProblem& P, double lambda, cudaStream_t st);   // P.vinv = (V_j + lambda I)^-1
 void launch_scale_prep(const DevProblem& P, const double* d, double* dS, cudaStream_t st);
 void launch_unpermute(const DevProblem& P, const double* xs, const double* d, double* pc, cudaStream_t st);
-void launch_backsub(const DevProblem& P, double lambda, const double* pc, double* p, cudaStream_t st);
+void launch_backsub(const DevProblem& P, double lambda, const double* pc, double* p, double* partial,
+                    const double* camDiag, const double* camG, double* jpOut, cudaStream_t st);
 void launch_vec_ops_sum(const double* a, int n, double* partial, double* scal, int slot, cudaStream_t st);
 void launch_dot(const double* a, const double* b, int n, double* partial, double* scal, int slot, cudaStream_t st);
 void launch_axpy(double alpha, const double* x, const double* y, double* out, int n, cudaStream_t st);

@@ -731,44 +731,220 @@ void launch_unpermute(const DevProblem& P, const double* xs, const double* d, do
     count_launch();
 }
 
-// back-substitution for the object points; p[0:nC] must already hold the camera/IO step
-__global__ void __launch_bounds__(128) k_backsub(DevProblem P, double lambda, double* __restrict__ p) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.nOP) return;
-    const int* opc = P.op_col + 3 * (size_t)j;
-    if (opc[0] < 0 && opc[1] < 0 && opc[2] < 0) return;
-    const double* rec = P.pt + (size_t)j * DBAT_PT_STRIDE;
-    double Vi[6];
-    point_inverse(rec, opc, lambda, Vi);
-    double t[3] = {-rec[6], -rec[7], -rec[8]};
+// back-substitution for the object points; p[0:nC] must already hold the camera/IO step.
+// By-product (stats != nullptr): this block's share of  p'J'Jp = |Jp|^2  and  r'Jp = g'p  over the point
+// columns, from the blocks already in registers - with a_j = W~_j' p_c and the UNDAMPED V_j, g_j:
+//     |Jp|^2 = p_c' N_cc p_c + sum_j ( p_j' V_j p_j + 2 p_j' a_j ),     r'Jp = g_c' p_c + sum_j g_j' p_j
+// (levenberg_marquardt.m:162 forms J*p explicitly; same number, one pass over the observations less).
+__global__ void __launch_bounds__(128) k_backsub(DevProblem P, double lambda, double* __restrict__ p,
+                                                  double* __restrict__ stats, int statStride,
+                                                  const int* __restrict__ list, int nList) {
+    __shared__ double red[2][4];
+    const int jj = blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = list ? (jj < nList ? list[jj] : P.nOP) : jj;
+    double jp2 = 0.0, rjp = 0.0;
+    if (j < P.nOP) {
+        const int* opc = P.op_col + 3 * (size_t)j;
+        if (!(opc[0] < 0 && opc[1] < 0 && opc[2] < 0)) {
+            const double* rec = P.pt + (size_t)j * DBAT_PT_STRIDE;
+            double Vi[6];
+            point_inverse(rec, opc, lambda, Vi);
+            double a[3] = {0.0, 0.0, 0.0};                  // W~_j' p_c
 #pragma unroll
-    for (int s = 0; s < DBAT_NSLOT; ++s) {
-        const int c = P.sh_col[s];
-        if (c < 0) continue;
-        const double pv = p[c];
-        const double* ws = rec + DBAT_PT_WSH + 3 * s;
-        t[0] -= ws[0] * pv; t[1] -= ws[1] * pv; t[2] -= ws[2] * pv;
-    }
-    const int o0 = P.pt_start[j], o1 = P.pt_start[j + 1];
-    for (int ob = o0; ob < o1; ++ob) {
-        const int* ec = P.eo_col + 6 * (size_t)P.img_pm[ob];
-        const double* Wo = P.W + (size_t)ob * DBAT_W_STRIDE;
+            for (int s = 0; s < DBAT_NSLOT; ++s) {
+                const int c = P.sh_col[s];
+                if (c < 0) continue;
+                const double pv = p[c];
+                const double* ws = rec + DBAT_PT_WSH + 3 * s;
+                a[0] += ws[0] * pv; a[1] += ws[1] * pv; a[2] += ws[2] * pv;
+            }
+            const int o0 = P.pt_start[j], o1 = P.pt_start[j + 1];
+            for (int ob = o0; ob < o1; ++ob) {
+                const int* ec = P.eo_col + 6 * (size_t)P.img_pm[ob];
+                const double* Wo = P.W + (size_t)ob * DBAT_W_STRIDE;
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            const int c = ec[a];
-            if (c < 0) continue;
-            const double pv = p[c];
-            t[0] -= Wo[3 * a] * pv; t[1] -= Wo[3 * a + 1] * pv; t[2] -= Wo[3 * a + 2] * pv;
+                for (int e = 0; e < 6; ++e) {
+                    const int c = ec[e];
+                    if (c < 0) continue;
+                    const double pv = p[c];
+                    a[0] += Wo[3 * e] * pv; a[1] += Wo[3 * e + 1] * pv; a[2] += Wo[3 * e + 2] * pv;
+                }
+            }
+            const double t[3] = {-rec[6] - a[0], -rec[7] - a[1], -rec[8] - a[2]};
+            double y[3];
+            symv3(Vi, t, y);
+#pragma unroll
+            for (int e = 0; e < 3; ++e) if (opc[e] >= 0) p[opc[e]] = y[e]; else y[e] = 0.0;
+            const double Vy0 = rec[0] * y[0] + rec[1] * y[1] + rec[2] * y[2];
+            const double Vy1 = rec[1] * y[0] + rec[3] * y[1] + rec[4] * y[2];
+            const double Vy2 = rec[2] * y[0] + rec[4] * y[1] + rec[5] * y[2];
+            jp2 = y[0] * (Vy0 + 2.0 * a[0]) + y[1] * (Vy1 + 2.0 * a[1]) + y[2] * (Vy2 + 2.0 * a[2]);
+            rjp = rec[6] * y[0] + rec[7] * y[1] + rec[8] * y[2];
         }
     }
-    double y[3];
-    symv3(Vi, t, y);
+    if (stats) {                                             // fixed-order block sums: bit-reproducible
 #pragma unroll
-    for (int a = 0; a < 3; ++a) if (opc[a] >= 0) p[opc[a]] = y[a];
+        for (int o = 16; o > 0; o >>= 1) { jp2 += __shfl_xor_sync(0xffffffffu, jp2, o); rjp += __shfl_xor_sync(0xffffffffu, rjp, o); }
+        if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = jp2; red[1][threadIdx.x >> 5] = rjp; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            stats[blockIdx.x] = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+            stats[statStride + blockIdx.x] = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+        }
+    }
 }
-void launch_backsub(const DevProblem& P, double lambda, const double* pc, double* p, cudaStream_t st) {
+// The same back-substitution with one thread per OBSERVATION for the streaming part (default): the blocks of
+// k_point_side_obs (whole points, at most DBAT_PSB observations).  Phase 1: thread o reads its cross block W_o
+// (144 contiguous bytes, consecutive threads consecutive blocks: fully coalesced) and the six EO entries of p_c
+// of its image and leaves a_o = W_o' p_c in shared memory.  Phase 2: one thread per point adds the a_o of its
+// observations in image order, the shared IO part, solves with (V_j + lambda I)^-1 and forms the |Jp|^2 / r'Jp terms.
+__global__ void __launch_bounds__(DBAT_PSB) k_backsub_obs(DevProblem P, double lambda, double* __restrict__ p,
+                                                           double* __restrict__ stats, int statStride) {
+    __shared__ double ao[DBAT_PSB * 3];
+    __shared__ double red[2][DBAT_PSB / 32];
+    const int tid = threadIdx.x;
+    const int p0 = P.psb_pt[2 * blockIdx.x], p1 = P.psb_pt[2 * blockIdx.x + 1];
+    const int ob0 = P.pt_start[p0], nob = P.pt_start[p1] - ob0;
+    if (tid < nob) {
+        const int ob = ob0 + tid;
+        const int* ec = P.eo_col + 6 * (size_t)P.img_pm[ob];
+        const double2* Wo = reinterpret_cast<const double2*>(P.W + (size_t)ob * DBAT_W_STRIDE);
+        double w[18];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) { const double2 t = Wo[q]; w[2 * q] = t.x; w[2 * q + 1] = t.y; }
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+        for (int e = 0; e < 6; ++e) {
+            const int c = ec[e];
+            const double pv = c >= 0 ? p[c] : 0.0;
+            a0 += w[3 * e] * pv; a1 += w[3 * e + 1] * pv; a2 += w[3 * e + 2] * pv;
+        }
+        ao[3 * tid] = a0; ao[3 * tid + 1] = a1; ao[3 * tid + 2] = a2;
+    }
+    __syncthreads();
+    double jp2 = 0.0, rjp = 0.0;
+    const int j = p0 + tid;
+    if (j < p1) {
+        const int* opc = P.op_col + 3 * (size_t)j;
+        if (!(opc[0] < 0 && opc[1] < 0 && opc[2] < 0)) {
+            const double* rec = P.pt + (size_t)j * DBAT_PT_STRIDE;
+            double Vi[6];
+            point_inverse(rec, opc, lambda, Vi);
+            double a[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+            for (int s = 0; s < DBAT_NSLOT; ++s) {
+                const int c = P.sh_col[s];
+                if (c < 0) continue;
+                const double pv = p[c];
+                const double* ws = rec + DBAT_PT_WSH + 3 * s;
+                a[0] += ws[0] * pv; a[1] += ws[1] * pv; a[2] += ws[2] * pv;
+            }
+            for (int r = P.pt_start[j] - ob0; r < P.pt_start[j + 1] - ob0; ++r) { a[0] += ao[3 * r]; a[1] += ao[3 * r + 1]; a[2] += ao[3 * r + 2]; }
+            const double t[3] = {-rec[6] - a[0], -rec[7] - a[1], -rec[8] - a[2]};
+            double y[3];
+            symv3(Vi, t, y);
+#pragma unroll
+            for (int e = 0; e < 3; ++e) if (opc[e] >= 0) p[opc[e]] = y[e]; else y[e] = 0.0;
+            const double Vy0 = rec[0] * y[0] + rec[1] * y[1] + rec[2] * y[2];
+            const double Vy1 = rec[1] * y[0] + rec[3] * y[1] + rec[4] * y[2];
+            const double Vy2 = rec[2] * y[0] + rec[4] * y[1] + rec[5] * y[2];
+            jp2 = y[0] * (Vy0 + 2.0 * a[0]) + y[1] * (Vy1 + 2.0 * a[1]) + y[2] * (Vy2 + 2.0 * a[2]);
+            rjp = rec[6] * y[0] + rec[7] * y[1] + rec[8] * y[2];
+        }
+    }
+    if (stats) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { jp2 += __shfl_xor_sync(0xffffffffu, jp2, o); rjp += __shfl_xor_sync(0xffffffffu, rjp, o); }
+        if ((tid & 31) == 0) { red[0][tid >> 5] = jp2; red[1][tid >> 5] = rjp; }
+        __syncthreads();
+        if (tid == 0) {
+            double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+            for (int w = 0; w < DBAT_PSB / 32; ++w) { s0 += red[0][w]; s1 += red[1][w]; }
+            stats[blockIdx.x] = s0; stats[statStride + blockIdx.x] = s1;
+        }
+    }
+}
+// camera part of p'J'Jp and g'p: per image (p_io; p_eo_i)' G_i (p_io; p_eo_i) from the per-image Grams (their IO x IO
+// blocks add up to the shared block), the prior terms of the camera-side columns by image 0's thread block
+__global__ void __launch_bounds__(128) k_jp_cam(DevProblem P, const double* __restrict__ p,
+                                                 const double* __restrict__ camDiag, const double* __restrict__ camG,
+                                                 double* __restrict__ stats) {
+    __shared__ double red[2][4];
+    __shared__ double vs[4][DBAT_NSLOT + 6 + 2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = blockIdx.x * 4 + warp;                      // one warp per image
+    constexpr int NV = DBAT_NSLOT + 6;
+    double jp2 = 0.0, rjp = 0.0;
+    if (i < P.nImg) {
+        if (lane < NV) {
+            const int c = lane < DBAT_NSLOT ? P.sh_col[lane] : P.eo_col[6 * (size_t)i + lane - DBAT_NSLOT];
+            vs[warp][lane] = c >= 0 ? p[c] : 0.0;
+        }
+        __syncwarp();
+        const double* G = P.imgG + (size_t)i * DBAT_GSZ;
+        for (int e = lane; e < NV * NV; e += 32) {
+            const int a = e / NV, b = e - a * NV;
+            jp2 += vs[warp][a] * gram_at(G, a, b) * vs[warp][b];
+        }
+        if (lane < NV) rjp += vs[warp][lane] * gram_at(G, lane, DBAT_COL_R);
+    }
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < P.nC; c += gridDim.x * blockDim.x) {   // prior rows
+        jp2 += camDiag[c] * p[c] * p[c];
+        rjp += camG[c] * p[c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { jp2 += __shfl_xor_sync(0xffffffffu, jp2, o); rjp += __shfl_xor_sync(0xffffffffu, rjp, o); }
+    if (lane == 0) { red[0][warp] = jp2; red[1][warp] = rjp; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        stats[blockIdx.x] = (red[0][0] + red[0][1]) + (red[0][2] + red[0][3]);
+        stats[gridDim.x + blockIdx.x] = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
+    }
+}
+// sums of two partial arrays (a[0..n), a[n..2n)) into out[0], out[1]; one block, fixed order
+__global__ void __launch_bounds__(1024) k_sum_pair(const double* __restrict__ a, int n, double* __restrict__ out) {
+    __shared__ double sm[2][32];
+    double s0 = 0.0, s1 = 0.0;
+    for (int k = threadIdx.x; k < n; k += blockDim.x) { s0 += a[k]; s1 += a[n + k]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+    if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = s0; sm[1][threadIdx.x >> 5] = s1; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s0 = sm[0][threadIdx.x]; s1 = sm[1][threadIdx.x];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
+        if (threadIdx.x == 0) { out[0] = s0; out[1] = s1; }
+    }
+}
+// p = [pc ; back-substituted points].  jpOut (4 doubles, may be null): [0..1] point part of |Jp|^2, r'Jp (a multi-rank
+// run sums these over the ranks), [2..3] the camera part (identical on every rank).
+void launch_backsub(const DevProblem& P, double lambda, const double* pc, double* p, double* partial,
+                    const double* camDiag, const double* camG, double* jpOut, cudaStream_t st) {
+    static const bool perPoint = getenv("DBAT_POINT_SIDE_PER_POINT") != nullptr;
     if (pc != p) cudaMemcpyAsync(p, pc, sizeof(double) * P.nC, cudaMemcpyDeviceToDevice, st);
-    if (P.nOP > 0) { k_backsub<<<(P.nOP + 127) / 128, 128, 0, st>>>(P, lambda, p); count_launch(); }
+    int nb = 0;
+    if (P.nOP > 0) {
+        if (perPoint || !P.psb_pt) {
+            nb = (P.nOP + 127) / 128;
+            k_backsub<<<nb, 128, 0, st>>>(P, lambda, p, jpOut ? partial : nullptr, nb, nullptr, 0);
+            count_launch();
+        } else {
+            const int nbBig = P.nPsbig > 0 ? (P.nPsbig + 127) / 128 : 0;
+            nb = P.nPsb + nbBig;
+            if (P.nPsb > 0) { k_backsub_obs<<<P.nPsb, DBAT_PSB, 0, st>>>(P, lambda, p, jpOut ? partial : nullptr, nb); count_launch(); }
+            if (nbBig > 0) { k_backsub<<<nbBig, 128, 0, st>>>(P, lambda, p, jpOut ? partial + P.nPsb : nullptr, nb, P.psbig, P.nPsbig); count_launch(); }
+        }
+    }
+    if (jpOut) {
+        if (nb > 0) k_sum_pair<<<1, 1024, 0, st>>>(partial, nb, jpOut);
+        else cudaMemsetAsync(jpOut, 0, 2 * sizeof(double), st);
+        const int nbc = (P.nImg + 3) / 4;
+        k_jp_cam<<<nbc, 128, 0, st>>>(P, p, camDiag, camG, partial + 2 * nb);
+        k_sum_pair<<<1, 1024, 0, st>>>(partial + 2 * nb, nbc, jpOut + 2);
+        count_launch(3);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -21,6 +21,11 @@ from oracle.dbatstruct import buildserialindices, buildweightmatrix, serialize
 
 RES_RTOL = 1e-12
 EST_RTOL = 1e-9
+# Elements that are (nearly) zero by the choice of the object frame - a point on an axis, an angle of 1e-6 rad -
+# have no relative scale; they are held to 1e-11 absolute (the estimates are metres, millimetres and radians: that
+# is 1e-9 of a centimetre).  The sum order inside the Schur update is not fixed, so the last bits of such elements
+# move by ~1e-12 from run to run.
+EST_ATOL = 1e-11
 
 
 @pytest.fixture(scope='module', autouse=True)
@@ -154,7 +159,7 @@ def test_optimisers(case, damping):
     assert E.code == Eo.code == 0
     np.testing.assert_allclose(s0, s0o, rtol=EST_RTOL)
     if damping in ('gna', 'lmp'):
-        np.testing.assert_allclose(E.x, Eo.x, rtol=EST_RTOL, atol=1e-12)
+        np.testing.assert_allclose(E.x, Eo.x, rtol=EST_RTOL, atol=EST_ATOL)
         np.testing.assert_allclose(s1.IO.val, s2.IO.val, rtol=EST_RTOL, atol=1e-12)
         np.testing.assert_allclose(s1.EO.val, s2.EO.val, rtol=EST_RTOL, atol=1e-12)
         np.testing.assert_allclose(s1.OP.val, s2.OP.val, rtol=EST_RTOL, atol=1e-12)
@@ -449,7 +454,7 @@ def test_prague2016_cam_golden_cuda(stub, sigma0, last):
     so, oko, iterso, s0o, Eo = obundle(so, 'gna')
     assert ok and oko and iters == iterso
     assert abs(s0 - sigma0) < 6e-6 and abs(E.res[-1] - last) < 6e-4
-    np.testing.assert_allclose(E.x, Eo.x, rtol=EST_RTOL, atol=1e-12)
+    np.testing.assert_allclose(E.x, Eo.x, rtol=EST_RTOL, atol=EST_ATOL)
     np.testing.assert_allclose(s0, s0o, rtol=EST_RTOL)
     for w in ('CEO', 'COP'):
         Cg = dbat_b200.bundle_cov(s, E, w).toarray()
@@ -472,7 +477,7 @@ def test_prague2016_selfcalibration(damping):
     np.testing.assert_allclose(s0, s0o, rtol=EST_RTOL)
     if damping != 'lm':
         assert iters == iterso
-        np.testing.assert_allclose(E.x, Eo.x, rtol=EST_RTOL, atol=1e-12)
+        np.testing.assert_allclose(E.x, Eo.x, rtol=EST_RTOL, atol=EST_ATOL)
     else:
         np.testing.assert_allclose(E.x, Eo.x, rtol=1e-6, atol=1e-9)
 
@@ -493,7 +498,7 @@ def test_stpierre_selfcalibration(damping):
     assert abs(s0 - 1.0282960127) < 1e-8                   # value of the oracle at the time of writing
     if damping != 'lm':
         assert iters == iterso
-        np.testing.assert_allclose(E.x, Eo.x, rtol=EST_RTOL, atol=1e-12)
+        np.testing.assert_allclose(E.x, Eo.x, rtol=EST_RTOL, atol=EST_ATOL)
         np.testing.assert_allclose(E.res, Eo.res, rtol=1e-9)
     else:
         np.testing.assert_allclose(E.x, Eo.x, rtol=1e-6, atol=1e-9)
@@ -638,7 +643,7 @@ def test_gauss_markov_direct_call(case):
     x, code, n, final, T, rr = dbat_b200.gauss_markov(P, x0, W, 20, 1e-6, False, False)
     xo, codeo, no, finalo, To, rro = ogm(lambda xx, j: brown_euler_cam4(xx, s, j), x0, W, 20, 1e-6, False, False)
     assert code == codeo == 0 and n == no
-    np.testing.assert_allclose(x, xo, rtol=EST_RTOL, atol=1e-12)
+    np.testing.assert_allclose(x, xo, rtol=EST_RTOL, atol=EST_ATOL)
     np.testing.assert_allclose(rr, rro, rtol=1e-10)
     np.testing.assert_allclose(T, To, rtol=1e-8, atol=1e-10)
     np.testing.assert_allclose(final.weighted.r, finalo.weighted.r, rtol=1e-9, atol=1e-11)
