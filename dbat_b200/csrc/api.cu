@@ -988,42 +988,84 @@ static bool term_fun(const dbat_opts* o, double jp2, double rr) {
 }
 
 // sprank(J) < n (levenberg_marquardt.m:126-135, gauss_newton_armijo.m:132-143): maximum bipartite
-// matching between the columns and rows of the exported sparse Jacobian (exact zeros dropped, like
-// the reference's J).  Greedy initialisation + augmenting paths (iterative DFS).  Only used when the
-// problem is small enough to export J on every run; larger problems use the counting screen below.
-static int build_csc(dbat_handle* h, int weighted);
+// matching between the columns and rows of the sparse Jacobian (exact zeros dropped, like the
+// reference's J).  The device exports only the non-zero PATTERN of the per-observation blocks (8 bytes per
+// observation); the adjacency of a column is enumerated from the problem's own index structure - all
+// observations for a shared IO column, the image's for an EO column, the point's for an OP column, plus prior
+// rows - so no CSC matrix is ever formed and the exact test runs at any size.  Greedy initialisation +
+// augmenting paths (iterative DFS).
 static bool matching_deficient(dbat_handle* h) {
-    if (build_csc(h, 1)) return false;
-    const int n = h->P.n, m = h->m;
-    const std::vector<int64_t>& Jc = h->cscJc; const std::vector<int64_t>& Ir = h->cscIr;
+    DevProblem& P = h->P;
+    if (!h->params_valid) { set_params(h, h->d_x); h->params_valid = true; }
+    const int n = P.n, m = h->m, nObs = P.nObs;
+    const int LD = DBAT_NSLOT + 9;
+    std::vector<unsigned long long> mask(std::max(1, nObs));
+    {
+        unsigned long long* dm = nullptr;
+        if (cudaMalloc(&dm, sizeof(unsigned long long) * mask.size()) != cudaSuccess) return false;
+        launch_export_mask(P, dm, h->st);
+        cudaError_t e = cudaMemcpyAsync(mask.data(), dm, sizeof(unsigned long long) * mask.size(), cudaMemcpyDeviceToHost, h->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->st);
+        cudaFree(dm);
+        if (e != cudaSuccess) return false;
+    }
+    // column -> (kind, index)
+    std::vector<int> kind(n, -1), idx(n, -1);
+    for (int s = 0; s < DBAT_NSLOT; ++s) if (h->h_sh_col[s] >= 0) { kind[h->h_sh_col[s]] = 0; idx[h->h_sh_col[s]] = s; }
+    for (int e2 = 0; e2 < 6 * P.nImg; ++e2) if (h->h_eo_col[e2] >= 0) { kind[h->h_eo_col[e2]] = 1; idx[h->h_eo_col[e2]] = e2; }
+    for (int e2 = 0; e2 < 3 * P.nOP; ++e2) if (h->h_op_col[e2] >= 0) { kind[h->h_op_col[e2]] = 2; idx[h->h_op_col[e2]] = e2; }
+    std::vector<std::vector<int>> priorRows(n);
+    for (int k = 0; k < P.nPrior; ++k) priorRows[h->h_prior_col[k]].push_back(2 * nObs + k);
+    // adjacency of column c: position pos in [0, deg(c)) -> row or -1 (entry is an exact zero)
+    auto degree = [&](int c) -> int64_t {
+        int64_t d = (int64_t)priorRows[c].size();
+        if (kind[c] == 0) d += 2 * (int64_t)nObs;
+        else if (kind[c] == 1) { const int i = idx[c] / 6; d += 2 * (int64_t)(h->h_img_start[i + 1] - h->h_img_start[i]); }
+        else if (kind[c] == 2) { const int j = idx[c] / 3; d += 2 * (int64_t)(h->h_pt_start[j + 1] - h->h_pt_start[j]); }
+        return d;
+    };
+    auto row_at = [&](int c, int64_t pos) -> int {
+        int64_t nb = degree(c) - (int64_t)priorRows[c].size();
+        if (pos >= nb) return priorRows[c][(size_t)(pos - nb)];
+        const int r = (int)(pos & 1);
+        int k, slot;
+        if (kind[c] == 0) { k = (int)(pos >> 1); slot = idx[c]; }
+        else if (kind[c] == 1) { k = h->h_img_start[idx[c] / 6] + (int)(pos >> 1); slot = DBAT_NSLOT + idx[c] % 6; }
+        else { k = h->h_pm2cm[h->h_pt_start[idx[c] / 3] + (int)(pos >> 1)]; slot = DBAT_NSLOT + 6 + idx[c] % 3; }
+        return ((mask[k] >> (LD * r + slot)) & 1ull) ? 2 * k + r : -1;
+    };
     std::vector<int> matchRow(m, -1), matchCol(n, -1), stamp(m, -1);
     int matched = 0;
-    for (int c = 0; c < n; ++c)                                  // greedy pass
-        for (int64_t e = Jc[c]; e < Jc[c + 1]; ++e)
-            if (matchRow[Ir[e]] < 0) { matchRow[Ir[e]] = c; matchCol[c] = (int)Ir[e]; ++matched; break; }
-    std::vector<int> stackCol; std::vector<int64_t> stackPos; std::vector<int> pathRow;
+    for (int c = 0; c < n; ++c) {                                // greedy pass
+        const int64_t d = degree(c);
+        for (int64_t pos = 0; pos < d; ++pos) {
+            const int r = row_at(c, pos);
+            if (r >= 0 && matchRow[r] < 0) { matchRow[r] = c; matchCol[c] = r; ++matched; break; }
+        }
+    }
+    std::vector<int> stackCol; std::vector<int64_t> stackPos, stackDeg; std::vector<int> pathRow;
     for (int c0 = 0; c0 < n && matched < n; ++c0) {
         if (matchCol[c0] >= 0) continue;
         // iterative DFS for an augmenting path starting at the free column c0
-        stackCol.assign(1, c0); stackPos.assign(1, Jc[c0]); pathRow.clear();
+        stackCol.assign(1, c0); stackPos.assign(1, 0); stackDeg.assign(1, degree(c0)); pathRow.clear();
         bool found = false;
         while (!stackCol.empty() && !found) {
             const int c = stackCol.back();
             int64_t& pos = stackPos.back();
-            if (pos >= Jc[c + 1]) { stackCol.pop_back(); stackPos.pop_back(); if (!pathRow.empty()) pathRow.pop_back(); continue; }
-            const int r = (int)Ir[pos++];
-            if (stamp[r] == c0) continue;
+            if (pos >= stackDeg.back()) { stackCol.pop_back(); stackPos.pop_back(); stackDeg.pop_back(); if (!pathRow.empty()) pathRow.pop_back(); continue; }
+            const int r = row_at(c, pos++);
+            if (r < 0 || stamp[r] == c0) continue;
             stamp[r] = c0;
             if (matchRow[r] < 0) { pathRow.push_back(r); found = true; break; }
             pathRow.push_back(r);
-            stackCol.push_back(matchRow[r]); stackPos.push_back(Jc[matchRow[r]]);
+            const int c2 = matchRow[r];
+            stackCol.push_back(c2); stackPos.push_back(0); stackDeg.push_back(degree(c2));
         }
         if (found) {                                              // flip the path: column k takes row pathRow[k]
             for (size_t k = 0; k < stackCol.size(); ++k) { matchRow[pathRow[k]] = stackCol[k]; matchCol[stackCol[k]] = pathRow[k]; }
             ++matched;
         }
     }
-    h->cscWeighted = -1; h->cscIr.clear(); h->cscIr.shrink_to_fit(); h->cscV.clear(); h->cscV.shrink_to_fit();
     return matched < n;
 }
 
@@ -1045,8 +1087,9 @@ static bool structurally_deficient(dbat_handle* h) {
         for (int a = 0; a < 6; ++a) { const int c = h->h_eo_col[6 * (size_t)i + a]; if (c >= 0) { ++freec; pri += priorCnt[c]; } }
         if (freec && 2 * (h->h_img_start[i + 1] - h->h_img_start[i]) + pri < freec) return true;
     }
-    if ((int64_t)P.nObs <= 300000) return matching_deficient(h);   // exact test where exporting J is cheap
-    return false;
+    static const bool skipExact = getenv("DBAT_NO_SPRANK") != nullptr;
+    if (skipExact) return false;
+    return matching_deficient(h);          // exact at any size: 8 bytes per observation cross the bus
 }
 
 static int trace_sum(dbat_handle* h, double* tr) {

@@ -671,6 +671,47 @@ __global__ void __launch_bounds__(128) k_export_jac(DevProblem P, double* __rest
         r0[DBAT_NSLOT + 6 + c] = o.dOP[0][c] * w0; r1[DBAT_NSLOT + 6 + c] = o.dOP[1][c] * w1;
     }
 }
+// Pattern only (the structural-rank test, levenberg_marquardt.m:126-135): one 64-bit mask per observation, bit
+// 23 * row + slot set when that Jacobian entry is non-zero (slots as in k_export_jac) - 8 bytes per observation
+// instead of 368, so the exact test runs at any problem size.
+template <int MODEL>
+__global__ void __launch_bounds__(128) k_export_mask(DevProblem P, unsigned long long* __restrict__ out) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P.nObs) return;
+    const double2 uv = P.uv_cm[k];
+    const int j = P.pt_cm[k];
+    const ImgRec g = P.img[P.img_cm[k]];
+    const IORec io = P.io[g.io];
+    const double Q[3] = {P.OPval[3 * (size_t)j], P.OPval[3 * (size_t)j + 1], P.OPval[3 * (size_t)j + 2]};
+    ObsJac o;
+    obs_model<MODEL, true, true>(Q, g, io, P.nK, P.nP, uv.x, uv.y, o);
+    unsigned long long m = 0;
+    const int LD = DBAT_NSLOT + 9;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int s = 0; s < DBAT_NSLOT; ++s) if (o.dIO[s][r] != 0.0) m |= 1ull << (LD * r + s);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (o.dC[r][c] != 0.0) m |= 1ull << (LD * r + DBAT_NSLOT + c);
+            if (o.dA[r][c] != 0.0) m |= 1ull << (LD * r + DBAT_NSLOT + 3 + c);
+            if (o.dOP[r][c] != 0.0) m |= 1ull << (LD * r + DBAT_NSLOT + 6 + c);
+        }
+    }
+    out[k] = m;
+}
+void launch_export_mask(const DevProblem& P, unsigned long long* out, cudaStream_t st) {
+    if (P.nObs <= 0) return;
+    const int nb = (P.nObs + 127) / 128;
+    switch (P.model) {
+        case 0: k_export_mask<0><<<nb, 128, 0, st>>>(P, out); break;
+        case 1: k_export_mask<1><<<nb, 128, 0, st>>>(P, out); break;
+        case 2: k_export_mask<2><<<nb, 128, 0, st>>>(P, out); break;
+        case 3: k_export_mask<3><<<nb, 128, 0, st>>>(P, out); break;
+        default: k_export_mask<4><<<nb, 128, 0, st>>>(P, out); break;
+    }
+    count_launch();
+}
 void launch_export_jac(const DevProblem& P, double* out, int weighted, cudaStream_t st) {
     if (P.nObs <= 0) return;
     const int nb = (P.nObs + 127) / 128;

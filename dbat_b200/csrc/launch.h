@@ -22,6 +22,7 @@ void launch_prior_rr(const DevProblem& P, const double* x, double* partial, doub
 void launch_jp(const DevProblem& P, const double* x, const double* p, double* partial, double* scal,
                int slot2, int slotr, cudaStream_t st);
 void launch_export_jac(const DevProblem& P, double* out, int weighted, cudaStream_t st);
+void launch_export_mask(const DevProblem& P, unsigned long long* out, cudaStream_t st);
 
 // schur.cu
 void launch_diag(const DevProblem& P, const double* camDiag, double* diagN, cudaStream_t st);
