@@ -78,6 +78,9 @@ struct dbat_handle {
     // host copies (CSC export, covariance layout)
     std::vector<int> h_img_cm, h_pt_cm, h_img_start, h_pt_start, h_pm2cm;
     std::vector<int> h_sh_col, h_eo_col, h_op_col, h_io_col;   // io_col: NC x nImg
+    std::vector<int> h_io_colx;         // nImg x NSLOT: x column of every (image, IO slot)
+    std::vector<int> h_glob_x;          // IO columns used by more than one image (all of them with one shared block)
+    std::vector<int> h_colLocalImg;     // per camera-side x column: the one image that uses this IO column, or -1
     std::vector<int> h_prior_col;
     std::vector<double> h_prior_isig;
     // device allocations
@@ -179,21 +182,36 @@ static int setup_reduced(dbat_handle* h, int nParts, int myPart) {
         h->err = "symbolic analysis of the reduced system failed"; return DBAT_E_STATE;
     }
     std::vector<int> sh_s(DBAT_NSLOT, -1), eo_s((size_t)6 * nImg, -1), s2x(sym.ld, -1);
+    std::vector<int> cam_colx((size_t)DBAT_NCAM * nImg, -1), cam_s((size_t)DBAT_NCAM * nImg, -1);
     h->h_x2s.assign(std::max(1, nC), -1);
-    int k = 0;
-    for (int sl = 0; sl < DBAT_NSLOT; ++sl) if (h->h_sh_col[sl] >= 0) sh_s[sl] = sym.ioS + k++;
+    for (size_t k = 0; k < h->h_glob_x.size(); ++k) h->h_x2s[h->h_glob_x[k]] = sym.ioS + (int)k;     // global IO columns, x order
     for (int i = 0; i < nImg; ++i) {
         int q = 0;
-        for (int a = 0; a < 6; ++a) if (h->h_eo_col[(size_t)i * 6 + a] >= 0) eo_s[(size_t)i * 6 + a] = sym.imgS[i] + q++;
+        for (int a = 0; a < 6; ++a) {
+            const int c = h->h_eo_col[(size_t)i * 6 + a];
+            if (c >= 0) { eo_s[(size_t)i * 6 + a] = sym.imgS[i] + q; h->h_x2s[c] = sym.imgS[i] + q; ++q; }
+        }
+        for (int sl = 0; sl < DBAT_NSLOT; ++sl) {             // this image's own IO columns follow its EO elements
+            const int c = h->h_io_colx[(size_t)i * DBAT_NSLOT + sl];
+            if (c >= 0 && h->h_colLocalImg[c] == i && h->h_x2s[c] < 0) { h->h_x2s[c] = sym.imgS[i] + q; ++q; }
+        }
     }
-    for (int sl = 0; sl < DBAT_NSLOT; ++sl) if (sh_s[sl] >= 0) { s2x[sh_s[sl]] = h->h_sh_col[sl]; h->h_x2s[h->h_sh_col[sl]] = sh_s[sl]; }
-    for (size_t e = 0; e < eo_s.size(); ++e) if (eo_s[e] >= 0) { s2x[eo_s[e]] = h->h_eo_col[e]; h->h_x2s[h->h_eo_col[e]] = eo_s[e]; }
+    for (int c = 0; c < nC; ++c) if (h->h_x2s[c] >= 0) s2x[h->h_x2s[c]] = c;
+    for (int sl = 0; sl < DBAT_NSLOT; ++sl) if (h->h_sh_col[sl] >= 0) sh_s[sl] = h->h_x2s[h->h_sh_col[sl]];
+    for (int i = 0; i < nImg; ++i)
+        for (int a = 0; a < DBAT_NCAM; ++a) {
+            const int c = a < DBAT_NSLOT ? h->h_io_colx[(size_t)i * DBAT_NSLOT + a] : h->h_eo_col[(size_t)i * 6 + a - DBAT_NSLOT];
+            cam_colx[(size_t)i * DBAT_NCAM + a] = c;
+            cam_s[(size_t)i * DBAT_NCAM + a] = c >= 0 ? h->h_x2s[c] : -1;
+        }
     if (h->tc.d.tiles) tchol_free(h->tc);
     if (tchol_alloc(h->tc, sym)) { h->err = "out of memory for the reduced system"; return DBAT_E_OOM; }
     int rc = 0;
-    int *d_shs = nullptr, *d_eos = nullptr, *d_s2x = nullptr;
-    if ((rc = dev_upload(h, &d_shs, sh_s)) || (rc = dev_upload(h, &d_eos, eo_s)) || (rc = dev_upload(h, &d_s2x, s2x))) return rc;
+    int *d_shs = nullptr, *d_eos = nullptr, *d_s2x = nullptr, *d_ccx = nullptr, *d_cs = nullptr, *d_gx = nullptr;
+    if ((rc = dev_upload(h, &d_shs, sh_s)) || (rc = dev_upload(h, &d_eos, eo_s)) || (rc = dev_upload(h, &d_s2x, s2x)) ||
+        (rc = dev_upload(h, &d_ccx, cam_colx)) || (rc = dev_upload(h, &d_cs, cam_s)) || (rc = dev_upload(h, &d_gx, h->h_glob_x))) return rc;
     P.sh_s = d_shs; P.eo_s = d_eos; P.s2x = d_s2x; P.T = h->tc.d;
+    P.cam_colx = d_ccx; P.cam_s = d_cs; P.glob_x = d_gx; P.nGlob = (int)h->h_glob_x.size();
     P.ldS = sym.ld;
     if ((rc = dev_alloc(h, &h->d_dS, (size_t)sym.ld)) || (rc = dev_alloc(h, &P.rhs, (size_t)sym.ld)) ||
         (rc = dev_alloc(h, &h->d_pc, (size_t)sym.ld))) return rc;
@@ -267,15 +285,21 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
         colIO[3] = -1; colIO[4] = -1;          // aspect / skew do not exist in the legacy models
         for (int i = 1; i < nImg; ++i) { colIO[(size_t)i * NC + 3] = -1; colIO[(size_t)i * NC + 4] = -1; }
     }
+    // IO column of every (image, slot); one block shared by all images -> fast path, anything else (image-variant
+    // parameters, several cameras: IO.struct.block, multi_res.m:92-111) -> general path
+    h->h_io_colx.assign((size_t)nImg * DBAT_NSLOT, -1);
+    for (int i = 0; i < nImg; ++i)
+        for (int r = 0; r < NC; ++r) h->h_io_colx[(size_t)i * DBAT_NSLOT + slot_of(r)] = colIO[(size_t)i * NC + r];
+    bool general = false;
     for (int r = 0; r < NC; ++r) {
         int v = firstImg >= 0 ? colIO[(size_t)firstImg * NC + r] : -1;
         for (int i = 0; i < nImg; ++i)
-            if (imgHasObs[i] && colIO[(size_t)i * NC + r] != v)
-                return fail_create(h, DBAT_E_UNSUPPORTED,
-                                   "IO parameters must form one block shared by all images (image-variant / "
-                                   "multi-camera IO is not built yet)");
+            if (imgHasObs[i] && colIO[(size_t)i * NC + r] != v) general = true;
         h->h_sh_col[slot_of(r)] = v;
     }
+    if (general && legacy) return fail_create(h, DBAT_E_UNSUPPORTED, "the legacy models take one camera");
+    if (general) h->h_sh_col.assign(DBAT_NSLOT, -1);      // no column is "the" shared column of a slot
+    P.ioGeneral = general ? 1 : 0;
     {
         std::vector<int> owner(nC, -1);
         for (int i = 0; i < nImg; ++i)
@@ -293,12 +317,11 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
                 if (c <= prev) return fail_create(h, DBAT_E_UNSUPPORTED, "EO columns must be in serialisation order");
                 prev = c;
             }
-        for (int s = 0; s < DBAT_NSLOT; ++s)
-            if (h->h_sh_col[s] >= 0 && prev >= 0) {
-                int minEO = nC;
-                for (int c : colEO) if (c >= 0) minEO = std::min(minEO, c);
-                if (h->h_sh_col[s] > minEO) return fail_create(h, DBAT_E_UNSUPPORTED, "IO columns must precede EO columns in x");
-            }
+        if (prev >= 0) {
+            int minEO = nC;
+            for (int c : colEO) if (c >= 0) minEO = std::min(minEO, c);
+            for (int c : h->h_io_colx) if (c > minEO) return fail_create(h, DBAT_E_UNSUPPORTED, "IO columns must precede EO columns in x");
+        }
     }
     h->h_io_col = colIO; h->h_eo_col = colEO; h->h_op_col = colOP;
 
@@ -309,6 +332,7 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
         for (int i = 0; i < nImg; ++i) {
             const int src = legacy ? 0 : i;
             std::vector<double> key(d->IOval + (size_t)src * NC, d->IOval + (size_t)(src + 1) * NC);
+            if (general) key.push_back((double)i);          // estimated per-image parameters diverge: one record per image
             auto it = seen.find(key);
             if (it == seen.end()) { it = seen.emplace(key, (int)rep.size()).first; rep.push_back(i); }
             ioOfImg[i] = it->second;
@@ -433,8 +457,21 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
         for (int i = 0; i < nImg; ++i) for (int a = 0; a < 3; ++a) h->h_xyz[3 * (size_t)i + a] = d->EOval[6 * (size_t)i + a];
         h->h_nEO.assign(nImg, 0);
         for (int i = 0; i < nImg; ++i) for (int a = 0; a < 6; ++a) if (colEO[(size_t)i * 6 + a] >= 0) h->h_nEO[i]++;
-        h->h_nIOest = 0;
-        for (int sl = 0; sl < DBAT_NSLOT; ++sl) if (h->h_sh_col[sl] >= 0) h->h_nIOest++;
+        // IO columns: used by one image -> they travel with that image (like its EO elements); used by several ->
+        // "global", last in S.  (One shared block: every estimated IO column is global.)
+        std::vector<int> users(std::max(1, nC), 0), lastUser(std::max(1, nC), -1);
+        for (int i = 0; i < nImg; ++i)
+            for (int sl = 0; sl < DBAT_NSLOT; ++sl) {
+                const int c = h->h_io_colx[(size_t)i * DBAT_NSLOT + sl];
+                if (c >= 0 && lastUser[c] != i) { users[c]++; lastUser[c] = i; }
+            }
+        h->h_glob_x.clear();
+        h->h_colLocalImg.assign(std::max(1, nC), -1);
+        for (int c = 0; c < nC; ++c) {
+            if (users[c] >= 2 || (users[c] == 1 && !general)) h->h_glob_x.push_back(c);
+            else if (users[c] == 1) { h->h_colLocalImg[c] = lastUser[c]; h->h_nEO[lastUser[c]]++; }
+        }
+        h->h_nIOest = (int)h->h_glob_x.size();
         if ((rc = setup_reduced(h, 1, 0))) return fail_create(h, rc, h->err);
     }
     const std::vector<int>& imgRank = h->tc.sym.imgRank;
@@ -452,6 +489,7 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     }
     AL(P.pt, (size_t)std::max(1, nOP) * DBAT_PT_STRIDE);
     AL(P.W, (size_t)std::max(1, nObs) * DBAT_W_STRIDE);
+    if (P.ioGeneral) AL(P.Wfull, (size_t)std::max(1, nObs) * DBAT_WF_STRIDE);
     {   // deterministic Schur index: inverse permutation, point of every pm observation, pair blocks
         std::vector<int> cm2pm(nObs), pt_pm(nObs);
         for (int o = 0; o < nObs; ++o) { cm2pm[h->h_pm2cm[o]] = o; pt_pm[o] = h->h_pt_cm[h->h_pm2cm[o]]; }
@@ -860,7 +898,12 @@ static int build_csc(dbat_handle* h, int weighted) {
     // column -> (kind, index)
     const int n = P.n, nC = P.nC;
     std::vector<int> kind(n, -1), idx(n, -1);
-    for (int s = 0; s < DBAT_NSLOT; ++s) if (h->h_sh_col[s] >= 0) { kind[h->h_sh_col[s]] = 0; idx[h->h_sh_col[s]] = s; }
+    std::vector<std::vector<int>> ioUsers(n);   // IO column -> (image * NSLOT + slot) of every image that uses it, ascending
+    for (int i = 0; i < P.nImg; ++i)
+        for (int s = 0; s < DBAT_NSLOT; ++s) {
+            const int c = h->h_io_colx[(size_t)i * DBAT_NSLOT + s];
+            if (c >= 0) { kind[c] = 0; ioUsers[c].push_back(i * DBAT_NSLOT + s); }
+        }
     for (int e2 = 0; e2 < 6 * P.nImg; ++e2) if (h->h_eo_col[e2] >= 0) { kind[h->h_eo_col[e2]] = 1; idx[h->h_eo_col[e2]] = e2; }
     for (int e2 = 0; e2 < 3 * P.nOP; ++e2) if (h->h_op_col[e2] >= 0) { kind[h->h_op_col[e2]] = 2; idx[h->h_op_col[e2]] = e2; }
     std::vector<std::vector<int>> priorOfCol;   // rows of prior observations per column (rare)
@@ -872,10 +915,12 @@ static int build_csc(dbat_handle* h, int weighted) {
     (void)nC;
     for (int c = 0; c < n; ++c) {
         if (kind[c] == 0) {
-            const int s = idx[c];
-            for (int k = 0; k < P.nObs; ++k) {
-                push(2 * (int64_t)k, J[((size_t)k * 2) * LD + s]);
-                push(2 * (int64_t)k + 1, J[((size_t)k * 2 + 1) * LD + s]);
+            for (int u : ioUsers[c]) {                        // the observations of every image that uses the column
+                const int i = u / DBAT_NSLOT, s = u % DBAT_NSLOT;
+                for (int k = h->h_img_start[i]; k < h->h_img_start[i + 1]; ++k) {
+                    push(2 * (int64_t)k, J[((size_t)k * 2) * LD + s]);
+                    push(2 * (int64_t)k + 1, J[((size_t)k * 2 + 1) * LD + s]);
+                }
             }
         } else if (kind[c] == 1) {
             const int i = idx[c] / 6, a2 = idx[c] % 6;
@@ -1011,7 +1056,16 @@ static bool matching_deficient(dbat_handle* h) {
     }
     // column -> (kind, index)
     std::vector<int> kind(n, -1), idx(n, -1);
-    for (int s = 0; s < DBAT_NSLOT; ++s) if (h->h_sh_col[s] >= 0) { kind[h->h_sh_col[s]] = 0; idx[h->h_sh_col[s]] = s; }
+    std::vector<std::vector<int>> ioUsers(n);            // IO column -> image * NSLOT + slot, images ascending
+    std::vector<std::vector<int64_t>> ioCum(n);          // ... and the running count of their observations
+    for (int i = 0; i < P.nImg; ++i)
+        for (int s = 0; s < DBAT_NSLOT; ++s) {
+            const int c = h->h_io_colx[(size_t)i * DBAT_NSLOT + s];
+            if (c < 0) continue;
+            kind[c] = 0;
+            ioUsers[c].push_back(i * DBAT_NSLOT + s);
+            ioCum[c].push_back((ioCum[c].empty() ? 0 : ioCum[c].back()) + (h->h_img_start[i + 1] - h->h_img_start[i]));
+        }
     for (int e2 = 0; e2 < 6 * P.nImg; ++e2) if (h->h_eo_col[e2] >= 0) { kind[h->h_eo_col[e2]] = 1; idx[h->h_eo_col[e2]] = e2; }
     for (int e2 = 0; e2 < 3 * P.nOP; ++e2) if (h->h_op_col[e2] >= 0) { kind[h->h_op_col[e2]] = 2; idx[h->h_op_col[e2]] = e2; }
     std::vector<std::vector<int>> priorRows(n);
@@ -1019,7 +1073,7 @@ static bool matching_deficient(dbat_handle* h) {
     // adjacency of column c: position pos in [0, deg(c)) -> row or -1 (entry is an exact zero)
     auto degree = [&](int c) -> int64_t {
         int64_t d = (int64_t)priorRows[c].size();
-        if (kind[c] == 0) d += 2 * (int64_t)nObs;
+        if (kind[c] == 0) d += 2 * (ioCum[c].empty() ? 0 : ioCum[c].back());
         else if (kind[c] == 1) { const int i = idx[c] / 6; d += 2 * (int64_t)(h->h_img_start[i + 1] - h->h_img_start[i]); }
         else if (kind[c] == 2) { const int j = idx[c] / 3; d += 2 * (int64_t)(h->h_pt_start[j + 1] - h->h_pt_start[j]); }
         return d;
@@ -1029,7 +1083,12 @@ static bool matching_deficient(dbat_handle* h) {
         if (pos >= nb) return priorRows[c][(size_t)(pos - nb)];
         const int r = (int)(pos & 1);
         int k, slot;
-        if (kind[c] == 0) { k = (int)(pos >> 1); slot = idx[c]; }
+        if (kind[c] == 0) {
+            const int64_t q = pos >> 1;
+            const size_t u = (size_t)(std::upper_bound(ioCum[c].begin(), ioCum[c].end(), q) - ioCum[c].begin());
+            const int i = ioUsers[c][u] / DBAT_NSLOT;
+            k = h->h_img_start[i] + (int)(q - (u ? ioCum[c][u - 1] : 0)); slot = ioUsers[c][u] % DBAT_NSLOT;
+        }
         else if (kind[c] == 1) { k = h->h_img_start[idx[c] / 6] + (int)(pos >> 1); slot = DBAT_NSLOT + idx[c] % 6; }
         else { k = h->h_pm2cm[h->h_pt_start[idx[c] / 3] + (int)(pos >> 1)]; slot = DBAT_NSLOT + 6 + idx[c] % 3; }
         return ((mask[k] >> (LD * r + slot)) & 1ull) ? 2 * k + r : -1;
@@ -1280,6 +1339,10 @@ static int solve_lmp(dbat_handle* h, const dbat_opts* o, dbat_result* res, Trace
         } else {
             int nt = std::max(std::max(3 * P.nOP, 6 * P.nImg), DBAT_NSLOT);
             cudaMemsetAsync(h->d_g, 0, sizeof(double) * nn, h->st);
+            if (P.ioGeneral) {          // IO columns: prior part, then the sums over the images that use the column
+                cudaMemcpyAsync(h->d_g, h->d_camG, sizeof(double) * P.nC, cudaMemcpyDeviceToDevice, h->st);
+                launch_io_diag_grad_gen(P, nullptr, nullptr, nullptr, h->d_g, h->st);
+            }
             k_gradient<<<(nt + 255) / 256, 256, 0, h->st>>>(P, h->d_camG, h->d_g); count_launch();
             double gg = 0, jg2 = 0, dummy = 0;
             if ((rc = dev_dot(h, h->d_g, h->d_g, nn, &gg))) return rc;
@@ -1541,6 +1604,11 @@ extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
     const double s02 = s0 * s0;
     const int nC = P.nC, ld = ldd;
     const std::vector<int>& x2s = h->h_x2s;
+    if ((which == DBAT_COV_CXX || which == DBAT_COV_CXX_OP) && P.ioGeneral) {
+        cudaFree(Z); cudaFree(C);
+        h->err = "the dense point covariance (CXX / COPF) is built for one shared IO block only; use CIO / CEO / COP";
+        return DBAT_E_UNSUPPORTED;
+    }
     if (which == DBAT_COV_CXX || which == DBAT_COV_CXX_OP) {
         const int m3 = P.n - nC;
         const size_t limit = (size_t)1 << 28;                 // 2 GB of doubles per dense block
@@ -1596,7 +1664,8 @@ extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
         double* dOut = nullptr;
         cudaMalloc(&dOut, sizeof(double) * 9 * (size_t)std::max(1, P.nOP));
         cudaMemsetAsync(dOut, 0, sizeof(double) * 9 * (size_t)std::max(1, P.nOP), h->st);
-        if (P.nOP > 0) { k_cop<<<(P.nOP + 3) / 4, 128, 0, h->st>>>(P, C, ld, h->d_dS, s02, dOut); count_launch(); }
+        if (P.nOP > 0 && P.ioGeneral) launch_cop_gen(P, C, ld, h->d_dS, s02, dOut, h->st);
+        else if (P.nOP > 0) { k_cop<<<(P.nOP + 3) / 4, 128, 0, h->st>>>(P, C, ld, h->d_dS, s02, dOut); count_launch(); }
         cudaMemcpyAsync(out, dOut, sizeof(double) * 9 * (size_t)P.nOP, cudaMemcpyDeviceToHost, h->st);
         e = cudaStreamSynchronize(h->st);
         cudaFree(dOut);

@@ -451,6 +451,7 @@ static void launch_point_side_t(const DevProblem& P, cudaStream_t st) {
     if (P.nPsbig > 0) { k_point_side<MODEL><<<(P.nPsbig + 127) / 128, 128, 0, st>>>(P, P.psbig, P.nPsbig); count_launch(); }
 }
 void launch_point_side(const DevProblem& P, cudaStream_t st) {
+    if (P.ioGeneral) { launch_point_side_gen(P, st); return; }
     switch (P.model) {
         case 0: launch_point_side_t<0>(P, st); break;
         case 1: launch_point_side_t<1>(P, st); break;
@@ -580,7 +581,7 @@ __global__ void __launch_bounds__(RES_BLOCK) k_jp(DevProblem P, const double* __
         double j0 = 0.0, j1 = 0.0;
 #pragma unroll
         for (int s = 0; s < DBAT_NSLOT; ++s) {
-            const int c = P.sh_col[s];
+            const int c = P.cam_colx[(size_t)DBAT_NCAM * i + s];          // this image's IO column of the slot
             if (c >= 0) { const double pv = p[c]; j0 += o.dIO[s][0] * pv; j1 += o.dIO[s][1] * pv; }
         }
 #pragma unroll

@@ -16,6 +16,8 @@
 #define DBAT_PT_STRIDE 52          // doubles per point record: V[6] g[3] pad Wsh[14][3]
 #define DBAT_PT_WSH 10
 #define DBAT_W_STRIDE 18
+#define DBAT_NCAM (DBAT_NSLOT + 6)  // camera-side parameters of one image: IO slots then EO
+#define DBAT_WF_STRIDE (3 * DBAT_NCAM)
 #define DBAT_PTAUX_STRIDE 46       // Vg[3], pad, Ysh[14][3]
 #define DBAT_PTAUX_YSH 4
 #define DBAT_SHCOLS 16              // NSLOT shared columns + rhs + pad
@@ -58,6 +60,13 @@ struct DevProblem {
     const int* sh_s;       // NSLOT
     const int* eo_s;       // nImg x 6
     const int* s2x;        // ldS: x column of every S index (-1: padding / rhs row)
+    // general IO block structure (image-variant parameters, several cameras: IO.struct.block, buildserialindices.m:162-221)
+    int ioGeneral;         // 0: one IO block shared by all images (fast path); 1: per-image column maps below are used
+    const int* cam_colx;   // nImg x 20: x column of [NSLOT IO slots | 6 EO elements] of every image (-1 fixed); both modes
+    const int* cam_s;      // nImg x 20: the same as S indices
+    double* Wfull;         // general mode: nObs x 60, cross blocks [IO slots | EO] x OP of every observation (point-major)
+    int nGlob;             // IO columns used by more than one image (they sit last in S)
+    const int* glob_x;     // nGlob: their x columns
     TCholDev T;            // the reduced system itself: 64 x 64 tiles of the sparse pattern (tilechol.cu)
     // prior observations
     const int* prior_col; const double* prior_val; const double* prior_isig;

@@ -40,6 +40,15 @@ void launch_axpy(double alpha, const double* x, const double* y, double* out, in
 void launch_inv_sqrt(const double* in, double* out, int n, cudaStream_t st);
 void launch_mul(const double* a, const double* b, double* out, int n, cudaStream_t st);
 
+// general_io.cu (general IO block structure)
+void launch_point_side_gen(const DevProblem& P, cudaStream_t st);
+void launch_build_S_gen(const DevProblem& P, const double* camDiag, const double* camG, double lambda, cudaStream_t st);
+void launch_schur_gen(const DevProblem& P, double lambda, cudaStream_t st);
+int launch_backsub_gen(const DevProblem& P, double lambda, double* p, double* stats, cudaStream_t st);
+void launch_cop_gen(const DevProblem& P, const double* C, int ldc, const double* dsc, double s02, double* out, cudaStream_t st);
+void launch_io_diag_grad_gen(const DevProblem& P, const double* camDiag, const double* camG, double* diagN, double* grad,
+                             cudaStream_t st);
+
 // schur_index.cu
 int build_pair_index(const int* d_pt_start, const int* d_img_pm, const long long* h_pair_off, int nOP,
                      int nImg, long long** d_pairs, long long** d_blk_key, long long** d_blk_off, int* nBlk,

@@ -78,6 +78,10 @@ __global__ void k_diag(DevProblem P, const double* __restrict__ camDiag, double*
     }
 }
 void launch_diag(const DevProblem& P, const double* camDiag, double* diagN, cudaStream_t st) {
+    if (P.ioGeneral) {      // IO columns: prior term, then the Gram diagonals of every image that uses the column
+        cudaMemcpyAsync(diagN, camDiag, sizeof(double) * P.nC, cudaMemcpyDeviceToDevice, st);
+        launch_io_diag_grad_gen(P, camDiag, nullptr, diagN, nullptr, st);
+    }
     int n = P.nOP * 3;
     if (P.nImg * 6 > n) n = P.nImg * 6;
     if (DBAT_NSLOT > n) n = DBAT_NSLOT;
@@ -135,6 +139,7 @@ __global__ void k_build_S(DevProblem P, const double* __restrict__ camDiag, cons
 }
 void launch_build_S(const DevProblem& P, const double* camDiag, const double* camG, double lambda,
                     cudaStream_t st) {
+    if (P.ioGeneral) { launch_build_S_gen(P, camDiag, camG, lambda, st); return; }
     tchol_zero_dev(P.T, st);
     k_build_S<<<P.nImg + 1, 128, 0, st>>>(P, camDiag, camG, lambda);
     count_launch();
@@ -660,6 +665,7 @@ static int g_schur_mode = -1;       // 0 = grouped atomic (default), 1 = determi
 static double* g_shAcc = nullptr;
 void launch_schur(const DevProblem& P, double lambda, cudaStream_t st) {
     if (P.nOP <= 0) return;
+    if (P.ioGeneral) { launch_schur_gen(P, lambda, st); return; }
     if (g_schur_mode < 0) {
         const char* e = getenv("DBAT_SCHUR");
         g_schur_mode = (e && e[0] == 'd') ? 1 : (e && e[0] == 'p') ? 2 : 0;
@@ -878,7 +884,7 @@ __global__ void __launch_bounds__(128) k_jp_cam(DevProblem P, const double* __re
     double jp2 = 0.0, rjp = 0.0;
     if (i < P.nImg) {
         if (lane < NV) {
-            const int c = lane < DBAT_NSLOT ? P.sh_col[lane] : P.eo_col[6 * (size_t)i + lane - DBAT_NSLOT];
+            const int c = P.cam_colx[(size_t)DBAT_NCAM * i + lane];
             vs[warp][lane] = c >= 0 ? p[c] : 0.0;
         }
         __syncwarp();
@@ -925,7 +931,9 @@ void launch_backsub(const DevProblem& P, double lambda, const double* pc, double
     static const bool perPoint = getenv("DBAT_POINT_SIDE_PER_POINT") != nullptr;
     if (pc != p) cudaMemcpyAsync(p, pc, sizeof(double) * P.nC, cudaMemcpyDeviceToDevice, st);
     int nb = 0;
-    if (P.nOP > 0) {
+    if (P.nOP > 0 && P.ioGeneral) {
+        nb = launch_backsub_gen(P, lambda, p, jpOut ? partial : nullptr, st);
+    } else if (P.nOP > 0) {
         if (perPoint || !P.psb_pt) {
             nb = (P.nOP + 127) / 128;
             k_backsub<<<nb, 128, 0, st>>>(P, lambda, p, jpOut ? partial : nullptr, nb, nullptr, 0);

@@ -317,12 +317,81 @@ def test_unsupported_configurations_fail_loudly():
     s.IO.model.distModel[:] = 7
     with pytest.raises(dbat_b200._lib.DbatError):
         dbat_b200.Problem(s)
-    s, _ = scene(model=3)
-    s.IO.struct.block = np.tile(np.arange(1, s.IO.val.shape[1] + 1), (10, 1))   # image-variant IO
+    s, _ = scene(model=3)                                   # the dense point covariance needs one shared IO block
+    s.IO.struct.block[1:3, :] = np.arange(1, s.IO.val.shape[1] + 1)
     s.bundle.serial = None
     buildserialindices(s)
+    P = dbat_b200.Problem(s)
+    P(serialize(s))
     with pytest.raises(dbat_b200._lib.DbatError):
-        dbat_b200.Problem(s)
+        P.cov('cxx', 1.0)
+    P.close()
+
+
+def _general_io_scene(kind):
+    """IO block structures beyond one shared camera (IO.struct.block, buildserialindices.m:162-221)."""
+    s, truth = make_scene(24, 260, rays=8, seed=21, build_indices=False)
+    nImg = s.IO.val.shape[1]
+    if kind == 'image-variant-pp':
+        # romabundledemo_imagevariant.m:44: every image its own principal point, everything else shared
+        s.IO.struct.block[1:3, :] = np.arange(1, nImg + 1)
+    elif kind == 'two-cameras':
+        # setdbatcamsandimages.m:28: one block per camera; the second camera has its own lens
+        cam = (np.arange(nImg) % 2) + 1
+        s.IO.struct.block[:] = cam[None, :]
+        s.IO.val[0, cam == 2] *= 1.01
+        s.IO.val[1, cam == 2] += 0.05
+    elif kind == 'image-variant-all':
+        s.IO.struct.block[:] = np.arange(1, nImg + 1)[None, :]
+        s.bundle.est.IO[3:, :] = False                      # per image: cc and pp only (keeps every image well determined)
+    s.bundle.serial = None
+    buildserialindices(s)
+    return s
+
+
+@pytest.mark.parametrize('kind', ['image-variant-pp', 'two-cameras', 'image-variant-all'])
+def test_general_io_blocks(kind):
+    """More than one IO block (per-image IO columns of multi_res.m:92-111): residual and Jacobian
+    (pattern bit-exact), one damped step against the dense solve, GNA / LMP / LM against the oracle, and the
+    posterior covariances - the whole hot path through the general-IO kernels (general_io.cu)."""
+    s = _general_io_scene(kind)
+    x0 = serialize(s)
+    W = buildweightmatrix(s)
+    P = dbat_b200.Problem(copy.deepcopy(s))
+    r = P(x0)
+    ro, Jo = brown_euler_cam4(x0, s, True)
+    assert relmax(r, ro) < RES_RTOL
+    J = P.jacobian(True)
+    Jw = Jo.multiply(np.sqrt(W)[:, None]).tocsc()
+    Jw.sort_indices()
+    assert np.array_equal(J.indptr, Jw.indptr) and np.array_equal(J.indices, Jw.indices)
+    np.testing.assert_allclose(J.data, Jw.data, rtol=1e-11, atol=1e-13 * np.abs(Jw.data).max())
+    rw = ro * np.sqrt(W)
+    N = (Jw.T @ Jw).toarray()
+    for lam, jacobi in ((0.0, False), (1e3, False), (0.0, True)):
+        p, st = P.normal_step(x0, lam, jacobi)
+        po = np.linalg.solve(N + lam * np.eye(N.shape[0]), -(Jw.T @ rw))
+        assert relmax(p, po) < 5e-9, (lam, jacobi)
+        jp = Jw @ po
+        assert abs(st['jp2'] - jp @ jp) <= 1e-9 * (jp @ jp)
+        assert abs(st['rjp'] - rw @ jp) <= 1e-9 * abs(rw @ jp)
+    P.close()
+    for damping in ('gna', 'lmp', 'lm'):
+        s1, s2 = copy.deepcopy(s), copy.deepcopy(s)
+        s1, ok, it, s0, E = dbat_b200.bundle(s1, damping)
+        s2, oko, ito, s0o, Eo = obundle(s2, damping)
+        assert ok and oko and E.code == Eo.code == 0
+        np.testing.assert_allclose(s0, s0o, rtol=EST_RTOL)
+        if damping != 'lm':
+            assert it == ito
+            np.testing.assert_allclose(E.x, Eo.x, rtol=EST_RTOL, atol=EST_ATOL)
+            np.testing.assert_allclose(s1.IO.val, s2.IO.val, rtol=EST_RTOL, atol=EST_ATOL)
+        else:
+            np.testing.assert_allclose(E.x, Eo.x, rtol=1e-6, atol=1e-9)
+        if damping == 'gna':
+            for w in ('CIO', 'CEO', 'COP'):
+                Cg, Co = dense(dbat_b200.bundle_cov(s1, E, w)), dense(ocov(s2, Eo, w))
+                assert Cg.shape == Co.shape and relmax(Cg, Co) < 1e-7, w
 
 
 def test_full_size_properties():
