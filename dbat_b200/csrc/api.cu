@@ -882,7 +882,7 @@ extern "C" int dbat_eval(dbat_handle* h, const double* x, double* r, int weighte
 
 static int build_csc(dbat_handle* h, int weighted) {
     if (h->cscWeighted == weighted) return 0;
-    if (h->nranks > 1) { h->err = "Jacobian export is single-rank only"; return DBAT_E_UNSUPPORTED; }
+    // several ranks: every rank exports the rows of ITS observations (and its prior rows); columns are x columns
     DevProblem& P = h->P;
     if (!h->params_valid) { set_params(h, h->d_x); h->params_valid = true; }
     const int LD = DBAT_NSLOT + 9;
@@ -1560,14 +1560,22 @@ __global__ void k_point_pd_check(DevProblem P, int* __restrict__ bad) {
 
 extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
     if (!h || !out) return DBAT_E_BADARG;
-    if (h->nranks > 1) { h->err = "dbat_cov is single-rank only"; return DBAT_E_UNSUPPORTED; }
+    // several ranks: every rank holds the whole (summed) reduced system and inverts it redundantly; CIO / CEO come out
+    // identical everywhere, COP covers the points of this rank (it shards by point like the solve, bundle_cov.m:400-455)
     DevProblem& P = h->P;
     int rc;
     if (!h->normal_valid) { if ((rc = eval_full(h))) return rc; }
     // undamped, Jacobi-scaled reduced system (tiles, S order) -> dense copy -> dense factor -> explicit
     // inverse.  The dense path (chol.cu) is kept for the covariances: inv(S) is a full matrix.
     launch_build_S(P, h->d_camDiag, h->d_camG, 0.0, h->st);
+    if (h->nranks > 1 && h->rank != 0) { tchol_zero(h->tc, h->st); cudaMemsetAsync(P.rhs, 0, sizeof(double) * P.ldS, h->st); }
     launch_schur(P, 0.0, h->st);
+    if (h->nranks > 1) {                     // every tile of S, summed, on every rank
+        const TCholDev& td = h->tc.d;
+        rc = allreduce(h, td.tiles, (size_t)td.nTopS * TC_TT);
+        if (!rc && td.nOwnS > 0) rc = allreduce(h, td.tiles + (size_t)td.nTop * TC_TT, (size_t)td.nOwnS * TC_TT);
+        if (rc) return rc;
+    }
     launch_diag(P, h->d_camDiag, h->d_diagN, h->st);
     launch_inv_sqrt(h->d_diagN, h->d_dscale, P.nC, h->st);
     launch_scale_prep(P, h->d_dscale, h->d_dS, h->st);

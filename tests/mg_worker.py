@@ -52,6 +52,23 @@ for method in ('lm', 'gna', 'lmp'):
             bad.append(method + ' iteration count')
         check(method + ' x', xg, o1.x, 1e-9)
         check(method + ' rr', o.rr, o1.rr, 1e-10)
+# posterior covariances on the shards: camera blocks identical on every rank, point blocks for the rank's own points
+o = P.solve('gna', x0, want_trace=False, want_resid=False)
+s0 = 1.3
+ceo, cop = P.cov('ceo', s0), P.cov('cop', s0)
+lo, hi = P.parts[rank]
+t = torch.zeros(s.OP.val.shape[1], 3, 3, dtype=torch.float64, device='cuda')
+t[lo:hi] = torch.from_numpy(cop[:hi - lo]).cuda()
+dist.all_reduce(t)
+if rank == 0:
+    P1.solve('gna', x0, want_trace=False, want_resid=False)
+    check('CEO', ceo, P1.cov('ceo', s0), 1e-8)
+    check('COP', t.cpu().numpy(), P1.cov('cop', s0), 1e-8)
+    # Jacobian of the shard: the rows of this rank's observations out of the single-GPU Jacobian
+    Js, J1 = P.jacobian(True), P1.jacobian(True)
+    sel = np.flatnonzero((s.IP.op >= lo) & (s.IP.op < hi))
+    rows = np.stack([2 * sel, 2 * sel + 1], axis=1).ravel()
+    check('J rows of the shard', Js[:2 * len(sel)].toarray(), J1[rows].toarray(), 1e-12)
 flag = torch.tensor([len(bad)], device='cuda')
 dist.broadcast(flag, src=0)
 dist.barrier()
