@@ -219,14 +219,15 @@ def tile_symbolic(img, op, nImg, nOP, nEO, nIO, mode=-1, leaf=120, parts=1, part
                termPtr=np.empty(out['nTasks'] + 1, np.int64), termAB=np.empty(max(1, 2 * out['nTerms']), np.int64),
                level=np.empty(nT, np.int64), s2kind=np.empty(out['ld'], np.int64), bwdCols=np.empty(nT, np.int64))
     lib().dbat_tile_symbolic_get(*[iptr(arr[k]) for k in ('imgS', 'tix', 'taskIJ', 'termPtr', 'termAB', 'level', 's2kind', 'bwdCols')])
-    arr2 = dict(taskMode=np.empty(max(1, out['nTasks']), np.int64), colOwner=np.empty(nT, np.int64),
+    arr2 = dict(taskMode=np.empty(max(1, 4 * out['nTasks']), np.int64), colOwner=np.empty(nT, np.int64),
                 ownSBegin=np.empty(out['nParts'] + 1, np.int64))
     lib().dbat_tile_symbolic_get2(*[iptr(arr2[k]) for k in ('taskMode', 'colOwner', 'ownSBegin')])
     out.update(arr)
     out.update(arr2)
     out['tix'] = out['tix'].reshape(nT, nT)
     out['taskIJ'] = out['taskIJ'][:2 * out['nTasks']].reshape(-1, 2)
-    out['taskMode'] = out['taskMode'][:out['nTasks']]
+    tm = out['taskMode'][:4 * out['nTasks']].reshape(-1, 4)
+    out['taskMode'], out['taskWait'], out['taskSet'], out['taskInit'] = tm[:, 0].copy(), tm[:, 1].copy(), tm[:, 2].copy(), tm[:, 3].copy()
     out['termAB'] = out['termAB'][:2 * out['nTerms']].reshape(-1, 2)
     out['bwdCols'] = out['bwdCols'][out['bwdCols'] >= 0]
     return out

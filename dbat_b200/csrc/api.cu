@@ -817,6 +817,10 @@ static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, 
     ph_end(h, PH_SCHUR, a);
     a = ph_begin(h);
     tchol_put_rhs(tc, P.rhs, h->st, !dist || h->rank == 0);
+    static const char* profPath = getenv("DBAT_TCHOL_PROF");       // debugging: per-task time stamps of the 3rd factorisation
+    static int profCount = 0;
+    unsigned long long* dprof = nullptr;
+    if (profPath && ++profCount == 3) { cudaMalloc(&dprof, sizeof(unsigned long long) * 4 * tc.sym.nTasks); cudaMemset(dprof, 0, sizeof(unsigned long long) * 4 * tc.sym.nTasks); tc.d.prof = dprof; }
     tchol_factor_begin(tc, h->st);
     if (dist) {
         // every rank has factored the columns of its own subtree and subtracted its subtree's contribution from the
@@ -825,6 +829,23 @@ static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, 
         if (rc) return rc;
     }
     tchol_factor_end(tc, h->st);
+    if (dprof) {
+        cudaStreamSynchronize(h->st);
+        const TileSym& sy = tc.sym;
+        std::vector<unsigned long long> hp((size_t)4 * sy.nTasks);
+        cudaMemcpy(hp.data(), dprof, sizeof(unsigned long long) * hp.size(), cudaMemcpyDeviceToHost);
+        unsigned long long t0 = ~0ull;
+        for (int t = 0; t < sy.nTasks; ++t) if (hp[4 * t]) t0 = std::min(t0, hp[4 * t]);
+        if (FILE* f = fopen(profPath, "w")) {
+            fprintf(f, "task,I,J,level,mode,nterms,t_claim,t_terms,t_deps,t_end\n");
+            for (int t = 0; t < sy.nTasks; ++t)
+                fprintf(f, "%d,%d,%d,%d,%d,%lld,%lld,%lld,%lld,%lld\n", t, sy.taskI[t], sy.taskJ[t], sy.level[sy.taskJ[t]], (int)sy.taskMode[t],
+                        (long long)(sy.termPtr[t + 1] - sy.termPtr[t]), (long long)(hp[4 * t] - t0), (long long)(hp[4 * t + 1] - t0),
+                        (long long)(hp[4 * t + 2] - t0), (long long)(hp[4 * t + 3] - t0));
+            fclose(f);
+        }
+        cudaFree(dprof); tc.d.prof = nullptr;
+    }
     ph_end(h, PH_CHOL, a);
     a = ph_begin(h);
     tchol_solve(tc, h->st);

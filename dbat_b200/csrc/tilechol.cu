@@ -234,16 +234,18 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int 
         double* tile = D.tiles + ((size_t)slot << 12);
         const long long t0 = D.termPtr[task];
         const int nterm = (int)(D.termPtr[task + 1] - t0);
-        // ---- accumulator: -S(I,J) for tiles of the pattern of S, zero for fill tiles
+        // ---- accumulator: minus the tile's content (S itself, or what an earlier link of this tile's chain / the
+        //      other ranks left there), or zero for a fill tile nobody has touched
         double acc[4][4][2];
-        if (D.inS(slot) || (D.taskMode[task] == 0 && slot < D.nTop && D.nTop < D.nSlots)) {
-            // tiles of S; in a distributed run also every top tile of phase 2 (it holds the summed partial results)
+        const int waitAux = D.taskWait[task];
+        if (waitAux >= 0) warp_wait_flag(D.aux + waitAux, epoch, lane);
+        if (D.taskInit[task]) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const double* p0 = tile + (wn + 8 * j + 2 * fk) * 64 + wm + 8 * i + fr;
-                    acc[i][j][0] = -p0[0]; acc[i][j][1] = -p0[64];
+                    acc[i][j][0] = -__ldcg(p0); acc[i][j][1] = -__ldcg(p0 + 64);
                 }
         } else {
 #pragma unroll
@@ -347,6 +349,12 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int 
                     double* p0 = tile + (wn + 8 * j + 2 * fk) * 64 + wm + 8 * i + fr;
                     p0[0] = -acc[i][j][0]; p0[64] = -acc[i][j][1];
                 }
+            const int setAux = D.taskSet[task];
+            if (setAux >= 0) {
+                __syncthreads();                               // every thread's stores before the release
+                if (tid == 0) st_release(D.aux + setAux, epoch);
+            }
+            TC_STAMP(3)
             continue;
         }
         // ---- C = S - sum (= -acc) into the work tile (column-major, stride LA)
@@ -599,6 +607,8 @@ int tchol_alloc(TChol& w, const TileSym& sym) {
     bad |= up(w, &d.slotI, s.slotI); bad |= up(w, &d.slotJ, s.slotJ);
     bad |= up(w, &d.colPtr, s.colPtr); bad |= up(w, &d.colSlot, s.colSlot);
     bad |= up(w, &d.taskI, s.taskI); bad |= up(w, &d.taskJ, s.taskJ); bad |= up(w, &d.taskMode, s.taskMode);
+    bad |= up(w, &d.taskWait, s.taskWait); bad |= up(w, &d.taskSet, s.taskSet); bad |= up(w, &d.taskInit, s.taskInit);
+    bad |= al(w, &d.aux, (size_t)std::max(1, s.nAux), true);
     d.nTopS = s.nTopS; d.nTop = s.nTop; d.nOwnS = s.nOwnS;
     {
         std::vector<long long> tp(s.termPtr.begin(), s.termPtr.end());

@@ -21,6 +21,8 @@ struct TCholDev {
     const int* slotI = nullptr; const int* slotJ = nullptr;
     const int* colPtr = nullptr; const int* colSlot = nullptr;
     const int* taskI = nullptr; const int* taskJ = nullptr; const unsigned char* taskMode = nullptr;
+    const int* taskWait = nullptr; const int* taskSet = nullptr; const unsigned char* taskInit = nullptr;
+    int* aux = nullptr;                // nAux flags of the partial-sum chains (== epoch when the link is done)
     const long long* termPtr = nullptr; const int* termA = nullptr; const int* termB = nullptr;
     const int* bwdCols = nullptr;
     const unsigned char* valid = nullptr;   // per S index: 1 = real unknown (enters the pivot statistics)

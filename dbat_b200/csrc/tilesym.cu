@@ -398,35 +398,70 @@ int tile_symbolic(int nImg, const int64_t* adjPtr, const int32_t* adj, const int
     std::vector<int> cols(nT);
     std::iota(cols.begin(), cols.end(), 0);
     std::stable_sort(cols.begin(), cols.end(), [&](int a, int b) { return out.level[a] < out.level[b]; });
-    out.taskI.clear(); out.taskJ.clear(); out.taskMode.clear(); out.termPtr.assign(1, 0); out.termA.clear(); out.termB.clear();
+    out.taskI.clear(); out.taskJ.clear(); out.taskMode.clear(); out.taskWait.clear(); out.taskSet.clear(); out.taskInit.clear(); out.termPtr.assign(1, 0); out.termA.clear(); out.termB.clear();
     const int me = out.myPart;
-    struct Tmp { double key; int I, J, mode; std::vector<int> a, b; };
+    struct Tmp { double key; int I, J, mode, wait, set, init; std::vector<int> a, b, lev; };
+    auto inS = [&](int slot) { return slot < out.nTopS || (slot >= out.nTop && slot < out.nTop + out.nOwnS); };
     auto collect = [&](int I, int J, int mode_, int termOwner, Tmp& t) -> bool {   // terms whose column k has owner termOwner
         const std::vector<int>& ri = rowCols[I];
         const std::vector<int>& rj = rowCols[J];
         size_t a = 0, b = 0;
-        int maxLevel = -1;
-        t.I = I; t.J = J; t.mode = mode_; t.a.clear(); t.b.clear();
+        std::vector<std::pair<int, int>> tk;                       // (level, k) of the common columns
+        t.I = I; t.J = J; t.mode = mode_; t.a.clear(); t.b.clear(); t.lev.clear();
         while (a < ri.size() && b < rj.size() && ri[a] < J && rj[b] < J) {
             if (ri[a] < rj[b]) ++a;
             else if (ri[a] > rj[b]) ++b;
             else {
-                if (out.colOwner[ri[a]] == termOwner) {
-                    t.a.push_back(out.tix[(size_t)I * nT + ri[a]]);
-                    t.b.push_back(out.tix[(size_t)J * nT + rj[b]]);
-                    maxLevel = std::max(maxLevel, out.level[ri[a]]);
-                }
+                if (out.colOwner[ri[a]] == termOwner) tk.emplace_back(out.level[ri[a]], ri[a]);
                 ++a; ++b;
             }
         }
-        // a final task sorts with its column; a partial sum right after the last column it reads
-        t.key = mode_ == 0 ? (double)out.level[J] : maxLevel + 0.5;
+        // in the order the tiles become available (elimination-tree level), not by index: a task must not sit on a
+        // tile of a late subtree while others are ready
+        std::stable_sort(tk.begin(), tk.end());
+        for (auto& lk : tk) {
+            t.a.push_back(out.tix[(size_t)I * nT + lk.second]);
+            t.b.push_back(out.tix[(size_t)J * nT + lk.second]);
+            t.lev.push_back(lk.first);
+        }
         return !(mode_ == 1 && t.a.empty());                       // nothing to add from this subtree: no task
+    };
+    // A task with many terms becomes a chain: partial sums of <= TC_CHUNK terms each, written back to the tile and
+    // released through an auxiliary flag, then the task proper with the last terms.  Every link sorts into the list
+    // right after the last column it reads, so the early links run long before the tile's turn and the link on the
+    // critical path is short.
+    const int TC_CHUNK = getenv("DBAT_TC_CHUNK") ? std::max(2, atoi(getenv("DBAT_TC_CHUNK"))) : 10;
+    int nAux = 0;
+    auto emit_chain = [&](const Tmp& t, bool alwaysFromTile, std::vector<Tmp>& list) {
+        const int slot = out.tix[(size_t)t.I * nT + t.J];
+        const int n = (int)t.a.size();
+        const int firstInit = (alwaysFromTile || inS(slot)) ? 1 : 0;
+        const double finalKey = t.mode == 0 ? (double)out.level[t.J] : (n ? t.lev.back() + 0.5 : 0.0);
+        if (n <= TC_CHUNK + TC_CHUNK / 2) {
+            Tmp u = t; u.key = finalKey; u.wait = -1; u.set = -1; u.init = firstInit;
+            list.push_back(u);
+            return;
+        }
+        int prev = -1;
+        for (int b0 = 0; b0 < n; b0 += TC_CHUNK) {
+            int b1 = std::min(n, b0 + TC_CHUNK);
+            if (n - b1 < TC_CHUNK / 2) b1 = n;                     // no tiny last link
+            Tmp u;
+            u.I = t.I; u.J = t.J;
+            u.a.assign(t.a.begin() + b0, t.a.begin() + b1);
+            u.b.assign(t.b.begin() + b0, t.b.begin() + b1);
+            u.wait = prev; u.init = prev >= 0 ? 1 : firstInit;
+            if (b1 == n) { u.mode = t.mode; u.set = -1; u.key = finalKey; }
+            else { u.mode = 1; u.set = nAux++; u.key = t.lev[b1 - 1] + 0.5; prev = u.set; }
+            list.push_back(u);
+            if (b1 == n) break;
+        }
     };
     auto flush = [&](std::vector<Tmp>& list) {
         std::stable_sort(list.begin(), list.end(), [](const Tmp& x, const Tmp& y) { return x.key < y.key; });
         for (const Tmp& t : list) {
             out.taskI.push_back(t.I); out.taskJ.push_back(t.J); out.taskMode.push_back((unsigned char)t.mode);
+            out.taskWait.push_back(t.wait); out.taskSet.push_back(t.set); out.taskInit.push_back((unsigned char)t.init);
             out.termA.insert(out.termA.end(), t.a.begin(), t.a.end());
             out.termB.insert(out.termB.end(), t.b.begin(), t.b.end());
             out.termPtr.push_back((int64_t)out.termA.size());
@@ -439,22 +474,24 @@ int tile_symbolic(int nImg, const int64_t* adjPtr, const int32_t* adj, const int
         for (int J : cols) {
             if (out.colOwner[J] != me) continue;
             for (int e = out.colPtr[J]; e < out.colPtr[J + 1]; ++e)
-                if (collect(out.slotI[out.colSlot[e]], J, 0, me, tmp)) list.push_back(tmp);
+                if (collect(out.slotI[out.colSlot[e]], J, 0, me, tmp)) emit_chain(tmp, false, list);
         }
         for (int J : cols) {
             if (out.colOwner[J] >= 0) continue;
             for (int e = out.colPtr[J]; e < out.colPtr[J + 1]; ++e)
-                if (collect(out.slotI[out.colSlot[e]], J, 1, me, tmp)) list.push_back(tmp);
+                if (collect(out.slotI[out.colSlot[e]], J, 1, me, tmp)) emit_chain(tmp, false, list);
         }
         flush(list);
     }
     out.nTasks1 = (int)out.taskI.size();
+    const bool distributed = out.nParts > 1;
     for (int J : cols) {
         if (out.colOwner[J] >= 0) continue;
         for (int e = out.colPtr[J]; e < out.colPtr[J + 1]; ++e)
-            if (collect(out.slotI[out.colSlot[e]], J, 0, -1, tmp)) list.push_back(tmp);
+            if (collect(out.slotI[out.colSlot[e]], J, 0, -1, tmp)) emit_chain(tmp, distributed, list);   // distributed: the top tiles hold the summed partial results
     }
     flush(list);
+    out.nAux = nAux;
     out.nTasks = (int)out.taskI.size();
     out.nTerms = (int64_t)out.termA.size();
     // backward substitution: top columns (descending level) first, then this part's own columns
@@ -524,7 +561,10 @@ extern "C" int dbat_tile_symbolic_get(int64_t* imgS, int64_t* tix, int64_t* task
 extern "C" int dbat_tile_symbolic_get2(int64_t* taskMode, int64_t* colOwner, int64_t* ownSBegin) {
     const TileSym& s = g_last_sym;
     if (s.nT == 0) return DBAT_E_BADARG;
-    if (taskMode) for (int t = 0; t < s.nTasks; ++t) taskMode[t] = s.taskMode[t];
+    // taskMode: 4 values per task: mode, wait (aux flag or -1), set (aux flag or -1), init (1 = start from the tile)
+    if (taskMode) for (int t = 0; t < s.nTasks; ++t) {
+        taskMode[4 * t] = s.taskMode[t]; taskMode[4 * t + 1] = s.taskWait[t]; taskMode[4 * t + 2] = s.taskSet[t]; taskMode[4 * t + 3] = s.taskInit[t];
+    }
     if (colOwner) for (int J = 0; J < s.nT; ++J) colOwner[J] = s.colOwner[J];
     if (ownSBegin) for (size_t k = 0; k < s.ownSBegin.size(); ++k) ownSBegin[k] = s.ownSBegin[k];
     return DBAT_OK;

@@ -27,6 +27,9 @@ struct TileSym {
     int nTasks = 0, nTasks1 = 0, depth = 0;   // tasks [0, nTasks1): phase 1 (own columns + partial sums into top tiles),
                                               // [nTasks1, nTasks): phase 2 (top columns, after the partial sums are reduced)
     std::vector<unsigned char> taskMode;      // 0 = final (factor / solve, sets the tile's flag), 1 = partial sum only
+    std::vector<int> taskWait, taskSet;       // chains of partial sums on one tile: auxiliary flag to wait for / to set (-1: none)
+    std::vector<unsigned char> taskInit;      // 1: the accumulation starts from the tile's content, 0: from zero
+    int nAux = 0;
     int nBwd1 = 0;                            // bwdCols[0, nBwd1): top columns; [nBwd1, ..): this part's own columns
     int64_t nTerms = 0;
     int order_mode = 0;            // 0 natural, 1 rcm, 2 nested dissection

@@ -52,16 +52,30 @@ def _emulate(sym, S, rhs):
     # every entry of the lower triangle must lie in a stored tile
     r, c = np.nonzero(np.tril(M))
     assert np.all(tix[r // T, c // T] >= 0)
-    for (I, J), t0, t1 in zip(sym['taskIJ'], sym['termPtr'][:-1], sym['termPtr'][1:]):
+    aux = set()
+    cur = {}                                               # tiles under accumulation (chains of partial sums)
+    for k, ((I, J), t0, t1) in enumerate(zip(sym['taskIJ'], sym['termPtr'][:-1], sym['termPtr'][1:])):
         slot = tix[I, J]
         assert slot >= 0 and slot not in done
         inS = slot < sym['nTopS'] or sym['nTop'] <= slot < sym['nTop'] + sym['nOwnS']
-        C = M[I * T:(I + 1) * T, J * T:(J + 1) * T].copy() if inS else np.zeros((T, T))
         if not inS:
             assert not M[I * T:(I + 1) * T, J * T:(J + 1) * T].any()      # a fill tile holds no entry of S
+        if sym['taskWait'][k] >= 0:
+            assert sym['taskWait'][k] in aux, 'chain link before its predecessor'
+        if sym['taskInit'][k]:
+            C = cur.get(slot, M[I * T:(I + 1) * T, J * T:(J + 1) * T]).copy()
+            assert inS or slot in cur
+        else:
+            assert not inS and slot not in cur
+            C = np.zeros((T, T))
         for a, b in sym['termAB'][t0:t1]:
             assert a in done and b in done, 'task list is not a topological order'
             C -= tiles[a] @ tiles[b].T
+        if sym['taskMode'][k] == 1:
+            cur[slot] = C
+            if sym['taskSet'][k] >= 0:
+                aux.add(int(sym['taskSet'][k]))
+            continue
         if I == J:
             tiles[slot] = np.linalg.cholesky(np.tril(C) + np.tril(C, -1).T)
         else:
@@ -69,7 +83,8 @@ def _emulate(sym, S, rhs):
             assert d in done
             tiles[slot] = np.linalg.solve(tiles[d], C.T).T
         done.add(slot)
-    assert len(done) == sym['nSlots'] == sym['nTasks']
+    assert int((sym['taskMode'] == 0).sum()) == sym['nSlots']
+    assert len(done) == sym['nSlots']
     L = np.zeros((ld, ld))
     for I in range(nT):
         for J in range(I + 1):
@@ -172,6 +187,8 @@ def test_distributed_schedule_factors_the_reduced_system(built_lib, parts):
         tiles.append(t)
         final.append(set())
 
+    auxs = [set() for _ in range(parts)]
+
     def run(g, lo, hi, phase):
         sg, t, fin = syms[g], tiles[g], final[g]
         for k in range(lo, hi):
@@ -179,15 +196,21 @@ def test_distributed_schedule_factors_the_reduced_system(built_lib, parts):
             slot = int(tix[I, J])
             mode = int(sg['taskMode'][k])
             if phase == 1:
-                assert (owner[J] == g and mode == 0) or (owner[J] < 0 and mode == 1)
+                assert (owner[J] == g) or (owner[J] < 0 and mode == 1)
             else:
-                assert owner[J] < 0 and mode == 0
-            C = t[slot].copy()
+                assert owner[J] < 0
+            if sg['taskWait'][k] >= 0:
+                assert int(sg['taskWait'][k]) in auxs[g]
+            C = t[slot].copy() if sg['taskInit'][k] else np.zeros((T, T))
+            if not sg['taskInit'][k]:
+                assert not t[slot].any()
             for a, b in sg['termAB'][sg['termPtr'][k]:sg['termPtr'][k + 1]]:
                 assert int(a) in fin and int(b) in fin, 'read of a tile that is not final on this part'
                 C -= t[int(a)] @ t[int(b)].T
             if mode == 1:
                 t[slot] = C
+                if sg['taskSet'][k] >= 0:
+                    auxs[g].add(int(sg['taskSet'][k]))
                 continue
             if I == J:
                 t[slot] = np.linalg.cholesky(np.tril(C) + np.tril(C, -1).T)
