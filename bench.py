@@ -9,7 +9,8 @@ trial points are taken, so successive steps walk the real LM path.
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 N = 1: BASELINE config 4 (1000 cameras x 200k points x 2M observations, shared Brown IO, depend datum).
-N > 1 (torchrun, one rank per GPU): the block grows with N like BASELINE config 5 - 1000 cameras, 200k
+N > 1 (torchrun, one rank per GPU; --nimg / --nop select other shapes, e.g. --nimg 10000 --nop 500000 on 8 GPUs is
+BASELINE config 5 itself): the block grows with N like BASELINE config 5 - 1000 cameras, 200k
 points and 2M observations PER RANK (N = 8: 8000 x 1.6M x 16M; config 5 itself is 10k x 4M x 40M) - so the
 reduced camera system and its collective grow with N; every rank generates only its own points.  `value`
 counts 2M-observation equivalents, i.e. it aggregates over ranks (weak scaling).
@@ -168,8 +169,11 @@ def run_reference(args, rank, world):
         'steps': done, 'steps_requested': args.steps, 'warmup': 0, 'ms_per_step': 1e3 / its,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
         'config': {'workload': workload_name(nImg, args.nop, nobs, n, n - 3 * args.nop),
-                   'same_config': True,
-                   'note': 'full config, %d of %d requested iterations inside the %.0f s budget' % (done, args.steps, args.ref_budget)},
+                   'same_config': world == 1,
+                   'note': 'full config, %d of %d requested iterations inside the %.0f s budget' % (done, args.steps, args.ref_budget)
+                           + ('' if world == 1 else '; the GPU arm at %d ranks runs a %dx larger block (one such config per rank): the '
+                              'CPU figure is per 2M-observation equivalent of the 1-rank config, which flatters the CPU (its cost '
+                              'per observation grows with the block)' % (world, world))},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': '%d full LM iterations on the config itself; %s' % (done, CPU_DESC)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -313,9 +317,12 @@ def main():
                    'timing': 'CUDA events on the library stream around each step (max over ranks); wall '
                              'clock %.3f ms/step' % (1e3 * wall / args.steps),
                    'parallelism': ('single GPU' if world == 1 else
-                                   'points sharded over %d ranks; per solve one ncclAllReduce of the %d tiles of the '
-                                   'reduced system (%.1f MB) + rhs, per evaluation one of the per-image Grams; '
-                                   'factorisation replicated' % (world, info['nSlotsS'], sbytes / 1e6)),
+                                   'points sharded over %d ranks (every rank generates and uploads only its own points); per '
+                                   'evaluation one ncclAllReduce of the per-image Grams; per solve the factorisation of the '
+                                   'reduced system is distributed by elimination subtree: ncclReduce of the %d tiles of S '
+                                   '(%.1f MB) to their owners, ncclAllReduce of the separator tiles, of the rhs and of the '
+                                   'solution; the separators above the cut are factored on every rank'
+                                   % (world, info['nSlotsS'], sbytes / 1e6)),
                    'reduced_system': {k: info[k] for k in ('nT', 'nSlots', 'nSlotsS', 'nTasks', 'nTerms', 'depth', 'order_mode', 'nSeg')}},
         'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 8 * n * world, 'd2h_bytes_per_step': (8 * n + 64) * world},
         'gpu_launches': int(launches),

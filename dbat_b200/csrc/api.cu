@@ -71,7 +71,8 @@ static bool nccl_load() {
 // --------------------------------------------------------------------------------------------
 struct dbat_handle {
     std::string err;
-    cudaStream_t st = nullptr;
+    cudaStream_t st = nullptr, st2 = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr;
     DevProblem P{};
     int NC = 0, m = 0, nIOrec = 0;
     int nPriorIO = 0, nPriorEO = 0, nPriorOP = 0;
@@ -392,7 +393,10 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     for (int e = 0; e < 3 * nOP; ++e) if (colOP[e] >= 0) col2pt[colOP[e] - nC] = e;
 
     // ---- device side
-    if (cudaStreamCreate(&h->st) != cudaSuccess) return fail_create(h, DBAT_E_CUDA, "cudaStreamCreate failed");
+    if (cudaStreamCreate(&h->st) != cudaSuccess || cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming) != cudaSuccess)
+        return fail_create(h, DBAT_E_CUDA, "cudaStreamCreate failed");
     int rc = 0;
 #define UP(ptr, vec) if ((rc = dev_upload(h, &ptr, vec))) return fail_create(h, rc, h->err)
 #define AL(ptr, cnt) if ((rc = dev_alloc(h, &ptr, (size_t)(cnt)))) return fail_create(h, rc, h->err)
@@ -633,6 +637,9 @@ extern "C" void dbat_destroy(dbat_handle* h) {
     tchol_free(h->tc);
     for (auto& e : h->ev) cudaEventDestroy(e);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
+    if (h->st2) cudaStreamDestroy(h->st2);
+    if (h->evFork) cudaEventDestroy(h->evFork);
+    if (h->evJoin) cudaEventDestroy(h->evJoin);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
 }
@@ -702,8 +709,14 @@ static int eval_full(dbat_handle* h) {
     h->jp_vec = nullptr;
     set_params(h, h->d_x);
     h->params_valid = true;
+    // camera side and point side read the same parameters and write disjoint outputs; both are latency- rather than
+    // bandwidth-bound, so they run side by side on two streams
+    cudaEventRecord(h->evFork, h->st);
+    cudaStreamWaitEvent(h->st2, h->evFork, 0);
+    launch_point_side(h->P, h->st2);
+    cudaEventRecord(h->evJoin, h->st2);
     launch_cam_side(h->P, h->d_img_chunk_start, h->d_tmpG, h->st);
-    launch_point_side(h->P, h->st);
+    cudaStreamWaitEvent(h->st, h->evJoin, 0);
     launch_prior_apply(h->P, h->d_x, h->d_camDiag, h->d_camG, h->d_col2pt, h->st);
     // r'r = Gram(r,r) + prior rows
     double* hG = h->h_G;

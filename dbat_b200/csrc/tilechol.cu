@@ -214,7 +214,11 @@ __device__ void tc_potrf64(double* As, double* Xd, double* colb, int warp, int l
 // ---------------------------------------------------------------------------------------------
 // the factorisation kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int epoch, int taskBegin, int taskEnd, int counter) {
+// queue[qBegin, qEnd): the task ids this launch serves, claimed in order through counters[counter].  chain != 0: this
+// launch holds the few CTAs of the dependency chain (launched with enough dynamic shared memory to have an SM each);
+// they let the bulk launch, which waits on them programmatically, start as soon as they are all resident.
+__global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int epoch, int qBegin, int qEnd, int counter, int chain) {
+    if (chain) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     extern __shared__ __align__(16) double sm[];
     __shared__ int s_task;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -224,10 +228,10 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int 
     double* colb = sm + TC_OFF_COLB;
     for (;;) {
         __syncthreads();                                      // previous task's shared memory is free
-        if (tid == 0) s_task = taskBegin + atomicAdd(D.counters + counter, 1);
+        if (tid == 0) { const int q = qBegin + atomicAdd(D.counters + counter, 1); s_task = q < qEnd ? D.queue[q] : -1; }
         __syncthreads();
         const int task = s_task;
-        if (task >= taskEnd) break;
+        if (task < 0) break;
         TC_STAMP(0)
         const int I = D.taskI[task], J = D.taskJ[task];
         const int slot = D.tix[(size_t)I * D.nT + J];
@@ -472,7 +476,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tchol_bwd(TCholDev D, int epoch,
     const int nT = D.nT;
     for (;;) {
         __syncthreads();
-        if (tid == 0) s_task = atomicAdd(D.counters + 1, 1);
+        if (tid == 0) s_task = atomicAdd(D.counters + 4, 1);
         __syncthreads();
         if (s_task >= nCols) break;
         const int J = D.bwdCols[s_task];
@@ -599,6 +603,10 @@ static int al(TChol& w, T** dst, size_t cnt, bool zero) {
 
 int tchol_alloc(TChol& w, const TileSym& sym) {
     w.sym = sym;
+    {   // the task ids in list order behind the four queues: the unsplit launch walks them
+        TileSym& ms = w.sym;
+        for (int t = 0; t < ms.nTasks; ++t) ms.queue.push_back(t);
+    }
     const TileSym& s = w.sym;
     TCholDev& d = w.d;
     d.nT = s.nT; d.ld = s.ld; d.nSlots = s.nSlots; d.nSlotsS = s.nSlotsS; d.nTasks = s.nTasks;
@@ -616,6 +624,7 @@ int tchol_alloc(TChol& w, const TileSym& sym) {
     }
     bad |= up(w, &d.termA, s.termA); bad |= up(w, &d.termB, s.termB);
     bad |= up(w, &d.bwdCols, s.bwdCols);
+    bad |= up(w, &d.queue, s.queue);
     bad |= up(w, &w.colOwnerDev, s.colOwner);
     {
         std::vector<unsigned char> valid(s.ld);
@@ -626,7 +635,7 @@ int tchol_alloc(TChol& w, const TileSym& sym) {
     bad |= al(w, &d.invD, (size_t)s.nT * TC_XD, true);
     bad |= al(w, &d.flag, (size_t)s.nSlots, true);
     bad |= al(w, &d.xflag, (size_t)s.nT, true);
-    bad |= al(w, &d.counters, 4, true);
+    bad |= al(w, &d.counters, 8, true);
     bad |= al(w, &d.info, 1, true);
     bad |= al(w, &d.minmax, 2, true);
     bad |= al(w, &w.xs, (size_t)s.ld, true);
@@ -641,6 +650,17 @@ int tchol_alloc(TChol& w, const TileSym& sym) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_tchol_factor, TC_THREADS, smem);
     if (occ < 1) occ = 1;
     w.gridFactor = std::max(1, std::min(std::max(s.nTasks1, s.nTasks - s.nTasks1), sms * occ));
+    // chain CTAs: a shared-memory request above half an SM keeps every other CTA off their SM
+    int smemMax = 0;
+    cudaDeviceGetAttribute(&smemMax, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    w.smemChain = std::min(smemMax, 160 * 1024);
+    {
+        const char* e = getenv("DBAT_TC_CHAIN_CTAS");
+        w.nCrit = e ? atoi(e) : 24;
+        if (w.smemChain < 120 * 1024 || sms < 4 * w.nCrit) w.nCrit = 0;
+        if (w.nCrit > 0) w.gridFactor = std::max(1, std::min(w.gridFactor, (sms - w.nCrit) * occ));
+    }
+    cudaFuncSetAttribute(k_tchol_factor, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(smem, w.smemChain));
     int occ2 = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_tchol_bwd, TC_THREADS, 0);
     if (occ2 < 1) occ2 = 1;
@@ -675,22 +695,46 @@ void tchol_pack_stats(TChol& w, unsigned long long* buf, bool unpack, cudaStream
     k_tc_pack_stats<<<1, 32, 0, st>>>(w.d, buf, unpack ? 1 : 0);
     count_launch();
 }
-static void factor_launch(TChol& w, int t0, int t1, int counter, cudaStream_t st) {
-    if (t1 <= t0) return;
-    const int grid = std::max(1, std::min(w.gridFactor, t1 - t0));
-    k_tchol_factor<<<grid, TC_THREADS, TC_SMEM_DOUBLES * 8, st>>>(w.d, w.epoch, t0, t1, counter);
-    count_launch();
+// One phase: the chain queue on w.nCrit CTAs that own an SM each (their dynamic shared memory request leaves no room
+// for a second CTA), the bulk queue on a second launch in the same stream with programmatic stream serialisation: it
+// starts once every chain CTA is resident and has executed griddepcontrol.launch_dependents - so the chain CTAs can
+// never be locked out by spinning bulk CTAs.  Small systems: one launch serves both queues.
+static void factor_phase(TChol& w, int ph, cudaStream_t st) {
+    const TileSym& s = w.sym;
+    const int c0 = s.qOff[2 * ph], b0 = s.qOff[2 * ph + 1], b1 = s.qOff[2 * ph + 2];
+    if (b1 <= c0) return;
+    const int smemBulk = TC_SMEM_DOUBLES * 8;
+    if (w.nCrit <= 0 || b0 - c0 < 4 * w.nCrit) {
+        // no split: the two queues are served one after the other by the same CTAs would break the priority order,
+        // so merge them back by task id
+        k_tchol_factor<<<std::max(1, std::min(w.gridFactor, b1 - c0)), TC_THREADS, smemBulk, st>>>(w.d, w.epoch, s.qOff[4] + (ph == 0 ? 0 : s.nTasks1),
+            s.qOff[4] + (ph == 0 ? s.nTasks1 : s.nTasks), 2 * ph, 0);
+        count_launch();
+        return;
+    }
+    k_tchol_factor<<<w.nCrit, TC_THREADS, w.smemChain, st>>>(w.d, w.epoch, c0, b0, 2 * ph, 1);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)std::max(1, std::min(w.gridFactor, b1 - b0)));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smemBulk;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_tchol_factor, w.d, w.epoch, b0, b1, 2 * ph + 1, 0);
+    count_launch(2);
 }
 void tchol_factor_begin(TChol& w, cudaStream_t st) {
     ++w.epoch;
-    cudaMemsetAsync(w.d.counters, 0, sizeof(int) * 4, st);
+    cudaMemsetAsync(w.d.counters, 0, sizeof(int) * 8, st);
     cudaMemsetAsync(w.d.info, 0, sizeof(int), st);
     static const unsigned long long init[2] = {0x7fefffffffffffffull, 0ull};      // DBL_MAX, 0
     cudaMemcpyAsync(w.d.minmax, init, sizeof(init), cudaMemcpyHostToDevice, st);
-    factor_launch(w, 0, w.sym.nTasks1, 0, st);
+    factor_phase(w, 0, st);
 }
 void tchol_factor_end(TChol& w, cudaStream_t st) {
-    factor_launch(w, w.sym.nTasks1, w.sym.nTasks, 2, st);
+    factor_phase(w, 1, st);
 }
 void tchol_factor(TChol& w, cudaStream_t st) {
     tchol_factor_begin(w, st);

@@ -22,6 +22,7 @@ struct TCholDev {
     const int* colPtr = nullptr; const int* colSlot = nullptr;
     const int* taskI = nullptr; const int* taskJ = nullptr; const unsigned char* taskMode = nullptr;
     const int* taskWait = nullptr; const int* taskSet = nullptr; const unsigned char* taskInit = nullptr;
+    const int* queue = nullptr;        // task ids of the chain / bulk queues of both phases
     int* aux = nullptr;                // nAux flags of the partial-sum chains (== epoch when the link is done)
     const long long* termPtr = nullptr; const int* termA = nullptr; const int* termB = nullptr;
     const int* bwdCols = nullptr;
@@ -36,7 +37,8 @@ struct TChol {
     TileSym sym;
     TCholDev d;
     int epoch = 0;
-    int gridFactor = 0, gridBwd = 0;
+    int smemChain = 0;
+    int gridFactor = 0, gridBwd = 0, nCrit = 0;    // nCrit > 0: that many CTAs, alone on their SMs, serve the chain queue
     double* xs = nullptr;              // ld: solution in S order
     const int* colOwnerDev = nullptr;  // nT: owning part of every tile column (-1 = top)
     std::vector<void*> allocs;

@@ -494,6 +494,20 @@ int tile_symbolic(int nImg, const int64_t* adjPtr, const int32_t* adj, const int
     out.nAux = nAux;
     out.nTasks = (int)out.taskI.size();
     out.nTerms = (int64_t)out.termA.size();
+    // two queues per phase: the tasks on the dependency chain (every diagonal tile and, per column, the tile in the
+    // row of its elimination-tree parent - the last input of the parent's diagonal tile) and the bulk
+    out.queue.clear();
+    for (int ph = 0; ph < 2; ++ph) {
+        const int t0 = ph == 0 ? 0 : out.nTasks1, t1 = ph == 0 ? out.nTasks1 : out.nTasks;
+        for (int crit = 1; crit >= 0; --crit) {
+            out.qOff[2 * ph + (1 - crit)] = (int)out.queue.size();
+            for (int t = t0; t < t1; ++t) {
+                const bool c = out.taskMode[t] == 0 && (out.taskI[t] == out.taskJ[t] || out.taskI[t] == parent[out.taskJ[t]]);
+                if (c == (crit == 1)) out.queue.push_back(t);
+            }
+        }
+    }
+    out.qOff[4] = (int)out.queue.size();
     // backward substitution: top columns (descending level) first, then this part's own columns
     out.bwdCols.clear();
     for (auto it = cols.rbegin(); it != cols.rend(); ++it) if (out.colOwner[*it] < 0) out.bwdCols.push_back(*it);

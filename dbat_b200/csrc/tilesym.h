@@ -30,6 +30,8 @@ struct TileSym {
     std::vector<int> taskWait, taskSet;       // chains of partial sums on one tile: auxiliary flag to wait for / to set (-1: none)
     std::vector<unsigned char> taskInit;      // 1: the accumulation starts from the tile's content, 0: from zero
     int nAux = 0;
+    std::vector<int> queue;                   // task ids: [phase 1 chain | phase 1 bulk | phase 2 chain | phase 2 bulk]
+    int qOff[5] = {0, 0, 0, 0, 0};
     int nBwd1 = 0;                            // bwdCols[0, nBwd1): top columns; [nBwd1, ..): this part's own columns
     int64_t nTerms = 0;
     int order_mode = 0;            // 0 natural, 1 rcm, 2 nested dissection
