@@ -304,9 +304,12 @@ def main():
     if world == 1:
         wl = workload_name(nImg, nOP, nObsGlobal, n, nRed)
     else:
-        wl = ('BASELINE config 5 shape at %d/10 scale per axis: synthetic %d cameras x %d points x %d observations '
-              '(1000 x 200k x 2M per rank), shared IO + Brown self-calibration (model 3), LM iteration; n=%d '
-              'unknowns, reduced order %d' % (world, nImg, nOP, nObsGlobal, nGlobal, nRed))
+        c5 = (nImg, nOP) == (10000, 4000000)
+        wl = ('%s: synthetic %d cameras x %d points x %d observations (%d points and %d observations per rank, '
+              'every rank sees all cameras), shared IO + Brown self-calibration (model 3), LM iteration; n=%d '
+              'unknowns, reduced order %d'
+              % ('BASELINE config 5' if c5 else 'BASELINE config 5 shape (config 5 itself: 10000 x 4M x 40M), 1000 cameras + 200k points per rank',
+                 nImg, nOP, nObsGlobal, args.nop, nObsLocal, nGlobal, nRed))
     sbytes = info['nSlotsS'] * 4096 * 8
     line = {
         'metric': 'lm_iterations_per_s', 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
