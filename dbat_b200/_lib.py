@@ -61,7 +61,7 @@ EXPORTS = ['dbat_create', 'dbat_destroy', 'dbat_last_error', 'dbat_num_unknowns'
            'dbat_forwintersect', 'dbat_forwintersect_error', 'dbat_resect3', 'dbat_camera_order',
            'dbat_tile_symbolic', 'dbat_tile_symbolic_get', 'dbat_tile_symbolic_get2', 'dbat_tile_symbolic_coords',
            'dbat_tile_chol_solve',
-           'dbat_reduced_info']
+           'dbat_reduced_info', 'dbat_set_devices']
 
 _lib = None
 
@@ -131,6 +131,8 @@ def lib():
     L.dbat_resect3.restype = C.c_int
     L.dbat_camera_order.argtypes = [C.c_int64, C.c_int64, C.c_int64, c_ip, c_ip, c_ip, C.POINTER(C.c_int64)]
     L.dbat_camera_order.restype = C.c_int
+    L.dbat_set_devices.argtypes = [vp, C.POINTER(C.c_int), C.c_int]
+    L.dbat_set_devices.restype = C.c_int
     L.dbat_reduced_info.argtypes = [vp, c_ip]
     L.dbat_reduced_info.restype = C.c_int
     L.dbat_tile_symbolic.argtypes = [C.c_int64, C.c_int64, C.c_int64, c_ip, c_ip, c_ip, C.c_int64, C.c_int64,

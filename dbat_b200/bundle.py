@@ -164,6 +164,13 @@ class Problem:
         return p, dict(f=st[0], jp2=st[1], rjp=st[2], singular=bool(st[3]), launches=int(st[4]),
                        f_new=st[5], device_ms=st[6])
 
+    def set_devices(self, devices):
+        """One process, several GPUs (dbat_set_devices): shard this problem's object points over the listed CUDA
+        devices.  Every later call on the handle runs on all of them and returns merged results."""
+        arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+        self._check(_lib.lib().dbat_set_devices(self._h, arr, len(devices)))
+        return self
+
     def reduced_info(self):
         """Structure of the reduced camera system (tile counts, factorisation work, chain depth)."""
         v = np.zeros(16, dtype=np.int64)

@@ -12,6 +12,11 @@
 #include <string>
 #include <iterator>
 #include <vector>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <dlfcn.h>
 
 #include "../../include/dbat_gpu.h"
@@ -108,6 +113,9 @@ struct dbat_handle {
     bool normal_valid = false;          // Gram / point records correspond to d_x
     // comm
     void* comm = nullptr; int nranks = 1, rank = 0;
+    // a deep copy of the problem description (dbat_set_devices re-creates the problem per device from it)
+    struct DescCopy* dcopy = nullptr;
+    struct DevGroup* group = nullptr;   // non-null: this handle fronts one sub-problem per device
     // CSC cache
     std::vector<int64_t> cscJc, cscIr; std::vector<double> cscV; int cscWeighted = -1;
     // phase timing
@@ -170,6 +178,17 @@ static int fail_create(dbat_handle* h, int code, const std::string& msg) {
     if (h) dbat_destroy(h);
     return code;
 }
+
+struct DescCopy;
+static int group_eval(dbat_handle* h, const double* x, double* r, int weighted);
+static int group_normal_step(dbat_handle* h, const double* x, double lambda, int flags, double* p, double* stats);
+static int group_solve(dbat_handle* h, int method, const dbat_opts* opts, const double* x0, dbat_result* res);
+static int group_cov(dbat_handle* h, int which, double s0, double* out);
+static const dbat_handle* group_first(const dbat_handle* h);
+static DescCopy* copy_desc(const dbat_problem_desc* d, int NC);
+static void free_desc(DescCopy* c);
+static void group_destroy(dbat_handle* h);
+static thread_local bool g_in_group_create = false;
 
 // (Re)build everything that depends on the tiling of the reduced system: symbolic analysis for nParts parts, the S
 // index maps, the tile storage and the S-ordered work vectors.  dbat_create calls it for one part; dbat_comm_init
@@ -624,12 +643,15 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     for (auto& e : h->ev) cudaEventCreate(&e);
     cudaMemset(h->d_p, 0, sizeof(double) * P.n);
     if (cudaDeviceSynchronize() != cudaSuccess) return fail_create(h, DBAT_E_CUDA, "device error during create");
+    if (!g_in_group_create) h->dcopy = copy_desc(d, NC);
     *out = h;
     return DBAT_OK;
 }
 
 extern "C" void dbat_destroy(dbat_handle* h) {
     if (!h) return;
+    if (h->group) group_destroy(h);
+    if (h->dcopy) { free_desc(h->dcopy); h->dcopy = nullptr; }
     if (h->st) cudaStreamSynchronize(h->st);
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_scal) cudaFreeHost(h->h_scal);
@@ -648,6 +670,7 @@ extern "C" int64_t dbat_num_unknowns(const dbat_handle* h) { return h ? h->P.n :
 extern "C" int64_t dbat_num_residuals(const dbat_handle* h) { return h ? h->m : 0; }
 extern "C" int dbat_reduced_info(const dbat_handle* h, int64_t* info) {
     if (!h || !info) return DBAT_E_BADARG;
+    if (h->group) h = group_first(h);
     const TileSym& s = h->tc.sym;
     const int64_t v[16] = {s.nT, s.ld, s.nS, s.nSlots, s.nSlotsS, s.nTasks, s.nTerms, s.depth, s.order_mode, s.nSeg,
                            h->tc.gridFactor, h->tc.gridBwd, 0, 0, 0, 0};
@@ -905,6 +928,7 @@ __global__ void k_gradient(DevProblem P, const double* __restrict__ camG, double
 // --------------------------------------------------------------------------------------------
 extern "C" int dbat_eval(dbat_handle* h, const double* x, double* r, int weighted) {
     if (!h || !x) return DBAT_E_BADARG;
+    if (h->group) return group_eval(h, x, r, weighted);
     CK(cudaMemcpyAsync(h->d_x, x, sizeof(double) * h->P.n, cudaMemcpyHostToDevice, h->st));
     set_params(h, h->d_x);
     h->params_valid = true; h->normal_valid = false; h->cscWeighted = -1;
@@ -980,6 +1004,7 @@ static int build_csc(dbat_handle* h, int weighted) {
 }
 extern "C" int dbat_jacobian_nnz(dbat_handle* h, int weighted, int64_t* nnz) {
     if (!h || !nnz) return DBAT_E_BADARG;
+    if (h->group) { h->err = "Jacobian export of a multi-device handle is not built: export from a single-device handle"; return DBAT_E_UNSUPPORTED; }
     int rc = build_csc(h, weighted ? 1 : 0);
     if (rc) return rc;
     *nnz = (int64_t)h->cscIr.size();
@@ -987,6 +1012,7 @@ extern "C" int dbat_jacobian_nnz(dbat_handle* h, int weighted, int64_t* nnz) {
 }
 extern "C" int dbat_jacobian_csc(dbat_handle* h, int weighted, int64_t* Jc, int64_t* Ir, double* vals) {
     if (!h || !Jc || !Ir || !vals) return DBAT_E_BADARG;
+    if (h->group) { h->err = "Jacobian export of a multi-device handle is not built: export from a single-device handle"; return DBAT_E_UNSUPPORTED; }
     int rc = build_csc(h, weighted ? 1 : 0);
     if (rc) return rc;
     memcpy(Jc, h->cscJc.data(), sizeof(int64_t) * h->cscJc.size());
@@ -999,6 +1025,7 @@ extern "C" int dbat_normal_step(dbat_handle* h, const double* x, double lambda, 
                                 double* stats) {
     // flags: bit0 Jacobi scaling, bit1 also evaluate the trial point x+p, bit2 accept it when f decreases
     if (!h) return DBAT_E_BADARG;
+    if (h->group) return group_normal_step(h, x, lambda, flags, p, stats);
     ph_reset(h);
     const size_t tot = ph_begin(h);
     if (x) { CK(cudaMemcpyAsync(h->d_x, x, sizeof(double) * h->P.n, cudaMemcpyHostToDevice, h->st)); h->cscWeighted = -1; mask_unowned(h, h->d_x); }
@@ -1032,6 +1059,7 @@ extern "C" int dbat_normal_step(dbat_handle* h, const double* x, double lambda, 
 
 extern "C" int dbat_phase_times(const dbat_handle* h, const char** names, double* ms, int64_t* count, int cap) {
     if (!h) return 0;
+    if (h->group) h = group_first(h);
     int n = std::min(cap, (int)PH_N);
     for (int i = 0; i < n; ++i) { if (names) names[i] = kPhaseNames[i]; if (ms) ms[i] = h->phase_ms[i]; if (count) count[i] = h->phase_cnt[i]; }
     return n;
@@ -1436,6 +1464,7 @@ static int solve_lmp(dbat_handle* h, const dbat_opts* o, dbat_result* res, Trace
 
 extern "C" int dbat_solve(dbat_handle* h, int method, const dbat_opts* opts, const double* x0, dbat_result* res) {
     if (!h || !opts || !x0 || !res || !res->x || !res->rr || !res->damping) return DBAT_E_BADARG;
+    if (h->group) return group_solve(h, method, opts, x0, res);
     const int nn = h->P.n;
     CK(cudaMemcpyAsync(h->d_x, x0, sizeof(double) * nn, cudaMemcpyHostToDevice, h->st));
     mask_unowned(h, h->d_x);
@@ -1594,6 +1623,7 @@ __global__ void k_point_pd_check(DevProblem P, int* __restrict__ bad) {
 
 extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
     if (!h || !out) return DBAT_E_BADARG;
+    if (h->group) return group_cov(h, which, s0, out);
     // several ranks: every rank holds the whole (summed) reduced system and inverts it redundantly; CIO / CEO come out
     // identical everywhere, COP covers the points of this rank (it shards by point like the solve, bundle_cov.m:400-455)
     DevProblem& P = h->P;
@@ -1955,6 +1985,300 @@ extern "C" int dbat_tile_chol_solve(int64_t n, const double* A, const double* b,
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(st);
     if (e != cudaSuccess) { g_create_err = std::string("dbat_tile_chol_solve: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
     return info != 0 ? DBAT_E_NOTSPD : DBAT_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+// dbat_set_devices: one process, several devices (a MATLAB mexFunction has one interpreter thread,
+// code/test/postcov/icpc_mex.c:495, and cannot be launched once per GPU).  The handle becomes the front of a group:
+// the object points are cut into one range per device, every device gets its own sub-problem (created from the
+// retained copy of the description) on its own persistent host thread, the sub-problems are joined by NCCL exactly
+// like the ranks of a multi-process run, and every API call on the front handle runs on all of them and merges the
+// results (camera part from the first device, every point and observation from its owner).
+// --------------------------------------------------------------------------------------------
+struct DescCopy {
+    dbat_problem_desc d;
+    std::vector<double> IOval, EOval, OPval, IPval, IPstd, pxSize, prior_val, prior_std;
+    std::vector<int64_t> IPimg, IPop, IOs, IOd, EOs, EOd, OPs, OPd, prior_x, ca, cb;
+    void bind() {
+        d.IOval = IOval.data(); d.EOval = EOval.data(); d.OPval = OPval.data(); d.IPval = IPval.data(); d.IPstd = IPstd.data();
+        d.IPimg = IPimg.data(); d.IPop = IPop.data(); d.pxSize = pxSize.data();
+        d.IOdes_src = IOs.data(); d.IOdes_dest = IOd.data(); d.EOdes_src = EOs.data(); d.EOdes_dest = EOd.data();
+        d.OPdes_src = OPs.data(); d.OPdes_dest = OPd.data();
+        d.prior_x = prior_x.data(); d.prior_val = prior_val.data(); d.prior_std = prior_std.data();
+        d.covis_a = ca.data(); d.covis_b = cb.data(); d.nCovis = (int64_t)ca.size();
+    }
+};
+static DescCopy* copy_desc(const dbat_problem_desc* d, int NC) {
+    DescCopy* c = new DescCopy();
+    c->d = *d;
+    const size_t nImg = (size_t)d->nImg, nOP = (size_t)d->nOP, nIP = (size_t)d->nIP;
+    const size_t nPr = (size_t)(d->nPriorIO + d->nPriorEO + d->nPriorOP);
+    c->IOval.assign(d->IOval, d->IOval + (size_t)NC * nImg); c->EOval.assign(d->EOval, d->EOval + 6 * nImg);
+    c->OPval.assign(d->OPval, d->OPval + 3 * nOP); c->IPval.assign(d->IPval, d->IPval + 2 * nIP);
+    c->IPstd.assign(d->IPstd, d->IPstd + 2 * nIP); c->pxSize.assign(d->pxSize, d->pxSize + 2 * nImg);
+    c->IPimg.assign(d->IPimg, d->IPimg + nIP); c->IPop.assign(d->IPop, d->IPop + nIP);
+    c->IOs.assign(d->IOdes_src, d->IOdes_src + d->nIOdes); c->IOd.assign(d->IOdes_dest, d->IOdes_dest + d->nIOdes);
+    c->EOs.assign(d->EOdes_src, d->EOdes_src + d->nEOdes); c->EOd.assign(d->EOdes_dest, d->EOdes_dest + d->nEOdes);
+    c->OPs.assign(d->OPdes_src, d->OPdes_src + d->nOPdes); c->OPd.assign(d->OPdes_dest, d->OPdes_dest + d->nOPdes);
+    if (nPr) { c->prior_x.assign(d->prior_x, d->prior_x + nPr); c->prior_val.assign(d->prior_val, d->prior_val + nPr); c->prior_std.assign(d->prior_std, d->prior_std + nPr); }
+    if (d->nCovis > 0 && d->covis_a && d->covis_b) { c->ca.assign(d->covis_a, d->covis_a + d->nCovis); c->cb.assign(d->covis_b, d->covis_b + d->nCovis); }
+    c->bind();
+    return c;
+}
+static void free_desc(DescCopy* c) { delete c; }
+
+struct GroupWorker {
+    std::thread th; std::mutex m; std::condition_variable cv;
+    std::function<void()> job; bool has = false, quit = false;
+};
+struct DevGroup {
+    int ndev = 0;
+    std::vector<int> dev;
+    std::vector<dbat_handle*> sub;
+    std::vector<std::unique_ptr<GroupWorker>> w;
+    std::vector<int> lo, hi;                         // object-point range of every device
+    std::vector<std::vector<int64_t>> obs;           // per device: global observation index of its observations
+    std::vector<std::vector<int64_t>> prow;          // per device: global prior-row index of its prior rows
+    std::vector<std::vector<int64_t>> ownCols;       // per device: x columns of its object points (0-based)
+    std::vector<std::unique_ptr<DescCopy>> sd;
+    int nC = 0;
+    void run_all(const std::function<void(int)>& fn) {
+        std::mutex dm; std::condition_variable dcv; int left = ndev;
+        for (int r = 0; r < ndev; ++r) {
+            GroupWorker& k = *w[r];
+            std::lock_guard<std::mutex> g(k.m);
+            k.job = [&, r]() { fn(r); { std::lock_guard<std::mutex> g2(dm); --left; } dcv.notify_one(); };
+            k.has = true;
+            k.cv.notify_one();
+        }
+        std::unique_lock<std::mutex> lk(dm);
+        dcv.wait(lk, [&] { return left == 0; });
+    }
+};
+static void worker_loop(GroupWorker* k, int device) {
+    cudaSetDevice(device);
+    for (;;) {
+        std::function<void()> job;
+        {
+            std::unique_lock<std::mutex> lk(k->m);
+            k->cv.wait(lk, [&] { return k->has || k->quit; });
+            if (k->quit && !k->has) return;
+            job.swap(k->job); k->has = false;
+        }
+        job();
+    }
+}
+static const dbat_handle* group_first(const dbat_handle* h) { return h->group->sub[0]; }
+static void group_destroy(dbat_handle* h) {
+    DevGroup* G = h->group;
+    G->run_all([&](int r) { if (G->sub[r]) { dbat_destroy(G->sub[r]); G->sub[r] = nullptr; } });
+    for (auto& k : G->w) { { std::lock_guard<std::mutex> g(k->m); k->quit = true; } k->cv.notify_one(); k->th.join(); }
+    delete G;
+    h->group = nullptr;
+}
+
+extern "C" int dbat_set_devices(dbat_handle* h, const int* dev, int ndev) {
+    if (!h || !dev || ndev < 1) return DBAT_E_BADARG;
+    if (h->group) { h->err = "dbat_set_devices was already called on this handle"; return DBAT_E_STATE; }
+    if (h->nranks > 1) { h->err = "the handle is a rank of a multi-process run"; return DBAT_E_STATE; }
+    if (!h->dcopy) { h->err = "no description retained"; return DBAT_E_STATE; }
+    int have = 0;
+    cudaGetDeviceCount(&have);
+    for (int r = 0; r < ndev; ++r) if (dev[r] < 0 || dev[r] >= have) { h->err = "device index out of range"; return DBAT_E_BADARG; }
+    const dbat_problem_desc& D = h->dcopy->d;
+    const int nOP = (int)D.nOP, nImg = (int)D.nImg, nObs = (int)D.nIP;
+    DevGroup* G = new DevGroup();
+    G->ndev = ndev; G->dev.assign(dev, dev + ndev); G->sub.assign(ndev, nullptr); G->nC = h->P.nC;
+    // contiguous point ranges balanced by observation count (parallel.py:partition_points)
+    {
+        std::vector<int64_t> cum((size_t)nOP + 1, 0);
+        for (int k = 0; k < nObs; ++k) cum[(size_t)D.IPop[k]]++;
+        for (int j = 0; j < nOP; ++j) cum[(size_t)j + 1] += cum[(size_t)j];
+        G->lo.assign(ndev, 0); G->hi.assign(ndev, nOP);
+        for (int r = 1; r < ndev; ++r) {
+            const int64_t target = cum[(size_t)nOP] * r / ndev;
+            int b = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+            b = std::max(G->lo[r - 1], std::min(b, nOP));
+            G->lo[r] = b; G->hi[r - 1] = b;
+        }
+    }
+    // global co-visibility edges (the front handle analysed the whole project at create)
+    std::vector<int64_t> ea, eb;
+    for (int i = 0; i < nImg; ++i)
+        for (int64_t k = h->h_adjPtr[i]; k < h->h_adjPtr[i + 1]; ++k) if (h->h_adj[k] > i) { ea.push_back(i + 1); eb.push_back(h->h_adj[k] + 1); }
+    G->obs.resize(ndev); G->prow.resize(ndev); G->ownCols.resize(ndev); G->sd.resize(ndev);
+    const int64_t nPr = D.nPriorIO + D.nPriorEO + D.nPriorOP;
+    for (int r = 0; r < ndev; ++r) {
+        const int lo = G->lo[r], hi = G->hi[r];
+        std::unique_ptr<DescCopy> c(new DescCopy());
+        const DescCopy& A = *h->dcopy;
+        c->d = A.d;
+        c->IOval = A.IOval; c->EOval = A.EOval; c->pxSize = A.pxSize;
+        c->IOs = A.IOs; c->IOd = A.IOd; c->EOs = A.EOs; c->EOd = A.EOd;
+        c->OPval.assign(A.OPval.begin() + 3 * (size_t)lo, A.OPval.begin() + 3 * (size_t)hi);
+        for (int k = 0; k < nObs; ++k) {
+            const int64_t j = A.IPop[k] - 1;
+            if (j < lo || j >= hi) continue;
+            G->obs[r].push_back(k);
+            c->IPimg.push_back(A.IPimg[k]); c->IPop.push_back(j - lo + 1);
+            c->IPval.push_back(A.IPval[2 * (size_t)k]); c->IPval.push_back(A.IPval[2 * (size_t)k + 1]);
+            c->IPstd.push_back(A.IPstd[2 * (size_t)k]); c->IPstd.push_back(A.IPstd[2 * (size_t)k + 1]);
+        }
+        std::vector<char> own((size_t)D.n, 0);
+        for (int64_t k = 0; k < D.nOPdes; ++k) {
+            const int64_t dd = A.OPd[k] - 1;
+            if (dd < 3 * (int64_t)lo || dd >= 3 * (int64_t)hi) continue;
+            c->OPs.push_back(A.OPs[k]); c->OPd.push_back(dd - 3 * (int64_t)lo + 1);
+            own[(size_t)(A.OPs[k] - 1)] = 1; G->ownCols[r].push_back(A.OPs[k] - 1);
+        }
+        int64_t nIO = 0, nEO = 0, nOPp = 0;
+        for (int64_t q = 0; q < nPr; ++q) {
+            const bool isCam = q < D.nPriorIO + D.nPriorEO;
+            if (isCam ? (r != 0) : !own[(size_t)(A.prior_x[q] - 1)]) continue;
+            c->prior_x.push_back(A.prior_x[q]); c->prior_val.push_back(A.prior_val[q]); c->prior_std.push_back(A.prior_std[q]);
+            G->prow[r].push_back(q);
+            if (q < D.nPriorIO) ++nIO; else if (isCam) ++nEO; else ++nOPp;
+        }
+        c->ca = ea; c->cb = eb;
+        c->d.nOP = hi - lo; c->d.nIP = (int64_t)G->obs[r].size();
+        c->d.nOPdes = (int64_t)c->OPs.size();
+        c->d.nPriorIO = nIO; c->d.nPriorEO = nEO; c->d.nPriorOP = nOPp;
+        c->bind();
+        G->sd[r] = std::move(c);
+    }
+    for (int r = 0; r < ndev; ++r) {
+        G->w.emplace_back(new GroupWorker());
+        G->w[r]->th = std::thread(worker_loop, G->w[r].get(), dev[r]);
+    }
+    std::vector<int> rcs(ndev, 0);
+    std::vector<std::string> errs(ndev);
+    G->run_all([&](int r) {
+        g_in_group_create = true;
+        rcs[r] = dbat_create(&G->sd[r]->d, &G->sub[r]);
+        g_in_group_create = false;
+        if (rcs[r]) errs[r] = g_create_err;
+    });
+    int rc = 0;
+    for (int r = 0; r < ndev; ++r) if (rcs[r]) { rc = rcs[r]; h->err = "device " + std::to_string(dev[r]) + ": " + errs[r]; }
+    if (!rc && ndev > 1) {
+        char uid[128];
+        rc = dbat_comm_unique_id(uid);
+        if (rc) h->err = "ncclGetUniqueId failed";
+        if (!rc) {
+            G->run_all([&](int r) { rcs[r] = dbat_comm_init(G->sub[r], ndev, r, uid); if (rcs[r]) errs[r] = G->sub[r]->err; });
+            for (int r = 0; r < ndev; ++r) if (rcs[r]) { rc = rcs[r]; h->err = "device " + std::to_string(dev[r]) + ": " + errs[r]; }
+        }
+    }
+    h->group = G;
+    if (rc) { group_destroy(h); return rc; }
+    for (auto& c : G->sd) c.reset();                  // the sub-problems hold their own copies now
+    return DBAT_OK;
+}
+
+static int group_rc(dbat_handle* h, const std::vector<int>& rcs) {
+    DevGroup* G = h->group;
+    for (int r = 0; r < G->ndev; ++r)
+        if (rcs[r]) { h->err = "device " + std::to_string(G->dev[r]) + ": " + G->sub[r]->err; return rcs[r]; }
+    return DBAT_OK;
+}
+static void group_merge_x(DevGroup* G, int n, const std::vector<std::vector<double>>& part, double* out) {
+    // camera part from the first device, every point column from its owner; columns nobody owns (none) keep part[0]
+    memcpy(out, part[0].data(), sizeof(double) * (size_t)n);
+    for (int r = 1; r < G->ndev; ++r) for (int64_t c : G->ownCols[r]) out[c] = part[r][(size_t)c];
+}
+static void group_merge_r(dbat_handle* h, const std::vector<std::vector<double>>& part, double* out) {
+    DevGroup* G = h->group;
+    const int64_t nObs = h->P.nObs;
+    for (int r = 0; r < G->ndev; ++r) {
+        const std::vector<int64_t>& ob = G->obs[r];
+        for (size_t k = 0; k < ob.size(); ++k) { out[2 * ob[k]] = part[r][2 * k]; out[2 * ob[k] + 1] = part[r][2 * k + 1]; }
+        for (size_t q = 0; q < G->prow[r].size(); ++q) out[2 * nObs + G->prow[r][q]] = part[r][2 * ob.size() + q];
+    }
+}
+static int group_eval(dbat_handle* h, const double* x, double* r, int weighted) {
+    DevGroup* G = h->group;
+    std::vector<int> rcs(G->ndev, 0);
+    std::vector<std::vector<double>> part(G->ndev);
+    G->run_all([&](int k) {
+        part[k].resize((size_t)std::max<int64_t>(1, dbat_num_residuals(G->sub[k])));
+        rcs[k] = dbat_eval(G->sub[k], x, r ? part[k].data() : nullptr, weighted);
+    });
+    int rc = group_rc(h, rcs);
+    if (!rc && r) group_merge_r(h, part, r);
+    return rc;
+}
+static int group_normal_step(dbat_handle* h, const double* x, double lambda, int flags, double* p, double* stats) {
+    DevGroup* G = h->group;
+    const int n = h->P.n;
+    std::vector<int> rcs(G->ndev, 0);
+    std::vector<std::vector<double>> part(G->ndev), st(G->ndev, std::vector<double>(8, 0.0));
+    G->run_all([&](int k) {
+        if (p) part[k].assign((size_t)n, 0.0);
+        rcs[k] = dbat_normal_step(G->sub[k], x, lambda, flags, p ? part[k].data() : nullptr, st[k].data());
+    });
+    int rc = group_rc(h, rcs);
+    if (rc) return rc;
+    if (p) group_merge_x(G, n, part, p);
+    if (stats) { memcpy(stats, st[0].data(), sizeof(double) * 8); for (int k = 1; k < G->ndev; ++k) stats[6] = std::max(stats[6], st[k][6]); }
+    return DBAT_OK;
+}
+static int group_solve(dbat_handle* h, int method, const dbat_opts* opts, const double* x0, dbat_result* res) {
+    DevGroup* G = h->group;
+    const int n = h->P.n, cap = opts->maxIter + 2;
+    struct Buf { std::vector<double> x, p, rw, ru, tr, rr, dmp, rho; std::vector<int32_t> steps; dbat_result r; };
+    std::vector<Buf> B(G->ndev);
+    std::vector<int> rcs(G->ndev, 0);
+    G->run_all([&](int k) {
+        Buf& b = B[k];
+        const size_t mk = (size_t)std::max<int64_t>(1, dbat_num_residuals(G->sub[k]));
+        b.x.assign(n, 0.0); b.p.assign(n, 0.0); b.rr.assign(cap + 1, NAN); b.dmp.assign(cap + 1, NAN); b.rho.assign(cap, NAN); b.steps.assign(cap, 0);
+        memset(&b.r, 0, sizeof(b.r));
+        b.r.x = b.x.data(); b.r.p = res->p ? b.p.data() : nullptr;
+        if (res->r_w) { b.rw.assign(mk, 0.0); b.r.r_w = b.rw.data(); }
+        if (res->r_u) { b.ru.assign(mk, 0.0); b.r.r_u = b.ru.data(); }
+        if (res->trace) { b.tr.assign((size_t)n * cap, NAN); b.r.trace = b.tr.data(); }
+        b.r.rr = b.rr.data(); b.r.damping = b.dmp.data(); b.r.rhos = res->rhos ? b.rho.data() : nullptr; b.r.steps = res->steps ? b.steps.data() : nullptr;
+        rcs[k] = dbat_solve(G->sub[k], method, opts, x0, &b.r);
+    });
+    int rc = group_rc(h, rcs);
+    if (rc) return rc;
+    const dbat_result& r0 = B[0].r;
+    res->code = r0.code; res->iters = r0.iters; res->nTrace = r0.nTrace; res->nRr = r0.nRr; res->nDamping = r0.nDamping; res->nRhos = r0.nRhos;
+    res->seconds = r0.seconds; res->launches = r0.launches;
+    memcpy(res->rr, B[0].rr.data(), sizeof(double) * (cap + 1));
+    memcpy(res->damping, B[0].dmp.data(), sizeof(double) * (cap + 1));
+    if (res->rhos) memcpy(res->rhos, B[0].rho.data(), sizeof(double) * cap);
+    if (res->steps) memcpy(res->steps, B[0].steps.data(), sizeof(int32_t) * cap);
+    std::vector<std::vector<double>> part(G->ndev);
+    for (int k = 0; k < G->ndev; ++k) part[k].swap(B[k].x);
+    group_merge_x(G, n, part, res->x);
+    if (res->p) { for (int k = 0; k < G->ndev; ++k) part[k].swap(B[k].p); group_merge_x(G, n, part, res->p); }
+    if (res->r_w) { for (int k = 0; k < G->ndev; ++k) part[k].swap(B[k].rw); group_merge_r(h, part, res->r_w); }
+    if (res->r_u) { for (int k = 0; k < G->ndev; ++k) part[k].swap(B[k].ru); group_merge_r(h, part, res->r_u); }
+    if (res->trace)
+        for (int c = 0; c < std::min(res->nTrace, cap); ++c) {
+            memcpy(res->trace + (size_t)c * n, B[0].tr.data() + (size_t)c * n, sizeof(double) * (size_t)n);
+            for (int k = 1; k < G->ndev; ++k) for (int64_t col : G->ownCols[k]) res->trace[(size_t)c * n + col] = B[k].tr[(size_t)c * n + col];
+        }
+    return DBAT_OK;
+}
+static int group_cov(dbat_handle* h, int which, double s0, double* out) {
+    DevGroup* G = h->group;
+    if (which == DBAT_COV_CXX || which == DBAT_COV_CXX_OP) { h->err = "the dense point covariance is single-device only; use COP"; return DBAT_E_UNSUPPORTED; }
+    std::vector<int> rcs(G->ndev, 0);
+    std::vector<std::vector<double>> part(G->ndev);
+    const size_t camSize = which == DBAT_COV_CIO ? (size_t)h->NC * h->NC * h->P.nImg : which == DBAT_COV_CEO ? (size_t)36 * h->P.nImg : (size_t)G->nC * G->nC;
+    G->run_all([&](int k) {
+        part[k].assign(which == DBAT_COV_COP ? (size_t)9 * std::max(1, G->hi[k] - G->lo[k]) : std::max<size_t>(1, camSize), 0.0);
+        rcs[k] = dbat_cov(G->sub[k], which, s0, part[k].data());
+    });
+    bool notspd = false;
+    for (int k = 0; k < G->ndev; ++k) if (rcs[k] == DBAT_E_NOTSPD) { notspd = true; rcs[k] = 0; }
+    int rc = group_rc(h, rcs);
+    if (rc) return rc;
+    if (which == DBAT_COV_COP) { for (int k = 0; k < G->ndev; ++k) memcpy(out + 9 * (size_t)G->lo[k], part[k].data(), sizeof(double) * 9 * (size_t)(G->hi[k] - G->lo[k])); }
+    else memcpy(out, part[0].data(), sizeof(double) * camSize);
+    return notspd ? DBAT_E_NOTSPD : DBAT_OK;
 }
 
 // --------------------------------------------------------------------------------------------

@@ -158,7 +158,7 @@ struct GemmCfg {
     static constexpr int smem = STAGES * KS * (BM + 4 + BN + 4) * 8;
     static void launch(dim3 grid, cudaStream_t st, const double* A, int lda, const double* B, int ldb,
                        double* C, int ldc, int K, double alpha, double beta, int tri) {
-        static bool done = false;
+        static thread_local bool done = false;       // per thread = per device (one host thread drives one device)
         if (!done) {
             cudaFuncSetAttribute(k_gemm_nt<BM, BN, WTM, WTN, STAGES, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             done = true;
@@ -609,14 +609,14 @@ void chol_free(CholWork& w) {
     w = CholWork();
 }
 
-static cudaStream_t g_aux = nullptr;
-static cudaEvent_t g_evA = nullptr, g_evB = nullptr;
+static thread_local cudaStream_t g_aux = nullptr;
+static thread_local cudaEvent_t g_evA = nullptr, g_evB = nullptr;
 
 // Right-looking blocked Cholesky with one step of look-ahead: as soon as block column k+1 has
 // received the update of step k, its potrf + panel solve run on a second stream while the main
 // stream finishes the rest of the trailing update of step k.
 static void chol_factor_body(CholWork& w, double* A, cudaStream_t st) {
-    static bool attr = false;
+    static thread_local bool attr = false;
     const int psmem = POTRF_SMEM_DOUBLES * 8;
     if (!attr) {
         cudaFuncSetAttribute(k_potrf128, cudaFuncAttributeMaxDynamicSharedMemorySize, psmem);
@@ -879,10 +879,10 @@ __global__ void __launch_bounds__(256, 1) k_bwd_pipe(const double* __restrict__ 
     if (t == 0) atomicExch(&flags[j], 1);
 }
 
-static double* g_solve_tmp = nullptr;
-static int* g_solve_flags = nullptr;
-static int g_solve_tmp_n = 0;
-static int g_coop_max = -1;
+static thread_local double* g_solve_tmp = nullptr;
+static thread_local int* g_solve_flags = nullptr;
+static thread_local int g_solve_tmp_n = 0;
+static thread_local int g_coop_max = -1;
 // After chol_factor on a matrix prepared with chol_put_rhs: x (length ld) = A^-1 rhs.
 void chol_solve(const CholWork& w, const double* A, double* x, cudaStream_t st) {
     if (g_solve_tmp_n < w.ld) {
@@ -902,7 +902,7 @@ void chol_solve(const CholWork& w, const double* A, double* x, cudaStream_t st) 
     double* y = g_solve_tmp;
     k_get_y_row<<<(w.ld + 255) / 256, 256, 0, st>>>(A, w.ld, y, w.n);
     count_launch();
-    static int pipe_ok = -1;
+    static thread_local int pipe_ok = -1;
     const int pipe_smem = (3 * BWD_BUF + 4 * NB) * 8;
     if (pipe_ok < 0) {
         const char* e = getenv("DBAT_BWD");

@@ -238,7 +238,7 @@ template <int MODEL>
 static void launch_cam_side_t(const DevProblem& P, const int* img_chunk_start, double* tmp,
                               cudaStream_t st) {
     const size_t smem = (size_t)4 * DBAT_GW * XT_LD * sizeof(double);
-    static bool attr_done = false;
+    static thread_local bool attr_done = false;      // cudaFuncSetAttribute is per device; one host thread drives one device
     if (!attr_done) {
         cudaFuncSetAttribute(k_cam_side<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;

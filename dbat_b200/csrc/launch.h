@@ -7,7 +7,7 @@ struct DevProblem;
 
 // every kernel launch of the library is counted (reported as gpu_launches by bench.py)
 extern int64_t g_dbat_launches;
-static inline void count_launch(int n = 1) { g_dbat_launches += n; }
+static inline void count_launch(int n = 1) { __atomic_fetch_add(&g_dbat_launches, (int64_t)n, __ATOMIC_RELAXED); }
 
 // eval.cu
 void launch_deserialize(const double* x, const int* src, const int* dest, double* arr, int cnt, cudaStream_t st);

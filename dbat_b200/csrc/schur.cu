@@ -662,7 +662,7 @@ void launch_point_vinv(const DevProblem& P, double lambda, cudaStream_t st) {
     if (P.nOP > 0) { k_point_vinv<<<(P.nOP + 255) / 256, 256, 0, st>>>(P, lambda); count_launch(); }
 }
 static int g_schur_mode = -1;       // 0 = grouped atomic (default), 1 = deterministic, 2 = per-point atomic
-static double* g_shAcc = nullptr;
+static thread_local double* g_shAcc = nullptr;       // per device (one host thread drives one device)
 void launch_schur(const DevProblem& P, double lambda, cudaStream_t st) {
     if (P.nOP <= 0) return;
     if (P.ioGeneral) { launch_schur_gen(P, lambda, st); return; }
@@ -681,7 +681,7 @@ void launch_schur(const DevProblem& P, double lambda, cudaStream_t st) {
         } else {
             k_point_vinv<<<(P.nOP + 255) / 256, 256, 0, st>>>(P, lambda);
             if (P.nGrp > 0) {
-                static bool attr = false;
+                static thread_local bool attr = false;
                 auto smem_for = [](int mm) { return (2 * ((6 * mm + 7) & ~7) + 32) * GRP_LDK * 8; };
                 if (!attr) { cudaFuncSetAttribute(k_schur_group, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(DBAT_GRP_MAXM)); attr = true; }
                 k_schur_group<<<std::min(P.nGrp, 148 * 24), GRP_TH, smem_for(P.grpMaxRays), st>>>(P, g_shAcc);

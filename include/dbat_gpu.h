@@ -205,6 +205,14 @@ int dbat_tile_chol_solve(int64_t n, const double *A, const double *b, double *x,
 int dbat_dense_chol_solve(int64_t n, const double *A, const double *b, double *x, double *Ainv,
                           int repeat, double *ms_out);
 
+/* One process, several devices (a MEX gateway has one interpreter thread): after dbat_create and before
+ * the first evaluation, turn the handle into the front of `ndev` sub-problems, one per listed CUDA device.  The object
+ * points are cut into one range per device, the sub-problems are joined by NCCL, and every later call on the handle
+ * (dbat_eval, dbat_normal_step, dbat_solve, dbat_cov blocks, dbat_phase_times) runs on all of them and merges the
+ * results; x, p and residuals keep the single-device layout.  Not available on a multi-device handle: the Jacobian
+ * export and the dense point covariances (CXX / CXX_OP).  ndev = 1 moves the problem to dev[0]. */
+int dbat_set_devices(dbat_handle *h, const int *dev, int ndev);
+
 /* Multi-GPU: one process per GPU.  unique_id = the 128 bytes of ncclGetUniqueId from
  * rank 0 (dbat_comm_unique_id), distributed by the host plumbing (torch.distributed). */
 int dbat_comm_unique_id(void *id128);
