@@ -643,6 +643,151 @@ __global__ void __launch_bounds__(GRP_TH, 3) k_schur_group(DevProblem P, double*
         }
     }
 }
+// ---------------------------------------------------------------------------------------------
+// k_schur_group2: the same contraction with a third fewer instructions (the first version issued 20 k warp
+// instructions per group, most of them index arithmetic).
+//   * staging by (point, observation, block row): warp w takes points w, w + 8; a lane reads the 3 consecutive
+//     doubles of one row of a cross block (consecutive lanes -> consecutive 24-byte pieces: coalesced), applies
+//     (V + lambda I)^-1 at once and stores BOTH the What and the Yhat entry - no second pass, one barrier less;
+//     all divisions are by constants;
+//   * the list of lower-triangular tile pairs is a table in shared memory, built once per CTA;
+//   * What / Yhat are cleared with 16-byte stores at the top of every group.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GRP_TH, 3) k_schur_group2(DevProblem P, double* __restrict__ shAcc) {
+    extern __shared__ __align__(16) double dsm[];
+    __shared__ GrpHeader s_hdr[2];
+    __shared__ unsigned char s_tij[2 * 153];              // (ti, tj) of the tile pairs, RT <= 17
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int RWmax = (6 * P.grpMaxRays + 7) & ~7;
+    double* What = dsm;
+    double* Yhat = What + RWmax * GRP_LDK;
+    double* Wsh = Yhat + (RWmax + 16) * GRP_LDK;
+    for (int i = t; i < (2 * RWmax + 32) * GRP_LDK; i += GRP_TH) dsm[i] = 0.0;
+    for (int u = t; u < 153; u += GRP_TH) {
+        int i = (int)((sqrtf(8.0f * u + 1.0f) - 1.0f) * 0.5f);
+        while ((i + 1) * (i + 2) / 2 <= u) ++i;
+        while (i * (i + 1) / 2 > u) --i;
+        s_tij[2 * u] = (unsigned char)i; s_tij[2 * u + 1] = (unsigned char)(u - i * (i + 1) / 2);
+    }
+    double accSh[2] = {0.0, 0.0};
+    int buf = 0;
+    {
+        GrpPrefetch f;
+        grp_prefetch(P, blockIdx.x, t, f);
+        grp_store(s_hdr[0], t, f);
+    }
+    __syncthreads();
+    for (int grp = blockIdx.x; grp < P.nGrp; grp += gridDim.x, buf ^= 1) {
+        GrpHeader& H = s_hdr[buf];
+        GrpPrefetch nxt;
+        grp_prefetch(P, grp + gridDim.x, t, nxt);
+        const int m = H.m, ng = H.ng;
+        const int R = 6 * m, RT = (R + 7) >> 3;
+        const int K = 3 * ng, Kp = (K + 3) & ~3;
+        // ---- stage What and Yhat = What V^-1, Wsh and Ysh: warp w owns points w, w + 8
+        for (int gi = warp; gi < ng; gi += GRP_TH / 32) {
+            const double* sv = H.vi + 6 * gi;
+            const double v0 = sv[0], v1 = sv[1], v2 = sv[2], v3 = sv[3], v4 = sv[4], v5 = sv[5];
+            const int ob0 = H.ob[gi], nIt = 6 * H.nob[gi];
+            for (int it = lane; it < nIt; it += 32) {
+                const int o = it / 6, a = it - 6 * o;
+                const double* w = P.W + (size_t)(ob0 + o) * DBAT_W_STRIDE + 3 * a;
+                const double w0 = w[0], w1 = w[1], w2 = w[2];
+                const int row = 6 * P.obs_slot[ob0 + o] + a;
+                double* pw = What + row * GRP_LDK + 3 * gi;
+                double* py = Yhat + row * GRP_LDK + 3 * gi;
+                pw[0] = w0; pw[1] = w1; pw[2] = w2;
+                py[0] = v0 * w0 + v1 * w1 + v2 * w2; py[1] = v1 * w0 + v3 * w1 + v4 * w2; py[2] = v2 * w0 + v4 * w1 + v5 * w2;
+            }
+            if (lane < 15) {                                  // 14 shared IO slots and the gradient
+                const double* rec = P.pt + (size_t)H.j[gi] * DBAT_PT_STRIDE;
+                const double* w = lane < DBAT_NSLOT ? rec + DBAT_PT_WSH + 3 * lane : rec + 6;
+                const double w0 = w[0], w1 = w[1], w2 = w[2];
+                double* pw = Wsh + lane * GRP_LDK + 3 * gi;
+                double* py = Yhat + (RWmax + lane) * GRP_LDK + 3 * gi;
+                pw[0] = w0; pw[1] = w1; pw[2] = w2;
+                py[0] = v0 * w0 + v1 * w1 + v2 * w2; py[1] = v1 * w0 + v3 * w1 + v4 * w2; py[2] = v2 * w0 + v4 * w1 + v5 * w2;
+            }
+        }
+        grp_store(s_hdr[buf ^ 1], t, nxt);
+        __syncthreads();
+        // ---- tiles: pair tiles (ti >= tj) of Yhat What', then RT x 2 tiles of Yhat Wsh'
+        const int nPair = RT * (RT + 1) / 2, nTile = nPair + 2 * RT;
+        for (int tile = warp; tile < nTile; tile += GRP_TH / 32) {
+            int ti, tj; const double* Bm;
+            if (tile < nPair) { ti = s_tij[2 * tile]; tj = s_tij[2 * tile + 1]; Bm = What; }
+            else { ti = (tile - nPair) >> 1; tj = (tile - nPair) & 1; Bm = Wsh; }
+            const double* pa = Yhat + (8 * ti + fr) * GRP_LDK + fk;
+            const double* pb = Bm + (8 * tj + fr) * GRP_LDK + fk;
+            double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+            for (int k0 = 0; k0 < Kp; k0 += 8) {
+                dmma_s(c0, c1, pa[k0], pb[k0]);
+                if (k0 + 4 < Kp) dmma_s(d0, d1, pa[k0 + 4], pb[k0 + 4]);
+            }
+            c0 += d0; c1 += d1;
+            const int r = 8 * ti + fr;
+            if (r < R) {
+                const int row = H.eoc[r];
+                if (row >= 0) {
+                    if (tile < nPair) {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int c = 8 * tj + 2 * fk + e;
+                            const double v = e ? c1 : c0;
+                            if (c < R && v != 0.0) {
+                                const int col = H.eoc[c];
+                                if (col >= 0 && col <= row) atomicAdd(tc_at(P.T, row, col), -v);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int sidx = 8 * tj + 2 * fk + e;
+                            if (sidx < DBAT_NSLOT) {
+                                const int srow = P.sh_s[sidx];
+                                if (srow >= 0) atomicAdd(tc_at(P.T, srow, row), -(e ? c1 : c0));
+                            } else if (sidx == DBAT_NSLOT) {
+                                atomicAdd(&P.rhs[row], e ? c1 : c0);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (warp < 4) {
+            const int ta = warp >> 1, tb = warp & 1;
+            const double* pa = Yhat + (RWmax + 8 * ta + fr) * GRP_LDK + fk;
+            const double* pb = Wsh + (8 * tb + fr) * GRP_LDK + fk;
+            for (int k0 = 0; k0 < Kp; k0 += 4) dmma_s(accSh[0], accSh[1], pa[k0], pb[k0]);
+        }
+        __syncthreads();
+        // ---- clear what this group wrote (rows of images a point does not see must read as zero): lane = 16-byte
+        //      piece of a row (Kp <= 48: at most 24 pieces), warps stride the rows of What, Yhat, Ysh, Wsh
+        if (lane < (Kp >> 1)) {
+            const int nA = 8 * RT;
+            for (int row = warp; row < 2 * nA + 32; row += GRP_TH / 32) {
+                double* base = row < nA ? What + row * GRP_LDK
+                             : row < 2 * nA ? Yhat + (row - nA) * GRP_LDK
+                             : row < 2 * nA + 16 ? Yhat + (RWmax + row - 2 * nA) * GRP_LDK
+                             : Wsh + (row - 2 * nA - 16) * GRP_LDK;
+                *reinterpret_cast<double2*>(base + 2 * lane) = make_double2(0.0, 0.0);
+            }
+        }
+        __syncthreads();
+    }
+    if (warp < 4) {
+        const int a = 8 * (warp >> 1) + fr;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int b = 8 * (warp & 1) + 2 * fk + e;
+            if (a < DBAT_NSLOT && (b == DBAT_NSLOT || b <= a) && b <= DBAT_NSLOT) {
+                const double v = e ? accSh[1] : accSh[0];
+                if (v != 0.0) atomicAdd(&shAcc[a * (DBAT_NSLOT + 1) + b], v);
+            }
+        }
+    }
+}
 __global__ void k_schur_sh_apply(DevProblem P, const double* __restrict__ shAcc) {
     for (int e = threadIdx.x; e < DBAT_NSLOT * (DBAT_NSLOT + 1); e += blockDim.x) {
         const int a = e / (DBAT_NSLOT + 1), b = e % (DBAT_NSLOT + 1);
@@ -683,8 +828,14 @@ void launch_schur(const DevProblem& P, double lambda, cudaStream_t st) {
             if (P.nGrp > 0) {
                 static thread_local bool attr = false;
                 auto smem_for = [](int mm) { return (2 * ((6 * mm + 7) & ~7) + 32) * GRP_LDK * 8; };
-                if (!attr) { cudaFuncSetAttribute(k_schur_group, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(DBAT_GRP_MAXM)); attr = true; }
-                k_schur_group<<<std::min(P.nGrp, 148 * 24), GRP_TH, smem_for(P.grpMaxRays), st>>>(P, g_shAcc);
+                if (!attr) {
+                    cudaFuncSetAttribute(k_schur_group, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(DBAT_GRP_MAXM));
+                    cudaFuncSetAttribute(k_schur_group2, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_for(DBAT_GRP_MAXM));
+                    attr = true;
+                }
+                static const bool v1 = getenv("DBAT_SCHUR_GROUP_V1") != nullptr;
+                if (v1) k_schur_group<<<std::min(P.nGrp, 148 * 24), GRP_TH, smem_for(P.grpMaxRays), st>>>(P, g_shAcc);
+                else k_schur_group2<<<std::min(P.nGrp, 148 * 24), GRP_TH, smem_for(P.grpMaxRays), st>>>(P, g_shAcc);
                 count_launch();
             }
             if (P.nBig > 0) {
