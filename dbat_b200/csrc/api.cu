@@ -583,7 +583,7 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
         // greedy groups of consecutive points: at most gcap points, union of their image lists at most
         // `mu` images (a single point always fits).  A point that lacks an image of the union simply
         // has zero rows there.
-        const int gcap = std::max(1, std::min(16, (int)(cand.size() / (148 * 8))));   // <= GRP_CAP of schur.cu
+        const int gcap = std::max(1, std::min(WIN_GP, (int)(cand.size() / (148 * 8))));   // <= WIN_GP (and GRP_CAP of schur.cu)
         int mu = 12;
         if (const char* e = getenv("DBAT_GRP_MU")) mu = std::max(1, std::min(DBAT_GRP_MAXM, atoi(e)));
         std::vector<int> gstart, gimg_off, gimg, uni, tmp;
@@ -627,6 +627,105 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
         UP(d_gp, cand); UP(d_gs, gstart); UP(d_big, big);
         P.grp_pt = d_gp; P.grp_start = d_gs; P.big_pt = d_big;
         AL(P.vinv, (size_t)std::max(1, nOP) * 8);
+        // ---- window Schur (schur_win.cu): group headers, clusters of consecutive groups whose unions span at most
+        //      WIN_MAXW images, and the fixed-order reduction index of the cluster images
+        P.nCand = noCand ? 0 : (int)cand.size();
+        const int nGrp = P.nGrp;
+        std::vector<WinHdr> hdr((size_t)std::max(1, nGrp));
+        std::vector<int> clu_grp(1, 0), clu_img_off(1, 0), clu_img;
+        std::vector<long long> clu_stg(1, 0);
+        struct Contrib { long long key, off; };
+        std::vector<Contrib> contrib;
+        std::vector<std::pair<int, long long>> icontrib;         // (image, staging offset of its shared rows)
+        const std::vector<int>& imgOrder = h->tc.sym.imgOrder;
+        for (int g = 0; g < nGrp; ++g) {
+            WinHdr& H = hdr[g];
+            memset(&H, 0, sizeof(H));
+            memset(H.obsOf, 255, sizeof(H.obsOf));
+            H.m = gimg_off[g + 1] - gimg_off[g];
+            H.ng = gstart[g + 1] - gstart[g];
+            H.p0 = gstart[g];
+            for (int gi = 0; gi < H.ng; ++gi) {
+                const int j = cand[gstart[g] + gi];
+                H.j[gi] = j; H.ob[gi] = ps[j];
+                for (int o = ps[j]; o < ps[j + 1]; ++o) H.obsOf[gi][slot[o]] = (unsigned char)(o - ps[j]);
+            }
+        }
+        {
+            const int capG = std::max(4, std::min(48, nGrp / (148 * 8)));
+            std::vector<int> win, tmpw, rg;
+            unsigned char bm[WIN_MAXW][WIN_MAXW];
+            auto close_cluster = [&](int gEnd) {
+                const int c = (int)clu_grp.size() - 1, mw = (int)win.size();
+                const long long base = clu_stg.back(), nb36 = (long long)(mw * (mw + 1) / 2) * 36;
+                memset(bm, 0, sizeof(bm));
+                for (int g = clu_grp.back(); g < gEnd; ++g) {
+                    WinHdr& H = hdr[g];
+                    for (int k = 0; k < H.m; ++k)
+                        H.wslot[k] = (unsigned char)(std::lower_bound(win.begin(), win.end(), imgRank[gimg[gimg_off[g] + k]]) - win.begin());
+                    for (int gi = 0; gi < H.ng; ++gi) {
+                        const int j = H.j[gi];
+                        for (int o1 = ps[j]; o1 < ps[j + 1]; ++o1)
+                            for (int o2 = ps[j]; o2 < ps[j + 1]; ++o2) {
+                                const int wa = H.wslot[slot[o1]], wb = H.wslot[slot[o2]];
+                                if (wa >= wb) bm[wa][wb] = 1;
+                            }
+                    }
+                }
+                for (int wa = 0; wa < mw; ++wa)
+                    for (int wb = 0; wb <= wa; ++wb)
+                        if (bm[wa][wb]) contrib.push_back({(long long)win[wa] * nImg + win[wb], base + (long long)(wa * (wa + 1) / 2 + wb) * 36});
+                for (int w = 0; w < mw; ++w) {
+                    clu_img.push_back(imgOrder[win[w]]);
+                    icontrib.push_back({imgOrder[win[w]], base + nb36 + 6 * w});
+                }
+                (void)c;
+                clu_img_off.push_back((int)clu_img.size());
+                clu_stg.push_back(base + nb36 + 16 * 6 * WIN_MAXW + 256);
+                clu_grp.push_back(gEnd);
+            };
+            for (int g = 0; g < nGrp; ++g) {
+                rg.clear();
+                for (int k = gimg_off[g]; k < gimg_off[g + 1]; ++k) rg.push_back(imgRank[gimg[k]]);
+                tmpw.clear();
+                std::set_union(win.begin(), win.end(), rg.begin(), rg.end(), std::back_inserter(tmpw));
+                const int cnt = g - clu_grp.back();
+                if (cnt > 0 && ((int)tmpw.size() > WIN_MAXW || cnt >= capG)) { close_cluster(g); win = rg; }
+                else win.swap(tmpw);
+            }
+            if (nGrp > 0) close_cluster(nGrp);
+        }
+        P.nClu = (int)clu_grp.size() - 1;
+        std::stable_sort(contrib.begin(), contrib.end(), [](const Contrib& a, const Contrib& b) { return a.key < b.key; });
+        std::vector<int> red_ptr, red_imgA, red_imgB;
+        std::vector<long long> red_off(std::max<size_t>(1, contrib.size()));
+        for (size_t k = 0; k < contrib.size(); ++k) {
+            if (k == 0 || contrib[k].key != contrib[k - 1].key) {
+                red_ptr.push_back((int)k);
+                red_imgA.push_back(imgOrder[(int)(contrib[k].key / nImg)]);
+                red_imgB.push_back(imgOrder[(int)(contrib[k].key % nImg)]);
+            }
+            red_off[k] = contrib[k].off;
+        }
+        P.nRedBlk = (int)red_ptr.size();
+        red_ptr.push_back((int)contrib.size());
+        if (red_imgA.empty()) { red_imgA.push_back(0); red_imgB.push_back(0); }
+        std::stable_sort(icontrib.begin(), icontrib.end(), [](const std::pair<int, long long>& a, const std::pair<int, long long>& b) { return a.first < b.first; });
+        std::vector<int> redi_ptr(nImg + 1, 0);
+        std::vector<long long> redi_off(std::max<size_t>(1, icontrib.size()));
+        for (size_t k = 0; k < icontrib.size(); ++k) { redi_ptr[icontrib[k].first + 1]++; redi_off[k] = icontrib[k].second; }
+        for (int i = 0; i < nImg; ++i) redi_ptr[i + 1] += redi_ptr[i];
+        if (clu_img.empty()) clu_img.push_back(0);
+        {
+            WinHdr* d_h; int *d_cg, *d_cio, *d_ci, *d_rp, *d_ra, *d_rb, *d_ip; long long *d_cs, *d_ro, *d_io;
+            UP(d_h, hdr); UP(d_cg, clu_grp); UP(d_cio, clu_img_off); UP(d_ci, clu_img); UP(d_cs, clu_stg);
+            UP(d_rp, red_ptr); UP(d_ra, red_imgA); UP(d_rb, red_imgB); UP(d_ro, red_off); UP(d_ip, redi_ptr); UP(d_io, redi_off);
+            P.win_hdr = d_h; P.clu_grp = d_cg; P.clu_img_off = d_cio; P.clu_img = d_ci; P.clu_stg = d_cs;
+            P.red_ptr = d_rp; P.red_imgA = d_ra; P.red_imgB = d_rb; P.red_off = d_ro; P.redi_ptr = d_ip; P.redi_off = d_io;
+        }
+        AL(P.winM, ((size_t)P.nCand + WIN_GP) * 6);
+        AL(P.win_stg, (size_t)std::max<long long>(2, clu_stg.back()));
+        AL(P.win_ssPart, (size_t)((P.nClu + 31) / 32 + 1) * 256);
     }
     AL(h->d_tmpG, (size_t)64 * DBAT_GSZ);
     const int nPartial = std::max(2 * ((std::max(nObs, P.n) + 255) / 256),

@@ -27,6 +27,21 @@ static_assert(DBAT_NSLOT + 7 <= DBAT_GW, "Gram width");
 
 struct Chunk { int img, start, count, pad; };
 
+// window Schur (schur_win.cu): header of one group of <= WIN_GP neighbouring points whose image lists have a
+// union of <= DBAT_GRP_MAXM images.  A cluster is a run of consecutive groups whose unions together span
+// <= WIN_MAXW images (the "window").
+#define WIN_GP 14                  // points per group (K = 3 * 14 = 42 columns of the contraction)
+#define WIN_MAXW 20                // images per window = largest ray count the grouped path takes
+struct __align__(16) WinHdr {
+    int m, ng, p0, pad;                         // images in the union, points, position of the first point in grp_pt
+    int j[WIN_GP];                              // point ids
+    int ob[WIN_GP];                             // first point-major observation of every point
+    unsigned char wslot[WIN_MAXW];              // window slot of every image of the union (ascending)
+    unsigned char obsOf[WIN_GP][WIN_MAXW];      // observation (offset inside the point) of point x union image; 255 = not seen
+    unsigned char pad2[4];
+};
+static_assert(sizeof(WinHdr) == 432, "WinHdr layout");
+
 // Device view of one problem (all pointers are device pointers).
 struct DevProblem {
     int nImg, nOP, nObs, nK, nP, model;
@@ -101,5 +116,23 @@ struct DevProblem {
     const int* big_pt;     // points with more than DBAT_GRP_MAXM rays (per-point kernel)
     int nBig;
     double* vinv;          // nOP x 8: (V_j + lambda I)^-1 (6 entries) of the current solve
+    // window Schur (default, schur_win.cu): clusters of consecutive groups accumulate their camera x camera blocks in
+    // shared memory; every cluster leaves ONE image of its window in a staging buffer and a second kernel sums the
+    // images per block of S in a fixed order (index built at create) - no atomics, bit-reproducible
+    const WinHdr* win_hdr; // nGrp
+    const int* clu_grp;    // nClu+1: first group of every cluster
+    const int* clu_img_off;      // nClu+1 offsets into clu_img
+    const int* clu_img;    // window images of every cluster (ascending elimination rank)
+    const long long* clu_stg;    // nClu+1 offsets (doubles) of the cluster images in win_stg
+    int nClu, nCand;
+    double* winM;          // nCand x 6: inv(chol(V_j + lambda I)) of the grouped points, in grp_pt order
+    double* win_stg;       // staging: per cluster [window blocks (lower, 36 each) | 16 x 6*WIN_MAXW shared rows | 16 x 16]
+    const int* red_ptr;    // nRedBlk+1: contributions of every camera-pair block of S
+    const int* red_imgA; const int* red_imgB;   // images of the block (rank A >= rank B)
+    const long long* red_off;    // staging offset of every contribution (36 doubles)
+    int nRedBlk;
+    const int* redi_ptr;   // nImg+1: contributions to the shared-IO x EO rows of every image
+    const long long* redi_off;   // staging offset of entry (shared row 0, EO element 0) of the contribution
+    double* win_ssPart;    // per 32 clusters: partial sums of the 16 x 16 shared x shared tables
 };
-#define DBAT_GRP_MAXM 21   // grouped path up to 21 rays per point (header staging uses threads 64..64+6m of 192)
+#define DBAT_GRP_MAXM 20   // grouped path up to 20 rays per point (= WIN_MAXW); more rays: per-point kernel

@@ -40,6 +40,9 @@ void launch_axpy(double alpha, const double* x, const double* y, double* out, in
 void launch_inv_sqrt(const double* in, double* out, int n, cudaStream_t st);
 void launch_mul(const double* a, const double* b, double* out, int n, cudaStream_t st);
 
+// schur_win.cu (default Schur reduction: window accumulation per point cluster + fixed-order sums, no atomics)
+void launch_schur_win(const DevProblem& P, double lambda, const double* shAcc, cudaStream_t st);
+
 // general_io.cu (general IO block structure)
 void launch_point_side_gen(const DevProblem& P, cudaStream_t st);
 void launch_build_S_gen(const DevProblem& P, const double* camDiag, const double* camG, double lambda, cudaStream_t st);

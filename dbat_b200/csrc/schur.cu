@@ -806,14 +806,28 @@ __global__ void k_schur_sh_apply(DevProblem P, const double* __restrict__ shAcc)
 void launch_point_vinv(const DevProblem& P, double lambda, cudaStream_t st) {
     if (P.nOP > 0) { k_point_vinv<<<(P.nOP + 255) / 256, 256, 0, st>>>(P, lambda); count_launch(); }
 }
-static int g_schur_mode = -1;       // 0 = grouped atomic (default), 1 = deterministic, 2 = per-point atomic
+static int g_schur_mode = -1;       // 0 = window (default, no atomics), 1 = deterministic pair index, 2 = per-point atomic, 3 = grouped atomic
 static thread_local double* g_shAcc = nullptr;       // per device (one host thread drives one device)
 void launch_schur(const DevProblem& P, double lambda, cudaStream_t st) {
     if (P.nOP <= 0) return;
     if (P.ioGeneral) { launch_schur_gen(P, lambda, st); return; }
     if (g_schur_mode < 0) {
         const char* e = getenv("DBAT_SCHUR");
-        g_schur_mode = (e && e[0] == 'd') ? 1 : (e && e[0] == 'p') ? 2 : 0;
+        g_schur_mode = (e && e[0] == 'd') ? 1 : (e && e[0] == 'p') ? 2 : (e && e[0] == 'g') ? 3 : 0;
+    }
+    if (g_schur_mode == 0) {
+        // window accumulation + fixed-order reduction (schur_win.cu); only points with more than DBAT_GRP_MAXM rays
+        // (none at BASELINE configs 4 / 5) go through the per-point kernel and its atomics
+        const double* shAcc = nullptr;
+        if (P.nBig > 0) {
+            if (!g_shAcc) cudaMalloc(&g_shAcc, sizeof(double) * DBAT_NSLOT * (DBAT_NSLOT + 1));
+            cudaMemsetAsync(g_shAcc, 0, sizeof(double) * DBAT_NSLOT * (DBAT_NSLOT + 1), st);
+            k_schur_atomic<<<std::min((P.nBig + 7) / 8, 148 * 8), 256, 0, st>>>(P, lambda, g_shAcc, P.big_pt, P.nBig);
+            count_launch();
+            shAcc = g_shAcc;
+        }
+        launch_schur_win(P, lambda, shAcc, st);
+        return;
     }
     if (g_schur_mode != 1) {
         if (!g_shAcc) cudaMalloc(&g_shAcc, sizeof(double) * DBAT_NSLOT * (DBAT_NSLOT + 1));

@@ -219,6 +219,10 @@ def test_mid_size_step_and_solve_against_the_oracle():
         assert abs(st['f'] - 0.5 * rw @ rw) <= 1e-12 * 0.5 * rw @ rw
         assert abs(st['jp2'] - jp @ jp) <= 1e-9 * (jp @ jp)
         assert abs(st['rjp'] - rw @ jp) <= 1e-9 * abs(rw @ jp)
+        # the default path has no atomics anywhere (window Schur + fixed-order sums, data-flow Cholesky with a
+        # static term order): the step is bit-identical from run to run
+        p2, _ = P.normal_step(x0, lam, jacobi)
+        assert np.array_equal(p, p2), 'default path not bit-reproducible'
     P.close()
     s1, s2 = copy.deepcopy(s), copy.deepcopy(s)
     s1, ok, it, s0, E = dbat_b200.bundle(s1, 'gna')
@@ -545,12 +549,13 @@ print('DET-OK')
     assert 'DET-OK' in out.stdout, out.stdout + out.stderr
 
 
-@pytest.mark.parametrize('mode', ['maxm', 'perpoint'])
+@pytest.mark.parametrize('mode', ['maxm', 'perpoint', 'grouped'])
 def test_schur_fallback_paths_subprocess(mode):
-    """The grouped Schur kernel hands points with more than 21 rays to the per-point kernel.  No small
+    """The window Schur kernel hands points with more than 20 rays to the per-point kernel.  No small
     scene has such points, so the threshold is lowered (DBAT_GRP_MAXM=6: the 10-ray points of the test
     scene take the per-point kernel, the ragged 3-ray ones stay grouped); DBAT_SCHUR=perpoint runs the
-    per-point kernel for everything.  Same step as the oracle in both."""
+    per-point kernel for everything, DBAT_SCHUR=grouped the round-1 kernel with one atomic per entry and group.
+    Same step as the oracle in all of them."""
     import subprocess
     import sys
     code = r'''
@@ -572,7 +577,7 @@ for case in ('priors+fixed', 'ragged'):
     assert np.abs(p1 - po).max() / np.abs(po).max() < 5e-9, case
 print('FALLBACK-OK')
 ''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, DBAT_GRP_MAXM='6') if mode == 'maxm' else dict(os.environ, DBAT_SCHUR='perpoint')
+    env = dict(os.environ, DBAT_GRP_MAXM='6') if mode == 'maxm' else dict(os.environ, DBAT_SCHUR=mode)
     out = subprocess.run([sys.executable, '-c', code], env=env, capture_output=True, text=True, timeout=600)
     assert 'FALLBACK-OK' in out.stdout, out.stdout + out.stderr
 

@@ -25,9 +25,17 @@ RUN_SPECIFIC = re.compile(
 _NUM = re.compile(r'-?\d+\.?\d*(?:e[-+]?\d+)?')
 
 
+_TIE = re.compile(r'^(\s*(?:Max|X|Y|Z): -?[0-9.]+ ou) \(CP\d+, pt \d+\)\s*$')
+
+
 def _same(a, b, rtol):
     """Equal up to rtol on every printed number (and one unit of its last printed digit)."""
     if a == b:
+        return True
+    if rtol > 0 and _TIE.match(a) and _TIE.match(b) and _TIE.match(a).group(1) == _TIE.match(b).group(1):
+        # "X: 0.001 ou (CP2, pt 1002)": the arg-max label of a maximum over control points.  When two points tie to
+        # the printed digits (prague2016 weighted: |dZ| of CP2 and CP4 differ by 2e-9 relative, 1e-12 of the
+        # coordinate - below the convergence tolerance of the run) the label is decided by rounding noise.
         return True
     if rtol == 0 or _NUM.sub('#', a) != _NUM.sub('#', b):
         return False
