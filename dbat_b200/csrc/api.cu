@@ -717,6 +717,12 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
         for (int i = 0; i < nImg; ++i) redi_ptr[i + 1] += redi_ptr[i];
         if (clu_img.empty()) clu_img.push_back(0);
         {
+            std::vector<int> order((size_t)std::max(1, P.nClu), 0);
+            for (int c = 0; c < P.nClu; ++c) order[c] = c;
+            std::stable_sort(order.begin(), order.begin() + P.nClu, [&](int a, int b) { return clu_grp[a + 1] - clu_grp[a] > clu_grp[b + 1] - clu_grp[b]; });
+            int* d_co; UP(d_co, order); P.clu_order = d_co;
+        }
+        {
             WinHdr* d_h; int *d_cg, *d_cio, *d_ci, *d_rp, *d_ra, *d_rb, *d_ip; long long *d_cs, *d_ro, *d_io;
             UP(d_h, hdr); UP(d_cg, clu_grp); UP(d_cio, clu_img_off); UP(d_ci, clu_img); UP(d_cs, clu_stg);
             UP(d_rp, red_ptr); UP(d_ra, red_imgA); UP(d_rb, red_imgB); UP(d_ro, red_off); UP(d_ip, redi_ptr); UP(d_io, redi_off);
@@ -725,7 +731,7 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
         }
         AL(P.winM, ((size_t)P.nCand + WIN_GP) * 6);
         AL(P.win_stg, (size_t)std::max<long long>(2, clu_stg.back()));
-        AL(P.win_ssPart, (size_t)((P.nClu + 31) / 32 + 1) * 256);
+        AL(P.win_ssPart, (size_t)((P.nClu + 255) / 256 + 1) * 256);
     }
     AL(h->d_tmpG, (size_t)64 * DBAT_GSZ);
     const int nPartial = std::max(2 * ((std::max(nObs, P.n) + 255) / 256),

@@ -121,6 +121,7 @@ struct DevProblem {
     // images per block of S in a fixed order (index built at create) - no atomics, bit-reproducible
     const WinHdr* win_hdr; // nGrp
     const int* clu_grp;    // nClu+1: first group of every cluster
+    const int* clu_order;  // nClu: cluster ids, most groups first (launch order)
     const int* clu_img_off;      // nClu+1 offsets into clu_img
     const int* clu_img;    // window images of every cluster (ascending elimination rank)
     const long long* clu_stg;    // nClu+1 offsets (doubles) of the cluster images in win_stg
@@ -133,6 +134,6 @@ struct DevProblem {
     int nRedBlk;
     const int* redi_ptr;   // nImg+1: contributions to the shared-IO x EO rows of every image
     const long long* redi_off;   // staging offset of entry (shared row 0, EO element 0) of the contribution
-    double* win_ssPart;    // per 32 clusters: partial sums of the 16 x 16 shared x shared tables
+    double* win_ssPart;    // per 256 clusters: partial sums of the 16 x 16 shared x shared tables
 };
 #define DBAT_GRP_MAXM 20   // grouped path up to 20 rays per point (= WIN_MAXW); more rays: per-point kernel

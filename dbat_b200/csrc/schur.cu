@@ -115,7 +115,7 @@ __global__ void k_build_S(DevProblem P, const double* __restrict__ camDiag, cons
                 P.rhs[row] = -(gram_at(G, DBAT_COL_EO + a, DBAT_COL_R) + camG[ec[a]]);
             }
         }
-    } else {
+    } else if (i == P.nImg) {
         for (int e = threadIdx.x; e < DBAT_NSLOT * (DBAT_NSLOT + 1); e += blockDim.x) {
             const int a = e / (DBAT_NSLOT + 1), b = e % (DBAT_NSLOT + 1);
             const int row = P.sh_s[a];
@@ -130,18 +130,19 @@ __global__ void k_build_S(DevProblem P, const double* __restrict__ camDiag, cons
                 P.rhs[row] = -(gram_at(P.shG, a, DBAT_COL_R) + camG[P.sh_col[a]]);
             }
         }
-        for (int k = threadIdx.x; k < P.ldS; k += blockDim.x) {
-            if (P.s2x[k] >= 0) continue;
-            P.rhs[k] = 0.0;
-            if (k != P.ldS - 1) *tc_at(P.T, k, k) = 1.0;     // the rhs row gets its diagonal in tchol_put_rhs
-        }
+    }
+    // padding positions: one thread each, spread over all blocks (a single block walking ldS entries cost 28 us)
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < P.ldS && P.s2x[k] < 0) {
+        P.rhs[k] = 0.0;
+        if (k != P.ldS - 1) *tc_at(P.T, k, k) = 1.0;         // the rhs row gets its diagonal in tchol_put_rhs
     }
 }
 void launch_build_S(const DevProblem& P, const double* camDiag, const double* camG, double lambda,
                     cudaStream_t st) {
     if (P.ioGeneral) { launch_build_S_gen(P, camDiag, camG, lambda, st); return; }
     tchol_zero_dev(P.T, st);
-    k_build_S<<<P.nImg + 1, 128, 0, st>>>(P, camDiag, camG, lambda);
+    k_build_S<<<std::max(P.nImg + 1, (P.ldS + 127) / 128), 128, 0, st>>>(P, camDiag, camG, lambda);
     count_launch();
 }
 

@@ -26,12 +26,18 @@
 #include "kernels.cuh"
 #include "launch.h"
 
+#ifndef WIN_TH
 #define WIN_TH 256
+#endif
+#ifndef WIN_UNIT
+#define WIN_UNIT 3                       // column tiles per work unit (they share the A fragment)
+#endif
 #define WIN_SHLD (6 * WIN_MAXW)          // row stride of the shared-row accumulator
 #define WIN_NBLK (WIN_MAXW * (WIN_MAXW + 1) / 2)
 #define WIN_ACC (WIN_NBLK * 36)
 #define WIN_MAXRT ((6 * WIN_MAXW + 7) / 8)         // 15 row tiles of camera rows at most
-#define WIN_MAXUNIT 64
+#define WIN_MAXUNIT 96
+#define WIN_SSPART 256                   // clusters per partial sum of the shared x shared table
 
 // work units of the tile product for every number RT of camera row tiles: (row tile, first column tile, count <= 3)
 // over the lower triangle of the RT camera tiles followed by the two tiles of shared rows (virtual tile indices)
@@ -42,7 +48,7 @@ static void build_units(unsigned int (*tab)[WIN_MAXUNIT], int* cnt) {
     for (int RT = 0; RT <= WIN_MAXRT; ++RT) {
         std::vector<unsigned int> u;
         for (int ti = 0; ti < RT + 2; ++ti)
-            for (int tj = 0; tj <= ti; tj += 3) u.push_back((unsigned)ti | ((unsigned)tj << 8) | ((unsigned)std::min(3, ti + 1 - tj) << 16));
+            for (int tj = 0; tj <= ti; tj += WIN_UNIT) u.push_back((unsigned)ti | ((unsigned)tj << 8) | ((unsigned)std::min(WIN_UNIT, ti + 1 - tj) << 16));
         std::stable_sort(u.begin(), u.end(), [](unsigned a, unsigned b) { return (a >> 16) > (b >> 16); });   // big units first
         cnt[RT] = (int)u.size();
         for (size_t k = 0; k < u.size(); ++k) tab[RT][k] = u[k];
@@ -80,7 +86,9 @@ __global__ void k_point_minv(DevProblem P, double lambda) {
 }
 
 struct WinPrefetch { int4 h; double2 m; };
+#ifndef WIN_CELLS
 #define WIN_CELLS 5                      // cells (point, row) of the next group a thread keeps in registers
+#endif
 
 // row stride of the k-major operand Zt[k][row]: smallest value >= rows with stride = 4 mod 8 (conflict-free
 // fragment loads: lanes (fr, fk) of a half warp read Zt[(k0 + fk) * LDR + row0 + fr], fk * LDR mod 16 = 0, 4, 8, 12 in some order)
@@ -116,7 +124,7 @@ __global__ void __launch_bounds__(WIN_TH, 2) k_schur_win(DevProblem P) {
     double* Acc = Zt + ZT;
     double* AccSh = Acc + WIN_ACC;
     double* AccSS = AccSh + 16 * WIN_SHLD;
-    const int clu = blockIdx.x;
+    const int clu = P.clu_order[blockIdx.x];                 // largest clusters first
     const int g0 = P.clu_grp[clu], g1 = P.clu_grp[clu + 1];
     const int mw = P.clu_img_off[clu + 1] - P.clu_img_off[clu];
     for (int i = t; i < (ZT + WIN_ACC + 16 * WIN_SHLD + 256) / 2; i += WIN_TH)
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(WIN_TH, 2) k_schur_win(DevProblem P) {
 // Fixed-order sums of the cluster images into S.  Block ranges of the grid:
 //   [0, nbA)          camera-pair blocks: thread = (block, entry), 7 blocks (252 threads) per CTA
 //   [nbA, nbA + nbB)  shared-IO x EO rows and the reduced gradient: thread = (image, shared row, EO element), 2 images per CTA
-//   [nbA + nbB, ...)  shared x shared: partial sums over 32 clusters each
+//   [nbA + nbB, ...)  shared x shared: partial sums over WIN_SSPART clusters each
 __global__ void __launch_bounds__(256) k_schur_reduce(DevProblem P, int nbA, int nbB) {
     const int t = threadIdx.x;
     if ((int)blockIdx.x < nbA) {
@@ -295,6 +303,13 @@ __global__ void __launch_bounds__(256) k_schur_reduce(DevProblem P, int nbA, int
         const int c0 = P.red_ptr[blk], c1 = P.red_ptr[blk + 1];
         double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
         int c = c0;
+        for (; c + 7 < c1; c += 8) {
+            const double v0 = P.win_stg[P.red_off[c] + e], v1 = P.win_stg[P.red_off[c + 1] + e];
+            const double v2 = P.win_stg[P.red_off[c + 2] + e], v3 = P.win_stg[P.red_off[c + 3] + e];
+            const double v4 = P.win_stg[P.red_off[c + 4] + e], v5 = P.win_stg[P.red_off[c + 5] + e];
+            const double v6 = P.win_stg[P.red_off[c + 6] + e], v7 = P.win_stg[P.red_off[c + 7] + e];
+            s0 += v0; s1 += v1; s2 += v2; s3 += v3; s0 += v4; s1 += v5; s2 += v6; s3 += v7;
+        }
         for (; c + 3 < c1; c += 4) {
             s0 += P.win_stg[P.red_off[c] + e]; s1 += P.win_stg[P.red_off[c + 1] + e];
             s2 += P.win_stg[P.red_off[c + 2] + e]; s3 += P.win_stg[P.red_off[c + 3] + e];
@@ -328,10 +343,15 @@ __global__ void __launch_bounds__(256) k_schur_reduce(DevProblem P, int nbA, int
         return;
     }
     const int part = blockIdx.x - nbA - nbB;
-    const int k0 = part * 32, k1 = min(P.nClu, k0 + 32);
-    double s = 0.0;
-    for (int k = k0; k < k1; ++k) s += P.win_stg[P.clu_stg[k + 1] - 256 + t];
-    P.win_ssPart[(size_t)part * 256 + t] = s;
+    const int k0 = part * WIN_SSPART, k1 = min(P.nClu, k0 + WIN_SSPART);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int k = k0;
+    for (; k + 3 < k1; k += 4) {
+        s0 += P.win_stg[P.clu_stg[k + 1] - 256 + t]; s1 += P.win_stg[P.clu_stg[k + 2] - 256 + t];
+        s2 += P.win_stg[P.clu_stg[k + 3] - 256 + t]; s3 += P.win_stg[P.clu_stg[k + 4] - 256 + t];
+    }
+    for (; k < k1; ++k) s0 += P.win_stg[P.clu_stg[k + 1] - 256 + t];
+    P.win_ssPart[(size_t)part * 256 + t] = (s0 + s1) + (s2 + s3);
 }
 
 // shared x shared block and the shared part of the reduced gradient: sum of the partial tables (+ what the
@@ -373,7 +393,7 @@ void launch_schur_win(const DevProblem& P, double lambda, const double* shAcc, c
         cudaFuncSetAttribute(k_schur_win<WIN_LDR_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)schur_win_smem(WIN_LDR_LARGE));
         init = true;
     }
-    const int nPart = (P.nClu + 31) / 32;
+    const int nPart = (P.nClu + WIN_SSPART - 1) / WIN_SSPART;
     if (P.nClu > 0) {
         k_point_minv<<<(P.nCand + 255) / 256, 256, 0, st>>>(P, lambda);
         if (P.grpMaxRays <= 12) k_schur_win<WIN_LDR_SMALL><<<P.nClu, WIN_TH, schur_win_smem(WIN_LDR_SMALL), st>>>(P);
