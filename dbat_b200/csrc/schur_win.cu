@@ -22,6 +22,7 @@
 // Compared with the grouped kernel this replaces (k_schur_group2: one FP64 `red` per non-zero entry and group,
 // 60 M atomic lanes at BASELINE config 4), S is touched once per entry, and the result is bit-reproducible.
 #include <algorithm>
+#include <cstdio>
 #include <vector>
 #include "kernels.cuh"
 #include "launch.h"
@@ -86,9 +87,6 @@ __global__ void k_point_minv(DevProblem P, double lambda) {
 }
 
 struct WinPrefetch { int4 h; double2 m; };
-#ifndef WIN_CELLS
-#define WIN_CELLS 5                      // cells (point, row) of the next group a thread keeps in registers
-#endif
 
 // row stride of the k-major operand Zt[k][row]: smallest value >= rows with stride = 4 mod 8 (conflict-free
 // fragment loads: lanes (fr, fk) of a half warp read Zt[(k0 + fk) * LDR + row0 + fr], fk * LDR mod 16 = 0, 4, 8, 12 in some order)
@@ -115,6 +113,7 @@ __global__ void __launch_bounds__(WIN_TH, 2) k_schur_win(DevProblem P) {
     extern __shared__ __align__(16) double dsm[];
     __shared__ __align__(16) WinHdr s_hdr[3];
     __shared__ __align__(16) double s_M[2][WIN_GP * 6];
+    __shared__ int s_rowTab[8 * WIN_MAXRT], s_colTab[4 * WIN_MAXRT], s_colSh[4 * WIN_MAXRT];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int fr = lane >> 2, fk = lane & 3;
     const int RTmaxP = (6 * P.grpMaxRays + 7) >> 3;          // camera row tiles of the largest union of the problem
@@ -129,43 +128,54 @@ __global__ void __launch_bounds__(WIN_TH, 2) k_schur_win(DevProblem P) {
     const int mw = P.clu_img_off[clu + 1] - P.clu_img_off[clu];
     for (int i = t; i < (ZT + WIN_ACC + 16 * WIN_SHLD + 256) / 2; i += WIN_TH)
         reinterpret_cast<double2*>(dsm)[i] = make_double2(0.0, 0.0);
-    // ---- raw cells of a group: cell idx = (point gi, row r), r < 6m: row of a cross block (zero if the point does
-    //      not see the image), then the 14 shared IO rows, the gradient row and a zero row
-    auto cell_ptr = [&](const WinHdr& H, int m6, int R1, unsigned inv, int idx, int& gi, int& zrow) -> const double* {
-        gi = (int)(((unsigned)idx * inv) >> 24);
-        const int r = idx - gi * R1;
-        if (r < m6) {
-            const int slot = (r * 43) >> 8, a = r - 6 * slot;
-            const int o = H.obsOf[gi][slot];
-            zrow = r;
-            return o != 255 ? P.W + (size_t)(H.ob[gi] + o) * DBAT_W_STRIDE + 3 * a : nullptr;
-        }
-        const int s = r - m6;
-        zrow = shRow0 + s;
-        if (s > DBAT_NSLOT) return nullptr;
-        const double* rec = P.pt + (size_t)H.j[gi] * DBAT_PT_STRIDE;
-        return s < DBAT_NSLOT ? rec + DBAT_PT_WSH + 3 * s : rec + 6;
-    };
-    double cw[WIN_CELLS][3];
-    auto load_cells = [&](const WinHdr& H) {
-        const int m6 = 6 * H.m, R1 = m6 + 16, ncell = H.ng * R1;
-        const unsigned inv = (0x1000000u + R1 - 1) / R1;
+    // ---- raw cells of a group: cell idx = (point gi, q): q < m - the 6 x 3 cross block of the point in union image
+    //      q (zeros if the point does not see it); q = m, m+1, m+2 - shared IO rows 0-5, 6-11, 12-13 + gradient + zero
+    //      row.  One cell = 18 doubles = nine 16-byte loads; a group has at most 14 * 15 = 210 cells when its union
+    //      holds <= 12 images: one per thread, kept in registers while the previous group's products run.
+    auto cell_load = [&](const WinHdr& H, int idx, int mq, unsigned inv, double2 (&w)[9]) {
+        const int gi = (int)(((unsigned)idx * inv) >> 24), q = idx - gi * mq;
 #pragma unroll
-        for (int c = 0; c < WIN_CELLS; ++c) {
-            const int idx = t + c * WIN_TH;
-            cw[c][0] = 0.0; cw[c][1] = 0.0; cw[c][2] = 0.0;
-            if (idx < ncell) {
-                int gi, zrow;
-                const double* w = cell_ptr(H, m6, R1, inv, idx, gi, zrow);
-                if (w) { cw[c][0] = w[0]; cw[c][1] = w[1]; cw[c][2] = w[2]; }
+        for (int k = 0; k < 9; ++k) w[k] = make_double2(0.0, 0.0);
+        if (q < mq - 3) {
+            const int o = H.obsOf[gi][q];
+            if (o != 255) {
+                const double2* p = reinterpret_cast<const double2*>(P.W + (size_t)(H.ob[gi] + o) * DBAT_W_STRIDE);
+#pragma unroll
+                for (int k = 0; k < 9; ++k) w[k] = p[k];
+            }
+        } else {
+            const int b = q - (mq - 3);
+            const double2* rec = reinterpret_cast<const double2*>(P.pt + (size_t)H.j[gi] * DBAT_PT_STRIDE);
+            if (b < 2) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) w[k] = rec[5 + 9 * b + k];       // Wsh rows 6b .. 6b+5 (record offset 10 + 18 b)
+            } else {
+                w[0] = rec[23]; w[1] = rec[24]; w[2] = rec[25];              // Wsh rows 12, 13
+                const double2 g01 = rec[3], g2 = rec[4];                     // gradient (record offset 6)
+                w[3] = g01; w[4] = make_double2(g2.x, 0.0);
             }
         }
     };
-    auto put_cell = [&](const double* Mg, int gi, int zrow, double w0, double w1, double w2) {
-        double* z = Zt + (3 * gi) * LDR + zrow;              // Mg = m00 m10 m11 m20 m21 m22
-        z[0] = w0 * Mg[0];
-        z[LDR] = w0 * Mg[1] + w1 * Mg[2];
-        z[2 * LDR] = w0 * Mg[3] + w1 * Mg[4] + w2 * Mg[5];
+    auto cell_put = [&](const WinHdr& H, const double* Ms, int idx, int mq, unsigned inv, const double2 (&w)[9]) {
+        const int gi = (int)(((unsigned)idx * inv) >> 24), q = idx - gi * mq;
+        const int row0 = q < mq - 3 ? 6 * q : shRow0 + 6 * (q - (mq - 3));
+        const double* Mg = Ms + 6 * gi;                      // m00 m10 m11 m20 m21 m22
+        const double m00 = Mg[0], m10 = Mg[1], m11 = Mg[2], m20 = Mg[3], m21 = Mg[4], m22 = Mg[5];
+        double* z = Zt + (3 * gi) * LDR + row0;
+        const double* wd = reinterpret_cast<const double*>(w);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const double w0 = wd[3 * a], w1 = wd[3 * a + 1], w2 = wd[3 * a + 2];
+            z[a] = w0 * m00;
+            z[LDR + a] = w0 * m10 + w1 * m11;
+            z[2 * LDR + a] = w0 * m20 + w1 * m21 + w2 * m22;
+        }
+    };
+    double2 cw[9];
+    auto load_cells = [&](const WinHdr& H) {
+        const int mq = H.m + 3;
+        const unsigned inv = (0x1000000u + mq - 1) / mq;
+        if (t < H.ng * mq) cell_load(H, t, mq, inv, cw);
     };
     auto prefetch = [&](int g, int p0, WinPrefetch& f) {
         f.h = make_int4(0, 0, 0, 0); f.m = make_double2(0.0, 0.0);
@@ -194,28 +204,38 @@ __global__ void __launch_bounds__(WIN_TH, 2) k_schur_win(DevProblem P) {
         const int m6 = 6 * H.m, ng = H.ng;
         const int RT = (m6 + 7) >> 3;
         const int K = 3 * ng, Kp = (K + 3) & ~3;
-        // ---- Zt = ([W~ ; Wsh ; g'] M')' from the cells loaded during the previous group's products
+        // ---- Zt = ([W~ ; Wsh ; g'] M')' from the cells loaded during the previous group's products; the lookup
+        //      tables of the epilogue (row / column of the compact product -> offset in the window accumulators)
         {
-            const int R1 = m6 + 16, ncell = ng * R1;
-            const unsigned inv = (0x1000000u + R1 - 1) / R1;
-#pragma unroll
-            for (int c = 0; c < WIN_CELLS; ++c) {
-                const int idx = t + c * WIN_TH;
-                if (idx < ncell) {
-                    const int gi = (int)(((unsigned)idx * inv) >> 24), r = idx - gi * R1;
-                    put_cell(s_M[mb] + 6 * gi, gi, r < m6 ? r : shRow0 + r - m6, cw[c][0], cw[c][1], cw[c][2]);
-                }
-            }
-            for (int idx = t + WIN_CELLS * WIN_TH; idx < ncell; idx += WIN_TH) {      // unions of more than 12 images
-                int gi, zrow;
-                const double* w = cell_ptr(H, m6, R1, inv, idx, gi, zrow);
-                put_cell(s_M[mb] + 6 * gi, gi, zrow, w ? w[0] : 0.0, w ? w[1] : 0.0, w ? w[2] : 0.0);
+            const int mq = H.m + 3, ncell = ng * mq;
+            const unsigned inv = (0x1000000u + mq - 1) / mq;
+            if (t < ncell) cell_put(H, s_M[mb], t, mq, inv, cw);
+            for (int idx = t + WIN_TH; idx < ncell; idx += WIN_TH) {                  // unions of more than 14 images
+                double2 w[9];
+                cell_load(H, idx, mq, inv, w);
+                cell_put(H, s_M[mb], idx, mq, inv, w);
             }
             for (int idx = t; idx < (Kp - K) * LDR; idx += WIN_TH) Zt[K * LDR + idx] = 0.0;   // k padding
+            if (t < 8 * RT) {                                // row r of the product
+                const int a = (t * 43) >> 8, wa = H.wslot[min(a, WIN_MAXW - 1)];
+                s_rowTab[t] = t < m6 ? (a << 24) | (((wa * (wa + 1)) >> 1) * 36 + (t - 6 * a) * 6) : -1;
+            } else if (t >= 128 && t < 128 + 4 * RT) {       // column pair cc = 2 (t - 128)
+                const int cc = 2 * (t - 128), b = (cc * 43) >> 8, wb = H.wslot[min(b, WIN_MAXW - 1)];
+                s_colTab[t - 128] = cc < m6 ? (b << 24) | (wb * 36 + (cc - 6 * b)) : (127 << 24);   // 127: never <= a
+                s_colSh[t - 128] = cc < m6 ? 6 * wb + (cc - 6 * b) : -1;
+            }
         }
         WinPrefetch nxt;
         prefetch(g + 2, g + 1 < g1 ? s_hdr[hn].p0 : -1, nxt);
         __syncthreads();
+#ifdef WIN_DEBUG
+        for (int i = t; i < Kp * LDR; i += WIN_TH) {
+            const double v = Zt[i];
+            if (v != v) printf("Zt NaN clu %d g %d k %d row %d (m6 %d ng %d)\n", clu, g, i / LDR, i % LDR, m6, ng);
+        }
+        for (int i = t; i < 6 * ng; i += WIN_TH) { const double v = s_M[mb][i]; if (v != v) printf("M NaN clu %d g %d i %d\n", clu, g, i); }
+        __syncthreads();
+#endif
         if (g + 1 < g1) load_cells(s_hdr[hn]);               // in flight during the products
         // ---- tile products, one unit = one A fragment row and up to three column tiles; results straight into
         //      the window accumulators
@@ -235,37 +255,33 @@ __global__ void __launch_bounds__(WIN_TH, 2) k_schur_win(DevProblem P) {
             else if (cnt == 2) win_unit_mma<LDR, 2>(pa, pb0, pb1, pb2, Kp, c);
             else win_unit_mma<LDR, 1>(pa, pb0, pb1, pb2, Kp, c);
             // epilogue: lane holds C(r, cc), C(r, cc + 1) of every tile (virtual coordinates: camera rows first)
-            const int r = 8 * ti + fr;
             if (ti < RT) {                                   // camera x camera: block (wa, wb), wb <= wa
-                const int a = (r * 43) >> 8;
-                const int wa = H.wslot[min(a, WIN_MAXW - 1)];
-                const double* rowBase = Acc + ((wa * (wa + 1)) >> 1) * 36 + (r - 6 * a) * 6;
+                const int rt = s_rowTab[8 * ti + fr];
+                if (rt >= 0) {
+                    const int a = rt >> 24;
+                    double* rowBase = Acc + (rt & 0xffffff);
 #pragma unroll
-                for (int n = 0; n < 3; ++n) {
-                    if (n < cnt) {
-                        const int cc = 8 * (tj0 + n) + 2 * fk, b = (cc * 43) >> 8;
-                        if (r < m6 && b <= a) {
-                            double2* dst = (double2*)(rowBase + H.wslot[b] * 36 + (cc - 6 * b));
-                            double2 v = *dst;
-                            v.x += c[n][0]; v.y += c[n][1];
-                            *dst = v;
+                    for (int n = 0; n < 3; ++n) {
+                        if (n < cnt) {
+                            const int ct = s_colTab[4 * (tj0 + n) + fk];
+                            if ((ct >> 24) <= a) {
+                                double2* dst = (double2*)(rowBase + (ct & 0xffffff));
+                                double2 v = *dst;
+                                v.x += c[n][0]; v.y += c[n][1];
+                                *dst = v;
+                            }
                         }
                     }
                 }
             } else {
-                const int s = r - 8 * RT;                    // shared row 0..15
+                const int s = 8 * (ti - RT) + fr;            // shared row 0..15
 #pragma unroll
                 for (int n = 0; n < 3; ++n) {
                     if (n < cnt) {
-                        const int tj = tj0 + n, cc = 8 * tj + 2 * fk;
-                        double2* dst = nullptr;
-                        if (tj < RT) {                       // shared x camera
-                            const int b = (cc * 43) >> 8;
-                            if (cc < m6) dst = (double2*)(AccSh + s * WIN_SHLD + 6 * H.wslot[b] + (cc - 6 * b));
-                        } else {
-                            dst = (double2*)(AccSS + s * 16 + (cc - 8 * RT));
-                        }
-                        if (dst) {
+                        const int tj = tj0 + n;
+                        const int off = tj < RT ? s_colSh[4 * tj + fk] : 16 * WIN_SHLD + (8 * (tj - RT) + 2 * fk) + s * (16 - WIN_SHLD);
+                        if (off >= 0) {                      // AccSS follows AccSh: one base pointer serves both
+                            double2* dst = (double2*)(AccSh + s * WIN_SHLD + off);
                             double2 v = *dst;
                             v.x += c[n][0]; v.y += c[n][1];
                             *dst = v;
@@ -278,6 +294,9 @@ __global__ void __launch_bounds__(WIN_TH, 2) k_schur_win(DevProblem P) {
         hc = hn; mb ^= 1;
     }
     __syncthreads();
+#ifdef WIN_DEBUG
+    for (int i = t; i < WIN_ACC + 16 * WIN_SHLD + 256; i += WIN_TH) { const double v = Acc[i]; if (v != v) printf("Acc NaN clu %d i %d\n", clu, i); }
+#endif
     // ---- the cluster's window image: blocks (wa >= wb), shared rows, shared x shared
     double* out = P.win_stg + P.clu_stg[clu];
     const int nb = (mw * (mw + 1) / 2) * 36;
@@ -398,6 +417,7 @@ void launch_schur_win(const DevProblem& P, double lambda, const double* shAcc, c
         k_point_minv<<<(P.nCand + 255) / 256, 256, 0, st>>>(P, lambda);
         if (P.grpMaxRays <= 12) k_schur_win<WIN_LDR_SMALL><<<P.nClu, WIN_TH, schur_win_smem(WIN_LDR_SMALL), st>>>(P);
         else k_schur_win<WIN_LDR_LARGE><<<P.nClu, WIN_TH, schur_win_smem(WIN_LDR_LARGE), st>>>(P);
+        { cudaError_t e = cudaGetLastError(); if (e != cudaSuccess) fprintf(stderr, "dbat: k_schur_win launch failed: %s\n", cudaGetErrorString(e)); }
         const int nbA = (P.nRedBlk + 6) / 7, nbB = (P.nImg + 1) / 2;
         k_schur_reduce<<<nbA + nbB + nPart, 256, 0, st>>>(P, nbA, nbB);
         count_launch(3);
