@@ -9,11 +9,11 @@ trial points are taken, so successive steps walk the real LM path.
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 N = 1: BASELINE config 4 (1000 cameras x 200k points x 2M observations, shared Brown IO, depend datum).
-N > 1 (torchrun, one rank per GPU; --nimg / --nop select other shapes, e.g. --nimg 10000 --nop 500000 on 8 GPUs is
-BASELINE config 5 itself): the block grows with N like BASELINE config 5 - 1000 cameras, 200k
-points and 2M observations PER RANK (N = 8: 8000 x 1.6M x 16M; config 5 itself is 10k x 4M x 40M) - so the
-reduced camera system and its collective grow with N; every rank generates only its own points.  `value`
-counts 2M-observation equivalents, i.e. it aggregates over ranks (weak scaling).
+N > 1 (torchrun, one rank per GPU): BASELINE config 5 cut to N/8 of its cameras and points - 1250 cameras, 500k
+points and 5M observations PER RANK, so that N = 8 runs config 5 itself (10k cameras x 4M points x 40M
+observations) and N = 2 / 4 the same block density at 2500 / 5000 cameras.  The reduced camera system and its
+collectives grow with N; every rank generates only its own points.  `value` counts 2M-observation equivalents,
+i.e. it aggregates over ranks (weak scaling).  --nimg / --nop-per-rank select other shapes.
 """
 import argparse
 import json
@@ -29,6 +29,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 C4 = dict(nImg=1000, nOP=200000, rays=10)
+C5_PER_RANK = dict(nImg=1250, nOP=500000)          # config 5 / 8: N = 8 is config 5 itself
 UNIT = 'LM iterations/s (2M-observation equivalents)'
 # algorithmic HBM bytes per observation: what the kernel has to move at least
 ALG_BYTES = {
@@ -47,8 +48,9 @@ def parse():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200')
-    ap.add_argument('--nimg', type=int, default=0, help='cameras (default 1000 per rank)')
-    ap.add_argument('--nop', type=int, default=C4['nOP'], help='object points per rank')
+    ap.add_argument('--nimg', type=int, default=0, help='cameras in total (default: 1000 at N = 1, 1250 per rank at N > 1)')
+    ap.add_argument('--nop', '--nop-per-rank', dest='nop', type=int, default=0,
+                    help='object points per rank (default: 200k at N = 1, 500k at N > 1)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--ref-budget', type=float, default=420.0, help='wall seconds for the reference arm')
     return ap.parse_args()
@@ -157,6 +159,7 @@ def run_reference(args, rank, world):
         return
     from dbat_b200.synth import make_scene
     nImg = args.nimg or C4['nImg']
+    args.nop = args.nop or C4['nOP']
     s, _ = make_scene(nImg, args.nop, rays=C4['rays'], cache_dir=os.environ.get('DBAT_SCENE_CACHE', '/tmp'))
     nobs = len(s.IP.img)
     n = s.bundle.serial.n
@@ -171,9 +174,10 @@ def run_reference(args, rank, world):
         'config': {'workload': workload_name(nImg, args.nop, nobs, n, n - 3 * args.nop),
                    'same_config': world == 1,
                    'note': 'full config, %d of %d requested iterations inside the %.0f s budget' % (done, args.steps, args.ref_budget)
-                           + ('' if world == 1 else '; the GPU arm at %d ranks runs a %dx larger block (one such config per rank): the '
-                              'CPU figure is per 2M-observation equivalent of the 1-rank config, which flatters the CPU (its cost '
-                              'per observation grows with the block)' % (world, world))},
+                           + ('' if world == 1 else '; the GPU arm at %d ranks runs BASELINE config 5 cut to %d/8 (%.1fx the '
+                              'observations of this block, which is config 4): the CPU figure is per 2M-observation equivalent '
+                              'of config 4, which flatters the CPU (its cost per observation grows with the block)'
+                              % (world, world, 2.5 * world))},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': '%d full LM iterations on the config itself; %s' % (done, CPU_DESC)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
@@ -226,7 +230,9 @@ def main():
     from dbat_b200.parallel import ShardedProblem
     from dbat_b200.synth import make_scene, make_scene_shard
 
-    nImg = args.nimg or C4['nImg'] * world
+    per = C4 if world == 1 else C5_PER_RANK
+    args.nop = args.nop or per['nOP']
+    nImg = args.nimg or per['nImg'] * world
     nOP = args.nop * world
     if world > 1:
         # every rank generates its own share of the points; the cameras are the same everywhere
@@ -308,7 +314,7 @@ def main():
         wl = ('%s: synthetic %d cameras x %d points x %d observations (%d points and %d observations per rank, '
               'every rank sees all cameras), shared IO + Brown self-calibration (model 3), LM iteration; n=%d '
               'unknowns, reduced order %d'
-              % ('BASELINE config 5' if c5 else 'BASELINE config 5 shape (config 5 itself: 10000 x 4M x 40M), 1000 cameras + 200k points per rank',
+              % ('BASELINE config 5' if c5 else 'BASELINE config 5 cut to %d/8 of its cameras and points (config 5 itself: 10000 x 4M x 40M at 8 ranks)' % world,
                  nImg, nOP, nObsGlobal, args.nop, nObsLocal, nGlobal, nRed))
     sbytes = info['nSlotsS'] * 4096 * 8
     line = {
@@ -358,7 +364,7 @@ def main():
     for phn, (b, kern) in {'eval_jac_assembly': (ALG_BYTES['cam_side'] + ALG_BYTES['point_side'], 'k_cam_side+k_point_side'),
                            'trial_residual': (ALG_BYTES['resid'], 'k_resid'),
                            'jp_stats': (ALG_BYTES['jp'], 'k_jp'),
-                           'build_schur': (ALG_BYTES['schur'], 'k_schur_group')}.items():
+                           'build_schur': (ALG_BYTES['schur'], 'k_schur_win+k_schur_reduce')}.items():
         if ph_ms.get(phn, 0) > 0:
             g = b * nObsLocal / (ph_ms[phn] * 1e-3) / 1e9
             roofs[phn] = {'bound': 'hbm', 'achieved': g, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': g / hbm_peak,
