@@ -511,6 +511,12 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
         h->d_prr = h->d_camG + nCp;
     }
     AL(P.pt, (size_t)std::max(1, nOP) * DBAT_PT_STRIDE);
+    cudaMemset(P.pt, 0, sizeof(double) * (size_t)std::max(1, nOP) * DBAT_PT_STRIDE);   // the compact assembly leaves the rows of unestimated IO slots alone
+    {   // compact evaluation kernels (eval.cu): one shared IO block whose estimated slots all lie in f, pp, b1, K1-K3, P1-P2
+        bool ok = !general && nK <= 3 && nP <= 2 && getenv("DBAT_EVAL_GENERIC") == nullptr;
+        for (int sl = 0; sl < DBAT_NSLOT; ++sl) if (h->h_sh_col[sl] >= 0 && !((0x0CEFu >> sl) & 1)) ok = false;
+        P.evalCompact = ok ? 1 : 0;
+    }
     AL(P.W, (size_t)std::max(1, nObs) * DBAT_W_STRIDE);
     if (P.ioGeneral) AL(P.Wfull, (size_t)std::max(1, nObs) * DBAT_WF_STRIDE);
     {   // deterministic Schur index: inverse permutation, point of every pm observation, pair blocks

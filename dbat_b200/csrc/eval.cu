@@ -205,6 +205,124 @@ __global__ void __launch_bounds__(128, 3) k_cam_side(DevProblem P) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// compact camera side: the common self-calibration set - f, principal point, b1, K1-K3, P1-P2 estimated, no skew -
+// has 9 IO columns; with the 6 EO columns and the residual that is exactly 16 Gram columns = 2 DMMA tiles = 3 tile
+// pairs instead of 6 (half the tensor-pipe work of the 24-wide Gram), and nK / nP are compile-time constants in the
+// model.  The chunk Gram leaves the kernel in the same canonical layout (columns of the other slots zero).
+// ---------------------------------------------------------------------------------------------
+#define CE_MASK 0x0CEFu              // slots f px py b1 | K1 K2 K3 | P1 P2
+#define CE_NK 3
+#define CE_NP 2
+#define CE_NA 9                      // IO columns
+#define CE_EO CE_NA                  // first EO column
+#define CE_R (CE_NA + 6)             // residual column
+__host__ __device__ constexpr int ce_col(int s) { int r = 0; for (int k = 0; k < s; ++k) r += (CE_MASK >> k) & 1; return r; }
+static_assert(ce_col(DBAT_NSLOT) == CE_NA && CE_R == 15, "compact column set");
+
+template <int MODEL>
+__global__ void __launch_bounds__(128, 3) k_cam_side_c(DevProblem P) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(16) ImgRec s_g;
+    __shared__ __align__(16) IORec s_io;
+    __shared__ __align__(8) unsigned long long s_bar;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* Xt = smem + (size_t)warp * 16 * XT_LD;         // [16][XT_LD] per warp
+    const Chunk ck = P.chunks[blockIdx.x];
+    if (threadIdx.x == 0) {
+        const unsigned b = (unsigned)__cvta_generic_to_shared(&s_bar);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(b) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(b), "r"((unsigned)(sizeof(ImgRec) + sizeof(IORec))) : "memory");
+        tma_stage(&s_g, P.img + ck.img, sizeof(ImgRec), &s_bar);
+        tma_stage(&s_io, P.io + P.img_io[ck.img], sizeof(IORec), &s_bar);
+    }
+    __syncthreads();
+    {
+        const unsigned b = (unsigned)__cvta_generic_to_shared(&s_bar);
+        unsigned done = 0;
+        while (!done) {
+            asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\nselp.u32 %0, 1, 0, p;\n}"
+                         : "=r"(done) : "r"(b) : "memory");
+        }
+    }
+    const ImgRec& g = s_g;
+    const IORec& io = s_io;
+    double acc[3][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    for (int base = warp * 32; base < ck.count; base += 128) {
+        const int k = base + lane;
+        ObsJac o;
+        double w0 = 0.0, w1 = 0.0;
+        const bool valid = k < ck.count;
+        if (valid) {
+            const int idx = ck.start + k;
+            const double2 uv = P.uv_cm[idx];
+            const double2 is = P.isig_cm[idx];
+            const int j = P.pt_cm[idx];
+            const double Q[3] = {P.OPval[3 * (size_t)j], P.OPval[3 * (size_t)j + 1], P.OPval[3 * (size_t)j + 2]};
+            obs_model<MODEL, true, false>(Q, g, io, CE_NK, CE_NP, uv.x, uv.y, o);
+            w0 = is.x; w1 = is.y;
+        }
+        __syncwarp();
+        double2* col;
+#pragma unroll
+        for (int s = 0; s < DBAT_NSLOT; ++s) {
+            if ((CE_MASK >> s) & 1) {
+                col = reinterpret_cast<double2*>(Xt + ce_col(s) * XT_LD) + lane;
+                *col = valid ? make_double2(o.dIO[s][0] * w0, o.dIO[s][1] * w1) : make_double2(0.0, 0.0);
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            col = reinterpret_cast<double2*>(Xt + (CE_EO + c) * XT_LD) + lane;
+            *col = valid ? make_double2(o.dC[0][c] * w0, o.dC[1][c] * w1) : make_double2(0.0, 0.0);
+            col = reinterpret_cast<double2*>(Xt + (CE_EO + 3 + c) * XT_LD) + lane;
+            *col = valid ? make_double2(o.dA[0][c] * w0, o.dA[1][c] * w1) : make_double2(0.0, 0.0);
+        }
+        col = reinterpret_cast<double2*>(Xt + CE_R * XT_LD) + lane;
+        *col = valid ? make_double2(o.r[0] * w0, o.r[1] * w1) : make_double2(0.0, 0.0);
+        __syncwarp();
+        const double* fr = Xt + (lane >> 2) * XT_LD + (lane & 3);
+#pragma unroll 4
+        for (int k0 = 0; k0 < 64; k0 += 4) {
+            const double f0 = fr[k0], f1 = fr[8 * XT_LD + k0];
+            dmma884(acc[0][0], acc[0][1], f0, f0);
+            dmma884(acc[1][0], acc[1][1], f1, f0);
+            dmma884(acc[2][0], acc[2][1], f1, f1);
+        }
+    }
+    // cross-warp reduction in fixed order, then one partial Gram per chunk in the canonical 24-column layout
+    __syncthreads();
+    double* red = smem;                                     // [4][3 * 2][32]
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        red[(warp * 6 + 2 * t) * 32 + lane] = acc[t][0];
+        red[(warp * 6 + 2 * t + 1) * 32 + lane] = acc[t][1];
+    }
+    __syncthreads();
+    double* out = P.chunkG + (size_t)blockIdx.x * DBAT_GSZ;
+    for (int e = threadIdx.x; e < DBAT_GSZ; e += 128) {
+        const int tp = e >> 6, l = (e & 63) >> 1, h = e & 1;
+        const int p = tp < 1 ? 0 : (tp < 3 ? 1 : 2), q = tp - p * (p + 1) / 2;
+        const int R = 8 * p + (l >> 2), C = 8 * q + 2 * (l & 3) + h;                  // canonical Gram entry
+        auto cmap = [](int c) -> int {
+            if (c < DBAT_NSLOT) return ((CE_MASK >> c) & 1) ? __popc(CE_MASK & ((1u << c) - 1u)) : -1;
+            if (c < DBAT_COL_R) return CE_EO + (c - DBAT_COL_EO);
+            return c == DBAT_COL_R ? CE_R : -1;
+        };
+        int a = cmap(R), b = cmap(C);
+        double s = 0.0;
+        if (a >= 0 && b >= 0) {
+            if ((a >> 3) < (b >> 3)) { const int t2 = a; a = b; b = t2; }
+            const int tq = (a >> 3) == 0 ? 0 : 1 + (b >> 3);
+            const int src = (2 * tq + (b & 1)) * 32 + (a & 7) * 4 + ((b & 7) >> 1);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) s += red[w * 6 * 32 + src];
+        }
+        out[e] = s;
+    }
+}
+
 // per-image Gram = sum of its chunk Grams in chunk order
 __global__ void k_cam_reduce(DevProblem P, const int* __restrict__ img_chunk_start) {
     const int i = blockIdx.x;
@@ -243,7 +361,10 @@ static void launch_cam_side_t(const DevProblem& P, const int* img_chunk_start, d
         cudaFuncSetAttribute(k_cam_side<MODEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_done = true;
     }
-    if (P.nChunks > 0) k_cam_side<MODEL><<<P.nChunks, 128, smem, st>>>(P);
+    if (P.nChunks > 0) {
+        if (P.evalCompact) k_cam_side_c<MODEL><<<P.nChunks, 128, (size_t)4 * 16 * XT_LD * sizeof(double), st>>>(P);
+        else k_cam_side<MODEL><<<P.nChunks, 128, smem, st>>>(P);
+    }
     k_cam_reduce<<<P.nImg, 128, 0, st>>>(P, img_chunk_start);
     k_sh_reduce<<<DBAT_GSZ / 64, 256, 0, st>>>(P);
     (void)tmp;
@@ -439,6 +560,94 @@ __global__ void __launch_bounds__(DBAT_PSB, 3) k_point_side_obs(DevProblem P) {
     }
 }
 
+// compact point side (see k_cam_side_c): 9 IO columns, nK / nP compile-time; 11 items per point in phase 2
+#define PSC_ROW 27     // A_op 6 | r 2 | A_io 18 (+1: odd stride)
+#define PSC_ITEMS (CE_NA + 2)
+__device__ __constant__ unsigned char c_ceSlot[CE_NA] = {0, 1, 2, 3, 5, 6, 7, 10, 11};
+template <int MODEL>
+__global__ void __launch_bounds__(DBAT_PSB, 5) k_point_side_obs_c(DevProblem P) {
+    __shared__ double rows[DBAT_PSB * PSC_ROW];
+    const int tid = threadIdx.x;
+    const int p0 = P.psb_pt[2 * blockIdx.x], p1 = P.psb_pt[2 * blockIdx.x + 1];
+    const int ob0 = P.pt_start[p0], nob = P.pt_start[p1] - ob0;
+    if (tid < nob) {
+        const int ob = ob0 + tid;
+        const int j = P.pt_pm[ob];
+        const double2 uv = P.uv_pm[ob];
+        const double2 is = P.isig_pm[ob];
+        const ImgRec g = P.img[P.img_pm[ob]];
+        const IORec io = P.io[g.io];
+        const double Q[3] = {P.OPval[3 * (size_t)j], P.OPval[3 * (size_t)j + 1], P.OPval[3 * (size_t)j + 2]};
+        ObsJac o;
+        obs_model<MODEL, true, true>(Q, g, io, CE_NK, CE_NP, uv.x, uv.y, o);
+        double* row = rows + tid * PSC_ROW;
+        double A[2][3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const double m = P.op_col[3 * (size_t)j + t] >= 0 ? 1.0 : 0.0;
+            A[0][t] = o.dOP[0][t] * is.x * m; A[1][t] = o.dOP[1][t] * is.y * m;
+            row[t] = A[0][t]; row[3 + t] = A[1][t];
+        }
+        row[6] = o.r[0] * is.x; row[7] = o.r[1] * is.y;
+#pragma unroll
+        for (int s = 0; s < DBAT_NSLOT; ++s) {
+            if ((CE_MASK >> s) & 1) { row[8 + 2 * ce_col(s)] = o.dIO[s][0] * is.x; row[9 + 2 * ce_col(s)] = o.dIO[s][1] * is.y; }
+        }
+        double w[18];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const double a0 = o.dC[0][c] * is.x, a1 = o.dC[1][c] * is.y;
+            const double b0 = o.dA[0][c] * is.x, b1 = o.dA[1][c] * is.y;
+#pragma unroll
+            for (int t = 0; t < 3; ++t) {
+                w[c * 3 + t] = a0 * A[0][t] + a1 * A[1][t];
+                w[(3 + c) * 3 + t] = b0 * A[0][t] + b1 * A[1][t];
+            }
+        }
+        double2* Wo = reinterpret_cast<double2*>(P.W + (size_t)ob * DBAT_W_STRIDE);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) Wo[q] = make_double2(w[2 * q], w[2 * q + 1]);
+    }
+    __syncthreads();
+    const int nItems = (p1 - p0) * PSC_ITEMS;
+    for (int item = tid; item < nItems; item += DBAT_PSB) {
+        const int jj = item / PSC_ITEMS, it = item - jj * PSC_ITEMS;
+        const int j = p0 + jj;
+        const int r0 = P.pt_start[j] - ob0, r1 = P.pt_start[j + 1] - ob0;
+        double* rec = P.pt + (size_t)j * DBAT_PT_STRIDE;
+        if (it < CE_NA) {                                    // IO slot x OP cross block
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            for (int r = r0; r < r1; ++r) {
+                const double* row = rows + r * PSC_ROW;
+                const double u0 = row[8 + 2 * it], u1 = row[9 + 2 * it];
+                a0 += u0 * row[0] + u1 * row[3]; a1 += u0 * row[1] + u1 * row[4]; a2 += u0 * row[2] + u1 * row[5];
+            }
+            double* d = rec + DBAT_PT_WSH + 3 * c_ceSlot[it];
+            d[0] = a0; d[1] = a1; d[2] = a2;
+        } else if (it == CE_NA) {                            // V_j (upper triangle, row-wise)
+            double V[6] = {0, 0, 0, 0, 0, 0};
+            for (int r = r0; r < r1; ++r) {
+                const double* row = rows + r * PSC_ROW;
+                V[0] += row[0] * row[0] + row[3] * row[3];
+                V[1] += row[0] * row[1] + row[3] * row[4];
+                V[2] += row[0] * row[2] + row[3] * row[5];
+                V[3] += row[1] * row[1] + row[4] * row[4];
+                V[4] += row[1] * row[2] + row[4] * row[5];
+                V[5] += row[2] * row[2] + row[5] * row[5];
+            }
+#pragma unroll
+            for (int k = 0; k < 6; ++k) rec[k] = V[k];
+        } else {                                             // g_j
+            double g0 = 0.0, g1 = 0.0, g2 = 0.0;
+            for (int r = r0; r < r1; ++r) {
+                const double* row = rows + r * PSC_ROW;
+                g0 += row[0] * row[6] + row[3] * row[7]; g1 += row[1] * row[6] + row[4] * row[7]; g2 += row[2] * row[6] + row[5] * row[7];
+            }
+            rec[6] = g0; rec[7] = g1; rec[8] = g2; rec[9] = 0.0;
+        }
+    }
+}
+
 template <int MODEL>
 static void launch_point_side_t(const DevProblem& P, cudaStream_t st) {
     static const bool perPoint = getenv("DBAT_POINT_SIDE_PER_POINT") != nullptr;
@@ -447,7 +656,11 @@ static void launch_point_side_t(const DevProblem& P, cudaStream_t st) {
         count_launch();
         return;
     }
-    if (P.nPsb > 0) { k_point_side_obs<MODEL><<<P.nPsb, DBAT_PSB, 0, st>>>(P); count_launch(); }
+    if (P.nPsb > 0) {
+        if (P.evalCompact) k_point_side_obs_c<MODEL><<<P.nPsb, DBAT_PSB, 0, st>>>(P);
+        else k_point_side_obs<MODEL><<<P.nPsb, DBAT_PSB, 0, st>>>(P);
+        count_launch();
+    }
     if (P.nPsbig > 0) { k_point_side<MODEL><<<(P.nPsbig + 127) / 128, 128, 0, st>>>(P, P.psbig, P.nPsbig); count_launch(); }
 }
 void launch_point_side(const DevProblem& P, cudaStream_t st) {

@@ -77,6 +77,7 @@ struct DevProblem {
     const int* s2x;        // ldS: x column of every S index (-1: padding / rhs row)
     // general IO block structure (image-variant parameters, several cameras: IO.struct.block, buildserialindices.m:162-221)
     int ioGeneral;         // 0: one IO block shared by all images (fast path); 1: per-image column maps below are used
+    int evalCompact;       // 1: every estimated IO slot is one of f, pp, b1, K1-K3, P1-P2 (nK <= 3, nP <= 2): compact evaluation kernels
     const int* cam_colx;   // nImg x 20: x column of [NSLOT IO slots | 6 EO elements] of every image (-1 fixed); both modes
     const int* cam_s;      // nImg x 20: the same as S indices
     double* Wfull;         // general mode: nObs x 60, cross blocks [IO slots | EO] x OP of every observation (point-major)
