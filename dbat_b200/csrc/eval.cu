@@ -561,37 +561,36 @@ __global__ void __launch_bounds__(DBAT_PSB, 3) k_point_side_obs(DevProblem P) {
 }
 
 // compact point side (see k_cam_side_c): 9 IO columns, nK / nP compile-time; 11 items per point in phase 2
-#define PSC_ROW 27     // A_op 6 | r 2 | A_io 18 (+1: odd stride)
+#define PSC_ROW 27     // A_op 6 | r 2 | A_io x-rows 9 | A_io y-rows 9 (+1: odd stride)
 #define PSC_ITEMS (CE_NA + 2)
 __device__ __constant__ unsigned char c_ceSlot[CE_NA] = {0, 1, 2, 3, 5, 6, 7, 10, 11};
 template <int MODEL>
 __global__ void __launch_bounds__(DBAT_PSB, 5) k_point_side_obs_c(DevProblem P) {
-    __shared__ double rows[DBAT_PSB * PSC_ROW];
-    const int tid = threadIdx.x;
+    __shared__ __align__(16) double rows[DBAT_PSB * PSC_ROW];
+    const int tid = threadIdx.x, lane = tid & 31;
     const int p0 = P.psb_pt[2 * blockIdx.x], p1 = P.psb_pt[2 * blockIdx.x + 1];
     const int ob0 = P.pt_start[p0], nob = P.pt_start[p1] - ob0;
-    if (tid < nob) {
+    const bool valid = tid < nob;
+    ObsJac o;
+    double A[2][3];
+    double2 is = make_double2(0.0, 0.0);
+    // the warp's own part of `rows` first serves as staging area for its cross blocks: every thread leaves its 144
+    // bytes there, then the warp writes the 32 x 144 contiguous bytes of W with fully coalesced 16-byte stores (a
+    // per-thread store of W touches 32 different 128-byte lines per instruction)
+    double* stage = rows + (tid - lane) * PSC_ROW;
+    if (valid) {
         const int ob = ob0 + tid;
         const int j = P.pt_pm[ob];
         const double2 uv = P.uv_pm[ob];
-        const double2 is = P.isig_pm[ob];
+        is = P.isig_pm[ob];
         const ImgRec g = P.img[P.img_pm[ob]];
         const IORec io = P.io[g.io];
         const double Q[3] = {P.OPval[3 * (size_t)j], P.OPval[3 * (size_t)j + 1], P.OPval[3 * (size_t)j + 2]};
-        ObsJac o;
         obs_model<MODEL, true, true>(Q, g, io, CE_NK, CE_NP, uv.x, uv.y, o);
-        double* row = rows + tid * PSC_ROW;
-        double A[2][3];
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
             const double m = P.op_col[3 * (size_t)j + t] >= 0 ? 1.0 : 0.0;
             A[0][t] = o.dOP[0][t] * is.x * m; A[1][t] = o.dOP[1][t] * is.y * m;
-            row[t] = A[0][t]; row[3 + t] = A[1][t];
-        }
-        row[6] = o.r[0] * is.x; row[7] = o.r[1] * is.y;
-#pragma unroll
-        for (int s = 0; s < DBAT_NSLOT; ++s) {
-            if ((CE_MASK >> s) & 1) { row[8 + 2 * ce_col(s)] = o.dIO[s][0] * is.x; row[9 + 2 * ce_col(s)] = o.dIO[s][1] * is.y; }
         }
         double w[18];
 #pragma unroll
@@ -604,9 +603,31 @@ __global__ void __launch_bounds__(DBAT_PSB, 5) k_point_side_obs_c(DevProblem P) 
                 w[(3 + c) * 3 + t] = b0 * A[0][t] + b1 * A[1][t];
             }
         }
-        double2* Wo = reinterpret_cast<double2*>(P.W + (size_t)ob * DBAT_W_STRIDE);
+        double2* sw = reinterpret_cast<double2*>(stage + lane * DBAT_W_STRIDE);
 #pragma unroll
-        for (int q = 0; q < 9; ++q) Wo[q] = make_double2(w[2 * q], w[2 * q + 1]);
+        for (int q = 0; q < 9; ++q) sw[q] = make_double2(w[2 * q], w[2 * q + 1]);
+    }
+    __syncwarp();
+    {
+        const int nv = min(32, nob - (tid - lane));           // observations of this warp
+        double2* Wg = reinterpret_cast<double2*>(P.W + (size_t)(ob0 + tid - lane) * DBAT_W_STRIDE);
+        const double2* ss = reinterpret_cast<const double2*>(stage);
+#pragma unroll
+        for (int q = 0; q < 9; ++q) {
+            const int piece = q * 32 + lane;
+            if (piece < nv * 9) Wg[piece] = ss[piece];
+        }
+    }
+    __syncwarp();
+    if (valid) {
+        double* row = rows + tid * PSC_ROW;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) { row[t] = A[0][t]; row[3 + t] = A[1][t]; }
+        row[6] = o.r[0] * is.x; row[7] = o.r[1] * is.y;
+#pragma unroll
+        for (int s = 0; s < DBAT_NSLOT; ++s) {
+            if ((CE_MASK >> s) & 1) { row[8 + ce_col(s)] = o.dIO[s][0] * is.x; row[8 + CE_NA + ce_col(s)] = o.dIO[s][1] * is.y; }
+        }
     }
     __syncthreads();
     const int nItems = (p1 - p0) * PSC_ITEMS;
@@ -619,8 +640,8 @@ __global__ void __launch_bounds__(DBAT_PSB, 5) k_point_side_obs_c(DevProblem P) 
             double a0 = 0.0, a1 = 0.0, a2 = 0.0;
             for (int r = r0; r < r1; ++r) {
                 const double* row = rows + r * PSC_ROW;
-                const double u0 = row[8 + 2 * it], u1 = row[9 + 2 * it];
-                a0 += u0 * row[0] + u1 * row[3]; a1 += u0 * row[1] + u1 * row[4]; a2 += u0 * row[2] + u1 * row[5];
+                const double u0 = row[8 + it], u1 = row[8 + CE_NA + it];
+                a0 = fma(u1, row[3], fma(u0, row[0], a0)); a1 = fma(u1, row[4], fma(u0, row[1], a1)); a2 = fma(u1, row[5], fma(u0, row[2], a2));
             }
             double* d = rec + DBAT_PT_WSH + 3 * c_ceSlot[it];
             d[0] = a0; d[1] = a1; d[2] = a2;
