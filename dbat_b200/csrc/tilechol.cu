@@ -59,6 +59,11 @@ __device__ __forceinline__ void warp_wait_flag(const int* f, int epoch, int lane
     if (lane == 0) { while (ld_acquire(f) != epoch) { __nanosleep(32); } }
     __syncwarp();
 }
+// panel progress of a tile: wait until at least `need` of its four 16-column panels are final
+__device__ __forceinline__ void warp_wait_prog(const int* f, int need, int lane) {
+    if (lane == 0) { while (ld_acquire(f) < need) { __nanosleep(20); } }
+    __syncwarp();
+}
 __device__ __forceinline__ unsigned long long gtimer() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -173,27 +178,62 @@ __device__ __forceinline__ void tc_utile(double* As, int c0, int ti, int tj, int
     pc[LA] -= (acc[0][1] + acc[1][1]) + (acc[2][1] + acc[3][1]);
 }
 
+// Every finished 16-column panel leaves for global memory at once (with the inverse of its diagonal block) and is
+// published through the tile's progress word: the triangular solves of the tiles below start on panel 0 while
+// panels 1..3 are still being factored.
+// Look-ahead inside the tile: after the rows below a panel are solved, the three 8 x 8 tiles of the NEXT diagonal
+// block are updated first; warp 0 then runs the 16 serial pivots of that block while warps 1..3 apply the rest of
+// the trailing update and write the finished panel out - the pivot sweeps (half of the time of this routine) no
+// longer wait for the trailing update, and nobody waits for the write-out.
+__device__ __forceinline__ void tc_utile_t(double* As, int c0, int t, int lane) {
+    int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    tc_utile(As, c0, ti, t - ti * (ti + 1) / 2, lane);
+}
 __device__ void tc_potrf64(double* As, double* Xd, double* colb, int warp, int lane,
                            const unsigned char* __restrict__ valid, int gcol0, int* info, unsigned long long* minmax,
-                           int J) {
+                           int J, double* __restrict__ tile, double* __restrict__ gx, int* prog, int progBase) {
     double lmin = 1e300, lmax = 0.0;
     int bad = 0;
+    const int tid = warp * 32 + lane;
+    // panel q: columns 16q .. 16q+15 of L(J,J) (zeros above the diagonal) and inv(L_qq), by `nth` threads (index u)
+    auto publish = [&](int q, int u, int nth) {
+        const int c0 = PB * q;
+        for (int idx = u; idx < PB * 32; idx += nth) {
+            const int c = c0 + (idx >> 5), r2 = (idx & 31) * 2;
+            double2 v;
+            v.x = (r2 >= c) ? As[c * LA + r2] : 0.0;
+            v.y = (r2 + 1 >= c) ? As[c * LA + r2 + 1] : 0.0;
+            *reinterpret_cast<double2*>(tile + c * 64 + r2) = v;
+        }
+        for (int idx = u; idx < PB * TC_XLD; idx += nth) gx[q * PB * TC_XLD + idx] = Xd[q * PB * TC_XLD + idx];
+    };
     for (int p = 0; p < 4; ++p) {
         const int c0 = PB * p;
         const int m = 6 - 2 * p;                              // 8-row tiles below the diagonal block
-        if (warp == 0) tc_diag16(As, Xd + p * PB * TC_XLD, colb, c0, lane, valid, gcol0 + c0, lmin, lmax, bad);
+        if (warp == 0) {
+            tc_diag16(As, Xd + p * PB * TC_XLD, colb, c0, lane, valid, gcol0 + c0, lmin, lmax, bad);
+        } else if (p > 0) {
+            // the rest of the trailing update of panel p-1 (its first three tiles - this diagonal block - are done),
+            // then panel p-1 leaves; warps 1..3 synchronise among themselves (named barrier 1, 96 threads)
+            const int mp = m + 2, ntp = mp * (mp + 1) / 2;
+            for (int t = 3 + (warp - 1); t < ntp; t += 3) tc_utile_t(As, c0 - PB, t, lane);
+            publish(p - 1, tid - 32, TC_THREADS - 32);
+            asm volatile("bar.sync 1, 96;" ::: "memory");
+            if (tid == 32) st_release(prog, progBase + p);
+        }
         __syncthreads();
         for (int q = warp; q < m; q += TC_THREADS / 32) tc_rtile(As, Xd + p * PB * TC_XLD, c0, q, lane);
         __syncthreads();
-        const int ntile = m * (m + 1) / 2;
-        for (int t = warp; t < ntile; t += TC_THREADS / 32) {
-            int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-            while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-            while (ti * (ti + 1) / 2 > t) --ti;
-            tc_utile(As, c0, ti, t - ti * (ti + 1) / 2, lane);
+        if (p < 3) {
+            if (warp < 3) tc_utile_t(As, c0, warp, lane);    // the next diagonal block: tiles (0,0), (1,0), (1,1)
+            __syncthreads();
         }
-        __syncthreads();
     }
+    publish(3, tid, TC_THREADS);
+    __syncthreads();                                          // every thread's stores before the release
+    if (tid == 0) st_release(prog, progBase + 4);
     if (warp == 0) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -263,9 +303,42 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int 
             //      critical path of the factorisation - costs one L2 round trip and 64 uninterrupted k-steps.
             for (int term = 0; term < nterm; ++term) {
                 const int sa = D.termA[t0 + term];
-                warp_wait_flag(D.flag + sa, epoch, lane);
                 double* As = sm + (term & 1) * (64 * LA);
                 const double* ga = D.tiles + ((size_t)sa << 12);
+                if (term == nterm - 1) {
+                    // the last term is the tile the dependency chain just produced: take its 16-column panels as
+                    // they are published (the triangular solve that writes it is still working on the later ones)
+                    for (int p = 0; p < 4; ++p) {
+                        warp_wait_prog(D.prog + sa, 8 * epoch + p + 1, lane);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            const int chunk = tid + c * TC_THREADS;
+                            const int kk = 16 * p + (chunk >> 5), m2 = (chunk & 31) * 2;
+                            cp_async16(As + kk * LA + m2, ga + kk * 64 + m2);
+                        }
+                        cp_async_commit();
+                        cp_async_wait<0>();
+                        __syncthreads();
+                        if (wm >= wn) {
+#pragma unroll
+                            for (int k0 = 16 * p; k0 < 16 * p + 16; k0 += 4) {
+                                double af[4], bf[4];
+                                const double* ap = As + (k0 + fk) * LA + wm + fr;
+                                const double* bp = As + (k0 + fk) * LA + wn + fr;
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) af[i] = ap[8 * i];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) bf[j] = bp[8 * j];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                                    for (int j = 0; j < 4; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                            }
+                        }
+                    }
+                    continue;
+                }
+                warp_wait_flag(D.flag + sa, epoch, lane);
 #pragma unroll
                 for (int c = 0; c < 16; ++c) {
                     const int chunk = tid + c * TC_THREADS;
@@ -373,41 +446,35 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int 
         if (I == J) {
             __syncthreads();
             TC_STAMP(2)
-            tc_potrf64(Cs, Xd, colb, warp, lane, D.valid, 64 * J, D.info, D.minmax, J);
-            // write L(J,J) (lower triangle; zeros above) and the inverse diagonal blocks
-            for (int idx = tid; idx < 64 * 32; idx += TC_THREADS) {
-                const int c = idx >> 5, r2 = (idx & 31) * 2;
-                double2 v;
-                v.x = (r2 >= c) ? Cs[c * LA + r2] : 0.0;
-                v.y = (r2 + 1 >= c) ? Cs[c * LA + r2 + 1] : 0.0;
-                *reinterpret_cast<double2*>(tile + c * 64 + r2) = v;
-            }
-            double* gx = D.invD + (size_t)J * TC_XD;
-            for (int idx = tid; idx < TC_XD; idx += TC_THREADS) gx[idx] = Xd[idx];
+            // L(J,J) (lower triangle; zeros above) and the inverse diagonal blocks leave panel by panel
+            tc_potrf64(Cs, Xd, colb, warp, lane, D.valid, 64 * J, D.info, D.minmax, J, tile, D.invD + (size_t)J * TC_XD,
+                       D.prog + slot, 8 * epoch);
         } else {
             // ---- X = C inv(L(J,J))' by 16-column panels; warp w owns rows 16w .. 16w+15
+            // Panel p needs the inverse of the p-th diagonal block of L(J,J) and the rows of panel p in the columns
+            // before it: both are final once panels 0..p of the diagonal tile are published, so this solve follows
+            // the factorisation of the diagonal tile one panel behind instead of waiting for all of it.
             const int dslot = D.tix[(size_t)J * D.nT + J];
-            warp_wait_flag(D.flag + dslot, epoch, lane);
-            __syncthreads();                                   // all warps have stored C and seen the flag
-            {
-                double* Ls = sm + TC_OFF_LS;
-                const double* gl = D.tiles + ((size_t)dslot << 12);
-                for (int chunk = tid; chunk < 48 * 32; chunk += TC_THREADS) {
-                    const int c = chunk >> 5, m2 = (chunk & 31) * 2;
-                    cp_async16(Ls + c * LA + m2, gl + c * 64 + m2);
-                }
-                cp_async_commit();
-                const double* gx = D.invD + (size_t)J * TC_XD;
-                for (int idx = tid; idx < TC_XD; idx += TC_THREADS) Xd[idx] = __ldcg(gx + idx);
-                cp_async_wait<0>();
-                __syncthreads();
-            }
-            TC_STAMP(2)
+            double* LsW = sm + TC_OFF_LS;
+            const double* gl = D.tiles + ((size_t)dslot << 12);
+            const double* gx = D.invD + (size_t)J * TC_XD;
             const double* Ls = sm + TC_OFF_LS;
             const int R0 = 16 * warp;
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 const int c0 = PB * p;
+                warp_wait_prog(D.prog + dslot, 8 * epoch + p + 1, lane);
+                if (p < 3) {                                   // columns of panel p: operands of the later panels
+                    for (int chunk = tid; chunk < PB * 32; chunk += TC_THREADS) {
+                        const int c = c0 + (chunk >> 5), m2 = (chunk & 31) * 2;
+                        cp_async16(LsW + c * LA + m2, gl + c * 64 + m2);
+                    }
+                }
+                cp_async_commit();
+                for (int idx = tid; idx < PB * TC_XLD; idx += TC_THREADS) Xd[p * PB * TC_XLD + idx] = __ldcg(gx + p * PB * TC_XLD + idx);
+                cp_async_wait<0>();
+                __syncthreads();                               // C stored (p = 0), panel operands in place
+                if (p == 0) TC_STAMP(2)
                 double t[2][2][2];
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
@@ -453,7 +520,8 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int 
                         double* g0 = tile + (c0 + 8 * j + 2 * fk) * 64 + R0 + 8 * i + fr;
                         g0[0] = x[i][j][0]; g0[64] = x[i][j][1];
                     }
-                __syncwarp();
+                __syncthreads();                               // panel p of this tile is final in global memory
+                if (tid == 0) st_release(D.prog + slot, 8 * epoch + p + 1);
             }
         }
         __syncthreads();                                      // orders every thread's tile stores before the release
@@ -634,6 +702,7 @@ int tchol_alloc(TChol& w, const TileSym& sym) {
     bad |= al(w, &d.tiles, (size_t)s.nSlots * TC_TT, true);
     bad |= al(w, &d.invD, (size_t)s.nT * TC_XD, true);
     bad |= al(w, &d.flag, (size_t)s.nSlots, true);
+    bad |= al(w, &d.prog, (size_t)s.nSlots, true);
     bad |= al(w, &d.xflag, (size_t)s.nT, true);
     bad |= al(w, &d.counters, 8, true);
     bad |= al(w, &d.info, 1, true);

@@ -13,6 +13,7 @@ struct TCholDev {
     double* tiles = nullptr;
     double* invD = nullptr;            // nT x TC_XD: inverse of the four 16 x 16 diagonal blocks of L(J,J)
     int* flag = nullptr;               // nSlots: == epoch when the tile holds its final L values
+    int* prog = nullptr;               // nSlots: 8 * epoch + k once the first k 16-column panels of the tile are final (k = 1..4)
     int* xflag = nullptr;              // nT: == epoch when block J of the backward solution is published
     int* counters = nullptr;           // [0] next factor task, [1] next backward column
     int* info = nullptr;               // != 0: a pivot was not positive

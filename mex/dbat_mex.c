@@ -146,6 +146,14 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     if (!strcmp(cmd, "destroy")) {
         dbat_destroy(h);
         if (--nHandles == 0) mexUnlock();
+    } else if (!strcmp(cmd, "devices")) {
+        /* dbat_mex('devices', h, [0 1 2 3]): one MATLAB process drives several GPUs (dbat_set_devices) */
+        if (nrhs != 3) ERR("nrhs", "devices(h,deviceList)");
+        const mwSize nd = mxGetNumberOfElements(prhs[2]);
+        int dev[64];
+        if (nd < 1 || nd > 64) ERR("badSize", "1 to 64 devices.");
+        for (mwSize k = 0; k < nd; ++k) dev[k] = (int)mxGetDoubles(prhs[2])[k];
+        check(h, dbat_set_devices(h, dev, (int)nd));
     } else if (!strcmp(cmd, "eval")) {
         if (nrhs != 4 || mxGetNumberOfElements(prhs[2]) != n) ERR("badSize", "x must have n elements.");
         plhs[0] = mxCreateDoubleMatrix(m, 1, mxREAL);

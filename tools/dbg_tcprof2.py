@@ -24,3 +24,15 @@ print('potrf mean', (diag.t_end - diag.t_deps).mean(), 'diag wait after terms', 
 tl = d[(d.I != d.J) & (d['mode'] == 0)]
 print('tile solve mean', (tl.t_end - tl.t_deps).mean(), 'tile deps wait mean', (tl.t_deps - tl.t_terms).mean())
 print('claim->terms mean per term (ns)', ((d.t_terms - d.t_claim) / d.nterms.clip(lower=1)).mean())
+# the dependency chain of the last separator: diagonal tasks of the highest levels, and the sub-diagonal tile between them
+last = diag[diag.level >= diag.level.max() - 12].sort_values('J')
+prev_end = None
+for _, r in last.iterrows():
+    sub = d[(d.I == r.J + 1) & (d.J == r.J) & (d['mode'] == 0)]
+    s_txt = ''
+    if len(sub):
+        q = sub.iloc[0]
+        s_txt = 'sub(%d,%d): terms %.1f deps %.1f end %.1f' % (q.I, q.J, q.t_terms / 1e3, q.t_deps / 1e3, q.t_end / 1e3)
+    print('J=%d terms %.1f potrf %.1f..%.1f (%.1f) step %s | %s' % (r.J, r.t_terms / 1e3, r.t_deps / 1e3, r.t_end / 1e3, (r.t_end - r.t_deps) / 1e3,
+          '' if prev_end is None else '%.1f' % ((r.t_end - prev_end) / 1e3), s_txt))
+    prev_end = r.t_end
