@@ -8,9 +8,12 @@ python - <<'PY'
 import __graft_entry__ as g
 g.build()
 PY
-timeout 500 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_r2f.csv \
+# ncu serialises kernels: the factorisation must then be ONE launch (DBAT_TC_CHAIN_CTAS=0), not the chain launch + the
+# bulk launch that waits on it programmatically - the chain CTAs would spin on tiles of a launch ncu holds back
+export DBAT_TC_CHAIN_CTAS=0
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_r2f.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_r2f.log 2>&1
-timeout 600 ncu --set full --import-source on --clock-control none \
+timeout 400 ncu --set full --import-source on --clock-control none \
     -k regex:"k_cam_side_c|k_point_side_obs_c|k_schur_win|k_schur_reduce|k_tchol_factor|k_tchol_bwd|k_backsub_obs|k_resid|k_build_S|k_point_minv" \
     --launch-skip 40 -c 14 -o gpurun_out/r2f_kernels python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_r2f.log 2>&1
 tail -2 gpurun_out/ncu_r2f.log | cut -c1-300
