@@ -1732,16 +1732,15 @@ __global__ void k_point_pd_check(DevProblem P, int* __restrict__ bad) {
     if (!ok) *bad = 1;
 }
 
-extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
-    if (!h || !out) return DBAT_E_BADARG;
-    if (h->group) return group_cov(h, which, s0, out);
+// Common front of the covariance entry points: the undamped, Jacobi-scaled reduced system (tiles, S order) -> dense
+// copy -> dense factor -> explicit inverse C (device, ld x ld, S order, of the SCALED system; h->d_dscale unscales).
+// The dense path (chol.cu) is kept for the covariances: inv(S) is a full matrix.  *info != 0: not positive definite.
+static int cov_factor(dbat_handle* h, double** Zp, double** Cp, int* ldp, int* infop) {
     // several ranks: every rank holds the whole (summed) reduced system and inverts it redundantly; CIO / CEO come out
     // identical everywhere, COP covers the points of this rank (it shards by point like the solve, bundle_cov.m:400-455)
     DevProblem& P = h->P;
     int rc;
     if (!h->normal_valid) { if ((rc = eval_full(h))) return rc; }
-    // undamped, Jacobi-scaled reduced system (tiles, S order) -> dense copy -> dense factor -> explicit
-    // inverse.  The dense path (chol.cu) is kept for the covariances: inv(S) is a full matrix.
     launch_build_S(P, h->d_camDiag, h->d_camG, 0.0, h->st);
     if (h->nranks > 1 && h->rank != 0) { tchol_zero(h->tc, h->st); cudaMemsetAsync(P.rhs, 0, sizeof(double) * P.ldS, h->st); }
     launch_schur(P, 0.0, h->st);
@@ -1784,6 +1783,20 @@ extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
     cudaFree(Sd); cudaFree(d_bad);
     if (e != cudaSuccess) { cudaFree(Z); cudaFree(C); h->err = std::string("dbat_cov: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
     if (badPts) info = -1;
+    *Zp = Z; *Cp = C; *ldp = ldd; *infop = info;
+    return 0;
+}
+
+extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
+    if (!h || !out) return DBAT_E_BADARG;
+    if (h->group) return group_cov(h, which, s0, out);
+    DevProblem& P = h->P;
+    int rc;
+    double *Z = nullptr, *C = nullptr;
+    int ldd = 0, info = 0;
+    if ((rc = cov_factor(h, &Z, &C, &ldd, &info))) return rc;
+    const size_t sz = sizeof(double) * (size_t)ldd * ldd;
+    cudaError_t e = cudaSuccess;
     const double s02 = s0 * s0;
     const int nC = P.nC, ld = ldd;
     const std::vector<int>& x2s = h->h_x2s;
@@ -1874,6 +1887,65 @@ extern "C" int dbat_cov(dbat_handle* h, int which, double s0, double* out) {
     cudaFree(Z); cudaFree(C);
     if (e != cudaSuccess) { h->err = std::string("dbat_cov: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
     return info != 0 ? DBAT_E_NOTSPD : DBAT_OK;
+}
+
+// ---- report-side consumers of the covariance on the device (covstats.cu)
+int cov_block_stats(const double* d_blocks, const int* d_cols, int k, long long N, double thres, double* d_std_x,
+                    long long cap, long long* nHits, long long* h_block, int* h_row, int* h_col, double* h_rho,
+                    cudaStream_t st);
+void launch_cam_blocks(const double* C, int ld, const int* x2s, const double* dsc, const int* cols, int k, long long N,
+                       double s02, int bad, double* out, cudaStream_t st);
+__global__ void k_cop(DevProblem P, const double* __restrict__ C, int ldc, const double* __restrict__ dsc, double s02,
+                      double* __restrict__ out);
+
+extern "C" int dbat_cov_stats(dbat_handle* h, double s0, double thres, double* std_x, dbat_cov_hit_list* io,
+                              dbat_cov_hit_list* eo, dbat_cov_hit_list* op) {
+    if (!h || !std_x) return DBAT_E_BADARG;
+    if (h->group || h->nranks > 1) { h->err = "dbat_cov_stats runs on a single-device handle; use dbat_cov per rank"; return DBAT_E_UNSUPPORTED; }
+    DevProblem& P = h->P;
+    int rc;
+    double *Z = nullptr, *C = nullptr;
+    int ld = 0, info = 0;
+    if ((rc = cov_factor(h, &Z, &C, &ld, &info))) return rc;
+    cudaFree(Z);
+    const double s02 = s0 * s0;
+    const int NC = h->NC, nImg = P.nImg;
+    int *d_x2s = nullptr, *d_iocol = nullptr;
+    double *d_std = nullptr, *d_blk = nullptr;
+    const size_t nBlk = std::max<size_t>(std::max<size_t>((size_t)NC * NC * nImg, (size_t)36 * nImg), (size_t)9 * std::max(1, P.nOP));
+    if (cudaMalloc(&d_x2s, sizeof(int) * std::max<size_t>(1, h->h_x2s.size())) || cudaMalloc(&d_iocol, sizeof(int) * std::max<size_t>(1, h->h_io_col.size())) ||
+        cudaMalloc(&d_std, sizeof(double) * std::max(1, P.n)) || cudaMalloc(&d_blk, sizeof(double) * std::max<size_t>(1, nBlk))) {
+        cudaFree(C); cudaFree(d_x2s); cudaFree(d_iocol); cudaFree(d_std); cudaFree(d_blk);
+        h->err = "out of memory for the covariance statistics"; return DBAT_E_OOM;
+    }
+    cudaMemcpyAsync(d_x2s, h->h_x2s.data(), sizeof(int) * h->h_x2s.size(), cudaMemcpyHostToDevice, h->st);
+    cudaMemcpyAsync(d_iocol, h->h_io_col.data(), sizeof(int) * h->h_io_col.size(), cudaMemcpyHostToDevice, h->st);
+    cudaMemsetAsync(d_std, 0, sizeof(double) * std::max(1, P.n), h->st);
+    int ce = 0;
+    auto run = [&](const int* cols, int k, long long N, dbat_cov_hit_list* L) {
+        long long nh = 0;
+        dbat_cov_hit_list none = {0, 0, nullptr, nullptr, nullptr, nullptr};
+        if (!L) L = &none;
+        const int e1 = cov_block_stats(d_blk, cols, k, N, thres, d_std, (long long)L->cap, &nh, (long long*)L->block, L->row, L->col, L->rho, h->st);
+        L->n = nh;
+        if (e1 && !ce) ce = e1;
+    };
+    // IO: the NC x NC block of every image (images of one camera hold identical blocks), EO: 6 x 6 per image
+    launch_cam_blocks(C, ld, d_x2s, h->d_dscale, d_iocol, NC, nImg, s02, info != 0, d_blk, h->st);
+    run(d_iocol, NC, nImg, io);
+    launch_cam_blocks(C, ld, d_x2s, h->d_dscale, P.eo_col, 6, nImg, s02, info != 0, d_blk, h->st);
+    run(P.eo_col, 6, nImg, eo);
+    // OP: 3 x 3 per point, as dbat_cov(COP) forms them
+    cudaMemsetAsync(d_blk, 0, sizeof(double) * 9 * (size_t)std::max(1, P.nOP), h->st);
+    if (P.nOP > 0 && P.ioGeneral) launch_cop_gen(P, C, ld, h->d_dS, s02, d_blk, h->st);
+    else if (P.nOP > 0) { k_cop<<<(P.nOP + 3) / 4, 128, 0, h->st>>>(P, C, ld, h->d_dS, s02, d_blk); count_launch(); }
+    run(P.op_col, 3, P.nOP, op);
+    cudaMemcpyAsync(std_x, d_std, sizeof(double) * P.n, cudaMemcpyDeviceToHost, h->st);
+    cudaError_t e = cudaStreamSynchronize(h->st);
+    cudaFree(C); cudaFree(d_x2s); cudaFree(d_iocol); cudaFree(d_std); cudaFree(d_blk);
+    if (e != cudaSuccess || ce) { h->err = std::string("dbat_cov_stats: ") + cudaGetErrorString(e != cudaSuccess ? e : (cudaError_t)ce); return DBAT_E_CUDA; }
+    if (info != 0) { for (int c = 0; c < P.n; ++c) std_x[c] = NAN; return DBAT_E_NOTSPD; }
+    return DBAT_OK;
 }
 
 // COP: one warp per point.  Row set of W~_j: shared IO slots (NSLOT) then 6 per observation.

@@ -156,6 +156,24 @@ int dbat_normal_step(dbat_handle *h, const double *x, double lambda, int flags,
 /* Posterior covariances from the undamped factorisation at the current x, times s0^2. */
 int dbat_cov(dbat_handle *h, int which, double s0, double *out);
 
+/* Report-side consumers of the posterior covariance, computed on the device from ONE factorisation.
+ * Replaces the host post-processing of code/bundle/bundle_result_file.m:92-153 (standard deviations),
+ * code/misc/corrmat.m:21-47 and code/bundle/private/high_{io,eo,op}_correlations.m (block form):
+ *   std_x[n]  posterior standard deviation of every unknown, x order (NaN after a failed factorisation);
+ *   io/eo/op  the pairs of one block whose correlation exceeds `thres` in magnitude - IO: the NC x NC block of
+ *             every image (images of one camera hold identical blocks; rows in the struct's IO order), EO: 6 x 6 per
+ *             image, OP: 3 x 3 per object point - in the reference's order (block, then column, then row).
+ * A list may be NULL.  `n` returns the number of pairs found; at most `cap` are stored.  Indices are 0-based. */
+typedef struct dbat_cov_hit_list {
+    int64_t  cap;            /* in: capacity of the arrays */
+    int64_t  n;              /* out: pairs found */
+    int64_t *block;          /* image or object point of the pair */
+    int32_t *row, *col;      /* positions inside the block, row > col */
+    double  *rho;            /* correlation, clipped to [-1, 1] */
+} dbat_cov_hit_list;
+int dbat_cov_stats(dbat_handle *h, double s0, double thres, double *std_x, dbat_cov_hit_list *io,
+                   dbat_cov_hit_list *eo, dbat_cov_hit_list *op);
+
 /* Elimination order of the images for a banded factorisation of the reduced camera system (host only, no
  * device needed): reverse Cuthill-McKee on the co-visibility graph - images i, j are adjacent when they
  * observe a common object point, which is exactly when S has a non-zero 6x6 block (i, j).  obs_img / obs_op

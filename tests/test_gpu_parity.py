@@ -424,6 +424,38 @@ def test_full_size_properties():
     P.close()
 
 
+def test_full_size_step_against_the_oracle():
+    """BASELINE config 4 itself (1000 cameras x 200 000 points x 2 000 000 observations, n = 606 002): one damped
+    step of the device against the oracle's sparse solve of the FULL normal equations (J'J + lambda I) p = -J'r as
+    the reference forms them (levenberg_marquardt.m:76-82,119) - 1994 Schur clusters, 100 tile columns of the reduced
+    system, 36 elimination levels.  Also the residual vector itself (1e-12) and |Jp|^2, r'Jp."""
+    import scipy.sparse as sp
+    from oracle import lsa
+    s, _ = make_scene(1000, 200000, rays=10)
+    x0 = serialize(s)
+    R = np.sqrt(buildweightmatrix(s))
+    P = dbat_b200.Problem(copy.deepcopy(s))
+    ro, Jo = brown_euler_cam4(x0, s, True)
+    r_dev = P(x0, weighted=False)
+    assert np.abs(r_dev - ro).max() <= RES_RTOL * np.abs(ro).max()
+    Jw = (sp.diags(R) @ Jo).tocsc()
+    rw = R * ro
+    N = (Jw.T @ Jw).tocsc()
+    n = len(x0)
+    nC = n - len(s.bundle.serial.OP.dest)
+    lam = 1e-10 * N.diagonal().sum() / n                       # lambda0 of levenberg_marquardt.m:88-106
+    po = lsa.solve_spd_pointfirst(N + lam * sp.identity(n, format='csc'), -(Jw.T @ rw), nC)
+    p, st = P.normal_step(x0, lam, False)
+    assert relmax(p, po) < 5e-9
+    jp = Jw @ po
+    assert abs(st['f'] - 0.5 * rw @ rw) <= 1e-12 * 0.5 * rw @ rw
+    assert abs(st['jp2'] - jp @ jp) <= 1e-9 * (jp @ jp)
+    assert abs(st['rjp'] - rw @ jp) <= 1e-9 * abs(rw @ jp)
+    p2, _ = P.normal_step(x0, lam, False)
+    assert np.array_equal(p, p2), 'default path not bit-reproducible'
+    P.close()
+
+
 @pytest.mark.parametrize('n', [100, 129, 700])
 def test_dense_cholesky_solver(n):
     """The reduced-system solver on its own: blocked DMMA Cholesky, folded forward
