@@ -56,7 +56,7 @@ class Result(C.Structure):
 
 EXPORTS = ['dbat_create', 'dbat_destroy', 'dbat_last_error', 'dbat_num_unknowns',
            'dbat_num_residuals', 'dbat_eval', 'dbat_jacobian_nnz', 'dbat_jacobian_csc',
-           'dbat_default_opts', 'dbat_solve', 'dbat_normal_step', 'dbat_cov',
+           'dbat_default_opts', 'dbat_solve', 'dbat_normal_step', 'dbat_cov', 'dbat_cov_stats',
            'dbat_comm_unique_id', 'dbat_comm_init', 'dbat_phase_times', 'dbat_dense_chol_solve',
            'dbat_forwintersect', 'dbat_forwintersect_error', 'dbat_resect3', 'dbat_camera_order',
            'dbat_tile_symbolic', 'dbat_tile_symbolic_get', 'dbat_tile_symbolic_get2', 'dbat_tile_symbolic_coords',
@@ -64,6 +64,12 @@ EXPORTS = ['dbat_create', 'dbat_destroy', 'dbat_last_error', 'dbat_num_unknowns'
            'dbat_reduced_info', 'dbat_set_devices']
 
 _lib = None
+
+
+class CovHitList(C.Structure):
+    """dbat_cov_hit_list (include/dbat_gpu.h): pairs of one block whose correlation exceeds the threshold."""
+    _fields_ = [('cap', C.c_int64), ('n', C.c_int64), ('block', C.POINTER(C.c_int64)),
+                ('row', C.POINTER(C.c_int32)), ('col', C.POINTER(C.c_int32)), ('rho', C.POINTER(C.c_double))]
 
 
 class FwiDesc(C.Structure):
@@ -115,6 +121,8 @@ def lib():
     L.dbat_normal_step.restype = C.c_int
     L.dbat_cov.argtypes = [vp, C.c_int, C.c_double, c_dp]
     L.dbat_cov.restype = C.c_int
+    L.dbat_cov_stats.argtypes = [vp, C.c_double, C.c_double, c_dp, C.POINTER(CovHitList), C.POINTER(CovHitList), C.POINTER(CovHitList)]
+    L.dbat_cov_stats.restype = C.c_int
     L.dbat_comm_unique_id.argtypes = [C.c_void_p]
     L.dbat_comm_unique_id.restype = C.c_int
     L.dbat_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_void_p]

@@ -221,6 +221,34 @@ class Problem:
         self.last_phase = self.phase_times()
         return out
 
+    def cov_stats(self, s0, thres=0.95):
+        """Report-side consumers of the posterior covariance, computed on the device from one factorisation
+        (`dbat_cov_stats`; bundle_result_file.m:92-153, corrmat.m, high_{io,eo,op}_correlations.m in block form).
+        Returns a dict: 'std' (n, x order) and 'io' / 'eo' / 'op' = (row, col, block, rho) arrays of the pairs with
+        |correlation| > thres, 0-based, in the reference's order (block, then column, then row).  After a failed
+        factorisation the deviations are NaN and the lists empty."""
+        L = _lib.lib()
+        s = self.s
+        nImg, nOP, NC = s.EO.val.shape[1], s.OP.val.shape[1], s.IO.val.shape[0]
+        std = np.zeros(self.n)
+        caps = {'io': nImg * NC * (NC - 1) // 2, 'eo': nImg * 15, 'op': nOP * 3}
+        lists, keep = {}, {}
+        for k, cap in caps.items():
+            cap = max(1, cap)
+            arr = (np.zeros(cap, dtype=np.int64), np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32), np.zeros(cap))
+            keep[k] = arr
+            lists[k] = _lib.CovHitList(cap, 0, arr[0].ctypes.data_as(C.POINTER(C.c_int64)), arr[1].ctypes.data_as(C.POINTER(C.c_int32)),
+                                       arr[2].ctypes.data_as(C.POINTER(C.c_int32)), arr[3].ctypes.data_as(C.POINTER(C.c_double)))
+        rc = L.dbat_cov_stats(self._h, float(s0), float(thres), _lib.dptr(std), C.byref(lists['io']), C.byref(lists['eo']), C.byref(lists['op']))
+        if rc not in (0, _lib.E_NOTSPD):
+            self._check(rc)
+        out = {'std': std, 'failed': rc != 0}
+        for k in caps:
+            m = 0 if rc else int(min(lists[k].n, lists[k].cap))
+            b, r, c, v = keep[k]
+            out[k] = (r[:m].astype(np.int64), c[:m].astype(np.int64), b[:m].copy(), v[:m].copy())
+        return out
+
     def cov(self, which, s0):
         L = _lib.lib()
         s = self.s

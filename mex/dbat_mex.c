@@ -209,6 +209,30 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         const mwSize sz[3] = {(mwSize)dims[0], (mwSize)dims[1], (mwSize)dims[2]};
         plhs[0] = mxCreateNumericArray(3, sz, mxDOUBLE_CLASS, mxREAL);
         check(h, dbat_cov(h, (int)mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), mxGetDoubles(plhs[0])));
+    } else if (!strcmp(cmd, "covstats")) {
+        /* [sd, eo, op, io] = dbat_mex('covstats', h, s0, thres): standard deviations (n x 1) and, per block kind, a
+         * k x 4 matrix [block row col rho] (1-based) of the pairs with |correlation| > thres (dbat_cov_stats) */
+        if (nrhs != 4) ERR("nrhs", "covstats(h,s0,thres)");
+        plhs[0] = mxCreateDoubleMatrix(n, 1, mxREAL);
+        dbat_cov_hit_list L[3];
+        const mwSize cap = 1 << 20;
+        for (int k = 0; k < 3; ++k) {
+            L[k].cap = (int64_t)cap; L[k].n = 0;
+            L[k].block = (int64_t *)mxMalloc(cap * sizeof(int64_t));
+            L[k].row = (int32_t *)mxMalloc(cap * sizeof(int32_t));
+            L[k].col = (int32_t *)mxMalloc(cap * sizeof(int32_t));
+            L[k].rho = (double *)mxMalloc(cap * sizeof(double));
+        }
+        check(h, dbat_cov_stats(h, mxGetScalar(prhs[2]), mxGetScalar(prhs[3]), mxGetDoubles(plhs[0]), &L[2], &L[0], &L[1]));
+        for (int k = 0; k < 3 && k + 1 < nlhs; ++k) {
+            const mwSize m = (mwSize)(L[k].n < L[k].cap ? L[k].n : L[k].cap);
+            plhs[k + 1] = mxCreateDoubleMatrix(m, 4, mxREAL);
+            double *o = mxGetDoubles(plhs[k + 1]);
+            for (mwSize q = 0; q < m; ++q) {
+                o[q] = (double)L[k].block[q] + 1; o[m + q] = L[k].row[q] + 1; o[2 * m + q] = L[k].col[q] + 1; o[3 * m + q] = L[k].rho[q];
+            }
+        }
+        for (int k = 0; k < 3; ++k) { mxFree(L[k].block); mxFree(L[k].row); mxFree(L[k].col); mxFree(L[k].rho); }
     } else {
         ERR("badCommand", "Unknown command.");
     }

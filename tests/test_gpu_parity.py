@@ -424,6 +424,42 @@ def test_full_size_properties():
     P.close()
 
 
+@pytest.mark.parametrize('case', ['model3', 'priors+fixed'])
+def test_covariance_statistics_on_the_device(case):
+    """dbat_cov_stats: posterior standard deviations of every unknown and the pairs of every IO / EO /
+    OP block whose correlation exceeds a threshold, computed on the device - against the same statistics taken on
+    the host from the oracle's bundle_cov blocks (corrmat.m, high_{eo,op}_correlations.m in block form)."""
+    from dbat_b200.report import corrmat
+    s, _ = scene(**CASES[case])
+    so = copy.deepcopy(s)
+    s, ok, it, s0, E = dbat_b200.bundle(s, 'gna')
+    so, oko, ito, s0o, Eo = obundle(so, 'gna')
+    assert ok and oko
+    thres = 0.3                                              # low enough that every kind has pairs
+    st = E.problem.cov_stats(s0, thres)
+    assert not st['failed']
+    ser = s.bundle.serial
+    for which, k, key, src, dst in (('CIO', s.IO.val.shape[0], 'io', ser.IO.src, ser.IO.dest),
+                                    ('CEO', 6, 'eo', ser.EO.src, ser.EO.dest), ('COP', 3, 'op', ser.OP.src, ser.OP.dest)):
+        Co = dense(ocov(so, Eo, which))
+        N = Co.shape[0] // k
+        B = np.stack([Co[i * k:(i + 1) * k, i * k:(i + 1) * k] for i in range(N)])
+        R, sd = corrmat(B, True)
+        # standard deviations: element `src` of the stacked parameter array is unknown `dest` of x
+        np.testing.assert_allclose(st['std'][np.asarray(dst)], sd.reshape(-1)[np.asarray(src)], rtol=1e-6)
+        M = np.tril(np.abs(R), -1) > thres
+        n_, c_, r_ = np.nonzero(M.transpose(0, 2, 1))        # block, then column, then row
+        r, c, b, v = st[key]
+        # the device lists every image's IO block; the oracle's CIO block of an image that shares its camera with an
+        # earlier one is the same block: compare all of them
+        margin = np.abs(np.abs(R[n_, r_, c_]) - thres) > 1e-6
+        assert len(r) == len(r_) or not margin.all()
+        if margin.all():
+            assert np.array_equal(b, n_) and np.array_equal(r, r_) and np.array_equal(c, c_)
+            np.testing.assert_allclose(v, R[n_, r_, c_], rtol=1e-6, atol=1e-9)
+    E.problem.close()
+
+
 def test_full_size_step_against_the_oracle():
     """BASELINE config 4 itself (1000 cameras x 200 000 points x 2 000 000 observations, n = 606 002): one damped
     step of the device against the oracle's sparse solve of the FULL normal equations (J'J + lambda I) p = -J'r as
