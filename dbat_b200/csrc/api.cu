@@ -36,7 +36,7 @@ static std::string g_create_err;
         }                                                                                          \
     } while (0)
 
-enum { SC_RR = 0, SC_JP2 = 1, SC_RJP = 2, SC_TRACE = 3, SC_A = 4, SC_B = 5, SC_C = 6, SC_PRR = 7, SC_JPP = 8 /* 8..11 */, SC_N = 16 };
+enum { SC_RR = 0, SC_JP2 = 1, SC_RJP = 2, SC_TRACE = 3, SC_A = 4, SC_B = 5, SC_C = 6, SC_PRR = 7, SC_JPP = 8 /* 8..11 */, SC_RRT = 12, SC_N = 16 };
 enum { PH_EVAL = 0, PH_SCHUR, PH_CHOL, PH_SOLVE, PH_TRIAL, PH_JP, PH_TOTAL, PH_N };
 static const char* kPhaseNames[PH_N] = {"eval_jac_assembly", "build_schur", "cholesky", "solve_backsub",
                                         "trial_residual", "jp_stats", "total"};
@@ -98,6 +98,9 @@ struct dbat_handle {
     double *d_tmpG = nullptr, *d_partial = nullptr, *d_scal = nullptr;
     double* h_scal = nullptr;           // pinned
     double* h_G = nullptr;              // pinned: summed Gram of the last evaluation
+    unsigned long long* h_piv = nullptr;   // pinned: min / max pivot and the breakdown flag of the last factorisation
+    double* solve_pout = nullptr;       // step vector of a solve_step whose host-side part (finish_solve) is still due
+    bool solve_jp = false;
     double *d_x = nullptr, *d_t = nullptr, *d_p = nullptr, *d_pgn = nullptr, *d_g = nullptr, *d_pc = nullptr;
     double *d_camDiag = nullptr, *d_camG = nullptr, *d_diagN = nullptr, *d_dscale = nullptr;
     double *d_evalRed = nullptr, *d_prr = nullptr; size_t nEvalRed = 0;
@@ -509,6 +512,9 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
         h->d_camDiag = P.shG + DBAT_GSZ;
         h->d_camG = h->d_camDiag + nCp;
         h->d_prr = h->d_camG + nCp;
+        // without prior observations the prior terms stay zero for the life of the handle (launch_prior_apply /
+        // launch_prior_rr then queue nothing)
+        cudaMemset(h->d_camDiag, 0, sizeof(double) * (2 * nCp + 8));
     }
     AL(P.pt, (size_t)std::max(1, nOP) * DBAT_PT_STRIDE);
     cudaMemset(P.pt, 0, sizeof(double) * (size_t)std::max(1, nOP) * DBAT_PT_STRIDE);   // the compact assembly leaves the rows of unestimated IO slots alone
@@ -748,7 +754,8 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     AL(h->d_diagN, P.n); AL(h->d_dscale, P.n);
     AL(h->d_r, h->m);
     if (cudaMallocHost((void**)&h->h_scal, sizeof(double) * SC_N) != cudaSuccess ||
-        cudaMallocHost((void**)&h->h_G, sizeof(double) * DBAT_GSZ) != cudaSuccess)
+        cudaMallocHost((void**)&h->h_G, sizeof(double) * DBAT_GSZ) != cudaSuccess ||
+        cudaMallocHost((void**)&h->h_piv, sizeof(unsigned long long) * 4) != cudaSuccess)
         return fail_create(h, DBAT_E_OOM, "cudaMallocHost failed");
     h->ev.resize(4096);
     for (auto& e : h->ev) cudaEventCreate(&e);
@@ -767,6 +774,7 @@ extern "C" void dbat_destroy(dbat_handle* h) {
     for (void* p : h->allocs) cudaFree(p);
     if (h->h_scal) cudaFreeHost(h->h_scal);
     if (h->h_G) cudaFreeHost(h->h_G);
+    if (h->h_piv) cudaFreeHost(h->h_piv);
     tchol_free(h->tc);
     for (auto& e : h->ev) cudaEventDestroy(e);
     if (h->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->comm);
@@ -824,10 +832,17 @@ static int allreduce_max_u64(dbat_handle* h, unsigned long long* buf, size_t cnt
 
 // scatter device vector xdev into the parameter arrays and rebuild the per-image records
 static void set_params(dbat_handle* h, const double* xdev) {
-    launch_deserialize(xdev, h->d_IOsrc, h->d_IOdst, h->P.IOval, h->nIOdes, h->st);
-    launch_deserialize(xdev, h->d_EOsrc, h->d_EOdst, h->P.EOval, h->nEOdes, h->st);
-    launch_deserialize(xdev, h->d_OPsrc, h->d_OPdst, h->P.OPval, h->nOPdes, h->st);
-    launch_param_setup(h->P, h->d_rep, h->nIOrec, h->st);
+    static const bool split = getenv("DBAT_SETPARAMS_SPLIT") != nullptr;     // debugging: the five separate launches
+    if (split) {
+        launch_deserialize(xdev, h->d_IOsrc, h->d_IOdst, h->P.IOval, h->nIOdes, h->st);
+        launch_deserialize(xdev, h->d_EOsrc, h->d_EOdst, h->P.EOval, h->nEOdes, h->st);
+        launch_deserialize(xdev, h->d_OPsrc, h->d_OPdst, h->P.OPval, h->nOPdes, h->st);
+        launch_param_setup(h->P, h->d_rep, h->nIOrec, h->st);
+        return;
+    }
+    launch_set_params(h->P, xdev, ScatterList{h->d_IOsrc, h->d_IOdst, h->P.IOval, h->nIOdes, 0},
+                      ScatterList{h->d_EOsrc, h->d_EOdst, h->P.EOval, h->nEOdes, 0},
+                      ScatterList{h->d_OPsrc, h->d_OPdst, h->P.OPval, h->nOPdes, 0}, h->d_rep, h->nIOrec, h->st);
 }
 
 static inline double gram_host(const double* G, int R, int C) {
@@ -836,8 +851,18 @@ static inline double gram_host(const double* G, int R, int C) {
     return G[(p * (p + 1) / 2 + q) * 64 + (i * 4 + (j >> 1)) * 2 + (j & 1)];
 }
 
-// residual + Jacobian + assembly at d_x.  On return h_scal[SC_RR] = r'r (global).
-static int eval_full(dbat_handle* h) {
+// host-side end of eval_full once the stream has been synchronised: h_scal[SC_RR] = r'r (global)
+static int finish_eval(dbat_handle* h) {
+    h->h_scal[SC_RR] = gram_host(h->h_G, DBAT_COL_R, DBAT_COL_R) + h->h_scal[SC_PRR];
+    h->normal_valid = true;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { h->err = std::string("eval_full: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
+    return 0;
+}
+
+// residual + Jacobian + assembly at d_x.  On return h_scal[SC_RR] = r'r (global).  sync = false: everything is only
+// queued on the stream (no host round trip); the caller synchronises later and calls finish_eval.
+static int eval_full(dbat_handle* h, bool sync = true) {
     size_t a = ph_begin(h);
     h->cscWeighted = -1;                    // any cached Jacobian export belongs to an older x
     h->jp_vec = nullptr;
@@ -851,10 +876,11 @@ static int eval_full(dbat_handle* h) {
     cudaEventRecord(h->evJoin, h->st2);
     launch_cam_side(h->P, h->d_img_chunk_start, h->d_tmpG, h->st);
     cudaStreamWaitEvent(h->st, h->evJoin, 0);
-    launch_prior_apply(h->P, h->d_x, h->d_camDiag, h->d_camG, h->d_col2pt, h->st);
+    const bool clearPrior = h->nranks > 1;      // the in-place allreduce below leaves the sums of all ranks in these arrays
+    launch_prior_apply(h->P, h->d_x, h->d_camDiag, h->d_camG, h->d_col2pt, clearPrior, h->st);
     // r'r = Gram(r,r) + prior rows
     double* hG = h->h_G;
-    launch_prior_rr(h->P, h->d_x, h->d_partial, h->d_prr, 0, h->st);
+    launch_prior_rr(h->P, h->d_x, h->d_partial, h->d_prr, 0, clearPrior, h->st);
     if (h->nranks > 1) {
         // camera-side sums are partial per rank (each rank holds a subset of the points): one allreduce
         int rc = allreduce(h, h->d_evalRed, h->nEvalRed);
@@ -863,26 +889,24 @@ static int eval_full(dbat_handle* h) {
     cudaMemcpyAsync(hG, h->P.shG, sizeof(double) * DBAT_GSZ, cudaMemcpyDeviceToHost, h->st);
     cudaMemcpyAsync(h->h_scal + SC_PRR, h->d_prr, sizeof(double), cudaMemcpyDeviceToHost, h->st);
     ph_end(h, PH_EVAL, a);
+    if (!sync) return 0;
     cudaStreamSynchronize(h->st);
-    h->h_scal[SC_RR] = gram_host(hG, DBAT_COL_R, DBAT_COL_R) + h->h_scal[SC_PRR];
-    h->normal_valid = true;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) { h->err = std::string("eval_full: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
-    return 0;
+    return finish_eval(h);
 }
 
 // weighted r'r at device vector xdev (residual only)
-static int eval_rr(dbat_handle* h, const double* xdev, double* rr) {
+static int eval_rr(dbat_handle* h, const double* xdev, double* rr, bool sync = true) {
     size_t a = ph_begin(h);
     set_params(h, xdev);
     h->params_valid = (xdev == h->d_x);
     launch_resid(h->P, xdev, h->d_partial, h->d_scal, SC_RR, nullptr, 1, h->st);
     if (h->nranks > 1) { int rc = allreduce(h, h->d_scal + SC_RR, 1); if (rc) return rc; }
-    cudaMemcpyAsync(h->h_scal + SC_RR, h->d_scal + SC_RR, sizeof(double), cudaMemcpyDeviceToHost, h->st);
+    cudaMemcpyAsync(h->h_scal + SC_RRT, h->d_scal + SC_RR, sizeof(double), cudaMemcpyDeviceToHost, h->st);   // own slot: SC_RR keeps r'r at d_x
     ph_end(h, PH_TRIAL, a);
+    if (!sync) return 0;                        // the caller reads h_scal[SC_RRT] after its own synchronisation
     cudaError_t e = cudaStreamSynchronize(h->st);
     if (e != cudaSuccess) { h->err = std::string("eval_rr: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
-    *rr = h->h_scal[SC_RR];
+    *rr = h->h_scal[SC_RRT];
     return 0;
 }
 
@@ -934,9 +958,27 @@ static void mask_unowned(dbat_handle* h, double* x) {
     count_launch();
 }
 
+// host-side end of solve_step once the stream has been synchronised
+static void finish_solve(dbat_handle* h, int* singular) {
+    // MATLAB's mldivide warns (singularMatrix / nearlySingularMatrix) when rcond < eps; with the
+    // Cholesky factor rcond ~ (min pivot / max pivot)^2.
+    double mm[2];
+    memcpy(mm, h->h_piv, sizeof(mm));
+    const int info = (int)h->h_piv[2];
+    h->jp_vec = nullptr;
+    if (h->solve_jp) {
+        h->jp_cache[0] = h->h_scal[SC_JPP] + h->h_scal[SC_JPP + 2];
+        h->jp_cache[1] = h->h_scal[SC_JPP + 1] + h->h_scal[SC_JPP + 3];
+        h->jp_vec = h->solve_pout;
+    }
+    const double ratio = mm[1] > 0 ? mm[0] / mm[1] : 1.0;      // no camera-side unknown at all: nothing to be singular
+    *singular = (info != 0) || !(ratio * ratio > 2.220446049250313e-16);
+}
+
 // Solve the (damped, optionally Jacobi-scaled) normal equations at d_x -> step in `pout`.
 // singular: 1 if the reduced system was not positive definite / numerically singular.
-static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, int* singular) {
+// sync = false: queued only; the caller synchronises the stream later and calls finish_solve.
+static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, int* singular, bool sync = true) {
     DevProblem& P = h->P;
     TChol& tc = h->tc;
     size_t a = ph_begin(h);
@@ -1005,29 +1047,22 @@ static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, 
     launch_unpermute(P, tc.xs, jacobi ? h->d_dscale : nullptr, h->d_pc, h->st);
     static const bool fusedJp = !getenv("DBAT_JP_SEPARATE");
     double* jpOut = fusedJp ? h->d_scal + SC_JPP : nullptr;
-    launch_backsub(P, lambda, h->d_pc, pout, h->d_partial, h->d_camDiag, h->d_camG, jpOut, h->st);
+    launch_backsub(P, lambda, h->d_pc, pout, h->d_partial, h->d_camDiag, h->d_camG, jpOut, h->st, h->st2, h->evFork, h->evJoin);
     if (jpOut) {
         if (h->nranks > 1) { int rc = allreduce(h, jpOut, 2); if (rc) return rc; }     // point parts; the camera part is global already
         cudaMemcpyAsync(h->h_scal + SC_JPP, jpOut, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->st);
     }
-    int info = 0; unsigned long long mmb[2] = {0, 0};
-    cudaMemcpyAsync(&info, tc.d.info, sizeof(int), cudaMemcpyDeviceToHost, h->st);
-    cudaMemcpyAsync(mmb, tc.d.minmax, sizeof(mmb), cudaMemcpyDeviceToHost, h->st);
+    // pivot statistics into pinned memory (a copy into pageable memory would block the host until it has run)
+    h->h_piv[2] = 0;
+    cudaMemcpyAsync(h->h_piv + 2, tc.d.info, sizeof(int), cudaMemcpyDeviceToHost, h->st);
+    cudaMemcpyAsync(h->h_piv, tc.d.minmax, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->st);
     ph_end(h, PH_SOLVE, a);
+    h->solve_pout = pout; h->solve_jp = jpOut != nullptr;
+    h->jp_vec = nullptr;
+    if (!sync) return 0;
     cudaError_t e = cudaStreamSynchronize(h->st);
     if (e != cudaSuccess) { h->err = std::string("solve_step: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
-    // MATLAB's mldivide warns (singularMatrix / nearlySingularMatrix) when rcond < eps; with the
-    // Cholesky factor rcond ~ (min pivot / max pivot)^2.
-    double mm[2];
-    memcpy(mm, mmb, sizeof(mm));
-    h->jp_vec = nullptr;
-    if (jpOut) {
-        h->jp_cache[0] = h->h_scal[SC_JPP] + h->h_scal[SC_JPP + 2];
-        h->jp_cache[1] = h->h_scal[SC_JPP + 1] + h->h_scal[SC_JPP + 3];
-        h->jp_vec = pout;
-    }
-    const double ratio = mm[1] > 0 ? mm[0] / mm[1] : 1.0;      // no camera-side unknown at all: nothing to be singular
-    *singular = (info != 0) || !(ratio * ratio > 2.220446049250313e-16);
+    finish_solve(h, singular);
     return 0;
 }
 
@@ -1141,23 +1176,35 @@ extern "C" int dbat_normal_step(dbat_handle* h, const double* x, double lambda, 
     const size_t tot = ph_begin(h);
     if (x) { CK(cudaMemcpyAsync(h->d_x, x, sizeof(double) * h->P.n, cudaMemcpyHostToDevice, h->st)); h->cscWeighted = -1; mask_unowned(h, h->d_x); }
     const int64_t l0 = g_dbat_launches;
-    int rc = eval_full(h);
+    // The whole iteration is queued without a host round trip; one synchronisation at the end, then the host-side
+    // parts of the three stages (DBAT_STEP_SYNC: synchronise after every stage, as the optimisers' first iteration does).
+    static const bool stepSync = getenv("DBAT_STEP_SYNC") != nullptr;
+    int rc = eval_full(h, stepSync);
     if (rc) return rc;
-    const double f = 0.5 * h->h_scal[SC_RR];
     int sing = 0;
-    rc = solve_step(h, lambda, (flags & 1) != 0, h->d_p, &sing);
+    rc = solve_step(h, lambda, (flags & 1) != 0, h->d_p, &sing, stepSync);
     if (rc) return rc;
-    double jp2 = 0, rjp = 0, fNew = NAN;
-    rc = eval_jp(h, h->d_p, &jp2, &rjp);
-    if (rc) return rc;
+    double jp2 = 0, rjp = 0, fNew = NAN, rrT = 0;
     if (p) CK(cudaMemcpyAsync(p, h->d_p, sizeof(double) * h->P.n, cudaMemcpyDeviceToHost, h->st));
     if (flags & 2) {
         launch_axpy(1.0, h->d_p, h->d_x, h->d_t, h->P.n, h->st);
-        double rrT = 0;
-        rc = eval_rr(h, h->d_t, &rrT);
+        rc = eval_rr(h, h->d_t, &rrT, stepSync);
         if (rc) return rc;
+    }
+    if (!stepSync) {
+        cudaError_t e = cudaStreamSynchronize(h->st);
+        if (e != cudaSuccess) { h->err = std::string("dbat_normal_step: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
+        if ((rc = finish_eval(h))) return rc;
+        finish_solve(h, &sing);
+        rrT = h->h_scal[SC_RRT];
+    }
+    const double f = 0.5 * h->h_scal[SC_RR];
+    const bool jpCached = h->jp_vec == h->d_p;      // otherwise eval_jp sets the parameter arrays back to d_x
+    rc = eval_jp(h, h->d_p, &jp2, &rjp);
+    if (rc) return rc;
+    if (flags & 2) {
         fNew = 0.5 * rrT;
-        if ((flags & 4) && fNew < f) { std::swap(h->d_x, h->d_t); h->params_valid = true; h->normal_valid = false; h->cscWeighted = -1; }
+        if ((flags & 4) && fNew < f) { std::swap(h->d_x, h->d_t); h->params_valid = jpCached; h->normal_valid = false; h->cscWeighted = -1; }
     }
     ph_end(h, PH_TOTAL, tot);
     ph_collect(h);
@@ -1352,7 +1399,11 @@ static int solve_lm(dbat_handle* h, const dbat_opts* o, dbat_result* res, TraceO
     while (true) {
         while (n <= o->maxIter) {                                     // :117
             int sing = 0;
-            if ((rc = solve_step(h, lambda, false, h->d_p, &sing))) return rc;   // :119
+            // after the first iteration the solve and the trial-point residual are queued back to back and the host
+            // waits once (LM never looks at the singular flag; the |Jp| statistics come out of the back-substitution)
+            static const bool stepSync = getenv("DBAT_STEP_SYNC") != nullptr;
+            const bool defer = n > 0 && !stepSync;
+            if ((rc = solve_step(h, lambda, false, h->d_p, &sing, !defer))) return rc;   // :119
             if (res->nRr < cap + 1) res->rr[res->nRr++] = std::sqrt(rr);      // :122
             if (n == 0 && structurally_deficient(h)) {                // :126-135 (p = NaN)
                 code = -4; cudaMemsetAsync(h->d_p, 0xff, sizeof(double) * nn, h->st); break;
@@ -1361,10 +1412,14 @@ static int solve_lm(dbat_handle* h, const dbat_opts* o, dbat_result* res, TraceO
             if (o->doTrace) printf("Levenberg-Marquardt: iteration %d, residual norm=%.2g, lambda=%.2g\n", n, std::sqrt(rr), lambda);
             T.store_x(h, n);                                          // :149-156
             n++;                                                      // :159
-            if ((rc = eval_jp(h, h->d_p, &jp2, &rjp))) return rc;     // :162
+            if (!defer && (rc = eval_jp(h, h->d_p, &jp2, &rjp))) return rc;     // :162
             launch_axpy(1.0, h->d_p, h->d_x, h->d_t, nn, h->st);      // :165 t=x+p
             double rrNew = 0;
             if ((rc = eval_rr(h, h->d_t, &rrNew))) return rc;         // :166-167
+            if (defer) {
+                finish_solve(h, &sing);
+                if ((rc = eval_jp(h, h->d_p, &jp2, &rjp))) return rc; // :162
+            }
             const double fNew = 0.5 * rrNew;
             if (fNew < f) {                                           // :177 (no veto function)
                 std::swap(h->d_x, h->d_t);

@@ -82,6 +82,46 @@ void launch_param_setup(const DevProblem& P, const int* rep, int nIO, cudaStream
     count_launch(2);
 }
 
+// The same in two launches instead of five (they sit on the critical path of every evaluation and every trial point):
+// one kernel runs the three deserialisation lists, one builds the image and the IO records.
+__global__ void __launch_bounds__(256) k_scatter3(const double* __restrict__ x, ScatterList a, ScatterList b, ScatterList c) {
+    int blk = blockIdx.x;
+    ScatterList l = a;
+    if (blk >= a.nb) { blk -= a.nb; l = b; if (blk >= b.nb) { blk -= b.nb; l = c; } }
+    const int k = blk * 256 + threadIdx.x;
+    if (k < l.cnt) l.arr[l.dest[k]] = x[l.src[k]];
+}
+__global__ void __launch_bounds__(128) k_param_setup(DevProblem P, const int* __restrict__ rep, int nIO, int nbImg) {
+    if ((int)blockIdx.x < nbImg) {
+        const int i = blockIdx.x * 128 + threadIdx.x;
+        if (i >= P.nImg) return;
+        const double* e = P.EOval + 6 * (size_t)i;
+        ImgRec& g = P.img[i];
+        g.q0[0] = e[0]; g.q0[1] = e[1]; g.q0[2] = e[2];
+        sincos(e[3], &g.sw, &g.cw);
+        sincos(e[4], &g.sp, &g.cp);
+        sincos(e[5], &g.sk, &g.ck);
+        return;
+    }
+    const int u = (blockIdx.x - nbImg) * 128 + threadIdx.x;
+    if (u >= nIO) return;
+    const int NC = 5 + P.nK + P.nP;
+    const double* c = P.IOval + (size_t)NC * rep[u];
+    IORec& r = P.io[u];
+    for (int s = 0; s < DBAT_NSLOT; ++s) r.v[s] = 0.0;
+    for (int s = 0; s < 5; ++s) r.v[s] = c[s];
+    for (int k = 0; k < P.nK; ++k) r.v[DBAT_SLOT_K + k] = c[5 + k];
+    for (int k = 0; k < P.nP; ++k) r.v[DBAT_SLOT_P + k] = c[5 + P.nK + k];
+}
+void launch_set_params(const DevProblem& P, const double* x, ScatterList io, ScatterList eo, ScatterList op,
+                       const int* rep, int nIO, cudaStream_t st) {
+    io.nb = (io.cnt + 255) / 256; eo.nb = (eo.cnt + 255) / 256; op.nb = (op.cnt + 255) / 256;
+    const int nb = io.nb + eo.nb + op.nb;
+    if (nb > 0) { k_scatter3<<<nb, 256, 0, st>>>(x, io, eo, op); count_launch(); }
+    const int nbImg = (P.nImg + 127) / 128, nbIO = (nIO + 127) / 128;
+    if (nbImg + nbIO > 0) { k_param_setup<<<nbImg + nbIO, 128, 0, st>>>(P, rep, nIO, nbImg); count_launch(); }
+}
+
 // ---------------------------------------------------------------------------------------------
 // camera side: Gram of weighted rows on the FP64 tensor pipe
 // ---------------------------------------------------------------------------------------------
@@ -334,12 +374,13 @@ __global__ void k_cam_reduce(DevProblem P, const int* __restrict__ img_chunk_sta
     }
 }
 
-// sum over images in ONE launch: block b owns 64 Gram entries, its four thread groups a quarter of the images each
-// (fixed order: bit-reproducible)
-__global__ void __launch_bounds__(256) k_sh_reduce(DevProblem P) {
-    __shared__ double part[4][64];
+// sum over images in ONE launch: block b owns 64 Gram entries, its 16 thread groups a sixteenth of the images each with
+// four loads in flight (the loop is latency-bound); fixed order: bit-reproducible
+#define SHR_G 16
+__global__ void __launch_bounds__(64 * SHR_G) k_sh_reduce(DevProblem P) {
+    __shared__ double part[SHR_G][64];
     const int e = blockIdx.x * 64 + (threadIdx.x & 63), q = threadIdx.x >> 6;
-    const int per = (P.nImg + 3) / 4, i0 = q * per, i1 = min(P.nImg, i0 + per);
+    const int per = (P.nImg + SHR_G - 1) / SHR_G, i0 = min(P.nImg, q * per), i1 = min(P.nImg, i0 + per);
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int i = i0;
     for (; i + 3 < i1; i += 4) {
@@ -349,7 +390,12 @@ __global__ void __launch_bounds__(256) k_sh_reduce(DevProblem P) {
     for (; i < i1; ++i) s0 += P.imgG[(size_t)i * DBAT_GSZ + e];
     part[q][threadIdx.x & 63] = (s0 + s1) + (s2 + s3);
     __syncthreads();
-    if (threadIdx.x < 64) P.shG[e] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
+    if (threadIdx.x < 64) {
+        double t = 0.0;
+#pragma unroll
+        for (int g = 0; g < SHR_G; ++g) t += part[g][threadIdx.x];
+        P.shG[e] = t;
+    }
 }
 
 template <int MODEL>
@@ -366,7 +412,7 @@ static void launch_cam_side_t(const DevProblem& P, const int* img_chunk_start, d
         else k_cam_side<MODEL><<<P.nChunks, 128, smem, st>>>(P);
     }
     k_cam_reduce<<<P.nImg, 128, 0, st>>>(P, img_chunk_start);
-    k_sh_reduce<<<DBAT_GSZ / 64, 256, 0, st>>>(P);
+    k_sh_reduce<<<DBAT_GSZ / 64, 64 * SHR_G, 0, st>>>(P);
     (void)tmp;
     count_launch(3);
 }
@@ -563,6 +609,9 @@ __global__ void __launch_bounds__(DBAT_PSB, 3) k_point_side_obs(DevProblem P) {
 // compact point side (see k_cam_side_c): 9 IO columns, nK / nP compile-time; 11 items per point in phase 2
 #define PSC_ROW 27     // A_op 6 | r 2 | A_io x-rows 9 | A_io y-rows 9 (+1: odd stride)
 #define PSC_ITEMS (CE_NA + 2)
+#ifndef PSC_DMMA
+#define PSC_DMMA 1                   // 0: the scalar phase 2 (one thread per (point, item)), kept as a cross-check
+#endif
 __device__ __constant__ unsigned char c_ceSlot[CE_NA] = {0, 1, 2, 3, 5, 6, 7, 10, 11};
 template <int MODEL>
 __global__ void __launch_bounds__(DBAT_PSB, 5) k_point_side_obs_c(DevProblem P) {
@@ -630,6 +679,54 @@ __global__ void __launch_bounds__(DBAT_PSB, 5) k_point_side_obs_c(DevProblem P) 
         }
     }
     __syncthreads();
+#if PSC_DMMA
+    {
+        // Phase 2 on the FP64 tensor pipe: per point the 3 x 13 product  A_op' [A_op | r | A_io]  over its 2 n rows
+        // (observation, x/y).  One warp per point; one k-step of m8n8k4 takes two observations; rows 3..7 of the A
+        // fragment are zero.  Three shared-memory loads per step instead of ~8 per (item, observation).
+        const int warp = tid >> 5;
+        const int fm = lane >> 2, fk = lane & 3;             // A: row fm, k fk;  B: k fk, column fm;  C: row fm, columns 2fk, 2fk+1
+        const int xy = fk & 1, oo = fk >> 1;
+        const int nB = 8 + fm;                               // column of the second tile
+        const int offA = 3 * xy + fm;
+        const int offB0 = fm < 3 ? 3 * xy + fm : (fm == 3 ? 6 + xy : 8 + CE_NA * xy + (fm - 4));
+        const bool b1ok = nB < 4 + CE_NA;
+        const int offB1 = 8 + CE_NA * xy + (nB - 4);
+        for (int jj = warp; jj < p1 - p0; jj += DBAT_PSB / 32) {
+            const int j = p0 + jj;
+            const int r0 = P.pt_start[j] - ob0, r1 = P.pt_start[j + 1] - ob0;
+            double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+            for (int r = r0; r < r1; r += 2) {
+                const int ro = r + oo;
+                const bool in = ro < r1;
+                const double* row = rows + ro * PSC_ROW;
+                const double a = (in && fm < 3) ? row[offA] : 0.0;
+                const double b0 = in ? row[offB0] : 0.0;
+                const double b1 = (in && b1ok) ? row[offB1] : 0.0;
+                dmma884(c00, c01, a, b0);
+                dmma884(c10, c11, a, b1);
+            }
+            if (fm < 3) {
+                double* rec = P.pt + (size_t)j * DBAT_PT_STRIDE;
+                // first tile: columns 0..2 V(fm, .), 3 g(fm), 4..7 IO columns 0..3; second tile: IO columns 4..8
+                if (fk == 0) {
+                    if (fm == 0) { rec[0] = c00; rec[1] = c01; } else if (fm == 1) rec[3] = c01;
+                    rec[DBAT_PT_WSH + 3 * c_ceSlot[4] + fm] = c10; rec[DBAT_PT_WSH + 3 * c_ceSlot[5] + fm] = c11;
+                } else if (fk == 1) {
+                    rec[fm == 0 ? 2 : (fm == 1 ? 4 : 5)] = c00; rec[6 + fm] = c01;
+                    rec[DBAT_PT_WSH + 3 * c_ceSlot[6] + fm] = c10; rec[DBAT_PT_WSH + 3 * c_ceSlot[7] + fm] = c11;
+                } else if (fk == 2) {
+                    rec[DBAT_PT_WSH + 3 * c_ceSlot[0] + fm] = c00; rec[DBAT_PT_WSH + 3 * c_ceSlot[1] + fm] = c01;
+                    rec[DBAT_PT_WSH + 3 * c_ceSlot[8] + fm] = c10;
+                } else {
+                    rec[DBAT_PT_WSH + 3 * c_ceSlot[2] + fm] = c00; rec[DBAT_PT_WSH + 3 * c_ceSlot[3] + fm] = c01;
+                    if (fm == 0) rec[9] = 0.0;
+                }
+            }
+        }
+    }
+    return;
+#endif
     const int nItems = (p1 - p0) * PSC_ITEMS;
     for (int item = tid; item < nItems; item += DBAT_PSB) {
         const int jj = item / PSC_ITEMS, it = item - jj * PSC_ITEMS;
@@ -695,9 +792,11 @@ void launch_point_side(const DevProblem& P, cudaStream_t st) {
     }
 }
 void launch_prior_apply(const DevProblem& P, const double* x, double* camDiag, double* camG,
-                        const int* col2pt, cudaStream_t st) {
-    cudaMemsetAsync(camDiag, 0, sizeof(double) * P.nC, st);
-    cudaMemsetAsync(camG, 0, sizeof(double) * P.nC, st);
+                        const int* col2pt, bool clear, cudaStream_t st) {
+    if (clear || P.nPrior > 0) {             // single rank without prior rows: zeroed at create, nothing ever writes them
+        cudaMemsetAsync(camDiag, 0, sizeof(double) * P.nC, st);
+        cudaMemsetAsync(camG, 0, sizeof(double) * P.nC, st);
+    }
     if (P.nPrior > 0) {
         k_prior_apply<<<(P.nPrior + 127) / 128, 128, 0, st>>>(P, x, camDiag, camG, col2pt);
         count_launch();
@@ -707,9 +806,14 @@ void launch_prior_apply(const DevProblem& P, const double* x, double* camDiag, d
 // ---------------------------------------------------------------------------------------------
 // residual only (trial points) and J*p statistics
 // ---------------------------------------------------------------------------------------------
+#ifndef RES_BLOCK
 #define RES_BLOCK 256
+#endif
+#ifndef RES_MINB
+#define RES_MINB 1
+#endif
 template <int MODEL, bool WRITE>
-__global__ void __launch_bounds__(RES_BLOCK) k_resid(DevProblem P, double* __restrict__ partial,
+__global__ void __launch_bounds__(RES_BLOCK, RES_MINB) k_resid(DevProblem P, double* __restrict__ partial,
                                                       double2* __restrict__ r_out, int weighted) {
     __shared__ double sm[32];
     double s = 0.0;
@@ -785,12 +889,12 @@ void launch_resid(const DevProblem& P, const double* x, double* partial, double*
 }
 
 // scal[slot] = sum of squared weighted prior residuals at x
-void launch_prior_rr(const DevProblem& P, const double* x, double* partial, double* scal, int slot, cudaStream_t st) {
+void launch_prior_rr(const DevProblem& P, const double* x, double* partial, double* scal, int slot, bool clear, cudaStream_t st) {
     if (P.nPrior > 0) {
         k_prior_resid<<<1, 256, 0, st>>>(P, x, partial, nullptr, 1);
         k_final_sum<<<1, 32, 0, st>>>(partial, 1, scal, slot, 0);
         count_launch(2);
-    } else {
+    } else if (clear) {                      // single rank without prior rows: zeroed at create and stays zero
         cudaMemsetAsync(scal + slot, 0, sizeof(double), st);
     }
 }

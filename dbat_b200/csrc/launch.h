@@ -12,13 +12,16 @@ static inline void count_launch(int n = 1) { __atomic_fetch_add(&g_dbat_launches
 // eval.cu
 void launch_deserialize(const double* x, const int* src, const int* dest, double* arr, int cnt, cudaStream_t st);
 void launch_param_setup(const DevProblem& P, const int* rep, int nIO, cudaStream_t st);
+struct ScatterList { const int* src; const int* dest; double* arr; int cnt; int nb; };
+void launch_set_params(const DevProblem& P, const double* x, ScatterList io, ScatterList eo, ScatterList op,
+                       const int* rep, int nIO, cudaStream_t st);
 void launch_cam_side(const DevProblem& P, const int* img_chunk_start, double* tmp, cudaStream_t st);
 void launch_point_side(const DevProblem& P, cudaStream_t st);
 void launch_prior_apply(const DevProblem& P, const double* x, double* camDiag, double* camG,
-                        const int* col2pt, cudaStream_t st);
+                        const int* col2pt, bool clear, cudaStream_t st);
 void launch_resid(const DevProblem& P, const double* x, double* partial, double* scal, int slot,
                   double* r_out, int weighted, cudaStream_t st);
-void launch_prior_rr(const DevProblem& P, const double* x, double* partial, double* scal, int slot, cudaStream_t st);
+void launch_prior_rr(const DevProblem& P, const double* x, double* partial, double* scal, int slot, bool clear, cudaStream_t st);
 void launch_jp(const DevProblem& P, const double* x, const double* p, double* partial, double* scal,
                int slot2, int slotr, cudaStream_t st);
 void launch_export_jac(const DevProblem& P, double* out, int weighted, cudaStream_t st);
@@ -33,7 +36,8 @@ void launch_point_vinv(const DevProblem& P, double lambda, cudaStream_t st);   /
 void launch_scale_prep(const DevProblem& P, const double* d, double* dS, cudaStream_t st);
 void launch_unpermute(const DevProblem& P, const double* xs, const double* d, double* pc, cudaStream_t st);
 void launch_backsub(const DevProblem& P, double lambda, const double* pc, double* p, double* partial,
-                    const double* camDiag, const double* camG, double* jpOut, cudaStream_t st);
+                    const double* camDiag, const double* camG, double* jpOut, cudaStream_t st,
+                    cudaStream_t st2 = nullptr, cudaEvent_t evFork = nullptr, cudaEvent_t evJoin = nullptr);
 void launch_vec_ops_sum(const double* a, int n, double* partial, double* scal, int slot, cudaStream_t st);
 void launch_dot(const double* a, const double* b, int n, double* partial, double* scal, int slot, cudaStream_t st);
 void launch_axpy(double alpha, const double* x, const double* y, double* out, int n, cudaStream_t st);

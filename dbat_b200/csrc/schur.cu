@@ -1074,11 +1074,20 @@ __global__ void __launch_bounds__(128) k_jp_cam(DevProblem P, const double* __re
         stats[gridDim.x + blockIdx.x] = (red[1][0] + red[1][1]) + (red[1][2] + red[1][3]);
     }
 }
-// sums of two partial arrays (a[0..n), a[n..2n)) into out[0], out[1]; one block, fixed order
-__global__ void __launch_bounds__(1024) k_sum_pair(const double* __restrict__ a, int n, double* __restrict__ out) {
+// sums of two partial arrays (a[0..n), a[n..2n)) into out[0], out[1]; one block per array pair, fixed order, four
+// independent chains per thread (the loop is latency-bound).  Block 1 (if launched) does the same for (b, nb) -> out[2..3].
+__global__ void __launch_bounds__(1024) k_sum_pair(const double* __restrict__ a, int n, double* __restrict__ out,
+                                                    const double* __restrict__ b, int nb) {
     __shared__ double sm[2][32];
-    double s0 = 0.0, s1 = 0.0;
-    for (int k = threadIdx.x; k < n; k += blockDim.x) { s0 += a[k]; s1 += a[n + k]; }
+    if (blockIdx.x == 1) { a = b; n = nb; out += 2; }
+    double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0, u0 = 0.0, u1 = 0.0, v0 = 0.0, v1 = 0.0;
+    int k = threadIdx.x;
+    for (; k + 3072 < n; k += 4096) {
+        s0 += a[k]; s1 += a[n + k]; t0 += a[k + 1024]; t1 += a[n + k + 1024];
+        u0 += a[k + 2048]; u1 += a[n + k + 2048]; v0 += a[k + 3072]; v1 += a[n + k + 3072];
+    }
+    for (; k < n; k += 1024) { s0 += a[k]; s1 += a[n + k]; }
+    s0 = (s0 + t0) + (u0 + v0); s1 = (s1 + t1) + (u1 + v1);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o); }
     if ((threadIdx.x & 31) == 0) { sm[0][threadIdx.x >> 5] = s0; sm[1][threadIdx.x >> 5] = s1; }
@@ -1093,31 +1102,44 @@ __global__ void __launch_bounds__(1024) k_sum_pair(const double* __restrict__ a,
 // p = [pc ; back-substituted points].  jpOut (4 doubles, may be null): [0..1] point part of |Jp|^2, r'Jp (a multi-rank
 // run sums these over the ranks), [2..3] the camera part (identical on every rank).
 void launch_backsub(const DevProblem& P, double lambda, const double* pc, double* p, double* partial,
-                    const double* camDiag, const double* camG, double* jpOut, cudaStream_t st) {
+                    const double* camDiag, const double* camG, double* jpOut, cudaStream_t st,
+                    cudaStream_t st2, cudaEvent_t evFork, cudaEvent_t evJoin) {
     static const bool perPoint = getenv("DBAT_POINT_SIDE_PER_POINT") != nullptr;
     if (pc != p) cudaMemcpyAsync(p, pc, sizeof(double) * P.nC, cudaMemcpyDeviceToDevice, st);
+    // number of per-block partial pairs the point kernels will write (the camera part's partials follow them)
     int nb = 0;
-    if (P.nOP > 0 && P.ioGeneral) {
-        nb = launch_backsub_gen(P, lambda, p, jpOut ? partial : nullptr, st);
+    const int nbBig = P.nPsbig > 0 ? (P.nPsbig + 127) / 128 : 0;
+    const bool general = P.nOP > 0 && P.ioGeneral, onePerPoint = P.nOP > 0 && !P.ioGeneral && (perPoint || !P.psb_pt);
+    if (general) nb = (P.nOP + 127) / 128;        // launch_backsub_gen: one warp-free block per 128 points
+    else if (onePerPoint) nb = (P.nOP + 127) / 128;
+    else if (P.nOP > 0) nb = P.nPsb + nbBig;
+    const int nbc = (P.nImg + 3) / 4;
+    const bool side = jpOut && st2 && evFork && evJoin;
+    if (side) {
+        // the camera part of |Jp|^2, r'Jp needs only p_c and the Grams: it runs beside the back-substitution
+        cudaEventRecord(evFork, st);
+        cudaStreamWaitEvent(st2, evFork, 0);
+        k_jp_cam<<<nbc, 128, 0, st2>>>(P, p, camDiag, camG, partial + 2 * nb);
+        cudaEventRecord(evJoin, st2);
+        count_launch();
+    }
+    if (general) {
+        launch_backsub_gen(P, lambda, p, jpOut ? partial : nullptr, st);
+    } else if (onePerPoint) {
+        k_backsub<<<nb, 128, 0, st>>>(P, lambda, p, jpOut ? partial : nullptr, nb, nullptr, 0);
+        count_launch();
     } else if (P.nOP > 0) {
-        if (perPoint || !P.psb_pt) {
-            nb = (P.nOP + 127) / 128;
-            k_backsub<<<nb, 128, 0, st>>>(P, lambda, p, jpOut ? partial : nullptr, nb, nullptr, 0);
-            count_launch();
-        } else {
-            const int nbBig = P.nPsbig > 0 ? (P.nPsbig + 127) / 128 : 0;
-            nb = P.nPsb + nbBig;
-            if (P.nPsb > 0) { k_backsub_obs<<<P.nPsb, DBAT_PSB, 0, st>>>(P, lambda, p, jpOut ? partial : nullptr, nb); count_launch(); }
-            if (nbBig > 0) { k_backsub<<<nbBig, 128, 0, st>>>(P, lambda, p, jpOut ? partial + P.nPsb : nullptr, nb, P.psbig, P.nPsbig); count_launch(); }
-        }
+        if (P.nPsb > 0) { k_backsub_obs<<<P.nPsb, DBAT_PSB, 0, st>>>(P, lambda, p, jpOut ? partial : nullptr, nb); count_launch(); }
+        if (nbBig > 0) { k_backsub<<<nbBig, 128, 0, st>>>(P, lambda, p, jpOut ? partial + P.nPsb : nullptr, nb, P.psbig, P.nPsbig); count_launch(); }
     }
     if (jpOut) {
-        if (nb > 0) k_sum_pair<<<1, 1024, 0, st>>>(partial, nb, jpOut);
-        else cudaMemsetAsync(jpOut, 0, 2 * sizeof(double), st);
-        const int nbc = (P.nImg + 3) / 4;
-        k_jp_cam<<<nbc, 128, 0, st>>>(P, p, camDiag, camG, partial + 2 * nb);
-        k_sum_pair<<<1, 1024, 0, st>>>(partial + 2 * nb, nbc, jpOut + 2);
-        count_launch(3);
+        if (side) cudaStreamWaitEvent(st, evJoin, 0);
+        else { k_jp_cam<<<nbc, 128, 0, st>>>(P, p, camDiag, camG, partial + 2 * nb); count_launch(); }
+        if (nb == 0) cudaMemsetAsync(jpOut, 0, 2 * sizeof(double), st);
+        // block 0: point part -> jpOut[0..1]; block 1: camera part -> jpOut[2..3]
+        if (nb > 0) k_sum_pair<<<2, 1024, 0, st>>>(partial, nb, jpOut, partial + 2 * nb, nbc);
+        else k_sum_pair<<<1, 1024, 0, st>>>(partial + 2 * nb, nbc, jpOut + 2, nullptr, 0);
+        count_launch();
     }
 }
 

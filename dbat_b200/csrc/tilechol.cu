@@ -621,8 +621,12 @@ __global__ void __launch_bounds__(TC_THREADS) k_tchol_bwd(TCholDev D, int epoch,
 // ---------------------------------------------------------------------------------------------
 // putTop = 0: leave the top tile columns alone (distributed: their tiles are summed over the ranks, so only one
 // rank may contribute the rhs row and the 1e300 corner)
+// The same launch resets what a factorisation + solve start from: task counters and pivot statistics.
 __global__ void k_tc_put_rhs(TCholDev D, const double* __restrict__ rhs, const int* __restrict__ colOwner, int putTop) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < 8) D.counters[s] = 0;
+    if (s == 8) *D.info = 0;
+    if (s == 9) { D.minmax[0] = 0x7fefffffffffffffull; D.minmax[1] = 0ull; }      // DBL_MAX, 0
     if (s >= D.ld) return;
     if (!putTop && colOwner[s >> 6] < 0) return;
     const int slot = D.tix[(size_t)(D.nT - 1) * D.nT + (s >> 6)];
@@ -752,6 +756,7 @@ void tchol_zero_dev(const TCholDev& d, cudaStream_t st) {
 void tchol_zero(TChol& w, cudaStream_t st) { tchol_zero_dev(w.d, st); }
 void tchol_put_rhs(TChol& w, const double* rhs, cudaStream_t st, bool putTop) {
     k_tc_put_rhs<<<(w.d.ld + 255) / 256, 256, 0, st>>>(w.d, rhs, w.colOwnerDev, putTop ? 1 : 0);
+    w.resetDone = true;
     count_launch();
 }
 // [~min pivot bits, max pivot bits, info] as three uint64: one max-allreduce combines the statistics of all ranks
@@ -796,10 +801,13 @@ static void factor_phase(TChol& w, int ph, cudaStream_t st) {
 }
 void tchol_factor_begin(TChol& w, cudaStream_t st) {
     ++w.epoch;
-    cudaMemsetAsync(w.d.counters, 0, sizeof(int) * 8, st);
-    cudaMemsetAsync(w.d.info, 0, sizeof(int), st);
-    static const unsigned long long init[2] = {0x7fefffffffffffffull, 0ull};      // DBL_MAX, 0
-    cudaMemcpyAsync(w.d.minmax, init, sizeof(init), cudaMemcpyHostToDevice, st);
+    if (!w.resetDone) {                       // normally done by the tchol_put_rhs launch just before
+        cudaMemsetAsync(w.d.counters, 0, sizeof(int) * 8, st);
+        cudaMemsetAsync(w.d.info, 0, sizeof(int), st);
+        static const unsigned long long init[2] = {0x7fefffffffffffffull, 0ull};      // DBL_MAX, 0
+        cudaMemcpyAsync(w.d.minmax, init, sizeof(init), cudaMemcpyHostToDevice, st);
+    }
+    w.resetDone = false;
     factor_phase(w, 0, st);
 }
 void tchol_factor_end(TChol& w, cudaStream_t st) {

@@ -38,6 +38,7 @@ struct TChol {
     TileSym sym;
     TCholDev d;
     int epoch = 0;
+    bool resetDone = false;            // tchol_put_rhs has reset the task counters / pivot statistics for the next factorisation
     int smemChain = 0;
     int gridFactor = 0, gridBwd = 0, nCrit = 0;    // nCrit > 0: that many CTAs, alone on their SMs, serve the chain queue
     double* xs = nullptr;              // ld: solution in S order
