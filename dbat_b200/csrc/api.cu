@@ -102,6 +102,7 @@ struct dbat_handle {
     double* solve_pout = nullptr;       // step vector of a solve_step whose host-side part (finish_solve) is still due
     bool solve_jp = false;
     double *d_x = nullptr, *d_t = nullptr, *d_p = nullptr, *d_pgn = nullptr, *d_g = nullptr, *d_pc = nullptr;
+    double* d_pEO = nullptr;             // nImg x 6: EO part of the last camera-side step per image (0 = fixed element)
     double *d_camDiag = nullptr, *d_camG = nullptr, *d_diagN = nullptr, *d_dscale = nullptr;
     double *d_evalRed = nullptr, *d_prr = nullptr; size_t nEvalRed = 0;
     double *d_r = nullptr;              // m doubles (export)
@@ -752,6 +753,7 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     AL(h->d_scal, SC_N);
     AL(h->d_x, P.n); AL(h->d_t, P.n); AL(h->d_p, P.n); AL(h->d_pgn, P.n); AL(h->d_g, P.n);
     AL(h->d_diagN, P.n); AL(h->d_dscale, P.n);
+    AL(h->d_pEO, (size_t)6 * std::max(1, nImg) + 2);
     AL(h->d_r, h->m);
     if (cudaMallocHost((void**)&h->h_scal, sizeof(double) * SC_N) != cudaSuccess ||
         cudaMallocHost((void**)&h->h_G, sizeof(double) * DBAT_GSZ) != cudaSuccess ||
@@ -1044,10 +1046,10 @@ static int solve_step(dbat_handle* h, double lambda, bool jacobi, double* pout, 
         if (!rc) { tchol_pack_stats(tc, h->d_stats, false, h->st); rc = allreduce_max_u64(h, h->d_stats, 3); tchol_pack_stats(tc, h->d_stats, true, h->st); }
         if (rc) return rc;
     }
-    launch_unpermute(P, tc.xs, jacobi ? h->d_dscale : nullptr, h->d_pc, h->st);
+    launch_unpermute(P, tc.xs, jacobi ? h->d_dscale : nullptr, h->d_pc, h->d_pEO, h->st);
     static const bool fusedJp = !getenv("DBAT_JP_SEPARATE");
     double* jpOut = fusedJp ? h->d_scal + SC_JPP : nullptr;
-    launch_backsub(P, lambda, h->d_pc, pout, h->d_partial, h->d_camDiag, h->d_camG, jpOut, h->st, h->st2, h->evFork, h->evJoin);
+    launch_backsub(P, lambda, h->d_pc, h->d_pEO, pout, h->d_partial, h->d_camDiag, h->d_camG, jpOut, h->st, h->st2, h->evFork, h->evJoin);
     if (jpOut) {
         if (h->nranks > 1) { int rc = allreduce(h, jpOut, 2); if (rc) return rc; }     // point parts; the camera part is global already
         cudaMemcpyAsync(h->h_scal + SC_JPP, jpOut, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->st);

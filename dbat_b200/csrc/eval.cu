@@ -260,8 +260,11 @@ __global__ void __launch_bounds__(128, 3) k_cam_side(DevProblem P) {
 __host__ __device__ constexpr int ce_col(int s) { int r = 0; for (int k = 0; k < s; ++k) r += (CE_MASK >> k) & 1; return r; }
 static_assert(ce_col(DBAT_NSLOT) == CE_NA && CE_R == 15, "compact column set");
 
+#ifndef CAMC_MINB
+#define CAMC_MINB 4                    // 126 registers without spills: four CTAs (16 warps) per SM
+#endif
 template <int MODEL>
-__global__ void __launch_bounds__(128, 3) k_cam_side_c(DevProblem P) {
+__global__ void __launch_bounds__(128, CAMC_MINB) k_cam_side_c(DevProblem P) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(16) ImgRec s_g;
     __shared__ __align__(16) IORec s_io;
@@ -613,8 +616,11 @@ __global__ void __launch_bounds__(DBAT_PSB, 3) k_point_side_obs(DevProblem P) {
 #define PSC_DMMA 1                   // 0: the scalar phase 2 (one thread per (point, item)), kept as a cross-check
 #endif
 __device__ __constant__ unsigned char c_ceSlot[CE_NA] = {0, 1, 2, 3, 5, 6, 7, 10, 11};
+#ifndef PSC_MINB
+#define PSC_MINB 5
+#endif
 template <int MODEL>
-__global__ void __launch_bounds__(DBAT_PSB, 5) k_point_side_obs_c(DevProblem P) {
+__global__ void __launch_bounds__(DBAT_PSB, PSC_MINB) k_point_side_obs_c(DevProblem P) {
     __shared__ __align__(16) double rows[DBAT_PSB * PSC_ROW];
     const int tid = threadIdx.x, lane = tid & 31;
     const int p0 = P.psb_pt[2 * blockIdx.x], p1 = P.psb_pt[2 * blockIdx.x + 1];

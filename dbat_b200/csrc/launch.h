@@ -34,8 +34,8 @@ void launch_build_S(const DevProblem& P, const double* camDiag, const double* ca
 void launch_schur(const DevProblem& P, double lambda, cudaStream_t st);
 void launch_point_vinv(const DevProblem& P, double lambda, cudaStream_t st);   // P.vinv = (V_j + lambda I)^-1
 void launch_scale_prep(const DevProblem& P, const double* d, double* dS, cudaStream_t st);
-void launch_unpermute(const DevProblem& P, const double* xs, const double* d, double* pc, cudaStream_t st);
-void launch_backsub(const DevProblem& P, double lambda, const double* pc, double* p, double* partial,
+void launch_unpermute(const DevProblem& P, const double* xs, const double* d, double* pc, double* pEO, cudaStream_t st);
+void launch_backsub(const DevProblem& P, double lambda, const double* pc, const double* pEO, double* p, double* partial,
                     const double* camDiag, const double* camG, double* jpOut, cudaStream_t st,
                     cudaStream_t st2 = nullptr, cudaEvent_t evFork = nullptr, cudaEvent_t evJoin = nullptr);
 void launch_vec_ops_sum(const double* a, int n, double* partial, double* scal, int slot, cudaStream_t st);

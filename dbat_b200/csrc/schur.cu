@@ -890,16 +890,28 @@ void launch_scale_prep(const DevProblem& P, const double* d, double* dS, cudaStr
     k_scale_prep<<<(P.ldS + 255) / 256, 256, 0, st>>>(P, d, dS);
     count_launch();
 }
-// camera-side step from the solution in S order: pc[x column] = xs[s] (* d)
+// camera-side step from the solution in S order: pc[x column] = xs[s] (* d).  The blocks behind the first ldS threads
+// fill the dense per-image table pEO[image][6] of the EO step (0 for fixed elements) that the back-substitution
+// gathers with three 16-byte loads per observation instead of a column lookup plus a second gather.
 __global__ void k_unpermute(DevProblem P, const double* __restrict__ xs, const double* __restrict__ d,
-                            double* __restrict__ pc) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= P.ldS) return;
-    const int c = P.s2x[s];
-    if (c >= 0) pc[c] = d ? xs[s] * d[c] : xs[s];
+                            double* __restrict__ pc, double* __restrict__ pEO, int nbS) {
+    if ((int)blockIdx.x < nbS) {
+        const int s = blockIdx.x * blockDim.x + threadIdx.x;
+        if (s >= P.ldS) return;
+        const int c = P.s2x[s];
+        if (c >= 0) pc[c] = d ? xs[s] * d[c] : xs[s];
+        return;
+    }
+    const int t = (blockIdx.x - nbS) * blockDim.x + threadIdx.x;
+    if (t >= 6 * P.nImg) return;
+    const int si = P.eo_s[t];
+    double v = 0.0;
+    if (si >= 0) v = d ? xs[si] * d[P.eo_col[t]] : xs[si];
+    pEO[t] = v;
 }
-void launch_unpermute(const DevProblem& P, const double* xs, const double* d, double* pc, cudaStream_t st) {
-    k_unpermute<<<(P.ldS + 255) / 256, 256, 0, st>>>(P, xs, d, pc);
+void launch_unpermute(const DevProblem& P, const double* xs, const double* d, double* pc, double* pEO, cudaStream_t st) {
+    const int nbS = (P.ldS + 255) / 256, nbE = pEO ? (6 * P.nImg + 255) / 256 : 0;
+    k_unpermute<<<nbS + nbE, 256, 0, st>>>(P, xs, d, pc, pEO, nbS);
     count_launch();
 }
 
@@ -970,27 +982,60 @@ __global__ void __launch_bounds__(128) k_backsub(DevProblem P, double lambda, do
 // (144 contiguous bytes, consecutive threads consecutive blocks: fully coalesced) and the six EO entries of p_c
 // of its image and leaves a_o = W_o' p_c in shared memory.  Phase 2: one thread per point adds the a_o of its
 // observations in image order, the shared IO part, solves with (V_j + lambda I)^-1 and forms the |Jp|^2 / r'Jp terms.
+#ifndef BSO_V2
+#define BSO_V2 1                    // 0: column lookup + gather of p per observation, no prefetch (the earlier version)
+#endif
+// BSO_V2: the EO step of the observation's image comes from the dense table pEO (three 16-byte loads instead of a column
+// lookup and a dependent gather); the lines phase 2 will need (point record, column map) start towards L1 at once and
+// the shared IO step is read once per block.  Measured and dropped: the point's (V + lambda I)^-1 before the barrier
+// (more registers, fewer resident blocks: slower).
 __global__ void __launch_bounds__(DBAT_PSB) k_backsub_obs(DevProblem P, double lambda, double* __restrict__ p,
+                                                           const double* __restrict__ pEO,
                                                            double* __restrict__ stats, int statStride) {
     __shared__ double ao[DBAT_PSB * 3];
     __shared__ double red[2][DBAT_PSB / 32];
+    __shared__ double psh[DBAT_NSLOT + 2];
+    __shared__ int pshOk[DBAT_NSLOT + 2];
     const int tid = threadIdx.x;
     const int p0 = P.psb_pt[2 * blockIdx.x], p1 = P.psb_pt[2 * blockIdx.x + 1];
     const int ob0 = P.pt_start[p0], nob = P.pt_start[p1] - ob0;
+#if BSO_V2
+    if (p0 + tid < p1) {
+        const char* rec = reinterpret_cast<const char*>(P.pt + (size_t)(p0 + tid) * DBAT_PT_STRIDE);
+#pragma unroll
+        for (int b = 0; b < DBAT_PT_STRIDE * 8; b += 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(rec + b));
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(rec + DBAT_PT_STRIDE * 8 - 8));      // the record's last line when it straddles a fifth one
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(P.op_col + 3 * (size_t)(p0 + tid)));
+    }
+    if (tid >= DBAT_PSB - DBAT_NSLOT) {                          // the shared IO step, once per block
+        const int s = tid - (DBAT_PSB - DBAT_NSLOT);
+        const int c = P.sh_col[s];
+        psh[s] = c >= 0 ? p[c] : 0.0;
+        pshOk[s] = c >= 0;
+    }
+#endif
     if (tid < nob) {
         const int ob = ob0 + tid;
-        const int* ec = P.eo_col + 6 * (size_t)P.img_pm[ob];
         const double2* Wo = reinterpret_cast<const double2*>(P.W + (size_t)ob * DBAT_W_STRIDE);
         double w[18];
 #pragma unroll
         for (int q = 0; q < 9; ++q) { const double2 t = Wo[q]; w[2 * q] = t.x; w[2 * q + 1] = t.y; }
         double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#if BSO_V2
+        const double2* pe = reinterpret_cast<const double2*>(pEO + 6 * (size_t)P.img_pm[ob]);
+        const double2 e01 = pe[0], e23 = pe[1], e45 = pe[2];
+        const double pv[6] = {e01.x, e01.y, e23.x, e23.y, e45.x, e45.y};
+#pragma unroll
+        for (int e = 0; e < 6; ++e) { a0 += w[3 * e] * pv[e]; a1 += w[3 * e + 1] * pv[e]; a2 += w[3 * e + 2] * pv[e]; }
+#else
+        const int* ec = P.eo_col + 6 * (size_t)P.img_pm[ob];
 #pragma unroll
         for (int e = 0; e < 6; ++e) {
             const int c = ec[e];
             const double pv = c >= 0 ? p[c] : 0.0;
             a0 += w[3 * e] * pv; a1 += w[3 * e + 1] * pv; a2 += w[3 * e + 2] * pv;
         }
+#endif
         ao[3 * tid] = a0; ao[3 * tid + 1] = a1; ao[3 * tid + 2] = a2;
     }
     __syncthreads();
@@ -1005,9 +1050,14 @@ __global__ void __launch_bounds__(DBAT_PSB) k_backsub_obs(DevProblem P, double l
             double a[3] = {0.0, 0.0, 0.0};
 #pragma unroll
             for (int s = 0; s < DBAT_NSLOT; ++s) {
+#if BSO_V2
+                if (!pshOk[s]) continue;
+                const double pv = psh[s];
+#else
                 const int c = P.sh_col[s];
                 if (c < 0) continue;
                 const double pv = p[c];
+#endif
                 const double* ws = rec + DBAT_PT_WSH + 3 * s;
                 a[0] += ws[0] * pv; a[1] += ws[1] * pv; a[2] += ws[2] * pv;
             }
@@ -1101,7 +1151,7 @@ __global__ void __launch_bounds__(1024) k_sum_pair(const double* __restrict__ a,
 }
 // p = [pc ; back-substituted points].  jpOut (4 doubles, may be null): [0..1] point part of |Jp|^2, r'Jp (a multi-rank
 // run sums these over the ranks), [2..3] the camera part (identical on every rank).
-void launch_backsub(const DevProblem& P, double lambda, const double* pc, double* p, double* partial,
+void launch_backsub(const DevProblem& P, double lambda, const double* pc, const double* pEO, double* p, double* partial,
                     const double* camDiag, const double* camG, double* jpOut, cudaStream_t st,
                     cudaStream_t st2, cudaEvent_t evFork, cudaEvent_t evJoin) {
     static const bool perPoint = getenv("DBAT_POINT_SIDE_PER_POINT") != nullptr;
@@ -1129,7 +1179,7 @@ void launch_backsub(const DevProblem& P, double lambda, const double* pc, double
         k_backsub<<<nb, 128, 0, st>>>(P, lambda, p, jpOut ? partial : nullptr, nb, nullptr, 0);
         count_launch();
     } else if (P.nOP > 0) {
-        if (P.nPsb > 0) { k_backsub_obs<<<P.nPsb, DBAT_PSB, 0, st>>>(P, lambda, p, jpOut ? partial : nullptr, nb); count_launch(); }
+        if (P.nPsb > 0) { k_backsub_obs<<<P.nPsb, DBAT_PSB, 0, st>>>(P, lambda, p, pEO, jpOut ? partial : nullptr, nb); count_launch(); }
         if (nbBig > 0) { k_backsub<<<nbBig, 128, 0, st>>>(P, lambda, p, jpOut ? partial + P.nPsb : nullptr, nb, P.psbig, P.nPsbig); count_launch(); }
     }
     if (jpOut) {

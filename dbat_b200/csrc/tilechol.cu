@@ -534,6 +534,9 @@ __global__ void __launch_bounds__(TC_THREADS, 3) k_tchol_factor(TCholDev D, int 
 // backward substitution L' x = y (y = the rhs row of the factor).  One task per tile column, taken
 // in descending elimination-tree level; block J waits for the blocks of the rows of its column.
 // ---------------------------------------------------------------------------------------------
+#ifndef TC_BWD_ILP
+#define TC_BWD_ILP 1                   // 0: every dot product of the backward substitution as one dependent chain (cross-check)
+#endif
 #define BW_LD 65
 __global__ void __launch_bounds__(TC_THREADS) k_tchol_bwd(TCholDev D, int epoch, double* __restrict__ xs, int nCols) {
     __shared__ double Ls[64 * BW_LD];
@@ -563,6 +566,9 @@ __global__ void __launch_bounds__(TC_THREADS) k_tchol_bwd(TCholDev D, int epoch,
         }
         const int c = tid >> 1, h = tid & 1;
         double acc = 0.0;
+#if TC_BWD_ILP
+        double acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#endif
         double2 v[16];
         bool have = false;
         for (int e = e1 - 1; e > e0; --e) {                    // rows descending: highest level first
@@ -578,8 +584,16 @@ __global__ void __launch_bounds__(TC_THREADS) k_tchol_bwd(TCholDev D, int epoch,
             if (tid < 64) xv[tid] = (I == nT - 1 && tid == 63) ? 0.0 : __ldcg(xs + (size_t)I * 64 + tid);
             __syncthreads();
             const double* xx = xv + 32 * h;
+#if TC_BWD_ILP
+#pragma unroll
+            for (int k = 0; k < 16; k += 2) {                   // four independent chains
+                acc = fma(v[k].x, xx[2 * k], acc); acc1 = fma(v[k].y, xx[2 * k + 1], acc1);
+                acc2 = fma(v[k + 1].x, xx[2 * k + 2], acc2); acc3 = fma(v[k + 1].y, xx[2 * k + 3], acc3);
+            }
+#else
 #pragma unroll
             for (int k = 0; k < 16; ++k) { acc = fma(v[k].x, xx[2 * k], acc); acc = fma(v[k].y, xx[2 * k + 1], acc); }
+#endif
             have = false;
             if (e - 1 > e0) {                                   // prefetch the next tile before the next wait
                 const int s2 = D.colSlot[e - 1];
@@ -590,11 +604,46 @@ __global__ void __launch_bounds__(TC_THREADS) k_tchol_bwd(TCholDev D, int epoch,
             }
             __syncthreads();                                    // xv is reused
         }
+#if TC_BWD_ILP
+        acc = (acc + acc1) + (acc2 + acc3);
+#endif
         acc += __shfl_xor_sync(0xffffffffu, acc, 1);
         __syncthreads();
         if (h == 0) yv[c] -= acc;
         __syncthreads();
         // L(J,J)' x = y by 16-blocks, last block first
+#if TC_BWD_ILP
+        // every dot product of the chain is cut into short independent pieces: x_p by 64 threads (4 terms + two
+        // shuffles), the update of the rows above by all 128 (8 terms + one shuffle)
+        for (int p = 3; p >= 0; --p) {
+            if (tid < 64) {                                     // x_p = inv(L_pp)' y_p
+                const int i = tid >> 2, q = tid & 3;
+                double s = 0.0, s2 = 0.0;
+                if (q >= i) s = Xd[p * 256 + q * 16 + i] * yv[16 * p + q];
+                if (q + 4 >= i) s2 = Xd[p * 256 + (q + 4) * 16 + i] * yv[16 * p + q + 4];
+                if (q + 8 >= i) s = fma(Xd[p * 256 + (q + 8) * 16 + i], yv[16 * p + q + 8], s);
+                if (q + 12 >= i) s2 = fma(Xd[p * 256 + (q + 12) * 16 + i], yv[16 * p + q + 12], s2);
+                s += s2;
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                if (q == 0) xv[16 * p + i] = s;
+            }
+            __syncthreads();
+            {                                                   // y(0:16p) -= L(p rows, 0:16p)' x_p
+                double s = 0.0, s2 = 0.0;
+                if (c < 16 * p) {
+                    const double* lp = Ls + c * BW_LD + 16 * p + 8 * h;
+                    const double* xp = xv + 16 * p + 8 * h;
+#pragma unroll
+                    for (int r = 0; r < 8; r += 2) { s = fma(lp[r], xp[r], s); s2 = fma(lp[r + 1], xp[r + 1], s2); }
+                }
+                s += s2;
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                if (h == 0 && c < 16 * p) yv[c] -= s;
+            }
+            __syncthreads();
+        }
+#else
         for (int p = 3; p >= 0; --p) {
             if (tid < 16) {                                     // x_p = inv(L_pp)' y_p
                 double s = 0.0;
@@ -610,6 +659,7 @@ __global__ void __launch_bounds__(TC_THREADS) k_tchol_bwd(TCholDev D, int epoch,
             }
             __syncthreads();
         }
+#endif
         if (tid < 64) xs[(size_t)J * 64 + tid] = xv[tid];
         __syncthreads();
         if (tid == 0) st_release(D.xflag + J, epoch);
