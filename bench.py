@@ -58,7 +58,9 @@ def parse():
 
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md): one
-    long-running `nvidia-smi -lms 50` whose lines are collected by this thread."""
+    long-running `nvidia-smi -lms 10` whose lines are collected by this thread.  The timed region of the
+    device-resident arm is only tens of milliseconds long, so the samples that count are those taken from the
+    start of its warm-up steps to the end of the end-to-end arm - the device runs the same iteration throughout."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
          'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
          'clocks_event_reasons.sw_power_cap')
@@ -71,7 +73,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '50'],
+                                          '--format=csv,noheader,nounits', '-lms', '10'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
@@ -230,6 +232,10 @@ def main():
     from dbat_b200.parallel import ShardedProblem
     from dbat_b200.synth import make_scene, make_scene_shard
 
+    # nvidia-smi needs about a second before its first line: start it before the scene is generated
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     per = C4 if world == 1 else C5_PER_RANK
     args.nop = args.nop or per['nOP']
     nImg = args.nimg or per['nImg'] * world
@@ -280,13 +286,10 @@ def main():
         return time.perf_counter() - t0, dev_ms, launches
 
     # device-resident arm
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     P.normal_step(x0, lam, trial=True, accept=False, want_p=False)       # upload x0
+    sampler.mark()
     timed(args.warmup, True)
     P.normal_step(x0, lam, trial=True, accept=False, want_p=False)       # restart the path at x0
-    sampler.mark()
     wall, dev_ms, launches = timed(args.steps, True)
     phases = P.phase_times() if hasattr(P, 'phase_times') else {}
     # end-to-end arm (host x in, host p out every step)

@@ -77,7 +77,7 @@ static bool nccl_load() {
 struct dbat_handle {
     std::string err;
     cudaStream_t st = nullptr, st2 = nullptr;
-    cudaEvent_t evFork = nullptr, evJoin = nullptr;
+    cudaEvent_t evFork = nullptr, evJoin = nullptr, evStep = nullptr;
     DevProblem P{};
     int NC = 0, m = 0, nIOrec = 0;
     int nPriorIO = 0, nPriorEO = 0, nPriorOP = 0;
@@ -418,7 +418,8 @@ extern "C" int dbat_create(const dbat_problem_desc* d, dbat_handle** out) {
     // ---- device side
     if (cudaStreamCreate(&h->st) != cudaSuccess || cudaStreamCreateWithFlags(&h->st2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->evFork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&h->evJoin, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->evStep, cudaEventDisableTiming) != cudaSuccess)
         return fail_create(h, DBAT_E_CUDA, "cudaStreamCreate failed");
     int rc = 0;
 #define UP(ptr, vec) if ((rc = dev_upload(h, &ptr, vec))) return fail_create(h, rc, h->err)
@@ -783,6 +784,7 @@ extern "C" void dbat_destroy(dbat_handle* h) {
     if (h->st2) cudaStreamDestroy(h->st2);
     if (h->evFork) cudaEventDestroy(h->evFork);
     if (h->evJoin) cudaEventDestroy(h->evJoin);
+    if (h->evStep) cudaEventDestroy(h->evStep);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
 }
@@ -1187,14 +1189,23 @@ extern "C" int dbat_normal_step(dbat_handle* h, const double* x, double lambda, 
     rc = solve_step(h, lambda, (flags & 1) != 0, h->d_p, &sing, stepSync);
     if (rc) return rc;
     double jp2 = 0, rjp = 0, fNew = NAN, rrT = 0;
-    if (p) CK(cudaMemcpyAsync(p, h->d_p, sizeof(double) * h->P.n, cudaMemcpyDeviceToHost, h->st));
+    // the step goes back to the host on the second stream, beside the trial-point residual (queued after it in host
+    // order: a pageable destination makes the copy call block)
+    const bool sideCopy = p && (flags & 2) && !stepSync;
+    if (sideCopy) cudaEventRecord(h->evStep, h->st);
+    else if (p) CK(cudaMemcpyAsync(p, h->d_p, sizeof(double) * h->P.n, cudaMemcpyDeviceToHost, h->st));
     if (flags & 2) {
         launch_axpy(1.0, h->d_p, h->d_x, h->d_t, h->P.n, h->st);
         rc = eval_rr(h, h->d_t, &rrT, stepSync);
         if (rc) return rc;
     }
+    if (sideCopy) {
+        cudaStreamWaitEvent(h->st2, h->evStep, 0);
+        CK(cudaMemcpyAsync(p, h->d_p, sizeof(double) * h->P.n, cudaMemcpyDeviceToHost, h->st2));
+    }
     if (!stepSync) {
         cudaError_t e = cudaStreamSynchronize(h->st);
+        if (e == cudaSuccess && sideCopy) e = cudaStreamSynchronize(h->st2);
         if (e != cudaSuccess) { h->err = std::string("dbat_normal_step: ") + cudaGetErrorString(e); return DBAT_E_CUDA; }
         if ((rc = finish_eval(h))) return rc;
         finish_solve(h, &sing);
