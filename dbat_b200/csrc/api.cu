@@ -874,11 +874,22 @@ static int eval_full(dbat_handle* h, bool sync = true) {
     h->params_valid = true;
     // camera side and point side read the same parameters and write disjoint outputs; both are latency- rather than
     // bandwidth-bound, so they run side by side on two streams
+    // The camera-side kernel (the shorter one) is launched first: the two kernels cannot share an SM's registers, so they
+    // run one after the other anyway, and this way the chunk -> image -> total sums run beside the point side.  Capping
+    // the camera-side CTAs per SM to make room for point-side CTAs was measured and is slower (DBAT_EVAL_POINT_FIRST:
+    // the earlier order).
+    static const bool camFirst = getenv("DBAT_EVAL_POINT_FIRST") == nullptr;
     cudaEventRecord(h->evFork, h->st);
     cudaStreamWaitEvent(h->st2, h->evFork, 0);
-    launch_point_side(h->P, h->st2);
-    cudaEventRecord(h->evJoin, h->st2);
-    launch_cam_side(h->P, h->d_img_chunk_start, h->d_tmpG, h->st);
+    if (camFirst) {
+        launch_cam_side(h->P, h->d_img_chunk_start, h->d_tmpG, h->st);
+        launch_point_side(h->P, h->st2);
+        cudaEventRecord(h->evJoin, h->st2);
+    } else {
+        launch_point_side(h->P, h->st2);
+        cudaEventRecord(h->evJoin, h->st2);
+        launch_cam_side(h->P, h->d_img_chunk_start, h->d_tmpG, h->st);
+    }
     cudaStreamWaitEvent(h->st, h->evJoin, 0);
     const bool clearPrior = h->nranks > 1;      // the in-place allreduce below leaves the sums of all ranks in these arrays
     launch_prior_apply(h->P, h->d_x, h->d_camDiag, h->d_camG, h->d_col2pt, clearPrior, h->st);

@@ -411,8 +411,9 @@ static void launch_cam_side_t(const DevProblem& P, const int* img_chunk_start, d
         attr_done = true;
     }
     if (P.nChunks > 0) {
-        if (P.evalCompact) k_cam_side_c<MODEL><<<P.nChunks, 128, (size_t)4 * 16 * XT_LD * sizeof(double), st>>>(P);
-        else k_cam_side<MODEL><<<P.nChunks, 128, smem, st>>>(P);
+        if (P.evalCompact) {
+            k_cam_side_c<MODEL><<<P.nChunks, 128, (size_t)4 * 16 * XT_LD * sizeof(double), st>>>(P);
+        } else k_cam_side<MODEL><<<P.nChunks, 128, smem, st>>>(P);
     }
     k_cam_reduce<<<P.nImg, 128, 0, st>>>(P, img_chunk_start);
     k_sh_reduce<<<DBAT_GSZ / 64, 64 * SHR_G, 0, st>>>(P);
@@ -816,7 +817,7 @@ void launch_prior_apply(const DevProblem& P, const double* x, double* camDiag, d
 #define RES_BLOCK 256
 #endif
 #ifndef RES_MINB
-#define RES_MINB 1
+#define RES_MINB 4
 #endif
 template <int MODEL, bool WRITE>
 __global__ void __launch_bounds__(RES_BLOCK, RES_MINB) k_resid(DevProblem P, double* __restrict__ partial,
