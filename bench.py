@@ -294,7 +294,7 @@ def main():
     phases = P.phase_times() if hasattr(P, 'phase_times') else {}
     # end-to-end arm (host x in, host p out every step)
     timed(min(args.warmup, 3), False)
-    wall_e2e, _, _ = timed(args.steps, False)
+    wall_e2e, dev_ms_e2e, _ = timed(args.steps, False)
     sampler.stop()
 
     t = torch.tensor([wall, wall_e2e, float(np.sum(dev_ms))], dtype=torch.float64, device='cuda')
@@ -336,7 +336,11 @@ def main():
                                    'solution; the separators above the cut are factored on every rank'
                                    % (world, info['nSlotsS'], sbytes / 1e6)),
                    'reduced_system': {k: info[k] for k in ('nT', 'nSlots', 'nSlotsS', 'nTasks', 'nTerms', 'depth', 'order_mode', 'nSeg')}},
-        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 8 * n * world, 'd2h_bytes_per_step': (8 * n + 64) * world},
+        'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': 8 * n * world, 'd2h_bytes_per_step': (8 * n + 64) * world,
+                'ms_per_step_wall': 1e3 * wall_e2e / args.steps,
+                # rank 0's CUDA-event time of the same steps: upload of x + the iteration (the download of the step
+                # runs on the second stream beside the trial residual and is not inside this figure)
+                'ms_per_step_device_rank0': float(np.mean(dev_ms_e2e))},
         'gpu_launches': int(launches),
         'clocks': sampler.summary(),
         'phases_ms_last_step': {k: v[0] for k, v in phases.items()},
