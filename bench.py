@@ -113,7 +113,8 @@ class ClockSampler(threading.Thread):
 CPU_DESC = ("oracle port of levenberg_marquardt.m:76-82,117-206 on the host cores: sparse Jacobian as multi_res.m "
             "builds it (SciPy CSC), J'J by sparse product, (J'J+lambda I)\\(-J'r) as MATLAB's CHOLMOD would order it "
             "(3x3 point blocks first, dense LAPACK Cholesky of the camera front: oracle.lsa.solve_spd_pointfirst), "
-            "trial residual; no MATLAB/Octave exists in this image")
+            "trial residual; the sparse products run on one thread (SciPy), the dense factorisation on all `cores` "
+            "(LAPACK); no MATLAB/Octave exists in this image")
 
 
 def cpu_lm_iterations(s, max_iters, budget_s):
