@@ -117,6 +117,20 @@ CPU_DESC = ("oracle port of levenberg_marquardt.m:76-82,117-206 on the host core
             "(LAPACK); no MATLAB/Octave exists in this image")
 
 
+def host_threads():
+    """All host cores for the LAPACK part of the CPU arm.  torchrun exports OMP_NUM_THREADS=1 to its workers,
+    which would silently make the reference arm at N > 1 single-threaded; the limit is lifted here and the
+    thread count actually in effect is what the JSON line reports as `cores`."""
+    want = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(limits=want)
+        got = [p.get('num_threads', 1) for p in threadpool_info() if p.get('user_api') == 'blas']
+        return max(got) if got else 1
+    except Exception:
+        return int(os.environ.get('OMP_NUM_THREADS', want))
+
+
 def cpu_lm_iterations(s, max_iters, budget_s):
     """LM iterations of the reference CPU algorithm on scene `s` until `max_iters` or the wall budget.
     Returns (iterations done, seconds)."""
@@ -166,10 +180,11 @@ def run_reference(args, rank, world):
     s, _ = make_scene(nImg, args.nop, rays=C4['rays'], cache_dir=os.environ.get('DBAT_SCENE_CACHE', '/tmp'))
     nobs = len(s.IP.img)
     n = s.bundle.serial.n
+    import scipy.linalg  # noqa: F401  (loads the BLAS whose thread limit host_threads() lifts)
+    cores = host_threads()
     done, dt = cpu_lm_iterations(s, max(1, args.steps), args.ref_budget)
     its = done / dt
     value = its * nobs / 2.0e6
-    cores = os.cpu_count() or 1
     line = {
         'impl': 'reference', 'metric': 'lm_iterations_per_s', 'value': value, 'unit': UNIT, 'n_gpus': 0,
         'steps': done, 'steps_requested': args.steps, 'warmup': 0, 'ms_per_step': 1e3 / its,
@@ -383,8 +398,10 @@ def main():
     line['roofline'] = roofs.get(dom, roofs.get('cholesky'))
     line['rooflines'] = roofs
     if world == 1 and not args.no_cpu_baseline:
+        import scipy.linalg  # noqa: F401
+        cores = host_threads()
         done, dt = cpu_lm_iterations(s, 1, 1.0)
-        line['cpu_baseline'] = {'value': done / dt * nObsGlobal / 2.0e6, 'unit': UNIT, 'cores': os.cpu_count() or 1,
+        line['cpu_baseline'] = {'value': done / dt * nObsGlobal / 2.0e6, 'unit': UNIT, 'cores': cores,
                                 'kind': 'port', 'sample': '%d full LM iteration(s) on the config itself (%.1f s); %s' % (done, dt, CPU_DESC)}
     print(json.dumps(line), flush=True)
     if world > 1:
