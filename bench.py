@@ -131,9 +131,9 @@ def host_threads():
         return int(os.environ.get('OMP_NUM_THREADS', want))
 
 
-def cpu_lm_iterations(s, max_iters, budget_s):
+def cpu_lm_iterations(s, max_iters, budget_s, phases=None):
     """LM iterations of the reference CPU algorithm on scene `s` until `max_iters` or the wall budget.
-    Returns (iterations done, seconds)."""
+    Returns (iterations done, seconds); `phases` (a dict) receives the seconds spent per stage."""
     import scipy.sparse as sp
     from oracle import lsa
     from oracle.cameramodel import brown_euler_cam4
@@ -144,19 +144,31 @@ def cpu_lm_iterations(s, max_iters, budget_s):
     nC = n - len(s.bundle.serial.OP.dest)
     I = sp.identity(n, format='csc')
     done = 0
-    t0 = time.perf_counter()
+    ph = phases if phases is not None else {}
+    clk = [time.perf_counter()]
+
+    def lap(name):
+        t = time.perf_counter()
+        ph[name] = ph.get(name, 0.0) + t - clk[0]
+        clk[0] = t
+
+    t0 = clk[0]
     while done < max_iters:
         f, J = brown_euler_cam4(x, s, True)
+        lap('residual_jacobian')
         r = R * f
         Jw = (sp.diags(R) @ J).tocsc()
         N = (Jw.T @ Jw).tocsc()
         g = Jw.T @ r
+        lap('normal_equations')
         lam = 1e-10 * N.diagonal().sum() / n if done == 0 else 0.0          # levenberg_marquardt.m:88-106,181
         p = lsa.solve_spd_pointfirst(N + lam * I, -g, nC)
+        lap('solve')
         Jp = Jw @ p                                                          # :162
         fNew = brown_euler_cam4(x + p, s, False)[0]
         if np.sum((R * fNew) ** 2) < r @ r:
             x = x + p
+        lap('trial_residual')
         done += 1
         if time.perf_counter() - t0 > budget_s:
             break
@@ -182,7 +194,8 @@ def run_reference(args, rank, world):
     n = s.bundle.serial.n
     import scipy.linalg  # noqa: F401  (loads the BLAS whose thread limit host_threads() lifts)
     cores = host_threads()
-    done, dt = cpu_lm_iterations(s, max(1, args.steps), args.ref_budget)
+    ph = {}
+    done, dt = cpu_lm_iterations(s, max(1, args.steps), args.ref_budget, ph)
     its = done / dt
     value = its * nobs / 2.0e6
     line = {
@@ -197,7 +210,8 @@ def run_reference(args, rank, world):
                               'of config 4, which flatters the CPU (its cost per observation grows with the block)'
                               % (world, world, 2.5 * world))},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': '%d full LM iterations on the config itself; %s' % (done, CPU_DESC)},
+                         'sample': '%d full LM iterations on the config itself; %s' % (done, CPU_DESC),
+                         'seconds_per_iteration': {k: v / done for k, v in ph.items()}},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0, 'seconds': dt,
     }
@@ -400,9 +414,11 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         import scipy.linalg  # noqa: F401
         cores = host_threads()
-        done, dt = cpu_lm_iterations(s, 1, 1.0)
+        ph = {}
+        done, dt = cpu_lm_iterations(s, 1, 1.0, ph)
         line['cpu_baseline'] = {'value': done / dt * nObsGlobal / 2.0e6, 'unit': UNIT, 'cores': cores,
-                                'kind': 'port', 'sample': '%d full LM iteration(s) on the config itself (%.1f s); %s' % (done, dt, CPU_DESC)}
+                                'kind': 'port', 'sample': '%d full LM iteration(s) on the config itself (%.1f s); %s' % (done, dt, CPU_DESC),
+                                'seconds_per_iteration': {k: v / done for k, v in ph.items()}}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
