@@ -8,8 +8,11 @@
  *
  *     mex -R2018a CFLAGS='$CFLAGS -Wall' -I../include dbat_mex.c -L../dbat_b200 -ldbatgpu
  *
- * NOT compiled in this repository (no mex.h in the build image); the identical C ABI is
- * exercised through ctypes in tests/.
+ * No MATLAB / mex.h exists in the build image.  tests/test_mex_gateway.py compiles this file (-Wall -Wextra
+ * -Werror) against tests/mexstub/mex.h, a stand-in declaring the documented MEX API subset used here, links it
+ * to libdbatgpu.so and drives mexFunction: argument validation and error ids on CPU, and on a B200 a whole
+ * create / eval / jacobian / solve / cov / covstats / forwintersect / destroy session whose results equal the
+ * ctypes path bit for bit (profiles/mex_gateway_session_r2g.log).
  *
  *   h        = dbat_mex('create', d)        d: struct with the fields of dbat_problem_desc
  *   [f]      = dbat_mex('eval', h, x, weighted)
@@ -23,7 +26,7 @@
 #include "matrix.h"
 #include "dbat_gpu.h"
 
-#define ERR(id, msg) mexErrMsgIdAndTxt("DBAT:dbat_mex:" id, msg)
+#define ERR(id, msg) mexErrMsgIdAndTxt("DBAT:dbat_mex:" id, "%s", msg)
 
 static int nHandles = 0;
 
