@@ -11,7 +11,7 @@
  * No MATLAB / mex.h exists in the build image.  tests/test_mex_gateway.py compiles this file (-Wall -Wextra
  * -Werror) against tests/mexstub/mex.h, a stand-in declaring the documented MEX API subset used here, links it
  * to libdbatgpu.so and drives mexFunction: argument validation and error ids on CPU, and on a B200 a whole
- * create / eval / jacobian / solve / cov / covstats / forwintersect / destroy session whose results equal the
+ * create / eval / jacobian / solve / cov / covstats / forwintersect / resect3 / destroy session whose results equal the
  * ctypes path bit for bit (profiles/mex_gateway_session_r2g.log).
  *
  *   h        = dbat_mex('create', d)        d: struct with the fields of dbat_problem_desc

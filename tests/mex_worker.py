@@ -90,6 +90,37 @@ def main():
                       float(s.IO.model.nK), float(s.IO.model.nP), nlhs=2)
     assert np.array_equal(OP, s2.OP.val[0:3]) and np.array_equal(rs.ravel(), res)
 
+    # [EO, res] = dbat_mex('resect3', X3, x3, int64(testStart), XT, xT, behind): the batch the host mirror of
+    # resect.m:52-95 prepares (captured from dbat_b200.photogrammetry.resect), through the gateway and through ctypes
+    import ctypes as C
+    from dbat_b200 import _lib
+    _lib.lib()                                  # argtypes are bound to the real ResectDesc before it is wrapped
+    cap = {}
+    orig = _lib.ResectDesc
+
+    def capture(nCam, X3, x3, ts, XT, xT, behind):
+        t = np.ctypeslib.as_array(ts, (nCam + 1,)).copy()
+        cap.update(nCam=nCam, ts=t, behind=behind, X3=np.ctypeslib.as_array(X3, (9 * nCam,)).copy(),
+                   x3=np.ctypeslib.as_array(x3, (6 * nCam,)).copy(), XT=np.ctypeslib.as_array(XT, (3 * int(t[-1]),)).copy(),
+                   xT=np.ctypeslib.as_array(xT, (2 * int(t[-1]),)).copy())
+        return orig(nCam, X3, x3, ts, XT, xT, behind)
+
+    _lib.ResectDesc = capture
+    try:
+        photogrammetry.resect(s, 'all', cpId=np.asarray(s.OP.id) if getattr(s.OP, 'id', None) is not None
+                              else np.arange(s.OP.val.shape[1]), n=2)
+    finally:
+        _lib.ResectDesc = orig
+    nC = cap['nCam']
+    assert nC >= nImg, nC
+    d = orig(nC, _lib.dptr(cap['X3']), _lib.dptr(cap['x3']), _lib.iptr(cap['ts']), _lib.dptr(cap['XT']), _lib.dptr(cap['xT']), 1)
+    EOc, resc = np.empty((nC, 6)), np.empty(nC)
+    assert _lib.lib().dbat_resect3(C.byref(d), _lib.dptr(EOc), _lib.dptr(resc)) == 0
+    EOm, resm = mex.call('resect3', cap['X3'], cap['x3'], cap['ts'], cap['XT'], cap['xT'], True, nlhs=2)
+    assert EOm.shape == (6, nC) and np.array_equal(EOm.T, EOc, equal_nan=True) and np.array_equal(resm.ravel(), resc, equal_nan=True)
+    assert np.isfinite(resc).any()
+    print('resect3: %d candidates, %d with a solution' % (nC, int(np.isfinite(resc).sum())))
+
     mex.call('destroy', h, nlhs=0)
     assert mex.H.hs_lock_count() == 0
     P.close()
